@@ -1,0 +1,272 @@
+"""Brute-force (subset-enumeration) definitions of the ANOVA / FM / FFM quantities.
+
+TEST INFRASTRUCTURE ONLY -- used to pin oracle/ref_cpu.c the same way the reference pins its own
+fast code (differential tests against naive re-implementations; the reference holds no golden
+vectors).  Restated from the reference's test helpers (paths relative to /root/reference/tests/):
+
+  anova_slow            kernels_slow.nim:18-27 + comb.nim:1-9
+  fm_decision_function  model/fm_slow.nim:42-60
+  fm_grad               model/fm_slow.nim:111-134 (comb.nim:12-23 combNotj)
+  ffm_decision_function model/ffm_slow.nim:38-56
+  ffm_grad              model/ffm_slow.nim:110-127
+  cd_slow_fit           optimizer/cd_slow.nim:44-139 + optimizer/fit_linear_slow.nim:4-45
+  adagrad_slow_fit      optimizer/adagrad_slow.nim:29-102
+  sgd_slow_fit          optimizer/sgd_slow.nim:38-91
+
+Pure Python loops over itertools.combinations: only for the reference's tiny test shapes.
+"""
+from itertools import combinations
+import math
+
+import numpy as np
+
+
+def anova_slow(x, p, degree, d, m):
+    """sum over all index subsets of size `degree` of prod p_j x_j; features j >= d are dummies (x=1)."""
+    res = 0.0
+    for idx in combinations(range(d + m), degree):
+        prod = 1.0
+        for j in idx:
+            prod *= p[j]
+            if j < d:
+                prod *= x[j]
+        res += prod
+    return res
+
+
+def n_orders(degree, fit_lower):
+    if degree == 1:
+        return 0
+    return degree - 1 if fit_lower == "explicit" else 1
+
+
+def n_augments(degree, fit_lower, fit_linear):
+    if fit_lower != "augment":
+        return 0
+    return degree - 2 if fit_linear else degree - 1
+
+
+def fm_decision_function(X, P, w, intercept, degree):
+    """X dense [n,d]; P model layout [nOrders,k,d+nAug]."""
+    n, d = X.shape
+    nO, k, dd = P.shape
+    m = dd - d
+    out = np.zeros(n)
+    for i in range(n):
+        r = intercept
+        for j in range(d):
+            r += w[j] * X[i, j]
+        for o in range(nO):
+            for s in range(k):
+                r += anova_slow(X[i], P[o, s], degree - o, d, m)
+        out[i] = r
+    return out
+
+
+def fm_grad(X, i, P, degree, dL, grad):
+    """grad[o,s,j] += dL * d(yhat_i)/dP[o,s,j]   (fm_slow.nim:111-134)."""
+    n, d = X.shape
+    nO, k, dd = P.shape
+    for o in range(nO):
+        deg = degree - o
+        for s in range(k):
+            for j in range(dd):
+                others = [q for q in range(dd) if q != j]
+                tmp = 0.0
+                if deg - 1 == 0:
+                    tmp = 1.0
+                else:
+                    for idx in combinations(others, deg - 1):
+                        prod = 1.0
+                        for j2 in idx:
+                            prod *= P[o, s, j2]
+                            if j2 < d:
+                                prod *= X[i, j2]
+                        tmp += prod
+                if j < d:
+                    tmp *= X[i, j]
+                grad[o, s, j] += dL * tmp
+
+
+def ffm_decision_function(X, fields, P, w, intercept):
+    """X dense [n,d]; fields[j] = field of feature j; P [nFields, d, k] (ffm_slow.nim:38-56)."""
+    n, d = X.shape
+    out = np.zeros(n)
+    for i in range(n):
+        r = intercept
+        for j in range(d):
+            r += w[j] * X[i, j]
+        for j1 in range(d):
+            for j2 in range(j1 + 1, d):
+                inter = X[i, j1] * X[i, j2]
+                if inter == 0.0:
+                    continue
+                r += inter * float(np.dot(P[fields[j2], j1], P[fields[j1], j2]))
+        out[i] = r
+    return out
+
+
+def ffm_grad(X, fields, i, P, dL, grad):
+    n, d = X.shape
+    for j1 in range(d):
+        for j2 in range(j1 + 1, d):
+            inter = X[i, j1] * X[i, j2]
+            if inter == 0.0:
+                continue
+            grad[fields[j2], j1] += dL * P[fields[j1], j2] * inter
+            grad[fields[j1], j2] += dL * P[fields[j2], j1] * inter
+
+
+# ---------------------------------------------------------------------------------------------
+# losses (loss.nim), in Python so the slow solvers are independent of the C oracle
+# ---------------------------------------------------------------------------------------------
+def loss_val(kind, y, p):
+    if kind == "squared":
+        return 0.5 * (y - p) ** 2
+    if kind == "squared_hinge":
+        return max(1 - p * y, 0.0) ** 2
+    if kind == "logistic":
+        z = p * y
+        return math.log(1 + math.exp(-z)) if z > 0 else math.log(math.exp(z) + 1) - z
+    raise ValueError(kind)
+
+
+def dloss_val(kind, y, p):
+    if kind == "squared":
+        return p - y
+    if kind == "squared_hinge":
+        z = 1 - p * y
+        return -2 * y * z if z > 0 else 0.0
+    if kind == "logistic":
+        z = p * y
+        return -y * math.exp(-z) / (1 + math.exp(-z)) if z > 0 else -y / (math.exp(z) + 1)
+    raise ValueError(kind)
+
+
+MU = {"squared": 1.0, "squared_hinge": 2.0, "logistic": 0.25}
+
+
+def cd_slow_fit(X, y, P, w, intercept, degree, fit_linear, fit_intercept, loss, max_iter, alpha0,
+                alpha, beta):
+    """CDSlow.fit (cd_slow.nim:97-139): naive gradients, full re-prediction after every update."""
+    n, d = X.shape
+    nO, k, dd = P.shape
+    m = dd - d
+    P = P.copy()
+    w = w.copy()
+    alpha0, alpha, beta = alpha0 * n, alpha * n, beta * n
+    mu = MU[loss]
+    col_norm_sq = (X ** 2).sum(axis=0)
+    y_pred = fm_decision_function(X, P, w, intercept, degree)
+    for _ in range(max_iter):
+        if fit_intercept:  # fit_linear_slow / fit_linear.nim:28-38
+            upd = alpha0 * intercept + sum(dloss_val(loss, y[i], y_pred[i]) for i in range(n))
+            upd /= mu * n + alpha0
+            intercept -= upd
+            y_pred = fm_decision_function(X, P, w, intercept, degree)
+        if fit_linear:
+            for j in range(d):
+                upd = alpha * w[j]
+                for i in range(n):
+                    upd += dloss_val(loss, y[i], y_pred[i]) * X[i, j]
+                inv = mu * col_norm_sq[j] + alpha
+                if inv < 1e-12:
+                    continue
+                upd /= inv
+                w[j] -= upd
+                for i in range(n):
+                    y_pred[i] -= upd * X[i, j]
+            y_pred = fm_decision_function(X, P, w, intercept, degree)
+        for o in range(nO):
+            deg = degree - o
+            for s in range(k):
+                for j in range(dd):
+                    dA = np.zeros(n)
+                    others = [q for q in range(dd) if q != j]
+                    for i in range(n):
+                        acc = 0.0
+                        if deg - 1 == 0:
+                            acc = 1.0
+                        else:
+                            for idx in combinations(others, deg - 1):
+                                prod = 1.0
+                                for j2 in idx:
+                                    prod *= P[o, s, j2]
+                                    if j2 < d:
+                                        prod *= X[i, j2]
+                                acc += prod
+                        if j < d:
+                            acc *= X[i, j]
+                        dA[i] = acc
+                    inv = float((dA ** 2).sum()) * mu + beta
+                    g = beta * P[o, s, j]
+                    for i in range(n):
+                        g += dloss_val(loss, y[i], y_pred[i]) * dA[i]
+                    upd = g / inv
+                    P[o, s, j] -= upd
+                    y_pred = fm_decision_function(X, P, w, intercept, degree)
+    return P, w, intercept
+
+
+def adagrad_slow_fit(X, y, P, w, intercept, degree, fit_linear, fit_intercept, loss, max_iter, eta0,
+                     alpha0, alpha, beta, eps):
+    """AdaGradSlow.fit (adagrad_slow.nim:29-102), shuffle=false: dense dual-averaging update."""
+    n, d = X.shape
+    P = P.copy()
+    w = w.copy()
+    gsP = np.zeros_like(P)
+    gnP = np.zeros_like(P) + eps
+    gsw = np.zeros(d)
+    gnw = np.zeros(d) + eps
+    gsb, gnb = 0.0, eps
+    it = 1
+    for _ in range(max_iter):
+        for i in range(n):
+            y_pred = fm_decision_function(X[i:i + 1], P, w, intercept, degree)[0]
+            dL = dloss_val(loss, y[i], y_pred)
+            grad = np.zeros_like(P)
+            fm_grad(X, i, P, degree, dL, grad)
+            t = float(it)
+            if fit_intercept:
+                gsb += dL
+                gnb += dL ** 2
+                intercept = -eta0 * gsb / (math.sqrt(gnb) + eta0 * t * alpha0)
+            if fit_linear:
+                den = eta0 * t * alpha
+                for j in range(d):
+                    gsw[j] += dL * X[i, j]
+                    gnw[j] += (dL * X[i, j]) ** 2
+                    w[j] = -eta0 * gsw[j] / (den + math.sqrt(gnw[j]))
+            den = eta0 * t * beta
+            gsP += grad
+            gnP += grad ** 2
+            P = -eta0 * gsP / (den + np.sqrt(gnP))
+            it += 1
+    return P, w, intercept
+
+
+def sgd_slow_fit(X, y, P, w, intercept, degree, fit_linear, fit_intercept, loss, max_iter, eta0,
+                 alpha0, alpha, beta, power=1.0):
+    """SGDSlow.fit (sgd_slow.nim:38-91), shuffle=false, scheduling=optimal: dense updates with the
+    L2 shrink applied to every parameter at every step."""
+    n, d = X.shape
+    P = P.copy()
+    w = w.copy()
+    it = 1
+
+    def eta(reg):
+        return eta0 / (1.0 + eta0 * reg * it) ** power
+
+    for _ in range(max_iter):
+        for i in range(n):
+            y_pred = fm_decision_function(X[i:i + 1], P, w, intercept, degree)[0]
+            dL = dloss_val(loss, y[i], y_pred)
+            grad = np.zeros_like(P)
+            fm_grad(X, i, P, degree, dL, grad)
+            P -= eta(beta) * (grad + beta * P)
+            if fit_linear:
+                w -= eta(alpha) * (dL * X[i] + alpha * w)
+            if fit_intercept:
+                intercept -= eta(alpha0) * (dL + alpha0 * intercept)
+            it += 1
+    return P, w, intercept

@@ -1,0 +1,184 @@
+"""Pins oracle/ref_cpu.c against the brute-force definitions restated from the reference's own
+test helpers (tests/kernels_slow.nim, tests/model/*_slow.nim, tests/optimizer/*_slow.nim), on the
+reference's test shapes and tolerances.  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import bruteforce as bf
+from oracle.oracle import CSR
+from helpers import make_dense, make_fm_params, make_field_csr
+
+
+# tests/test_kernels.nim:7-46: n=20, d=10, k=10, degrees 2..5, 0..3 dummies, |fast-slow| < 1e-6
+@pytest.mark.parametrize("is_csc", [False, True])
+def test_anova_vs_subset_enumeration(oracle, is_csc):
+    n, d, k, n_aug_max = 20, 10, 10, 3
+    X = make_dense(n, d, 42)
+    rng = np.random.default_rng(7)
+    P = rng.standard_normal((k, d + n_aug_max))
+    csr = CSR.from_dense(X)
+    mat = oracle.csr_to_csc(csr) if is_csc else csr
+    for m in range(n_aug_max + 1):
+        for degree in range(2, 6):
+            for s in range(0, k, 3):
+                Ps = P[s, :d + m]
+                A = oracle.anova(mat, Ps, degree, n_aug=m, is_csc=is_csc)
+                for i in range(0, n, 4):
+                    expect = bf.anova_slow(X[i], Ps, degree, d, m)
+                    assert abs(A[i, degree] - expect) < 1e-6 * max(1.0, abs(expect))
+
+
+# model/fm_slow.nim:42-60 -- decisionFunction incl. dummy features, all fitLower kinds
+@pytest.mark.parametrize("degree", [2, 3, 4])
+@pytest.mark.parametrize("fit_lower", ["explicit", "none", "augment"])
+def test_fm_decision_function_vs_bruteforce(oracle, degree, fit_lower):
+    n, d, k = 12, 6, 4
+    X = make_dense(n, d, 3, density=0.7)
+    P, w, nA = make_fm_params(d, degree, k, fit_lower, True, seed=degree)
+    csr = CSR.from_dense(X)
+    expect = bf.fm_decision_function(X, P, w, 0.3, degree)
+    got_r = oracle.fm_decision_function(csr, P, w, 0.3, degree)
+    got_c = oracle.fm_decision_function(oracle.csr_to_csc(csr), P, w, 0.3, degree, is_csc=True)
+    np.testing.assert_allclose(got_r, expect, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(got_c, expect, rtol=1e-10, atol=1e-12)
+
+
+# model/fm_slow.nim:111-134 -- gradient by combNotj enumeration vs sgd.nim:176-188 recurrences
+@pytest.mark.parametrize("degree", [2, 3, 4, 5])
+@pytest.mark.parametrize("fit_lower", ["explicit", "none", "augment"])
+def test_fm_grad_vs_bruteforce(oracle, degree, fit_lower):
+    n, d, k = 6, 6, 3
+    X = make_dense(n, d, 11, density=0.8)
+    y = np.random.default_rng(0).standard_normal(n)
+    P, w, nA = make_fm_params(d, degree, k, fit_lower, True, seed=degree + 10)
+    csr = CSR.from_dense(X)
+    res = oracle.fm_loss_grad(csr, y, P, w, 0.1, degree, "squared", mini_batch_size=1)
+    yhat = bf.fm_decision_function(X, P, w, 0.1, degree)
+    np.testing.assert_allclose(res["y_pred"], yhat, rtol=1e-10, atol=1e-12)
+    grad = np.zeros_like(P)
+    gw = np.zeros(d)
+    gb = 0.0
+    for i in range(n):
+        dL = yhat[i] - y[i]
+        bf.fm_grad(X, i, P, degree, dL, grad)
+        gw += dL * X[i]
+        gb += dL
+    np.testing.assert_allclose(res["gP"], grad, rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(res["gw"], gw, rtol=1e-10, atol=1e-12)
+    assert abs(res["gb"] - gb) < 1e-10
+
+
+# model/ffm_slow.nim:38-56,110-127; shape of tests/test_sgd_ffm.nim:10-14 (d=20, 5 fields, k=4)
+def test_ffm_vs_bruteforce(oracle):
+    n, d, nF, k = 10, 20, 5, 4
+    X, csr, field_of = make_field_csr(n, d, nF, 5)
+    rng = np.random.default_rng(1)
+    P = rng.standard_normal((nF, d, k)) * 0.3
+    w = rng.standard_normal(d) * 0.1
+    y = rng.standard_normal(n)
+    expect = bf.ffm_decision_function(X, field_of, P, w, -0.2)
+    got = oracle.ffm_decision_function(csr, P, w, -0.2)
+    np.testing.assert_allclose(got, expect, rtol=1e-10, atol=1e-12)
+    res = oracle.ffm_loss_grad(csr, y, P, w, -0.2, "squared", mini_batch_size=1)
+    np.testing.assert_allclose(res["y_pred"], expect, rtol=1e-10, atol=1e-12)
+    grad = np.zeros_like(P)
+    for i in range(n):
+        bf.ffm_grad(X, field_of, i, P, expect[i] - y[i], grad)
+    np.testing.assert_allclose(res["gP"], grad, rtol=1e-9, atol=1e-12)
+
+
+# tests/test_cd.nim:93-128 -- fast CD vs CDSlow after 3 iterations (rtol 1e-6 / atol 1e-9)
+@pytest.mark.parametrize("degree,fit_lower", [(2, "explicit"), (3, "explicit"), (3, "augment"),
+                                              (3, "none"), (4, "explicit")])
+@pytest.mark.parametrize("fit_linear,fit_intercept", [(True, True), (False, False)])
+def test_cd_vs_slow(oracle, degree, fit_lower, fit_linear, fit_intercept):
+    n, d, k = 14, 5, 2
+    X = make_dense(n, d, 21, density=0.8)
+    rng = np.random.default_rng(2)
+    y = rng.standard_normal(n)
+    P, w, nA = make_fm_params(d, degree, k, fit_lower, fit_linear, seed=5)
+    csc = oracle.csr_to_csc(CSR.from_dense(X))
+    fast = oracle.cd_fit(csc, y, P, w, 0.0, degree, "squared", fit_linear, fit_intercept,
+                         max_iter=2, alpha0=1e-6, alpha=1e-3, beta=1e-3)
+    Ps, ws, bs = bf.cd_slow_fit(X, y, P, w, 0.0, degree, fit_linear, fit_intercept, "squared", 2,
+                                1e-6, 1e-3, 1e-3)
+    np.testing.assert_allclose(fast["P"], Ps, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(fast["w"], ws, rtol=1e-6, atol=1e-9)
+    assert abs(fast["intercept"] - bs) < 1e-7
+    # the cached predictions must equal a from-scratch forward with the final parameters
+    yp = oracle.fm_decision_function(csc, fast["P"], fast["w"], fast["intercept"], degree, is_csc=True)
+    np.testing.assert_allclose(fast["y_pred"], yp, rtol=1e-9, atol=1e-11)
+
+
+# tests/test_adagrad.nim:92-126 -- AdaGrad vs AdaGradSlow (5 epochs in the reference; 2 here)
+@pytest.mark.parametrize("degree,fit_lower", [(2, "explicit"), (3, "explicit"), (3, "augment"), (4, "none")])
+def test_adagrad_vs_slow(oracle, degree, fit_lower):
+    n, d, k = 10, 5, 2
+    X = make_dense(n, d, 31, density=0.7)
+    y = np.random.default_rng(3).standard_normal(n)
+    P, w, nA = make_fm_params(d, degree, k, fit_lower, True, seed=8)
+    w = np.zeros(d)
+    csr = CSR.from_dense(X)
+    fast = oracle.adagrad_fit(csr, y, P, w, 0.0, degree, "squared", True, True, max_iter=2)
+    Ps, ws, bs = bf.adagrad_slow_fit(X, y, P, w, 0.0, degree, True, True, "squared", 2, 0.1, 1e-6,
+                                     1e-3, 1e-3, 1e-10)
+    np.testing.assert_allclose(fast["P"], Ps, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(fast["w"], ws, rtol=1e-6, atol=1e-9)
+    assert abs(fast["intercept"] - bs) < 1e-7
+
+
+# tests/test_sgd.nim:92-126 -- SGD (lazy scaling) vs SGDSlow (dense shrink)
+@pytest.mark.parametrize("degree,fit_lower", [(2, "explicit"), (3, "explicit"), (3, "augment"), (4, "none")])
+def test_sgd_vs_slow(oracle, degree, fit_lower):
+    n, d, k = 10, 5, 2
+    X = make_dense(n, d, 41, density=0.5)
+    y = np.random.default_rng(4).standard_normal(n)
+    P, w, nA = make_fm_params(d, degree, k, fit_lower, True, seed=9)
+    csr = CSR.from_dense(X)
+    fast = oracle.sgd_fit(csr, y, P, w, 0.0, degree, "squared", True, True, max_iter=2)
+    Ps, ws, bs = bf.sgd_slow_fit(X, y, P, w, 0.0, degree, True, True, "squared", 2, 0.01, 1e-6,
+                                 1e-3, 1e-3)
+    np.testing.assert_allclose(fast["P"], Ps, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(fast["w"], ws, rtol=1e-6, atol=1e-9)
+    assert abs(fast["intercept"] - bs) < 1e-7
+
+
+# tests/test_dataset.nim:6-52 style: CSR<->CSC round trip + nnz equality + stable ordering
+def test_transpose_bookkeeping(oracle):
+    X = make_dense(17, 9, 51, density=0.4)
+    csr = CSR.from_dense(X)
+    csc = oracle.csr_to_csc(csr)
+    assert csc.indptr[-1] == csr.indptr[-1] == np.count_nonzero(X)
+    for j in range(9):
+        rows = csc.indices[csc.indptr[j]:csc.indptr[j + 1]]
+        assert np.all(np.diff(rows) > 0)           # stable in row order
+        np.testing.assert_array_equal(rows, np.nonzero(X[:, j])[0])
+    back = oracle.csc_to_csr(csc)
+    np.testing.assert_array_equal(back.indptr, csr.indptr)
+    np.testing.assert_array_equal(back.indices, csr.indices)
+    np.testing.assert_array_equal(back.data, csr.data)
+    sub = oracle.csr_take_rows(csr, [3, 0, 16])
+    np.testing.assert_array_equal(sub.to_dense(), X[[3, 0, 16]])
+    sl = oracle.csc_slice_rows(csc, 4, 11)
+    np.testing.assert_array_equal(oracle.csc_to_csr(sl).to_dense(), X[4:12])
+
+
+def test_mbpsgd_reduces_to_full_gradient_step(oracle):
+    """With mb == n, maxIterInner == 1, one MBPSGD epoch is one (P - eta*g)/(1+eta*beta) step on the
+    mean gradient (minibatch_psgd.nim:96-122, params.nim:90-98)."""
+    n, d, k, degree = 9, 6, 3, 3
+    X = make_dense(n, d, 61, density=0.6)
+    y = np.sign(np.random.default_rng(5).standard_normal(n))
+    P, w, nA = make_fm_params(d, degree, k, "explicit", True, seed=3)
+    csr = CSR.from_dense(X)
+    res = oracle.mbpsgd_fit(csr, y, P, w, 0.05, degree, "logistic", max_iter=1, mini_batch_size=n,
+                            eta0=0.1, alpha0=1e-6, alpha=1e-3, beta=1e-4)
+    g = oracle.fm_loss_grad(csr, y, P, w, 0.05, degree, "logistic", mini_batch_size=n)
+    eta_P = 0.1 / (1 + 0.1 * 1e-4 * 1)
+    eta_w = 0.1 / (1 + 0.1 * 1e-3 * 1)
+    eta_b = 0.1 / (1 + 0.1 * 1e-6 * 1)
+    np.testing.assert_allclose(res["P"], (P - eta_P * g["gP"]) / (1 + eta_P * 1e-4), rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(res["w"], (w - eta_w * g["gw"]) / (1 + eta_w * 1e-3), rtol=1e-12, atol=1e-15)
+    assert abs(res["intercept"] - (0.05 - eta_b * g["gb"]) / (1 + eta_b * 1e-6)) < 1e-14
+    assert abs(res["epoch_loss"][0] - g["loss"] / n) < 1e-14
+    assert res["it"] == 2
