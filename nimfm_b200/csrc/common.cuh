@@ -1,0 +1,208 @@
+// common.cuh -- private structures and helpers of libnimfm_cuda.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/nimfm_cuda.h"
+
+struct ncclComm;
+
+#define NIMFM_MAX_DEGREE 6   // device row kernels are instantiated for degree 2..6
+
+struct nimfm_ctx {
+  int device = 0;
+  int numSMs = 0;
+  int smemOptin = 0;          // max opt-in dynamic shared memory per block
+  int smemPerSM = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  // scratch (grown on demand)
+  double *partials = nullptr;  // per-group partial sums written by the row kernels
+  size_t partialsCap = 0;
+  double *scalars = nullptr;   // small device scalar block (64 doubles)
+  double *hostScalars = nullptr;  // pinned mirror
+  int64_t *idxScratch = nullptr;  // device copy of host-provided row ids
+  size_t idxCap = 0;
+  int32_t *idx32Scratch = nullptr;
+  // host-streaming staging (nimfm_fm_loss_grad_host): two buffer sets + a copy stream
+  cudaStream_t copyStream = nullptr;
+  cudaEvent_t evCopied[2] = {nullptr, nullptr}, evComputed[2] = {nullptr, nullptr};
+  cudaEvent_t tev0 = nullptr, tev1 = nullptr;   // nimfm_timer_*
+  struct Stage {
+    double *data = nullptr, *y = nullptr;
+    int64_t *idx64 = nullptr, *indptr = nullptr;
+    int32_t *idx32 = nullptr;
+    size_t capNnz = 0, capRows = 0;
+  } stage[2];
+  // communicator
+  ncclComm *comm = nullptr;
+  int rank = 0, nranks = 1;
+};
+
+struct nimfm_dataset {
+  int kind = NIMFM_DS_CSR;
+  int64_t n = 0, d = 0, nnz = 0;     // n rows (samples), d columns (features) of the LOGICAL matrix
+  int64_t nFields = 0;
+  int64_t maxSegNnz = 0;             // longest row (CSR) / column (CSC)
+  double *data = nullptr;
+  int32_t *indices = nullptr;        // column ids (CSR) / row ids (CSC), narrowed to int32
+  int64_t *indptr = nullptr;
+  int32_t *fields = nullptr;
+  double *y = nullptr;
+  // CD only: runs of consecutive columns with pairwise-disjoint row support (built at cd_begin)
+  std::vector<int64_t> cdBatchStart;
+};
+
+struct nimfm_fm {
+  int degree = 2, k = 1, nOrders = 1, nAug = 0;
+  int64_t d = 0;           // nFeatures (without dummies)
+  int fitLinear = 1, fitIntercept = 1;
+  int64_t dd() const { return d + nAug; }
+  int64_t nP() const { return (int64_t)nOrders * dd() * k; }
+  // device parameters, layout P[j][o][s] ("feature-major": one feature's nOrders*k doubles contiguous)
+  double *P = nullptr, *w = nullptr, *lams = nullptr;
+  double *b = nullptr;     // device scalar block: [0]=intercept
+  bool lamsAreOnes = true;
+  // gradient buffer: [gP (nP) | gw (d) | gb, lossSum] contiguous for a single all-reduce
+  double *grad = nullptr;
+  // AdaGrad state (same layouts): g_sum, g_norm, and per-minibatch deltas
+  double *gsP = nullptr, *gnP = nullptr, *gsw = nullptr, *gnw = nullptr;
+  double *dG = nullptr;    // [dGsP (nP) | dGnP (nP) | dGsw (d) | dGnw (d) | touched (d+nAug) | loss, sum dL, sum dL^2, viol]
+  double *adaScal = nullptr;   // device: [gsb, gnb]
+  bool adaReady = false;
+  // SGD lazy-scaling caches
+  double *scalingsP = nullptr, *scalingsW = nullptr, *sgdScal = nullptr;  // sgdScal: [scaling_P, scaling_w, viol, loss]
+  bool sgdReady = false;
+  // CD caches
+  double *Pcm = nullptr;       // component-major copy P[o][s][j] used by the column kernels
+  double *yPred = nullptr, *Acache = nullptr, *colNormSq = nullptr, *cdScal = nullptr;
+  int64_t cdN = 0;
+  bool cdReady = false;
+  // reusable host staging
+  std::vector<double> hostTmp;
+};
+
+struct nimfm_ffm {
+  int k = 1;
+  int64_t nFields = 0, d = 0;
+  int fitLinear = 1, fitIntercept = 1;
+  int64_t nP() const { return nFields * d * k; }
+  // device layout P[j][f][s]: one feature's nFields*k doubles contiguous
+  double *P = nullptr, *w = nullptr, *b = nullptr;
+  double *grad = nullptr;      // [gP | gw | gb, lossSum]
+  double *gsP = nullptr, *gnP = nullptr, *gsw = nullptr, *gnw = nullptr, *dG = nullptr, *adaScal = nullptr;
+  bool adaReady = false;
+  double *scalingsP = nullptr, *scalingsW = nullptr, *sgdScal = nullptr;
+  bool sgdReady = false;
+  std::vector<double> hostTmp;
+};
+
+// ------------------------------------------------------------------ error plumbing
+int nimfm_fail(nimfm_ctx *ctx, int code, const char *fmt, ...);
+
+#define CK(call)                                                                             \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess)                                                                   \
+      return nimfm_fail(ctx, NIMFM_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,      \
+                        cudaGetErrorString(e_));                                             \
+  } while (0)
+
+#define REQUIRE(cond, ...)                                                \
+  do {                                                                    \
+    if (!(cond)) return nimfm_fail(ctx, NIMFM_ERR_INVALID, __VA_ARGS__);  \
+  } while (0)
+
+#define LAUNCHED(ctx) ((ctx)->launches++)
+
+int nimfm_ensure_partials(nimfm_ctx *ctx, size_t nDoubles);
+int nimfm_ensure_idx(nimfm_ctx *ctx, size_t n);
+int nimfm_allreduce_sum(nimfm_ctx *ctx, double *buf, int64_t n);
+
+// upload host int64 row ids into ctx->idx32Scratch as int32 (validated against n)
+int nimfm_stage_row_ids(nimfm_ctx *ctx, const int64_t *ids, int64_t count, int64_t n);
+
+// ------------------------------------------------------------------ device helpers
+#ifdef __CUDACC__
+
+__device__ __forceinline__ double dev_loss(int kind, double thr, double y, double p) {
+  switch (kind) {
+    case NIMFM_LOSS_SQUARED: { double z = y - p; return 0.5 * (z * z); }
+    case NIMFM_LOSS_SQUARED_HINGE: { double z = fmax(1.0 - p * y, 0.0); return z * z; }
+    case NIMFM_LOSS_LOGISTIC: {
+      double z = p * y;
+      return z > 0 ? log(1.0 + exp(-z)) : log(exp(z) + 1.0) - z;
+    }
+    default: {
+      double z = fabs(y - p);
+      return z < thr ? 0.5 * (z * z) : thr * (z - 0.5 * thr);
+    }
+  }
+}
+
+__device__ __forceinline__ double dev_dloss(int kind, double thr, double y, double p) {
+  switch (kind) {
+    case NIMFM_LOSS_SQUARED: return p - y;
+    case NIMFM_LOSS_SQUARED_HINGE: { double z = 1.0 - p * y; return z > 0 ? -2.0 * y * z : 0.0; }
+    case NIMFM_LOSS_LOGISTIC: {
+      double z = p * y;
+      if (z > 0) { double e = exp(-z); return -y * e / (1.0 + e); }
+      return -y / (exp(z) + 1.0);
+    }
+    default: {  // loss.nim:90-93 (sign quirk preserved)
+      double z = fabs(y - p);
+      return z < thr ? y - p : thr;
+    }
+  }
+}
+
+__host__ __device__ __forceinline__ double loss_mu(int kind) {
+  return kind == NIMFM_LOSS_SQUARED_HINGE ? 2.0 : (kind == NIMFM_LOSS_LOGISTIC ? 0.25 : 1.0);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// sum over aligned sub-groups of G lanes (G power of two <= 32); every lane of the warp must call
+__device__ __forceinline__ double group_sum(double v, int G) {
+  for (int off = G >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// block-wide sum; result valid in thread 0.  red must hold blockDim.x/32 doubles.
+__device__ __forceinline__ double block_sum(double v, double *red) {
+  v = warp_sum(v);
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (wid == 0) {
+    int nw = (blockDim.x + 31) >> 5;
+    r = lane < nw ? red[lane] : 0.0;
+    r = warp_sum(r);
+  }
+  return r;
+}
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+#endif  // __CUDACC__

@@ -1,0 +1,238 @@
+// context.cu -- lifecycle, error plumbing, scratch pools, NCCL communicator (dlopen'ed lazily so the
+// library loads on a box without NCCL/GPU; there is still no CPU compute path).
+#include <dlfcn.h>
+#include <stdarg.h>
+
+#include "common.cuh"
+
+// minimal NCCL surface (types as in nccl.h 2.27/2.28; resolved at run time)
+typedef struct { char internal[128]; } nimfm_ncclUniqueId;
+typedef int (*fn_ncclGetUniqueId)(nimfm_ncclUniqueId *);
+typedef int (*fn_ncclCommInitRank)(ncclComm **, int, nimfm_ncclUniqueId, int);
+typedef int (*fn_ncclAllReduce)(const void *, void *, size_t, int, int, ncclComm *, cudaStream_t);
+typedef int (*fn_ncclCommDestroy)(ncclComm *);
+typedef const char *(*fn_ncclGetErrorString)(int);
+static struct {
+  void *h;
+  fn_ncclGetUniqueId getUniqueId;
+  fn_ncclCommInitRank commInitRank;
+  fn_ncclAllReduce allReduce;
+  fn_ncclCommDestroy commDestroy;
+  fn_ncclGetErrorString errStr;
+} g_nccl;
+
+static int load_nccl() {
+  if (g_nccl.h) return 0;
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return -1;
+  g_nccl.getUniqueId = (fn_ncclGetUniqueId)dlsym(h, "ncclGetUniqueId");
+  g_nccl.commInitRank = (fn_ncclCommInitRank)dlsym(h, "ncclCommInitRank");
+  g_nccl.allReduce = (fn_ncclAllReduce)dlsym(h, "ncclAllReduce");
+  g_nccl.commDestroy = (fn_ncclCommDestroy)dlsym(h, "ncclCommDestroy");
+  g_nccl.errStr = (fn_ncclGetErrorString)dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.getUniqueId || !g_nccl.commInitRank || !g_nccl.allReduce || !g_nccl.commDestroy) return -1;
+  g_nccl.h = h;
+  return 0;
+}
+
+static thread_local std::string g_noctx_err;
+
+int nimfm_fail(nimfm_ctx *ctx, int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  else g_noctx_err = buf;
+  return code;
+}
+
+extern "C" {
+
+int32_t nimfm_version(void) { return 100; }
+
+const char *nimfm_last_error(const nimfm_ctx *ctx) { return ctx ? ctx->err.c_str() : g_noctx_err.c_str(); }
+
+int64_t nimfm_launch_count(const nimfm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t nimfm_ctx_create(int32_t device, nimfm_ctx **out) {
+  nimfm_ctx *ctx = nullptr;
+  if (!out) return nimfm_fail(nullptr, NIMFM_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return nimfm_fail(nullptr, NIMFM_ERR_CUDA,
+                      "no CUDA device available (%s); libnimfm_cuda has no CPU fallback",
+                      e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (device < 0 || device >= count)
+    return nimfm_fail(nullptr, NIMFM_ERR_INVALID, "device %d out of range [0,%d)", device, count);
+  ctx = new nimfm_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    delete ctx;
+    return nimfm_fail(nullptr, NIMFM_ERR_CUDA, "cannot select device %d", device);
+  }
+  if (prop.major < 10) {
+    int maj = prop.major, mnr = prop.minor;
+    delete ctx;
+    return nimfm_fail(nullptr, NIMFM_ERR_UNSUPPORTED,
+                      "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, maj, mnr);
+  }
+  ctx->numSMs = prop.multiProcessorCount;
+  ctx->smemOptin = (int)prop.sharedMemPerBlockOptin;
+  ctx->smemPerSM = (int)prop.sharedMemPerMultiprocessor;
+  CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&ctx->ev0));
+  CK(cudaEventCreate(&ctx->ev1));
+  CK(cudaEventCreate(&ctx->tev0));
+  CK(cudaEventCreate(&ctx->tev1));
+  CK(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+  for (int s = 0; s < 2; s++) {
+    CK(cudaEventCreateWithFlags(&ctx->evCopied[s], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->evComputed[s], cudaEventDisableTiming));
+  }
+  CK(cudaMalloc(&ctx->scalars, 64 * sizeof(double)));
+  CK(cudaMemset(ctx->scalars, 0, 64 * sizeof(double)));
+  CK(cudaMallocHost(&ctx->hostScalars, 64 * sizeof(double)));
+  *out = ctx;
+  return NIMFM_OK;
+}
+
+int32_t nimfm_ctx_destroy(nimfm_ctx *ctx) {
+  if (!ctx) return NIMFM_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->comm && g_nccl.commDestroy) g_nccl.commDestroy(ctx->comm);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->partials);
+  cudaFree(ctx->scalars);
+  cudaFree(ctx->idxScratch);
+  cudaFree(ctx->idx32Scratch);
+  cudaFreeHost(ctx->hostScalars);
+  for (int s = 0; s < 2; s++) {
+    cudaFree(ctx->stage[s].data); cudaFree(ctx->stage[s].y); cudaFree(ctx->stage[s].idx64);
+    cudaFree(ctx->stage[s].indptr); cudaFree(ctx->stage[s].idx32);
+    if (ctx->evCopied[s]) cudaEventDestroy(ctx->evCopied[s]);
+    if (ctx->evComputed[s]) cudaEventDestroy(ctx->evComputed[s]);
+  }
+  if (ctx->tev0) cudaEventDestroy(ctx->tev0);
+  if (ctx->tev1) cudaEventDestroy(ctx->tev1);
+  if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return NIMFM_OK;
+}
+
+int32_t nimfm_comm_unique_id(void *uid128) {
+  if (!uid128) return nimfm_fail(nullptr, NIMFM_ERR_INVALID, "uid is NULL");
+  if (load_nccl() != 0) return nimfm_fail(nullptr, NIMFM_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+  nimfm_ncclUniqueId id;
+  int rc = g_nccl.getUniqueId(&id);
+  if (rc != 0) return nimfm_fail(nullptr, NIMFM_ERR_NCCL, "ncclGetUniqueId: %s", g_nccl.errStr ? g_nccl.errStr(rc) : "?");
+  memcpy(uid128, &id, 128);
+  return NIMFM_OK;
+}
+
+int32_t nimfm_comm_init(nimfm_ctx *ctx, int32_t rank, int32_t nranks, const void *uid128) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank %d / nranks %d", rank, nranks);
+  ctx->rank = rank;
+  ctx->nranks = nranks;
+  if (nranks == 1) return NIMFM_OK;
+  REQUIRE(uid128 != nullptr, "uid is NULL");
+  if (load_nccl() != 0) return nimfm_fail(ctx, NIMFM_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+  CK(cudaSetDevice(ctx->device));
+  nimfm_ncclUniqueId id;
+  memcpy(&id, uid128, 128);
+  int rc = g_nccl.commInitRank(&ctx->comm, nranks, id, rank);
+  if (rc != 0) return nimfm_fail(ctx, NIMFM_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.errStr ? g_nccl.errStr(rc) : "?");
+  return NIMFM_OK;
+}
+
+int32_t nimfm_comm_size(const nimfm_ctx *ctx) { return ctx ? ctx->nranks : 0; }
+
+int32_t nimfm_timer_start(nimfm_ctx *ctx) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->tev0, ctx->stream));
+  return NIMFM_OK;
+}
+
+int32_t nimfm_timer_stop(nimfm_ctx *ctx, float *ms) {
+  if (!ctx || !ms) return NIMFM_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->tev1, ctx->stream));
+  CK(cudaEventSynchronize(ctx->tev1));
+  CK(cudaEventElapsedTime(ms, ctx->tev0, ctx->tev1));
+  return NIMFM_OK;
+}
+
+}  // extern "C"
+
+int nimfm_allreduce_sum(nimfm_ctx *ctx, double *buf, int64_t n) {
+  if (ctx->nranks == 1) return NIMFM_OK;
+  if (!ctx->comm) return nimfm_fail(ctx, NIMFM_ERR_NCCL, "communicator not initialised (nimfm_comm_init)");
+  int rc = g_nccl.allReduce(buf, buf, (size_t)n, /*ncclDouble*/ 8, /*ncclSum*/ 0, ctx->comm, ctx->stream);
+  if (rc != 0) return nimfm_fail(ctx, NIMFM_ERR_NCCL, "ncclAllReduce: %s", g_nccl.errStr ? g_nccl.errStr(rc) : "?");
+  return NIMFM_OK;
+}
+
+int nimfm_ensure_partials(nimfm_ctx *ctx, size_t nDoubles) {
+  if (ctx->partialsCap >= nDoubles) return NIMFM_OK;
+  if (ctx->partials) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(ctx->partials));
+    ctx->partials = nullptr;
+    ctx->partialsCap = 0;
+  }
+  size_t cap = nDoubles < 65536 ? 65536 : nDoubles;
+  CK(cudaMalloc(&ctx->partials, cap * sizeof(double)));
+  ctx->partialsCap = cap;
+  return NIMFM_OK;
+}
+
+int nimfm_ensure_idx(nimfm_ctx *ctx, size_t n) {
+  if (ctx->idxCap >= n) return NIMFM_OK;
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->idxScratch) CK(cudaFree(ctx->idxScratch));
+  if (ctx->idx32Scratch) CK(cudaFree(ctx->idx32Scratch));
+  ctx->idxScratch = nullptr;
+  ctx->idx32Scratch = nullptr;
+  ctx->idxCap = 0;
+  size_t cap = n < 4096 ? 4096 : n;
+  CK(cudaMalloc(&ctx->idxScratch, cap * sizeof(int64_t)));
+  CK(cudaMalloc(&ctx->idx32Scratch, cap * sizeof(int32_t)));
+  ctx->idxCap = cap;
+  return NIMFM_OK;
+}
+
+__global__ void narrow_ids_kernel(const int64_t *in, int32_t *out, int64_t count, int64_t n, int *bad) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t v = in[i];
+    if (v < 0 || v >= n) { *bad = 1; v = 0; }
+    out[i] = (int32_t)v;
+  }
+}
+
+int nimfm_stage_row_ids(nimfm_ctx *ctx, const int64_t *ids, int64_t count, int64_t n) {
+  int rc = nimfm_ensure_idx(ctx, (size_t)count + 2);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->idxScratch, ids, (size_t)count * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+  int *bad = reinterpret_cast<int *>(ctx->scalars + 60);
+  CK(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
+  int grid = (int)((count + 255) / 256);
+  if (grid > 4096) grid = 4096;
+  if (grid < 1) grid = 1;
+  narrow_ids_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->idxScratch, ctx->idx32Scratch, count, n, bad);
+  LAUNCHED(ctx);
+  int hbad = 0;
+  CK(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (hbad) return nimfm_fail(ctx, NIMFM_ERR_INVALID, "row index out of range [0,%lld)", (long long)n);
+  return NIMFM_OK;
+}

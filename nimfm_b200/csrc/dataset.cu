@@ -1,0 +1,184 @@
+// dataset.cu -- device-resident CSR / CSC / CSR-with-fields containers.
+// Integer bookkeeping only: index narrowing int64 -> int32, row-shard rebasing (X[slice],
+// tensor/sparse.nim:263-290) and the stable counting-sort transpose (sparse.nim:490-527).
+#include <algorithm>
+
+#include "common.cuh"
+
+static int alloc_copy(nimfm_ctx *ctx, void **dst, const void *src, size_t bytes) {
+  CK(cudaMalloc(dst, bytes ? bytes : 16));
+  if (bytes) CK(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return NIMFM_OK;
+}
+
+static int upload_common(nimfm_ctx *ctx, int kind, int64_t nSeg, int64_t nOther, int64_t n, int64_t d,
+                         const double *data, const int64_t *indices, const int64_t *indptr,
+                         const int64_t *fields, int64_t nFields, int64_t segBegin, int64_t segEnd,
+                         nimfm_dataset **out) {
+  // nSeg: number of compressed segments in the host arrays (rows for CSR, columns for CSC);
+  // nOther: extent of the index values.
+  REQUIRE(out != nullptr, "out is NULL");
+  REQUIRE(n >= 0 && d >= 0, "negative shape");
+  REQUIRE(indptr != nullptr, "indptr is NULL");
+  REQUIRE(segBegin >= 0 && segBegin <= segEnd && segEnd <= nSeg, "bad segment range [%lld,%lld) of %lld",
+          (long long)segBegin, (long long)segEnd, (long long)nSeg);
+  REQUIRE(nOther < (int64_t)2147483647, "index extent %lld does not fit int32", (long long)nOther);
+  const int64_t base = indptr[segBegin];
+  const int64_t nnz = indptr[segEnd] - base;
+  REQUIRE(nnz >= 0, "indptr is not monotone");
+  REQUIRE(nnz == 0 || (data != nullptr && indices != nullptr), "data/indices are NULL");
+  const int64_t ns = segEnd - segBegin;
+  std::vector<int64_t> ptr((size_t)ns + 1);
+  int64_t maxSeg = 0;
+  for (int64_t s = 0; s <= ns; s++) {
+    ptr[s] = indptr[segBegin + s] - base;
+    if (s > 0) {
+      int64_t len = ptr[s] - ptr[s - 1];
+      REQUIRE(len >= 0, "indptr is not monotone at %lld", (long long)(segBegin + s));
+      maxSeg = std::max(maxSeg, len);
+    }
+  }
+  std::vector<int32_t> idx32((size_t)nnz);
+  for (int64_t q = 0; q < nnz; q++) {
+    int64_t v = indices[base + q];
+    REQUIRE(v >= 0 && v < nOther, "index %lld out of range [0,%lld) at nnz %lld", (long long)v,
+            (long long)nOther, (long long)(base + q));
+    idx32[q] = (int32_t)v;
+  }
+  std::vector<int32_t> f32;
+  if (fields) {
+    f32.resize((size_t)nnz);
+    for (int64_t q = 0; q < nnz; q++) {
+      int64_t v = fields[base + q];
+      REQUIRE(v >= 0 && v < nFields, "field %lld out of range [0,%lld)", (long long)v, (long long)nFields);
+      f32[q] = (int32_t)v;
+    }
+  }
+  nimfm_dataset *ds = new nimfm_dataset();
+  ds->kind = kind;
+  ds->n = (kind == NIMFM_DS_CSC) ? n : ns;
+  ds->d = (kind == NIMFM_DS_CSC) ? ns : d;
+  ds->nnz = nnz;
+  ds->nFields = fields ? nFields : 0;
+  ds->maxSegNnz = maxSeg;
+  int rc;
+  if ((rc = alloc_copy(ctx, (void **)&ds->data, data ? data + base : nullptr, (size_t)nnz * 8))) return rc;
+  if ((rc = alloc_copy(ctx, (void **)&ds->indices, idx32.data(), (size_t)nnz * 4))) return rc;
+  if ((rc = alloc_copy(ctx, (void **)&ds->indptr, ptr.data(), ((size_t)ns + 1) * 8))) return rc;
+  if (fields && (rc = alloc_copy(ctx, (void **)&ds->fields, f32.data(), (size_t)nnz * 4))) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  *out = ds;
+  return NIMFM_OK;
+}
+
+extern "C" {
+
+int32_t nimfm_csr_upload(nimfm_ctx *ctx, int64_t n, int64_t d, const double *data,
+                         const int64_t *indices, const int64_t *indptr, const int64_t *fields,
+                         int64_t nFields, int64_t rowBegin, int64_t rowEnd, nimfm_dataset **out) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  return upload_common(ctx, fields ? NIMFM_DS_CSR_FIELD : NIMFM_DS_CSR, n, d, n, d, data, indices, indptr,
+                       fields, nFields, rowBegin, rowEnd, out);
+}
+
+int32_t nimfm_csc_upload(nimfm_ctx *ctx, int64_t n, int64_t d, const double *data,
+                         const int64_t *indices, const int64_t *indptr, nimfm_dataset **out) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  return upload_common(ctx, NIMFM_DS_CSC, d, n, n, d, data, indices, indptr, nullptr, 0, 0, d, out);
+}
+
+int32_t nimfm_dataset_set_targets(nimfm_ctx *ctx, nimfm_dataset *ds, const double *y) {
+  if (!ctx || !ds) return NIMFM_ERR_INVALID;
+  REQUIRE(y != nullptr || ds->n == 0, "y is NULL");
+  CK(cudaSetDevice(ctx->device));
+  if (!ds->y) CK(cudaMalloc(&ds->y, (size_t)(ds->n ? ds->n : 1) * 8));
+  CK(cudaMemcpyAsync(ds->y, y, (size_t)ds->n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return NIMFM_OK;
+}
+
+int32_t nimfm_dataset_info(const nimfm_dataset *ds, int64_t *n, int64_t *d, int64_t *nnz, int32_t *kind,
+                           int64_t *nFields, int64_t *maxRowNnz) {
+  if (!ds) return NIMFM_ERR_INVALID;
+  if (n) *n = ds->n;
+  if (d) *d = ds->d;
+  if (nnz) *nnz = ds->nnz;
+  if (kind) *kind = ds->kind;
+  if (nFields) *nFields = ds->nFields;
+  if (maxRowNnz) *maxRowNnz = ds->maxSegNnz;
+  return NIMFM_OK;
+}
+
+int32_t nimfm_dataset_download(nimfm_ctx *ctx, const nimfm_dataset *ds, double *data, int64_t *indices,
+                               int64_t *indptr, int64_t *fields) {
+  if (!ctx || !ds) return NIMFM_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  const int64_t ns = ds->kind == NIMFM_DS_CSC ? ds->d : ds->n;
+  if (data) CK(cudaMemcpy(data, ds->data, (size_t)ds->nnz * 8, cudaMemcpyDeviceToHost));
+  if (indptr) CK(cudaMemcpy(indptr, ds->indptr, ((size_t)ns + 1) * 8, cudaMemcpyDeviceToHost));
+  if (indices) {
+    std::vector<int32_t> tmp((size_t)ds->nnz);
+    CK(cudaMemcpy(tmp.data(), ds->indices, (size_t)ds->nnz * 4, cudaMemcpyDeviceToHost));
+    for (int64_t q = 0; q < ds->nnz; q++) indices[q] = tmp[q];
+  }
+  if (fields) {
+    REQUIRE(ds->fields != nullptr, "dataset has no fields");
+    std::vector<int32_t> tmp((size_t)ds->nnz);
+    CK(cudaMemcpy(tmp.data(), ds->fields, (size_t)ds->nnz * 4, cudaMemcpyDeviceToHost));
+    for (int64_t q = 0; q < ds->nnz; q++) fields[q] = tmp[q];
+  }
+  return NIMFM_OK;
+}
+
+// toCSCMatrix / toCSRMatrix (tensor/sparse.nim:490-527): counting sort by the other axis, stable in
+// segment order.  Runs on the host inside the library (O(nnz) integer work, done once per dataset).
+int32_t nimfm_dataset_transpose(nimfm_ctx *ctx, const nimfm_dataset *in, nimfm_dataset **out) {
+  if (!ctx || !in) return NIMFM_ERR_INVALID;
+  REQUIRE(out != nullptr, "out is NULL");
+  REQUIRE(in->kind != NIMFM_DS_CSR_FIELD, "transpose of field datasets is not supported");
+  CK(cudaSetDevice(ctx->device));
+  const bool toCsc = in->kind == NIMFM_DS_CSR;
+  const int64_t nsIn = toCsc ? in->n : in->d, nsOut = toCsc ? in->d : in->n, nnz = in->nnz;
+  std::vector<double> data((size_t)nnz), odata((size_t)nnz);
+  std::vector<int32_t> idx((size_t)nnz);
+  std::vector<int64_t> ptr((size_t)nsIn + 1), optr((size_t)nsOut + 1, 0), oidx((size_t)nnz), offs((size_t)nsOut, 0);
+  CK(cudaMemcpy(data.data(), in->data, (size_t)nnz * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(idx.data(), in->indices, (size_t)nnz * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(ptr.data(), in->indptr, ((size_t)nsIn + 1) * 8, cudaMemcpyDeviceToHost));
+  for (int64_t q = 0; q < nnz; q++) optr[(size_t)idx[q] + 1] += 1;
+  for (int64_t s = 0; s < nsOut; s++) optr[s + 1] += optr[s];
+  for (int64_t s = 0; s < nsIn; s++)
+    for (int64_t q = ptr[s]; q < ptr[s + 1]; q++) {
+      const int64_t t = idx[q];
+      odata[optr[t] + offs[t]] = data[q];
+      oidx[optr[t] + offs[t]] = s;
+      offs[t] += 1;
+    }
+  nimfm_dataset *o = nullptr;
+  int rc = toCsc ? nimfm_csc_upload(ctx, in->n, in->d, odata.data(), oidx.data(), optr.data(), &o)
+                 : nimfm_csr_upload(ctx, in->n, in->d, odata.data(), oidx.data(), optr.data(), nullptr, 0, 0,
+                                    in->n, &o);
+  if (rc) return rc;
+  if (in->y) {
+    CK(cudaMalloc(&o->y, (size_t)(o->n ? o->n : 1) * 8));
+    CK(cudaMemcpy(o->y, in->y, (size_t)o->n * 8, cudaMemcpyDeviceToDevice));
+  }
+  *out = o;
+  return NIMFM_OK;
+}
+
+int32_t nimfm_dataset_free(nimfm_ctx *ctx, nimfm_dataset *ds) {
+  if (!ds) return NIMFM_OK;
+  if (ctx) cudaSetDevice(ctx->device);
+  cudaFree(ds->data);
+  cudaFree(ds->indices);
+  cudaFree(ds->indptr);
+  cudaFree(ds->fields);
+  cudaFree(ds->y);
+  delete ds;
+  return NIMFM_OK;
+}
+
+}  // extern "C"

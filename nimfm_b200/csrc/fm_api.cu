@@ -1,0 +1,859 @@
+// fm_api.cu -- FactorizationMachine state on the device and the row-parallel entry points:
+// decisionFunction (K1), predict+grad (K2), MBPSGD epoch (K2+K3), AdaGrad epoch (K4+K5).
+#include <math.h>
+
+#include <algorithm>
+
+#include "fm_rows.cuh"
+
+typedef void (*RowKernel)(const RowArgs);
+RowKernel nimfm_row_kernel_predict(int degree, bool explicitLower);
+RowKernel nimfm_row_kernel_grad(int degree, bool explicitLower);
+RowKernel nimfm_row_kernel_adagrad(int degree, bool explicitLower);
+
+// ------------------------------------------------------------------ layout permutations
+// reference model layout  R[o][s][j]   (factorization_machine.nim:33-36)
+// reference solver layout S[o][j][s]   (sgd.nim:92-96)
+// device layout           D[j][o][s]
+__global__ void permute_model_to_dev(const double *R, double *D, int nO, int k, int64_t dd) {
+  const int64_t total = (int64_t)nO * k * dd;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(e % k);
+    const int64_t t = e / k;
+    const int o = (int)(t % nO);
+    const int64_t j = t / nO;
+    D[e] = R[((int64_t)o * k + s) * dd + j];
+  }
+}
+__global__ void permute_dev_to_model(const double *D, double *R, int nO, int k, int64_t dd) {
+  const int64_t total = (int64_t)nO * k * dd;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = e % dd;
+    const int64_t t = e / dd;
+    const int s = (int)(t % k);
+    const int o = (int)(t / k);
+    R[e] = D[(j * nO + o) * k + s];
+  }
+}
+__global__ void permute_solver_dev(const double *S, double *D, int nO, int k, int64_t dd, int toDev) {
+  const int64_t total = (int64_t)nO * k * dd;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(e % k);
+    const int64_t t = e / k;
+    const int o = (int)(t % nO);
+    const int64_t j = t / nO;
+    const int64_t se = ((int64_t)o * dd + j) * k + s;
+    if (toDev) D[e] = S[se];
+    else const_cast<double *>(S)[se] = D[e];
+  }
+}
+
+static inline int ew_grid(nimfm_ctx *ctx, int64_t n, int block = 256) {
+  int64_t g = (n + block - 1) / block;
+  int64_t cap = (int64_t)ctx->numSMs * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ------------------------------------------------------------------ small reductions
+// sums partials[nRows4][4] column-wise in a fixed order; out[c] (+)= sum
+__global__ void reduce_partials_kernel(const double *partials, int64_t rows, double *out, int accumulate) {
+  __shared__ double red[8];
+  double acc[4] = {0, 0, 0, 0};
+  for (int64_t r = threadIdx.x; r < rows; r += blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) acc[c] += partials[r * 4 + c];
+  }
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    double v = block_sum(acc[c], red);
+    if (threadIdx.x == 0) out[c] = accumulate ? out[c] + v : v;
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ MBPSGD dense step (K3)
+// Params.step (params.nim:90-98) = add (:33-48) then scale (:61-66), the prox of
+// minibatch_psgd.nim:119-121, and "grads <- 0" (:99) for the next minibatch, in one pass.
+// tail = [gb, lossSum] (already all-reduced).  scal[0] accumulates the epoch's loss sum.
+__global__ void mbpsgd_step_kernel(double *P, double *gP, int64_t nP, double negEtaP, double rP, int reg,
+                                   double lam, double *w, double *gw, int64_t d, double negEtaW, double rW,
+                                   int fitLinear, double *b, double *tail, double negEtaB, double rB,
+                                   int fitIntercept, double *scal) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (int64_t e = tid; e < nP; e += stride) {
+    double p = P[e] + negEtaP * gP[e];
+    p *= rP;
+    if (reg == NIMFM_REG_L1) {  // softthreshold, regularizer/utils.nim:4-5
+      const double m = fabs(p) - lam;
+      p = (p > 0 ? 1.0 : (p < 0 ? -1.0 : 0.0)) * (m > 0.0 ? m : 0.0);
+    }
+    P[e] = p;
+    gP[e] = 0.0;
+  }
+  if (fitLinear)
+    for (int64_t e = tid; e < d; e += stride) {
+      double v = w[e] + negEtaW * gw[e];
+      w[e] = v * rW;
+      gw[e] = 0.0;
+    }
+  else
+    for (int64_t e = tid; e < d; e += stride) gw[e] = 0.0;
+  if (tid == 0) {
+    double bb = b[0];
+    if (fitIntercept && fitLinear) bb += negEtaB * tail[0];  // params.nim:47 (quirk: needs grad.fitLinear)
+    if (fitIntercept) bb *= rB;                              // params.nim:65-66
+    b[0] = bb;
+    scal[0] += tail[1];
+    tail[0] = 0.0;
+    tail[1] = 0.0;
+  }
+}
+
+// ------------------------------------------------------------------ AdaGrad dense kernels (K5)
+// after a minibatch: refresh P/w for touched features from the OLD state (adagrad.nim:87-110),
+// then g_sum += dGs, g_norm += dGn, and clear the deltas.
+__global__ void adagrad_apply_kernel(double *P, double *gsP, double *gnP, double *dGsP, double *dGnP,
+                                     int64_t dd, int SB8, const double *touched, double *w, double *gsw,
+                                     double *gnw, double *dGsw, double *dGnw, int64_t d, int fitLinear,
+                                     double eta0, double tIt, double alpha, double beta, int first) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t nP = dd * SB8;
+  const double tmpP = eta0 * tIt * beta;
+  for (int64_t e = tid; e < nP; e += stride) {
+    const int64_t j = e / SB8;
+    const double gs = gsP[e], gn = gnP[e];
+    if (!first && touched[j] != 0.0) P[e] = -(eta0 * gs) / (tmpP + sqrt(gn));
+    gsP[e] = gs + dGsP[e];
+    gnP[e] = gn + dGnP[e];
+    dGsP[e] = 0.0;
+    dGnP[e] = 0.0;
+  }
+  const double denW = tIt * eta0 * alpha;
+  for (int64_t j = tid; j < d; j += stride) {
+    const double gs = gsw[j], gn = gnw[j];
+    if (fitLinear) {
+      if (!first && touched[j] != 0.0) w[j] = -eta0 * gs / (denW + sqrt(gn));
+      gsw[j] = gs + dGsw[j];
+      gnw[j] = gn + dGnw[j];
+    }
+    dGsw[j] = 0.0;
+    dGnw[j] = 0.0;
+  }
+}
+// intercept part of update()/updateG() (adagrad.nim:101-105,126-128) + epoch accumulators.
+// part = [loss, sum dL, sum dL^2, viol] of the batch (all-reduced); scal = [lossEpoch, violEpoch]
+__global__ void adagrad_scalar_kernel(double *b, double *adaScal, const double *part, double *scal,
+                                      int fitIntercept, double eta0, double tIt, double alpha0, int first) {
+  double viol = part[3];
+  if (fitIntercept) {
+    if (!first) {
+      const double old = b[0];
+      const double den = sqrt(adaScal[1]) + eta0 * tIt * alpha0;
+      const double nb = -eta0 * adaScal[0] / den;
+      viol += fabs(old - nb);
+      b[0] = nb;
+    }
+    adaScal[0] += part[1];
+    adaScal[1] += part[2];
+  }
+  scal[0] += part[0];
+  scal[1] += viol;
+}
+// AdaGrad.finalize (adagrad.nim:65-84)
+__global__ void adagrad_finalize_kernel(double *P, const double *gsP, const double *gnP, int64_t nP, double *w,
+                                        const double *gsw, const double *gnw, int64_t d, int fitLinear,
+                                        double *b, const double *adaScal, int fitIntercept, double eta0,
+                                        double tIt, double alpha0, double alpha, double beta) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const double denP = eta0 * tIt * beta;
+  for (int64_t e = tid; e < nP; e += stride) P[e] = (-eta0 * gsP[e]) / (denP + sqrt(gnP[e]));
+  if (fitLinear) {
+    const double denW = eta0 * tIt * alpha;
+    for (int64_t j = tid; j < d; j += stride) w[j] = (-eta0 * gsw[j]) / (denW + sqrt(gnw[j]));
+  }
+  if (tid == 0 && fitIntercept) {
+    const double den = sqrt(adaScal[1]) + eta0 * tIt * alpha0;
+    b[0] = -eta0 * adaScal[0] / den;
+  }
+}
+__global__ void fill_kernel(double *p, int64_t n, double v) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) p[e] = v;
+}
+
+// ------------------------------------------------------------------ launch planning
+struct RowPlan {
+  int G, CH, block, grid;
+  size_t smem;
+  int64_t nWarps;
+};
+
+static int plan_rows(nimfm_ctx *ctx, const nimfm_fm *fm, const nimfm_dataset *X, int64_t nRows,
+                     RowKernel kern, RowPlan *pl) {
+  const int k = fm->k;
+  const int G = k <= 8 ? 8 : (k <= 16 ? 16 : 32);
+  const int gpw = 32 / G;
+  const int SB8 = fm->nOrders * k;
+  const size_t perNnz = (size_t)SB8 * 8 + 12;
+  int64_t z = X->maxSegNnz + fm->nAug;
+  if (z < 1) z = 1;
+  const size_t capPerGroup = 40 * 1024;
+  int64_t CH = std::min<int64_t>(z, (int64_t)(capPerGroup / perNnz));
+  if (CH < 1) return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "nOrders*nComponents=%d too large for the device row kernel", SB8);
+  const size_t perGroup = (((size_t)CH * perNnz) + 15) & ~(size_t)15;
+  int bestBlock = 0, bestOcc = 0, bestWarps = -1;
+  for (int block : {256, 128, 64, 32}) {
+    const size_t smem = (size_t)(block / 32) * gpw * perGroup;
+    if (smem > (size_t)ctx->smemOptin) continue;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem));
+    const int warps = occ * block / 32;
+    if (warps > bestWarps) {
+      bestWarps = warps;
+      bestBlock = block;
+      bestOcc = occ;
+    }
+  }
+  if (bestBlock == 0 || bestOcc == 0)
+    return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "row kernel does not fit on an SM (perGroup=%zu B)", perGroup);
+  pl->G = G;
+  pl->CH = (int)CH;
+  pl->block = bestBlock;
+  pl->smem = (size_t)(bestBlock / 32) * gpw * perGroup;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+  const int64_t tiles = (nRows + gpw - 1) / gpw;
+  const int warpsPerBlock = bestBlock / 32;
+  int64_t grid = (tiles + warpsPerBlock - 1) / warpsPerBlock;
+  const int64_t cap = (int64_t)bestOcc * ctx->numSMs;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  pl->grid = (int)grid;
+  pl->nWarps = grid * warpsPerBlock;
+  return NIMFM_OK;
+}
+
+static int check_fm_ds(nimfm_ctx *ctx, const nimfm_fm *fm, const nimfm_dataset *X, bool needY) {
+  REQUIRE(fm && X, "NULL handle");
+  REQUIRE(X->kind == NIMFM_DS_CSR || X->kind == NIMFM_DS_CSR_FIELD, "a CSR dataset is required");
+  REQUIRE(X->d == fm->d, "Invalid nFeatures. (dataset %lld, model %lld)", (long long)X->d, (long long)fm->d);
+  REQUIRE(!needY || X->y != nullptr, "dataset has no targets (nimfm_dataset_set_targets)");
+  return NIMFM_OK;
+}
+
+static void fill_row_args(RowArgs &a, const nimfm_fm *fm, const nimfm_dataset *X) {
+  memset(&a, 0, sizeof(a));
+  a.data = X->data;
+  a.indices = X->indices;
+  a.indptr = X->indptr;
+  a.y = X->y;
+  a.n = X->n;
+  a.k = fm->k;
+  a.nAug = fm->nAug;
+  a.d = fm->d;
+  a.P = fm->P;
+  a.w = fm->w;
+  a.b = fm->b;
+  a.lams = fm->lamsAreOnes ? nullptr : fm->lams;
+  a.fitLinear = fm->fitLinear;
+  a.fitIntercept = fm->fitIntercept;
+  a.mb = 1.0;
+}
+
+static bool is_explicit(const nimfm_fm *fm) { return fm->degree > 2 && fm->nOrders == fm->degree - 1; }
+
+extern "C" {
+
+// ================================================================== model state
+int32_t nimfm_fm_create(nimfm_ctx *ctx, int32_t degree, int32_t nComponents, int32_t nOrders,
+                        int32_t nAugments, int64_t nFeatures, int32_t fitLinear, int32_t fitIntercept,
+                        nimfm_fm **out) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  REQUIRE(out != nullptr, "out is NULL");
+  REQUIRE(degree >= 2, "degree < 2 has no ANOVA term; not supported on the device path");
+  if (degree > NIMFM_MAX_DEGREE)
+    return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "degree %d > %d not instantiated", degree, NIMFM_MAX_DEGREE);
+  REQUIRE(nComponents >= 1, "nComponents < 1.");
+  REQUIRE(nOrders == 1 || nOrders == degree - 1, "nOrders must be 1 or degree-1 (factorization_machine.nim:89-97)");
+  REQUIRE(nAugments >= 0 && nAugments < degree, "bad nAugments");
+  REQUIRE(nFeatures >= 1, "nFeatures < 1");
+  CK(cudaSetDevice(ctx->device));
+  nimfm_fm *fm = new nimfm_fm();
+  fm->degree = degree;
+  fm->k = nComponents;
+  fm->nOrders = nOrders;
+  fm->nAug = nAugments;
+  fm->d = nFeatures;
+  fm->fitLinear = fitLinear != 0;
+  fm->fitIntercept = fitIntercept != 0;
+  const int64_t nP = fm->nP(), d = fm->d;
+  CK(cudaMalloc(&fm->P, (size_t)nP * 8));
+  CK(cudaMalloc(&fm->w, (size_t)d * 8));
+  CK(cudaMalloc(&fm->lams, (size_t)fm->k * 8));
+  CK(cudaMalloc(&fm->b, 8 * 8));
+  CK(cudaMalloc(&fm->grad, (size_t)(nP + d + 2) * 8));
+  CK(cudaMemsetAsync(fm->P, 0, (size_t)nP * 8, ctx->stream));
+  CK(cudaMemsetAsync(fm->w, 0, (size_t)d * 8, ctx->stream));
+  CK(cudaMemsetAsync(fm->b, 0, 8 * 8, ctx->stream));
+  CK(cudaMemsetAsync(fm->grad, 0, (size_t)(nP + d + 2) * 8, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *out = fm;
+  return NIMFM_OK;
+}
+
+int32_t nimfm_fm_free(nimfm_ctx *ctx, nimfm_fm *fm) {
+  if (!fm) return NIMFM_OK;
+  if (ctx) cudaSetDevice(ctx->device);
+  for (double *p : {fm->P, fm->w, fm->lams, fm->b, fm->grad, fm->gsP, fm->gnP, fm->gsw, fm->gnw, fm->dG,
+                    fm->adaScal, fm->scalingsP, fm->scalingsW, fm->sgdScal, fm->Pcm, fm->yPred, fm->Acache,
+                    fm->colNormSq, fm->cdScal})
+    cudaFree(p);
+  delete fm;
+  return NIMFM_OK;
+}
+
+int32_t nimfm_fm_set_params(nimfm_ctx *ctx, nimfm_fm *fm, const double *P, const double *w, double intercept,
+                            const double *lams) {
+  if (!ctx || !fm) return NIMFM_ERR_INVALID;
+  REQUIRE(P != nullptr && w != nullptr, "P / w are NULL");
+  CK(cudaSetDevice(ctx->device));
+  const int64_t nP = fm->nP();
+  double *tmp = nullptr;
+  CK(cudaMalloc(&tmp, (size_t)nP * 8));
+  CK(cudaMemcpyAsync(tmp, P, (size_t)nP * 8, cudaMemcpyHostToDevice, ctx->stream));
+  permute_model_to_dev<<<ew_grid(ctx, nP), 256, 0, ctx->stream>>>(tmp, fm->P, fm->nOrders, fm->k, fm->dd());
+  LAUNCHED(ctx);
+  CK(cudaMemcpyAsync(fm->w, w, (size_t)fm->d * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(fm->b, &intercept, 8, cudaMemcpyHostToDevice, ctx->stream));
+  fm->lamsAreOnes = true;
+  if (lams) {
+    for (int s = 0; s < fm->k; s++)
+      if (lams[s] != 1.0) fm->lamsAreOnes = false;
+    CK(cudaMemcpyAsync(fm->lams, lams, (size_t)fm->k * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaFree(tmp));
+  CK(cudaGetLastError());
+  return NIMFM_OK;
+}
+
+static int get_permuted(nimfm_ctx *ctx, nimfm_fm *fm, const double *dev, double *host) {
+  const int64_t nP = fm->nP();
+  double *tmp = nullptr;
+  CK(cudaMalloc(&tmp, (size_t)nP * 8));
+  permute_dev_to_model<<<ew_grid(ctx, nP), 256, 0, ctx->stream>>>(dev, tmp, fm->nOrders, fm->k, fm->dd());
+  LAUNCHED(ctx);
+  CK(cudaMemcpyAsync(host, tmp, (size_t)nP * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaFree(tmp));
+  CK(cudaGetLastError());
+  return NIMFM_OK;
+}
+
+int32_t nimfm_fm_get_params(nimfm_ctx *ctx, nimfm_fm *fm, double *P, double *w, double *intercept) {
+  if (!ctx || !fm) return NIMFM_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  if (P) {
+    int rc = get_permuted(ctx, fm, fm->P, P);
+    if (rc) return rc;
+  }
+  if (w) CK(cudaMemcpy(w, fm->w, (size_t)fm->d * 8, cudaMemcpyDeviceToHost));
+  if (intercept) CK(cudaMemcpy(intercept, fm->b, 8, cudaMemcpyDeviceToHost));
+  return NIMFM_OK;
+}
+
+int32_t nimfm_fm_get_grads(nimfm_ctx *ctx, nimfm_fm *fm, double *gP, double *gw, double *gb) {
+  if (!ctx || !fm) return NIMFM_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  const int64_t nP = fm->nP();
+  if (gP) {
+    int rc = get_permuted(ctx, fm, fm->grad, gP);
+    if (rc) return rc;
+  }
+  if (gw) CK(cudaMemcpy(gw, fm->grad + nP, (size_t)fm->d * 8, cudaMemcpyDeviceToHost));
+  if (gb) CK(cudaMemcpy(gb, fm->grad + nP + fm->d, 8, cudaMemcpyDeviceToHost));
+  return NIMFM_OK;
+}
+
+int32_t nimfm_fm_grad_device_ptr(nimfm_fm *fm, void **ptr, int64_t *nDoubles) {
+  if (!fm || !ptr) return NIMFM_ERR_INVALID;
+  *ptr = fm->grad;
+  if (nDoubles) *nDoubles = fm->nP() + fm->d + 2;
+  return NIMFM_OK;
+}
+
+// ================================================================== K1: decisionFunction
+int32_t nimfm_fm_decision_function(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, double *out) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  REQUIRE(fm && X && out, "NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  nimfm_dataset *twin = nullptr;
+  const nimfm_dataset *Xr = X;
+  if (X->kind == NIMFM_DS_CSC) {
+    // The ColDataset kernels (kernels.nim:4-11,22-43) visit columns in ascending order, which is the
+    // order a CSR row with sorted indices is visited in; run the row kernel on the stable transpose.
+    int rc = nimfm_dataset_transpose(ctx, X, &twin);
+    if (rc) return rc;
+    Xr = twin;
+  }
+  int rc = check_fm_ds(ctx, fm, Xr, false);
+  if (rc) { nimfm_dataset_free(ctx, twin); return rc; }
+  const int64_t n = Xr->n;
+  if (n == 0) { nimfm_dataset_free(ctx, twin); return NIMFM_OK; }
+  RowKernel kern = nimfm_row_kernel_predict(fm->degree, is_explicit(fm));
+  RowPlan pl;
+  if ((rc = plan_rows(ctx, fm, Xr, n, kern, &pl))) { nimfm_dataset_free(ctx, twin); return rc; }
+  double *dOut = nullptr;
+  CK(cudaMalloc(&dOut, (size_t)n * 8));
+  RowArgs a;
+  fill_row_args(a, fm, Xr);
+  a.rowBegin = 0;
+  a.nRows = n;
+  a.yOut = dOut;
+  a.G = pl.G;
+  a.CH = pl.CH;
+  kern<<<pl.grid, pl.block, pl.smem, ctx->stream>>>(a);
+  LAUNCHED(ctx);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, dOut, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaFree(dOut));
+  nimfm_dataset_free(ctx, twin);
+  return NIMFM_OK;
+}
+
+// ================================================================== K2: predict + grad
+static int launch_loss_grad(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, int loss, double thr,
+                            int64_t rowBegin, int64_t nRows, const int32_t *rowIdxDev, double mb,
+                            double *yOutDev) {
+  RowKernel kern = nimfm_row_kernel_grad(fm->degree, is_explicit(fm));
+  RowPlan pl;
+  int rc = plan_rows(ctx, fm, X, nRows, kern, &pl);
+  if (rc) return rc;
+  if ((rc = nimfm_ensure_partials(ctx, (size_t)pl.nWarps * 4))) return rc;
+  RowArgs a;
+  fill_row_args(a, fm, X);
+  a.rowBegin = rowBegin;
+  a.nRows = nRows;
+  a.rowIdx = rowIdxDev;
+  a.yOut = yOutDev;
+  a.gP = fm->grad;
+  a.gw = fm->grad + fm->nP();
+  a.partials = ctx->partials;
+  a.loss = loss;
+  a.thr = thr;
+  a.mb = mb;
+  a.G = pl.G;
+  a.CH = pl.CH;
+  kern<<<pl.grid, pl.block, pl.smem, ctx->stream>>>(a);
+  LAUNCHED(ctx);
+  // tail += [sum coef, sum loss]: partial columns are (loss, coef, dL^2, viol) -> reorder via scratch
+  reduce_partials_kernel<<<1, 256, 0, ctx->stream>>>(ctx->partials, pl.nWarps, ctx->scalars + 8, 0);
+  LAUNCHED(ctx);
+  return NIMFM_OK;
+}
+
+__global__ void add_tail_kernel(double *tail, const double *red4) {
+  tail[0] += red4[1];  // gb  += sum coef
+  tail[1] += red4[0];  // loss
+}
+
+int32_t nimfm_fm_loss_grad(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, int32_t loss,
+                           double huberThreshold, int64_t rowBegin, int64_t nRows, const int64_t *rowIdx,
+                           int64_t miniBatchSize, int32_t zeroGrads, int32_t allreduce, double *lossSum) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  int rc = check_fm_ds(ctx, fm, X, true);
+  if (rc) return rc;
+  REQUIRE(nRows >= 0 && miniBatchSize >= 1, "bad nRows / miniBatchSize");
+  REQUIRE(rowIdx != nullptr || (rowBegin >= 0 && (rowBegin < X->n || nRows == 0)), "rowBegin out of range");
+  const int64_t nG = fm->nP() + fm->d + 2;
+  if (zeroGrads) CK(cudaMemsetAsync(fm->grad, 0, (size_t)nG * 8, ctx->stream));
+  const int32_t *idxDev = nullptr;
+  if (rowIdx && nRows > 0) {
+    if ((rc = nimfm_stage_row_ids(ctx, rowIdx, nRows, X->n))) return rc;
+    idxDev = ctx->idx32Scratch;
+  }
+  if (nRows > 0) {
+    if ((rc = launch_loss_grad(ctx, fm, X, loss, huberThreshold, rowBegin, nRows, idxDev, (double)miniBatchSize, nullptr)))
+      return rc;
+    add_tail_kernel<<<1, 1, 0, ctx->stream>>>(fm->grad + nG - 2, ctx->scalars + 8);
+    LAUNCHED(ctx);
+  }
+  if (allreduce && (rc = nimfm_allreduce_sum(ctx, fm->grad, nG))) return rc;
+  CK(cudaGetLastError());
+  if (lossSum) CK(cudaMemcpyAsync(lossSum, fm->grad + nG - 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return NIMFM_OK;
+}
+
+int32_t nimfm_fm_time_loss_grad(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, int32_t loss,
+                                int64_t nRows, int64_t miniBatchSize, int32_t reps, int32_t gradToo,
+                                float *msPerLaunch) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  int rc = check_fm_ds(ctx, fm, X, gradToo != 0);
+  if (rc) return rc;
+  REQUIRE(reps >= 1 && nRows >= 1 && msPerLaunch, "bad arguments");
+  RowKernel kern = gradToo ? nimfm_row_kernel_grad(fm->degree, is_explicit(fm))
+                           : nimfm_row_kernel_predict(fm->degree, is_explicit(fm));
+  RowPlan pl;
+  if ((rc = plan_rows(ctx, fm, X, nRows, kern, &pl))) return rc;
+  if ((rc = nimfm_ensure_partials(ctx, (size_t)pl.nWarps * 4))) return rc;
+  double *dOut = nullptr;
+  if (!gradToo) CK(cudaMalloc(&dOut, (size_t)nRows * 8));
+  RowArgs a;
+  fill_row_args(a, fm, X);
+  a.nRows = nRows;
+  a.yOut = dOut;
+  a.gP = fm->grad;
+  a.gw = fm->grad + fm->nP();
+  a.partials = ctx->partials;
+  a.loss = loss;
+  a.thr = 1.0;
+  a.mb = (double)miniBatchSize;
+  a.G = pl.G;
+  a.CH = pl.CH;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  for (int r = 0; r < reps; r++) {
+    kern<<<pl.grid, pl.block, pl.smem, ctx->stream>>>(a);
+    LAUNCHED(ctx);
+  }
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaEventSynchronize(ctx->ev1));
+  CK(cudaGetLastError());
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  *msPerLaunch = ms / reps;
+  if (dOut) CK(cudaFree(dOut));
+  return NIMFM_OK;
+}
+
+// ================================================================== MBPSGD epoch (minibatch_psgd.nim:91-124)
+static double get_eta(int sched, double eta0, double power, double reg, int64_t it) {  // sgd.nim:60-69
+  switch (sched) {
+    case NIMFM_SCHED_CONSTANT: return eta0;
+    case NIMFM_SCHED_OPTIMAL: return eta0 / pow(1.0 + eta0 * reg * (double)it, power);
+    case NIMFM_SCHED_INVSCALING: return eta0 / pow((double)it, power);
+    default: return 1.0 / (reg * (double)it);
+  }
+}
+
+int32_t nimfm_fm_mbpsgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, const nimfm_mbpsgd_cfg *cfg,
+                              int64_t localBatch, int64_t *it, int64_t *ii, const int64_t *sampleIdx,
+                              double *runningLoss) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  int rc = check_fm_ds(ctx, fm, X, true);
+  if (rc) return rc;
+  REQUIRE(cfg && it && ii, "NULL argument");
+  REQUIRE(cfg->miniBatchSize >= 1 && cfg->maxIterInner >= 1, "miniBatchSize / maxIterInner must be resolved (>= 1)");
+  REQUIRE(cfg->reg == NIMFM_REG_IDENTITY || cfg->reg == NIMFM_REG_L1, "unsupported regulariser");
+  if (localBatch <= 0) localBatch = cfg->miniBatchSize;
+  REQUIRE(X->n > 0, "empty dataset");
+  const int64_t nP = fm->nP(), d = fm->d, nG = nP + d + 2;
+  const int64_t total = localBatch * cfg->maxIterInner;
+  const int32_t *idxDev = nullptr;
+  if (sampleIdx) {
+    if ((rc = nimfm_stage_row_ids(ctx, sampleIdx, total, X->n))) return rc;
+    idxDev = ctx->idx32Scratch;
+  }
+  CK(cudaMemsetAsync(fm->grad, 0, (size_t)nG * 8, ctx->stream));       // grads <- 0 (:99)
+  CK(cudaMemsetAsync(ctx->scalars, 0, 8, ctx->stream));
+  int64_t cur = *ii;
+  for (int64_t inner = 0; inner < cfg->maxIterInner; inner++) {
+    if ((rc = launch_loss_grad(ctx, fm, X, cfg->loss, cfg->huberThreshold, cur, localBatch,
+                               idxDev ? idxDev + inner * localBatch : nullptr, (double)cfg->miniBatchSize, nullptr)))
+      return rc;
+    add_tail_kernel<<<1, 1, 0, ctx->stream>>>(fm->grad + nG - 2, ctx->scalars + 8);
+    LAUNCHED(ctx);
+    if ((rc = nimfm_allreduce_sum(ctx, fm->grad, nG))) return rc;
+    const double etaP = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->beta, *it);     // :114-116
+    const double etaW = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->alpha, *it);
+    const double etaB = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->alpha0, *it);
+    const double rP = 1.0 / (1.0 + etaP * cfg->beta), rW = 1.0 / (1.0 + etaW * cfg->alpha),
+                 rB = 1.0 / (1.0 + etaB * cfg->alpha0);
+    const double lam = cfg->gamma * etaP / (1.0 + etaP * cfg->beta);                         // :119-121
+    mbpsgd_step_kernel<<<ew_grid(ctx, nP), 256, 0, ctx->stream>>>(
+        fm->P, fm->grad, nP, -etaP, rP, cfg->reg, lam, fm->w, fm->grad + nP, d, -etaW, rW, fm->fitLinear, fm->b,
+        fm->grad + nG - 2, -etaB, rB, fm->fitIntercept, ctx->scalars);
+    LAUNCHED(ctx);
+    *it += 1;
+    cur = (cur + localBatch) % X->n;
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctx->hostScalars, ctx->scalars, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *ii = cur;
+  // runningLoss / (miniBatchSize*maxIterInner) (:124); the loss sum was all-reduced with the gradient
+  if (runningLoss) *runningLoss = ctx->hostScalars[0] / (double)(cfg->miniBatchSize * cfg->maxIterInner);
+  return NIMFM_OK;
+}
+
+// ================================================================== AdaGrad (adagrad.nim)
+int32_t nimfm_fm_adagrad_init(nimfm_ctx *ctx, nimfm_fm *fm, double eps, int32_t reset) {
+  if (!ctx || !fm) return NIMFM_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  const int64_t nP = fm->nP(), d = fm->d, dd = fm->dd();
+  const bool fresh = !fm->gsP;
+  if (fresh) {
+    CK(cudaMalloc(&fm->gsP, (size_t)nP * 8));
+    CK(cudaMalloc(&fm->gnP, (size_t)nP * 8));
+    CK(cudaMalloc(&fm->gsw, (size_t)d * 8));
+    CK(cudaMalloc(&fm->gnw, (size_t)d * 8));
+    CK(cudaMalloc(&fm->dG, (size_t)(2 * nP + 2 * d + dd + 4) * 8));
+    CK(cudaMalloc(&fm->adaScal, 8 * 8));
+  }
+  if (fresh || reset) {   // AdaGrad.init, :47-55
+    CK(cudaMemsetAsync(fm->gsP, 0, (size_t)nP * 8, ctx->stream));
+    CK(cudaMemsetAsync(fm->gsw, 0, (size_t)d * 8, ctx->stream));
+    fill_kernel<<<ew_grid(ctx, nP), 256, 0, ctx->stream>>>(fm->gnP, nP, eps);
+    fill_kernel<<<ew_grid(ctx, d), 256, 0, ctx->stream>>>(fm->gnw, d, eps);
+    ctx->launches += 2;
+    const double sc[2] = {0.0, eps};
+    CK(cudaMemcpyAsync(fm->adaScal, sc, 16, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CK(cudaMemsetAsync(fm->dG, 0, (size_t)(2 * nP + 2 * d + dd + 4) * 8, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  fm->adaReady = true;
+  return NIMFM_OK;
+}
+
+int32_t nimfm_fm_adagrad_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, const nimfm_adagrad_cfg *cfg,
+                               int64_t *it, const int64_t *perm, int64_t nRows, double *viol, double *lossSum) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  int rc = check_fm_ds(ctx, fm, X, true);
+  if (rc) return rc;
+  REQUIRE(cfg && it, "NULL argument");
+  if (!fm->adaReady) return nimfm_fail(ctx, NIMFM_ERR_STATE, "nimfm_fm_adagrad_init was not called");
+  REQUIRE(cfg->miniBatchSize >= 1, "miniBatchSize < 1");
+  REQUIRE(nRows >= 0 && (perm != nullptr || nRows <= X->n), "bad nRows");
+  const int64_t nP = fm->nP(), d = fm->d, dd = fm->dd();
+  const int32_t *idxDev = nullptr;
+  if (perm && nRows > 0) {
+    if ((rc = nimfm_stage_row_ids(ctx, perm, nRows, X->n))) return rc;
+    idxDev = ctx->idx32Scratch;
+  }
+  RowKernel kern = nimfm_row_kernel_adagrad(fm->degree, is_explicit(fm));
+  CK(cudaMemsetAsync(ctx->scalars, 0, 16, ctx->stream));
+  double *dGsP = fm->dG, *dGnP = fm->dG + nP, *dGsw = fm->dG + 2 * nP, *dGnw = fm->dG + 2 * nP + d;
+  double *touched = fm->dG + 2 * nP + 2 * d;
+  double *part = touched + dd;              // [loss, sum dL, sum dL^2, viol]
+  const int64_t nDelta = 2 * nP + 2 * d + dd + 4;
+  const int64_t mb = cfg->miniBatchSize;
+  for (int64_t start = 0; start < nRows; start += mb) {
+    const int64_t cnt = std::min<int64_t>(mb, nRows - start);
+    RowPlan pl;
+    if ((rc = plan_rows(ctx, fm, X, cnt, kern, &pl))) return rc;
+    if ((rc = nimfm_ensure_partials(ctx, (size_t)pl.nWarps * 4))) return rc;
+    RowArgs a;
+    fill_row_args(a, fm, X);
+    a.rowBegin = start;
+    a.nRows = cnt;
+    a.rowIdx = idxDev ? idxDev + start : nullptr;
+    a.gP = dGsP;
+    a.gw = dGsw;
+    a.dGnP = dGnP;
+    a.dGnw = dGnw;
+    a.partials = ctx->partials;
+    a.loss = cfg->loss;
+    a.thr = cfg->huberThreshold;
+    a.gsP = fm->gsP; a.gnP = fm->gnP; a.gsw = fm->gsw; a.gnw = fm->gnw; a.adaScal = fm->adaScal;
+    a.touched = touched;
+    a.eta0 = cfg->eta0; a.tIt = (double)(*it - 1); a.alpha0 = cfg->alpha0; a.alpha = cfg->alpha; a.beta = cfg->beta;
+    a.first = (*it == 1);
+    a.G = pl.G;
+    a.CH = pl.CH;
+    kern<<<pl.grid, pl.block, pl.smem, ctx->stream>>>(a);
+    LAUNCHED(ctx);
+    reduce_partials_kernel<<<1, 256, 0, ctx->stream>>>(ctx->partials, pl.nWarps, part, 0);
+    LAUNCHED(ctx);
+    // synchronous data parallelism: all-reduce the deltas [dGs | dGn | dGsw | dGnw | loss, dL, dL^2, viol]
+    if ((rc = nimfm_allreduce_sum(ctx, fm->dG, nDelta))) return rc;
+    adagrad_scalar_kernel<<<1, 1, 0, ctx->stream>>>(fm->b, fm->adaScal, part, ctx->scalars, fm->fitIntercept, cfg->eta0,
+                                                    a.tIt, cfg->alpha0, a.first);
+    LAUNCHED(ctx);
+    adagrad_apply_kernel<<<ew_grid(ctx, nP), 256, 0, ctx->stream>>>(
+        fm->P, fm->gsP, fm->gnP, dGsP, dGnP, dd, fm->nOrders * fm->k, touched, fm->w, fm->gsw, fm->gnw, dGsw, dGnw,
+        d, fm->fitLinear, cfg->eta0, a.tIt, cfg->alpha, cfg->beta, a.first);
+    LAUNCHED(ctx);
+    fill_kernel<<<ew_grid(ctx, dd), 256, 0, ctx->stream>>>(touched, dd, 0.0);
+    LAUNCHED(ctx);
+    *it += cnt * (int64_t)ctx->nranks;
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctx->hostScalars, ctx->scalars, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (lossSum) *lossSum = ctx->hostScalars[0];
+  if (viol) *viol = ctx->hostScalars[1];
+  return NIMFM_OK;
+}
+
+int32_t nimfm_fm_adagrad_finalize(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_adagrad_cfg *cfg, int64_t it) {
+  if (!ctx || !fm || !cfg) return NIMFM_ERR_INVALID;
+  if (!fm->adaReady) return nimfm_fail(ctx, NIMFM_ERR_STATE, "nimfm_fm_adagrad_init was not called");
+  CK(cudaSetDevice(ctx->device));
+  adagrad_finalize_kernel<<<ew_grid(ctx, fm->nP()), 256, 0, ctx->stream>>>(
+      fm->P, fm->gsP, fm->gnP, fm->nP(), fm->w, fm->gsw, fm->gnw, fm->d, fm->fitLinear, fm->b, fm->adaScal,
+      fm->fitIntercept, cfg->eta0, (double)(it - 1), cfg->alpha0, cfg->alpha, cfg->beta);
+  LAUNCHED(ctx);
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  return NIMFM_OK;
+}
+
+static int permute_solver(nimfm_ctx *ctx, nimfm_fm *fm, double *hostSolver, double *dev, int toDev) {
+  const int64_t nP = fm->nP();
+  double *tmp = nullptr;
+  CK(cudaMalloc(&tmp, (size_t)nP * 8));
+  if (toDev) CK(cudaMemcpyAsync(tmp, hostSolver, (size_t)nP * 8, cudaMemcpyHostToDevice, ctx->stream));
+  permute_solver_dev<<<ew_grid(ctx, nP), 256, 0, ctx->stream>>>(tmp, dev, fm->nOrders, fm->k, fm->dd(), toDev);
+  LAUNCHED(ctx);
+  if (!toDev) CK(cudaMemcpyAsync(hostSolver, tmp, (size_t)nP * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaFree(tmp));
+  CK(cudaGetLastError());
+  return NIMFM_OK;
+}
+
+int32_t nimfm_fm_adagrad_get_state(nimfm_ctx *ctx, nimfm_fm *fm, double *gsP, double *gnP, double *gsw, double *gnw,
+                                   double *gsb, double *gnb) {
+  if (!ctx || !fm) return NIMFM_ERR_INVALID;
+  if (!fm->adaReady) return nimfm_fail(ctx, NIMFM_ERR_STATE, "nimfm_fm_adagrad_init was not called");
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if (gsP && (rc = permute_solver(ctx, fm, gsP, fm->gsP, 0))) return rc;
+  if (gnP && (rc = permute_solver(ctx, fm, gnP, fm->gnP, 0))) return rc;
+  if (gsw) CK(cudaMemcpy(gsw, fm->gsw, (size_t)fm->d * 8, cudaMemcpyDeviceToHost));
+  if (gnw) CK(cudaMemcpy(gnw, fm->gnw, (size_t)fm->d * 8, cudaMemcpyDeviceToHost));
+  double sc[2];
+  CK(cudaMemcpy(sc, fm->adaScal, 16, cudaMemcpyDeviceToHost));
+  if (gsb) *gsb = sc[0];
+  if (gnb) *gnb = sc[1];
+  return NIMFM_OK;
+}
+
+int32_t nimfm_fm_adagrad_set_state(nimfm_ctx *ctx, nimfm_fm *fm, const double *gsP, const double *gnP,
+                                   const double *gsw, const double *gnw, double gsb, double gnb) {
+  if (!ctx || !fm) return NIMFM_ERR_INVALID;
+  if (!fm->adaReady) return nimfm_fail(ctx, NIMFM_ERR_STATE, "nimfm_fm_adagrad_init was not called");
+  REQUIRE(gsP && gnP && gsw && gnw, "NULL state array");
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = permute_solver(ctx, fm, const_cast<double *>(gsP), fm->gsP, 1))) return rc;
+  if ((rc = permute_solver(ctx, fm, const_cast<double *>(gnP), fm->gnP, 1))) return rc;
+  CK(cudaMemcpy(fm->gsw, gsw, (size_t)fm->d * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(fm->gnw, gnw, (size_t)fm->d * 8, cudaMemcpyHostToDevice));
+  const double sc[2] = {gsb, gnb};
+  CK(cudaMemcpy(fm->adaScal, sc, 16, cudaMemcpyHostToDevice));
+  return NIMFM_OK;
+}
+
+}  // extern "C"
+
+// ================================================================== K2 fed from host buffers (end-to-end path)
+__global__ void narrow_rebase_kernel(const int64_t *idx64, int32_t *idx32, int64_t nnz, int64_t *indptr,
+                                     int64_t nRowsPlus1, int64_t base, int64_t d, int *bad) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (int64_t q = tid; q < nnz; q += stride) {
+    int64_t v = idx64[q];
+    if (v < 0 || v >= d) { *bad = 1; v = 0; }
+    idx32[q] = (int32_t)v;
+  }
+  for (int64_t r = tid; r < nRowsPlus1; r += stride) indptr[r] -= base;
+}
+
+static int ensure_stage(nimfm_ctx *ctx, nimfm_ctx::Stage &st, size_t rows, size_t nnz) {
+  if (st.capRows < rows) {
+    if (st.y) CK(cudaFree(st.y));
+    if (st.indptr) CK(cudaFree(st.indptr));
+    CK(cudaMalloc(&st.y, rows * 8));
+    CK(cudaMalloc(&st.indptr, (rows + 1) * 8));
+    st.capRows = rows;
+  }
+  if (st.capNnz < nnz) {
+    if (st.data) CK(cudaFree(st.data));
+    if (st.idx64) CK(cudaFree(st.idx64));
+    if (st.idx32) CK(cudaFree(st.idx32));
+    CK(cudaMalloc(&st.data, nnz * 8));
+    CK(cudaMalloc(&st.idx64, nnz * 8));
+    CK(cudaMalloc(&st.idx32, nnz * 4));
+    st.capNnz = nnz;
+  }
+  return NIMFM_OK;
+}
+
+extern "C" int32_t nimfm_fm_loss_grad_host(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t d,
+                                           const double *data, const int64_t *indices, const int64_t *indptr,
+                                           const double *y, int32_t loss, double huberThreshold,
+                                           int64_t miniBatchSize, int64_t chunkRows, int32_t zeroGrads,
+                                           int32_t allreduce, double *lossSum) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  REQUIRE(fm && indptr && y, "NULL argument");
+  REQUIRE(d == fm->d, "Invalid nFeatures. (batch %lld, model %lld)", (long long)d, (long long)fm->d);
+  REQUIRE(nRows >= 0 && miniBatchSize >= 1, "bad nRows / miniBatchSize");
+  if (chunkRows <= 0) chunkRows = 1 << 19;
+  const int64_t nG = fm->nP() + fm->d + 2;
+  if (zeroGrads) CK(cudaMemsetAsync(fm->grad, 0, (size_t)nG * 8, ctx->stream));
+  int *bad = reinterpret_cast<int *>(ctx->scalars + 60);
+  CK(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
+  // size the two staging sets for the largest chunk
+  size_t maxNnz = 1;
+  int64_t maxSeg = 0;
+  for (int64_t r0 = 0; r0 < nRows; r0 += chunkRows) {
+    const int64_t r1 = std::min(nRows, r0 + chunkRows);
+    maxNnz = std::max(maxNnz, (size_t)(indptr[r1] - indptr[r0]));
+  }
+  for (int64_t r = 0; r < nRows; r++) maxSeg = std::max(maxSeg, indptr[r + 1] - indptr[r]);
+  int rc;
+  for (int s = 0; s < 2; s++)
+    if ((rc = ensure_stage(ctx, ctx->stage[s], (size_t)std::min(nRows, chunkRows) + 1, maxNnz))) return rc;
+  int c = 0;
+  for (int64_t r0 = 0; r0 < nRows; r0 += chunkRows, c++) {
+    const int64_t r1 = std::min(nRows, r0 + chunkRows), rows = r1 - r0;
+    const int64_t base = indptr[r0], nnz = indptr[r1] - base;
+    nimfm_ctx::Stage &st = ctx->stage[c & 1];
+    if (c >= 2) CK(cudaStreamWaitEvent(ctx->copyStream, ctx->evComputed[c & 1], 0));   // buffer is free again
+    CK(cudaMemcpyAsync(st.data, data + base, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->copyStream));
+    CK(cudaMemcpyAsync(st.idx64, indices + base, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->copyStream));
+    CK(cudaMemcpyAsync(st.indptr, indptr + r0, (size_t)(rows + 1) * 8, cudaMemcpyHostToDevice, ctx->copyStream));
+    CK(cudaMemcpyAsync(st.y, y + r0, (size_t)rows * 8, cudaMemcpyHostToDevice, ctx->copyStream));
+    CK(cudaEventRecord(ctx->evCopied[c & 1], ctx->copyStream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->evCopied[c & 1], 0));
+    narrow_rebase_kernel<<<ew_grid(ctx, nnz), 256, 0, ctx->stream>>>(st.idx64, st.idx32, nnz, st.indptr, rows + 1,
+                                                                     base, d, bad);
+    LAUNCHED(ctx);
+    nimfm_dataset tmp;
+    tmp.kind = NIMFM_DS_CSR;
+    tmp.n = rows;
+    tmp.d = d;
+    tmp.nnz = nnz;
+    tmp.maxSegNnz = maxSeg;
+    tmp.data = st.data;
+    tmp.indices = st.idx32;
+    tmp.indptr = st.indptr;
+    tmp.y = st.y;
+    if ((rc = launch_loss_grad(ctx, fm, &tmp, loss, huberThreshold, 0, rows, nullptr, (double)miniBatchSize, nullptr)))
+      return rc;
+    add_tail_kernel<<<1, 1, 0, ctx->stream>>>(fm->grad + nG - 2, ctx->scalars + 8);
+    LAUNCHED(ctx);
+    CK(cudaEventRecord(ctx->evComputed[c & 1], ctx->stream));
+  }
+  if (allreduce && (rc = nimfm_allreduce_sum(ctx, fm->grad, nG))) return rc;
+  int hbad = 0;
+  CK(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (lossSum) CK(cudaMemcpyAsync(lossSum, fm->grad + nG - 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaStreamSynchronize(ctx->copyStream));
+  CK(cudaGetLastError());
+  if (hbad) return nimfm_fail(ctx, NIMFM_ERR_INVALID, "column index out of range [0,%lld)", (long long)d);
+  return NIMFM_OK;
+}

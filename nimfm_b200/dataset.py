@@ -1,0 +1,183 @@
+"""Host-side mirror of nimfm's dataset facade (dataset.nim:10-153, 406-427; tensor/sparse.nim:4-31).
+
+A dataset keeps the reference's host representation (f64 data, i64 indices / indptr [/ fields]) and a
+lazily created device twin owned by libnimfm_cuda.so.  Dummy-feature augmentation
+(dataset.nim:91-113) is applied inside the kernels (the model carries nAugments), so the host
+arrays never change.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class BaseDataset:
+    kind = _lib.DS_CSR
+
+    def __init__(self, data, indices, indptr, nSamples, nFeatures, fields=None, nFields=0):
+        self.data = _lib.f64(data)
+        self.indices = _lib.i64(indices)
+        self.indptr = _lib.i64(indptr)
+        self._n, self._d = int(nSamples), int(nFeatures)
+        self.fields = None if fields is None else _lib.i64(fields)
+        self._nFields = int(nFields)
+        self._handle = None
+        self._y_id = None
+        nseg = self._d if self.kind == _lib.DS_CSC else self._n
+        if len(self.indptr) != nseg + 1:
+            raise ValueError("len(indptr) != number of segments + 1")
+        if len(self.data) != len(self.indices) or len(self.data) != int(self.indptr[-1]):
+            raise ValueError("len(data), len(indices) and indptr[^1] disagree")
+
+    # dataset.nim:40-61
+    @property
+    def nSamples(self):
+        return self._n
+
+    @property
+    def nFeatures(self):
+        return self._d
+
+    @property
+    def nFields(self):
+        return self._nFields
+
+    @property
+    def shape(self):
+        return (self._n, self._d)
+
+    @property
+    def nnz(self):
+        return int(len(self.data))
+
+    # ---- device twin
+    def _upload(self):
+        raise NotImplementedError
+
+    def handle(self):
+        if self._handle is None:
+            self._upload()
+        return self._handle
+
+    def set_targets(self, y):
+        y = _lib.f64(y)
+        if len(y) != self._n:
+            raise ValueError("len(y) != nSamples")
+        _lib.check(_lib.load().nimfm_dataset_set_targets(_lib.ctx(), self.handle(), _lib.ptr(y)))
+
+    def info(self):
+        n, d, nnz, nf, mx = (C.c_int64() for _ in range(5))
+        kind = C.c_int32()
+        _lib.check(_lib.load().nimfm_dataset_info(self.handle(), C.byref(n), C.byref(d), C.byref(nnz),
+                                                  C.byref(kind), C.byref(nf), C.byref(mx)))
+        return dict(n=n.value, d=d.value, nnz=nnz.value, kind=kind.value, nFields=nf.value,
+                    maxSegNnz=mx.value)
+
+    def download(self):
+        """Device arrays read back in the reference dtypes (bit-exact bookkeeping checks)."""
+        inf = self.info()
+        nseg = inf["d"] if inf["kind"] == _lib.DS_CSC else inf["n"]
+        data = np.zeros(inf["nnz"])
+        indices = np.zeros(inf["nnz"], np.int64)
+        indptr = np.zeros(nseg + 1, np.int64)
+        fields = np.zeros(inf["nnz"], np.int64) if inf["kind"] == _lib.DS_CSR_FIELD else None
+        _lib.check(_lib.load().nimfm_dataset_download(_lib.ctx(), self.handle(), _lib.ptr(data),
+                                                      _lib.ptr(indices), _lib.ptr(indptr),
+                                                      _lib.ptr(fields)))
+        return data, indices, indptr, fields
+
+    def free(self):
+        if self._handle is not None:
+            _lib.load().nimfm_dataset_free(_lib.ctx(), self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class CSRDataset(BaseDataset):
+    kind = _lib.DS_CSR
+
+    def _upload(self, rowBegin=0, rowEnd=None):
+        h = C.c_void_p()
+        rowEnd = self._n if rowEnd is None else rowEnd
+        _lib.check(_lib.load().nimfm_csr_upload(
+            _lib.ctx(), self._n, self._d, _lib.ptr(self.data), _lib.ptr(self.indices),
+            _lib.ptr(self.indptr), _lib.ptr(self.fields), self._nFields, rowBegin, rowEnd, C.byref(h)))
+        self._handle = h
+
+    def toCSCDataset(self):
+        return toCSCDataset(self)
+
+
+class CSRFieldDataset(CSRDataset):
+    kind = _lib.DS_CSR_FIELD
+
+
+class CSCDataset(BaseDataset):
+    kind = _lib.DS_CSC
+
+    def _upload(self):
+        h = C.c_void_p()
+        _lib.check(_lib.load().nimfm_csc_upload(_lib.ctx(), self._n, self._d, _lib.ptr(self.data),
+                                                _lib.ptr(self.indices), _lib.ptr(self.indptr),
+                                                C.byref(h)))
+        self._handle = h
+
+    def toCSRDataset(self):
+        return toCSRDataset(self)
+
+
+# dataset.nim:116-153
+def newCSRDataset(data, indices, indptr, nSamples, nFeatures):
+    return CSRDataset(data, indices, indptr, nSamples, nFeatures)
+
+
+def newCSCDataset(data, indices, indptr, nSamples, nFeatures):
+    return CSCDataset(data, indices, indptr, nSamples, nFeatures)
+
+
+def newCSRFieldDataset(data, indices, indptr, fields, nSamples, nFeatures, nFields):
+    return CSRFieldDataset(data, indices, indptr, nSamples, nFeatures, fields=fields, nFields=nFields)
+
+
+def _transposed(src, cls):
+    """toCSCDataset / toCSRDataset (dataset.nim:406-427 -> tensor/sparse.nim:490-527): the stable
+    counting-sort transpose performed by the library; the result is read back so the new dataset has
+    host arrays like any other."""
+    h = C.c_void_p()
+    _lib.check(_lib.load().nimfm_dataset_transpose(_lib.ctx(), src.handle(), C.byref(h)))
+    out = cls.__new__(cls)
+    out._n, out._d, out._nFields, out.fields, out._y_id = src._n, src._d, 0, None, None
+    out._handle = h
+    out.data, out.indices, out.indptr, _ = BaseDataset.download(out)
+    return out
+
+
+def toCSCDataset(X):
+    if isinstance(X, CSRDataset):
+        return _transposed(X, CSCDataset)
+    return _from_dense(np.asarray(X, dtype=np.float64), CSCDataset)
+
+
+def toCSRDataset(X):
+    if isinstance(X, CSCDataset):
+        return _transposed(X, CSRDataset)
+    return _from_dense(np.asarray(X, dtype=np.float64), CSRDataset)
+
+
+def _from_dense(X, cls):
+    """toCSRDataset / toCSCDataset from seq[seq[float64]] (dataset.nim:406-415)."""
+    n, d = X.shape
+    M = X.T if cls is CSCDataset else X
+    data, indices, indptr = [], [], [0]
+    for row in M:
+        nz = np.nonzero(row)[0]
+        indices.extend(nz.tolist())
+        data.extend(row[nz].tolist())
+        indptr.append(len(indices))
+    return cls(data, indices, indptr, n, d)

@@ -1,0 +1,409 @@
+"""Host-side mirror of nimfm's solver objects: constructor signatures, fit() control flow (epoch
+loop, verbose printing, callback, tol stopping, NaN check) stay here exactly where the reference has
+them; every epoch body is ONE call into libnimfm_cuda.so.
+
+  CD      optimizer/cd.nim:12-13, 110-194
+  SGD     optimizer/sgd.nim:23-52, 261-328        (FFM: optimizer/sgd_ffm.nim:49-106)
+  AdaGrad optimizer/adagrad.nim:20-44, 137-203    (FFM: optimizer/adagrad_ffm.nim:11-66)
+  MBPSGD  optimizer/minibatch_psgd.nim:25-64, 127-211
+
+Shuffling uses a NumPy generator seeded from fm.randomState (Nim's RNG stream is not reproduced;
+SURVEY Appendix B): pass shuffle=False, or perms=..., for reproducible parity runs.
+"""
+import ctypes as C
+import math
+import sys
+
+import numpy as np
+
+from . import _lib
+from .dataset import CSCDataset, CSRDataset, CSRFieldDataset
+from .loss import Squared
+from .model import FactorizationMachine, FieldAwareFactorizationMachine
+
+constant, optimal, invscaling, pegasos = "constant", "optimal", "invscaling", "pegasos"
+
+
+# ---------------------------------------------------------------- optimizer/utils.nim:26-59
+def echoHeader(maxIter, viol=True, loss=True, regul=True):
+    s = "Epoch".ljust(len(str(maxIter)))
+    if viol:
+        s += "   " + "Violation".ljust(10)
+    if loss:
+        s += "   " + "Loss".ljust(10)
+    if regul:
+        s += "   Regularization"
+    sys.stdout.write(s + "\n")
+    sys.stdout.flush()
+
+
+def echoInfo(it, maxIter, viol, loss, regul):
+    s = str(it).ljust(max(5, len(str(maxIter))))
+    for v in (viol, loss, regul):
+        if v >= 0:
+            s += "   " + f"{v:<10.4e}"
+    sys.stdout.write(s + "\n")
+    sys.stdout.flush()
+
+
+def regularization(P, w, intercept, alpha0, alpha, beta):
+    """utils.nim:56-59 (host-side, for verbose output and objective checks)"""
+    return (0.5 * alpha0 * intercept ** 2 + 0.5 * alpha * float(np.sum(np.square(w)))
+            + 0.5 * beta * float(np.sum(np.square(P))))
+
+
+class _Base:                                  # optimizer_base.nim:1-14
+    def _rng(self, fm):
+        return np.random.default_rng(fm.randomState)
+
+    def _stopping(self, fm, lossVal, viol, epoch):   # sgd.nim:72-89 stoppingCriterion
+        if math.isnan(lossVal):
+            print("Loss is NaN. Use smaller learning rate.")
+            return False
+        if self.verbose > 0:
+            reg = regularization(fm.P, fm.w, fm.intercept, self.alpha0, self.alpha, self.beta)
+            echoInfo(epoch + 1, self.maxIter, viol, lossVal, reg)
+        if viol < self.tol:
+            if self.verbose > 0:
+                print(f"Converged at epoch {epoch}.")
+            self._converged = True
+            return False
+        return True
+
+
+# ================================================================ CD
+class CD(_Base):
+    def __init__(self, maxIter=100, alpha0=1e-6, alpha=1e-3, beta=1e-3, loss=None, verbose=1, tol=1e-3):
+        self.maxIter, self.alpha0, self.alpha, self.beta = maxIter, alpha0, alpha, beta
+        self.loss = loss if loss is not None else Squared()
+        self.verbose, self.tol = verbose, tol
+
+    def fit(self, X, y, fm, callback=None):
+        """cd.nim:110-194.  X must be a CSCDataset (ColDataset)."""
+        if not isinstance(X, CSCDataset):
+            raise TypeError("CD.fit needs a CSCDataset")
+        fm.init(X)
+        y = fm.checkTarget(y)
+        lib, ctx = _lib.load(), _lib.ctx()
+        X.set_targets(y)
+        h = fm._to_device(X.nFeatures)
+        cfg = _lib.CdCfg(self.loss.kind, self.loss.threshold, self.alpha0, self.alpha, self.beta)
+        self.history = []
+        try:
+            _lib.check(lib.nimfm_fm_cd_begin(ctx, h, X.handle(), C.byref(cfg)))
+            if self.verbose > 0:
+                echoHeader(self.maxIter)
+            converged = False
+            for it in range(self.maxIter):
+                viol, lossMean, reg = C.c_double(), C.c_double(), C.c_double()
+                _lib.check(lib.nimfm_fm_cd_epoch(ctx, h, X.handle(), C.byref(cfg), C.byref(viol),
+                                                 C.byref(lossMean), C.byref(reg)))
+                self.history.append((viol.value, lossMean.value, reg.value))
+                if callback is not None:
+                    fm._from_device(h)
+                    callback(self, fm)
+                if self.verbose > 0:
+                    echoInfo(it + 1, self.maxIter, viol.value, lossMean.value, reg.value)
+                if viol.value < self.tol:
+                    if self.verbose > 0:
+                        print(f"Converged at iteration {it + 1}.")
+                    converged = True
+                    break
+            if not converged and self.verbose > 0:
+                print("Objective did not converge. Increase maxIter.")
+            _lib.check(lib.nimfm_fm_cd_end(ctx, h))
+            fm._from_device(h)
+        finally:
+            lib.nimfm_fm_free(ctx, h)
+
+
+def newCD(maxIter=100, alpha0=1e-6, alpha=1e-3, beta=1e-3, loss=None, verbose=1, tol=1e-3):
+    return CD(maxIter, alpha0, alpha, beta, loss, verbose, tol)
+
+
+# ================================================================ SGD
+class SGD(_Base):
+    def __init__(self, maxIter=100, eta0=0.01, alpha0=1e-6, alpha=1e-3, beta=1e-3, loss=None,
+                 scheduling=optimal, power=1.0, verbose=1, tol=1e-3, shuffle=True, nCalls=-1):
+        self.maxIter, self.eta0, self.alpha0, self.alpha, self.beta = maxIter, eta0, alpha0, alpha, beta
+        self.loss = loss if loss is not None else Squared()
+        self.scheduling, self.power = scheduling, power
+        self.verbose, self.tol, self.shuffle, self.nCalls = verbose, tol, shuffle, nCalls
+        self.it = 1
+
+    def init(self):                            # sgd.nim:55-57
+        self.it = 1
+        if self.verbose > 0:
+            echoHeader(self.maxIter)
+
+    def fit(self, X, y, fm, maxThreads=None, callback=None, perms=None):
+        """sgd.nim:261-328 / sgd_ffm.nim:49-106.  maxThreads (the Hogwild variants' argument,
+        sgd_multi.nim:40) is accepted and ignored: the device path keeps the exact sequential
+        semantics."""
+        is_ffm = isinstance(fm, FieldAwareFactorizationMachine)
+        fm.init(X)
+        y = fm.checkTarget(y)
+        lib, ctx = _lib.load(), _lib.ctx()
+        X.set_targets(y)
+        n = X.nSamples
+        h = fm._to_device(X) if is_ffm else fm._to_device(X.nFeatures)
+        begin, epoch, end, free = ((lib.nimfm_ffm_sgd_begin, lib.nimfm_ffm_sgd_epoch, lib.nimfm_ffm_sgd_end,
+                                    lib.nimfm_ffm_free) if is_ffm else
+                                   (lib.nimfm_fm_sgd_begin, lib.nimfm_fm_sgd_epoch, lib.nimfm_fm_sgd_end,
+                                    lib.nimfm_fm_free))
+        cfg = _lib.SgdCfg(self.loss.kind, self.loss.threshold, self.eta0, self.alpha0, self.alpha, self.beta,
+                          _lib.SCHED[self.scheduling], self.power)
+        if not fm.warmStart:
+            self.init()
+        rng = self._rng(fm)
+        indices = np.arange(n, dtype=np.int64)
+        self._converged = False
+        self.history = []
+        try:
+            _lib.check(begin(ctx, h))
+            for ep in range(self.maxIter):
+                if perms is not None:
+                    indices = _lib.i64(perms[ep])
+                elif self.shuffle:
+                    rng.shuffle(indices)
+                it = C.c_int64(self.it)
+                viol, lossSum = C.c_double(), C.c_double()
+                _lib.check(epoch(ctx, h, X.handle(), C.byref(cfg), C.byref(it), _lib.ptr(indices), n,
+                                 C.byref(viol), C.byref(lossSum)))
+                self.it = it.value
+                runningLoss = lossSum.value / n
+                self.history.append((viol.value, runningLoss))
+                if callback is not None:
+                    # finalize + transpose back before the user sees the model (sgd.nim:310-316)
+                    _lib.check(end(ctx, h))
+                    fm._from_device(h)
+                    callback(self, fm)
+                elif self.verbose > 0:
+                    fm._from_device(h)      # un-finalized, as the reference's verbose line sees it
+                if not self._stopping(fm, runningLoss, viol.value, ep):
+                    break
+            if not self._converged and self.verbose > 0:
+                print("Objective did not converge. Increase maxIter.")
+            _lib.check(end(ctx, h))
+            fm._from_device(h)
+        finally:
+            free(ctx, h)
+
+
+def newSGD(maxIter=100, eta0=0.01, alpha0=1e-6, alpha=1e-3, beta=1e-3, loss=None, scheduling=optimal,
+           power=1.0, verbose=1, tol=1e-3, shuffle=True, nCalls=-1):
+    return SGD(maxIter, eta0, alpha0, alpha, beta, loss, scheduling, power, verbose, tol, shuffle, nCalls)
+
+
+# ================================================================ AdaGrad
+class AdaGrad(_Base):
+    def __init__(self, maxIter=100, eta0=0.1, alpha0=1e-6, alpha=1e-3, beta=1e-3, loss=None, eps=1e-10,
+                 verbose=1, tol=1e-3, shuffle=True, nCalls=-1, miniBatchSize=1):
+        """newAdaGrad (adagrad.nim:20-44).  miniBatchSize is this implementation's extra knob: 1 is
+        the reference's strictly sequential semantics; >1 is the synchronous-minibatch variant that
+        shards over GPUs."""
+        self.maxIter, self.eta0, self.alpha0, self.alpha, self.beta = maxIter, eta0, alpha0, alpha, beta
+        self.loss = loss if loss is not None else Squared()
+        self.eps, self.verbose, self.tol, self.shuffle, self.nCalls = eps, verbose, tol, shuffle, nCalls
+        self.miniBatchSize = int(miniBatchSize)
+        self.it = 1
+        self.g_sum = None
+        self.g_norm = None
+
+    def fit(self, X, y, fm, maxThreads=None, callback=None, perms=None):
+        """adagrad.nim:137-203 / adagrad_ffm.nim:11-66 (maxThreads of adagrad_multi.nim:39 is ignored)."""
+        is_ffm = isinstance(fm, FieldAwareFactorizationMachine)
+        fm.init(X)
+        y = fm.checkTarget(y)
+        lib, ctx = _lib.load(), _lib.ctx()
+        X.set_targets(y)
+        n = X.nSamples
+        h = fm._to_device(X) if is_ffm else fm._to_device(X.nFeatures)
+        init, epoch, fin, free = ((lib.nimfm_ffm_adagrad_init, lib.nimfm_ffm_adagrad_epoch,
+                                   lib.nimfm_ffm_adagrad_finalize, lib.nimfm_ffm_free) if is_ffm else
+                                  (lib.nimfm_fm_adagrad_init, lib.nimfm_fm_adagrad_epoch,
+                                   lib.nimfm_fm_adagrad_finalize, lib.nimfm_fm_free))
+        cfg = _lib.AdagradCfg(self.loss.kind, self.loss.threshold, self.eta0, self.alpha0, self.alpha,
+                              self.beta, self.eps, self.miniBatchSize)
+        if not fm.warmStart:                   # AdaGrad.init, adagrad.nim:47-62
+            self.it = 1
+        rng = self._rng(fm)
+        indices = np.arange(n, dtype=np.int64)
+        self._converged = False
+        self.history = []
+        try:
+            _lib.check(init(ctx, h, self.eps, 1))
+            if self.it != 1 and not is_ffm:
+                if self.g_sum is None:
+                    raise ValueError("warmStart=true but the optimizer has no g_sum / g_norm state.")
+                if self.g_sum["P"].shape != (fm.nOrders, X.nFeatures + fm.nAugments, fm.nComponents):
+                    raise ValueError("warmStart=true but P.shape != g_sum.P.shape.")   # adagrad.nim:57-59
+                _lib.check(lib.nimfm_fm_adagrad_set_state(
+                    ctx, h, _lib.ptr(_lib.f64(self.g_sum["P"])), _lib.ptr(_lib.f64(self.g_norm["P"])),
+                    _lib.ptr(_lib.f64(self.g_sum["w"])), _lib.ptr(_lib.f64(self.g_norm["w"])),
+                    float(self.g_sum["intercept"]), float(self.g_norm["intercept"])))
+            if self.verbose > 0:
+                echoHeader(self.maxIter)
+            for ep in range(self.maxIter):
+                if perms is not None:
+                    indices = _lib.i64(perms[ep])
+                elif self.shuffle:
+                    rng.shuffle(indices)
+                it = C.c_int64(self.it)
+                viol, lossSum = C.c_double(), C.c_double()
+                _lib.check(epoch(ctx, h, X.handle(), C.byref(cfg), C.byref(it), _lib.ptr(indices), n,
+                                 C.byref(viol), C.byref(lossSum)))
+                self.it = it.value
+                runningLoss = lossSum.value / n
+                self.history.append((viol.value, runningLoss))
+                if callback is not None:
+                    _lib.check(fin(ctx, h, C.byref(cfg), self.it))
+                    fm._from_device(h)
+                    callback(self, fm)
+                elif self.verbose > 0:
+                    fm._from_device(h)
+                if not self._stopping(fm, runningLoss, viol.value, ep):
+                    break
+            if not self._converged and self.verbose > 0:
+                print("Objective did not converge. Increase maxIter.")
+            if not is_ffm:
+                d, dd = X.nFeatures, X.nFeatures + fm.nAugments
+                gsP, gnP = np.zeros((fm.nOrders, dd, fm.nComponents)), np.zeros((fm.nOrders, dd, fm.nComponents))
+                gsw, gnw = np.zeros(d), np.zeros(d)
+                gsb, gnb = C.c_double(), C.c_double()
+                _lib.check(lib.nimfm_fm_adagrad_get_state(ctx, h, _lib.ptr(gsP), _lib.ptr(gnP), _lib.ptr(gsw),
+                                                          _lib.ptr(gnw), C.byref(gsb), C.byref(gnb)))
+                self.g_sum = dict(P=gsP, w=gsw, intercept=gsb.value)
+                self.g_norm = dict(P=gnP, w=gnw, intercept=gnb.value)
+            _lib.check(fin(ctx, h, C.byref(cfg), self.it))     # finalize, adagrad.nim:65-84
+            fm._from_device(h)
+        finally:
+            free(ctx, h)
+
+
+def newAdaGrad(maxIter=100, eta0=0.1, alpha0=1e-6, alpha=1e-3, beta=1e-3, loss=None, eps=1e-10, verbose=1,
+               tol=1e-3, shuffle=True, nCalls=-1, miniBatchSize=1):
+    return AdaGrad(maxIter, eta0, alpha0, alpha, beta, loss, eps, verbose, tol, shuffle, nCalls, miniBatchSize)
+
+
+# ================================================================ MBPSGD
+class L1:                                      # regularizer/l1.nim
+    kind = _lib.REG_L1
+
+
+class SquaredL12:                              # regularizer/squaredl12.nim (device path: gamma == 0 only)
+    kind = _lib.REG_IDENTITY
+
+
+def newL1():
+    return L1()
+
+
+def newSquaredL12():
+    return SquaredL12()
+
+
+class MBPSGD(_Base):
+    def __init__(self, maxIter=100, eta0=0.1, alpha0=1e-6, alpha=1e-3, beta=1e-4, gamma=1e-4, loss=None,
+                 reg=None, miniBatchSize=-1, maxIterInner=-1, scheduling=optimal, power=1.0, verbose=1,
+                 tol=1e-6, shuffle=True, nCalls=-1):
+        self.maxIter, self.eta0, self.alpha0, self.alpha, self.beta, self.gamma = maxIter, eta0, alpha0, alpha, beta, gamma
+        self.loss = loss if loss is not None else Squared()
+        self.reg = reg if reg is not None else SquaredL12()
+        self.miniBatchSize, self.maxIterInner = miniBatchSize, maxIterInner
+        self.scheduling, self.power, self.verbose, self.tol, self.shuffle = scheduling, power, verbose, tol, shuffle
+        self.it = 0                            # minibatch_psgd.nim:62
+
+    def resolve_sizes(self, X):
+        """minibatch_psgd.nim:157-165"""
+        mb = self.miniBatchSize
+        if mb <= 0:
+            mb = max((X.nFeatures * X.nSamples) // X.nnz, 1)
+        inner = self.maxIterInner
+        if inner <= 0:
+            inner = max((X.nSamples - 1) // mb + 1, 1)
+        return mb, inner
+
+    def fit(self, X, y, sfm, callback=None):
+        """minibatch_psgd.nim:127-211"""
+        if isinstance(self.reg, SquaredL12) and self.gamma != 0.0:
+            raise NotImplementedError(
+                "SquaredL12.prox with gamma != 0 is not on the device path yet (SURVEY 8f.1); use "
+                "gamma=0 (identity, squaredl12.nim:67-69) or reg=newL1()")
+        sfm.init(X)
+        y = sfm.checkTarget(y)
+        lib, ctx = _lib.load(), _lib.ctx()
+        X.set_targets(y)
+        n = X.nSamples
+        h = sfm._to_device(X.nFeatures)
+        if not sfm.warmStart:
+            self.it = 1                        # :151-152
+        mb, inner = self.resolve_sizes(X)
+        cfg = _lib.MbpsgdCfg(self.loss.kind, self.loss.threshold, self.eta0, self.alpha0, self.alpha, self.beta,
+                             self.gamma, self.reg.kind, _lib.SCHED[self.scheduling], self.power, mb, inner)
+        rng = self._rng(sfm)
+        indices = np.arange(n, dtype=np.int64)
+        if self.shuffle:
+            rng.shuffle(indices)               # :169-170
+        if self.verbose > 0:
+            print("Minibatch size: ", mb)
+            print("Number of inner iteration: ", inner)
+            echoHeader(self.maxIter, viol=False)
+        ii = 0
+        oldLoss = float("inf")
+        converged = False
+        self.history = []
+        try:
+            for ep in range(self.maxIter):
+                sample = None
+                if self.shuffle:
+                    # the cursor + reshuffle-at-wrap logic of epoch() (:102-111), evaluated on the host
+                    total = mb * inner
+                    sample = np.empty(total, dtype=np.int64)
+                    filled = 0
+                    while filled < total:
+                        take = min(total - filled, n - ii)
+                        sample[filled:filled + take] = indices[ii:ii + take]
+                        filled += take
+                        ii += take
+                        if ii >= n:
+                            ii = 0
+                            rng.shuffle(indices)
+                itc, iic, rl = C.c_int64(self.it), C.c_int64(ii), C.c_double()
+                _lib.check(lib.nimfm_fm_mbpsgd_epoch(ctx, h, X.handle(), C.byref(cfg), mb, C.byref(itc),
+                                                     C.byref(iic), _lib.ptr(sample), C.byref(rl)))
+                self.it = itc.value
+                if not self.shuffle:
+                    ii = iic.value
+                runningLoss = rl.value
+                self.history.append(runningLoss)
+                if callback is not None or self.verbose > 0:
+                    sfm._from_device(h)        # pgd.finalize, pgd.nim:45-51
+                    if callback is not None:
+                        callback(self, sfm)
+                if math.isnan(runningLoss):
+                    print("Loss is NaN. Use smaller learning rate.")
+                    break
+                if self.verbose > 0:
+                    regVal = regularization(sfm.P, sfm.w, sfm.intercept, self.alpha0, self.alpha, self.beta)
+                    if isinstance(self.reg, L1):
+                        regVal += self.gamma * sfm.nOrders * 0 + self.gamma * float(np.sum(np.abs(sfm.P)))
+                    echoInfo(ep + 1, self.maxIter, -1, runningLoss, regVal)
+                if abs(oldLoss - runningLoss) < self.tol:
+                    if self.verbose > 0:
+                        print("Converged at epoch ", ep + 1, ".")
+                    converged = True
+                    break
+                oldLoss = runningLoss
+            if not converged and self.verbose > 0:
+                print("Objective did not converge. Increase maxIter.")
+            sfm._from_device(h)
+        finally:
+            lib.nimfm_fm_free(ctx, h)
+
+
+def newMBPSGD(maxIter=100, eta0=0.1, alpha0=1e-6, alpha=1e-3, beta=1e-4, gamma=1e-4, loss=None, reg=None,
+              miniBatchSize=-1, maxIterInner=-1, scheduling=optimal, power=1.0, verbose=1, tol=1e-6,
+              shuffle=True, nCalls=-1):
+    return MBPSGD(maxIter, eta0, alpha0, alpha, beta, gamma, loss, reg, miniBatchSize, maxIterInner,
+                  scheduling, power, verbose, tol, shuffle, nCalls)
