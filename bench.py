@@ -35,7 +35,7 @@ B_FWD = Z * (8 + 4 + 8 + 8 * K * N_ORDERS) + 8 + 8
 B_GRAD = B_FWD + 8 + Z * (8 * K * N_ORDERS + 8)
 
 
-def gen_criteo_rows(n, seed, d=D_FEATURES):
+def gen_criteo_rows(n, seed, d=D_FEATURES, dist="criteo"):
     """Criteo-shaped synthetic CSR in the reference dtypes: 13 numeric slots (features 0..12, values
     U(0,1]) and 26 categorical slots, each with its own hashed id range and a Zipf(1.05)-like rank
     distribution (bounded inverse-CDF), value 1.0; indices sorted and unique within a row; y = +-1."""
@@ -54,6 +54,17 @@ def gen_criteo_rows(n, seed, d=D_FEATURES):
         np.clip(rank, 0, R - 1, out=rank)
         indices[a:b, N_NUM:] = N_NUM + np.arange(N_CAT)[None, :] * R + rank
     data[:, N_NUM:] = 1.0
+    if dist != "criteo":   # experiments only (never the reported workload)
+        R2 = d // Z
+        for a in range(0, n, step):
+            b = min(n, a + step)
+            if dist == "uniform":      # every slot uniform over its own id range: no hot features at all
+                rank = rng.integers(0, R2, size=(b - a, Z))
+            else:                      # "zipfall": every slot Zipf-like, no always-present columns
+                u = rng.random((b - a, Z))
+                rank = np.floor(((R2 ** (1.0 - s) - 1.0) * u + 1.0) ** (1.0 / (1.0 - s))).astype(np.int64) - 1
+                np.clip(rank, 0, R2 - 1, out=rank)
+            indices[a:b] = np.arange(Z)[None, :] * R2 + rank
     indptr = np.arange(n + 1, dtype=np.int64) * Z
     y = np.where(rng.random(n) < 0.5, -1.0, 1.0)
     return data.reshape(-1), indices.reshape(-1), indptr, y
@@ -218,6 +229,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bounded CPU-baseline sample")
     ap.add_argument("--ref-rows", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dist", default="criteo", choices=["criteo", "uniform", "zipfall"],
+                    help="index distribution; anything but 'criteo' is an experiment, not the reported workload")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -249,7 +262,7 @@ def main():
 
     n = args.rows
     t_gen = time.perf_counter()
-    data, indices, indptr, y = gen_criteo_rows(n, 1000 + rank)
+    data, indices, indptr, y = gen_criteo_rows(n, 1000 + rank, dist=args.dist)
     ds = nf.newCSRDataset(data, indices, indptr, n, D_FEATURES)
     ds.set_targets(y)
     P, w, b = model_params(7)
@@ -349,6 +362,8 @@ def main():
         "roofline": roofline,
         "loss_sum": loss_sum, "setup_seconds": t_gen,
     }
+    if args.dist != "criteo":
+        line["config"]["experiment_dist"] = args.dist
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
         orc.build()

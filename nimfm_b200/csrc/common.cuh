@@ -41,6 +41,8 @@ struct nimfm_ctx {
     int32_t *idx32 = nullptr;
     size_t capNnz = 0, capRows = 0;
   } stage[2];
+  uint8_t *stageHotSlot = nullptr;
+  int32_t *stageHotList = nullptr;
   // communicator
   ncclComm *comm = nullptr;
   int rank = 0, nranks = 1;
@@ -56,6 +58,10 @@ struct nimfm_dataset {
   int64_t *indptr = nullptr;
   int32_t *fields = nullptr;
   double *y = nullptr;
+  // hot features (CSR kinds): columns present in >= 1/16 of a row sample, at most 16 (fm_rows.cuh)
+  uint8_t *hotSlot = nullptr;        // [d], 255 = cold
+  int32_t *hotList = nullptr;        // [nHot]
+  int nHot = 0;
   // CD only: runs of consecutive columns with pairwise-disjoint row support (built at cd_begin)
   std::vector<int64_t> cdBatchStart;
 };

@@ -118,6 +118,8 @@ int32_t nimfm_ctx_destroy(nimfm_ctx *ctx) {
     if (ctx->evCopied[s]) cudaEventDestroy(ctx->evCopied[s]);
     if (ctx->evComputed[s]) cudaEventDestroy(ctx->evComputed[s]);
   }
+  cudaFree(ctx->stageHotSlot);
+  cudaFree(ctx->stageHotList);
   if (ctx->tev0) cudaEventDestroy(ctx->tev0);
   if (ctx->tev1) cudaEventDestroy(ctx->tev1);
   if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);

@@ -2,12 +2,49 @@
 // Integer bookkeeping only: index narrowing int64 -> int32, row-shard rebasing (X[slice],
 // tensor/sparse.nim:263-290) and the stable counting-sort transpose (sparse.nim:490-527).
 #include <algorithm>
+#include <unordered_map>
 
 #include "common.cuh"
 
 static int alloc_copy(nimfm_ctx *ctx, void **dst, const void *src, size_t bytes) {
   CK(cudaMalloc(dst, bytes ? bytes : 16));
   if (bytes) CK(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return NIMFM_OK;
+}
+
+// Find the "hot" columns of a CSR from an evenly spaced sample of at most 16384 rows: present in at
+// least 1/16 of the sampled rows, the 16 most frequent.  Pure bookkeeping; it only changes where the
+// kernels ACCUMULATE the gradients of those columns, never a result.
+int nimfm_find_hot(const int64_t *indices, const int64_t *indptr, int64_t rowBegin, int64_t rowEnd,
+                   std::vector<int32_t> &hot, int64_t maxSample) {
+  hot.clear();
+  const int64_t ns = rowEnd - rowBegin;
+  if (ns <= 0) return 0;
+  const int64_t stride = std::max<int64_t>(1, ns / maxSample);
+  std::unordered_map<int64_t, int> cnt;
+  int64_t sampled = 0;
+  for (int64_t r = rowBegin; r < rowEnd; r += stride, ++sampled)
+    for (int64_t q = indptr[r]; q < indptr[r + 1]; q++) cnt[indices[q]] += 1;
+  std::vector<std::pair<int, int64_t>> cand;
+  for (auto &kv : cnt)
+    if ((int64_t)kv.second * 16 >= sampled && kv.second >= 2) cand.push_back({kv.second, kv.first});
+  std::sort(cand.begin(), cand.end(), [](const std::pair<int, int64_t> &x, const std::pair<int, int64_t> &y) {
+    return x.first != y.first ? x.first > y.first : x.second < y.second;
+  });
+  for (size_t i = 0; i < cand.size() && i < 16; i++) hot.push_back((int32_t)cand[i].second);
+  return (int)hot.size();
+}
+
+int nimfm_upload_hot(nimfm_ctx *ctx, const std::vector<int32_t> &hot, int64_t d, uint8_t **hotSlot,
+                     int32_t **hotList) {
+  std::vector<uint8_t> tab((size_t)std::max<int64_t>(d, 1), 255);
+  for (size_t i = 0; i < hot.size(); i++) tab[(size_t)hot[i]] = (uint8_t)i;
+  if (!*hotSlot) CK(cudaMalloc(hotSlot, tab.size()));
+  if (!*hotList) CK(cudaMalloc(hotList, 16 * sizeof(int32_t)));
+  CK(cudaMemcpyAsync(*hotSlot, tab.data(), tab.size(), cudaMemcpyHostToDevice, ctx->stream));
+  if (!hot.empty())
+    CK(cudaMemcpyAsync(*hotList, hot.data(), hot.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   return NIMFM_OK;
 }
 
@@ -66,6 +103,11 @@ static int upload_common(nimfm_ctx *ctx, int kind, int64_t nSeg, int64_t nOther,
   if ((rc = alloc_copy(ctx, (void **)&ds->indices, idx32.data(), (size_t)nnz * 4))) return rc;
   if ((rc = alloc_copy(ctx, (void **)&ds->indptr, ptr.data(), ((size_t)ns + 1) * 8))) return rc;
   if (fields && (rc = alloc_copy(ctx, (void **)&ds->fields, f32.data(), (size_t)nnz * 4))) return rc;
+  if (kind != NIMFM_DS_CSC) {
+    std::vector<int32_t> hot;
+    ds->nHot = nimfm_find_hot(indices, indptr, segBegin, segEnd, hot, 16384);
+    if ((rc = nimfm_upload_hot(ctx, hot, d, &ds->hotSlot, &ds->hotList))) return rc;
+  }
   CK(cudaStreamSynchronize(ctx->stream));
   *out = ds;
   return NIMFM_OK;
@@ -177,6 +219,8 @@ int32_t nimfm_dataset_free(nimfm_ctx *ctx, nimfm_dataset *ds) {
   cudaFree(ds->indptr);
   cudaFree(ds->fields);
   cudaFree(ds->y);
+  cudaFree(ds->hotSlot);
+  cudaFree(ds->hotList);
   delete ds;
   return NIMFM_OK;
 }

@@ -4,12 +4,12 @@
 
 #include <algorithm>
 
-#include "fm_rows.cuh"
+#include "fm_rows_fast.cuh"
 
 typedef void (*RowKernel)(const RowArgs);
-RowKernel nimfm_row_kernel_predict(int degree, bool explicitLower);
-RowKernel nimfm_row_kernel_grad(int degree, bool explicitLower);
-RowKernel nimfm_row_kernel_adagrad(int degree, bool explicitLower);
+RowKernel nimfm_row_kernel_predict(int degree, bool explicitLower, int k);
+RowKernel nimfm_row_kernel_grad(int degree, bool explicitLower, int k);
+RowKernel nimfm_row_kernel_adagrad(int degree, bool explicitLower, int k);
 
 // ------------------------------------------------------------------ layout permutations
 // reference model layout  R[o][s][j]   (factorization_machine.nim:33-36)
@@ -187,24 +187,53 @@ __global__ void fill_kernel(double *p, int64_t n, double v) {
 
 // ------------------------------------------------------------------ launch planning
 struct RowPlan {
+  RowKernel kern;
+  bool fast;
   int G, CH, block, grid;
   size_t smem;
   int64_t nWarps;
 };
 
-static int plan_rows(nimfm_ctx *ctx, const nimfm_fm *fm, const nimfm_dataset *X, int64_t nRows,
-                     RowKernel kern, RowPlan *pl) {
+RowKernel nimfm_row_fast_kernel_predict(int degree, bool explicitLower, int k);
+RowKernel nimfm_row_fast_kernel_grad(int degree, bool explicitLower, int k);
+
+static bool is_explicit(const nimfm_fm *fm) { return fm->degree > 2 && fm->nOrders == fm->degree - 1; }
+
+// Chooses the kernel (tuned instance when one exists for the shape and every row fits the staging
+// buffer, else the generic one), the staging capacity CH, the block size that maximises resident
+// warps under the shared-memory budget, and a persistent grid of occupancy x numSMs blocks.
+static int plan_rows(nimfm_ctx *ctx, const nimfm_fm *fm, const nimfm_dataset *X, int64_t nRows, int mode,
+                     RowPlan *pl) {
+  const int nAcc = mode == MODE_PREDICT ? 0 : (mode == MODE_GRAD ? 1 : 2);
+  const int nHotTot = nAcc ? (X->hotSlot ? X->nHot : 0) + fm->nAug : 0;
   const int k = fm->k;
   const int G = k <= 8 ? 8 : (k <= 16 ? 16 : 32);
   const int gpw = 32 / G;
   const int SB8 = fm->nOrders * k;
-  const size_t perNnz = (size_t)SB8 * 8 + 12;
   int64_t z = X->maxSegNnz + fm->nAug;
   if (z < 1) z = 1;
   const size_t capPerGroup = 40 * 1024;
-  int64_t CH = std::min<int64_t>(z, (int64_t)(capPerGroup / perNnz));
-  if (CH < 1) return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "nOrders*nComponents=%d too large for the device row kernel", SB8);
-  const size_t perGroup = (((size_t)CH * perNnz) + 15) & ~(size_t)15;
+  const bool expl = is_explicit(fm);
+  RowKernel fast = nullptr;
+  if (mode == MODE_PREDICT) fast = nimfm_row_fast_kernel_predict(fm->degree, expl, k);
+  else if (mode == MODE_GRAD) fast = nimfm_row_fast_kernel_grad(fm->degree, expl, k);
+  if (fast && (size_t)z * ((size_t)SB8 * 8 + 16) > capPerGroup) fast = nullptr;   // a row does not fit
+  RowKernel kern = fast;
+  int64_t CH = z;
+  size_t perGroup;
+  if (fast) {
+    perGroup = fast_group_smem((int)CH, SB8, nHotTot);
+  } else {
+    kern = mode == MODE_PREDICT ? nimfm_row_kernel_predict(fm->degree, expl, k)
+           : mode == MODE_GRAD  ? nimfm_row_kernel_grad(fm->degree, expl, k)
+                                : nimfm_row_kernel_adagrad(fm->degree, expl, k);
+    const size_t perNnz = (size_t)SB8 * 8 + 13;
+    CH = std::min<int64_t>(z, (int64_t)(capPerGroup / perNnz));
+    if (CH < 1)
+      return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "nOrders*nComponents=%d too large for the device row kernel", SB8);
+    perGroup = row_group_smem((int)CH, SB8, nHotTot, nAcc ? nAcc : 1);
+  }
+  if (!kern) return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "no row kernel for degree %d", fm->degree);
   int bestBlock = 0, bestOcc = 0, bestWarps = -1;
   for (int block : {256, 128, 64, 32}) {
     const size_t smem = (size_t)(block / 32) * gpw * perGroup;
@@ -221,6 +250,8 @@ static int plan_rows(nimfm_ctx *ctx, const nimfm_fm *fm, const nimfm_dataset *X,
   }
   if (bestBlock == 0 || bestOcc == 0)
     return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "row kernel does not fit on an SM (perGroup=%zu B)", perGroup);
+  pl->kern = kern;
+  pl->fast = fast != nullptr;
   pl->G = G;
   pl->CH = (int)CH;
   pl->block = bestBlock;
@@ -262,9 +293,10 @@ static void fill_row_args(RowArgs &a, const nimfm_fm *fm, const nimfm_dataset *X
   a.fitLinear = fm->fitLinear;
   a.fitIntercept = fm->fitIntercept;
   a.mb = 1.0;
+  a.hotSlot = X->hotSlot;
+  a.hotList = X->hotList;
+  a.nHot = X->hotSlot ? X->nHot : 0;
 }
-
-static bool is_explicit(const nimfm_fm *fm) { return fm->degree > 2 && fm->nOrders == fm->degree - 1; }
 
 extern "C" {
 
@@ -404,9 +436,9 @@ int32_t nimfm_fm_decision_function(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dat
   if (rc) { nimfm_dataset_free(ctx, twin); return rc; }
   const int64_t n = Xr->n;
   if (n == 0) { nimfm_dataset_free(ctx, twin); return NIMFM_OK; }
-  RowKernel kern = nimfm_row_kernel_predict(fm->degree, is_explicit(fm));
   RowPlan pl;
-  if ((rc = plan_rows(ctx, fm, Xr, n, kern, &pl))) { nimfm_dataset_free(ctx, twin); return rc; }
+  if ((rc = plan_rows(ctx, fm, Xr, n, MODE_PREDICT, &pl))) { nimfm_dataset_free(ctx, twin); return rc; }
+  RowKernel kern = pl.kern;
   double *dOut = nullptr;
   CK(cudaMalloc(&dOut, (size_t)n * 8));
   RowArgs a;
@@ -430,10 +462,10 @@ int32_t nimfm_fm_decision_function(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dat
 static int launch_loss_grad(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, int loss, double thr,
                             int64_t rowBegin, int64_t nRows, const int32_t *rowIdxDev, double mb,
                             double *yOutDev) {
-  RowKernel kern = nimfm_row_kernel_grad(fm->degree, is_explicit(fm));
   RowPlan pl;
-  int rc = plan_rows(ctx, fm, X, nRows, kern, &pl);
+  int rc = plan_rows(ctx, fm, X, nRows, MODE_GRAD, &pl);
   if (rc) return rc;
+  RowKernel kern = pl.kern;
   if ((rc = nimfm_ensure_partials(ctx, (size_t)pl.nWarps * 4))) return rc;
   RowArgs a;
   fill_row_args(a, fm, X);
@@ -499,10 +531,9 @@ int32_t nimfm_fm_time_loss_grad(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_datase
   int rc = check_fm_ds(ctx, fm, X, gradToo != 0);
   if (rc) return rc;
   REQUIRE(reps >= 1 && nRows >= 1 && msPerLaunch, "bad arguments");
-  RowKernel kern = gradToo ? nimfm_row_kernel_grad(fm->degree, is_explicit(fm))
-                           : nimfm_row_kernel_predict(fm->degree, is_explicit(fm));
   RowPlan pl;
-  if ((rc = plan_rows(ctx, fm, X, nRows, kern, &pl))) return rc;
+  if ((rc = plan_rows(ctx, fm, X, nRows, gradToo ? MODE_GRAD : MODE_PREDICT, &pl))) return rc;
+  RowKernel kern = pl.kern;
   if ((rc = nimfm_ensure_partials(ctx, (size_t)pl.nWarps * 4))) return rc;
   double *dOut = nullptr;
   if (!gradToo) CK(cudaMalloc(&dOut, (size_t)nRows * 8));
@@ -640,7 +671,6 @@ int32_t nimfm_fm_adagrad_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset
     if ((rc = nimfm_stage_row_ids(ctx, perm, nRows, X->n))) return rc;
     idxDev = ctx->idx32Scratch;
   }
-  RowKernel kern = nimfm_row_kernel_adagrad(fm->degree, is_explicit(fm));
   CK(cudaMemsetAsync(ctx->scalars, 0, 16, ctx->stream));
   double *dGsP = fm->dG, *dGnP = fm->dG + nP, *dGsw = fm->dG + 2 * nP, *dGnw = fm->dG + 2 * nP + d;
   double *touched = fm->dG + 2 * nP + 2 * d;
@@ -650,7 +680,8 @@ int32_t nimfm_fm_adagrad_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset
   for (int64_t start = 0; start < nRows; start += mb) {
     const int64_t cnt = std::min<int64_t>(mb, nRows - start);
     RowPlan pl;
-    if ((rc = plan_rows(ctx, fm, X, cnt, kern, &pl))) return rc;
+    if ((rc = plan_rows(ctx, fm, X, cnt, MODE_ADAGRAD, &pl))) return rc;
+    RowKernel kern = pl.kern;
     if ((rc = nimfm_ensure_partials(ctx, (size_t)pl.nWarps * 4))) return rc;
     RowArgs a;
     fill_row_args(a, fm, X);
@@ -770,6 +801,11 @@ __global__ void narrow_rebase_kernel(const int64_t *idx64, int32_t *idx32, int64
   for (int64_t r = tid; r < nRowsPlus1; r += stride) indptr[r] -= base;
 }
 
+int nimfm_find_hot(const int64_t *indices, const int64_t *indptr, int64_t rowBegin, int64_t rowEnd,
+                   std::vector<int32_t> &hot, int64_t maxSample);
+int nimfm_upload_hot(nimfm_ctx *ctx, const std::vector<int32_t> &hot, int64_t d, uint8_t **hotSlot,
+                     int32_t **hotList);
+
 static int ensure_stage(nimfm_ctx *ctx, nimfm_ctx::Stage &st, size_t rows, size_t nnz) {
   if (st.capRows < rows) {
     if (st.y) CK(cudaFree(st.y));
@@ -816,6 +852,10 @@ extern "C" int32_t nimfm_fm_loss_grad_host(nimfm_ctx *ctx, nimfm_fm *fm, int64_t
   int rc;
   for (int s = 0; s < 2; s++)
     if ((rc = ensure_stage(ctx, ctx->stage[s], (size_t)std::min(nRows, chunkRows) + 1, maxNnz))) return rc;
+  // hot columns of this batch (row sample on the host; see nimfm_find_hot)
+  std::vector<int32_t> hot;
+  const int nHot = (indices && nRows > 0) ? nimfm_find_hot(indices, indptr, 0, nRows, hot, 2048) : 0;
+  if ((rc = nimfm_upload_hot(ctx, hot, d, &ctx->stageHotSlot, &ctx->stageHotList))) return rc;
   int c = 0;
   for (int64_t r0 = 0; r0 < nRows; r0 += chunkRows, c++) {
     const int64_t r1 = std::min(nRows, r0 + chunkRows), rows = r1 - r0;
@@ -841,6 +881,9 @@ extern "C" int32_t nimfm_fm_loss_grad_host(nimfm_ctx *ctx, nimfm_fm *fm, int64_t
     tmp.indices = st.idx32;
     tmp.indptr = st.indptr;
     tmp.y = st.y;
+    tmp.hotSlot = ctx->stageHotSlot;
+    tmp.hotList = ctx->stageHotList;
+    tmp.nHot = nHot;
     if ((rc = launch_loss_grad(ctx, fm, &tmp, loss, huberThreshold, 0, rows, nullptr, (double)miniBatchSize, nullptr)))
       return rc;
     add_tail_kernel<<<1, 1, 0, ctx->stream>>>(fm->grad + nG - 2, ctx->scalars + 8);

@@ -13,6 +13,11 @@
 //   4. backward (MODE_GRAD / MODE_ADAGRAD): the derivative recurrence (sgd.nim:176-188) re-reads the
 //      staged slice (no second gather) and scatters coef*dA with FP64 RED atomics
 //      (minibatch_psgd.nim:77-88 / adagrad.nim:113-134).
+// Hot features: columns present in a large fraction of the rows (dense numeric columns, dummy features
+// of fitLower=augment) would serialise ~nRows RED operations on the same few L2 addresses.  The dataset
+// carries a byte table hotSlot[j] (built from a row sample at upload); gradients of hot features are
+// accumulated in per-group shared-memory accumulators (each element owned by exactly one lane, so no
+// shared atomics or barriers) and flushed with one RED per element when the kernel ends.
 // Rows longer than the staging capacity CH are processed in chunks (the backward pass re-stages).
 // k > G is handled by looping component chunks (the forward is recomputed per chunk in backward).
 #pragma once
@@ -47,31 +52,56 @@ struct RowArgs {
   double *touched;    // per-feature touch marker (part of the all-reduced delta block)
   double eta0, tIt, alpha0, alpha, beta;   // tIt = float(it-1)
   int first;                               // it == 1: no refresh
+  // hot-feature accumulators (nullable table: no data-driven hot features)
+  const uint8_t *hotSlot;   // [d], 255 = cold
+  const int32_t *hotList;   // [nHot] feature id of each slot
+  int nHot;
   // geometry
   int G, CH;
 };
+
+#define NIMFM_COLD 255
+#define NIMFM_MAX_HOT 16
+
+// bytes of shared memory one row group needs (must match the carve-up in fm_rows_kernel)
+__host__ __device__ inline size_t row_group_smem(int CH, int SB8, int nHotTot, int nAcc) {
+  size_t b = ((size_t)CH * SB8 + CH + (size_t)nHotTot * (SB8 + 1) * nAcc) * 8 + (size_t)CH * 4 + (size_t)CH;
+  return (b + 15) & ~(size_t)15;
+}
 
 template <int DEGREE, bool EXPLICIT>
 struct RowCfg {
   static constexpr int NO = (EXPLICIT && DEGREE > 2) ? DEGREE - 1 : 1;
 };
 
-template <int DEGREE, bool EXPLICIT, int MODE>
+// KT > 0 fixes nComponents at compile time (KT in {8,16,32}: one lane per component, all index
+// arithmetic constant-folded); KT == 0 is the generic runtime-k kernel.
+template <int DEGREE, bool EXPLICIT, int MODE, int KT>
 __global__ void __launch_bounds__(256, 1) fm_rows_kernel(const RowArgs a) {
   constexpr int NO = RowCfg<DEGREE, EXPLICIT>::NO;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warpInBlock = threadIdx.x >> 5;
-  const int G = a.G, CH = a.CH, k = a.k;
+  const int G = KT ? (KT < 8 ? 8 : KT) : a.G;
+  const int CH = a.CH;
+  const int k = KT ? KT : a.k;
   const int gpw = 32 / G;
   const int gl = lane & (G - 1);
   const int gidInWarp = lane / G;
   const int SB8 = NO * k;  // doubles per feature slice
-  const size_t perGroup = (((size_t)CH * SB8 * 8 + (size_t)CH * 8 + (size_t)CH * 4) + 15) & ~(size_t)15;
+  constexpr int NACC = (MODE == MODE_ADAGRAD) ? 2 : 1;
+  const int nHotTot = (MODE == MODE_PREDICT) ? 0 : a.nHot + a.nAug;
+  const int ASTR = SB8 + 1;  // accumulator stride per slot: SB8 P-gradients + 1 w-gradient
+  const size_t perGroup = row_group_smem(CH, SB8, nHotTot, NACC);
   unsigned char *base = smem_raw + (size_t)(warpInBlock * gpw + gidInWarp) * perGroup;
   double *sP = reinterpret_cast<double *>(base);
   double *sVal = sP + (size_t)CH * SB8;
-  int *sIdx = reinterpret_cast<int *>(sVal + CH);
+  double *sAcc = sVal + CH;                               // [nHotTot][ASTR] gradient sums
+  double *sAccN = sAcc + (size_t)nHotTot * ASTR;          // AdaGrad: squared-gradient sums
+  int *sIdx = reinterpret_cast<int *>(sAcc + (size_t)nHotTot * ASTR * NACC);
+  unsigned char *sSlot = reinterpret_cast<unsigned char *>(sIdx + CH);
+  for (int e = gl; e < nHotTot * ASTR * NACC; e += G) sAcc[e] = 0.0;
+  __syncwarp();
 
   const int warpsPerBlock = blockDim.x >> 5;
   const int64_t warpGlobal = (int64_t)blockIdx.x * warpsPerBlock + warpInBlock;
@@ -126,6 +156,9 @@ __global__ void __launch_bounds__(256, 1) fm_rows_kernel(const RowArgs a) {
         }
         sIdx[u] = j;
         sVal[u] = x;
+        if (MODE != MODE_PREDICT)
+          sSlot[u] = pos >= zReal ? (unsigned char)(a.nHot + (pos - zReal))
+                                  : (a.hotSlot ? a.hotSlot[j] : (unsigned char)NIMFM_COLD);
         if (withLinear && pos < zReal) {
           if (MODE == MODE_ADAGRAD) {
             double wj = a.w[j];
@@ -281,6 +314,12 @@ __global__ void __launch_bounds__(256, 1) fm_rows_kernel(const RowArgs a) {
               const double x = sVal[u];
               const int64_t e0 = (int64_t)sIdx[u] * SB8 + s;
               const double *ps = sP + (size_t)u * SB8 + s;
+              const int slot = sSlot[u];
+              if (slot != NIMFM_COLD && sc == 0 && gl == 0 && a.fitLinear && sIdx[u] < a.d) {
+                const double gx = coef * x;               // w-gradient of a hot feature: owned by lane 0
+                sAcc[slot * ASTR + SB8] += gx;
+                if (MODE == MODE_ADAGRAD) sAccN[slot * ASTR + SB8] += gx * gx;
+              }
 #pragma unroll
               for (int o = 0; o < NO; ++o) {
                 const int M = DEGREE - o;
@@ -295,8 +334,13 @@ __global__ void __launch_bounds__(256, 1) fm_rows_kernel(const RowArgs a) {
                     if (tt < M) g = x * (A[o][tt] - p * g);
                 }
                 const double gr = coef * g;
-                atomicAdd(a.gP + e0 + o * k, gr);
-                if (MODE == MODE_ADAGRAD) atomicAdd(a.dGnP + e0 + o * k, gr * gr);
+                if (slot != NIMFM_COLD) {                  // element (slot, o, s) is private to this lane
+                  sAcc[slot * ASTR + o * k + s] += gr;
+                  if (MODE == MODE_ADAGRAD) sAccN[slot * ASTR + o * k + s] += gr * gr;
+                } else {
+                  atomicAdd(a.gP + e0 + o * k, gr);
+                  if (MODE == MODE_ADAGRAD) atomicAdd(a.dGnP + e0 + o * k, gr * gr);
+                }
               }
             }
           }
@@ -305,7 +349,7 @@ __global__ void __launch_bounds__(256, 1) fm_rows_kernel(const RowArgs a) {
             for (int u = gl; u < cnt; u += G) {
               const int j = sIdx[u];
               if (MODE == MODE_ADAGRAD) a.touched[j] = 1.0;
-              if (a.fitLinear && j < a.d) {
+              if (a.fitLinear && j < a.d && sSlot[u] == NIMFM_COLD) {
                 const double gx = coef * sVal[u];
                 atomicAdd(a.gw + j, gx);
                 if (MODE == MODE_ADAGRAD) atomicAdd(a.dGnw + j, gx * gx);
@@ -316,6 +360,33 @@ __global__ void __launch_bounds__(256, 1) fm_rows_kernel(const RowArgs a) {
       }
     }
     __syncwarp();
+  }
+
+  if (MODE != MODE_PREDICT && nHotTot > 0) {
+    // flush the hot-feature accumulators: every lane writes the elements it owns
+    __syncwarp();
+    for (int slot = 0; slot < nHotTot; ++slot) {
+      const int64_t j = slot < a.nHot ? (int64_t)a.hotList[slot] : a.d + (slot - a.nHot);
+      for (int s = gl; s < k; s += G) {
+#pragma unroll
+        for (int o = 0; o < NO; ++o) {
+          const double v = sAcc[slot * ASTR + o * k + s];
+          if (v != 0.0) atomicAdd(a.gP + j * SB8 + o * k + s, v);
+          if (MODE == MODE_ADAGRAD) {
+            const double v2 = sAccN[slot * ASTR + o * k + s];
+            if (v2 != 0.0) atomicAdd(a.dGnP + j * SB8 + o * k + s, v2);
+          }
+        }
+      }
+      if (gl == 0 && a.fitLinear && j < a.d) {
+        const double v = sAcc[slot * ASTR + SB8];
+        if (v != 0.0) atomicAdd(a.gw + j, v);
+        if (MODE == MODE_ADAGRAD) {
+          const double v2 = sAccN[slot * ASTR + SB8];
+          if (v2 != 0.0) atomicAdd(a.dGnw + j, v2);
+        }
+      }
+    }
   }
 
   if (MODE != MODE_PREDICT) {

@@ -1,10 +1,407 @@
-// TEMPORARY stubs (replaced as the kernels land)
+// sgd.cu -- SGD with lazy L2 scaling for FM (optimizer/sgd.nim:99-143, 205-258) and FFM
+// (optimizer/sgd_ffm.nim:11-46), SURVEY K6.
+//
+// SGD is strictly sequential per sample: step i reads the parameters step i-1 wrote (through P, w,
+// the intercept and the global scaling_P / scaling_w).  The device therefore runs the whole sample
+// loop inside ONE persistent thread block (the parallelism is inside a row: threads <-> (order,
+// component) for FM, (nonzero, component) for FFM) and keeps the reference's exact semantics.
+// "Replicas only" for multi-GPU; the data-parallel solvers are MBPSGD and minibatch AdaGrad.
+#include <math.h>
+
 #include "common.cuh"
-extern "C" {
-int32_t nimfm_fm_sgd_begin(nimfm_ctx *ctx, nimfm_fm *fm) { return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "nimfm_fm_sgd_begin: not implemented yet"); }
-int32_t nimfm_fm_sgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, const nimfm_sgd_cfg *cfg, int64_t *it, const int64_t *perm, int64_t nRows, double *viol, double *lossSum) { return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "nimfm_fm_sgd_epoch: not implemented yet"); }
-int32_t nimfm_fm_sgd_end(nimfm_ctx *ctx, nimfm_fm *fm) { return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "nimfm_fm_sgd_end: not implemented yet"); }
-int32_t nimfm_ffm_sgd_begin(nimfm_ctx *ctx, nimfm_ffm *m) { return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "nimfm_ffm_sgd_begin: not implemented yet"); }
-int32_t nimfm_ffm_sgd_epoch(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_dataset *X, const nimfm_sgd_cfg *cfg, int64_t *it, const int64_t *perm, int64_t nRows, double *viol, double *lossSum) { return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "nimfm_ffm_sgd_epoch: not implemented yet"); }
-int32_t nimfm_ffm_sgd_end(nimfm_ctx *ctx, nimfm_ffm *m) { return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "nimfm_ffm_sgd_end: not implemented yet"); }
+
+#define SGD_THREADS 256
+
+__device__ __forceinline__ double dev_eta(int sched, double eta0, double power, double reg, int64_t it) {
+  switch (sched) {  // getEta, sgd.nim:60-69
+    case NIMFM_SCHED_CONSTANT: return eta0;
+    case NIMFM_SCHED_OPTIMAL: return eta0 / pow(1.0 + eta0 * reg * (double)it, power);
+    case NIMFM_SCHED_INVSCALING: return eta0 / pow((double)it, power);
+    default: return 1.0 / (reg * (double)it);
+  }
 }
+
+struct SgdArgs {
+  const double *data;
+  const int32_t *indices, *fields;
+  const int64_t *indptr;
+  const double *y;
+  const int32_t *perm;
+  int64_t nRows, d, dd;
+  int degree, k, nOrders, nAug, nFields;
+  int fitLinear, fitIntercept;
+  double *P, *w, *b;
+  double *scalingsP, *scalingsW, *scal;   // scal: [scaling_P, scaling_w, viol, loss]
+  double *dA;                             // FFM scratch: [zmax][nFields][k]
+  nimfm_sgd_cfg cfg;
+  int64_t it0;
+};
+
+// dense pass of finalize / resetScaling (sgd.nim:99-131).  SB8 = doubles per feature slice.
+__device__ void sgd_materialize(const SgdArgs &a, int SB8, int64_t nFeatP, bool doW, bool doP, double scP,
+                                double scW) {
+  if (doW && a.fitLinear)
+    for (int64_t j = threadIdx.x; j < a.d; j += blockDim.x) {
+      double v = a.w[j] * scW;
+      a.w[j] = v / a.scalingsW[j];
+      a.scalingsW[j] = 1.0;
+    }
+  if (doP) {
+    for (int64_t e = threadIdx.x; e < nFeatP * SB8; e += blockDim.x) {
+      const int64_t j = e / SB8;
+      a.P[e] *= scP / a.scalingsP[j];
+    }
+    __syncthreads();
+    for (int64_t j = threadIdx.x; j < a.dd; j += blockDim.x) a.scalingsP[j] = 1.0;
+  }
+  __syncthreads();
+}
+
+template <bool FFM>
+__global__ void __launch_bounds__(SGD_THREADS, 1) sgd_epoch_kernel(const SgdArgs a) {
+  __shared__ double red[SGD_THREADS / 32];
+  __shared__ double sh[4];   // yhat, scaling_P, scaling_w, dL
+  const int k = a.k;
+  const int NO = FFM ? a.nFields : a.nOrders;
+  const int SB8 = NO * k;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  double viol = 0.0, lossAcc = 0.0;
+  if (tid == 0) {
+    sh[1] = a.scal[0];
+    sh[2] = a.scal[1];
+  }
+  __syncthreads();
+  const double alpha0 = a.cfg.alpha0, alpha = a.cfg.alpha, beta = a.cfg.beta;
+  for (int64_t q = 0; q < a.nRows; ++q) {
+    const int64_t i = a.perm ? (int64_t)a.perm[q] : q;
+    const int64_t it = a.it0 + q;
+    const int64_t rb = a.indptr[i];
+    const int zReal = (int)(a.indptr[i + 1] - rb);
+    const int z = zReal + (FFM ? 0 : a.nAug);
+    const double scP = sh[1], scW = sh[2];
+    // ---- lazilyUpdate (sgd.nim:134-143): real features only
+    for (int e = tid; e < zReal * SB8; e += nth) {
+      const int u = e / SB8, off = e - u * SB8;
+      const int64_t j = a.indices[rb + u];
+      a.P[j * SB8 + off] *= scP / a.scalingsP[j];
+    }
+    if (a.fitLinear)
+      for (int u = tid; u < zReal; u += nth) {
+        const int64_t j = a.indices[rb + u];
+        a.w[j] *= scW / a.scalingsW[j];
+      }
+    __syncthreads();
+    // ---- predictWithGrad: forward
+    double part = 0.0;
+    for (int u = tid; u < zReal; u += nth) part += a.w[a.indices[rb + u]] * a.data[rb + u];
+    if (!FFM) {
+      for (int os = tid; os < SB8; os += nth) {          // thread <-> (order, component)
+        const int o = os / k, s = os - o * k;
+        const int M = a.degree - o;
+        double A[NIMFM_MAX_DEGREE + 1];
+        A[0] = 1.0;
+        for (int t = 1; t <= M; t++) A[t] = 0.0;
+        for (int u = 0; u < z; u++) {
+          const int64_t j = u < zReal ? (int64_t)a.indices[rb + u] : a.d + (u - zReal);
+          const double x = u < zReal ? a.data[rb + u] : 1.0;
+          const double tv = a.P[j * SB8 + o * k + s] * x;
+          if (M == 2) {
+            A[1] += tv;
+            A[2] += tv * tv;
+          } else {
+            for (int t = M; t >= 1; t--) A[t] += A[t - 1] * tv;
+          }
+        }
+        if (M == 2) A[2] = (A[1] * A[1] - A[2]) / 2.0;
+        part += A[M];
+      }
+    } else {
+      // dA[u][f][s] = sum_{b != u, field_b == f} x_u x_b P[j_b][f_u][s]   (sgd_ffm.nim:18-30)
+      for (int e = tid; e < zReal * SB8; e += nth) a.dA[e] = 0.0;
+      __syncthreads();
+      for (int us = tid; us < zReal * k; us += nth) {    // thread <-> (nonzero, component)
+        const int u = us / k, s = us - u * k;
+        const int fu = a.fields[rb + u];
+        const double xu = a.data[rb + u];
+        for (int v = 0; v < zReal; v++) {
+          if (v == u) continue;
+          const int64_t jv = a.indices[rb + v];
+          const int fv = a.fields[rb + v];
+          a.dA[((size_t)u * NO + fv) * k + s] += (xu * a.data[rb + v]) * a.P[jv * SB8 + fu * k + s];
+        }
+      }
+      __syncthreads();
+      double pp = 0.0;
+      for (int e = tid; e < zReal * SB8; e += nth) {
+        const int u = e / SB8, off = e - u * SB8;
+        pp += a.P[(int64_t)a.indices[rb + u] * SB8 + off] * a.dA[e];
+      }
+      part += 0.5 * pp;
+    }
+    double yhat = block_sum(part, red);
+    if (tid == 0) {
+      yhat += a.b[0];
+      sh[0] = yhat;
+      const double yi = a.y[i];
+      lossAcc += dev_loss(a.cfg.loss, a.cfg.huberThreshold, yi, yhat);
+      sh[3] = dev_dloss(a.cfg.loss, a.cfg.huberThreshold, yi, yhat);
+    }
+    __syncthreads();
+    const double dL = sh[3];
+    // ---- update (sgd.nim:205-243)
+    const double etaW = dev_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, alpha, it);
+    const double etaP = dev_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, beta, it);
+    if (!FFM) {
+      for (int os = tid; os < SB8; os += nth) {
+        const int o = os / k, s = os - o * k;
+        const int M = a.degree - o;
+        // recompute the DP state of this (order, component), then the derivative recurrence (sgd.nim:176-188)
+        double A[NIMFM_MAX_DEGREE + 1];
+        A[0] = 1.0;
+        for (int t = 1; t <= M; t++) A[t] = 0.0;
+        for (int u = 0; u < z; u++) {
+          const int64_t j = u < zReal ? (int64_t)a.indices[rb + u] : a.d + (u - zReal);
+          const double x = u < zReal ? a.data[rb + u] : 1.0;
+          const double tv = a.P[j * SB8 + o * k + s] * x;
+          if (M == 2) A[1] += tv;
+          else
+            for (int t = M; t >= 1; t--) A[t] += A[t - 1] * tv;
+        }
+        for (int u = 0; u < z; u++) {
+          const int64_t j = u < zReal ? (int64_t)a.indices[rb + u] : a.d + (u - zReal);
+          const double x = u < zReal ? a.data[rb + u] : 1.0;
+          const int64_t e = j * SB8 + o * k + s;
+          const double p = a.P[e];
+          double g;
+          if (M == 2) g = x * (A[1] - p * x);
+          else {
+            g = x;
+            for (int t = 1; t < M; t++) g = x * (A[t] - p * g);
+          }
+          const double upd = etaP * (dL * g + beta * p);
+          viol += fabs(upd);
+          a.P[e] = p - upd;
+        }
+      }
+    } else {
+      for (int e = tid; e < zReal * SB8; e += nth) {
+        const int u = e / SB8, off = e - u * SB8;
+        const int64_t pe = (int64_t)a.indices[rb + u] * SB8 + off;
+        const double p = a.P[pe];
+        const double upd = etaP * (dL * a.dA[e] + beta * p);
+        viol += fabs(upd);
+        a.P[pe] = p - upd;
+      }
+    }
+    if (a.fitLinear)                                        // fitLinearSGD, fit_linear.nim:41-47
+      for (int u = tid; u < zReal; u += nth) {
+        const int64_t j = a.indices[rb + u];
+        const double upd = etaW * (dL * a.data[rb + u] + alpha * a.w[j]);
+        a.w[j] -= upd;
+        viol += fabs(upd);
+      }
+    const double nscP = scP * (1 - etaP * beta), nscW = scW * (1 - etaW * alpha);
+    for (int u = tid; u < zReal; u += nth) {
+      const int64_t j = a.indices[rb + u];
+      a.scalingsP[j] = nscP;
+      a.scalingsW[j] = nscW;
+    }
+    if (!FFM)
+      for (int u = tid; u < a.nAug; u += nth) a.scalingsP[a.d + u] = nscP;
+    if (tid == 0) {
+      if (a.fitIntercept) {
+        const double upd = dev_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, alpha0, it) * (dL + alpha0 * a.b[0]);
+        viol += fabs(upd);
+        a.b[0] -= upd;
+      }
+      sh[1] = nscP;
+      sh[2] = nscW;
+    }
+    __syncthreads();
+    // ---- resetScaling (sgd.nim:116-131)
+    const bool resetW = a.fitLinear && nscW < 1e-9, resetP = nscP < 1e-9;
+    if (resetW || resetP) {
+      sgd_materialize(a, SB8, a.d, resetW, resetP, nscP, nscW);   // P: features 0..d-1 only (:126)
+      if (tid == 0) {
+        if (resetW) sh[2] = 1.0;
+        if (resetP) sh[1] = 1.0;
+      }
+      __syncthreads();
+    }
+  }
+  viol = block_sum(viol, red);
+  __syncthreads();
+  lossAcc = block_sum(lossAcc, red);
+  if (tid == 0) {
+    a.scal[0] = sh[1];
+    a.scal[1] = sh[2];
+    a.scal[2] = viol;
+    a.scal[3] = lossAcc;
+  }
+}
+
+// finalize (sgd.nim:99-113)
+template <bool FFM>
+__global__ void __launch_bounds__(SGD_THREADS, 1) sgd_finalize_kernel(const SgdArgs a) {
+  const int SB8 = (FFM ? a.nFields : a.nOrders) * a.k;
+  const double scP = a.scal[0], scW = a.scal[1];
+  __syncthreads();
+  if (a.fitLinear) {
+    for (int64_t j = threadIdx.x; j < a.d; j += blockDim.x) {
+      double v = a.w[j] * scW;
+      a.w[j] = v / a.scalingsW[j];
+      a.scalingsW[j] = 1.0;
+    }
+  }
+  for (int64_t e = threadIdx.x; e < a.dd * SB8; e += blockDim.x) a.P[e] *= scP / a.scalingsP[e / SB8];
+  __syncthreads();
+  for (int64_t j = threadIdx.x; j < a.dd; j += blockDim.x) a.scalingsP[j] = 1.0;
+  if (threadIdx.x == 0) {
+    if (a.fitLinear) a.scal[1] = 1.0;
+    a.scal[0] = 1.0;
+  }
+}
+
+__global__ void sgd_fill_kernel(double *p, int64_t n, double v) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) p[e] = v;
+}
+
+template <class Model>
+static int sgd_begin_common(nimfm_ctx *ctx, Model *m, int64_t dd, int64_t d) {
+  CK(cudaSetDevice(ctx->device));
+  if (!m->scalingsP) {
+    CK(cudaMalloc(&m->scalingsP, (size_t)dd * 8));
+    CK(cudaMalloc(&m->scalingsW, (size_t)d * 8));
+    CK(cudaMalloc(&m->sgdScal, 8 * 8));
+  }
+  sgd_fill_kernel<<<64, 256, 0, ctx->stream>>>(m->scalingsP, dd, 1.0);   // sgd.nim:269-272
+  sgd_fill_kernel<<<64, 256, 0, ctx->stream>>>(m->scalingsW, d, 1.0);
+  ctx->launches += 2;
+  const double sc[4] = {1.0, 1.0, 0.0, 0.0};
+  CK(cudaMemcpyAsync(m->sgdScal, sc, 32, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  m->sgdReady = true;
+  return NIMFM_OK;
+}
+
+extern "C" {
+
+int32_t nimfm_fm_sgd_begin(nimfm_ctx *ctx, nimfm_fm *fm) {
+  if (!ctx || !fm) return NIMFM_ERR_INVALID;
+  return sgd_begin_common(ctx, fm, fm->dd(), fm->d);
+}
+
+int32_t nimfm_fm_sgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, const nimfm_sgd_cfg *cfg,
+                           int64_t *it, const int64_t *perm, int64_t nRows, double *viol, double *lossSum) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  REQUIRE(fm && X && cfg && it, "NULL argument");
+  if (!fm->sgdReady) return nimfm_fail(ctx, NIMFM_ERR_STATE, "nimfm_fm_sgd_begin was not called");
+  REQUIRE(X->kind != NIMFM_DS_CSC, "a CSR dataset is required");
+  REQUIRE(X->d == fm->d, "Invalid nFeatures.");
+  REQUIRE(X->y != nullptr, "dataset has no targets");
+  REQUIRE(nRows >= 0 && (perm || nRows <= X->n), "bad nRows");
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  const int32_t *permDev = nullptr;
+  if (perm && nRows > 0) {
+    if ((rc = nimfm_stage_row_ids(ctx, perm, nRows, X->n))) return rc;
+    permDev = ctx->idx32Scratch;
+  }
+  SgdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.data = X->data; a.indices = X->indices; a.indptr = X->indptr; a.y = X->y; a.perm = permDev;
+  a.nRows = nRows; a.d = fm->d; a.dd = fm->dd();
+  a.degree = fm->degree; a.k = fm->k; a.nOrders = fm->nOrders; a.nAug = fm->nAug;
+  a.fitLinear = fm->fitLinear; a.fitIntercept = fm->fitIntercept;
+  a.P = fm->P; a.w = fm->w; a.b = fm->b;
+  a.scalingsP = fm->scalingsP; a.scalingsW = fm->scalingsW; a.scal = fm->sgdScal;
+  a.cfg = *cfg; a.it0 = *it;
+  sgd_epoch_kernel<false><<<1, SGD_THREADS, 0, ctx->stream>>>(a);
+  LAUNCHED(ctx);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctx->hostScalars, fm->sgdScal, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *it += nRows;
+  if (viol) *viol = ctx->hostScalars[2];
+  if (lossSum) *lossSum = ctx->hostScalars[3];
+  return NIMFM_OK;
+}
+
+int32_t nimfm_fm_sgd_end(nimfm_ctx *ctx, nimfm_fm *fm) {
+  if (!ctx || !fm) return NIMFM_ERR_INVALID;
+  if (!fm->sgdReady) return nimfm_fail(ctx, NIMFM_ERR_STATE, "nimfm_fm_sgd_begin was not called");
+  CK(cudaSetDevice(ctx->device));
+  SgdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.d = fm->d; a.dd = fm->dd(); a.k = fm->k; a.nOrders = fm->nOrders; a.fitLinear = fm->fitLinear;
+  a.P = fm->P; a.w = fm->w; a.scalingsP = fm->scalingsP; a.scalingsW = fm->scalingsW; a.scal = fm->sgdScal;
+  sgd_finalize_kernel<false><<<1, SGD_THREADS, 0, ctx->stream>>>(a);
+  LAUNCHED(ctx);
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  return NIMFM_OK;
+}
+
+int32_t nimfm_ffm_sgd_begin(nimfm_ctx *ctx, nimfm_ffm *m) {
+  if (!ctx || !m) return NIMFM_ERR_INVALID;
+  return sgd_begin_common(ctx, m, m->d, m->d);
+}
+
+int32_t nimfm_ffm_sgd_epoch(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_dataset *X, const nimfm_sgd_cfg *cfg,
+                            int64_t *it, const int64_t *perm, int64_t nRows, double *viol, double *lossSum) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  REQUIRE(m && X && cfg && it, "NULL argument");
+  if (!m->sgdReady) return nimfm_fail(ctx, NIMFM_ERR_STATE, "nimfm_ffm_sgd_begin was not called");
+  REQUIRE(X->kind == NIMFM_DS_CSR_FIELD, "a CSRFieldDataset is required");
+  REQUIRE(X->d == m->d, "Invalid nFeatures.");
+  REQUIRE(X->nFields == m->nFields, "Invalid nFields.");
+  REQUIRE(X->y != nullptr, "dataset has no targets");
+  REQUIRE(nRows >= 0 && (perm || nRows <= X->n), "bad nRows");
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  const int32_t *permDev = nullptr;
+  if (perm && nRows > 0) {
+    if ((rc = nimfm_stage_row_ids(ctx, perm, nRows, X->n))) return rc;
+    permDev = ctx->idx32Scratch;
+  }
+  double *dA = nullptr;
+  const size_t dAn = (size_t)std::max<int64_t>(X->maxSegNnz, 1) * m->nFields * m->k;
+  CK(cudaMalloc(&dA, dAn * 8));
+  SgdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.data = X->data; a.indices = X->indices; a.fields = X->fields; a.indptr = X->indptr; a.y = X->y; a.perm = permDev;
+  a.nRows = nRows; a.d = m->d; a.dd = m->d;
+  a.k = m->k; a.nFields = (int)m->nFields;
+  a.fitLinear = m->fitLinear; a.fitIntercept = m->fitIntercept;
+  a.P = m->P; a.w = m->w; a.b = m->b;
+  a.scalingsP = m->scalingsP; a.scalingsW = m->scalingsW; a.scal = m->sgdScal; a.dA = dA;
+  a.cfg = *cfg; a.it0 = *it;
+  sgd_epoch_kernel<true><<<1, SGD_THREADS, 0, ctx->stream>>>(a);
+  LAUNCHED(ctx);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctx->hostScalars, m->sgdScal, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaFree(dA));
+  *it += nRows;
+  if (viol) *viol = ctx->hostScalars[2];
+  if (lossSum) *lossSum = ctx->hostScalars[3];
+  return NIMFM_OK;
+}
+
+int32_t nimfm_ffm_sgd_end(nimfm_ctx *ctx, nimfm_ffm *m) {
+  if (!ctx || !m) return NIMFM_ERR_INVALID;
+  if (!m->sgdReady) return nimfm_fail(ctx, NIMFM_ERR_STATE, "nimfm_ffm_sgd_begin was not called");
+  CK(cudaSetDevice(ctx->device));
+  SgdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.d = m->d; a.dd = m->d; a.k = m->k; a.nFields = (int)m->nFields; a.fitLinear = m->fitLinear;
+  a.P = m->P; a.w = m->w; a.scalingsP = m->scalingsP; a.scalingsW = m->scalingsW; a.scal = m->sgdScal;
+  sgd_finalize_kernel<true><<<1, SGD_THREADS, 0, ctx->stream>>>(a);
+  LAUNCHED(ctx);
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  return NIMFM_OK;
+}
+
+}  // extern "C"
