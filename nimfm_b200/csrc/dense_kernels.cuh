@@ -1,0 +1,148 @@
+// dense_kernels.cuh -- small dense / reduction kernels shared by the FM and FFM entry points:
+// fixed-order partial reduction, the MBPSGD dense step (K3) and the AdaGrad dense passes (K5).
+#pragma once
+#include "common.cuh"
+
+static inline int ew_grid(nimfm_ctx *ctx, int64_t n, int block = 256) {
+  int64_t g = (n + block - 1) / block;
+  int64_t cap = (int64_t)ctx->numSMs * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ------------------------------------------------------------------ small reductions
+// sums partials[nRows4][4] column-wise in a fixed order; out[c] (+)= sum
+static __global__ void reduce_partials_kernel(const double *partials, int64_t rows, double *out, int accumulate) {
+  __shared__ double red[8];
+  double acc[4] = {0, 0, 0, 0};
+  for (int64_t r = threadIdx.x; r < rows; r += blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) acc[c] += partials[r * 4 + c];
+  }
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    double v = block_sum(acc[c], red);
+    if (threadIdx.x == 0) out[c] = accumulate ? out[c] + v : v;
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ MBPSGD dense step (K3)
+// Params.step (params.nim:90-98) = add (:33-48) then scale (:61-66), the prox of
+// minibatch_psgd.nim:119-121, and "grads <- 0" (:99) for the next minibatch, in one pass.
+// tail = [gb, lossSum] (already all-reduced).  scal[0] accumulates the epoch's loss sum.
+static __global__ void mbpsgd_step_kernel(double *P, double *gP, int64_t nP, double negEtaP, double rP, int reg,
+                                   double lam, double *w, double *gw, int64_t d, double negEtaW, double rW,
+                                   int fitLinear, double *b, double *tail, double negEtaB, double rB,
+                                   int fitIntercept, double *scal) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (int64_t e = tid; e < nP; e += stride) {
+    double p = P[e] + negEtaP * gP[e];
+    p *= rP;
+    if (reg == NIMFM_REG_L1) {  // softthreshold, regularizer/utils.nim:4-5
+      const double m = fabs(p) - lam;
+      p = (p > 0 ? 1.0 : (p < 0 ? -1.0 : 0.0)) * (m > 0.0 ? m : 0.0);
+    }
+    P[e] = p;
+    gP[e] = 0.0;
+  }
+  if (fitLinear)
+    for (int64_t e = tid; e < d; e += stride) {
+      double v = w[e] + negEtaW * gw[e];
+      w[e] = v * rW;
+      gw[e] = 0.0;
+    }
+  else
+    for (int64_t e = tid; e < d; e += stride) gw[e] = 0.0;
+  if (tid == 0) {
+    double bb = b[0];
+    if (fitIntercept && fitLinear) bb += negEtaB * tail[0];  // params.nim:47 (quirk: needs grad.fitLinear)
+    if (fitIntercept) bb *= rB;                              // params.nim:65-66
+    b[0] = bb;
+    scal[0] += tail[1];
+    tail[0] = 0.0;
+    tail[1] = 0.0;
+  }
+}
+
+// ------------------------------------------------------------------ AdaGrad dense kernels (K5)
+// after a minibatch: refresh P/w for touched features from the OLD state (adagrad.nim:87-110),
+// then g_sum += dGs, g_norm += dGn, and clear the deltas.
+static __global__ void adagrad_apply_kernel(double *P, double *gsP, double *gnP, double *dGsP, double *dGnP,
+                                     int64_t dd, int SB8, const double *touched, double *w, double *gsw,
+                                     double *gnw, double *dGsw, double *dGnw, int64_t d, int fitLinear,
+                                     double eta0, double tIt, double alpha, double beta, int first) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t nP = dd * SB8;
+  const double tmpP = eta0 * tIt * beta;
+  for (int64_t e = tid; e < nP; e += stride) {
+    const int64_t j = e / SB8;
+    const double gs = gsP[e], gn = gnP[e];
+    if (!first && touched[j] != 0.0) P[e] = -(eta0 * gs) / (tmpP + sqrt(gn));
+    gsP[e] = gs + dGsP[e];
+    gnP[e] = gn + dGnP[e];
+    dGsP[e] = 0.0;
+    dGnP[e] = 0.0;
+  }
+  const double denW = tIt * eta0 * alpha;
+  for (int64_t j = tid; j < d; j += stride) {
+    const double gs = gsw[j], gn = gnw[j];
+    if (fitLinear) {
+      if (!first && touched[j] != 0.0) w[j] = -eta0 * gs / (denW + sqrt(gn));
+      gsw[j] = gs + dGsw[j];
+      gnw[j] = gn + dGnw[j];
+    }
+    dGsw[j] = 0.0;
+    dGnw[j] = 0.0;
+  }
+}
+// intercept part of update()/updateG() (adagrad.nim:101-105,126-128) + epoch accumulators.
+// part = [loss, sum dL, sum dL^2, viol] of the batch (all-reduced); scal = [lossEpoch, violEpoch]
+static __global__ void adagrad_scalar_kernel(double *b, double *adaScal, const double *part, double *scal,
+                                      int fitIntercept, double eta0, double tIt, double alpha0, int first) {
+  double viol = part[3];
+  if (fitIntercept) {
+    if (!first) {
+      const double old = b[0];
+      const double den = sqrt(adaScal[1]) + eta0 * tIt * alpha0;
+      const double nb = -eta0 * adaScal[0] / den;
+      viol += fabs(old - nb);
+      b[0] = nb;
+    }
+    adaScal[0] += part[1];
+    adaScal[1] += part[2];
+  }
+  scal[0] += part[0];
+  scal[1] += viol;
+}
+// AdaGrad.finalize (adagrad.nim:65-84)
+static __global__ void adagrad_finalize_kernel(double *P, const double *gsP, const double *gnP, int64_t nP, double *w,
+                                        const double *gsw, const double *gnw, int64_t d, int fitLinear,
+                                        double *b, const double *adaScal, int fitIntercept, double eta0,
+                                        double tIt, double alpha0, double alpha, double beta) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const double denP = eta0 * tIt * beta;
+  for (int64_t e = tid; e < nP; e += stride) P[e] = (-eta0 * gsP[e]) / (denP + sqrt(gnP[e]));
+  if (fitLinear) {
+    const double denW = eta0 * tIt * alpha;
+    for (int64_t j = tid; j < d; j += stride) w[j] = (-eta0 * gsw[j]) / (denW + sqrt(gnw[j]));
+  }
+  if (tid == 0 && fitIntercept) {
+    const double den = sqrt(adaScal[1]) + eta0 * tIt * alpha0;
+    b[0] = -eta0 * adaScal[0] / den;
+  }
+}
+static __global__ void fill_kernel(double *p, int64_t n, double v) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) p[e] = v;
+}
+
+
+// tail[0] (gb) += sum coef, tail[1] (loss) += sum loss; red4 = reduce_partials output
+static __global__ void add_tail_kernel(double *tail, const double *red4) {
+  tail[0] += red4[1];
+  tail[1] += red4[0];
+}

@@ -1,0 +1,194 @@
+"""Parity of the FFM kernels (K10/K11) and of the sequential SGD kernels (K6) against the CPU oracle,
+through the C ABI.  Shapes follow tests/test_sgd_ffm.nim:10-14 (n=80, d=20, 5 fields, k=4) and
+tests/test_sgd.nim:10-13 (n=80, d=8, k=4)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import nimfm_b200 as nf
+from nimfm_b200 import _lib
+from oracle import bruteforce as bf
+from oracle.oracle import CSR
+from helpers import make_dense, make_fm_params, make_field_csr, max_rel
+
+pytestmark = pytest.mark.gpu
+
+DEC_TOL, OBJ_TOL = 1e-10, 1e-8
+
+
+def field_ds(csr):
+    return nf.newCSRFieldDataset(csr.data, csr.indices, csr.indptr, csr.fields, csr.n, csr.d, csr.n_fields)
+
+
+def make_ffm(P, w, b, fit_linear=True, fit_intercept=True, task=nf.regression):
+    m = nf.newFieldAwareFactorizationMachine(task, nComponents=P.shape[2], fitLinear=fit_linear,
+                                             fitIntercept=fit_intercept, warmStart=True)
+    m.P, m.w, m.intercept, m.isInitialized = P.copy(), w.copy(), b, True
+    return m
+
+
+def one_per_field_csr(n, n_fields, per_field, seed):
+    """libffm / C5 shape: exactly one feature per field, field f owns ids [f*per_field, (f+1)*per_field)"""
+    rng = np.random.default_rng(seed)
+    idx = rng.integers(0, per_field, size=(n, n_fields)) + (np.arange(n_fields) * per_field)[None, :]
+    data = np.where(rng.random((n, n_fields)) < 0.5, 1.0, rng.random((n, n_fields)))
+    csr = CSR(data.ravel(), idx.ravel(), np.arange(n + 1) * n_fields, n, n_fields * per_field,
+              fields=np.tile(np.arange(n_fields), n), n_fields=n_fields)
+    return csr
+
+
+@pytest.mark.parametrize("k", [4, 8, 5])
+def test_ffm_decision_function(oracle, k):
+    n, d, nF = 80, 20, 5
+    X, csr, field_of = make_field_csr(n, d, nF, 7)
+    rng = np.random.default_rng(k)
+    P = rng.standard_normal((nF, d, k)) * 0.3
+    w = rng.standard_normal(d) * 0.1
+    m = make_ffm(P, w, -0.2)
+    got = m.decisionFunction(field_ds(csr))
+    assert max_rel(got, oracle.ffm_decision_function(csr, P, w, -0.2)) <= DEC_TOL
+    # and straight against the definition (tests/model/ffm_slow.nim:38-56)
+    np.testing.assert_allclose(got[:10], bf.ffm_decision_function(X[:10], field_of, P, w, -0.2), rtol=1e-9, atol=1e-12)
+
+
+def test_ffm_decision_function_one_feature_per_field(oracle):
+    n, nF, per, k = 500, 39, 50, 8            # C5 row shape: 39 fields, rank 8
+    csr = one_per_field_csr(n, nF, per, 3)
+    rng = np.random.default_rng(0)
+    P = rng.standard_normal((nF, nF * per, k)) * 0.1
+    w = rng.standard_normal(nF * per) * 0.1
+    m = make_ffm(P, w, 0.3)
+    got = m.decisionFunction(field_ds(csr))
+    assert max_rel(got, oracle.ffm_decision_function(csr, P, w, 0.3)) <= DEC_TOL
+
+
+def test_ffm_errors():
+    X, csr, _ = make_field_csr(10, 20, 5, 1)
+    P = np.zeros((4, 20, 3))                 # wrong nFields
+    m = make_ffm(P, np.zeros(20), 0.0)
+    with pytest.raises(ValueError):
+        m.decisionFunction(field_ds(csr))
+
+
+def ffm_dev_loss_grad(m, ds, y, loss, mb=None):
+    lib, ctx = _lib.load(), _lib.ctx()
+    ds.set_targets(y)
+    h = m._to_device(ds)
+    try:
+        n = ds.nSamples
+        ls = C.c_double()
+        _lib.check(lib.nimfm_ffm_loss_grad(ctx, h, ds.handle(), loss.kind, loss.threshold, 0, n, None,
+                                           n if mb is None else mb, 1, 0, C.byref(ls)))
+        gP, gw, gb = np.zeros_like(m.P), np.zeros(ds.nFeatures), C.c_double()
+        _lib.check(lib.nimfm_ffm_get_grads(ctx, h, _lib.ptr(gP), _lib.ptr(gw), C.byref(gb)))
+    finally:
+        lib.nimfm_ffm_free(ctx, h)
+    return ls.value, gP, gw, gb.value
+
+
+@pytest.mark.parametrize("shape", ["dense_fields", "one_per_field"])
+@pytest.mark.parametrize("loss_name", ["squared", "logistic"])
+def test_ffm_loss_grad(oracle, shape, loss_name):
+    if shape == "dense_fields":
+        X, csr, _ = make_field_csr(80, 20, 5, 11)
+        k = 4
+    else:
+        csr = one_per_field_csr(200, 13, 20, 5)
+        k = 8
+    rng = np.random.default_rng(2)
+    P = rng.standard_normal((csr.n_fields, csr.d, k)) * 0.2
+    w = rng.standard_normal(csr.d) * 0.1
+    y = rng.standard_normal(csr.n) if loss_name == "squared" else np.sign(rng.standard_normal(csr.n))
+    m = make_ffm(P, w, 0.1)
+    loss = nf.Squared() if loss_name == "squared" else nf.Logistic()
+    ls, gP, gw, gb = ffm_dev_loss_grad(m, field_ds(csr), y, loss)
+    ref = oracle.ffm_loss_grad(csr, y, P, w, 0.1, loss_name)
+    assert abs(ls - ref["loss"]) <= 1e-10 * max(1.0, abs(ref["loss"]))
+    assert max_rel(gP, ref["gP"]) <= 1e-9
+    assert max_rel(gw, ref["gw"]) <= 1e-9
+    assert abs(gb - ref["gb"]) <= 1e-10 * max(1.0, abs(ref["gb"]))
+
+
+@pytest.mark.parametrize("mb", [1, 8])
+def test_ffm_adagrad(oracle, mb):
+    """tests/test_adagrad_ffm.nim: naive comparison with shuffle=false (mb=1 == reference semantics)"""
+    X, csr, _ = make_field_csr(80, 20, 5, 13)
+    k = 4
+    rng = np.random.default_rng(3)
+    P = rng.standard_normal((5, 20, k)) * 0.1
+    w = np.zeros(20)
+    y = rng.standard_normal(80)
+    ref = oracle.ffm_adagrad_fit(csr, y, P, w, 0.0, "squared", max_iter=3, mini_batch_size=mb)
+    m = make_ffm(P, w, 0.0)
+    opt = nf.newAdaGrad(maxIter=3, verbose=0, tol=0.0, shuffle=False, miniBatchSize=mb)
+    opt.fit(field_ds(csr), y, m)
+    np.testing.assert_allclose([h[1] for h in opt.history], ref["loss"], rtol=OBJ_TOL)
+    np.testing.assert_allclose([h[0] for h in opt.history], ref["viol"], rtol=1e-8)
+    np.testing.assert_allclose(m.P, ref["P"], rtol=1e-8, atol=1e-13)
+    np.testing.assert_allclose(m.w, ref["w"], rtol=1e-8, atol=1e-13)
+    assert abs(m.intercept - ref["intercept"]) <= 1e-9
+    assert opt.it == ref["it"]
+
+
+def test_ffm_sgd(oracle):
+    """tests/test_sgd_ffm.nim:87-115"""
+    X, csr, _ = make_field_csr(80, 20, 5, 17)
+    k = 4
+    rng = np.random.default_rng(4)
+    P = rng.standard_normal((5, 20, k)) * 0.1
+    w = rng.standard_normal(20) * 0.1
+    y = rng.standard_normal(80)
+    ref = oracle.ffm_sgd_fit(csr, y, P, w, 0.0, "squared", max_iter=4)
+    m = make_ffm(P, w, 0.0)
+    opt = nf.newSGD(maxIter=4, verbose=0, tol=0.0, shuffle=False)
+    opt.fit(field_ds(csr), y, m)
+    np.testing.assert_allclose([h[1] for h in opt.history], ref["loss"], rtol=OBJ_TOL)
+    np.testing.assert_allclose([h[0] for h in opt.history], ref["viol"], rtol=1e-8)
+    np.testing.assert_allclose(m.P, ref["P"], rtol=1e-8, atol=1e-13)
+    np.testing.assert_allclose(m.w, ref["w"], rtol=1e-8, atol=1e-13)
+    assert abs(m.intercept - ref["intercept"]) <= 1e-9
+
+
+@pytest.mark.parametrize("degree,fit_lower", [(2, "explicit"), (3, "explicit"), (3, "augment"), (4, "none"), (4, "explicit")])
+@pytest.mark.parametrize("sched", ["optimal", "constant", "invscaling"])
+def test_fm_sgd(oracle, degree, fit_lower, sched):
+    """tests/test_sgd.nim:92-126: SGD with lazy scaling and the step-size schedules of sgd.nim:60-69
+    (pegasos is left out: eta*reg == 1 at it == 1 zeroes scaling_P, and the reference itself goes NaN)"""
+    n, d, k = 80, 8, 4
+    X = make_dense(n, d, 21, density=0.5, positive=False)
+    y = np.random.default_rng(5).standard_normal(n)
+    csr = CSR.from_dense(X)
+    P, w, nA = make_fm_params(d, degree, k, fit_lower, True, seed=7, scale=0.1)
+    kw = dict(eta0=0.01, alpha0=1e-6, alpha=1e-3, beta=1e-3, power=0.75 if sched == "invscaling" else 1.0)
+    ref = oracle.sgd_fit(csr, y, P, w, 0.0, degree, "squared", max_iter=4, scheduling=sched, **kw)
+    fm = nf.newFactorizationMachine(nf.regression, degree=degree, nComponents=k, fitLower=fit_lower, warmStart=True)
+    fm.P, fm.w, fm.intercept, fm.isInitialized = P.copy(), w.copy(), 0.0, True
+    opt = nf.newSGD(maxIter=4, verbose=0, tol=0.0, shuffle=False, scheduling=sched, **kw)
+    opt.fit(nf.newCSRDataset(csr.data, csr.indices, csr.indptr, n, d), y, fm)
+    np.testing.assert_allclose([h[1] for h in opt.history], ref["loss"], rtol=OBJ_TOL)
+    np.testing.assert_allclose([h[0] for h in opt.history], ref["viol"], rtol=1e-8)
+    np.testing.assert_allclose(fm.P, ref["P"], rtol=1e-8, atol=1e-13)
+    np.testing.assert_allclose(fm.w, ref["w"], rtol=1e-8, atol=1e-13)
+    assert abs(fm.intercept - ref["intercept"]) <= 1e-9
+    assert opt.it == ref["it"]
+
+
+def test_fm_sgd_reset_scaling_and_perms(oracle):
+    """strong L2 + large eta drive scaling_P below 1e-9 so resetScaling (sgd.nim:116-131) fires; the
+    host-supplied permutation replaces Nim's shuffle"""
+    n, d, k, degree = 60, 6, 3, 2
+    X = make_dense(n, d, 23, density=0.7, positive=False)
+    y = np.random.default_rng(6).standard_normal(n)
+    csr = CSR.from_dense(X)
+    P, w, _ = make_fm_params(d, degree, k, "explicit", True, seed=8, scale=0.1)
+    kw = dict(eta0=0.5, alpha0=1e-6, alpha=0.6, beta=0.6, scheduling="constant")
+    perms = np.array([np.random.default_rng(s).permutation(n) for s in range(3)])
+    ref = oracle.sgd_fit(csr, y, P, w, 0.0, degree, "squared", max_iter=3, perms=perms, **kw)
+    fm = nf.newFactorizationMachine(nf.regression, degree=degree, nComponents=k, warmStart=True)
+    fm.P, fm.w, fm.intercept, fm.isInitialized = P.copy(), w.copy(), 0.0, True
+    opt = nf.newSGD(maxIter=3, verbose=0, tol=0.0, **kw)
+    opt.fit(nf.newCSRDataset(csr.data, csr.indices, csr.indptr, n, d), y, fm, perms=perms)
+    np.testing.assert_allclose([h[1] for h in opt.history], ref["loss"], rtol=OBJ_TOL)
+    np.testing.assert_allclose(fm.P, ref["P"], rtol=1e-8, atol=1e-13)
+    np.testing.assert_allclose(fm.w, ref["w"], rtol=1e-8, atol=1e-13)
