@@ -1,8 +1,460 @@
-// TEMPORARY stubs (replaced as the kernels land)
-#include "common.cuh"
-extern "C" {
-int32_t nimfm_fm_cd_begin(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *Xcsc, const nimfm_cd_cfg *cfg) { return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "nimfm_fm_cd_begin: not implemented yet"); }
-int32_t nimfm_fm_cd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *Xcsc, const nimfm_cd_cfg *cfg, double *viol, double *lossMean, double *regOverN) { return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "nimfm_fm_cd_epoch: not implemented yet"); }
-int32_t nimfm_fm_cd_get_ypred(nimfm_ctx *ctx, nimfm_fm *fm, double *yPred) { return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "nimfm_fm_cd_get_ypred: not implemented yet"); }
-int32_t nimfm_fm_cd_end(nimfm_ctx *ctx, nimfm_fm *fm) { return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "nimfm_fm_cd_end: not implemented yet"); }
+// cd.cu -- coordinate descent for FM / HOFM on ONE GPU (optimizer/cd.nim:29-194,
+// optimizer/fit_linear.nim:5-38), SURVEY K7-K9.
+//
+// The coordinate loop is sequential over (order, component s, column j): update j+1 reads the
+// yPred / A-cache entries update j wrote.  The parallelism that preserves the reference's results is
+//   (1) inside a column: the reduction  sum_i dloss_i*dA_i , sum_i dA_i^2  and the in-place refresh
+//       of A[i, 1..m], yPred[i] over the column's rows (one warp, or one block for long columns);
+//   (2) across CONSECUTIVE columns whose row supports are pairwise disjoint: update j only touches
+//       yPred[i], A[i,:] of its own rows (cd.nim:41-44,67-73), so such a run can be updated
+//       concurrently with results identical to the sequential order.  The runs ("batches") are
+//       found once per dataset (all user columns, then all item columns, for one-hot user+item data).
+// One kernel launch per batch; the A-cache rebuild per component (cd.nim:58 / :85-88) is a
+// row-parallel kernel over a CSR twin of the data, visiting each row's nonzeros in ascending column
+// order exactly like the reference's column sweep does.
+// P stays in the reference's component-major layout P[o][s][j] here (cd.fit does not transpose).
+#include <math.h>
+
+#include <algorithm>
+
+#include "dense_kernels.cuh"
+
+int nimfm_fm_predict_device(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *Xcsr, double *dOut);
+
+#define CD_MAXDEG NIMFM_MAX_DEGREE
+
+struct CdState {
+  nimfm_dataset *csr = nullptr;          // row-major twin (A-cache builds)
+  std::vector<int64_t> batchStart;       // column batches over [0, d): batch b = [batchStart[b], batchStart[b+1])
+  std::vector<int64_t> batchMaxLen;
+  double *updAbs = nullptr;              // |update| of every coordinate step of one epoch (fixed-order viol sum)
+  int64_t updCap = 0;
+  double alpha0 = 0, alpha = 0, beta = 0;  // already multiplied by nSamples (cd.nim:123-125)
+};
+
+// cdScal layout: [0] viol, [1] loss mean, [2] reg/n, [3] sum dloss, [4] |w|^2, [5] |P|^2
+static std::vector<std::pair<nimfm_fm *, CdState *>> g_cd;   // small registry: fm -> CD state
+
+static CdState *cd_state(nimfm_fm *fm, bool create) {
+  for (auto &p : g_cd)
+    if (p.first == fm) return p.second;
+  if (!create) return nullptr;
+  g_cd.push_back({fm, new CdState()});
+  return g_cd.back().second;
 }
+
+// ------------------------------------------------------------------ layout: device P[j][o][s] <-> Pcm[o][s][j]
+static __global__ void cd_permute_kernel(double *D, double *R, int nO, int k, int64_t dd, int toCm) {
+  const int64_t total = (int64_t)nO * k * dd;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = e % dd;
+    const int64_t t = e / dd;
+    const int s = (int)(t % k), o = (int)(t / k);     // e indexes Pcm
+    const int64_t de = (j * nO + o) * k + s;
+    if (toCm) R[e] = D[de];
+    else D[de] = R[e];
+  }
+}
+
+// ------------------------------------------------------------------ reductions over rows
+static __global__ void cd_sum_dloss_kernel(const double *y, const double *yPred, int64_t n, int loss, double thr,
+                                           double *partials) {
+  __shared__ double red[8];
+  double acc = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    acc += dev_dloss(loss, thr, y[i], yPred[i]);
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+static __global__ void cd_sum_loss_kernel(const double *y, const double *yPred, int64_t n, int loss, double thr,
+                                          double *partials) {
+  __shared__ double red[8];
+  double acc = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    acc += dev_loss(loss, thr, y[i], yPred[i]);
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+static __global__ void cd_sumsq_kernel(const double *v, int64_t n, double *partials) {
+  __shared__ double red[8];
+  double acc = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    acc += v[i] * v[i];
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+// out[slot] = sum of partials[0..m) in a fixed order (one block)
+static __global__ void cd_final_sum_kernel(const double *partials, int64_t m, double *out, int slot) {
+  __shared__ double red[8];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < m; i += blockDim.x) acc += partials[i];
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) out[slot] = acc;
+}
+
+// fitInterceptCD (fit_linear.nim:28-38) after the dloss sum is in scal[3]
+static __global__ void cd_intercept_kernel(double *b, double *yPred, int64_t n, double alpha0, double mu, double *scal,
+                                           double *updAbs) {
+  const double r = (alpha0 * b[0] + scal[3]) / (mu * (double)n + alpha0);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    yPred[i] -= r;
+  if (blockIdx.x == 0 && threadIdx.x == 0) updAbs[0] = fabs(r);
+}
+static __global__ void cd_intercept_commit_kernel(double *b, double alpha0, double mu, int64_t n, const double *scal) {
+  b[0] -= (alpha0 * b[0] + scal[3]) / (mu * (double)n + alpha0);
+}
+
+// colNormSq = norm(X, 2, axis=0)^2 (cd.nim:141-142, extmath.nim:151-163): one warp per column
+static __global__ void cd_colnorm_kernel(const double *data, const int64_t *indptr, int64_t d, double *out) {
+  const int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (j >= d) return;
+  double acc = 0.0;
+  for (int64_t e = indptr[j] + lane; e < indptr[j + 1]; e += 32) acc += data[e] * data[e];
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    const double nr = sqrt(acc);
+    out[j] = nr * nr;
+  }
+}
+
+// ------------------------------------------------------------------ A-cache build (kernels.anova for one component)
+// thread per row over the CSR twin; dummy features (d+a, 1.0) follow the row (dataset.nim:182-189)
+static __global__ void cd_cache_kernel(const double *data, const int32_t *indices, const int64_t *indptr, int64_t n,
+                                       int64_t d, int nAug, const double *Ps, int deg, double *A, int astride) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double a[CD_MAXDEG + 1];
+    a[0] = 1.0;
+    for (int t = 1; t <= deg; t++) a[t] = 0.0;
+    const int64_t rb = indptr[i], re = indptr[i + 1];
+    for (int64_t q = rb; q < re + nAug; q++) {
+      const double p = q < re ? Ps[indices[q]] : Ps[d + (q - re)];
+      const double x = q < re ? data[q] : 1.0;
+      if (deg == 2) {
+        a[1] += x * p;                     // cacheDeg2[i] += val * P[s, j]   (cd.nim:85-88)
+      } else {
+        const double t = p * x;
+        for (int tt = deg; tt >= 1; tt--) a[tt] += a[tt - 1] * t;   // kernels.nim:31-35
+      }
+    }
+    for (int t = 0; t <= deg; t++) A[i * astride + t] = a[t];
+  }
+}
+
+// ------------------------------------------------------------------ one batch of coordinate updates
+struct CdColArgs {
+  const double *data;
+  const int32_t *rows;
+  const int64_t *indptr;
+  const double *y;
+  double *yPred, *A, *Ps, *updAbs;   // Ps: the parameter row being swept (P[o][s][:] or w); updAbs indexed by column
+  const double *colNormSq;
+  int64_t n, d, j0, j1;
+  int astride, deg;      // deg: 0 = linear term, 2 = epochDeg2, >2 = epoch
+  int loss;
+  double thr, mu, reg;   // reg: alpha (linear) or beta (already n-scaled)
+};
+
+template <bool BLOCK_PER_COL>
+static __global__ void cd_col_kernel(const CdColArgs a) {
+  __shared__ double red[32];
+  __shared__ double sh[2];
+  const int lane = threadIdx.x & 31;
+  int64_t j;
+  int tpos, tstep;
+  if (BLOCK_PER_COL) {
+    j = a.j0 + blockIdx.x;
+    tpos = threadIdx.x;
+    tstep = blockDim.x;
+  } else {
+    j = a.j0 + ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+    tpos = lane;
+    tstep = 32;
+  }
+  if (j >= a.j1) return;
+  const bool dummy = j >= a.d;                      // dummy column: every row, value 1.0 (dataset.nim:245-252)
+  const int64_t cb = dummy ? 0 : a.indptr[j];
+  const int64_t len = dummy ? a.n : a.indptr[j + 1] - cb;
+  const double psj = a.Ps[j];
+  const int deg = a.deg;
+  // ---- pass 1: gradient and curvature (update(), cd.nim:36-47 / cd.nim:93-97 / fit_linear.nim:14-17)
+  double upd = 0.0, inv = 0.0;
+  for (int64_t e = tpos; e < len; e += tstep) {
+    const int64_t i = dummy ? e : (int64_t)a.rows[cb + e];
+    const double x = dummy ? 1.0 : a.data[cb + e];
+    double g;
+    if (deg == 0) {
+      g = x;
+    } else if (deg == 2) {
+      g = (a.A[i * a.astride + 1] - psj * x) * x;
+    } else {
+      g = x;                                         // computeDerivative, cd.nim:29-33
+      for (int t = 1; t < deg; t++) g = x * (a.A[i * a.astride + t] - psj * g);
+    }
+    upd += dev_dloss(a.loss, a.thr, a.y[i], a.yPred[i]) * g;
+    inv += g * g;
+  }
+  if (BLOCK_PER_COL) {
+    upd = block_sum(upd, red);
+    __syncthreads();
+    inv = block_sum(inv, red);
+    if (threadIdx.x == 0) {
+      sh[0] = upd;
+      sh[1] = inv;
+    }
+    __syncthreads();
+    upd = sh[0];
+    inv = sh[1];
+  } else {
+    upd = warp_sum(upd);
+    inv = warp_sum(inv);
+  }
+  upd += a.reg * psj;
+  if (deg == 0) inv = a.mu * a.colNormSq[j] + a.reg;   // fit_linear.nim:18
+  else inv = inv * a.mu + a.reg;
+  const bool leader = BLOCK_PER_COL ? threadIdx.x == 0 : lane == 0;
+  if (deg <= 2 && inv < 1e-12) {                       // guard exists only in epochDeg2 / fitLinearCD
+    if (leader) a.updAbs[j] = 0.0;
+    return;
+  }
+  const double u = upd / inv;
+  // ---- pass 2: in-place refresh over the column (cd.nim:67-73 / :104-106 / fit_linear.nim:24-25)
+  for (int64_t e = tpos; e < len; e += tstep) {
+    const int64_t i = dummy ? e : (int64_t)a.rows[cb + e];
+    const double x = dummy ? 1.0 : a.data[cb + e];
+    if (deg == 0) {
+      a.yPred[i] -= u * x;
+    } else if (deg == 2) {
+      double *c = a.A + i * a.astride + 1;
+      a.yPred[i] -= u * (*c - psj * x) * x;
+      *c -= u * x;
+    } else {
+      double *Ai = a.A + i * a.astride;
+      double prev = x;                                 // dA[0]
+      for (int t = 1; t < deg; t++) {
+        const double cur = x * (Ai[t] - psj * prev);   // dA[t] from the OLD A[i,t]
+        Ai[t] -= u * prev;
+        prev = cur;
+      }
+      Ai[deg] -= u * prev;
+      a.yPred[i] -= u * prev;
+    }
+  }
+  if (leader) {
+    a.Ps[j] = psj - u;
+    a.updAbs[j] = fabs(u);
+  }
+}
+
+static int cd_reduce(nimfm_ctx *ctx, int kind, const double *v0, const double *v1, int64_t n, int loss, double thr,
+                     double *scal, int slot) {
+  const int grid = (int)std::min<int64_t>(1024, std::max<int64_t>(1, (n + 255) / 256));
+  int rc = nimfm_ensure_partials(ctx, 1024);
+  if (rc) return rc;
+  if (kind == 0) cd_sum_dloss_kernel<<<grid, 256, 0, ctx->stream>>>(v0, v1, n, loss, thr, ctx->partials);
+  else if (kind == 1) cd_sum_loss_kernel<<<grid, 256, 0, ctx->stream>>>(v0, v1, n, loss, thr, ctx->partials);
+  else cd_sumsq_kernel<<<grid, 256, 0, ctx->stream>>>(v0, n, ctx->partials);
+  cd_final_sum_kernel<<<1, 256, 0, ctx->stream>>>(ctx->partials, grid, scal, slot);
+  ctx->launches += 2;
+  return NIMFM_OK;
+}
+
+static int cd_sweep(nimfm_ctx *ctx, CdState *st, const nimfm_dataset *X, nimfm_fm *fm, const nimfm_cd_cfg *cfg,
+                    double *Ps, int deg, double reg, double *updAbs, int64_t nCols) {
+  // nCols == d for the linear sweep (dummy features removed, cd.nim:159), d + nAug otherwise
+  CdColArgs a;
+  memset(&a, 0, sizeof(a));
+  a.data = X->data; a.rows = X->indices; a.indptr = X->indptr; a.y = X->y;
+  a.yPred = fm->yPred; a.A = fm->Acache; a.Ps = Ps; a.updAbs = updAbs; a.colNormSq = fm->colNormSq;
+  a.n = X->n; a.d = X->d; a.astride = fm->degree + 1; a.deg = deg;
+  a.loss = cfg->loss; a.thr = cfg->huberThreshold; a.mu = loss_mu(cfg->loss); a.reg = reg;
+  const size_t nb = st->batchStart.size() - 1;
+  for (size_t b = 0; b < nb; b++) {
+    a.j0 = st->batchStart[b];
+    a.j1 = st->batchStart[b + 1];
+    const int64_t cols = a.j1 - a.j0;
+    if (st->batchMaxLen[b] > 2048) {
+      cd_col_kernel<true><<<(int)cols, 1024, 0, ctx->stream>>>(a);
+    } else {
+      const int64_t threads = cols * 32;
+      cd_col_kernel<false><<<(int)((threads + 127) / 128), 128, 0, ctx->stream>>>(a);
+    }
+    LAUNCHED(ctx);
+  }
+  for (int64_t j = X->d; j < nCols; j++) {   // dummy columns touch every row: one batch each
+    a.j0 = j;
+    a.j1 = j + 1;
+    cd_col_kernel<true><<<1, 1024, 0, ctx->stream>>>(a);
+    LAUNCHED(ctx);
+  }
+  return NIMFM_OK;
+}
+
+extern "C" {
+
+int32_t nimfm_fm_cd_begin(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, const nimfm_cd_cfg *cfg) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  REQUIRE(fm && X && cfg, "NULL argument");
+  REQUIRE(X->kind == NIMFM_DS_CSC, "CD needs a CSCDataset (ColDataset)");
+  REQUIRE(X->d == fm->d, "Invalid nFeatures.");
+  REQUIRE(X->y != nullptr, "dataset has no targets (nimfm_dataset_set_targets)");
+  CK(cudaSetDevice(ctx->device));
+  const int64_t n = X->n, d = X->d, dd = fm->dd(), nP = fm->nP();
+  CdState *st = cd_state(fm, true);
+  st->alpha0 = cfg->alpha0 * (double)n;   // cd.nim:123-125
+  st->alpha = cfg->alpha * (double)n;
+  st->beta = cfg->beta * (double)n;
+  int rc;
+  if (st->csr) nimfm_dataset_free(ctx, st->csr);
+  st->csr = nullptr;
+  if ((rc = nimfm_dataset_transpose(ctx, X, &st->csr))) return rc;
+  // ---- batches of consecutive, pairwise row-disjoint columns
+  {
+    std::vector<int32_t> rows((size_t)X->nnz);
+    std::vector<int64_t> ptr((size_t)d + 1);
+    CK(cudaMemcpy(rows.data(), X->indices, (size_t)X->nnz * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ptr.data(), X->indptr, ((size_t)d + 1) * 8, cudaMemcpyDeviceToHost));
+    std::vector<int64_t> mark((size_t)std::max<int64_t>(n, 1), -1);
+    st->batchStart.clear();
+    st->batchMaxLen.clear();
+    int64_t cur = -1;
+    for (int64_t j = 0; j < d; j++) {
+      bool conflict = cur < 0;
+      for (int64_t e = ptr[j]; e < ptr[j + 1] && !conflict; e++)
+        if (mark[rows[e]] == cur) conflict = true;
+      if (conflict) {
+        cur = (int64_t)st->batchStart.size();
+        st->batchStart.push_back(j);
+        st->batchMaxLen.push_back(0);
+      }
+      for (int64_t e = ptr[j]; e < ptr[j + 1]; e++) mark[rows[e]] = cur;
+      st->batchMaxLen.back() = std::max(st->batchMaxLen.back(), ptr[j + 1] - ptr[j]);
+    }
+    st->batchStart.push_back(d);
+  }
+  // ---- caches
+  for (double *p : {fm->Pcm, fm->yPred, fm->Acache, fm->colNormSq, fm->cdScal}) cudaFree(p);
+  fm->Pcm = fm->yPred = fm->Acache = fm->colNormSq = fm->cdScal = nullptr;
+  CK(cudaMalloc(&fm->Pcm, (size_t)std::max<int64_t>(nP, 1) * 8));
+  CK(cudaMalloc(&fm->yPred, (size_t)std::max<int64_t>(n, 1) * 8));
+  CK(cudaMalloc(&fm->Acache, (size_t)std::max<int64_t>(n, 1) * (fm->degree + 1) * 8));
+  CK(cudaMalloc(&fm->colNormSq, (size_t)d * 8));
+  CK(cudaMalloc(&fm->cdScal, 16 * 8));
+  CK(cudaMemsetAsync(fm->cdScal, 0, 16 * 8, ctx->stream));
+  const int64_t nUpd = 1 + d + (int64_t)fm->nOrders * fm->k * dd;
+  if (st->updCap < nUpd) {
+    cudaFree(st->updAbs);
+    CK(cudaMalloc(&st->updAbs, (size_t)nUpd * 8));
+    st->updCap = nUpd;
+  }
+  fm->cdN = n;
+  cd_permute_kernel<<<ew_grid(ctx, nP), 256, 0, ctx->stream>>>(fm->P, fm->Pcm, fm->nOrders, fm->k, dd, 1);
+  LAUNCHED(ctx);
+  if (fm->fitLinear) {
+    cd_colnorm_kernel<<<(int)((d * 32 + 127) / 128), 128, 0, ctx->stream>>>(X->data, X->indptr, d, fm->colNormSq);
+    LAUNCHED(ctx);
+  }
+  // yPred = linear + intercept + sum anova (cd.nim:144-151)
+  if ((rc = nimfm_fm_predict_device(ctx, fm, st->csr, fm->yPred))) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  fm->cdReady = true;
+  return NIMFM_OK;
+}
+
+int32_t nimfm_fm_cd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, const nimfm_cd_cfg *cfg, double *viol,
+                          double *lossMean, double *regOverN) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  REQUIRE(fm && X && cfg, "NULL argument");
+  if (!fm->cdReady) return nimfm_fail(ctx, NIMFM_ERR_STATE, "nimfm_fm_cd_begin was not called");
+  CdState *st = cd_state(fm, false);
+  REQUIRE(st && X->kind == NIMFM_DS_CSC && X->n == fm->cdN && X->d == fm->d, "dataset does not match cd_begin");
+  CK(cudaSetDevice(ctx->device));
+  const int64_t n = X->n, d = X->d, dd = fm->dd();
+  const double mu = loss_mu(cfg->loss);
+  const int64_t nUpd = 1 + d + (int64_t)fm->nOrders * fm->k * dd;
+  int rc;
+  CK(cudaMemsetAsync(st->updAbs, 0, (size_t)nUpd * 8, ctx->stream));
+  const int rowGrid = ew_grid(ctx, n);
+  if (fm->fitIntercept) {                                            // fitInterceptCD
+    if ((rc = cd_reduce(ctx, 0, X->y, fm->yPred, n, cfg->loss, cfg->huberThreshold, fm->cdScal, 3))) return rc;
+    cd_intercept_kernel<<<rowGrid, 256, 0, ctx->stream>>>(fm->b, fm->yPred, n, st->alpha0, mu, fm->cdScal, st->updAbs);
+    cd_intercept_commit_kernel<<<1, 1, 0, ctx->stream>>>(fm->b, st->alpha0, mu, n, fm->cdScal);
+    ctx->launches += 2;
+  }
+  if (fm->fitLinear)                                                 // fitLinearCD (dummy features removed)
+    if ((rc = cd_sweep(ctx, st, X, fm, cfg, fm->w, 0, st->alpha, st->updAbs + 1, d))) return rc;
+  const nimfm_dataset *R = st->csr;
+  for (int o = 0; o < fm->nOrders; o++) {
+    const int deg = fm->degree - o;
+    for (int s = 0; s < fm->k; s++) {
+      double *Ps = fm->Pcm + ((int64_t)o * fm->k + s) * dd;
+      cd_cache_kernel<<<rowGrid, 256, 0, ctx->stream>>>(R->data, R->indices, R->indptr, n, d, fm->nAug, Ps, deg,
+                                                        fm->Acache, fm->degree + 1);
+      LAUNCHED(ctx);
+      double *upd = st->updAbs + 1 + d + ((int64_t)o * fm->k + s) * dd;
+      if ((rc = cd_sweep(ctx, st, X, fm, cfg, Ps, deg, st->beta, upd, dd))) return rc;
+    }
+  }
+  // viol (fixed-order sum of |update|), mean loss, regularization / n (cd.nim:177-184)
+  int grid = (int)std::min<int64_t>(1024, std::max<int64_t>(1, (nUpd + 255) / 256));
+  if ((rc = nimfm_ensure_partials(ctx, 1024))) return rc;
+  cd_final_sum_kernel<<<1, 256, 0, ctx->stream>>>(st->updAbs, nUpd, fm->cdScal, 0);
+  LAUNCHED(ctx);
+  (void)grid;
+  if ((rc = cd_reduce(ctx, 1, X->y, fm->yPred, n, cfg->loss, cfg->huberThreshold, fm->cdScal, 1))) return rc;
+  if ((rc = cd_reduce(ctx, 2, fm->w, nullptr, d, 0, 0, fm->cdScal, 4))) return rc;
+  if ((rc = cd_reduce(ctx, 2, fm->Pcm, nullptr, fm->nP(), 0, 0, fm->cdScal, 5))) return rc;
+  // keep the feature-major copy current so get_params / callbacks see this epoch's parameters
+  cd_permute_kernel<<<ew_grid(ctx, fm->nP()), 256, 0, ctx->stream>>>(fm->P, fm->Pcm, fm->nOrders, fm->k, dd, 0);
+  LAUNCHED(ctx);
+  CK(cudaGetLastError());
+  double h[8];
+  CK(cudaMemcpyAsync(ctx->hostScalars, fm->cdScal, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  double hb = 0.0;
+  CK(cudaMemcpyAsync(&hb, fm->b, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  memcpy(h, ctx->hostScalars, 64);
+  if (viol) *viol = h[0];
+  if (lossMean) *lossMean = h[1] / (double)n;
+  if (regOverN) {
+    // regularization (optimizer/utils.nim:56-59): norm(.,2)^2 == sqrt(sum sq)^2
+    const double nw = sqrt(h[4]), np = sqrt(h[5]);
+    const double reg = 0.5 * st->alpha0 * (hb * hb) + 0.5 * st->alpha * (nw * nw) + 0.5 * st->beta * (np * np);
+    *regOverN = reg / (double)n;
+  }
+  return NIMFM_OK;
+}
+
+int32_t nimfm_fm_cd_get_ypred(nimfm_ctx *ctx, nimfm_fm *fm, double *yPred) {
+  if (!ctx || !fm || !yPred) return NIMFM_ERR_INVALID;
+  if (!fm->cdReady) return nimfm_fail(ctx, NIMFM_ERR_STATE, "nimfm_fm_cd_begin was not called");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpy(yPred, fm->yPred, (size_t)fm->cdN * 8, cudaMemcpyDeviceToHost));
+  return NIMFM_OK;
+}
+
+int32_t nimfm_fm_cd_end(nimfm_ctx *ctx, nimfm_fm *fm) {
+  if (!ctx || !fm) return NIMFM_ERR_INVALID;
+  if (!fm->cdReady) return nimfm_fail(ctx, NIMFM_ERR_STATE, "nimfm_fm_cd_begin was not called");
+  CK(cudaSetDevice(ctx->device));
+  cd_permute_kernel<<<ew_grid(ctx, fm->nP()), 256, 0, ctx->stream>>>(fm->P, fm->Pcm, fm->nOrders, fm->k, fm->dd(), 0);
+  LAUNCHED(ctx);
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  CdState *st = cd_state(fm, false);
+  if (st) {
+    nimfm_dataset_free(ctx, st->csr);
+    cudaFree(st->updAbs);
+    for (size_t i = 0; i < g_cd.size(); i++)
+      if (g_cd[i].first == fm) {
+        delete g_cd[i].second;
+        g_cd.erase(g_cd.begin() + i);
+        break;
+      }
+  }
+  fm->cdReady = false;
+  return NIMFM_OK;
+}
+
+}  // extern "C"

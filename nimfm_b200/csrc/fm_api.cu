@@ -283,6 +283,30 @@ int32_t nimfm_fm_grad_device_ptr(nimfm_fm *fm, void **ptr, int64_t *nDoubles) {
 }
 
 // ================================================================== K1: decisionFunction
+}  // extern "C"
+
+// device-resident variant used by the CD set-up (cd.nim:144-151): dOut[n] on the device
+int nimfm_fm_predict_device(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *Xcsr, double *dOut) {
+  int rc = check_fm_ds(ctx, fm, Xcsr, false);
+  if (rc) return rc;
+  if (Xcsr->n == 0) return NIMFM_OK;
+  RowPlan pl;
+  if ((rc = plan_rows(ctx, fm, Xcsr, Xcsr->n, MODE_PREDICT, &pl))) return rc;
+  RowArgs a;
+  fill_row_args(a, fm, Xcsr);
+  a.lams = nullptr;   // cd.fit sums A[:, degree-order] without lams (cd.nim:151)
+  a.nRows = Xcsr->n;
+  a.yOut = dOut;
+  a.G = pl.G;
+  a.CH = pl.CH;
+  pl.kern<<<pl.grid, pl.block, pl.smem, ctx->stream>>>(a);
+  LAUNCHED(ctx);
+  CK(cudaGetLastError());
+  return NIMFM_OK;
+}
+
+extern "C" {
+
 int32_t nimfm_fm_decision_function(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, double *out) {
   if (!ctx) return NIMFM_ERR_INVALID;
   REQUIRE(fm && X && out, "NULL argument");
