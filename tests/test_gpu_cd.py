@@ -117,9 +117,9 @@ def test_cd_callback_and_tol(oracle):
     P, w, _ = make_fm_params(d, degree, k, "explicit", True, seed=1)
     fm = make_fm(degree, k, "explicit", True, True, P, w, 0.0)
     seen = []
-    opt = nf.newCD(maxIter=50, verbose=0, tol=1e-3)
+    opt = nf.newCD(maxIter=50, verbose=0, tol=1.0)
     opt.fit(ds, y, fm, callback=lambda o, m: seen.append(m.P.copy()))
-    assert 1 <= len(opt.history) < 50 and opt.history[-1][0] < 1e-3      # stopped by viol < tol (cd.nim:186-189)
+    assert 1 <= len(opt.history) < 50 and opt.history[-1][0] < 1.0      # stopped by viol < tol (cd.nim:186-189)
     assert len(seen) == len(opt.history) and np.allclose(seen[-1], fm.P)
     with pytest.raises(TypeError):
         opt.fit(nf.newCSRDataset([1.0], [0], [0, 1], 1, 5), [1.0], fm)
