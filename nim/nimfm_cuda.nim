@@ -1,0 +1,153 @@
+## nimfm_cuda.nim -- the Nim side of the drop-in boundary: {.importc, dynlib.} declarations of
+## include/nimfm_cuda.h plus thin procs that keep nimfm's own signatures, so that
+## `import nimfm/cuda/nimfm_cuda` can stand in for the CPU kernels / solvers on the hot path.
+##
+## NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Nim toolchain (SURVEY.md, probe table).
+## The same symbols are exercised through the ctypes mirror (nimfm_b200/_lib.py), whose prototype
+## table is checked against the header by tests/test_abi_cpu.py.  See INTEGRATION.md for where each
+## proc plugs into nimfm's modules.
+##
+## Type mapping: Nim int -> int64 (cint64), float64 -> cdouble, bool -> int32, seq[T] -> (ptr T, len)
+## via `addr s[0]` (`nil` for empty seqs).
+
+const libName = "libnimfm_cuda.so"
+
+type
+  CtxObj {.incompleteStruct.} = object
+  DatasetObj {.incompleteStruct.} = object
+  FmObj {.incompleteStruct.} = object
+  FfmObj {.incompleteStruct.} = object
+  Ctx* = ptr CtxObj
+  DeviceDataset* = ptr DatasetObj
+  DeviceFM* = ptr FmObj
+  DeviceFFM* = ptr FfmObj
+
+  MbpsgdCfg* {.bycopy.} = object
+    loss*: int32
+    huberThreshold*: cdouble
+    eta0*, alpha0*, alpha*, beta*, gamma*: cdouble
+    reg*: int32
+    scheduling*: int32
+    power*: cdouble
+    miniBatchSize*, maxIterInner*: int64
+
+  AdagradCfg* {.bycopy.} = object
+    loss*: int32
+    huberThreshold*: cdouble
+    eta0*, alpha0*, alpha*, beta*, eps*: cdouble
+    miniBatchSize*: int64
+
+  SgdCfg* {.bycopy.} = object
+    loss*: int32
+    huberThreshold*: cdouble
+    eta0*, alpha0*, alpha*, beta*: cdouble
+    scheduling*: int32
+    power*: cdouble
+
+  CdCfg* {.bycopy.} = object
+    loss*: int32
+    huberThreshold*: cdouble
+    alpha0*, alpha*, beta*: cdouble
+
+{.push importc, dynlib: libName, cdecl.}
+proc nimfm_ctx_create(device: int32, outCtx: ptr Ctx): int32
+proc nimfm_ctx_destroy(ctx: Ctx): int32
+proc nimfm_last_error(ctx: Ctx): cstring
+proc nimfm_comm_unique_id(uid: pointer): int32
+proc nimfm_comm_init(ctx: Ctx, rank, nranks: int32, uid: pointer): int32
+proc nimfm_csr_upload(ctx: Ctx, n, d: int64, data: ptr cdouble, indices, indptr, fields: ptr int64,
+                      nFields, rowBegin, rowEnd: int64, outDs: ptr DeviceDataset): int32
+proc nimfm_csc_upload(ctx: Ctx, n, d: int64, data: ptr cdouble, indices, indptr: ptr int64,
+                      outDs: ptr DeviceDataset): int32
+proc nimfm_dataset_transpose(ctx: Ctx, src: DeviceDataset, outDs: ptr DeviceDataset): int32
+proc nimfm_dataset_set_targets(ctx: Ctx, ds: DeviceDataset, y: ptr cdouble): int32
+proc nimfm_dataset_free(ctx: Ctx, ds: DeviceDataset): int32
+proc nimfm_fm_create(ctx: Ctx, degree, nComponents, nOrders, nAugments: int32, nFeatures: int64,
+                     fitLinear, fitIntercept: int32, outFm: ptr DeviceFM): int32
+proc nimfm_fm_set_params(ctx: Ctx, fm: DeviceFM, P, w: ptr cdouble, intercept: cdouble, lams: ptr cdouble): int32
+proc nimfm_fm_get_params(ctx: Ctx, fm: DeviceFM, P, w: ptr cdouble, intercept: ptr cdouble): int32
+proc nimfm_fm_free(ctx: Ctx, fm: DeviceFM): int32
+proc nimfm_fm_decision_function(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, outY: ptr cdouble): int32
+proc nimfm_fm_loss_grad(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, loss: int32, huberThreshold: cdouble,
+                        rowBegin, nRows: int64, rowIdx: ptr int64, miniBatchSize: int64,
+                        zeroGrads, allreduce: int32, lossSum: ptr cdouble): int32
+proc nimfm_fm_mbpsgd_epoch(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr MbpsgdCfg, localBatch: int64,
+                           it, ii: ptr int64, sampleIdx: ptr int64, runningLoss: ptr cdouble): int32
+proc nimfm_fm_adagrad_init(ctx: Ctx, fm: DeviceFM, eps: cdouble, reset: int32): int32
+proc nimfm_fm_adagrad_epoch(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr AdagradCfg, it: ptr int64,
+                            perm: ptr int64, nRows: int64, viol, lossSum: ptr cdouble): int32
+proc nimfm_fm_adagrad_finalize(ctx: Ctx, fm: DeviceFM, cfg: ptr AdagradCfg, it: int64): int32
+proc nimfm_fm_sgd_begin(ctx: Ctx, fm: DeviceFM): int32
+proc nimfm_fm_sgd_epoch(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr SgdCfg, it: ptr int64,
+                        perm: ptr int64, nRows: int64, viol, lossSum: ptr cdouble): int32
+proc nimfm_fm_sgd_end(ctx: Ctx, fm: DeviceFM): int32
+proc nimfm_fm_cd_begin(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr CdCfg): int32
+proc nimfm_fm_cd_epoch(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr CdCfg,
+                       viol, lossMean, regOverN: ptr cdouble): int32
+proc nimfm_fm_cd_end(ctx: Ctx, fm: DeviceFM): int32
+proc nimfm_ffm_create(ctx: Ctx, nComponents: int32, nFields, nFeatures: int64, fitLinear, fitIntercept: int32,
+                      outM: ptr DeviceFFM): int32
+proc nimfm_ffm_set_params(ctx: Ctx, m: DeviceFFM, P, w: ptr cdouble, intercept: cdouble): int32
+proc nimfm_ffm_get_params(ctx: Ctx, m: DeviceFFM, P, w: ptr cdouble, intercept: ptr cdouble): int32
+proc nimfm_ffm_free(ctx: Ctx, m: DeviceFFM): int32
+proc nimfm_ffm_decision_function(ctx: Ctx, m: DeviceFFM, X: DeviceDataset, outY: ptr cdouble): int32
+proc nimfm_ffm_adagrad_init(ctx: Ctx, m: DeviceFFM, eps: cdouble, reset: int32): int32
+proc nimfm_ffm_adagrad_epoch(ctx: Ctx, m: DeviceFFM, X: DeviceDataset, cfg: ptr AdagradCfg, it: ptr int64,
+                             perm: ptr int64, nRows: int64, viol, lossSum: ptr cdouble): int32
+proc nimfm_ffm_adagrad_finalize(ctx: Ctx, m: DeviceFFM, cfg: ptr AdagradCfg, it: int64): int32
+proc nimfm_ffm_sgd_begin(ctx: Ctx, m: DeviceFFM): int32
+proc nimfm_ffm_sgd_epoch(ctx: Ctx, m: DeviceFFM, X: DeviceDataset, cfg: ptr SgdCfg, it: ptr int64,
+                         perm: ptr int64, nRows: int64, viol, lossSum: ptr cdouble): int32
+proc nimfm_ffm_sgd_end(ctx: Ctx, m: DeviceFFM): int32
+{.pop.}
+
+# ---------------------------------------------------------------- thin Nim layer (sketch)
+# The procs below show how nimfm's own signatures are kept; they rely on nimfm's types
+# (dataset.nim, model/factorization_machine.nim, loss.nim, optimizer/*.nim).
+
+var gCtx: Ctx
+
+proc ctx*(): Ctx =
+  if gCtx.isNil:
+    if nimfm_ctx_create(0, addr gCtx) != 0:
+      raise newException(IOError, "libnimfm_cuda: no CUDA device (there is no CPU fallback)")
+  result = gCtx
+
+template check(rc: int32) =
+  if rc != 0:
+    # same exception style as factorization_machine.nim:114-115
+    raise newException(ValueError, $nimfm_last_error(ctx()))
+
+when false:  # compiled only inside nimfm's tree, where these types exist
+  import ../dataset, ../tensor/tensor, ../model/factorization_machine, ../model/fm_base, ../loss
+
+  proc p[T](s: var seq[T]): ptr T = (if s.len == 0: nil else: addr s[0])
+
+  proc upload*(X: CSRDataset): DeviceDataset =
+    ## newCSRDataset (dataset.nim:116-122): data/indices/indptr are the public seqs of tensor/sparse.nim:4-31
+    check nimfm_csr_upload(ctx(), X.nSamples, X.data.shape[1], cast[ptr cdouble](p(X.data.data)),
+                           cast[ptr int64](p(X.data.indices)), cast[ptr int64](p(X.data.indptr)), nil, 0,
+                           0, X.nSamples, addr result)
+
+  proc flatP(fm: FactorizationMachine): seq[float64] =
+    ## Tensor is seq[Matrix] of ragged rows (tensor.nim:8-17): flatten to [order][s][j]
+    for o in 0..<fm.P.shape[0]:
+      for s in 0..<fm.P.shape[1]:
+        for j in 0..<fm.P.shape[2]: result.add(fm.P[o, s, j])
+
+  proc toDevice*(fm: FactorizationMachine, nFeatures: int): DeviceFM =
+    var P = flatP(fm)
+    check nimfm_fm_create(ctx(), int32(fm.degree), int32(fm.nComponents), int32(fm.nOrders),
+                          int32(fm.nAugments), nFeatures, int32(fm.fitLinear), int32(fm.fitIntercept), addr result)
+    check nimfm_fm_set_params(ctx(), result, cast[ptr cdouble](p(P)), cast[ptr cdouble](p(fm.w)),
+                              fm.intercept, cast[ptr cdouble](p(fm.lams)))
+
+  proc decisionFunction*(self: FactorizationMachine, X: CSRDataset): seq[float64] =
+    ## drop-in for factorization_machine.nim:100-122
+    self.checkInitialized()
+    let ds = upload(X)
+    let h = toDevice(self, X.nFeatures)
+    result = newSeq[float64](X.nSamples)
+    check nimfm_fm_decision_function(ctx(), h, ds, cast[ptr cdouble](p(result)))
+    discard nimfm_fm_free(ctx(), h)
+    discard nimfm_dataset_free(ctx(), ds)
