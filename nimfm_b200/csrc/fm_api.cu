@@ -2,10 +2,12 @@
 // decisionFunction (K1), predict+grad (K2), MBPSGD epoch (K2+K3), AdaGrad epoch (K4+K5).
 #include <math.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "dense_kernels.cuh"
-#include "fm_rows_fast.cuh"
+#include "fm_rows_stream.cuh"
 
 typedef void (*RowKernel)(const RowArgs);
 RowKernel nimfm_row_kernel_predict(int degree, bool explicitLower, int k);
@@ -59,6 +61,8 @@ struct RowPlan {
 };
 
 RowKernel nimfm_row_fast_kernel_predict(int degree, bool explicitLower, int k);
+RowKernel nimfm_row_stream_kernel_predict(int degree, bool explicitLower, int k);
+RowKernel nimfm_row_stream_kernel_grad(int degree, bool explicitLower, int k);
 RowKernel nimfm_row_fast_kernel_grad(int degree, bool explicitLower, int k);
 
 static bool is_explicit(const nimfm_fm *fm) { return fm->degree > 2 && fm->nOrders == fm->degree - 1; }
@@ -78,14 +82,30 @@ static int plan_rows(nimfm_ctx *ctx, const nimfm_fm *fm, const nimfm_dataset *X,
   if (z < 1) z = 1;
   const size_t capPerGroup = 40 * 1024;
   const bool expl = is_explicit(fm);
+  // variant: NIMFM_ROW_KERNEL = stream (default) | fast | generic   (A/B switch for profiling)
+  const char *env = getenv("NIMFM_ROW_KERNEL");
+  const bool wantGeneric = env && !strcmp(env, "generic");
+  const bool wantFast = env && !strcmp(env, "fast");
   RowKernel fast = nullptr;
-  if (mode == MODE_PREDICT) fast = nimfm_row_fast_kernel_predict(fm->degree, expl, k);
-  else if (mode == MODE_GRAD) fast = nimfm_row_fast_kernel_grad(fm->degree, expl, k);
-  if (fast && (size_t)z * ((size_t)SB8 * 8 + 16) > capPerGroup) fast = nullptr;   // a row does not fit
+  bool stream = false;
+  if (!wantGeneric && mode != MODE_ADAGRAD) {
+    if (!wantFast && z <= 512) {
+      fast = mode == MODE_PREDICT ? nimfm_row_stream_kernel_predict(fm->degree, expl, k)
+                                  : nimfm_row_stream_kernel_grad(fm->degree, expl, k);
+      stream = fast != nullptr;
+    }
+    if (!fast) {
+      fast = mode == MODE_PREDICT ? nimfm_row_fast_kernel_predict(fm->degree, expl, k)
+                                  : nimfm_row_fast_kernel_grad(fm->degree, expl, k);
+      if (fast && (size_t)z * ((size_t)SB8 * 8 + 16) > capPerGroup) fast = nullptr;   // a row does not fit
+    }
+  }
   RowKernel kern = fast;
   int64_t CH = z;
   size_t perGroup;
-  if (fast) {
+  if (stream) {
+    perGroup = stream_group_smem((int)CH, SB8, nHotTot);
+  } else if (fast) {
     perGroup = fast_group_smem((int)CH, SB8, nHotTot);
   } else {
     kern = mode == MODE_PREDICT ? nimfm_row_kernel_predict(fm->degree, expl, k)
