@@ -13,6 +13,7 @@ SURVEY Appendix B): pass shuffle=False, or perms=..., for reproducible parity ru
 import ctypes as C
 import math
 import sys
+import time
 
 import numpy as np
 
@@ -89,6 +90,7 @@ class CD(_Base):
         h = fm._to_device(X.nFeatures)
         cfg = _lib.CdCfg(self.loss.kind, self.loss.threshold, self.alpha0, self.alpha, self.beta)
         self.history = []
+        self.epoch_seconds = []     # host wall time of each epoch's single library call (blocking)
         try:
             _lib.check(lib.nimfm_fm_cd_begin(ctx, h, X.handle(), C.byref(cfg)))
             if self.verbose > 0:
@@ -96,8 +98,10 @@ class CD(_Base):
             converged = False
             for it in range(self.maxIter):
                 viol, lossMean, reg = C.c_double(), C.c_double(), C.c_double()
+                t0 = time.perf_counter()
                 _lib.check(lib.nimfm_fm_cd_epoch(ctx, h, X.handle(), C.byref(cfg), C.byref(viol),
                                                  C.byref(lossMean), C.byref(reg)))
+                self.epoch_seconds.append(time.perf_counter() - t0)
                 self.history.append((viol.value, lossMean.value, reg.value))
                 if callback is not None:
                     fm._from_device(h)
@@ -159,6 +163,7 @@ class SGD(_Base):
         indices = np.arange(n, dtype=np.int64)
         self._converged = False
         self.history = []
+        self.epoch_seconds = []     # host wall time of each epoch's single library call (blocking)
         try:
             _lib.check(begin(ctx, h))
             for ep in range(self.maxIter):
@@ -168,8 +173,10 @@ class SGD(_Base):
                     rng.shuffle(indices)
                 it = C.c_int64(self.it)
                 viol, lossSum = C.c_double(), C.c_double()
+                t0 = time.perf_counter()
                 _lib.check(epoch(ctx, h, X.handle(), C.byref(cfg), C.byref(it), _lib.ptr(indices), n,
                                  C.byref(viol), C.byref(lossSum)))
+                self.epoch_seconds.append(time.perf_counter() - t0)
                 self.it = it.value
                 runningLoss = lossSum.value / n
                 self.history.append((viol.value, runningLoss))
@@ -231,6 +238,7 @@ class AdaGrad(_Base):
         indices = np.arange(n, dtype=np.int64)
         self._converged = False
         self.history = []
+        self.epoch_seconds = []     # host wall time of each epoch's single library call (blocking)
         try:
             _lib.check(init(ctx, h, self.eps, 1))
             if self.it != 1 and not is_ffm:
@@ -251,8 +259,10 @@ class AdaGrad(_Base):
                     rng.shuffle(indices)
                 it = C.c_int64(self.it)
                 viol, lossSum = C.c_double(), C.c_double()
+                t0 = time.perf_counter()
                 _lib.check(epoch(ctx, h, X.handle(), C.byref(cfg), C.byref(it), _lib.ptr(indices), n,
                                  C.byref(viol), C.byref(lossSum)))
+                self.epoch_seconds.append(time.perf_counter() - t0)
                 self.it = it.value
                 runningLoss = lossSum.value / n
                 self.history.append((viol.value, runningLoss))
@@ -353,6 +363,7 @@ class MBPSGD(_Base):
         oldLoss = float("inf")
         converged = False
         self.history = []
+        self.epoch_seconds = []     # host wall time of each epoch's single library call (blocking)
         try:
             for ep in range(self.maxIter):
                 sample = None
@@ -370,8 +381,10 @@ class MBPSGD(_Base):
                             ii = 0
                             rng.shuffle(indices)
                 itc, iic, rl = C.c_int64(self.it), C.c_int64(ii), C.c_double()
+                t0 = time.perf_counter()
                 _lib.check(lib.nimfm_fm_mbpsgd_epoch(ctx, h, X.handle(), C.byref(cfg), mb, C.byref(itc),
                                                      C.byref(iic), _lib.ptr(sample), C.byref(rl)))
+                self.epoch_seconds.append(time.perf_counter() - t0)
                 self.it = itc.value
                 if not self.shuffle:
                     ii = iic.value
