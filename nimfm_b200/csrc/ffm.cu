@@ -51,6 +51,8 @@ struct __align__(16) FfmMeta {
   int32_t f;
 };
 
+#include "ffm_pairs.cuh"
+
 static size_t ffm_smem_bytes(int CH, int SB8, int nFields) {
   size_t b = (((size_t)CH * SB8 * 8 + 15) & ~(size_t)15) + (size_t)CH * sizeof(FfmMeta) + (size_t)CH * 4 +
              (size_t)(nFields + 1) * 4 * 2;
@@ -240,7 +242,60 @@ typedef void (*FfmKernel)(const FfmArgs);
 struct FfmPlan {
   int CH, grid;
   size_t smem;
+  FfmKernel kern = nullptr;
+  int block = FFM_THREADS;
+  int64_t partialRows = 0;   // rows of the [.][4] partials block the kernel writes
 };
+
+// pair-streaming kernel when k is 4/8/16/32 (predict / grad only), else nullptr
+static FfmKernel ffm_pairs_pick(int k, bool grad) {
+  switch (k) {
+    case 4: return grad ? ffm_pairs_kernel<1, 4, FfmArgs> : ffm_pairs_kernel<0, 4, FfmArgs>;
+    case 8: return grad ? ffm_pairs_kernel<1, 8, FfmArgs> : ffm_pairs_kernel<0, 8, FfmArgs>;
+    case 16: return grad ? ffm_pairs_kernel<1, 16, FfmArgs> : ffm_pairs_kernel<0, 16, FfmArgs>;
+    case 32: return grad ? ffm_pairs_kernel<1, 32, FfmArgs> : ffm_pairs_kernel<0, 32, FfmArgs>;
+    default: return nullptr;
+  }
+}
+
+static int ffm_plan(nimfm_ctx *ctx, const nimfm_ffm *m, const nimfm_dataset *X, int64_t nRows, FfmKernel kern,
+                    FfmPlan *pl);
+
+// mode: FFM_PREDICT / FFM_GRAD choose the pair kernel when available (NIMFM_FFM_KERNEL=block forces the
+// block-per-row kernel); FFM_ADAGRAD always runs the block-per-row kernel.
+static int ffm_plan_mode(nimfm_ctx *ctx, const nimfm_ffm *m, const nimfm_dataset *X, int64_t nRows, int mode,
+                         FfmPlan *pl) {
+  const char *env = getenv("NIMFM_FFM_KERNEL");
+  const bool forceBlock = env && !strcmp(env, "block");
+  const int CH = (int)std::max<int64_t>(X->maxSegNnz, 1);
+  FfmKernel pk = (mode == FFM_ADAGRAD || forceBlock || CH > 1024) ? nullptr : ffm_pairs_pick(m->k, mode == FFM_GRAD);
+  if (pk) {
+    const int block = 256, wpb = block / 32;
+    const size_t smem = (size_t)wpb * CH * sizeof(FfmRec);
+    CK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pk, block, smem));
+    if (occ < 1) return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "FFM pair kernel does not fit on an SM");
+    int64_t grid = std::min<int64_t>((nRows + wpb - 1) / wpb, (int64_t)occ * ctx->numSMs);
+    if (grid < 1) grid = 1;
+    pl->CH = CH;
+    pl->grid = (int)grid;
+    pl->smem = smem;
+    pl->kern = pk;
+    pl->block = block;
+    pl->partialRows = grid * wpb;
+    return NIMFM_OK;
+  }
+  FfmKernel bk = mode == FFM_PREDICT ? ffm_rows_kernel<FFM_PREDICT>
+                 : mode == FFM_GRAD  ? ffm_rows_kernel<FFM_GRAD>
+                                     : ffm_rows_kernel<FFM_ADAGRAD>;
+  int rc = ffm_plan(ctx, m, X, nRows, bk, pl);
+  if (rc) return rc;
+  pl->kern = bk;
+  pl->block = FFM_THREADS;
+  pl->partialRows = pl->grid;
+  return NIMFM_OK;
+}
 
 static int ffm_plan(nimfm_ctx *ctx, const nimfm_ffm *m, const nimfm_dataset *X, int64_t nRows, FfmKernel kern,
                     FfmPlan *pl) {
@@ -373,7 +428,7 @@ int32_t nimfm_ffm_decision_function(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_da
   const int64_t n = X->n;
   if (n == 0) return NIMFM_OK;
   FfmPlan pl;
-  if ((rc = ffm_plan(ctx, m, X, n, ffm_rows_kernel<FFM_PREDICT>, &pl))) return rc;
+  if ((rc = ffm_plan_mode(ctx, m, X, n, FFM_PREDICT, &pl))) return rc;
   double *dOut = nullptr;
   CK(cudaMalloc(&dOut, (size_t)n * 8));
   FfmArgs a;
@@ -381,7 +436,7 @@ int32_t nimfm_ffm_decision_function(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_da
   a.nRows = n;
   a.yOut = dOut;
   a.CH = pl.CH;
-  ffm_rows_kernel<FFM_PREDICT><<<pl.grid, FFM_THREADS, pl.smem, ctx->stream>>>(a);
+  pl.kern<<<pl.grid, pl.block, pl.smem, ctx->stream>>>(a);
   LAUNCHED(ctx);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, dOut, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -393,17 +448,17 @@ int32_t nimfm_ffm_decision_function(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_da
 static int ffm_launch_grad(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_dataset *X, int loss, double thr,
                            int64_t rowBegin, int64_t nRows, const int32_t *rowIdxDev, double mb) {
   FfmPlan pl;
-  int rc = ffm_plan(ctx, m, X, nRows, ffm_rows_kernel<FFM_GRAD>, &pl);
+  int rc = ffm_plan_mode(ctx, m, X, nRows, FFM_GRAD, &pl);
   if (rc) return rc;
-  if ((rc = nimfm_ensure_partials(ctx, (size_t)pl.grid * 4))) return rc;
+  if ((rc = nimfm_ensure_partials(ctx, (size_t)pl.partialRows * 4))) return rc;
   FfmArgs a;
   ffm_fill_args(a, m, X);
   a.rowBegin = rowBegin; a.nRows = nRows; a.rowIdx = rowIdxDev;
   a.gP = m->grad; a.gw = m->grad + m->nP(); a.partials = ctx->partials;
   a.loss = loss; a.thr = thr; a.mb = mb; a.CH = pl.CH;
-  ffm_rows_kernel<FFM_GRAD><<<pl.grid, FFM_THREADS, pl.smem, ctx->stream>>>(a);
+  pl.kern<<<pl.grid, pl.block, pl.smem, ctx->stream>>>(a);
   LAUNCHED(ctx);
-  reduce_partials_kernel<<<1, 256, 0, ctx->stream>>>(ctx->partials, pl.grid, ctx->scalars + 8, 0);
+  reduce_partials_kernel<<<1, 256, 0, ctx->stream>>>(ctx->partials, pl.partialRows, ctx->scalars + 8, 0);
   LAUNCHED(ctx);
   return NIMFM_OK;
 }
@@ -444,10 +499,10 @@ int32_t nimfm_ffm_time_loss_grad(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_datas
   int rc = check_ffm_ds(ctx, m, X, gradToo != 0);
   if (rc) return rc;
   REQUIRE(reps >= 1 && nRows >= 1 && msPerLaunch, "bad arguments");
-  FfmKernel kern = gradToo ? ffm_rows_kernel<FFM_GRAD> : ffm_rows_kernel<FFM_PREDICT>;
   FfmPlan pl;
-  if ((rc = ffm_plan(ctx, m, X, nRows, kern, &pl))) return rc;
-  if ((rc = nimfm_ensure_partials(ctx, (size_t)pl.grid * 4))) return rc;
+  if ((rc = ffm_plan_mode(ctx, m, X, nRows, gradToo ? FFM_GRAD : FFM_PREDICT, &pl))) return rc;
+  FfmKernel kern = pl.kern;
+  if ((rc = nimfm_ensure_partials(ctx, (size_t)pl.partialRows * 4))) return rc;
   double *dOut = nullptr;
   if (!gradToo) CK(cudaMalloc(&dOut, (size_t)nRows * 8));
   FfmArgs a;
@@ -457,7 +512,7 @@ int32_t nimfm_ffm_time_loss_grad(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_datas
   a.loss = loss; a.thr = 1.0; a.mb = (double)miniBatchSize; a.CH = pl.CH;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   for (int r = 0; r < reps; r++) {
-    kern<<<pl.grid, FFM_THREADS, pl.smem, ctx->stream>>>(a);
+    kern<<<pl.grid, pl.block, pl.smem, ctx->stream>>>(a);
     LAUNCHED(ctx);
   }
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
