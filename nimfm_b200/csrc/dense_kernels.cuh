@@ -68,42 +68,94 @@ static __global__ void mbpsgd_step_kernel(double *P, double *gP, int64_t nP, dou
 }
 
 // ------------------------------------------------------------------ AdaGrad dense kernels (K5)
-// after a minibatch: refresh P/w for touched features from the OLD state (adagrad.nim:87-110),
-// then g_sum += dGs, g_norm += dGn, and clear the deltas.
-static __global__ void adagrad_apply_kernel(double *P, double *gsP, double *gnP, double *dGsP, double *dGnP,
-                                     int64_t dd, int SB8, const double *touched, double *w, double *gsw,
-                                     double *gnw, double *dGsw, double *dGnw, int64_t d, int fitLinear,
-                                     double eta0, double tIt, double alpha, double beta, int first) {
+// A minibatch runs: count -> [all-reduce counts] -> refresh -> row kernel (reads P, scatters the
+// deltas) -> [all-reduce deltas] -> scalar + apply.
+//
+// cnt[j] += number of rows of the batch that contain feature j (dummy features: every row).
+static __global__ void adagrad_count_kernel(const int32_t *indices, const int64_t *indptr, int64_t n, int64_t rowBegin,
+                                            int64_t nRows, const int32_t *rowIdx, int64_t d, int nAug, double *cnt) {
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nWarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int64_t q = warp; q < nRows; q += nWarps) {
+    const int64_t r = rowIdx ? (int64_t)rowIdx[q] : (rowBegin + q) % n;
+    for (int64_t e = indptr[r] + lane; e < indptr[r + 1]; e += 32) atomicAdd(cnt + indices[e], 1.0);
+  }
+  if (warp == 0 && lane < nAug) cnt[d + lane] += (double)nRows;   // augmentation: one dummy per row
+}
+
+// update() of adagrad.nim:87-110 for every feature the batch touches, done ONCE per feature:
+// theta = -eta0*G/(eta0*t*reg + sqrt(N)); viol += cnt[j] * |P_old - theta| (the reference adds the
+// same |P_old - theta| once per row containing j, and 0 for every later row of the batch -- with the
+// snapshot semantics of the synchronous minibatch every incidence sees the pre-batch P).
+// partials: [gridDim][4], column 3 = viol.
+static __global__ void adagrad_refresh_kernel(double *P, const double *gsP, const double *gnP, int64_t dd, int SB8,
+                                              const double *cnt, double *w, const double *gsw, const double *gnw,
+                                              int64_t d, int fitLinear, double eta0, double tIt, double alpha,
+                                              double beta, double *partials) {
+  __shared__ double red[8];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t nP = dd * SB8;
   const double tmpP = eta0 * tIt * beta;
+  double viol = 0.0;
   for (int64_t e = tid; e < nP; e += stride) {
-    const int64_t j = e / SB8;
-    const double gs = gsP[e], gn = gnP[e];
-    if (!first && touched[j] != 0.0) P[e] = -(eta0 * gs) / (tmpP + sqrt(gn));
-    gsP[e] = gs + dGsP[e];
-    gnP[e] = gn + dGnP[e];
+    const double c = cnt[e / SB8];
+    if (c != 0.0) {
+      const double pn = -(eta0 * gsP[e]) / (tmpP + sqrt(gnP[e]));
+      viol += c * fabs(P[e] - pn);
+      P[e] = pn;
+    }
+  }
+  if (fitLinear) {
+    const double denW = tIt * eta0 * alpha;
+    for (int64_t j = tid; j < d; j += stride) {
+      const double c = cnt[j];
+      if (c != 0.0) {
+        const double wn = -eta0 * gsw[j] / (denW + sqrt(gnw[j]));   // fitLinearAdaGrad, fit_linear.nim:50-57
+        viol += c * fabs(w[j] - wn);
+        w[j] = wn;
+      }
+    }
+  }
+  viol = block_sum(viol, red);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x * 4 + 0] = 0.0;
+    partials[blockIdx.x * 4 + 1] = 0.0;
+    partials[blockIdx.x * 4 + 2] = 0.0;
+    partials[blockIdx.x * 4 + 3] = viol;
+  }
+}
+
+// updateG() of adagrad.nim:113-134 in dense form: g_sum += dGs, g_norm += dGn, deltas and counts cleared.
+static __global__ void adagrad_apply_kernel(double *gsP, double *gnP, double *dGsP, double *dGnP, int64_t nP,
+                                            double *gsw, double *gnw, double *dGsw, double *dGnw, int64_t d,
+                                            int fitLinear, double *cnt, int64_t dd) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (int64_t e = tid; e < nP; e += stride) {
+    gsP[e] += dGsP[e];
+    gnP[e] += dGnP[e];
     dGsP[e] = 0.0;
     dGnP[e] = 0.0;
   }
-  const double denW = tIt * eta0 * alpha;
   for (int64_t j = tid; j < d; j += stride) {
-    const double gs = gsw[j], gn = gnw[j];
     if (fitLinear) {
-      if (!first && touched[j] != 0.0) w[j] = -eta0 * gs / (denW + sqrt(gn));
-      gsw[j] = gs + dGsw[j];
-      gnw[j] = gn + dGnw[j];
+      gsw[j] += dGsw[j];
+      gnw[j] += dGnw[j];
     }
     dGsw[j] = 0.0;
     dGnw[j] = 0.0;
   }
+  for (int64_t j = tid; j < dd; j += stride) cnt[j] = 0.0;
 }
 // intercept part of update()/updateG() (adagrad.nim:101-105,126-128) + epoch accumulators.
-// part = [loss, sum dL, sum dL^2, viol] of the batch (all-reduced); scal = [lossEpoch, violEpoch]
-static __global__ void adagrad_scalar_kernel(double *b, double *adaScal, const double *part, double *scal,
-                                      int fitIntercept, double eta0, double tIt, double alpha0, int first) {
-  double viol = part[3];
+// part = [loss, sum dL, sum dL^2, -] of the batch (all-reduced); violRefresh = this rank's viol of the
+// refresh pass (identical on every rank: counts are all-reduced first); scal = [lossEpoch, violEpoch]
+static __global__ void adagrad_scalar_kernel(double *b, double *adaScal, const double *part, const double *violRefresh,
+                                      double *scal, int fitIntercept, double eta0, double tIt, double alpha0,
+                                      int first) {
+  double viol = first ? 0.0 : violRefresh[3];
   if (fitIntercept) {
     if (!first) {
       const double old = b[0];

@@ -73,10 +73,7 @@ __global__ void __launch_bounds__(FFM_THREADS, 1) ffm_rows_kernel(const FfmArgs 
   const int tid = threadIdx.x, nth = blockDim.x;
   double accLoss = 0.0, accB1 = 0.0, accB2 = 0.0, accViol = 0.0;
   double bias = a.b[0];
-  double tmpP = 0.0, denW = 0.0;
   if (MODE == FFM_ADAGRAD) {
-    tmpP = a.eta0 * a.tIt * a.beta;
-    denW = a.tIt * a.eta0 * a.alpha;
     if (!a.first && a.fitIntercept) {
       const double den = sqrt(a.adaScal[1]) + a.eta0 * a.tIt * a.alpha0;
       bias = -a.eta0 * a.adaScal[0] / den;
@@ -99,13 +96,7 @@ __global__ void __launch_bounds__(FFM_THREADS, 1) ffm_rows_kernel(const FfmArgs 
       m.x = a.data[rb + u];
       sMeta[u] = m;
       atomicAdd(&sStart[m.f + 1], 1);
-      double wj = a.w[m.j];
-      if (MODE == FFM_ADAGRAD && !a.first && a.fitLinear) {   // fitLinearAdaGrad, fit_linear.nim:50-57
-        const double wn = -a.eta0 * a.gsw[m.j] / (denW + sqrt(a.gnw[m.j]));
-        accViol += fabs(wj - wn);
-        wj = wn;
-      }
-      lin += wj * m.x;
+      lin += a.w[m.j] * m.x;
     }
     __syncthreads();
     if (tid == 0) {
@@ -114,8 +105,8 @@ __global__ void __launch_bounds__(FFM_THREADS, 1) ffm_rows_kernel(const FfmArgs 
       // stable by position: serial fill keeps the order deterministic (rows are short)
       for (int u = 0; u < z; u++) sOrd[sCursor[sMeta[u].f]++] = u;
     }
-    // ---- stage W = the row's feature slices
-    if (MODE != FFM_ADAGRAD) {
+    // ---- stage W = the row's feature slices (AdaGrad: P was refreshed by adagrad_refresh_kernel)
+    {
       if ((SB8 & 1) == 0) {
         const int units = SB8 >> 1, total = z * units;
         for (int v = tid; v < total; v += nth) {
@@ -130,20 +121,6 @@ __global__ void __launch_bounds__(FFM_THREADS, 1) ffm_rows_kernel(const FfmArgs 
         }
       }
       cp_async_wait_all();
-    } else {
-      // adagrad.update (adagrad.nim:87-99): every field x row feature x component entry is refreshed
-      const int total = z * SB8;
-      for (int v = tid; v < total; v += nth) {
-        const int qq = v / SB8, off = v - qq * SB8;
-        const int64_t e = (int64_t)sMeta[qq].j * SB8 + off;
-        double pv = a.P[e];
-        if (!a.first) {
-          const double pn = -(a.eta0 * a.gsP[e]) / (tmpP + sqrt(a.gnP[e]));
-          accViol += fabs(pv - pn);
-          pv = pn;
-        }
-        sW[(size_t)qq * SB8 + off] = pv;
-      }
     }
     __syncthreads();
 
@@ -202,7 +179,6 @@ __global__ void __launch_bounds__(FFM_THREADS, 1) ffm_rows_kernel(const FfmArgs 
     }
     for (int u = tid; u < z; u += nth) {
       const FfmMeta m = sMeta[u];
-      if (MODE == FFM_ADAGRAD) a.touched[m.j] = 1.0;
       if (a.fitLinear) {
         const double gx = coef * m.x;
         atomicAdd(a.gw + m.j, gx);
@@ -536,7 +512,7 @@ int32_t nimfm_ffm_adagrad_init(nimfm_ctx *ctx, nimfm_ffm *m, double eps, int32_t
     CK(cudaMalloc(&m->gnP, (size_t)nP * 8));
     CK(cudaMalloc(&m->gsw, (size_t)d * 8));
     CK(cudaMalloc(&m->gnw, (size_t)d * 8));
-    CK(cudaMalloc(&m->dG, (size_t)(2 * nP + 3 * d + 4) * 8));
+    CK(cudaMalloc(&m->dG, (size_t)(2 * nP + 3 * d + 8) * 8));
     CK(cudaMalloc(&m->adaScal, 64));
   }
   if (fresh || reset) {
@@ -548,7 +524,7 @@ int32_t nimfm_ffm_adagrad_init(nimfm_ctx *ctx, nimfm_ffm *m, double eps, int32_t
     const double sc[2] = {0.0, eps};
     CK(cudaMemcpyAsync(m->adaScal, sc, 16, cudaMemcpyHostToDevice, ctx->stream));
   }
-  CK(cudaMemsetAsync(m->dG, 0, (size_t)(2 * nP + 3 * d + 4) * 8, ctx->stream));
+  CK(cudaMemsetAsync(m->dG, 0, (size_t)(2 * nP + 3 * d + 8) * 8, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
   m->adaReady = true;
@@ -574,38 +550,57 @@ int32_t nimfm_ffm_adagrad_epoch(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_datase
   }
   CK(cudaMemsetAsync(ctx->scalars, 0, 16, ctx->stream));
   double *dGsP = m->dG, *dGnP = m->dG + nP, *dGsw = m->dG + 2 * nP, *dGnw = m->dG + 2 * nP + d;
-  double *touched = m->dG + 2 * nP + 2 * d;
-  double *part = touched + d;
-  const int64_t nDelta = 2 * nP + 3 * d + 4;
+  // delta block [dGsP | dGnP | dGsw | dGnw | loss, sum dL, sum dL^2, -], then per-feature row counts and
+  // the refresh pass's viol (same scheme as nimfm_fm_adagrad_epoch)
+  double *part = m->dG + 2 * nP + 2 * d;
+  double *cntF = part + 4;
+  double *violPart = cntF + d;
+  const int64_t nDelta = 2 * nP + 2 * d + 4;
   const int64_t mb = cfg->miniBatchSize;
   for (int64_t start = 0; start < nRows; start += mb) {
     const int64_t cnt = std::min<int64_t>(mb, nRows - start);
+    const int32_t *rows = idxDev ? idxDev + start : nullptr;
+    const double tIt = (double)(*it - 1);
+    const int first = (*it == 1);
+    if (!first) {
+      // adagrad.update for FFM refreshes all nFields x k entries of every row feature (adagrad.nim:93-99)
+      const int cgrid = (int)std::min<int64_t>((cnt * 32 + 255) / 256, (int64_t)ctx->numSMs * 16);
+      adagrad_count_kernel<<<cgrid < 1 ? 1 : cgrid, 256, 0, ctx->stream>>>(X->indices, X->indptr, X->n, start, cnt, rows,
+                                                                          d, 0, cntF);
+      LAUNCHED(ctx);
+      if ((rc = nimfm_allreduce_sum(ctx, cntF, d))) return rc;
+      const int rgrid = ew_grid(ctx, nP);
+      if ((rc = nimfm_ensure_partials(ctx, (size_t)rgrid * 4))) return rc;
+      adagrad_refresh_kernel<<<rgrid, 256, 0, ctx->stream>>>(m->P, m->gsP, m->gnP, d, SB8, cntF, m->w, m->gsw, m->gnw, d,
+                                                             m->fitLinear, cfg->eta0, tIt, cfg->alpha, cfg->beta,
+                                                             ctx->partials);
+      LAUNCHED(ctx);
+      reduce_partials_kernel<<<1, 256, 0, ctx->stream>>>(ctx->partials, rgrid, violPart, 0);
+      LAUNCHED(ctx);
+    }
     FfmPlan pl;
-    if ((rc = ffm_plan(ctx, m, X, cnt, ffm_rows_kernel<FFM_ADAGRAD>, &pl))) return rc;
-    if ((rc = nimfm_ensure_partials(ctx, (size_t)pl.grid * 4))) return rc;
+    if ((rc = ffm_plan_mode(ctx, m, X, cnt, FFM_ADAGRAD, &pl))) return rc;
+    if ((rc = nimfm_ensure_partials(ctx, (size_t)pl.partialRows * 4))) return rc;
     FfmArgs a;
     ffm_fill_args(a, m, X);
-    a.rowBegin = start; a.nRows = cnt; a.rowIdx = idxDev ? idxDev + start : nullptr;
-    a.gP = dGsP; a.gw = dGsw; a.dGnP = dGnP; a.dGnw = dGnw; a.touched = touched;
+    a.rowBegin = start; a.nRows = cnt; a.rowIdx = rows;
+    a.gP = dGsP; a.gw = dGsw; a.dGnP = dGnP; a.dGnw = dGnw;
     a.partials = ctx->partials;
     a.loss = cfg->loss; a.thr = cfg->huberThreshold;
     a.gsP = m->gsP; a.gnP = m->gnP; a.gsw = m->gsw; a.gnw = m->gnw; a.adaScal = m->adaScal;
-    a.eta0 = cfg->eta0; a.tIt = (double)(*it - 1); a.alpha0 = cfg->alpha0; a.alpha = cfg->alpha; a.beta = cfg->beta;
-    a.first = (*it == 1);
+    a.eta0 = cfg->eta0; a.tIt = tIt; a.alpha0 = cfg->alpha0; a.alpha = cfg->alpha; a.beta = cfg->beta;
+    a.first = first;
     a.CH = pl.CH;
-    ffm_rows_kernel<FFM_ADAGRAD><<<pl.grid, FFM_THREADS, pl.smem, ctx->stream>>>(a);
+    pl.kern<<<pl.grid, pl.block, pl.smem, ctx->stream>>>(a);
     LAUNCHED(ctx);
-    reduce_partials_kernel<<<1, 256, 0, ctx->stream>>>(ctx->partials, pl.grid, part, 0);
+    reduce_partials_kernel<<<1, 256, 0, ctx->stream>>>(ctx->partials, pl.partialRows, part, 0);
     LAUNCHED(ctx);
     if ((rc = nimfm_allreduce_sum(ctx, m->dG, nDelta))) return rc;
-    adagrad_scalar_kernel<<<1, 1, 0, ctx->stream>>>(m->b, m->adaScal, part, ctx->scalars, m->fitIntercept, cfg->eta0,
-                                                    a.tIt, cfg->alpha0, a.first);
+    adagrad_scalar_kernel<<<1, 1, 0, ctx->stream>>>(m->b, m->adaScal, part, violPart, ctx->scalars, m->fitIntercept,
+                                                    cfg->eta0, tIt, cfg->alpha0, first);
     LAUNCHED(ctx);
-    adagrad_apply_kernel<<<ew_grid(ctx, nP), 256, 0, ctx->stream>>>(m->P, m->gsP, m->gnP, dGsP, dGnP, d, SB8, touched,
-                                                                   m->w, m->gsw, m->gnw, dGsw, dGnw, d, m->fitLinear,
-                                                                   cfg->eta0, a.tIt, cfg->alpha, cfg->beta, a.first);
-    LAUNCHED(ctx);
-    fill_kernel<<<ew_grid(ctx, d), 256, 0, ctx->stream>>>(touched, d, 0.0);
+    adagrad_apply_kernel<<<ew_grid(ctx, nP), 256, 0, ctx->stream>>>(m->gsP, m->gnP, dGsP, dGnP, nP, m->gsw, m->gnw, dGsw,
+                                                                   dGnw, d, m->fitLinear, cntF, d);
     LAUNCHED(ctx);
     *it += cnt * (int64_t)ctx->nranks;
   }

@@ -63,6 +63,7 @@ struct RowPlan {
 RowKernel nimfm_row_fast_kernel_predict(int degree, bool explicitLower, int k);
 RowKernel nimfm_row_stream_kernel_predict(int degree, bool explicitLower, int k);
 RowKernel nimfm_row_stream_kernel_grad(int degree, bool explicitLower, int k);
+RowKernel nimfm_row_stream_kernel_adagrad(int degree, bool explicitLower, int k);
 RowKernel nimfm_row_fast_kernel_grad(int degree, bool explicitLower, int k);
 
 static bool is_explicit(const nimfm_fm *fm) { return fm->degree > 2 && fm->nOrders == fm->degree - 1; }
@@ -88,13 +89,14 @@ static int plan_rows(nimfm_ctx *ctx, const nimfm_fm *fm, const nimfm_dataset *X,
   const bool wantFast = env && !strcmp(env, "fast");
   RowKernel fast = nullptr;
   bool stream = false;
-  if (!wantGeneric && mode != MODE_ADAGRAD) {
+  if (!wantGeneric) {
     if (!wantFast && z <= 512) {
       fast = mode == MODE_PREDICT ? nimfm_row_stream_kernel_predict(fm->degree, expl, k)
-                                  : nimfm_row_stream_kernel_grad(fm->degree, expl, k);
+             : mode == MODE_GRAD  ? nimfm_row_stream_kernel_grad(fm->degree, expl, k)
+                                  : nimfm_row_stream_kernel_adagrad(fm->degree, expl, k);
       stream = fast != nullptr;
     }
-    if (!fast) {
+    if (!fast && mode != MODE_ADAGRAD) {
       fast = mode == MODE_PREDICT ? nimfm_row_fast_kernel_predict(fm->degree, expl, k)
                                   : nimfm_row_fast_kernel_grad(fm->degree, expl, k);
       if (fast && (size_t)z * ((size_t)SB8 * 8 + 16) > capPerGroup) fast = nullptr;   // a row does not fit
@@ -104,7 +106,7 @@ static int plan_rows(nimfm_ctx *ctx, const nimfm_fm *fm, const nimfm_dataset *X,
   int64_t CH = z;
   size_t perGroup;
   if (stream) {
-    perGroup = stream_group_smem((int)CH, SB8, nHotTot);
+    perGroup = stream_group_smem((int)CH, SB8, nHotTot, nAcc);
   } else if (fast) {
     perGroup = fast_group_smem((int)CH, SB8, nHotTot);
   } else {
@@ -540,7 +542,7 @@ int32_t nimfm_fm_adagrad_init(nimfm_ctx *ctx, nimfm_fm *fm, double eps, int32_t 
     CK(cudaMalloc(&fm->gnP, (size_t)nP * 8));
     CK(cudaMalloc(&fm->gsw, (size_t)d * 8));
     CK(cudaMalloc(&fm->gnw, (size_t)d * 8));
-    CK(cudaMalloc(&fm->dG, (size_t)(2 * nP + 2 * d + dd + 4) * 8));
+    CK(cudaMalloc(&fm->dG, (size_t)(2 * nP + 2 * d + dd + 8) * 8));
     CK(cudaMalloc(&fm->adaScal, 8 * 8));
   }
   if (fresh || reset) {   // AdaGrad.init, :47-55
@@ -552,7 +554,7 @@ int32_t nimfm_fm_adagrad_init(nimfm_ctx *ctx, nimfm_fm *fm, double eps, int32_t 
     const double sc[2] = {0.0, eps};
     CK(cudaMemcpyAsync(fm->adaScal, sc, 16, cudaMemcpyHostToDevice, ctx->stream));
   }
-  CK(cudaMemsetAsync(fm->dG, 0, (size_t)(2 * nP + 2 * d + dd + 4) * 8, ctx->stream));
+  CK(cudaMemsetAsync(fm->dG, 0, (size_t)(2 * nP + 2 * d + dd + 8) * 8, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
   fm->adaReady = true;
@@ -577,12 +579,35 @@ int32_t nimfm_fm_adagrad_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset
   }
   CK(cudaMemsetAsync(ctx->scalars, 0, 16, ctx->stream));
   double *dGsP = fm->dG, *dGnP = fm->dG + nP, *dGsw = fm->dG + 2 * nP, *dGnw = fm->dG + 2 * nP + d;
-  double *touched = fm->dG + 2 * nP + 2 * d;
-  double *part = touched + dd;              // [loss, sum dL, sum dL^2, viol]
-  const int64_t nDelta = 2 * nP + 2 * d + dd + 4;
+  // delta block: [dGsP | dGnP | dGsw | dGnw | loss, sum dL, sum dL^2, - ] (one all-reduce), then the
+  // per-feature row counts of the batch (their own small all-reduce) and the refresh pass's viol
+  double *part = fm->dG + 2 * nP + 2 * d;
+  double *cntF = part + 4;
+  double *violPart = cntF + dd;
+  const int64_t nDelta = 2 * nP + 2 * d + 4;
   const int64_t mb = cfg->miniBatchSize;
+  const int SB8 = fm->nOrders * fm->k;
   for (int64_t start = 0; start < nRows; start += mb) {
     const int64_t cnt = std::min<int64_t>(mb, nRows - start);
+    const int32_t *rows = idxDev ? idxDev + start : nullptr;
+    const double tIt = (double)(*it - 1);
+    const int first = (*it == 1);
+    if (!first) {
+      // update() (adagrad.nim:87-110), once per touched feature: count -> all-reduce -> refresh
+      const int cgrid = (int)std::min<int64_t>((cnt * 32 + 255) / 256, (int64_t)ctx->numSMs * 16);
+      adagrad_count_kernel<<<cgrid < 1 ? 1 : cgrid, 256, 0, ctx->stream>>>(X->indices, X->indptr, X->n, start, cnt, rows,
+                                                                          d, fm->nAug, cntF);
+      LAUNCHED(ctx);
+      if ((rc = nimfm_allreduce_sum(ctx, cntF, dd))) return rc;
+      const int rgrid = ew_grid(ctx, nP);
+      if ((rc = nimfm_ensure_partials(ctx, (size_t)rgrid * 4))) return rc;
+      adagrad_refresh_kernel<<<rgrid, 256, 0, ctx->stream>>>(fm->P, fm->gsP, fm->gnP, dd, SB8, cntF, fm->w, fm->gsw,
+                                                             fm->gnw, d, fm->fitLinear, cfg->eta0, tIt, cfg->alpha,
+                                                             cfg->beta, ctx->partials);
+      LAUNCHED(ctx);
+      reduce_partials_kernel<<<1, 256, 0, ctx->stream>>>(ctx->partials, rgrid, violPart, 0);
+      LAUNCHED(ctx);
+    }
     RowPlan pl;
     if ((rc = plan_rows(ctx, fm, X, cnt, MODE_ADAGRAD, &pl))) return rc;
     RowKernel kern = pl.kern;
@@ -591,7 +616,7 @@ int32_t nimfm_fm_adagrad_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset
     fill_row_args(a, fm, X);
     a.rowBegin = start;
     a.nRows = cnt;
-    a.rowIdx = idxDev ? idxDev + start : nullptr;
+    a.rowIdx = rows;
     a.gP = dGsP;
     a.gw = dGsw;
     a.dGnP = dGnP;
@@ -600,25 +625,21 @@ int32_t nimfm_fm_adagrad_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset
     a.loss = cfg->loss;
     a.thr = cfg->huberThreshold;
     a.gsP = fm->gsP; a.gnP = fm->gnP; a.gsw = fm->gsw; a.gnw = fm->gnw; a.adaScal = fm->adaScal;
-    a.touched = touched;
-    a.eta0 = cfg->eta0; a.tIt = (double)(*it - 1); a.alpha0 = cfg->alpha0; a.alpha = cfg->alpha; a.beta = cfg->beta;
-    a.first = (*it == 1);
+    a.eta0 = cfg->eta0; a.tIt = tIt; a.alpha0 = cfg->alpha0; a.alpha = cfg->alpha; a.beta = cfg->beta;
+    a.first = first;
     a.G = pl.G;
     a.CH = pl.CH;
     kern<<<pl.grid, pl.block, pl.smem, ctx->stream>>>(a);
     LAUNCHED(ctx);
     reduce_partials_kernel<<<1, 256, 0, ctx->stream>>>(ctx->partials, pl.nWarps, part, 0);
     LAUNCHED(ctx);
-    // synchronous data parallelism: all-reduce the deltas [dGs | dGn | dGsw | dGnw | loss, dL, dL^2, viol]
+    // synchronous data parallelism: all-reduce the deltas [dGs | dGn | dGsw | dGnw | loss, dL, dL^2, -]
     if ((rc = nimfm_allreduce_sum(ctx, fm->dG, nDelta))) return rc;
-    adagrad_scalar_kernel<<<1, 1, 0, ctx->stream>>>(fm->b, fm->adaScal, part, ctx->scalars, fm->fitIntercept, cfg->eta0,
-                                                    a.tIt, cfg->alpha0, a.first);
+    adagrad_scalar_kernel<<<1, 1, 0, ctx->stream>>>(fm->b, fm->adaScal, part, violPart, ctx->scalars, fm->fitIntercept,
+                                                    cfg->eta0, tIt, cfg->alpha0, first);
     LAUNCHED(ctx);
-    adagrad_apply_kernel<<<ew_grid(ctx, nP), 256, 0, ctx->stream>>>(
-        fm->P, fm->gsP, fm->gnP, dGsP, dGnP, dd, fm->nOrders * fm->k, touched, fm->w, fm->gsw, fm->gnw, dGsw, dGnw,
-        d, fm->fitLinear, cfg->eta0, a.tIt, cfg->alpha, cfg->beta, a.first);
-    LAUNCHED(ctx);
-    fill_kernel<<<ew_grid(ctx, dd), 256, 0, ctx->stream>>>(touched, dd, 0.0);
+    adagrad_apply_kernel<<<ew_grid(ctx, nP), 256, 0, ctx->stream>>>(fm->gsP, fm->gnP, dGsP, dGnP, nP, fm->gsw, fm->gnw,
+                                                                   dGsw, dGnw, d, fm->fitLinear, cntF, dd);
     LAUNCHED(ctx);
     *it += cnt * (int64_t)ctx->nranks;
   }

@@ -113,10 +113,7 @@ __global__ void __launch_bounds__(256, 1) fm_rows_kernel(const RowArgs a) {
 
   // AdaGrad: the intercept every row of this batch sees (adagrad.nim:101-105)
   double bias = a.b[0];
-  double tmpP = 0.0, denW = 0.0;
   if (MODE == MODE_ADAGRAD) {
-    tmpP = a.eta0 * a.tIt * a.beta;
-    denW = a.tIt * a.eta0 * a.alpha;
     if (!a.first && a.fitIntercept) {
       double den = sqrt(a.adaScal[1]) + a.eta0 * a.tIt * a.alpha0;
       bias = -a.eta0 * a.adaScal[0] / den;
@@ -135,7 +132,6 @@ __global__ void __launch_bounds__(256, 1) fm_rows_kernel(const RowArgs a) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) zmax = max(zmax, __shfl_xor_sync(0xffffffffu, zmax, off));
     const int nChunks = (zmax + CH - 1) / CH;
-    bool violPass = true;  // count AdaGrad viol only the first time an element is staged
 
     // ---- stage chunk c of every group of this warp (warp-uniform call)
     auto stage = [&](int c, bool withLinear, double &lin) {
@@ -159,61 +155,33 @@ __global__ void __launch_bounds__(256, 1) fm_rows_kernel(const RowArgs a) {
         if (MODE != MODE_PREDICT)
           sSlot[u] = pos >= zReal ? (unsigned char)(a.nHot + (pos - zReal))
                                   : (a.hotSlot ? a.hotSlot[j] : (unsigned char)NIMFM_COLD);
-        if (withLinear && pos < zReal) {
-          if (MODE == MODE_ADAGRAD) {
-            double wj = a.w[j];
-            if (!a.first && a.fitLinear) {  // fitLinearAdaGrad, fit_linear.nim:50-57
-              double wn = -a.eta0 * a.gsw[j] / (denW + sqrt(a.gnw[j]));
-              accViol += fabs(wj - wn);
-              wj = wn;
-            }
-            lin += wj * x;
-          } else {
-            lin += a.w[j] * x;
-          }
-        }
+        if (withLinear && pos < zReal) lin += a.w[j] * x;
       }
       __syncwarp();
-      if (MODE != MODE_ADAGRAD) {
-        if ((SB8 & 1) == 0) {
-          const int units = SB8 >> 1;
-          const int total = cnt * units;
-          if ((units & (units - 1)) == 0) {
-            const int sh = __ffs(units) - 1;
-            for (int u = gl; u < total; u += G) {
-              const int qq = u >> sh, off = (u & (units - 1)) << 1;
-              cp_async16(sP + (size_t)qq * SB8 + off, a.P + (int64_t)sIdx[qq] * SB8 + off);
-            }
-          } else {
-            for (int u = gl; u < total; u += G) {
-              const int qq = u / units, off = (u - qq * units) << 1;
-              cp_async16(sP + (size_t)qq * SB8 + off, a.P + (int64_t)sIdx[qq] * SB8 + off);
-            }
+      // (AdaGrad: P was refreshed from (g_sum, g_norm, t) by adagrad_refresh_kernel before this launch)
+      if ((SB8 & 1) == 0) {
+        const int units = SB8 >> 1;
+        const int total = cnt * units;
+        if ((units & (units - 1)) == 0) {
+          const int sh = __ffs(units) - 1;
+          for (int u = gl; u < total; u += G) {
+            const int qq = u >> sh, off = (u & (units - 1)) << 1;
+            cp_async16(sP + (size_t)qq * SB8 + off, a.P + (int64_t)sIdx[qq] * SB8 + off);
           }
         } else {
-          const int total = cnt * SB8;
           for (int u = gl; u < total; u += G) {
-            const int qq = u / SB8, off = u - qq * SB8;
-            cp_async8(sP + (size_t)qq * SB8 + off, a.P + (int64_t)sIdx[qq] * SB8 + off);
+            const int qq = u / units, off = (u - qq * units) << 1;
+            cp_async16(sP + (size_t)qq * SB8 + off, a.P + (int64_t)sIdx[qq] * SB8 + off);
           }
         }
-        cp_async_wait_all();
       } else {
-        // AdaGrad: the slice is a pure function of (g_sum, g_norm, t) (adagrad.nim:87-99)
         const int total = cnt * SB8;
         for (int u = gl; u < total; u += G) {
           const int qq = u / SB8, off = u - qq * SB8;
-          const int64_t e = (int64_t)sIdx[qq] * SB8 + off;
-          double pv = a.P[e];
-          if (!a.first) {
-            const double den = tmpP + sqrt(a.gnP[e]);
-            const double pn = -(a.eta0 * a.gsP[e]) / den;
-            if (violPass) accViol += fabs(pv - pn);
-            pv = pn;
-          }
-          sP[(size_t)qq * SB8 + off] = pv;
+          cp_async8(sP + (size_t)qq * SB8 + off, a.P + (int64_t)sIdx[qq] * SB8 + off);
         }
       }
+      cp_async_wait_all();
       __syncwarp();
     };
 
@@ -274,7 +242,6 @@ __global__ void __launch_bounds__(256, 1) fm_rows_kernel(const RowArgs a) {
     double part = 0.0;
     for (int sc = 0; sc < NS; ++sc) {
       part += fwd_all(sc, A, sc == 0, lin);
-      violPass = false;
     }
     // (for nChunks == 1 the staged slice stays resident for the backward pass)
     const double yhat = bias + group_sum(lin + part, G);
@@ -348,7 +315,6 @@ __global__ void __launch_bounds__(256, 1) fm_rows_kernel(const RowArgs a) {
             // linear-term gradient (real features only) and AdaGrad touched flags
             for (int u = gl; u < cnt; u += G) {
               const int j = sIdx[u];
-              if (MODE == MODE_ADAGRAD) a.touched[j] = 1.0;
               if (a.fitLinear && j < a.d && sSlot[u] == NIMFM_COLD) {
                 const double gx = coef * sVal[u];
                 atomicAdd(a.gw + j, gx);

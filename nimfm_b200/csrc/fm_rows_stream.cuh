@@ -14,14 +14,16 @@
 #pragma once
 #include "fm_rows_fast.cuh"
 
-__host__ __device__ inline size_t stream_group_smem(int CH, int SB8, int nHotTot) {
-  size_t b = (size_t)CH * sizeof(NnzMeta) + (size_t)nHotTot * (SB8 + 1) * 8;
+__host__ __device__ inline size_t stream_group_smem(int CH, int SB8, int nHotTot, int nAcc) {
+  size_t b = (size_t)CH * sizeof(NnzMeta) + (size_t)nHotTot * (SB8 + 1) * 8 * (nAcc > 0 ? nAcc : 1);
   return (b + 15) & ~(size_t)15;
 }
 
 template <int DEGREE, bool EXPLICIT, int MODE, int KT>
 __global__ void __launch_bounds__(256, 2) fm_rows_stream_kernel(const RowArgs a) {
-  static_assert(MODE == MODE_PREDICT || MODE == MODE_GRAD, "stream path: predict / grad only");
+  // MODE_ADAGRAD = MODE_GRAD with coef = dloss (adagrad.nim:113-124) and a second scatter of the
+  // squared gradient into the g_norm delta block; P was refreshed by adagrad_refresh_kernel.
+  constexpr int NACC = (MODE == MODE_ADAGRAD) ? 2 : 1;
   constexpr int NO = RowCfg<DEGREE, EXPLICIT>::NO;
   constexpr int G = KT;
   constexpr int GPW = 32 / G;
@@ -35,19 +37,22 @@ __global__ void __launch_bounds__(256, 2) fm_rows_stream_kernel(const RowArgs a)
   const int gidInWarp = lane / G;
   const int CH = a.CH;
   const int nHotTot = (MODE == MODE_PREDICT) ? 0 : a.nHot + a.nAug;
-  const size_t perGroup = stream_group_smem(CH, SB8, nHotTot);
+  const size_t perGroup = stream_group_smem(CH, SB8, nHotTot, NACC);
   unsigned char *base = smem_raw + (size_t)(warpInBlock * GPW + gidInWarp) * perGroup;
   NnzMeta *sMeta = reinterpret_cast<NnzMeta *>(base);
   double *sAcc = reinterpret_cast<double *>(sMeta + CH);
-  for (int e = gl; e < nHotTot * ASTR; e += G) sAcc[e] = 0.0;
+  double *sAccN = sAcc + (size_t)nHotTot * ASTR;   // AdaGrad only
+  for (int e = gl; e < nHotTot * ASTR * NACC; e += G) sAcc[e] = 0.0;
   __syncwarp();
 
   const int warpsPerBlock = blockDim.x >> 5;
   const int64_t warpGlobal = (int64_t)blockIdx.x * warpsPerBlock + warpInBlock;
   const int64_t nWarps = (int64_t)gridDim.x * warpsPerBlock;
   const int64_t tiles = (a.nRows + GPW - 1) / GPW;
-  double accLoss = 0.0, accB1 = 0.0;
-  const double bias = a.b[0];
+  double accLoss = 0.0, accB1 = 0.0, accB2 = 0.0;
+  double bias = a.b[0];
+  if (MODE == MODE_ADAGRAD && !a.first && a.fitIntercept)   // the intercept every row of the batch sees
+    bias = -a.eta0 * a.adaScal[0] / (sqrt(a.adaScal[1]) + a.eta0 * a.tIt * a.alpha0);
   const double *__restrict__ Pg = a.P + gl;
 
   for (int64_t tile = warpGlobal; tile < tiles; tile += nWarps) {
@@ -145,13 +150,16 @@ __global__ void __launch_bounds__(256, 2) fm_rows_stream_kernel(const RowArgs a)
     if (active) {
       if (a.yOut && gl == 0) a.yOut[q] = yhat;
       const double yi = a.y[r];
-      coef = dev_dloss(a.loss, a.thr, yi, yhat) / a.mb;
+      const double dL = dev_dloss(a.loss, a.thr, yi, yhat);
+      coef = (MODE == MODE_GRAD) ? dL / a.mb : dL;
       if (gl == 0) {
         accLoss += dev_loss(a.loss, a.thr, yi, yhat);
         accB1 += coef;
+        accB2 += dL * dL;
       }
     }
     double *__restrict__ gPg = a.gP + gl;
+    double *__restrict__ gNg = (MODE == MODE_ADAGRAD) ? a.dGnP + gl : nullptr;
     for (int c = 0; c < zmax; c += U) {
       double p[NO][U];
 #pragma unroll
@@ -185,10 +193,19 @@ __global__ void __launch_bounds__(256, 2) fm_rows_stream_kernel(const RowArgs a)
             double *ac = sAcc + m.acc + gl;
 #pragma unroll
             for (int o = 0; o < NO; ++o) ac[o * KT] += gr[o];
-          } else {
-            double *gp = gPg + (int64_t)m.j * SB8;
+            if (MODE == MODE_ADAGRAD) {
+              double *an = sAccN + m.acc + gl;
 #pragma unroll
-            for (int o = 0; o < NO; ++o) atomicAdd(gp + o * KT, gr[o]);
+              for (int o = 0; o < NO; ++o) an[o * KT] += gr[o] * gr[o];
+            }
+          } else {
+            const int64_t eo = (int64_t)m.j * SB8;
+#pragma unroll
+            for (int o = 0; o < NO; ++o) atomicAdd(gPg + eo + o * KT, gr[o]);
+            if (MODE == MODE_ADAGRAD) {
+#pragma unroll
+              for (int o = 0; o < NO; ++o) atomicAdd(gNg + eo + o * KT, gr[o] * gr[o]);
+            }
           }
         }
       }
@@ -198,8 +215,13 @@ __global__ void __launch_bounds__(256, 2) fm_rows_stream_kernel(const RowArgs a)
       for (int u = gl; u < zReal; u += G) {
         const NnzMeta m = sMeta[u];
         const double gx = coef * m.x;
-        if (m.acc >= 0) atomicAdd(sAcc + m.acc + SB8, gx);
-        else atomicAdd(a.gw + m.j, gx);
+        if (m.acc >= 0) {
+          atomicAdd(sAcc + m.acc + SB8, gx);
+          if (MODE == MODE_ADAGRAD) atomicAdd(sAccN + m.acc + SB8, gx * gx);
+        } else {
+          atomicAdd(a.gw + m.j, gx);
+          if (MODE == MODE_ADAGRAD) atomicAdd(a.dGnw + m.j, gx * gx);
+        }
       }
     }
   }
@@ -212,18 +234,27 @@ __global__ void __launch_bounds__(256, 2) fm_rows_stream_kernel(const RowArgs a)
       for (int o = 0; o < NO; ++o) {
         const double v = sAcc[slot * ASTR + o * KT + gl];
         if (v != 0.0) atomicAdd(a.gP + j * SB8 + o * KT + gl, v);
+        if (MODE == MODE_ADAGRAD) {
+          const double v2 = sAccN[slot * ASTR + o * KT + gl];
+          if (v2 != 0.0) atomicAdd(a.dGnP + j * SB8 + o * KT + gl, v2);
+        }
       }
       if (gl == 0 && a.fitLinear && j < a.d) {
         const double v = sAcc[slot * ASTR + SB8];
         if (v != 0.0) atomicAdd(a.gw + j, v);
+        if (MODE == MODE_ADAGRAD) {
+          const double v2 = sAccN[slot * ASTR + SB8];
+          if (v2 != 0.0) atomicAdd(a.dGnw + j, v2);
+        }
       }
     }
     accLoss = warp_sum(accLoss);
     accB1 = warp_sum(accB1);
+    accB2 = warp_sum(accB2);
     if (lane == 0) {
       a.partials[warpGlobal * 4 + 0] = accLoss;
       a.partials[warpGlobal * 4 + 1] = accB1;
-      a.partials[warpGlobal * 4 + 2] = 0.0;
+      a.partials[warpGlobal * 4 + 2] = accB2;
       a.partials[warpGlobal * 4 + 3] = 0.0;
     }
   }
