@@ -75,8 +75,21 @@ int32_t nimfm_csr_upload(nimfm_ctx *ctx, int64_t n, int64_t d, const double *dat
                          int64_t nFields, int64_t rowBegin, int64_t rowEnd, nimfm_dataset **out);
 int32_t nimfm_csc_upload(nimfm_ctx *ctx, int64_t n, int64_t d, const double *data,
                          const int64_t *indices, const int64_t *indptr, nimfm_dataset **out);
-/* toCSCDataset / toCSRDataset (dataset.nim:406-427 -> tensor/sparse.nim:490-527): stable counting sort */
+/* toCSCDataset / toCSRDataset (dataset.nim:418-427 -> tensor/sparse.nim:490-527): stable counting sort,
+ * run on the device as a stable radix sort by the other axis (bit-exact: same indptr, same order) */
 int32_t nimfm_dataset_transpose(nimfm_ctx *ctx, const nimfm_dataset *in, nimfm_dataset **out);
+/* X[indicesRow] for CSRDataset / CSRFieldDataset (dataset.nim:319-367 -> tensor/sparse.nim:263-285).
+ * Targets set on `in` are gathered too (== shuffle(X, y, indices), dataset.nim:372-381).  Out-of-range
+ * ids fail with the reference's messages (sparse.nim:254-260). */
+int32_t nimfm_dataset_take_rows(nimfm_ctx *ctx, const nimfm_dataset *in, const int64_t *rowIdx,
+                                int64_t nIdx, nimfm_dataset **out);
+/* X[first..last], INCLUSIVE like Nim's Slice (dataset.nim:328-348): CSR kinds gather the rows; a CSC
+ * is filtered per column in O(nnz) with row ids rebased (tensor/sparse.nim:300-325). */
+int32_t nimfm_dataset_slice_rows(nimfm_ctx *ctx, const nimfm_dataset *in, int64_t first, int64_t last,
+                                 nimfm_dataset **out);
+/* vstack (dataset.nim:452-483 -> tensor/sparse.nim:564-640): all parts of one kind and nFeatures */
+int32_t nimfm_dataset_vstack(nimfm_ctx *ctx, const nimfm_dataset *const *parts, int32_t nParts,
+                             nimfm_dataset **out);
 /* targets of fit(X, y, fm); length = nSamples of the (shard of the) dataset */
 int32_t nimfm_dataset_set_targets(nimfm_ctx *ctx, nimfm_dataset *ds, const double *y);
 int32_t nimfm_dataset_info(const nimfm_dataset *ds, int64_t *n, int64_t *d, int64_t *nnz,

@@ -60,6 +60,12 @@ proc nimfm_csr_upload(ctx: Ctx, n, d: int64, data: ptr cdouble, indices, indptr,
 proc nimfm_csc_upload(ctx: Ctx, n, d: int64, data: ptr cdouble, indices, indptr: ptr int64,
                       outDs: ptr DeviceDataset): int32
 proc nimfm_dataset_transpose(ctx: Ctx, src: DeviceDataset, outDs: ptr DeviceDataset): int32
+proc nimfm_dataset_take_rows(ctx: Ctx, src: DeviceDataset, rowIdx: ptr int64, nIdx: int64,
+                             outDs: ptr DeviceDataset): int32   # X[indicesRow], dataset.nim:319-367
+proc nimfm_dataset_slice_rows(ctx: Ctx, src: DeviceDataset, first, last: int64,
+                              outDs: ptr DeviceDataset): int32  # X[a..b], dataset.nim:328-348
+proc nimfm_dataset_vstack(ctx: Ctx, parts: ptr DeviceDataset, nParts: int32,
+                          outDs: ptr DeviceDataset): int32      # vstack, dataset.nim:452-483
 proc nimfm_dataset_set_targets(ctx: Ctx, ds: DeviceDataset, y: ptr cdouble): int32
 proc nimfm_dataset_free(ctx: Ctx, ds: DeviceDataset): int32
 proc nimfm_fm_create(ctx: Ctx, degree, nComponents, nOrders, nAugments: int32, nFeatures: int64,

@@ -5,7 +5,7 @@ nim/nimfm_cuda.nim.  There is no CPU fallback."""
 from . import _lib
 from ._lib import NimfmCudaError
 from .dataset import (CSCDataset, CSRDataset, CSRFieldDataset, newCSCDataset, newCSRDataset,
-                      newCSRFieldDataset, toCSCDataset, toCSRDataset)
+                      newCSRFieldDataset, shuffle, toCSCDataset, toCSRDataset, vstack)
 from .loss import (Huber, Logistic, Squared, SquaredHinge, newHuber, newLogistic, newSquared,
                    newSquaredHinge)
 from .model import (FactorizationMachine, FieldAwareFactorizationMachine, NotFittedError, augment,

@@ -61,6 +61,9 @@ SYMBOLS = {
     "nimfm_csr_upload": (c_i32, [VP, c_i64, c_i64, VP, VP, VP, VP, c_i64, c_i64, c_i64, PVP]),
     "nimfm_csc_upload": (c_i32, [VP, c_i64, c_i64, VP, VP, VP, PVP]),
     "nimfm_dataset_transpose": (c_i32, [VP, VP, PVP]),
+    "nimfm_dataset_take_rows": (c_i32, [VP, VP, VP, c_i64, PVP]),
+    "nimfm_dataset_slice_rows": (c_i32, [VP, VP, c_i64, c_i64, PVP]),
+    "nimfm_dataset_vstack": (c_i32, [VP, PVP, c_i32, PVP]),
     "nimfm_dataset_set_targets": (c_i32, [VP, VP, VP]),
     "nimfm_dataset_info": (c_i32, [VP, PI64, PI64, PI64, C.POINTER(c_i32), PI64, PI64]),
     "nimfm_dataset_download": (c_i32, [VP, VP, VP, VP, VP, VP]),

@@ -132,6 +132,9 @@ int nimfm_ensure_partials(nimfm_ctx *ctx, size_t nDoubles);
 int nimfm_ensure_idx(nimfm_ctx *ctx, size_t n);
 int nimfm_allreduce_sum(nimfm_ctx *ctx, double *buf, int64_t n);
 
+// hot-column table upload (dataset.cu)
+int nimfm_upload_hot(nimfm_ctx *ctx, const std::vector<int32_t> &hot, int64_t d, uint8_t **hotSlot, int32_t **hotList);
+
 // upload host int64 row ids into ctx->idx32Scratch as int32 (validated against n)
 int nimfm_stage_row_ids(nimfm_ctx *ctx, const int64_t *ids, int64_t count, int64_t n);
 

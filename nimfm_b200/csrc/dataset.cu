@@ -1,6 +1,6 @@
 // dataset.cu -- device-resident CSR / CSC / CSR-with-fields containers.
-// Integer bookkeeping only: index narrowing int64 -> int32, row-shard rebasing (X[slice],
-// tensor/sparse.nim:263-290) and the stable counting-sort transpose (sparse.nim:490-527).
+// Integer bookkeeping only: index narrowing int64 -> int32 and row-shard rebasing (X[slice],
+// tensor/sparse.nim:263-290).  Row gather / CSC slice / vstack / transpose live in dataset_ops.cu.
 #include <algorithm>
 #include <unordered_map>
 
@@ -171,43 +171,6 @@ int32_t nimfm_dataset_download(nimfm_ctx *ctx, const nimfm_dataset *ds, double *
     CK(cudaMemcpy(tmp.data(), ds->fields, (size_t)ds->nnz * 4, cudaMemcpyDeviceToHost));
     for (int64_t q = 0; q < ds->nnz; q++) fields[q] = tmp[q];
   }
-  return NIMFM_OK;
-}
-
-// toCSCMatrix / toCSRMatrix (tensor/sparse.nim:490-527): counting sort by the other axis, stable in
-// segment order.  Runs on the host inside the library (O(nnz) integer work, done once per dataset).
-int32_t nimfm_dataset_transpose(nimfm_ctx *ctx, const nimfm_dataset *in, nimfm_dataset **out) {
-  if (!ctx || !in) return NIMFM_ERR_INVALID;
-  REQUIRE(out != nullptr, "out is NULL");
-  REQUIRE(in->kind != NIMFM_DS_CSR_FIELD, "transpose of field datasets is not supported");
-  CK(cudaSetDevice(ctx->device));
-  const bool toCsc = in->kind == NIMFM_DS_CSR;
-  const int64_t nsIn = toCsc ? in->n : in->d, nsOut = toCsc ? in->d : in->n, nnz = in->nnz;
-  std::vector<double> data((size_t)nnz), odata((size_t)nnz);
-  std::vector<int32_t> idx((size_t)nnz);
-  std::vector<int64_t> ptr((size_t)nsIn + 1), optr((size_t)nsOut + 1, 0), oidx((size_t)nnz), offs((size_t)nsOut, 0);
-  CK(cudaMemcpy(data.data(), in->data, (size_t)nnz * 8, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(idx.data(), in->indices, (size_t)nnz * 4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(ptr.data(), in->indptr, ((size_t)nsIn + 1) * 8, cudaMemcpyDeviceToHost));
-  for (int64_t q = 0; q < nnz; q++) optr[(size_t)idx[q] + 1] += 1;
-  for (int64_t s = 0; s < nsOut; s++) optr[s + 1] += optr[s];
-  for (int64_t s = 0; s < nsIn; s++)
-    for (int64_t q = ptr[s]; q < ptr[s + 1]; q++) {
-      const int64_t t = idx[q];
-      odata[optr[t] + offs[t]] = data[q];
-      oidx[optr[t] + offs[t]] = s;
-      offs[t] += 1;
-    }
-  nimfm_dataset *o = nullptr;
-  int rc = toCsc ? nimfm_csc_upload(ctx, in->n, in->d, odata.data(), oidx.data(), optr.data(), &o)
-                 : nimfm_csr_upload(ctx, in->n, in->d, odata.data(), oidx.data(), optr.data(), nullptr, 0, 0,
-                                    in->n, &o);
-  if (rc) return rc;
-  if (in->y) {
-    CK(cudaMalloc(&o->y, (size_t)(o->n ? o->n : 1) * 8));
-    CK(cudaMemcpy(o->y, in->y, (size_t)o->n * 8, cudaMemcpyDeviceToDevice));
-  }
-  *out = o;
   return NIMFM_OK;
 }
 

@@ -87,6 +87,29 @@ class BaseDataset:
                                                       _lib.ptr(fields)))
         return data, indices, indptr, fields
 
+    # ---- X[indicesRow] / X[a..b] (dataset.nim:319-367; Nim slices are INCLUSIVE, Python's are not:
+    # X[2:5] here == X[2..4] there)
+    def __getitem__(self, key):
+        if isinstance(key, slice):
+            if key.step not in (None, 1):
+                raise ValueError("only contiguous slices are supported")
+            a = 0 if key.start is None else int(key.start)
+            b = self._n if key.stop is None else int(key.stop)
+            a = a + self._n if a < 0 else a
+            b = b + self._n if b < 0 else b
+            h = C.c_void_p()
+            _lib.check(_lib.load().nimfm_dataset_slice_rows(_lib.ctx(), self.handle(), a, b - 1, C.byref(h)))
+            return _adopt(h, type(self), self)
+        idx = _lib.i64(key)
+        if self.kind == _lib.DS_CSC:
+            # tensor/sparse.nim:298-299: "Accessing row vectors by openarray is not supported for CSCMatrix"
+            raise ValueError("Accessing row vectors by an index array is not supported for CSCDataset")
+        if len(idx) == 0:
+            raise ValueError("indicesRow is empty")      # max([]) raises in the reference (sparse.nim:255)
+        h = C.c_void_p()
+        _lib.check(_lib.load().nimfm_dataset_take_rows(_lib.ctx(), self.handle(), _lib.ptr(idx), len(idx), C.byref(h)))
+        return _adopt(h, type(self), self)
+
     def free(self):
         if self._handle is not None:
             _lib.load().nimfm_dataset_free(_lib.ctx(), self._handle)
@@ -143,6 +166,40 @@ def newCSCDataset(data, indices, indptr, nSamples, nFeatures):
 
 def newCSRFieldDataset(data, indices, indptr, fields, nSamples, nFeatures, nFields):
     return CSRFieldDataset(data, indices, indptr, nSamples, nFeatures, fields=fields, nFields=nFields)
+
+
+def _adopt(h, cls, like):
+    """Wrap a library-made dataset handle: host arrays are read back so it behaves like any other."""
+    out = cls.__new__(cls)
+    out._handle = h
+    out._y_id = None
+    inf = BaseDataset.info(out)
+    out._n, out._d, out._nFields = inf["n"], inf["d"], inf["nFields"]
+    out.data, out.indices, out.indptr, out.fields = BaseDataset.download(out)
+    return out
+
+
+def vstack(*datasets):
+    """vstack (dataset.nim:452-483 -> tensor/sparse.nim:564-640)"""
+    if len(datasets) == 1 and isinstance(datasets[0], (list, tuple)):
+        datasets = tuple(datasets[0])
+    if not datasets:
+        raise ValueError("vstack needs at least one dataset")
+    arr = (C.c_void_p * len(datasets))(*[X.handle() for X in datasets])
+    h = C.c_void_p()
+    _lib.check(_lib.load().nimfm_dataset_vstack(_lib.ctx(), arr, len(datasets), C.byref(h)))
+    return _adopt(h, type(datasets[0]), datasets[0])
+
+
+def shuffle(X, y, indices=None, rng=None):
+    """shuffle(X, y[, indices]) (dataset.nim:372-395): X[indices], y[indices].  Without `indices` a
+    permutation is drawn from `rng` (numpy Generator; Nim's RNG stream is unpinned)."""
+    y = np.asarray(y)
+    if indices is None:
+        rng = np.random.default_rng() if rng is None else rng
+        indices = rng.permutation(X.nSamples)
+    indices = _lib.i64(indices)
+    return X[indices], y[indices]
 
 
 def _transposed(src, cls):

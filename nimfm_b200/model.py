@@ -118,6 +118,83 @@ class FactorizationMachine(_FMBase):
         return out
 
 
+    def dump(self, fname):                     # factorization_machine.nim:142-165 (same text layout)
+        self.checkInitialized()
+        P = _lib.f64(self.P)
+        with open(fname, "w") as f:
+            f.write(f"task: {self.task}\n")
+            f.write(f"nFeatures: {P.shape[2] - self.nAugments}\n")
+            f.write(f"degree: {self.degree}\n")
+            f.write(f"nComponents: {self.nComponents}\n")
+            f.write(f"fitLower: {self.fitLower}\n")
+            f.write(f"fitIntercept: {_nim_bool(self.fitIntercept)}\n")
+            f.write(f"fitLinear: {_nim_bool(self.fitLinear)}\n")
+            f.write(f"randomState: {int(self.randomState)}\n")
+            f.write(f"scale: {_nim_float(self.scale)}\n")
+            f.write("lams:\n")
+            f.write(_join(self.lams) + "\n")
+            for order in range(P.shape[0]):
+                f.write(f"P[{order}]:\n")
+                for s in range(self.nComponents):
+                    f.write(_join(P[order, s]) + "\n")
+            f.write("w:\n")
+            f.write(_join(self.w) + "\n")
+            f.write(f"intercept: {_nim_float(self.intercept)}\n")
+
+    @classmethod
+    def load(cls, fname, warmStart=False):     # factorization_machine.nim:168-220
+        with open(fname) as f:
+            val = lambda: f.readline().rstrip("\n").split(" ")[1]
+            task = val()
+            nFeatures, degree, nComponents = int(val()), int(val()), int(val())
+            fitLower = val()
+            fitIntercept, fitLinear = _parse_bool(val()), _parse_bool(val())
+            randomState, scale = int(val()), float(val())
+            fm = cls(task, degree, nComponents, fitLower, fitIntercept, fitLinear, warmStart, randomState, scale)
+            f.readline()                                               # "lams:"
+            fm.lams = _parse_row(f.readline(), nComponents)
+            dd = nFeatures + fm.nAugments
+            fm.P = np.zeros((fm.nOrders, nComponents, dd))
+            for order in range(fm.nOrders):
+                f.readline()                                           # "P[order]:"
+                for s in range(nComponents):
+                    fm.P[order, s] = _parse_row(f.readline(), dd)
+            f.readline()                                               # "w:"
+            fm.w = _parse_row(f.readline(), nFeatures)
+            fm.intercept = float(f.readline().rstrip("\n").split(" ")[1])
+        fm.isInitialized = True
+        return fm
+
+
+def _nim_bool(b):
+    return "true" if b else "false"
+
+
+def _parse_bool(s):                            # strutils.parseBool
+    t = s.strip().lower()
+    if t in ("y", "yes", "true", "1", "on"):
+        return True
+    if t in ("n", "no", "false", "0", "off"):
+        return False
+    raise ValueError(f"cannot interpret as a bool: {s}")
+
+
+def _nim_float(x):
+    """Shortest round-trip decimal, as Nim's `$` (float64)."""
+    return repr(float(x))
+
+
+def _join(v):
+    return " ".join(_nim_float(x) for x in np.asarray(v, dtype=np.float64).ravel())
+
+
+def _parse_row(line, count):
+    vals = np.array(line.split(), dtype=np.float64)
+    if len(vals) < count:
+        raise ValueError(f"expected {count} values, found {len(vals)}")
+    return vals[:count].copy()
+
+
 def newFactorizationMachine(task, degree=2, nComponents=30, fitLower=explicit, fitIntercept=True,
                             fitLinear=True, warmStart=False, randomState=1, scale=0.01):
     """factorization_machine.nim:43-78"""
@@ -176,6 +253,47 @@ class FieldAwareFactorizationMachine(_FMBase):
         finally:
             _lib.load().nimfm_ffm_free(_lib.ctx(), h)
         return out
+
+
+    def dump(self, fname):                     # field_aware_factorization_machine.nim:95-115
+        self.checkInitialized()
+        P = _lib.f64(self.P)
+        with open(fname, "w") as f:
+            f.write(f"task: {self.task}\n")
+            f.write(f"nFields: {P.shape[0]}\n")
+            f.write(f"nFeatures: {P.shape[1]}\n")
+            f.write(f"nComponents: {self.nComponents}\n")
+            f.write(f"fitIntercept: {_nim_bool(self.fitIntercept)}\n")
+            f.write(f"fitLinear: {_nim_bool(self.fitLinear)}\n")
+            f.write(f"randomState: {int(self.randomState)}\n")
+            f.write(f"scale: {_nim_float(self.scale)}\n")
+            for field in range(P.shape[0]):
+                f.write(f"P[{field}]:\n")
+                for j in range(P.shape[1]):
+                    f.write(_join(P[field, j]) + "\n")
+            f.write("w:\n")
+            f.write(_join(self.w) + "\n")
+            f.write(f"intercept: {_nim_float(self.intercept)}\n")
+
+    @classmethod
+    def load(cls, fname, warmStart=False):     # field_aware_factorization_machine.nim:118-158
+        with open(fname) as f:
+            val = lambda: f.readline().rstrip("\n").split(" ")[1]
+            task = val()
+            nFields, nFeatures, nComponents = int(val()), int(val()), int(val())
+            fitIntercept, fitLinear = _parse_bool(val()), _parse_bool(val())
+            randomState, scale = int(val()), float(val())
+            ffm = cls(task, nComponents, fitIntercept, fitLinear, warmStart, randomState, scale)
+            ffm.P = np.zeros((nFields, nFeatures, nComponents))
+            for field in range(nFields):
+                f.readline()
+                for j in range(nFeatures):
+                    ffm.P[field, j] = _parse_row(f.readline(), nComponents)
+            f.readline()
+            ffm.w = _parse_row(f.readline(), nFeatures)
+            ffm.intercept = float(f.readline().rstrip("\n").split(" ")[1])
+        ffm.isInitialized = True
+        return ffm
 
 
 def newFieldAwareFactorizationMachine(task, nComponents=10, fitIntercept=True, fitLinear=True,

@@ -145,6 +145,44 @@ def csc_slice_rows(Xc, a, b):
     return CSR(od, oi, op, b - a + 1, Xc.d)
 
 
+def csr_vstack(parts):
+    """vstack of CSRMatrix / CSRFieldMatrix (tensor/sparse.nim:564-583, 612-640): data / indices
+    [/ fields] concatenated, indptr[1..] of each later part shifted by the nnz so far."""
+    data, indices, indptr = parts[0].data.copy(), parts[0].indices.copy(), parts[0].indptr.copy()
+    fields = None if parts[0].fields is None else parts[0].fields.copy()
+    n = parts[0].n
+    for X in parts[1:]:
+        if X.d != parts[0].d:
+            raise ValueError("All matrics must have the same shape[1].")
+        nnz = len(data)
+        data = np.concatenate([data, X.data])
+        indices = np.concatenate([indices, X.indices])
+        if fields is not None:
+            fields = np.concatenate([fields, X.fields])
+        indptr = np.concatenate([indptr, X.indptr[1:] + nnz])
+        n += X.n
+    return CSR(data, indices, indptr, n, parts[0].d, fields, parts[0].n_fields)
+
+
+def csc_vstack(parts):
+    """vstack of CSCMatrix (tensor/sparse.nim:586-609): per column j, the entries of every part in
+    turn with row ids offset by the rows of the parts before it."""
+    d = parts[0].d
+    for X in parts[1:]:
+        if X.d != d:
+            raise ValueError("All matrics must have the same shape[1].")
+    data, indices, indptr = [], [], np.zeros(d + 1, np.int64)
+    for j in range(d):
+        offset = 0
+        for X in parts:
+            for q in range(X.indptr[j], X.indptr[j + 1]):
+                data.append(X.data[q])
+                indices.append(X.indices[q] + offset)
+                indptr[j + 1] += 1
+            offset += X.n
+    return CSR(data, indices, np.cumsum(indptr), sum(X.n for X in parts), d)
+
+
 def anova(X, Ps, degree, n_aug=0, is_csc=False):
     """kernels.anova for one component; returns A [n, degree+1]."""
     A = np.zeros((X.n, degree + 1))

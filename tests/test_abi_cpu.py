@@ -82,3 +82,51 @@ def test_host_side_shape_rules():
     assert list(y) == [1.0, -1.0, 0.0]            # fm_base.nim:29-36 sgn
     with pytest.raises(ValueError):
         nf.newCSRDataset([1.0], [0], [0, 1, 1], 1, 3)
+
+
+def test_model_dump_load_roundtrip(tmp_path):
+    """dump / load text format (factorization_machine.nim:142-220,
+    field_aware_factorization_machine.nim:95-158): every parameter survives bit-exactly, the header
+    lines are the reference's (a file written by nimfm parses, and vice versa)."""
+    import nimfm_b200 as nf
+    rng = np.random.default_rng(3)
+    for fit_lower, fit_linear in ((nf.explicit, True), (nf.augment, False), (nf.none, True)):
+        fm = nf.newFactorizationMachine(nf.classification, degree=3, nComponents=4, fitLower=fit_lower,
+                                        fitLinear=fit_linear, randomState=7, scale=0.05)
+        fm.P = rng.standard_normal((fm.nOrders, 4, 6 + fm.nAugments)) * 1e-3
+        fm.w, fm.intercept, fm.isInitialized = rng.standard_normal(6), -1.5e-7, True
+        p = str(tmp_path / "fm.txt")
+        fm.dump(p)
+        lines = open(p).read().splitlines()
+        assert lines[:9] == ["task: c", "nFeatures: 6", "degree: 3", "nComponents: 4", f"fitLower: {fit_lower}",
+                             "fitIntercept: true", f"fitLinear: {'true' if fit_linear else 'false'}",
+                             "randomState: 7", "scale: 0.05"]
+        assert lines[9] == "lams:" and lines[11] == "P[0]:" and lines[-3] == "w:" and lines[-1].startswith("intercept: ")
+        g = nf.FactorizationMachine.load(p, warmStart=True)
+        assert g.isInitialized and g.warmStart and g.degree == 3 and g.fitLower == fit_lower
+        assert np.array_equal(g.P, fm.P) and np.array_equal(g.w, fm.w) and g.intercept == fm.intercept
+        assert np.array_equal(g.lams, fm.lams)
+    with pytest.raises(nf.NotFittedError):
+        nf.newFactorizationMachine(nf.regression).dump(str(tmp_path / "x"))
+    ffm = nf.newFieldAwareFactorizationMachine(nf.regression, nComponents=3, fitLinear=False)
+    ffm.P, ffm.w, ffm.intercept, ffm.isInitialized = rng.standard_normal((2, 5, 3)), rng.standard_normal(5), 0.5, True
+    p = str(tmp_path / "ffm.txt")
+    ffm.dump(p)
+    assert open(p).read().splitlines()[:4] == ["task: r", "nFields: 2", "nFeatures: 5", "nComponents: 3"]
+    h = nf.FieldAwareFactorizationMachine.load(p)
+    assert np.array_equal(h.P, ffm.P) and np.array_equal(h.w, ffm.w) and h.intercept == 0.5 and not h.fitLinear
+
+
+def test_oracle_vstack_matches_dense_definition():
+    from oracle import oracle as orc
+    from oracle.oracle import CSR
+    rng = np.random.default_rng(5)
+    mats = [rng.random((n, 7)) * (rng.random((n, 7)) < 0.4) for n in (4, 9, 1)]
+    parts = [CSR.from_dense(M) for M in mats]
+    st = orc.csr_vstack(parts)
+    assert np.array_equal(st.to_dense(), np.vstack(mats)) and st.n == 14
+    orc.build()
+    cst = orc.csc_vstack([orc.csr_to_csc(p) for p in parts])
+    whole = orc.csr_to_csc(st)
+    assert np.array_equal(cst.indptr, whole.indptr) and np.array_equal(cst.indices, whole.indices)
+    assert np.array_equal(cst.data, whole.data)
