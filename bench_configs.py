@@ -182,6 +182,17 @@ def main():
                                               "achieved_GBs": bts * n / (ms.value / 1e3) / 1e9,
                                               "frac_of_measured_hbm": bts * n / (ms.value / 1e3) / 1e9 / peak}
         lib.nimfm_ffm_free(ctx, h)
+        # the config's solver: AdaGrad with synchronous minibatches (2 epochs; the second has the refresh pass)
+        mbs = min(1 << 16, n)
+        opt = nf.newAdaGrad(maxIter=2, eta0=0.1, eps=1e-10, loss=nf.Logistic(), verbose=0, tol=0.0, shuffle=False,
+                            miniBatchSize=mbs)
+        t0 = time.perf_counter()
+        opt.fit(ds, y, m)
+        out["adagrad"] = {"miniBatchSize": mbs, "samples_per_s": n / float(np.min(opt.epoch_seconds)),
+                          "epoch_seconds": opt.epoch_seconds, "fit_wall_s": time.perf_counter() - t0,
+                          "epoch_loss": opt.history[-1][1],
+                          "note": "one blocking nimfm_ffm_adagrad_epoch call per epoch (count -> refresh -> pair "
+                                  "kernel -> apply per minibatch)"}
         line = {"config": "C5", "what": f"FFM 39 fields rank 8, one feature per field, d={d}, n={n}, logistic", **out}
         if args.cpu:
             csr = CSR(data, idx, ptr, n, d, fields=fields, n_fields=39)

@@ -57,6 +57,7 @@ struct nimfm_dataset {
   int32_t *indices = nullptr;        // column ids (CSR) / row ids (CSC), narrowed to int32
   int64_t *indptr = nullptr;
   int32_t *fields = nullptr;
+  mutable int fieldDup = -1;         // field datasets: does a row repeat a field? (-1 = not checked yet; ffm.cu)
   double *y = nullptr;
   // hot features (CSR kinds): columns present in >= 1/16 of a row sample, at most 16 (fm_rows.cuh)
   uint8_t *hotSlot = nullptr;        // [d], 255 = cold

@@ -84,6 +84,12 @@ static __global__ void adagrad_count_kernel(const int32_t *indices, const int64_
   if (warp == 0 && lane < nAug) cnt[d + lane] += (double)nRows;   // augmentation: one dummy per row
 }
 
+// The two per-minibatch AdaGrad passes below visit ONLY the features the batch touches (cnt[j] != 0):
+// a warp reads 32 counts at a time, then walks the touched ones with all lanes on the feature's
+// SB8 contiguous elements.  Untouched features carry zero deltas by construction, so skipping them is
+// exact; for FFM (nFields*k = 312 elements per feature, P = 2.5 GB) a dense pass per minibatch cost
+// more than the row kernel itself.
+//
 // update() of adagrad.nim:87-110 for every feature the batch touches, done ONCE per feature:
 // theta = -eta0*G/(eta0*t*reg + sqrt(N)); viol += cnt[j] * |P_old - theta| (the reference adds the
 // same |P_old - theta| once per row containing j, and 0 for every later row of the batch -- with the
@@ -94,27 +100,30 @@ static __global__ void adagrad_refresh_kernel(double *P, const double *gsP, cons
                                               int64_t d, int fitLinear, double eta0, double tIt, double alpha,
                                               double beta, double *partials) {
   __shared__ double red[8];
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t nP = dd * SB8;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nWarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const double tmpP = eta0 * tIt * beta;
+  const double denW = tIt * eta0 * alpha;
   double viol = 0.0;
-  for (int64_t e = tid; e < nP; e += stride) {
-    const double c = cnt[e / SB8];
-    if (c != 0.0) {
-      const double pn = -(eta0 * gsP[e]) / (tmpP + sqrt(gnP[e]));
-      viol += c * fabs(P[e] - pn);
-      P[e] = pn;
+  for (int64_t base = warp * 32; base < dd; base += nWarps * 32) {
+    const int64_t jm = base + lane;
+    const double cm = jm < dd ? cnt[jm] : 0.0;
+    if (fitLinear && cm != 0.0 && jm < d) {
+      const double wn = -eta0 * gsw[jm] / (denW + sqrt(gnw[jm]));   // fitLinearAdaGrad, fit_linear.nim:50-57
+      viol += cm * fabs(w[jm] - wn);
+      w[jm] = wn;
     }
-  }
-  if (fitLinear) {
-    const double denW = tIt * eta0 * alpha;
-    for (int64_t j = tid; j < d; j += stride) {
-      const double c = cnt[j];
-      if (c != 0.0) {
-        const double wn = -eta0 * gsw[j] / (denW + sqrt(gnw[j]));   // fitLinearAdaGrad, fit_linear.nim:50-57
-        viol += c * fabs(w[j] - wn);
-        w[j] = wn;
+    unsigned mask = __ballot_sync(0xffffffffu, cm != 0.0);
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const double c = __shfl_sync(0xffffffffu, cm, src);
+      const int64_t e0 = (base + src) * SB8;
+      for (int e = lane; e < SB8; e += 32) {
+        const double pn = -(eta0 * gsP[e0 + e]) / (tmpP + sqrt(gnP[e0 + e]));
+        viol += c * fabs(P[e0 + e] - pn);
+        P[e0 + e] = pn;
       }
     }
   }
@@ -127,27 +136,42 @@ static __global__ void adagrad_refresh_kernel(double *P, const double *gsP, cons
   }
 }
 
-// updateG() of adagrad.nim:113-134 in dense form: g_sum += dGs, g_norm += dGn, deltas and counts cleared.
+// updateG() of adagrad.nim:113-134 for the touched features: g_sum += dGs, g_norm += dGn, deltas and
+// counts cleared.
 static __global__ void adagrad_apply_kernel(double *gsP, double *gnP, double *dGsP, double *dGnP, int64_t nP,
                                             double *gsw, double *gnw, double *dGsw, double *dGnw, int64_t d,
                                             int fitLinear, double *cnt, int64_t dd) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  for (int64_t e = tid; e < nP; e += stride) {
-    gsP[e] += dGsP[e];
-    gnP[e] += dGnP[e];
-    dGsP[e] = 0.0;
-    dGnP[e] = 0.0;
-  }
-  for (int64_t j = tid; j < d; j += stride) {
-    if (fitLinear) {
-      gsw[j] += dGsw[j];
-      gnw[j] += dGnw[j];
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nWarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int SB8 = (int)(nP / dd);
+  for (int64_t base = warp * 32; base < dd; base += nWarps * 32) {
+    const int64_t jm = base + lane;
+    const double cm = jm < dd ? cnt[jm] : 0.0;
+    if (cm != 0.0) {
+      if (jm < d) {
+        if (fitLinear) {
+          gsw[jm] += dGsw[jm];
+          gnw[jm] += dGnw[jm];
+        }
+        dGsw[jm] = 0.0;
+        dGnw[jm] = 0.0;
+      }
+      cnt[jm] = 0.0;
     }
-    dGsw[j] = 0.0;
-    dGnw[j] = 0.0;
+    unsigned mask = __ballot_sync(0xffffffffu, cm != 0.0);
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int64_t e0 = (base + src) * SB8;
+      for (int e = lane; e < SB8; e += 32) {
+        gsP[e0 + e] += dGsP[e0 + e];
+        gnP[e0 + e] += dGnP[e0 + e];
+        dGsP[e0 + e] = 0.0;
+        dGnP[e0 + e] = 0.0;
+      }
+    }
   }
-  for (int64_t j = tid; j < dd; j += stride) cnt[j] = 0.0;
 }
 // intercept part of update()/updateG() (adagrad.nim:101-105,126-128) + epoch accumulators.
 // part = [loss, sum dL, sum dL^2, -] of the batch (all-reduced); violRefresh = this rank's viol of the

@@ -223,28 +223,63 @@ struct FfmPlan {
   int64_t partialRows = 0;   // rows of the [.][4] partials block the kernel writes
 };
 
-// pair-streaming kernel when k is 4/8/16/32 (predict / grad only), else nullptr
-static FfmKernel ffm_pairs_pick(int k, bool grad) {
+// pair-streaming kernel when k is 4/8/16/32, else nullptr
+template <int KT>
+static FfmKernel ffm_pairs_mode(int mode) {
+  return mode == FFM_PREDICT ? ffm_pairs_kernel<FFM_PAIRS_PREDICT, KT, FfmArgs>
+         : mode == FFM_GRAD  ? ffm_pairs_kernel<FFM_PAIRS_GRAD, KT, FfmArgs>
+                             : ffm_pairs_kernel<FFM_PAIRS_ADAGRAD, KT, FfmArgs>;
+}
+static FfmKernel ffm_pairs_pick(int k, int mode) {
   switch (k) {
-    case 4: return grad ? ffm_pairs_kernel<1, 4, FfmArgs> : ffm_pairs_kernel<0, 4, FfmArgs>;
-    case 8: return grad ? ffm_pairs_kernel<1, 8, FfmArgs> : ffm_pairs_kernel<0, 8, FfmArgs>;
-    case 16: return grad ? ffm_pairs_kernel<1, 16, FfmArgs> : ffm_pairs_kernel<0, 16, FfmArgs>;
-    case 32: return grad ? ffm_pairs_kernel<1, 32, FfmArgs> : ffm_pairs_kernel<0, 32, FfmArgs>;
+    case 4: return ffm_pairs_mode<4>(mode);
+    case 8: return ffm_pairs_mode<8>(mode);
+    case 16: return ffm_pairs_mode<16>(mode);
+    case 32: return ffm_pairs_mode<32>(mode);
     default: return nullptr;
   }
+}
+
+// does any row hold two nonzeros of one field?  (computed once per dataset, on the device)
+static int ffm_has_field_dups(nimfm_ctx *ctx, const nimfm_dataset *X, bool *dups) {
+  if (X->fieldDup < 0) {
+    int *flag = nullptr;
+    CK(cudaMalloc(&flag, sizeof(int)));
+    CK(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+    if (X->n > 0) {
+      const int grid = (int)std::min<int64_t>((X->n * 32 + 255) / 256, (int64_t)ctx->numSMs * 16);
+      ffm_field_dup_kernel<<<grid < 1 ? 1 : grid, 256, 0, ctx->stream>>>(X->fields, X->indptr, X->n, flag);
+      LAUNCHED(ctx);
+    }
+    int h = 0;
+    CK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(flag));
+    X->fieldDup = h ? 1 : 0;
+  }
+  *dups = X->fieldDup == 1;
+  return NIMFM_OK;
 }
 
 static int ffm_plan(nimfm_ctx *ctx, const nimfm_ffm *m, const nimfm_dataset *X, int64_t nRows, FfmKernel kern,
                     FfmPlan *pl);
 
-// mode: FFM_PREDICT / FFM_GRAD choose the pair kernel when available (NIMFM_FFM_KERNEL=block forces the
-// block-per-row kernel); FFM_ADAGRAD always runs the block-per-row kernel.
+// Every mode chooses the pair kernel when one exists for k (NIMFM_FFM_KERNEL=block forces the
+// block-per-row kernel); FFM_ADAGRAD additionally needs a dataset without repeated fields in a row.
 static int ffm_plan_mode(nimfm_ctx *ctx, const nimfm_ffm *m, const nimfm_dataset *X, int64_t nRows, int mode,
                          FfmPlan *pl) {
   const char *env = getenv("NIMFM_FFM_KERNEL");
   const bool forceBlock = env && !strcmp(env, "block");
   const int CH = (int)std::max<int64_t>(X->maxSegNnz, 1);
-  FfmKernel pk = (mode == FFM_ADAGRAD || forceBlock || CH > 1024) ? nullptr : ffm_pairs_pick(m->k, mode == FFM_GRAD);
+  FfmKernel pk = (forceBlock || CH > 1024) ? nullptr : ffm_pairs_pick(m->k, mode);
+  if (pk && mode == FFM_ADAGRAD) {
+    // the pair kernel squares per-pair contributions, which equals the per-sample gradient entry
+    // (adagrad.nim:119-124) only when no row has two nonzeros of one field
+    bool dups = false;
+    int rc = ffm_has_field_dups(ctx, X, &dups);
+    if (rc) return rc;
+    if (dups) pk = nullptr;
+  }
   if (pk) {
     const int block = 256, wpb = block / 32;
     const size_t smem = (size_t)wpb * CH * sizeof(FfmRec);
@@ -562,13 +597,16 @@ int32_t nimfm_ffm_adagrad_epoch(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_datase
     const int32_t *rows = idxDev ? idxDev + start : nullptr;
     const double tIt = (double)(*it - 1);
     const int first = (*it == 1);
-    if (!first) {
-      // adagrad.update for FFM refreshes all nFields x k entries of every row feature (adagrad.nim:93-99)
+    {
+      // per-feature row counts of the batch (all ranks): viol weights + the touched-feature set
       const int cgrid = (int)std::min<int64_t>((cnt * 32 + 255) / 256, (int64_t)ctx->numSMs * 16);
       adagrad_count_kernel<<<cgrid < 1 ? 1 : cgrid, 256, 0, ctx->stream>>>(X->indices, X->indptr, X->n, start, cnt, rows,
                                                                           d, 0, cntF);
       LAUNCHED(ctx);
       if ((rc = nimfm_allreduce_sum(ctx, cntF, d))) return rc;
+    }
+    if (!first) {
+      // adagrad.update for FFM refreshes all nFields x k entries of every row feature (adagrad.nim:93-99)
       const int rgrid = ew_grid(ctx, nP);
       if ((rc = nimfm_ensure_partials(ctx, (size_t)rgrid * 4))) return rc;
       adagrad_refresh_kernel<<<rgrid, 256, 0, ctx->stream>>>(m->P, m->gsP, m->gnP, d, SB8, cntF, m->w, m->gsw, m->gnw, d,

@@ -592,13 +592,17 @@ int32_t nimfm_fm_adagrad_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset
     const int32_t *rows = idxDev ? idxDev + start : nullptr;
     const double tIt = (double)(*it - 1);
     const int first = (*it == 1);
-    if (!first) {
-      // update() (adagrad.nim:87-110), once per touched feature: count -> all-reduce -> refresh
+    {
+      // per-feature row counts of the batch (all ranks): they weight viol in the refresh pass and tell
+      // the refresh / apply passes which features the batch touches
       const int cgrid = (int)std::min<int64_t>((cnt * 32 + 255) / 256, (int64_t)ctx->numSMs * 16);
       adagrad_count_kernel<<<cgrid < 1 ? 1 : cgrid, 256, 0, ctx->stream>>>(X->indices, X->indptr, X->n, start, cnt, rows,
                                                                           d, fm->nAug, cntF);
       LAUNCHED(ctx);
       if ((rc = nimfm_allreduce_sum(ctx, cntF, dd))) return rc;
+    }
+    if (!first) {
+      // update() (adagrad.nim:87-110), once per touched feature
       const int rgrid = ew_grid(ctx, nP);
       if ((rc = nimfm_ensure_partials(ctx, (size_t)rgrid * 4))) return rc;
       adagrad_refresh_kernel<<<rgrid, 256, 0, ctx->stream>>>(fm->P, fm->gsP, fm->gnP, dd, SB8, cntF, fm->w, fm->gsw,
