@@ -41,8 +41,11 @@ struct nimfm_ctx {
     int32_t *idx32 = nullptr;
     size_t capNnz = 0, capRows = 0;
   } stage[2];
-  uint8_t *stageHotSlot = nullptr;
+  uint8_t *stageHotSlot = nullptr;   // persistent [stageHotD] table; only the <=16 hot entries change per call
   int32_t *stageHotList = nullptr;
+  int64_t stageHotD = -1;
+  int stageNHot = 0;
+  int32_t stagePrevHot[16] = {0};
   // communicator
   ncclComm *comm = nullptr;
   int rank = 0, nranks = 1;

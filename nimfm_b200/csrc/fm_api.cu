@@ -735,6 +735,14 @@ int nimfm_find_hot(const int64_t *indices, const int64_t *indptr, int64_t rowBeg
 int nimfm_upload_hot(nimfm_ctx *ctx, const std::vector<int32_t> &hot, int64_t d, uint8_t **hotSlot,
                      int32_t **hotList);
 
+struct HotLists { int32_t v[32]; };   // [0,16): entries to clear, [16,32): entries to set (-1 = none)
+static __global__ void set_hot_table_kernel(uint8_t *slot, const HotLists hl) {
+  const int t = threadIdx.x;
+  if (t < 16 && hl.v[t] >= 0) slot[hl.v[t]] = 255;
+  __syncthreads();
+  if (t >= 16 && hl.v[t] >= 0) slot[hl.v[t]] = (uint8_t)(t - 16);
+}
+
 static int ensure_stage(nimfm_ctx *ctx, nimfm_ctx::Stage &st, size_t rows, size_t nnz) {
   if (st.capRows < rows) {
     if (st.y) CK(cudaFree(st.y));
@@ -765,37 +773,70 @@ extern "C" int32_t nimfm_fm_loss_grad_host(nimfm_ctx *ctx, nimfm_fm *fm, int64_t
   REQUIRE(fm && indptr && y, "NULL argument");
   REQUIRE(d == fm->d, "Invalid nFeatures. (batch %lld, model %lld)", (long long)d, (long long)fm->d);
   REQUIRE(nRows >= 0 && miniBatchSize >= 1, "bad nRows / miniBatchSize");
-  if (chunkRows <= 0) chunkRows = 1 << 19;
+  if (chunkRows <= 0) chunkRows = 1 << 17;   // 84 MB per chunk at 39 nnz/row: short pipeline ramp and tail
   const int64_t nG = fm->nP() + fm->d + 2;
   if (zeroGrads) CK(cudaMemsetAsync(fm->grad, 0, (size_t)nG * 8, ctx->stream));
   int *bad = reinterpret_cast<int *>(ctx->scalars + 60);
   CK(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
-  // size the two staging sets for the largest chunk
+  // size the two staging sets for the largest chunk (indptr is sampled at chunk boundaries only)
   size_t maxNnz = 1;
-  int64_t maxSeg = 0;
   for (int64_t r0 = 0; r0 < nRows; r0 += chunkRows) {
     const int64_t r1 = std::min(nRows, r0 + chunkRows);
+    REQUIRE(indptr[r1] >= indptr[r0], "indptr is not monotone");
     maxNnz = std::max(maxNnz, (size_t)(indptr[r1] - indptr[r0]));
   }
-  for (int64_t r = 0; r < nRows; r++) maxSeg = std::max(maxSeg, indptr[r + 1] - indptr[r]);
   int rc;
   for (int s = 0; s < 2; s++)
     if ((rc = ensure_stage(ctx, ctx->stage[s], (size_t)std::min(nRows, chunkRows) + 1, maxNnz))) return rc;
-  // hot columns of this batch (row sample on the host; see nimfm_find_hot)
-  std::vector<int32_t> hot;
-  const int nHot = (indices && nRows > 0) ? nimfm_find_hot(indices, indptr, 0, nRows, hot, 2048) : 0;
-  if ((rc = nimfm_upload_hot(ctx, hot, d, &ctx->stageHotSlot, &ctx->stageHotList))) return rc;
+  if (!ctx->stageHotSlot || ctx->stageHotD != d) {   // persistent hot-column table, all cold
+    if (ctx->stageHotSlot) CK(cudaFree(ctx->stageHotSlot));
+    ctx->stageHotSlot = nullptr;
+    CK(cudaMalloc(&ctx->stageHotSlot, (size_t)std::max<int64_t>(d, 1)));
+    CK(cudaMemsetAsync(ctx->stageHotSlot, 255, (size_t)std::max<int64_t>(d, 1), ctx->stream));
+    if (!ctx->stageHotList) CK(cudaMalloc(&ctx->stageHotList, 32 * sizeof(int32_t)));
+    ctx->stageHotD = d;
+    ctx->stageNHot = 0;
+  }
+  int nHot = 0;
   int c = 0;
   for (int64_t r0 = 0; r0 < nRows; r0 += chunkRows, c++) {
     const int64_t r1 = std::min(nRows, r0 + chunkRows), rows = r1 - r0;
     const int64_t base = indptr[r0], nnz = indptr[r1] - base;
     nimfm_ctx::Stage &st = ctx->stage[c & 1];
+    // the copies go out first; the host-side bookkeeping below overlaps with the DMA
     if (c >= 2) CK(cudaStreamWaitEvent(ctx->copyStream, ctx->evComputed[c & 1], 0));   // buffer is free again
     CK(cudaMemcpyAsync(st.data, data + base, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->copyStream));
     CK(cudaMemcpyAsync(st.idx64, indices + base, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->copyStream));
     CK(cudaMemcpyAsync(st.indptr, indptr + r0, (size_t)(rows + 1) * 8, cudaMemcpyHostToDevice, ctx->copyStream));
     CK(cudaMemcpyAsync(st.y, y + r0, (size_t)rows * 8, cudaMemcpyHostToDevice, ctx->copyStream));
     CK(cudaEventRecord(ctx->evCopied[c & 1], ctx->copyStream));
+    if (c == 0) {
+      // hot columns of this batch (row sample on the host; see nimfm_find_hot): the previous call's
+      // entries are cleared and the new ones set by one tiny kernel on the persistent table
+      std::vector<int32_t> hot;
+      nHot = (indices && nRows > 0) ? nimfm_find_hot(indices, indptr, 0, nRows, hot, 2048) : 0;
+      int32_t lists[32];
+      for (int i = 0; i < 16; i++) lists[i] = i < ctx->stageNHot ? ctx->stagePrevHot[i] : -1;
+      for (int i = 0; i < 16; i++) lists[16 + i] = i < nHot ? hot[i] : -1;
+      CK(cudaMemcpyAsync(ctx->stageHotList, lists + 16, 16 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+      HotLists hl;
+      memcpy(hl.v, lists, sizeof(lists));
+      set_hot_table_kernel<<<1, 32, 0, ctx->stream>>>(ctx->stageHotSlot, hl);
+      LAUNCHED(ctx);
+      for (int i = 0; i < nHot; i++) ctx->stagePrevHot[i] = hot[i];
+      ctx->stageNHot = nHot;
+    }
+    int64_t maxSeg = 0, minSeg = 0;
+    for (int64_t r = r0; r < r1; r++) {
+      const int64_t len = indptr[r + 1] - indptr[r];
+      maxSeg = std::max(maxSeg, len);
+      minSeg = std::min(minSeg, len);
+    }
+    if (minSeg < 0) {
+      cudaStreamSynchronize(ctx->copyStream);
+      cudaStreamSynchronize(ctx->stream);
+      return nimfm_fail(ctx, NIMFM_ERR_INVALID, "indptr is not monotone in rows [%lld,%lld)", (long long)r0, (long long)r1);
+    }
     CK(cudaStreamWaitEvent(ctx->stream, ctx->evCopied[c & 1], 0));
     narrow_rebase_kernel<<<ew_grid(ctx, nnz), 256, 0, ctx->stream>>>(st.idx64, st.idx32, nnz, st.indptr, rows + 1,
                                                                      base, d, bad);
