@@ -42,8 +42,13 @@ typedef enum {
 typedef enum { NIMFM_LOSS_SQUARED = 0, NIMFM_LOSS_SQUARED_HINGE = 1, NIMFM_LOSS_LOGISTIC = 2, NIMFM_LOSS_HUBER = 3 } nimfm_loss;
 /* optimizer/sgd.nim:8-12 SchedulingKind */
 typedef enum { NIMFM_SCHED_CONSTANT = 0, NIMFM_SCHED_OPTIMAL = 1, NIMFM_SCHED_INVSCALING = 2, NIMFM_SCHED_PEGASOS = 3 } nimfm_sched;
-/* prox for MBPSGD (minibatch_psgd.nim:119-121): identity == SquaredL12 with gamma=0 (squaredl12.nim:67-69); L1 == l1.nim:38-41 */
-typedef enum { NIMFM_REG_IDENTITY = 0, NIMFM_REG_L1 = 1 } nimfm_reg;
+/* prox for MBPSGD (minibatch_psgd.nim:119-121): identity == any regulariser at gamma=0; L1 == l1.nim:38-41;
+ * SQUAREDL12 == newSquaredL12(transpose=true), the MBPSGD default (squaredl12.nim:147-156: one vector per
+ * component over all features; degree 2 only, :103-106); SQUAREDL12_ROWS == transpose=false (:157-159);
+ * L21 == l21.nim:25-35 */
+typedef enum {
+  NIMFM_REG_IDENTITY = 0, NIMFM_REG_L1 = 1, NIMFM_REG_SQUAREDL12 = 2, NIMFM_REG_SQUAREDL12_ROWS = 3, NIMFM_REG_L21 = 4
+} nimfm_reg;
 typedef enum { NIMFM_DS_CSR = 0, NIMFM_DS_CSC = 1, NIMFM_DS_CSR_FIELD = 2 } nimfm_ds_kind;
 
 typedef struct nimfm_ctx nimfm_ctx;

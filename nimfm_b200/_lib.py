@@ -17,7 +17,7 @@ PD, PI64, VP = C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_void_p
 
 LOSS_SQUARED, LOSS_SQUARED_HINGE, LOSS_LOGISTIC, LOSS_HUBER = 0, 1, 2, 3
 SCHED = {"constant": 0, "optimal": 1, "invscaling": 2, "pegasos": 3}
-REG_IDENTITY, REG_L1 = 0, 1
+REG_IDENTITY, REG_L1, REG_SQUAREDL12, REG_SQUAREDL12_ROWS, REG_L21 = 0, 1, 2, 3, 4
 DS_CSR, DS_CSC, DS_CSR_FIELD = 0, 1, 2
 
 

@@ -82,6 +82,7 @@ struct nimfm_fm {
   bool lamsAreOnes = true;
   // gradient buffer: [gP (nP) | gw (d) | gb, lossSum] contiguous for a single all-reduce
   double *grad = nullptr;
+  double *proxState = nullptr;   // SquaredL12 column prox: [tau | prevCnt | done] (prox_kernels.cuh)
   // AdaGrad state (same layouts): g_sum, g_norm, and per-minibatch deltas
   double *gsP = nullptr, *gnP = nullptr, *gsw = nullptr, *gnw = nullptr;
   double *dG = nullptr;    // [dGsP (nP) | dGnP (nP) | dGsw (d) | dGnw (d) | touched (d+nAug) | loss, sum dL, sum dL^2, viol]

@@ -8,6 +8,7 @@
 
 #include "dense_kernels.cuh"
 #include "fm_rows_stream.cuh"
+#include "prox_kernels.cuh"
 
 typedef void (*RowKernel)(const RowArgs);
 RowKernel nimfm_row_kernel_predict(int degree, bool explicitLower, int k);
@@ -228,7 +229,7 @@ int32_t nimfm_fm_free(nimfm_ctx *ctx, nimfm_fm *fm) {
   if (ctx) cudaSetDevice(ctx->device);
   for (double *p : {fm->P, fm->w, fm->lams, fm->b, fm->grad, fm->gsP, fm->gnP, fm->gsw, fm->gnw, fm->dG,
                     fm->adaScal, fm->scalingsP, fm->scalingsW, fm->sgdScal, fm->Pcm, fm->yPred, fm->Acache,
-                    fm->colNormSq, fm->cdScal})
+                    fm->colNormSq, fm->cdScal, fm->proxState})
     cudaFree(p);
   delete fm;
   return NIMFM_OK;
@@ -480,6 +481,47 @@ static double get_eta(int sched, double eta0, double power, double reg, int64_t 
   }
 }
 
+// reg.prox(params.P[order], lam, degree-order) for every order (minibatch_psgd.nim:119-121), for the
+// regularisers the dense step kernel does not fuse (L1 is fused there).  Enqueued on ctx->stream; the
+// column-wise SquaredL12 iterates to its fixed point with a host check every few sweeps.
+static int apply_prox(nimfm_ctx *ctx, nimfm_fm *fm, int reg, double lam) {
+  if (reg == NIMFM_REG_IDENTITY || reg == NIMFM_REG_L1 || lam == 0.0) return NIMFM_OK;
+  const int64_t dd = fm->dd();
+  const int SB8 = fm->nOrders * fm->k;
+  if (reg == NIMFM_REG_L21 || reg == NIMFM_REG_SQUAREDL12_ROWS) {
+    if (fm->k > 32 * NIMFM_PROX_MAXE)
+      return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "row-wise prox supports nComponents <= %d", 32 * NIMFM_PROX_MAXE);
+    const int64_t nRows = dd * fm->nOrders;
+    prox_rows_kernel<<<ew_grid(ctx, nRows * 32), 256, 0, ctx->stream>>>(fm->P, nRows, fm->k, lam, reg);
+    LAUNCHED(ctx);
+    return NIMFM_OK;
+  }
+  if (reg != NIMFM_REG_SQUAREDL12) return nimfm_fail(ctx, NIMFM_ERR_INVALID, "unknown regulariser %d", reg);
+  if (SB8 > 1024) return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "nOrders*nComponents=%d > 1024", SB8);
+  const int R = std::max(1, 256 / SB8), block = R * SB8;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((dd + R - 1) / R, (int64_t)ctx->numSMs * 8));
+  int rc = nimfm_ensure_partials(ctx, (size_t)grid * SB8 * 2);
+  if (rc) return rc;
+  if (!fm->proxState) CK(cudaMalloc(&fm->proxState, (size_t)(2 * SB8 + 8) * 8));
+  sql12_init_kernel<<<1, 256, 0, ctx->stream>>>(fm->proxState, SB8);
+  LAUNCHED(ctx);
+  bool done = false;
+  for (int iter = 0; iter < 1024 && !done; ++iter) {
+    sql12_pass_kernel<<<grid, block, (size_t)block * 16, ctx->stream>>>(fm->P, dd, SB8, R, fm->proxState, ctx->partials);
+    sql12_update_kernel<<<1, 256, 0, ctx->stream>>>(ctx->partials, grid, SB8, lam, fm->proxState);
+    ctx->launches += 2;
+    if ((iter & 3) == 3) {
+      CK(cudaMemcpyAsync(ctx->hostScalars + 8, fm->proxState + 2 * SB8, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      done = ctx->hostScalars[8] != 0.0;
+    }
+  }
+  if (!done) return nimfm_fail(ctx, NIMFM_ERR_STATE, "SquaredL12 prox did not reach its fixed point");
+  sql12_apply_kernel<<<grid, block, 0, ctx->stream>>>(fm->P, dd, SB8, R, fm->proxState);
+  LAUNCHED(ctx);
+  return NIMFM_OK;
+}
+
 int32_t nimfm_fm_mbpsgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, const nimfm_mbpsgd_cfg *cfg,
                               int64_t localBatch, int64_t *it, int64_t *ii, const int64_t *sampleIdx,
                               double *runningLoss) {
@@ -489,7 +531,10 @@ int32_t nimfm_fm_mbpsgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset 
   if (rc) return rc;
   REQUIRE(cfg && it && ii, "NULL argument");
   REQUIRE(cfg->miniBatchSize >= 1 && cfg->maxIterInner >= 1, "miniBatchSize / maxIterInner must be resolved (>= 1)");
-  REQUIRE(cfg->reg == NIMFM_REG_IDENTITY || cfg->reg == NIMFM_REG_L1, "unsupported regulariser");
+  REQUIRE(cfg->reg >= NIMFM_REG_IDENTITY && cfg->reg <= NIMFM_REG_L21, "unsupported regulariser");
+  // SquaredL12.initSGD raises for degree != 2 (squaredl12.nim:103-106)
+  REQUIRE(!((cfg->reg == NIMFM_REG_SQUAREDL12 || cfg->reg == NIMFM_REG_SQUAREDL12_ROWS) && fm->degree != 2),
+          "SquaredL12 supports only degree=2.");
   if (localBatch <= 0) localBatch = cfg->miniBatchSize;
   REQUIRE(X->n > 0, "empty dataset");
   const int64_t nP = fm->nP(), d = fm->d, nG = nP + d + 2;
@@ -519,6 +564,7 @@ int32_t nimfm_fm_mbpsgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset 
         fm->P, fm->grad, nP, -etaP, rP, cfg->reg, lam, fm->w, fm->grad + nP, d, -etaW, rW, fm->fitLinear, fm->b,
         fm->grad + nG - 2, -etaB, rB, fm->fitIntercept, ctx->scalars);
     LAUNCHED(ctx);
+    if ((rc = apply_prox(ctx, fm, cfg->reg, lam))) return rc;
     *it += 1;
     cur = (cur + localBatch) % X->n;
   }

@@ -300,17 +300,51 @@ def newAdaGrad(maxIter=100, eta0=0.1, alpha0=1e-6, alpha=1e-3, beta=1e-3, loss=N
 class L1:                                      # regularizer/l1.nim
     kind = _lib.REG_L1
 
+    def eval(self, P, degree=2):               # P: one order, solver layout [nFeatures, nComponents]
+        return float(np.sum(np.abs(P)))
 
-class SquaredL12:                              # regularizer/squaredl12.nim (device path: gamma == 0 only)
-    kind = _lib.REG_IDENTITY
+    def initSGD(self, degree, nFeatures, nComponents):
+        pass
+
+
+class SquaredL12:                              # regularizer/squaredl12.nim
+    def __init__(self, transpose=True):        # newSquaredL12(transpose=true), :84-87
+        self.transpose = bool(transpose)
+
+    @property
+    def kind(self):
+        return _lib.REG_SQUAREDL12 if self.transpose else _lib.REG_SQUAREDL12_ROWS
+
+    def eval(self, P, degree=2):               # :72-81
+        if degree > 2:
+            raise ValueError("SquaredL12 supports only degree=2.")
+        return float(np.sum(np.sum(np.abs(P), axis=0 if self.transpose else 1) ** 2))
+
+    def initSGD(self, degree, nFeatures, nComponents):   # :103-106
+        if degree != 2:
+            raise ValueError("SquaredL12 supports only degree=2.")
+
+
+class L21:                                     # regularizer/l21.nim
+    kind = _lib.REG_L21
+
+    def eval(self, P, degree=2):               # :17-21
+        return float(np.sum(np.sqrt(np.sum(np.asarray(P) ** 2, axis=1))))
+
+    def initSGD(self, degree, nFeatures, nComponents):
+        pass
 
 
 def newL1():
     return L1()
 
 
-def newSquaredL12():
-    return SquaredL12()
+def newSquaredL12(transpose=True):
+    return SquaredL12(transpose)
+
+
+def newL21():
+    return L21()
 
 
 class MBPSGD(_Base):
@@ -336,10 +370,6 @@ class MBPSGD(_Base):
 
     def fit(self, X, y, sfm, callback=None):
         """minibatch_psgd.nim:127-211"""
-        if isinstance(self.reg, SquaredL12) and self.gamma != 0.0:
-            raise NotImplementedError(
-                "SquaredL12.prox with gamma != 0 is not on the device path yet (SURVEY 8f.1); use "
-                "gamma=0 (identity, squaredl12.nim:67-69) or reg=newL1()")
         sfm.init(X)
         y = sfm.checkTarget(y)
         lib, ctx = _lib.load(), _lib.ctx()
@@ -349,6 +379,9 @@ class MBPSGD(_Base):
         if not sfm.warmStart:
             self.it = 1                        # :151-152
         mb, inner = self.resolve_sizes(X)
+        # self.reg.initSGD(degree, nFeatures+nAugments, nComponents) (:172): SquaredL12 -- the default --
+        # raises for degree != 2 whatever gamma is (squaredl12.nim:103-106)
+        self.reg.initSGD(sfm.degree, X.nFeatures + sfm.nAugments, sfm.nComponents)
         cfg = _lib.MbpsgdCfg(self.loss.kind, self.loss.threshold, self.eta0, self.alpha0, self.alpha, self.beta,
                              self.gamma, self.reg.kind, _lib.SCHED[self.scheduling], self.power, mb, inner)
         rng = self._rng(sfm)
@@ -399,8 +432,8 @@ class MBPSGD(_Base):
                     break
                 if self.verbose > 0:
                     regVal = regularization(sfm.P, sfm.w, sfm.intercept, self.alpha0, self.alpha, self.beta)
-                    if isinstance(self.reg, L1):
-                        regVal += self.gamma * sfm.nOrders * 0 + self.gamma * float(np.sum(np.abs(sfm.P)))
+                    for order in range(sfm.nOrders):                      # :195-196
+                        regVal += self.gamma * self.reg.eval(np.asarray(sfm.P[order]).T, sfm.degree - order)
                     echoInfo(ep + 1, self.maxIter, -1, runningLoss, regVal)
                 if abs(oldLoss - runningLoss) < self.tol:
                     if self.verbose > 0:

@@ -270,3 +270,26 @@ def sgd_slow_fit(X, y, P, w, intercept, degree, fit_linear, fit_intercept, loss,
                 intercept -= eta(alpha0) * (dL + alpha0 * intercept)
             it += 1
     return P, w, intercept
+
+
+# ---------------------------------------------------------------- proximal operators (definitions)
+def prox_squaredl12_sorted(p, lam):
+    """argmin_q 0.5*||q - p||^2 + lam * ||q||_1^2 in closed form: with a = sort(|p|, descending) and
+    prefix sums c_m, theta = the largest m with a_m > 2*lam*c_m / (1 + 2*lam*m), S = c_theta / (1 +
+    2*lam*theta), q = softthreshold(p, 2*lam*S) -- what proxSquaredL12 (regularizer/squaredl12.nim:16-64)
+    finds by randomised selection."""
+    p = np.asarray(p, dtype=np.float64)
+    a = np.sort(np.abs(p))[::-1]
+    c = np.cumsum(a)
+    m = np.arange(1, len(a) + 1)
+    ok = a > 2 * lam * c / (1.0 + 2.0 * lam * m)
+    theta = int(np.max(m[ok])) if np.any(ok) else 0
+    S = (c[theta - 1] if theta else 0.0) / (1.0 + 2.0 * lam * theta)
+    return np.sign(p) * np.maximum(np.abs(p) - 2 * lam * S, 0.0)
+
+
+def prox_l21_row(p, lam):
+    """regularizer/l21.nim:25-29"""
+    p = np.asarray(p, dtype=np.float64)
+    nrm = np.sqrt(np.sum(p * p))
+    return p * (1.0 - lam / nrm) if nrm > lam else np.zeros_like(p)

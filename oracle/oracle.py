@@ -43,7 +43,7 @@ def lib():
         _lib = C.CDLL(_SO)
         for name in ("ref_loss", "ref_dloss", "ref_regularization", "ref_predict_with_grad",
                      "ref_fm_loss_grad", "ref_ffm_predict_with_grad", "ref_ffm_loss_grad",
-                     "ref_hogwild_adagrad_epoch"):
+                     "ref_hogwild_adagrad_epoch", "ref_reg_eval"):
             getattr(_lib, name).restype = c_dbl
         _lib.ref_mu.restype = c_dbl
     return _lib
@@ -233,6 +233,21 @@ def fm_loss_grad(X, y, P, w, intercept, degree, loss_kind="squared", row_begin=0
     return dict(loss=ls, y_pred=ypred, gP=to_component_major(gP), gw=gw, gb=gb.value)
 
 
+REG = {"identity": 0, "l1": 1, "squaredl12": 2, "squaredl12_rows": 3, "l21": 4}
+
+
+def prox_matrix(Pjs, lam, reg):
+    """reg.prox on one order's solver-layout matrix P[j][s] (returns a new array)."""
+    out = f64(Pjs).copy()
+    lib().ref_prox_matrix(_d(out), c_i64(out.shape[0]), c_int(out.shape[1]), c_dbl(lam), c_int(REG[reg]))
+    return out
+
+
+def reg_eval(Pjs, reg):
+    Pjs = f64(Pjs)
+    return lib().ref_reg_eval(_d(Pjs), c_i64(Pjs.shape[0]), c_int(Pjs.shape[1]), c_int(REG[reg]))
+
+
 def mbpsgd_fit(X, y, P, w, intercept, degree, loss_kind="squared", fit_linear=True,
                fit_intercept=True, max_iter=10, eta0=0.1, alpha0=1e-6, alpha=1e-3, beta=1e-4,
                gamma=0.0, reg="identity", mini_batch_size=-1, max_iter_inner=-1,
@@ -249,7 +264,7 @@ def mbpsgd_fit(X, y, P, w, intercept, degree, loss_kind="squared", fit_linear=Tr
         c_i64(X.n), c_i64(X.d), _d(X.data), _i(X.indices), _i(X.indptr), _d(f64(y)), c_int(degree),
         c_int(k), c_int(nO), c_int(dd - X.d), c_int(int(fit_linear)), c_int(int(fit_intercept)),
         _d(P), _d(w), C.byref(b), c_int(LOSS[loss_kind]), c_dbl(thr), c_int(max_iter), c_dbl(eta0),
-        c_dbl(alpha0), c_dbl(alpha), c_dbl(beta), c_dbl(gamma), c_int({"identity": 0, "l1": 1}[reg]),
+        c_dbl(alpha0), c_dbl(alpha), c_dbl(beta), c_dbl(gamma), c_int(REG[reg]),
         c_i64(mini_batch_size), c_i64(max_iter_inner), c_int(SCHED[scheduling]), c_dbl(power),
         c_dbl(tol), _i(perms), c_i64(0 if perms is None else perms.shape[0]), C.byref(itc), _d(el))
     return dict(P=P, w=w, intercept=b.value, it=itc.value, epoch_loss=el[:ne], epochs=ne)

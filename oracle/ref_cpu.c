@@ -415,9 +415,128 @@ static double softthreshold(double x, double a) {
 }
 
 /* ------------------------------------------------------------------ */
+/* Proximal operators used by MBPSGD (minibatch_psgd.nim:119-121)      */
+/* ------------------------------------------------------------------ */
+/* Deterministic stand-in for Nim's rand(max) (stdlib random, not under /root/reference): the pivot
+ * choice only affects the ORDER in which proxSquaredL12 finds theta, never theta or the set it sums
+ * (tests/test_oracle.py checks the result against the sort-based closed form). */
+static unsigned long long prox_rng_state = 0x9E3779B97F4A7C15ull;
+static i64 prox_rand(i64 maxIncl) {
+  prox_rng_state ^= prox_rng_state << 13;
+  prox_rng_state ^= prox_rng_state >> 7;
+  prox_rng_state ^= prox_rng_state << 17;
+  return (i64)(prox_rng_state % (unsigned long long)(maxIncl + 1));
+}
+static void swap_i64(i64 *a, i64 *b) { i64 t = *a; *a = *b; *b = t; }
+
+/* proxSquaredL12, regularizer/squaredl12.nim:16-64 (p strided so that a column of P[j][s] can be
+ * passed in place; candidates must hold n entries) */
+void ref_prox_squaredl12(double *p, i64 n, i64 stride, double lam, i64 *candidates) {
+  double S = 0.0;
+  i64 theta = 0, offset = 0, nCandidates = n;
+  for (i64 i = 0; i < n; i++) candidates[i] = i;
+  while (nCandidates != 0) {                                               /* :33 */
+    i64 ii = prox_rand(nCandidates - 1);
+    i64 i = candidates[offset + ii];
+    double pivot = fabs(p[i * stride]);
+    swap_i64(&candidates[offset + ii], &candidates[offset + nCandidates - 1]);
+    i64 nG = 1, nL = 0;
+    double SGi = pivot;
+    for (i64 ii2 = 0; ii2 < nCandidates - 1; ii2++) {                      /* :44-51 */
+      i64 i2 = candidates[offset + ii2];
+      if (pivot > fabs(p[i2 * stride])) {
+        swap_i64(&candidates[offset + nL], &candidates[offset + ii2]);
+        nL++;
+      } else {
+        nG++;
+        SGi += fabs(p[i2 * stride]);
+      }
+    }
+    if (pivot > 2 * lam * (S + SGi) / (1.0 + 2.0 * lam * (double)(theta + nG))) {   /* :53 L */
+      nCandidates = nL;
+      S += SGi;
+      theta += nG;
+    } else {                                                               /* :58-66 G */
+      offset = offset + nL;
+      nCandidates = 0;
+      for (i64 ii2 = 0; ii2 < nG - 1; ii2++) {
+        i64 i2 = candidates[offset + ii2];
+        if (pivot < fabs(p[i2 * stride])) {
+          swap_i64(&candidates[offset + ii2], &candidates[offset + nCandidates]);
+          nCandidates++;
+        }
+      }
+    }
+  }
+  S /= 1.0 + 2.0 * lam * (double)theta;                                    /* :67 */
+  for (i64 i = 0; i < n; i++) p[i * stride] = softthreshold(p[i * stride], 2 * lam * S);
+}
+
+/* L21.prox of one row, regularizer/l21.nim:25-29 (norm = sqrt of the sequential sum of squares) */
+void ref_prox_l21_row(double *pj, i64 k, double lam) {
+  double nrm = 0.0;
+  for (i64 s = 0; s < k; s++) nrm += pj[s] * pj[s];
+  nrm = sqrt(nrm);
+  if (nrm > lam) {
+    double f = 1.0 - lam / nrm;
+    for (i64 s = 0; s < k; s++) pj[s] *= f;
+  } else {
+    for (i64 s = 0; s < k; s++) pj[s] = 0.0;
+  }
+}
+
+/* reg.prox(P, lam, degree) on one order's SOLVER-layout matrix P[j][s] (dd x k):
+ * reg_kind 1 = L1 (l1.nim:38-41), 2 = SquaredL12 transpose=true (squaredl12.nim:147-156: one vector per
+ * component s over all features), 3 = SquaredL12 transpose=false (:157-159: one vector per feature),
+ * 4 = L21 (l21.nim:33-35). */
+void ref_prox_matrix(double *P, i64 dd, int k, double lam, int reg_kind) {
+  if (reg_kind == 1) {
+    for (i64 q = 0; q < dd * k; q++) P[q] = softthreshold(P[q], lam);
+  } else if (reg_kind == 2) {
+    i64 *cand = (i64 *)malloc(sizeof(i64) * (size_t)(dd > 0 ? dd : 1));
+    for (int s = 0; s < k; s++) ref_prox_squaredl12(P + s, dd, k, lam, cand);
+    free(cand);
+  } else if (reg_kind == 3) {
+    i64 *cand = (i64 *)malloc(sizeof(i64) * (size_t)(k > 0 ? k : 1));
+    for (i64 j = 0; j < dd; j++) ref_prox_squaredl12(P + j * k, k, 1, lam, cand);
+    free(cand);
+  } else if (reg_kind == 4) {
+    for (i64 j = 0; j < dd; j++) ref_prox_l21_row(P + j * k, k, lam);
+  }
+}
+
+/* reg.eval(P) on one order's solver-layout matrix (l1.nim eval, l21.nim:17-18, squaredl12.nim:72-75) */
+double ref_reg_eval(const double *P, i64 dd, int k, int reg_kind) {
+  double r = 0.0;
+  if (reg_kind == 1) {
+    for (i64 q = 0; q < dd * k; q++) r += fabs(P[q]);
+  } else if (reg_kind == 2) {
+    for (int s = 0; s < k; s++) {
+      double c = 0.0;
+      for (i64 j = 0; j < dd; j++) c += fabs(P[j * k + s]);
+      r += c * c;
+    }
+  } else if (reg_kind == 3) {
+    for (i64 j = 0; j < dd; j++) {
+      double c = 0.0;
+      for (int s = 0; s < k; s++) c += fabs(P[j * k + s]);
+      r += c * c;
+    }
+  } else if (reg_kind == 4) {
+    for (i64 j = 0; j < dd; j++) {
+      double c = 0.0;
+      for (int s = 0; s < k; s++) c += P[j * k + s] * P[j * k + s];
+      r += sqrt(c);
+    }
+  }
+  return r;
+}
+
+/* ------------------------------------------------------------------ */
 /* MBPSGD: optimizer/minibatch_psgd.nim:67-211, model/params.nim      */
 /* ------------------------------------------------------------------ */
-/* reg_kind: 0 = identity prox (SquaredL12 with gamma=0, squaredl12.nim:67-69), 1 = L1 (l1.nim:38-41).
+/* reg_kind: 0 = identity prox (SquaredL12 with gamma=0, squaredl12.nim:67-69), 1 = L1 (l1.nim:38-41),
+ * 2 / 3 = SquaredL12 transpose=true / false, 4 = L21 (see ref_prox_matrix).
  * perms: NULL (shuffle=false, cyclic order) or [nPerms][n] host-supplied permutations; the first is
  * used from the start and the next one replaces it each time the cursor wraps (:107-111,169-170).
  * P/w/intercept in/out use the MODEL layout; it_io is MBPSGD.it (1 unless warm-started, :151-152).
@@ -495,9 +614,9 @@ int ref_mbpsgd_fit(i64 n, i64 d, const double *data, const i64 *indices, const i
       if (fitLinear) for (i64 j = 0; j < d; j++) w[j] *= rw;
       if (fitIntercept) intercept *= rb_;
       /* reg.prox(params.P[order], gamma*eta_P/(1+eta_P*beta), degree-order), :119-121 */
-      if (reg_kind == 1) {
+      if (reg_kind != 0) {
         double lam = gamma * eta_P / (1.0 + eta_P * beta);
-        for (i64 q = 0; q < nP; q++) P[q] = softthreshold(P[q], lam);
+        for (int o = 0; o < nOrders; o++) ref_prox_matrix(P + (i64)o * dd * k, dd, k, lam, reg_kind);
       }
       it++;
     }

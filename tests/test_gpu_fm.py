@@ -193,31 +193,73 @@ def objective(oracle, csr, y, P, w, b, degree, loss_name, alpha0, alpha, beta):
     return float(np.mean(oracle.loss_vec(loss_name, y, yp))) + oracle.regularization(P, w, b, alpha0, alpha, beta)
 
 
+def make_reg(reg):
+    return {"identity": nf.newL1, "l1": nf.newL1, "l21": nf.newL21, "squaredl12": nf.newSquaredL12,
+            "squaredl12_rows": lambda: nf.newSquaredL12(transpose=False)}[reg]()
+
+
 @pytest.mark.parametrize("degree,fit_lower,reg", [(2, "explicit", "identity"), (3, "explicit", "identity"),
-                                                  (3, "augment", "l1"), (4, "none", "identity")])
+                                                  (3, "augment", "l1"), (4, "none", "identity"),
+                                                  (2, "explicit", "squaredl12"), (2, "augment", "squaredl12"),
+                                                  (2, "explicit", "squaredl12_rows"), (3, "explicit", "l21"),
+                                                  (2, "none", "l21")])
 @pytest.mark.parametrize("fit_linear,fit_intercept", [(True, True), (False, True), (True, False)])
 def test_mbpsgd_objective_matches_oracle(oracle, degree, fit_lower, reg, fit_linear, fit_intercept):
+    """identity prox == any regulariser at gamma=0 (the default SquaredL12 only exists for degree 2,
+    squaredl12.nim:103-106, so the degree-3/4 identity cases go through L1 with gamma=0)"""
     n, d, k = 80, 8, 4
     X = make_dense(n, d, 13, density=0.6, positive=False)
     y = np.sign(np.random.default_rng(2).standard_normal(n))
     csr = CSR.from_dense(X)
     P, w, nA = make_fm_params(d, degree, k, fit_lower, fit_linear, seed=11, scale=0.1)
-    kw = dict(eta0=0.1, alpha0=1e-6, alpha=1e-3, beta=1e-4, gamma=1e-3 if reg == "l1" else 0.0)
+    gamma = {"identity": 0.0, "l1": 1e-3, "l21": 5e-2, "squaredl12": 2e-1, "squaredl12_rows": 2e-1}[reg]
+    kw = dict(eta0=0.1, alpha0=1e-6, alpha=1e-3, beta=1e-4, gamma=gamma)
     # the model is injected with warmStart=true, so MBPSGD.it keeps its constructor value 0
     # (minibatch_psgd.nim:62,151-152); the oracle is started from the same counter
     ref = oracle.mbpsgd_fit(csr, y, P, w, 0.0, degree, "logistic", fit_linear, fit_intercept, max_iter=5,
                             reg=reg, mini_batch_size=7, it=0, **kw)
     fm = make_fm(degree, k, fit_lower, fit_linear, fit_intercept, P, w, 0.0, task=nf.classification)
-    opt = nf.newMBPSGD(maxIter=5, loss=nf.Logistic(), reg=nf.newL1() if reg == "l1" else nf.newSquaredL12(),
+    opt = nf.newMBPSGD(maxIter=5, loss=nf.Logistic(), reg=make_reg(reg),
                        miniBatchSize=7, verbose=0, tol=0.0, shuffle=False, **kw)
     opt.fit(csr_ds(csr), y, fm)
     np.testing.assert_allclose(opt.history, ref["epoch_loss"], rtol=OBJ_TOL)
+    if gamma > 0:   # the prox really acted: same sparsity pattern as the oracle, and some zeros
+        assert np.array_equal(fm.P == 0.0, ref["P"] == 0.0)
+        assert np.count_nonzero(ref["P"] == 0.0) > 0
     o_ref = objective(oracle, csr, y, ref["P"], ref["w"], ref["intercept"], degree, "logistic", 1e-6, 1e-3, 1e-4)
     o_dev = objective(oracle, csr, y, fm.P, fm.w, fm.intercept, degree, "logistic", 1e-6, 1e-3, 1e-4)
     assert abs(o_dev - o_ref) <= OBJ_TOL * abs(o_ref)
     assert max_rel(fm.P, ref["P"]) <= 1e-8
     assert max_rel(fm.w, ref["w"]) <= 1e-8
     assert opt.it == ref["it"]
+
+
+def test_mbpsgd_default_regulariser_is_degree2_only():
+    """newMBPSGD's default reg is SquaredL12 (minibatch_psgd.nim:26-27) whose initSGD raises for any
+    other degree (squaredl12.nim:103-106), whatever gamma is"""
+    csr = CSR.from_dense(make_dense(10, 5, 1))
+    P, w, _ = make_fm_params(5, 3, 2, "explicit", True, seed=1)
+    fm = make_fm(3, 2, "explicit", True, True, P, w, 0.0)
+    with pytest.raises(ValueError, match="SquaredL12 supports only degree=2"):
+        nf.newMBPSGD(maxIter=1, gamma=0.0, verbose=0).fit(csr_ds(csr), np.zeros(10), fm)
+
+
+@pytest.mark.parametrize("reg,gamma", [("squaredl12", 0.5), ("squaredl12_rows", 0.5), ("l21", 0.05)])
+def test_mbpsgd_prox_wide_model(oracle, reg, gamma):
+    """wider shapes for the prox kernels: 300 features (several blocks of the column sweep), k=40
+    (two elements per lane in the row-wise kernels), ragged rows"""
+    n, d, k = 120, 300, 40
+    csr = ragged_csr(n, d, 31, 12)
+    y = np.random.default_rng(5).standard_normal(n)
+    P, w, _ = make_fm_params(d, 2, k, "explicit", True, seed=7, scale=0.05)
+    kw = dict(eta0=0.2, alpha0=1e-6, alpha=1e-3, beta=1e-3, gamma=gamma)
+    ref = oracle.mbpsgd_fit(csr, y, P, w, 0.0, 2, "squared", max_iter=3, reg=reg, mini_batch_size=16, it=0, **kw)
+    fm = make_fm(2, k, "explicit", True, True, P, w, 0.0)
+    opt = nf.newMBPSGD(maxIter=3, reg=make_reg(reg), miniBatchSize=16, verbose=0, tol=0.0, shuffle=False, **kw)
+    opt.fit(csr_ds(csr), y, fm)
+    np.testing.assert_allclose(opt.history, ref["epoch_loss"], rtol=OBJ_TOL)
+    assert np.array_equal(fm.P == 0.0, ref["P"] == 0.0) and np.count_nonzero(ref["P"] == 0.0) > 0
+    assert max_rel(fm.P, ref["P"]) <= 1e-8 and max_rel(fm.w, ref["w"]) <= 1e-8
 
 
 def test_mbpsgd_default_minibatch_and_shuffle_contract(oracle):

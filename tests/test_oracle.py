@@ -182,3 +182,55 @@ def test_mbpsgd_reduces_to_full_gradient_step(oracle):
     assert abs(res["intercept"] - (0.05 - eta_b * g["gb"]) / (1 + eta_b * 1e-6)) < 1e-14
     assert abs(res["epoch_loss"][0] - g["loss"] / n) < 1e-14
     assert res["it"] == 2
+
+
+# ---------------------------------------------------------------- proximal operators
+@pytest.mark.parametrize("n,lam", [(1, 0.3), (7, 0.05), (50, 0.5), (200, 1e-3), (64, 10.0)])
+def test_prox_squaredl12_matches_closed_form_and_optimality(oracle, n, lam):
+    """proxSquaredL12 (squaredl12.nim:16-64) restated with a deterministic pivot stream == the sort-based
+    closed form, and satisfies the optimality condition q = softthreshold(p, 2*lam*||q||_1)."""
+    rng = np.random.default_rng(n)
+    for trial in range(5):
+        p = rng.standard_normal(n) * (rng.random(n) < 0.8)
+        if trial == 4:
+            p[: n // 2] = p[0]                          # ties
+        q = oracle.prox_matrix(p.reshape(-1, 1), lam, "squaredl12").ravel()
+        np.testing.assert_allclose(q, bf.prox_squaredl12_sorted(p, lam), rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(q, np.sign(p) * np.maximum(np.abs(p) - 2 * lam * np.sum(np.abs(q)), 0.0),
+                                   rtol=1e-10, atol=1e-14)
+        # transpose=false applies the same operator to every row
+        M = rng.standard_normal((3, n))
+        R = oracle.prox_matrix(M, lam, "squaredl12_rows")
+        for j in range(3):
+            np.testing.assert_allclose(R[j], bf.prox_squaredl12_sorted(M[j], lam), rtol=1e-12, atol=1e-15)
+
+
+def test_prox_l21_and_l1_and_eval(oracle):
+    rng = np.random.default_rng(9)
+    M = rng.standard_normal((6, 5))
+    M[2] *= 1e-3
+    R = oracle.prox_matrix(M, 0.1, "l21")
+    for j in range(6):
+        np.testing.assert_allclose(R[j], bf.prox_l21_row(M[j], 0.1), rtol=1e-14, atol=0)
+    assert np.all(R[2] == 0.0)
+    np.testing.assert_allclose(oracle.prox_matrix(M, 0.2, "l1"), np.sign(M) * np.maximum(np.abs(M) - 0.2, 0), rtol=1e-15)
+    np.testing.assert_allclose(oracle.reg_eval(M, "l1"), np.abs(M).sum(), rtol=1e-14)
+    np.testing.assert_allclose(oracle.reg_eval(M, "l21"), np.sqrt((M * M).sum(1)).sum(), rtol=1e-14)
+    np.testing.assert_allclose(oracle.reg_eval(M, "squaredl12"), (np.abs(M).sum(0) ** 2).sum(), rtol=1e-14)
+    np.testing.assert_allclose(oracle.reg_eval(M, "squaredl12_rows"), (np.abs(M).sum(1) ** 2).sum(), rtol=1e-14)
+
+
+def test_mbpsgd_with_squaredl12_decreases_and_sparsifies(oracle):
+    """the default nimfm MBPSGD configuration (reg=SquaredL12, gamma>0, degree 2) runs in the oracle:
+    a larger gamma gives a sparser P"""
+    X = make_dense(60, 12, 3, density=0.6)
+    csr = CSR.from_dense(X)
+    y = np.random.default_rng(4).standard_normal(60)
+    P, w, _ = make_fm_params(12, 2, 4, "explicit", True, 5)
+    nz = []
+    for gamma in (0.0, 1e-2, 1.0):
+        r = oracle.mbpsgd_fit(csr, y, P, w, 0.0, 2, "squared", max_iter=5, gamma=gamma, reg="squaredl12",
+                              mini_batch_size=10)
+        nz.append(int(np.count_nonzero(r["P"])))
+        assert np.all(np.isfinite(r["epoch_loss"]))
+    assert nz[0] >= nz[1] >= nz[2] and nz[2] < nz[0]
