@@ -103,6 +103,16 @@ int32_t nimfm_dataset_info(const nimfm_dataset *ds, int64_t *n, int64_t *d, int6
 int32_t nimfm_dataset_download(nimfm_ctx *ctx, const nimfm_dataset *ds, double *data,
                                int64_t *indices, int64_t *indptr, int64_t *fields);
 int32_t nimfm_dataset_free(nimfm_ctx *ctx, nimfm_dataset *ds);
+/* Text loaders (parsed by all host cores, uploaded straight to the device; targets are set on the
+ * dataset and read back with nimfm_dataset_get_targets).  nFeatures / nFields <= 0: inferred.
+ * loadSVMLightFile (dataset.nim:562-693; asCsc != 0 gives the CSCDataset overload, :643-686),
+ * loadFFMFile (dataset.nim:696-790), loadUserItemRatingFile (dataset.nim:840-990). */
+int32_t nimfm_load_svmlight(nimfm_ctx *ctx, const char *path, int64_t nFeatures, int32_t asCsc,
+                            nimfm_dataset **out);
+int32_t nimfm_load_ffm(nimfm_ctx *ctx, const char *path, int64_t nFeatures, int64_t nFields,
+                       nimfm_dataset **out);
+int32_t nimfm_load_user_item_rating(nimfm_ctx *ctx, const char *path, int32_t asCsc, nimfm_dataset **out);
+int32_t nimfm_dataset_get_targets(nimfm_ctx *ctx, const nimfm_dataset *ds, double *y);
 
 /* ---------------------------------------------------------------- FM model state
  * FactorizationMachine (model/factorization_machine.nim:11-139).  nOrders / nAug follow :81-97. */

@@ -68,6 +68,13 @@ proc nimfm_dataset_vstack(ctx: Ctx, parts: ptr DeviceDataset, nParts: int32,
                           outDs: ptr DeviceDataset): int32      # vstack, dataset.nim:452-483
 proc nimfm_dataset_set_targets(ctx: Ctx, ds: DeviceDataset, y: ptr cdouble): int32
 proc nimfm_dataset_free(ctx: Ctx, ds: DeviceDataset): int32
+proc nimfm_load_svmlight(ctx: Ctx, path: cstring, nFeatures: int64, asCsc: int32,
+                         outDs: ptr DeviceDataset): int32        # loadSVMLightFile, dataset.nim:616-693
+proc nimfm_load_ffm(ctx: Ctx, path: cstring, nFeatures, nFields: int64,
+                    outDs: ptr DeviceDataset): int32             # loadFFMFile, dataset.nim:768-790
+proc nimfm_load_user_item_rating(ctx: Ctx, path: cstring, asCsc: int32,
+                                 outDs: ptr DeviceDataset): int32  # loadUserItemRatingFile, dataset.nim:840-990
+proc nimfm_dataset_get_targets(ctx: Ctx, ds: DeviceDataset, y: ptr cdouble): int32
 proc nimfm_fm_create(ctx: Ctx, degree, nComponents, nOrders, nAugments: int32, nFeatures: int64,
                      fitLinear, fitIntercept: int32, outFm: ptr DeviceFM): int32
 proc nimfm_fm_set_params(ctx: Ctx, fm: DeviceFM, P, w: ptr cdouble, intercept: cdouble, lams: ptr cdouble): int32

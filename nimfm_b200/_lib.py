@@ -68,6 +68,10 @@ SYMBOLS = {
     "nimfm_dataset_info": (c_i32, [VP, PI64, PI64, PI64, C.POINTER(c_i32), PI64, PI64]),
     "nimfm_dataset_download": (c_i32, [VP, VP, VP, VP, VP, VP]),
     "nimfm_dataset_free": (c_i32, [VP, VP]),
+    "nimfm_load_svmlight": (c_i32, [VP, C.c_char_p, c_i64, c_i32, PVP]),
+    "nimfm_load_ffm": (c_i32, [VP, C.c_char_p, c_i64, c_i64, PVP]),
+    "nimfm_load_user_item_rating": (c_i32, [VP, C.c_char_p, c_i32, PVP]),
+    "nimfm_dataset_get_targets": (c_i32, [VP, VP, VP]),
     "nimfm_fm_create": (c_i32, [VP, c_i32, c_i32, c_i32, c_i32, c_i64, c_i32, c_i32, PVP]),
     "nimfm_fm_set_params": (c_i32, [VP, VP, VP, VP, c_dbl, VP]),
     "nimfm_fm_get_params": (c_i32, [VP, VP, VP, VP, PD]),

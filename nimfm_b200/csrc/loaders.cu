@@ -1,0 +1,289 @@
+// loaders.cu -- text loaders feeding the path: svmlight/libsvm, libffm and
+// user-item-rating files parsed on the host by all cores and uploaded straight into device datasets.
+//   loadSVMLightFile        dataset.nim:562-693   "label j:val j:val ..."   (CSR, or CSC via the stable transpose)
+//   loadFFMFile             dataset.nim:696-790   "label field:j:val ..."
+//   loadUserItemRatingFile  dataset.nim:840-990   "user<sep>item<sep>rating[<sep>comment]" -> one-hot user+item
+// Index conventions follow the reference: indices are assumed 1-based unless a 0 occurs
+// (offset = 0 iff min index == 0, :585-586); nFeatures = max index + 1 - offset, widened by the
+// caller's nFeatures (:623-632); a negative index raises "Negative index is included.".
+// The file is split at line boundaries into one slice per thread; slices are parsed independently and
+// concatenated in order, so the result is identical to a sequential read.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <charconv>
+#include <thread>
+
+#include "common.cuh"
+
+namespace {
+
+enum { FMT_SVM = 0, FMT_FFM = 1, FMT_UIR = 2 };
+
+struct Slice {
+  std::vector<double> data, y;
+  std::vector<int64_t> indices, fields, rowLen;
+  int64_t minIdx = 1, maxIdx = 0, minFld = 1, maxFld = 1;   // initial values as dataset.nim:569-570,705-708
+  int64_t minItem = 1, maxItem = 0;                          // user-item files: indices hold (user, item)
+  int64_t badLine = -1;                                      // slice-local number of the first malformed line
+};
+
+inline const char *skip_blank(const char *p, const char *e) {
+  while (p < e && (*p == ' ' || *p == '\t' || *p == '\r')) ++p;
+  return p;
+}
+
+inline bool parse_i64(const char *&p, const char *e, int64_t &v) {
+  if (p < e && *p == '+') ++p;
+  auto r = std::from_chars(p, e, v);
+  if (r.ec != std::errc()) return false;
+  p = r.ptr;
+  return true;
+}
+
+inline bool parse_f64(const char *&p, const char *e, double &v) {
+  if (p < e && *p == '+') ++p;
+  auto r = std::from_chars(p, e, v);
+  if (r.ec != std::errc()) return false;
+  p = r.ptr;
+  return true;
+}
+
+inline bool is_digit(char c) { return c >= '0' && c <= '9'; }
+
+void parse_slice(const char *b, const char *e, int fmt, Slice &s) {
+  int64_t lineNo = 0;
+  while (b < e) {
+    const char *le = static_cast<const char *>(memchr(b, '\n', (size_t)(e - b)));
+    if (!le) le = e;
+    const char *p = skip_blank(b, le);
+    ++lineNo;
+    if (fmt == FMT_UIR) {
+      if (le - b >= 5) {   // dataset.nim:869-870 skips shorter lines
+        int64_t user = 0, item = 0;
+        double rating = 0.0;
+        while (p < le && !is_digit(*p)) ++p;                     // skipUntil(line, Numbers)
+        bool ok = parse_i64(p, le, user);
+        while (p < le && !is_digit(*p)) ++p;
+        ok = ok && parse_i64(p, le, item);
+        while (p < le && !is_digit(*p)) ++p;
+        ok = ok && parse_f64(p, le, rating);
+        if (!ok) { if (s.badLine < 0) s.badLine = lineNo; }
+        else {
+          s.indices.push_back(user);
+          s.indices.push_back(item);
+          s.y.push_back(rating);
+          s.minIdx = std::min(s.minIdx, user); s.maxIdx = std::max(s.maxIdx, user);
+          s.minItem = std::min(s.minItem, item); s.maxItem = std::max(s.maxItem, item);
+        }
+      }
+    } else if (p < le) {   // blank lines carry no sample
+      double target = 0.0;
+      bool ok = parse_f64(p, le, target);
+      int64_t len = 0;
+      while (ok) {
+        p = skip_blank(p, le);
+        if (p >= le) break;
+        int64_t field = 0, j = 0;
+        double val = 0.0;
+        if (fmt == FMT_FFM) {
+          ok = parse_i64(p, le, field) && p < le && *p == ':';
+          if (!ok) break;
+          ++p;
+        }
+        ok = parse_i64(p, le, j) && p < le && *p == ':';
+        if (!ok) break;
+        ++p;
+        ok = parse_f64(p, le, val);
+        if (!ok) break;
+        if (fmt == FMT_FFM) {
+          s.fields.push_back(field);
+          s.minFld = std::min(s.minFld, field); s.maxFld = std::max(s.maxFld, field);
+        }
+        s.indices.push_back(j);
+        s.data.push_back(val);
+        s.minIdx = std::min(s.minIdx, j); s.maxIdx = std::max(s.maxIdx, j);
+        ++len;
+      }
+      if (!ok && s.badLine < 0) s.badLine = lineNo;
+      s.y.push_back(target);
+      s.rowLen.push_back(len);
+    }
+    b = le + 1;
+  }
+}
+
+struct Mapped {
+  const char *p = nullptr;
+  size_t n = 0;
+  int fd = -1;
+  ~Mapped() {
+    if (p && n) munmap(const_cast<char *>(p), n);
+    if (fd >= 0) close(fd);
+  }
+};
+
+int load_text(nimfm_ctx *ctx, const char *path, int fmt, std::vector<Slice> &slices) {
+  REQUIRE(path != nullptr, "path is NULL");
+  Mapped m;
+  m.fd = open(path, O_RDONLY);
+  if (m.fd < 0) return nimfm_fail(ctx, NIMFM_ERR_INVALID, "cannot open %s", path);   // IOError in the reference
+  struct stat st;
+  if (fstat(m.fd, &st) != 0) return nimfm_fail(ctx, NIMFM_ERR_INVALID, "cannot stat %s", path);
+  m.n = (size_t)st.st_size;
+  if (m.n == 0) { slices.assign(1, Slice()); return NIMFM_OK; }
+  void *mp = mmap(nullptr, m.n, PROT_READ, MAP_PRIVATE, m.fd, 0);
+  if (mp == MAP_FAILED) { m.n = 0; return nimfm_fail(ctx, NIMFM_ERR_INVALID, "cannot map %s", path); }
+  m.p = static_cast<const char *>(mp);
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t T = std::max<size_t>(1, std::min<size_t>({(size_t)(hw ? hw : 1), (size_t)64, m.n / (1 << 20) + 1}));
+  std::vector<const char *> cut(T + 1);
+  cut[0] = m.p;
+  cut[T] = m.p + m.n;
+  for (size_t t = 1; t < T; t++) {
+    const char *q = m.p + m.n * t / T;
+    if (q < cut[t - 1]) q = cut[t - 1];
+    const char *nl = static_cast<const char *>(memchr(q, '\n', (size_t)(m.p + m.n - q)));
+    cut[t] = nl ? nl + 1 : m.p + m.n;
+  }
+  slices.assign(T, Slice());
+  std::vector<std::thread> th;
+  for (size_t t = 1; t < T; t++) th.emplace_back(parse_slice, cut[t], cut[t + 1], fmt, std::ref(slices[t]));
+  parse_slice(cut[0], cut[1], fmt, slices[0]);
+  for (auto &x : th) x.join();
+  int64_t lines = 0;
+  for (size_t t = 0; t < T; t++) {
+    if (slices[t].badLine >= 0)
+      return nimfm_fail(ctx, NIMFM_ERR_INVALID, "%s: malformed line (line %lld of slice %zu, after ~%lld samples)", path,
+                        (long long)slices[t].badLine, t, (long long)lines);
+    lines += (int64_t)slices[t].y.size();
+  }
+  return NIMFM_OK;
+}
+
+int finish_upload(nimfm_ctx *ctx, int64_t n, int64_t d, std::vector<double> &data, std::vector<int64_t> &indices,
+                  std::vector<int64_t> &indptr, std::vector<int64_t> *fields, int64_t nFields,
+                  const std::vector<double> &y, int asCsc, nimfm_dataset **out) {
+  nimfm_dataset *csr = nullptr;
+  int rc = nimfm_csr_upload(ctx, n, d, data.data(), indices.data(), indptr.data(), fields ? fields->data() : nullptr,
+                            nFields, 0, n, &csr);
+  if (rc) return rc;
+  if (n > 0 && (rc = nimfm_dataset_set_targets(ctx, csr, y.data()))) { nimfm_dataset_free(ctx, csr); return rc; }
+  if (!asCsc) { *out = csr; return NIMFM_OK; }
+  // the CSC loaders (dataset.nim:643-686, 903-990) place entries column by column in row order:
+  // exactly the stable transpose
+  nimfm_dataset *csc = nullptr;
+  rc = nimfm_dataset_transpose(ctx, csr, &csc);
+  nimfm_dataset_free(ctx, csr);
+  if (rc) return rc;
+  *out = csc;
+  return NIMFM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t nimfm_load_svmlight(nimfm_ctx *ctx, const char *path, int64_t nFeatures, int32_t asCsc, nimfm_dataset **out) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  REQUIRE(out != nullptr, "out is NULL");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<Slice> sl;
+  int rc = load_text(ctx, path, FMT_SVM, sl);
+  if (rc) return rc;
+  int64_t n = 0, nnz = 0, minIdx = 1, maxIdx = 0;
+  for (auto &s : sl) {
+    n += (int64_t)s.y.size(); nnz += (int64_t)s.data.size();
+    minIdx = std::min(minIdx, s.minIdx); maxIdx = std::max(maxIdx, s.maxIdx);
+  }
+  REQUIRE(minIdx >= 0, "Negative index is included.");                       // dataset.nim:583-584
+  const int64_t offset = minIdx == 0 ? 0 : 1;                                // :585
+  const int64_t nPred = maxIdx + 1 - offset;                                 // :586
+  REQUIRE(!(nFeatures > 0 && nPred > nFeatures), "nFeatures is %lld but dataset has at least %lld features.",
+          (long long)nFeatures, (long long)nPred);                           // :625-628
+  std::vector<double> data((size_t)nnz), y((size_t)n);
+  std::vector<int64_t> indices((size_t)nnz), indptr((size_t)n + 1, 0);
+  int64_t r = 0, q = 0;
+  for (auto &s : sl) {
+    for (size_t i = 0; i < s.y.size(); i++, r++) { y[r] = s.y[i]; indptr[r + 1] = indptr[r] + s.rowLen[i]; }
+    for (size_t i = 0; i < s.data.size(); i++, q++) { data[q] = s.data[i]; indices[q] = s.indices[i] - offset; }
+  }
+  return finish_upload(ctx, n, std::max(nPred, nFeatures), data, indices, indptr, nullptr, 0, y, asCsc, out);
+}
+
+int32_t nimfm_load_ffm(nimfm_ctx *ctx, const char *path, int64_t nFeatures, int64_t nFields, nimfm_dataset **out) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  REQUIRE(out != nullptr, "out is NULL");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<Slice> sl;
+  int rc = load_text(ctx, path, FMT_FFM, sl);
+  if (rc) return rc;
+  int64_t n = 0, nnz = 0, minIdx = 1, maxIdx = 0, minFld = 1, maxFld = 1;
+  for (auto &s : sl) {
+    n += (int64_t)s.y.size(); nnz += (int64_t)s.data.size();
+    minIdx = std::min(minIdx, s.minIdx); maxIdx = std::max(maxIdx, s.maxIdx);
+    minFld = std::min(minFld, s.minFld); maxFld = std::max(maxFld, s.maxFld);
+  }
+  REQUIRE(minIdx >= 0, "Negative index is included.");                       // :732-733
+  REQUIRE(minFld >= 0, "Negative field index is included.");
+  const int64_t offset = minIdx == 0 ? 0 : 1, offsetField = minFld == 0 ? 0 : 1;   // :734-737
+  const int64_t nPred = maxIdx + 1 - offset, nFldPred = maxFld + 1 - offsetField;
+  REQUIRE(!(nFields > 0 && nFldPred > nFields), "nFields is %lld but dataset has at least %lld fields.",
+          (long long)nFields, (long long)nFldPred);                          // :778-781
+  REQUIRE(!(nFeatures > 0 && nPred > nFeatures), "nFeatures is %lld but dataset has at least %lld features.",
+          (long long)nFeatures, (long long)nPred);                           // :783-786
+  std::vector<double> data((size_t)nnz), y((size_t)n);
+  std::vector<int64_t> indices((size_t)nnz), fields((size_t)nnz), indptr((size_t)n + 1, 0);
+  int64_t r = 0, q = 0;
+  for (auto &s : sl) {
+    for (size_t i = 0; i < s.y.size(); i++, r++) { y[r] = s.y[i]; indptr[r + 1] = indptr[r] + s.rowLen[i]; }
+    for (size_t i = 0; i < s.data.size(); i++, q++) {
+      data[q] = s.data[i]; indices[q] = s.indices[i] - offset; fields[q] = s.fields[i] - offsetField;
+    }
+  }
+  return finish_upload(ctx, n, std::max(nPred, nFeatures), data, indices, indptr, &fields, std::max(nFldPred, nFields),
+                       y, 0, out);
+}
+
+int32_t nimfm_load_user_item_rating(nimfm_ctx *ctx, const char *path, int32_t asCsc, nimfm_dataset **out) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  REQUIRE(out != nullptr, "out is NULL");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<Slice> sl;
+  int rc = load_text(ctx, path, FMT_UIR, sl);
+  if (rc) return rc;
+  int64_t n = 0, minUser = 1, maxUser = 0, minItem = 1, maxItem = 0;
+  for (auto &s : sl) {
+    n += (int64_t)s.y.size();
+    minUser = std::min(minUser, s.minIdx); maxUser = std::max(maxUser, s.maxIdx);
+    minItem = std::min(minItem, s.minItem); maxItem = std::max(maxItem, s.maxItem);
+  }
+  REQUIRE(minUser >= 0, "The minimum user id < 0.");                         // :884-885
+  REQUIRE(minItem >= 0, "The minimum item id < 0.");                         // :887-888
+  const int64_t nUsers = maxUser - minUser + 1, nItems = maxItem - minItem + 1;   // :889-890
+  std::vector<double> data((size_t)n * 2, 1.0), y((size_t)n);
+  std::vector<int64_t> indices((size_t)n * 2), indptr((size_t)n + 1);
+  int64_t r = 0;
+  for (auto &s : sl)
+    for (size_t i = 0; i < s.y.size(); i++, r++) {
+      y[r] = s.y[i];
+      indices[2 * r] = s.indices[2 * i] - minUser;                           // :892-894
+      indices[2 * r + 1] = s.indices[2 * i + 1] + nUsers - minItem;
+    }
+  for (int64_t i = 0; i <= n; i++) indptr[i] = 2 * i;
+  return finish_upload(ctx, n, n > 0 ? nUsers + nItems : 0, data, indices, indptr, nullptr, 0, y, asCsc, out);
+}
+
+int32_t nimfm_dataset_get_targets(nimfm_ctx *ctx, const nimfm_dataset *ds, double *y) {
+  if (!ctx || !ds) return NIMFM_ERR_INVALID;
+  REQUIRE(y != nullptr || ds->n == 0, "y is NULL");
+  REQUIRE(ds->y != nullptr || ds->n == 0, "dataset has no targets");
+  CK(cudaSetDevice(ctx->device));
+  if (ds->n) CK(cudaMemcpy(y, ds->y, (size_t)ds->n * 8, cudaMemcpyDeviceToHost));
+  return NIMFM_OK;
+}
+
+}  // extern "C"

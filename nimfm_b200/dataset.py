@@ -6,6 +6,7 @@ lazily created device twin owned by libnimfm_cuda.so.  Dummy-feature augmentatio
 arrays never change.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -238,3 +239,69 @@ def _from_dense(X, cls):
         data.extend(row[nz].tolist())
         indptr.append(len(indices))
     return cls(data, indices, indptr, n, d)
+
+
+# ---------------------------------------------------------------- text formats (dataset.nim:562-990)
+def _loaded(h, cls):
+    out = _adopt(h, cls, None)
+    y = np.zeros(out.nSamples)
+    _lib.check(_lib.load().nimfm_dataset_get_targets(_lib.ctx(), h, _lib.ptr(y)))
+    return out, y
+
+
+def _path(f):
+    return os.path.expanduser(str(f)).encode()
+
+
+def loadSVMLightFile(f, nFeatures=-1, kind="csr"):
+    """loadSVMLightFile (dataset.nim:616-693): returns (CSRDataset | CSCDataset, y).  The file is parsed
+    by the library on all host cores and uploaded directly; 1-based indices unless a 0 occurs."""
+    h = C.c_void_p()
+    csc = {"csr": 0, "csc": 1}[kind]
+    _lib.check(_lib.load().nimfm_load_svmlight(_lib.ctx(), _path(f), int(nFeatures), csc, C.byref(h)))
+    return _loaded(h, CSCDataset if csc else CSRDataset)
+
+
+def loadFFMFile(f, nFeatures=-1, nFields=-1):
+    """loadFFMFile (dataset.nim:768-790): returns (CSRFieldDataset, y)"""
+    h = C.c_void_p()
+    _lib.check(_lib.load().nimfm_load_ffm(_lib.ctx(), _path(f), int(nFeatures), int(nFields), C.byref(h)))
+    return _loaded(h, CSRFieldDataset)
+
+
+def loadUserItemRatingFile(f, kind="csr"):
+    """loadUserItemRatingFile (dataset.nim:840-990): one-hot user + item features, value 1.0"""
+    h = C.c_void_p()
+    csc = {"csr": 0, "csc": 1}[kind]
+    _lib.check(_lib.load().nimfm_load_user_item_rating(_lib.ctx(), _path(f), csc, C.byref(h)))
+    return _loaded(h, CSCDataset if csc else CSRDataset)
+
+
+def _num(v):
+    """Nim's `$` / fmt of a number: integers print without a fraction, floats as the shortest round-trip"""
+    return str(int(v)) if isinstance(v, (int, np.integer)) else repr(float(v))
+
+
+def dumpSVMLightFile(f, X, y):
+    """dumpSVMLightFile (dataset.nim:793-805): 1-based "label j:val ...", no trailing newline"""
+    if X.nSamples != len(y):
+        raise ValueError("X.nSamples != len(y).")
+    with open(os.path.expanduser(str(f)), "w") as out:
+        for i in range(X.nSamples):
+            s, e = int(X.indptr[i]), int(X.indptr[i + 1])
+            out.write(_num(y[i]) + "".join(f" {int(X.indices[q]) + 1}:{_num(X.data[q])}" for q in range(s, e)))
+            if i + 1 != X.nSamples:
+                out.write("\n")
+
+
+def dumpFFMFile(f, X, y):
+    """dumpFFMFile (dataset.nim:825-837): 1-based "label field:j:val ..." """
+    if X.nSamples != len(y):
+        raise ValueError("X.nSamples != len(y).")
+    with open(os.path.expanduser(str(f)), "w") as out:
+        for i in range(X.nSamples):
+            s, e = int(X.indptr[i]), int(X.indptr[i + 1])
+            out.write(_num(y[i]) + "".join(
+                f" {int(X.fields[q]) + 1}:{int(X.indices[q]) + 1}:{_num(X.data[q])}" for q in range(s, e)))
+            if i + 1 != X.nSamples:
+                out.write("\n")

@@ -436,3 +436,85 @@ def hogwild_adagrad_epoch(X, y, Pf, w, intercept, degree, n_threads, is_ffm=Fals
         c_dbl(eta0), c_dbl(alpha0), c_dbl(alpha), c_dbl(beta), C.byref(itc), _d(gsP), _d(gnP),
         _d(gsw), _d(gnw), C.byref(gsb), C.byref(gnb), None, c_int(n_threads), C.byref(viol))
     return ls, viol.value
+
+
+# ---------------------------------------------------------------- text loaders (dataset.nim:562-990)
+def _tokens(line):
+    """the reference walks the line with parseFloat / parseInt, skipping ONE separator character after
+    every number (dataset.nim:573-582); for well-formed lines that is a split on blanks and colons"""
+    return line.replace(":", " ").split()
+
+
+def load_svmlight(path, n_features=-1):
+    """loadSVMLightFile -> CSR (dataset.nim:562-632): returns (CSR, y)"""
+    data, indices, indptr, y = [], [], [0], []
+    min_index, max_index = 1, 0                                   # :569-570
+    for line in open(os.path.expanduser(path)).read().split("\n"):
+        tok = _tokens(line)
+        if not tok:
+            continue
+        y.append(float(tok[0]))
+        for a in range(1, len(tok), 2):
+            j = int(tok[a])
+            min_index, max_index = min(j, min_index), max(j, max_index)
+            indices.append(j)
+            data.append(float(tok[a + 1]))
+        indptr.append(len(indices))
+    if min_index < 0:
+        raise ValueError("Negative index is included.")           # :583-584
+    offset = 0 if min_index == 0 else 1                           # :585
+    pred = max_index + 1 - offset                                 # :586
+    if n_features > 0 and pred > n_features:
+        raise ValueError(f"nFeatures is {n_features} but dataset has at least {pred} features.")
+    return CSR(data, np.array(indices, np.int64) - offset, indptr, len(y), max(pred, n_features)), f64(y)
+
+
+def load_ffm(path, n_features=-1, n_fields=-1):
+    """loadFFMFile (dataset.nim:696-790): returns (CSR with fields, y)"""
+    data, indices, fields, indptr, y = [], [], [], [0], []
+    min_index, max_index, min_field, max_field = 1, 0, 1, 1       # :705-708
+    for line in open(os.path.expanduser(path)).read().split("\n"):
+        tok = _tokens(line)
+        if not tok:
+            continue
+        y.append(float(tok[0]))
+        for a in range(1, len(tok), 3):
+            f, j = int(tok[a]), int(tok[a + 1])
+            min_field, max_field = min(f, min_field), max(f, max_field)
+            min_index, max_index = min(j, min_index), max(j, max_index)
+            fields.append(f)
+            indices.append(j)
+            data.append(float(tok[a + 2]))
+        indptr.append(len(indices))
+    if min_index < 0:
+        raise ValueError("Negative index is included.")
+    offset = 0 if min_index == 0 else 1
+    offset_field = 0 if min_field == 0 else 1                     # :736
+    pred, fpred = max_index + 1 - offset, max_field + 1 - offset_field
+    if n_fields > 0 and fpred > n_fields:
+        raise ValueError(f"nFields is {n_fields} but dataset has at least {fpred} fields.")
+    if n_features > 0 and pred > n_features:
+        raise ValueError(f"nFeatures is {n_features} but dataset has at least {pred} features.")
+    return CSR(data, np.array(indices, np.int64) - offset, indptr, len(y), max(pred, n_features),
+               fields=np.array(fields, np.int64) - offset_field, n_fields=max(fpred, n_fields)), f64(y)
+
+
+def load_user_item_rating(path):
+    """loadUserItemRatingFile -> CSR (dataset.nim:840-898)"""
+    import re
+    users, items, y = [], [], []
+    for line in open(os.path.expanduser(path)).read().split("\n"):
+        if len(line) < 5:                                         # :869-870
+            continue
+        nums = re.findall(r"\d+(?:\.\d+)?(?:[eE][-+]?\d+)?", line)
+        users.append(int(nums[0]))
+        items.append(int(nums[1]))
+        y.append(float(nums[2]))
+    n = len(y)
+    min_user, max_user = min([1] + users), max([0] + users)       # :862-866
+    min_item, max_item = min([1] + items), max([0] + items)
+    n_users, n_items = max_user - min_user + 1, max_item - min_item + 1
+    idx = np.empty(2 * n, np.int64)
+    idx[0::2] = np.array(users, np.int64) - min_user
+    idx[1::2] = np.array(items, np.int64) + n_users - min_item
+    return CSR(np.ones(2 * n), idx, np.arange(n + 1) * 2, n, n_users + n_items if n else 0), f64(y)

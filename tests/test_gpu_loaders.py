@@ -1,0 +1,132 @@
+"""Text loaders (loadSVMLightFile / loadFFMFile / loadUserItemRatingFile,
+dataset.nim:562-990) -- the library's threaded parser + direct device upload against the oracle's
+restatement of the reference's read loops.  Index bookkeeping must be bit-exact; values are parsed
+to the nearest double by both sides (shortest round-trip text), so they are compared exactly too."""
+import numpy as np
+import pytest
+
+import nimfm_b200 as nf
+from helpers import make_dense, make_field_csr
+from oracle.oracle import CSR
+
+pytestmark = pytest.mark.gpu
+
+
+def same(ds, ref, fields=False):
+    data, indices, indptr, fld = ds.download()
+    assert ds.shape == (ref.n, ref.d)
+    assert np.array_equal(indptr, ref.indptr) and np.array_equal(indices, ref.indices)
+    assert np.array_equal(data, ref.data)
+    if fields:
+        assert np.array_equal(fld, ref.fields) and ds.nFields == ref.n_fields
+
+
+def write_svm(path, csr, y, base=1, sep="\n", trailing=False):
+    lines = []
+    for i in range(csr.n):
+        s, e = csr.indptr[i], csr.indptr[i + 1]
+        lines.append(repr(float(y[i])) + "".join(f" {csr.indices[q] + base}:{float(csr.data[q])!r}" for q in range(s, e)))
+    open(path, "w").write(sep.join(lines) + (sep if trailing else ""))
+
+
+@pytest.mark.parametrize("base,trailing", [(1, False), (0, False), (1, True)])
+def test_svmlight_matches_reference_reader(oracle, tmp_path, base, trailing):
+    X = make_dense(57, 23, 3, density=0.3, positive=False)
+    X[5] = 0.0                                   # a sample without features
+    if base == 0:
+        X[0, 0] = 1.5                            # a 0 index makes the file 0-based (dataset.nim:585)
+    else:
+        X[:, 0] = 0.0                            # 1-based file without index 1: offset stays 1
+    csr = CSR.from_dense(X)
+    y = np.random.default_rng(1).standard_normal(57)
+    p = str(tmp_path / "a.svm")
+    write_svm(p, csr, y, base=base, trailing=trailing)
+    ref, yref = oracle.load_svmlight(p)
+    ds, yy = nf.loadSVMLightFile(p)
+    same(ds, ref)
+    assert np.array_equal(yy, yref) and np.array_equal(yy, y)
+    assert np.array_equal(ref.to_dense()[:, :X.shape[1]][:, :ref.d], X[:, :ref.d])
+    # nFeatures widens, or raises when too small (:625-632)
+    wide, _ = nf.loadSVMLightFile(p, nFeatures=40)
+    assert wide.shape == (57, 40)
+    with pytest.raises(ValueError, match="but dataset has at least"):
+        nf.loadSVMLightFile(p, nFeatures=3)
+    # the CSC overload (:643-686) == stable transpose of the CSR
+    csc, yc = nf.loadSVMLightFile(p, kind="csc")
+    cref = oracle.csr_to_csc(ref)
+    same(csc, cref)
+    assert isinstance(csc, nf.CSCDataset) and np.array_equal(yc, y)
+
+
+def test_svmlight_dump_load_roundtrip_and_large(tmp_path):
+    """dumpSVMLightFile -> loadSVMLightFile is the identity; a file large enough to be parsed by
+    several threads keeps row order"""
+    rng = np.random.default_rng(7)
+    n, d, z = 60_000, 500, 9
+    cols = np.sort(rng.integers(0, d // z, size=(n, z)) + (np.arange(z) * (d // z))[None, :], axis=1)
+    cols[0, 0], cols[-1, -1] = 0, d - 1
+    data = rng.standard_normal(n * z)
+    y = rng.integers(0, 2, n).astype(np.float64) * 2 - 1
+    ds = nf.newCSRDataset(data, cols.ravel(), np.arange(n + 1) * z, n, d)
+    p = str(tmp_path / "big.svm")
+    nf.dumpSVMLightFile(p, ds, y)
+    assert not open(p).read().endswith("\n")
+    back, yb = nf.loadSVMLightFile(p)
+    assert back.shape == (n, d)
+    assert np.array_equal(back.indices, cols.ravel()) and np.array_equal(back.data, data)
+    assert np.array_equal(back.indptr, np.arange(n + 1) * z) and np.array_equal(yb, y)
+
+
+def test_svmlight_errors(tmp_path):
+    p = str(tmp_path / "neg.svm")
+    open(p, "w").write("1 -2:0.5 3:1\n0 1:2\n")
+    with pytest.raises(ValueError, match="Negative index is included"):
+        nf.loadSVMLightFile(p)
+    open(p, "w").write("1 2:0.5 x:1\n")
+    with pytest.raises(ValueError, match="malformed"):
+        nf.loadSVMLightFile(p)
+    with pytest.raises(ValueError, match="cannot open"):
+        nf.loadSVMLightFile(str(tmp_path / "missing.svm"))
+
+
+def test_ffm_file_matches_reference_reader(oracle, tmp_path):
+    X, csr, field_of = make_field_csr(45, 14, 4, 9)
+    y = np.sign(np.random.default_rng(2).standard_normal(45))
+    ds0 = nf.newCSRFieldDataset(csr.data, csr.indices, csr.indptr, csr.fields, csr.n, csr.d, csr.n_fields)
+    p = str(tmp_path / "a.ffm")
+    nf.dumpFFMFile(p, ds0, y)
+    ref, yref = oracle.load_ffm(p)
+    ds, yy = nf.loadFFMFile(p)
+    same(ds, ref, fields=True)
+    assert np.array_equal(yy, yref) and np.array_equal(yy, y)
+    assert np.array_equal(ds.indices, csr.indices[:len(ds.indices)]) and np.array_equal(ds.fields, csr.fields)
+    wide, _ = nf.loadFFMFile(p, nFeatures=30, nFields=6)
+    assert wide.shape == (45, 30) and wide.nFields == 6
+    with pytest.raises(ValueError, match="fields"):
+        nf.loadFFMFile(p, nFields=2)
+    # and the loaded dataset drives the FFM path
+    rng = np.random.default_rng(3)
+    m = nf.newFieldAwareFactorizationMachine(nf.classification, nComponents=4, warmStart=True)
+    m.P, m.w, m.intercept, m.isInitialized = rng.standard_normal((4, ds.nFeatures, 4)) * 0.1, np.zeros(ds.nFeatures), 0.0, True
+    got = m.decisionFunction(ds)
+    want = oracle.ffm_decision_function(ref, m.P, m.w, 0.0)
+    assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-12)) < 1e-10
+
+
+def test_user_item_rating_file(oracle, tmp_path):
+    rng = np.random.default_rng(4)
+    n = 300
+    users, items = rng.integers(3, 40, n), rng.integers(10, 90, n)
+    ratings = rng.integers(1, 6, n)
+    seps = [" ", "|", "\t", "::"]
+    p = str(tmp_path / "u.data")
+    open(p, "w").write("\n".join(f"{u}{seps[i % 4]}{v}{seps[i % 4]}{r}{seps[i % 4]}8812345" for i, (u, v, r)
+                                 in enumerate(zip(users, items, ratings))) + "\n")
+    ref, yref = oracle.load_user_item_rating(p)
+    ds, y = nf.loadUserItemRatingFile(p)
+    same(ds, ref)
+    assert np.array_equal(y, yref) and np.array_equal(y, ratings.astype(np.float64))
+    # minUser / minItem start at 1 (dataset.nim:862-866): ids are taken as 1-based unless a 0 occurs
+    assert ds.nFeatures == (users.max() - 1 + 1) + (items.max() - 1 + 1)
+    csc, _ = nf.loadUserItemRatingFile(p, kind="csc")
+    same(csc, oracle.csr_to_csc(ref))
