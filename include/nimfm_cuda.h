@@ -222,6 +222,18 @@ typedef struct {
 int32_t nimfm_fm_cd_begin(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *Xcsc, const nimfm_cd_cfg *cfg);
 int32_t nimfm_fm_cd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *Xcsc, const nimfm_cd_cfg *cfg,
                           double *viol, double *lossMean, double *regOverN);
+/* PCD (optimizer/pcd.nim:38-200): cd.fit's sweeps with the sparsity regulariser's per-coordinate prox
+ * (L1: l1.nim:22-24; SquaredL12, either orientation: squaredl12.nim:108-114,161-185) and the
+ * invStepSize guard in every sweep (:55,96).  Uses nimfm_fm_cd_begin / _end / _get_ypred.
+ * regOverN is regularization/n without the gamma*reg.eval term (:181-183, printed by the host). */
+typedef struct {
+  int32_t loss;
+  double huberThreshold;
+  double alpha0, alpha, beta, gamma;            /* newPCD (:17-20), NOT yet multiplied by nSamples */
+  int32_t reg;                                  /* NIMFM_REG_L1 | NIMFM_REG_SQUAREDL12 | NIMFM_REG_SQUAREDL12_ROWS */
+} nimfm_pcd_cfg;
+int32_t nimfm_fm_pcd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *Xcsc, const nimfm_pcd_cfg *cfg,
+                           double *viol, double *lossMean, double *regOverN);
 int32_t nimfm_fm_cd_get_ypred(nimfm_ctx *ctx, nimfm_fm *fm, double *yPred);
 int32_t nimfm_fm_cd_end(nimfm_ctx *ctx, nimfm_fm *fm);
 

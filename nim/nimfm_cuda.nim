@@ -49,6 +49,13 @@ type
     huberThreshold*: cdouble
     alpha0*, alpha*, beta*: cdouble
 
+type
+  PcdCfg* {.bycopy.} = object     # nimfm_pcd_cfg
+    loss*: int32
+    huberThreshold*: cdouble
+    alpha0*, alpha*, beta*, gamma*: cdouble
+    reg*: int32                   # 1 = L1, 2 = SquaredL12(transpose=true), 3 = SquaredL12(transpose=false)
+
 {.push importc, dynlib: libName, cdecl.}
 proc nimfm_ctx_create(device: int32, outCtx: ptr Ctx): int32
 proc nimfm_ctx_destroy(ctx: Ctx): int32
@@ -97,6 +104,8 @@ proc nimfm_fm_sgd_end(ctx: Ctx, fm: DeviceFM): int32
 proc nimfm_fm_cd_begin(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr CdCfg): int32
 proc nimfm_fm_cd_epoch(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr CdCfg,
                        viol, lossMean, regOverN: ptr cdouble): int32
+proc nimfm_fm_pcd_epoch(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr PcdCfg,
+                        viol, lossMean, regOverN: ptr cdouble): int32   # pcd.nim:156-172
 proc nimfm_fm_cd_end(ctx: Ctx, fm: DeviceFM): int32
 proc nimfm_ffm_create(ctx: Ctx, nComponents: int32, nFields, nFeatures: int64, fitLinear, fitIntercept: int32,
                       outM: ptr DeviceFFM): int32

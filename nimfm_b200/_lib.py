@@ -47,6 +47,11 @@ class CdCfg(C.Structure):
                 ("beta", c_dbl)]
 
 
+class PcdCfg(C.Structure):
+    _fields_ = [("loss", c_i32), ("huberThreshold", c_dbl), ("alpha0", c_dbl), ("alpha", c_dbl),
+                ("beta", c_dbl), ("gamma", c_dbl), ("reg", c_i32)]
+
+
 # every symbol include/nimfm_cuda.h declares: name -> (restype, argtypes)
 PVP = C.POINTER(C.c_void_p)
 SYMBOLS = {
@@ -92,6 +97,7 @@ SYMBOLS = {
     "nimfm_fm_sgd_end": (c_i32, [VP, VP]),
     "nimfm_fm_cd_begin": (c_i32, [VP, VP, VP, C.POINTER(CdCfg)]),
     "nimfm_fm_cd_epoch": (c_i32, [VP, VP, VP, C.POINTER(CdCfg), PD, PD, PD]),
+    "nimfm_fm_pcd_epoch": (c_i32, [VP, VP, VP, C.POINTER(PcdCfg), PD, PD, PD]),
     "nimfm_fm_cd_get_ypred": (c_i32, [VP, VP, VP]),
     "nimfm_fm_cd_end": (c_i32, [VP, VP]),
     "nimfm_ffm_create": (c_i32, [VP, c_i32, c_i64, c_i64, c_i32, c_i32, PVP]),

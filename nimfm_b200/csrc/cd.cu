@@ -30,6 +30,8 @@ struct CdState {
   double *updAbs = nullptr;              // |update| of every coordinate step of one epoch (fixed-order viol sum)
   int64_t updCap = 0;
   double alpha0 = 0, alpha = 0, beta = 0;  // already multiplied by nSamples (cd.nim:123-125)
+  double *chain = nullptr;                 // PCD chained prox scratch: [a | c | u] x (d + nAug)
+  int64_t chainCap = 0;
 };
 
 // cdScal layout: [0] viol, [1] loss mean, [2] reg/n, [3] sum dloss, [4] |w|^2, [5] |P|^2
@@ -153,7 +155,21 @@ struct CdColArgs {
   int astride, deg;      // deg: 0 = linear term, 2 = epochDeg2, >2 = epoch
   int loss;
   double thr, mu, reg;   // reg: alpha (linear) or beta (already n-scaled)
+  // ---- PCD (optimizer/pcd.nim): per-coordinate prox of the sparsity regulariser
+  int prox;              // 0 = none (CD), NIMFM_REG_L1, NIMFM_REG_SQUAREDL12 (chained), NIMFM_REG_SQUAREDL12_ROWS
+  int guardAll;          // PCD skips invStepSize < 1e-12 in every sweep (pcd.nim:55,96); CD only for degree <= 2
+  int phase;             // 0 = fused; chained prox: 1 = gradient pass only, 2 = refresh pass only
+  double gamma;          // n-scaled (pcd.nim:121)
+  const double *Po;      // SQUAREDL12_ROWS: the order's P[s'][j] block, to form sum_{s' != s} |P[s'][j]|
+  int k, sIdx;
+  int64_t dd;
+  double *chainA, *chainC, *chainU;   // chained prox, per column: (psj-update)/(1+2lam), 2lam/(1+2lam) (<0: skipped), u
 };
+
+__device__ __forceinline__ double cd_soft(double x, double a) {   // softthreshold, regularizer/utils.nim:4-5
+  const double m = fabs(x) - a;
+  return (x > 0 ? 1.0 : (x < 0 ? -1.0 : 0.0)) * (m > 0.0 ? m : 0.0);
+}
 
 template <bool BLOCK_PER_COL>
 static __global__ void cd_col_kernel(const CdColArgs a) {
@@ -177,47 +193,76 @@ static __global__ void cd_col_kernel(const CdColArgs a) {
   const int64_t len = dummy ? a.n : a.indptr[j + 1] - cb;
   const double psj = a.Ps[j];
   const int deg = a.deg;
-  // ---- pass 1: gradient and curvature (update(), cd.nim:36-47 / cd.nim:93-97 / fit_linear.nim:14-17)
-  double upd = 0.0, inv = 0.0;
-  for (int64_t e = tpos; e < len; e += tstep) {
-    const int64_t i = dummy ? e : (int64_t)a.rows[cb + e];
-    const double x = dummy ? 1.0 : a.data[cb + e];
-    double g;
-    if (deg == 0) {
-      g = x;
-    } else if (deg == 2) {
-      g = (a.A[i * a.astride + 1] - psj * x) * x;
-    } else {
-      g = x;                                         // computeDerivative, cd.nim:29-33
-      for (int t = 1; t < deg; t++) g = x * (a.A[i * a.astride + t] - psj * g);
-    }
-    upd += dev_dloss(a.loss, a.thr, a.y[i], a.yPred[i]) * g;
-    inv += g * g;
-  }
-  if (BLOCK_PER_COL) {
-    upd = block_sum(upd, red);
-    __syncthreads();
-    inv = block_sum(inv, red);
-    if (threadIdx.x == 0) {
-      sh[0] = upd;
-      sh[1] = inv;
-    }
-    __syncthreads();
-    upd = sh[0];
-    inv = sh[1];
-  } else {
-    upd = warp_sum(upd);
-    inv = warp_sum(inv);
-  }
-  upd += a.reg * psj;
-  if (deg == 0) inv = a.mu * a.colNormSq[j] + a.reg;   // fit_linear.nim:18
-  else inv = inv * a.mu + a.reg;
   const bool leader = BLOCK_PER_COL ? threadIdx.x == 0 : lane == 0;
-  if (deg <= 2 && inv < 1e-12) {                       // guard exists only in epochDeg2 / fitLinearCD
-    if (leader) a.updAbs[j] = 0.0;
-    return;
+  double u, pnew = 0.0;
+  if (a.phase != 2) {
+    // ---- pass 1: gradient and curvature (update(), cd.nim:36-47 / cd.nim:93-97 / fit_linear.nim:14-17)
+    double upd = 0.0, inv = 0.0;
+    for (int64_t e = tpos; e < len; e += tstep) {
+      const int64_t i = dummy ? e : (int64_t)a.rows[cb + e];
+      const double x = dummy ? 1.0 : a.data[cb + e];
+      double g;
+      if (deg == 0) {
+        g = x;
+      } else if (deg == 2) {
+        g = (a.A[i * a.astride + 1] - psj * x) * x;
+      } else {
+        g = x;                                         // computeDerivative, cd.nim:29-33
+        for (int t = 1; t < deg; t++) g = x * (a.A[i * a.astride + t] - psj * g);
+      }
+      upd += dev_dloss(a.loss, a.thr, a.y[i], a.yPred[i]) * g;
+      inv += g * g;
+    }
+    if (BLOCK_PER_COL) {
+      upd = block_sum(upd, red);
+      __syncthreads();
+      inv = block_sum(inv, red);
+      if (threadIdx.x == 0) {
+        sh[0] = upd;
+        sh[1] = inv;
+      }
+      __syncthreads();
+      upd = sh[0];
+      inv = sh[1];
+    } else {
+      upd = warp_sum(upd);
+      inv = warp_sum(inv);
+    }
+    upd += a.reg * psj;
+    if (deg == 0) inv = a.mu * a.colNormSq[j] + a.reg;   // fit_linear.nim:18
+    else inv = inv * a.mu + a.reg;
+    // the guard exists in epochDeg2 / fitLinearCD, and in both sweeps of PCD (pcd.nim:55,96)
+    const bool skip = (deg <= 2 || a.guardAll) && inv < 1e-12;
+    if (a.phase == 1) {                                  // chained prox: hand (a_j, c_j) to pcd_chain_kernel
+      if (leader) {
+        const double lam = a.gamma / inv, den = 1 + 2 * lam;
+        a.chainA[j] = skip ? 0.0 : (psj - upd / inv) / den;
+        a.chainC[j] = skip ? -1.0 : 2 * lam / den;
+      }
+      return;
+    }
+    if (skip) {
+      if (leader) a.updAbs[j] = 0.0;
+      return;
+    }
+    u = upd / inv;
+    if (deg != 0 && a.prox == NIMFM_REG_L1) {            // l1.nim:22-24
+      pnew = cd_soft(psj - u, a.gamma / inv);
+      u = psj - pnew;
+    } else if (deg != 0 && a.prox == NIMFM_REG_SQUAREDL12_ROWS) {   // squaredl12.nim:108-114, transpose=false
+      double dcache = 0.0;
+      for (int s2 = 0; s2 < a.k; s2++)
+        if (s2 != a.sIdx) dcache += fabs(a.Po[(int64_t)s2 * a.dd + j]);
+      const double lam = a.gamma / inv;
+      pnew = cd_soft((psj - u) / (1 + 2 * lam), 2 * lam * dcache / (1 + 2 * lam));
+      u = psj - pnew;
+    } else {
+      pnew = psj - u;
+    }
+  } else {
+    if (a.chainC[j] < 0.0) return;                       // skipped coordinate: P stays, the chain zeroed updAbs
+    u = a.chainU[j];
   }
-  const double u = upd / inv;
   // ---- pass 2: in-place refresh over the column (cd.nim:67-73 / :104-106 / fit_linear.nim:24-25)
   for (int64_t e = tpos; e < len; e += tstep) {
     const int64_t i = dummy ? e : (int64_t)a.rows[cb + e];
@@ -241,9 +286,56 @@ static __global__ void cd_col_kernel(const CdColArgs a) {
     }
   }
   if (leader) {
-    a.Ps[j] = psj - u;
-    a.updAbs[j] = fabs(u);
+    if (a.phase == 0) {
+      a.Ps[j] = pnew;                                  // CD: psj - u; PCD: exactly the prox result
+      a.updAbs[j] = fabs(u);
+    } else {
+      a.Ps[j] = a.chainA[j];                           // the chain's prox result
+    }
   }
+}
+
+// The chained prox of SquaredL12(transpose=true) (squaredl12.nim:108-114,182-185): coordinate j's
+// threshold depends on cache = sum_j' |P[s][j']| as left by every earlier coordinate of the sweep, so
+// the batch's columns are resolved in order by ONE warp (all lanes carry the same running cache; lane t
+// keeps column base+t's result).  In: a_j, c_j from phase 1.  Out: the new P[s][j] (in chainA), u_j, |u_j|.
+static __global__ void pcd_chain_kernel(const double *Ps, double *chainA, const double *chainC, double *chainU,
+                                        double *updAbs, int64_t j0, int64_t j1, double *cache) {
+  const int lane = threadIdx.x & 31;
+  double c = *cache;
+  for (int64_t base = j0; base < j1; base += 32) {
+    const int64_t j = base + lane;
+    const double aj = j < j1 ? chainA[j] : 0.0, cj = j < j1 ? chainC[j] : -1.0, pj = j < j1 ? Ps[j] : 0.0;
+    double myU = 0.0, myP = pj;
+    const int cnt = (int)min((int64_t)32, j1 - base);
+    for (int t = 0; t < cnt; ++t) {
+      const double at = __shfl_sync(0xffffffffu, aj, t), ct = __shfl_sync(0xffffffffu, cj, t),
+                   pt = __shfl_sync(0xffffffffu, pj, t);
+      if (ct >= 0.0) {
+        const double ap = fabs(pt);
+        const double pn = cd_soft(at, ct * (c - ap));    // dcache = cache - absp[j]
+        c -= ap;                                         // updateCacheCD
+        c += fabs(pn);
+        if (lane == t) { myU = pt - pn; myP = pn; }
+      }
+    }
+    if (j < j1 && cj >= 0.0) {
+      chainA[j] = myP;        // committed to P by the refresh pass, which still needs the old value
+      chainU[j] = myU;
+      updAbs[j] = fabs(myU);
+    } else if (j < j1) {
+      updAbs[j] = 0.0;
+    }
+  }
+  if (lane == 0) *cache = c;
+}
+
+static __global__ void pcd_abs_sum_kernel(const double *v, int64_t n, double *out) {   // computeCacheCD: sum(absp)
+  __shared__ double red[8];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += fabs(v[i]);
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) *out = acc;
 }
 
 static int cd_reduce(nimfm_ctx *ctx, int kind, const double *v0, const double *v1, int64_t n, int loss, double thr,
@@ -259,8 +351,26 @@ static int cd_reduce(nimfm_ctx *ctx, int kind, const double *v0, const double *v
   return NIMFM_OK;
 }
 
+struct PcdProx {   // sparsity regulariser of a PCD sweep (zeros == plain CD)
+  int prox = 0, guardAll = 0;
+  double gamma = 0.0;
+  const double *Po = nullptr;
+  int k = 0, sIdx = 0;
+};
+
+static void cd_launch_cols(nimfm_ctx *ctx, const CdColArgs &a, bool blockPerCol) {
+  const int64_t cols = a.j1 - a.j0;
+  if (blockPerCol) {
+    cd_col_kernel<true><<<(int)cols, 1024, 0, ctx->stream>>>(a);
+  } else {
+    const int64_t threads = cols * 32;
+    cd_col_kernel<false><<<(int)((threads + 127) / 128), 128, 0, ctx->stream>>>(a);
+  }
+  LAUNCHED(ctx);
+}
+
 static int cd_sweep(nimfm_ctx *ctx, CdState *st, const nimfm_dataset *X, nimfm_fm *fm, const nimfm_cd_cfg *cfg,
-                    double *Ps, int deg, double reg, double *updAbs, int64_t nCols) {
+                    double *Ps, int deg, double reg, double *updAbs, int64_t nCols, const PcdProx &px) {
   // nCols == d for the linear sweep (dummy features removed, cd.nim:159), d + nAug otherwise
   CdColArgs a;
   memset(&a, 0, sizeof(a));
@@ -268,27 +378,44 @@ static int cd_sweep(nimfm_ctx *ctx, CdState *st, const nimfm_dataset *X, nimfm_f
   a.yPred = fm->yPred; a.A = fm->Acache; a.Ps = Ps; a.updAbs = updAbs; a.colNormSq = fm->colNormSq;
   a.n = X->n; a.d = X->d; a.astride = fm->degree + 1; a.deg = deg;
   a.loss = cfg->loss; a.thr = cfg->huberThreshold; a.mu = loss_mu(cfg->loss); a.reg = reg;
+  a.prox = deg == 0 ? 0 : px.prox; a.guardAll = px.guardAll; a.gamma = px.gamma;
+  a.Po = px.Po; a.k = px.k; a.sIdx = px.sIdx; a.dd = fm->dd();
+  const bool chained = a.prox == NIMFM_REG_SQUAREDL12;
+  double *cache = fm->cdScal + 8;
+  if (chained) {
+    a.chainA = st->chain; a.chainC = st->chain + a.dd; a.chainU = st->chain + 2 * a.dd;
+    pcd_abs_sum_kernel<<<1, 256, 0, ctx->stream>>>(Ps, nCols, cache);   // computeCacheCD (squaredl12.nim:173-179)
+    LAUNCHED(ctx);
+  }
+  auto run = [&](bool blockPerCol) {
+    if (!chained) {
+      a.phase = 0;
+      cd_launch_cols(ctx, a, blockPerCol);
+      return;
+    }
+    a.phase = 1;
+    cd_launch_cols(ctx, a, blockPerCol);
+    pcd_chain_kernel<<<1, 32, 0, ctx->stream>>>(Ps, a.chainA, a.chainC, a.chainU, updAbs, a.j0, a.j1, cache);
+    LAUNCHED(ctx);
+    a.phase = 2;
+    cd_launch_cols(ctx, a, blockPerCol);
+  };
   const size_t nb = st->batchStart.size() - 1;
   for (size_t b = 0; b < nb; b++) {
     a.j0 = st->batchStart[b];
     a.j1 = st->batchStart[b + 1];
-    const int64_t cols = a.j1 - a.j0;
-    if (st->batchMaxLen[b] > 2048) {
-      cd_col_kernel<true><<<(int)cols, 1024, 0, ctx->stream>>>(a);
-    } else {
-      const int64_t threads = cols * 32;
-      cd_col_kernel<false><<<(int)((threads + 127) / 128), 128, 0, ctx->stream>>>(a);
-    }
-    LAUNCHED(ctx);
+    run(st->batchMaxLen[b] > 2048);
   }
   for (int64_t j = X->d; j < nCols; j++) {   // dummy columns touch every row: one batch each
     a.j0 = j;
     a.j1 = j + 1;
-    cd_col_kernel<true><<<1, 1024, 0, ctx->stream>>>(a);
-    LAUNCHED(ctx);
+    run(true);
   }
   return NIMFM_OK;
 }
+
+static int cd_epoch_impl(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, const nimfm_cd_cfg *cfg, int prox,
+                         double gammaRaw, double *viol, double *lossMean, double *regOverN);
 
 extern "C" {
 
@@ -364,6 +491,30 @@ int32_t nimfm_fm_cd_begin(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, 
 
 int32_t nimfm_fm_cd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, const nimfm_cd_cfg *cfg, double *viol,
                           double *lossMean, double *regOverN) {
+  return cd_epoch_impl(ctx, fm, X, cfg, 0, 0.0, viol, lossMean, regOverN);
+}
+
+// One outer iteration of PCD.fit (pcd.nim:156-172): cd.fit's sweeps with the per-coordinate prox of the
+// sparsity regulariser and the invStepSize guard in every sweep.  regOverN excludes gamma*reg.eval
+// (the host adds it when it prints, :181-183).
+int32_t nimfm_fm_pcd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, const nimfm_pcd_cfg *cfg, double *viol,
+                           double *lossMean, double *regOverN) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  REQUIRE(cfg != nullptr, "NULL argument");
+  REQUIRE(cfg->reg == NIMFM_REG_L1 || cfg->reg == NIMFM_REG_SQUAREDL12 || cfg->reg == NIMFM_REG_SQUAREDL12_ROWS,
+          "PCD supports the L1 and SquaredL12 regularisers");
+  // SquaredL12.initCD raises for degree != 2 (squaredl12.nim:90-93)
+  REQUIRE(!(cfg->reg != NIMFM_REG_L1 && fm && fm->degree != 2), "SquaredL12 supports only degree=2.");
+  nimfm_cd_cfg c;
+  c.loss = cfg->loss; c.huberThreshold = cfg->huberThreshold;
+  c.alpha0 = cfg->alpha0; c.alpha = cfg->alpha; c.beta = cfg->beta;
+  return cd_epoch_impl(ctx, fm, X, &c, cfg->reg, cfg->gamma, viol, lossMean, regOverN);
+}
+
+}  // extern "C"
+
+static int cd_epoch_impl(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, const nimfm_cd_cfg *cfg, int prox,
+                         double gammaRaw, double *viol, double *lossMean, double *regOverN) {
   if (!ctx) return NIMFM_ERR_INVALID;
   REQUIRE(fm && X && cfg, "NULL argument");
   if (!fm->cdReady) return nimfm_fail(ctx, NIMFM_ERR_STATE, "nimfm_fm_cd_begin was not called");
@@ -382,18 +533,31 @@ int32_t nimfm_fm_cd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, 
     cd_intercept_commit_kernel<<<1, 1, 0, ctx->stream>>>(fm->b, st->alpha0, mu, n, fm->cdScal);
     ctx->launches += 2;
   }
+  PcdProx px;
+  px.prox = prox;
+  px.guardAll = prox != 0;
+  px.gamma = gammaRaw * (double)n;                                   // pcd.nim:121
+  px.k = fm->k;
+  if (prox == NIMFM_REG_SQUAREDL12 && st->chainCap < 3 * dd) {
+    cudaFree(st->chain);
+    st->chain = nullptr;
+    CK(cudaMalloc(&st->chain, (size_t)(3 * dd) * 8));
+    st->chainCap = 3 * dd;
+  }
   if (fm->fitLinear)                                                 // fitLinearCD (dummy features removed)
-    if ((rc = cd_sweep(ctx, st, X, fm, cfg, fm->w, 0, st->alpha, st->updAbs + 1, d))) return rc;
+    if ((rc = cd_sweep(ctx, st, X, fm, cfg, fm->w, 0, st->alpha, st->updAbs + 1, d, px))) return rc;
   const nimfm_dataset *R = st->csr;
   for (int o = 0; o < fm->nOrders; o++) {
     const int deg = fm->degree - o;
+    px.Po = fm->Pcm + (int64_t)o * fm->k * dd;
     for (int s = 0; s < fm->k; s++) {
       double *Ps = fm->Pcm + ((int64_t)o * fm->k + s) * dd;
+      px.sIdx = s;
       cd_cache_kernel<<<rowGrid, 256, 0, ctx->stream>>>(R->data, R->indices, R->indptr, n, d, fm->nAug, Ps, deg,
                                                         fm->Acache, fm->degree + 1);
       LAUNCHED(ctx);
       double *upd = st->updAbs + 1 + d + ((int64_t)o * fm->k + s) * dd;
-      if ((rc = cd_sweep(ctx, st, X, fm, cfg, Ps, deg, st->beta, upd, dd))) return rc;
+      if ((rc = cd_sweep(ctx, st, X, fm, cfg, Ps, deg, st->beta, upd, dd, px))) return rc;
     }
   }
   // viol (fixed-order sum of |update|), mean loss, regularization / n (cd.nim:177-184)
@@ -426,6 +590,8 @@ int32_t nimfm_fm_cd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, 
   return NIMFM_OK;
 }
 
+extern "C" {
+
 int32_t nimfm_fm_cd_get_ypred(nimfm_ctx *ctx, nimfm_fm *fm, double *yPred) {
   if (!ctx || !fm || !yPred) return NIMFM_ERR_INVALID;
   if (!fm->cdReady) return nimfm_fail(ctx, NIMFM_ERR_STATE, "nimfm_fm_cd_begin was not called");
@@ -446,6 +612,7 @@ int32_t nimfm_fm_cd_end(nimfm_ctx *ctx, nimfm_fm *fm) {
   if (st) {
     nimfm_dataset_free(ctx, st->csr);
     cudaFree(st->updAbs);
+    cudaFree(st->chain);
     for (size_t i = 0; i < g_cd.size(); i++)
       if (g_cd[i].first == fm) {
         delete g_cd[i].second;

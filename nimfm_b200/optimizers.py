@@ -125,6 +125,74 @@ def newCD(maxIter=100, alpha0=1e-6, alpha=1e-3, beta=1e-3, loss=None, verbose=1,
     return CD(maxIter, alpha0, alpha, beta, loss, verbose, tol)
 
 
+class PCD(_Base):
+    """Proximal coordinate descent (optimizer/pcd.nim:10-200): CD's sweeps with the sparsity
+    regulariser's per-coordinate prox.  reg: L1 or SquaredL12 (default, degree 2 only)."""
+
+    def __init__(self, maxIter=100, alpha0=1e-6, alpha=1e-3, beta=1e-4, gamma=1e-4, loss=None, reg=None,
+                 verbose=1, tol=1e-3):
+        self.maxIter, self.alpha0, self.alpha, self.beta, self.gamma = maxIter, alpha0, alpha, beta, gamma
+        self.loss = loss if loss is not None else Squared()
+        self.reg = reg if reg is not None else SquaredL12()
+        self.verbose, self.tol = verbose, tol
+
+    def fit(self, X, y, sfm, callback=None):
+        """pcd.nim:108-200.  X must be a CSCDataset (ColDataset)."""
+        if not isinstance(X, CSCDataset):
+            raise TypeError("PCD.fit needs a CSCDataset")
+        if isinstance(self.reg, L21):
+            raise TypeError("L21 has no coordinate-wise prox (it is a PBCD regulariser, l21.nim:24-29)")
+        sfm.init(X)
+        y = sfm.checkTarget(y)
+        lib, ctx = _lib.load(), _lib.ctx()
+        X.set_targets(y)
+        n = X.nSamples
+        h = sfm._to_device(X.nFeatures)
+        cdcfg = _lib.CdCfg(self.loss.kind, self.loss.threshold, self.alpha0, self.alpha, self.beta)
+        cfg = _lib.PcdCfg(self.loss.kind, self.loss.threshold, self.alpha0, self.alpha, self.beta, self.gamma,
+                          self.reg.kind)
+        self.history = []
+        self.epoch_seconds = []
+        try:
+            self.reg.initCD(sfm.degree, X.nFeatures + sfm.nAugments, sfm.nComponents)   # :151
+            _lib.check(lib.nimfm_fm_cd_begin(ctx, h, X.handle(), C.byref(cdcfg)))
+            if self.verbose > 0:
+                echoHeader(self.maxIter)
+            converged = False
+            for it in range(self.maxIter):
+                viol, lossMean, reg = C.c_double(), C.c_double(), C.c_double()
+                t0 = time.perf_counter()
+                _lib.check(lib.nimfm_fm_pcd_epoch(ctx, h, X.handle(), C.byref(cfg), C.byref(viol),
+                                                  C.byref(lossMean), C.byref(reg)))
+                self.epoch_seconds.append(time.perf_counter() - t0)
+                regVal = reg.value
+                if self.verbose > 0 or callback is not None:
+                    sfm._from_device(h)
+                if self.verbose > 0:            # :178-185: gamma (n-scaled) * reg.eval(P[order].T), all over n
+                    for order in range(sfm.nOrders):
+                        regVal += self.gamma * self.reg.eval(np.asarray(sfm.P[order]).T, sfm.degree - order)
+                self.history.append((viol.value, lossMean.value, regVal))
+                if self.verbose > 0:
+                    echoInfo(it + 1, self.maxIter, viol.value, lossMean.value, regVal)
+                if callback is not None:
+                    callback(self, sfm)
+                if viol.value < self.tol:
+                    if self.verbose > 0:
+                        print(f"Converged at iteration {it + 1}.")
+                    converged = True
+                    break
+            if not converged and self.verbose > 0:
+                print("Objective did not converge. Increase maxIter.")
+            _lib.check(lib.nimfm_fm_cd_end(ctx, h))
+            sfm._from_device(h)
+        finally:
+            lib.nimfm_fm_free(ctx, h)
+
+
+def newPCD(maxIter=100, alpha0=1e-6, alpha=1e-3, beta=1e-4, gamma=1e-4, loss=None, reg=None, verbose=1, tol=1e-3):
+    return PCD(maxIter, alpha0, alpha, beta, gamma, loss, reg, verbose, tol)
+
+
 # ================================================================ SGD
 class SGD(_Base):
     def __init__(self, maxIter=100, eta0=0.01, alpha0=1e-6, alpha=1e-3, beta=1e-3, loss=None,
@@ -306,6 +374,8 @@ class L1:                                      # regularizer/l1.nim
     def initSGD(self, degree, nFeatures, nComponents):
         pass
 
+    initCD = initSGD                           # l1.nim:44
+
 
 class SquaredL12:                              # regularizer/squaredl12.nim
     def __init__(self, transpose=True):        # newSquaredL12(transpose=true), :84-87
@@ -323,6 +393,8 @@ class SquaredL12:                              # regularizer/squaredl12.nim
     def initSGD(self, degree, nFeatures, nComponents):   # :103-106
         if degree != 2:
             raise ValueError("SquaredL12 supports only degree=2.")
+
+    initCD = initSGD                           # :90-93
 
 
 class L21:                                     # regularizer/l21.nim

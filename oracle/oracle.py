@@ -24,7 +24,7 @@ PI = C.POINTER(C.c_int64)
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("ref_cpu.c", "ref_hogwild.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("ref_cpu.c", "ref_hogwild.c", "ref_pcd.c")]
     if (not force and os.path.exists(_SO)
             and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs)):
         return _SO
@@ -337,6 +337,26 @@ def cd_fit(Xc, y, P, w, intercept, degree, loss_kind="squared", fit_linear=True,
         c_int(int(fit_intercept)), _d(P), _d(w), C.byref(b), c_int(LOSS[loss_kind]), c_dbl(thr),
         c_int(max_iter), c_dbl(alpha0), c_dbl(alpha), c_dbl(beta), c_dbl(tol), _d(viol), _d(ls),
         _d(rg), _d(yp))
+    return dict(P=P, w=w, intercept=b.value, viol=viol[:ni], loss=ls[:ni], reg=rg[:ni], iters=ni,
+                y_pred=yp)
+
+
+def pcd_fit(Xc, y, P, w, intercept, degree, loss_kind="squared", fit_linear=True, fit_intercept=True,
+            max_iter=10, alpha0=1e-6, alpha=1e-3, beta=1e-4, gamma=1e-4, reg="squaredl12", tol=0.0, thr=1.0):
+    """pcd.fit (optimizer/pcd.nim:108-200). Xc: CSC triple; P: model layout; reg in l1 / squaredl12 /
+    squaredl12_rows."""
+    P = f64(P).copy()
+    w = f64(w).copy()
+    nO, k, dd = P.shape
+    b = C.c_double(intercept)
+    viol, ls, rg = np.zeros(max_iter), np.zeros(max_iter), np.zeros(max_iter)
+    yp = np.zeros(Xc.n)
+    ni = lib().ref_pcd_fit(
+        c_i64(Xc.n), c_i64(Xc.d), _d(Xc.data), _i(Xc.indices), _i(Xc.indptr), _d(f64(y)),
+        c_int(degree), c_int(k), c_int(nO), c_int(dd - Xc.d), c_int(int(fit_linear)),
+        c_int(int(fit_intercept)), _d(P), _d(w), C.byref(b), c_int(LOSS[loss_kind]), c_dbl(thr),
+        c_int(max_iter), c_dbl(alpha0), c_dbl(alpha), c_dbl(beta), c_dbl(gamma), c_int(REG[reg]), c_dbl(tol),
+        _d(viol), _d(ls), _d(rg), _d(yp))
     return dict(P=P, w=w, intercept=b.value, viol=viol[:ni], loss=ls[:ni], reg=rg[:ni], iters=ni,
                 y_pred=yp)
 

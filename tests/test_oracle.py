@@ -234,3 +234,30 @@ def test_mbpsgd_with_squaredl12_decreases_and_sparsifies(oracle):
         nz.append(int(np.count_nonzero(r["P"])))
         assert np.all(np.isfinite(r["epoch_loss"]))
     assert nz[0] >= nz[1] >= nz[2] and nz[2] < nz[0]
+
+
+# ---------------------------------------------------------------- PCD
+def test_pcd_oracle_reduces_to_cd_and_minimises_coordinate_model(oracle):
+    """pcd.nim with gamma = 0 is cd.nim (degree 2; for degree > 2 PCD adds the 1e-12 guard, which never
+    fires here); with gamma > 0 the objective incl. gamma*reg decreases monotonically for the squared
+    loss (each coordinate step minimises an upper bound of it)."""
+    X = make_dense(50, 9, 21, density=0.5)
+    csr = CSR.from_dense(X)
+    csc = oracle.csr_to_csc(csr)
+    y = np.random.default_rng(6).standard_normal(50)
+    for degree, fl in ((2, "explicit"), (3, "explicit"), (3, "augment")):
+        P, w, _ = make_fm_params(9, degree, 3, fl, True, 8)
+        kw = dict(max_iter=4, alpha0=1e-6, alpha=1e-3, beta=1e-3)
+        a = oracle.cd_fit(csc, y, P, w, 0.0, degree, "squared", **kw)
+        for reg in ("l1", "squaredl12", "squaredl12_rows"):
+            if reg != "l1" and degree != 2:
+                continue
+            b = oracle.pcd_fit(csc, y, P, w, 0.0, degree, "squared", gamma=0.0, reg=reg, **kw)
+            np.testing.assert_allclose(b["P"], a["P"], rtol=1e-12, atol=1e-15)
+            np.testing.assert_allclose(b["viol"], a["viol"], rtol=1e-12)
+    P, w, _ = make_fm_params(9, 2, 3, "explicit", True, 8)
+    for reg in ("l1", "squaredl12", "squaredl12_rows"):
+        r = oracle.pcd_fit(csc, y, P, w, 0.0, 2, "squared", max_iter=8, gamma=5e-2, reg=reg, beta=1e-3)
+        obj = r["loss"] + r["reg"]
+        assert np.all(np.diff(obj) <= 1e-12), (reg, obj)
+        assert np.count_nonzero(r["P"] == 0.0) > 0
