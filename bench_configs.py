@@ -147,7 +147,8 @@ def main():
         t0 = time.perf_counter()
         yhat = fm.decisionFunction(ds)
         dt_pred = time.perf_counter() - t0
-        opt = nf.newAdaGrad(maxIter=1, eta0=0.1, eps=1e-10, loss=nf.Logistic(), verbose=0, tol=0.0, shuffle=False,
+        # eta0 small: the synchronous variant's first step scales like eta0*sqrt(minibatch) (sums, not means)
+        opt = nf.newAdaGrad(maxIter=1, eta0=1e-4, eps=1e-10, loss=nf.Logistic(), verbose=0, tol=0.0, shuffle=False,
                             miniBatchSize=1 << 20)
         t0 = time.perf_counter()
         opt.fit(ds, y, fm)
@@ -184,7 +185,7 @@ def main():
         lib.nimfm_ffm_free(ctx, h)
         # the config's solver: AdaGrad with synchronous minibatches (2 epochs; the second has the refresh pass)
         mbs = min(1 << 16, n)
-        opt = nf.newAdaGrad(maxIter=2, eta0=0.1, eps=1e-10, loss=nf.Logistic(), verbose=0, tol=0.0, shuffle=False,
+        opt = nf.newAdaGrad(maxIter=2, eta0=1e-3, eps=1e-10, loss=nf.Logistic(), verbose=0, tol=0.0, shuffle=False,
                             miniBatchSize=mbs)
         t0 = time.perf_counter()
         opt.fit(ds, y, m)

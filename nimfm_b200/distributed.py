@@ -33,8 +33,22 @@ def nccl_unique_id():
     return bytes(uid)
 
 
+_state = {"rank": 0, "world": 1}
+
+
+def rank():
+    return _state["rank"]
+
+
+def world():
+    return _state["world"]
+
+
 def init_comm(rank, world):
-    """Create the library-owned NCCL communicator for this process' context."""
+    """Create the library-owned NCCL communicator for this process' context.  After this call the
+    solvers' fit() treat X as THIS rank's row shard, miniBatchSize as the GLOBAL size (each rank
+    contributes local_batch(miniBatchSize, rank, world) rows per step) and all-reduce inside the library."""
+    _state["rank"], _state["world"] = int(rank), int(world)
     if world == 1:
         _lib.check(_lib.load().nimfm_comm_init(_lib.ctx(), 0, 1, None))
         return

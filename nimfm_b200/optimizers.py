@@ -18,6 +18,7 @@ import time
 import numpy as np
 
 from . import _lib
+from . import distributed as _dist
 from .dataset import CSCDataset, CSRDataset, CSRFieldDataset
 from .loss import Squared
 from .model import FactorizationMachine, FieldAwareFactorizationMachine
@@ -246,7 +247,7 @@ class SGD(_Base):
                                  C.byref(viol), C.byref(lossSum)))
                 self.epoch_seconds.append(time.perf_counter() - t0)
                 self.it = it.value
-                runningLoss = lossSum.value / n
+                runningLoss = lossSum.value / (n * world)      # the loss sum is all-reduced; shards are even
                 self.history.append((viol.value, runningLoss))
                 if callback is not None:
                     # finalize + transpose back before the user sees the model (sgd.nim:310-316)
@@ -298,8 +299,14 @@ class AdaGrad(_Base):
                                    lib.nimfm_ffm_adagrad_finalize, lib.nimfm_ffm_free) if is_ffm else
                                   (lib.nimfm_fm_adagrad_init, lib.nimfm_fm_adagrad_epoch,
                                    lib.nimfm_fm_adagrad_finalize, lib.nimfm_fm_free))
+        # data parallel (distributed.init_comm): X is this rank's shard and miniBatchSize the GLOBAL
+        # synchronous minibatch; the library all-reduces the per-minibatch deltas
+        world = _dist.world()
+        local = _dist.local_batch(self.miniBatchSize, _dist.rank(), world)
+        if local < 1:
+            raise ValueError("miniBatchSize is smaller than the number of ranks")
         cfg = _lib.AdagradCfg(self.loss.kind, self.loss.threshold, self.eta0, self.alpha0, self.alpha,
-                              self.beta, self.eps, self.miniBatchSize)
+                              self.beta, self.eps, local)
         if not fm.warmStart:                   # AdaGrad.init, adagrad.nim:47-62
             self.it = 1
         rng = self._rng(fm)
@@ -332,7 +339,7 @@ class AdaGrad(_Base):
                                  C.byref(viol), C.byref(lossSum)))
                 self.epoch_seconds.append(time.perf_counter() - t0)
                 self.it = it.value
-                runningLoss = lossSum.value / n
+                runningLoss = lossSum.value / (n * world)      # the loss sum is all-reduced; shards are even
                 self.history.append((viol.value, runningLoss))
                 if callback is not None:
                     _lib.check(fin(ctx, h, C.byref(cfg), self.it))
@@ -451,6 +458,14 @@ class MBPSGD(_Base):
         if not sfm.warmStart:
             self.it = 1                        # :151-152
         mb, inner = self.resolve_sizes(X)
+        # data parallel (distributed.init_comm): X is this rank's shard, mb the GLOBAL minibatch; every
+        # rank feeds its share of each minibatch and the library all-reduces grad P / w / b / loss
+        local = _dist.local_batch(mb, _dist.rank(), _dist.world())
+        if _dist.world() > 1:
+            if local < 1:
+                raise ValueError("miniBatchSize is smaller than the number of ranks")
+            if self.maxIterInner <= 0:
+                inner = max((n - 1) // local + 1, 1)
         # self.reg.initSGD(degree, nFeatures+nAugments, nComponents) (:172): SquaredL12 -- the default --
         # raises for degree != 2 whatever gamma is (squaredl12.nim:103-106)
         self.reg.initSGD(sfm.degree, X.nFeatures + sfm.nAugments, sfm.nComponents)
@@ -474,7 +489,7 @@ class MBPSGD(_Base):
                 sample = None
                 if self.shuffle:
                     # the cursor + reshuffle-at-wrap logic of epoch() (:102-111), evaluated on the host
-                    total = mb * inner
+                    total = local * inner
                     sample = np.empty(total, dtype=np.int64)
                     filled = 0
                     while filled < total:
@@ -487,7 +502,7 @@ class MBPSGD(_Base):
                             rng.shuffle(indices)
                 itc, iic, rl = C.c_int64(self.it), C.c_int64(ii), C.c_double()
                 t0 = time.perf_counter()
-                _lib.check(lib.nimfm_fm_mbpsgd_epoch(ctx, h, X.handle(), C.byref(cfg), mb, C.byref(itc),
+                _lib.check(lib.nimfm_fm_mbpsgd_epoch(ctx, h, X.handle(), C.byref(cfg), local, C.byref(itc),
                                                      C.byref(iic), _lib.ptr(sample), C.byref(rl)))
                 self.epoch_seconds.append(time.perf_counter() - t0)
                 self.it = itc.value
