@@ -153,7 +153,21 @@ def main():
         t0 = time.perf_counter()
         opt.fit(ds, y, fm)
         dt = time.perf_counter() - t0
-        print(json.dumps({"config": "C4b", "what": f"HOFM degree 3 rank 32, n={n}: decisionFunction (host result) "
+        cpu = {}
+        if args.cpu:
+            # the reference's multithreaded AdaGrad: Hogwild epochs (adagrad_multi.nim:15-101), T = 2*cores
+            # (sgd_multi.nim:13-18) and T = cores, on a row sample of the same data (racy by design: timed only)
+            csr = CSR(data, idx, ptr, n, bench.D_FEATURES)
+            nn = min(n, 200_000)
+            cores = os.cpu_count() or 1
+            for T in sorted({cores, min(2 * cores, 256)}):
+                Pf = orc.to_feature_major(P)
+                t0 = time.perf_counter()
+                orc.hogwild_adagrad_epoch(csr, y, Pf, w.copy(), b, 3, T, loss_kind="logistic", n_rows=nn)
+                cpu[f"hogwild_adagrad_samples_per_s_T{T}"] = nn / (time.perf_counter() - t0)
+            cpu["cpu_kind"] = (f"oracle port of adagrad_multi.nim (Hogwild, racy), first {nn} rows, host cores={cores}; "
+                               "Nim toolchain unavailable")
+        print(json.dumps({"config": "C4b", **cpu, "what": f"HOFM degree 3 rank 32, n={n}: decisionFunction (host result) "
                           "and one AdaGrad epoch with 1Mi-row synchronous minibatches",
                           "decision_function_samples_per_s": n / dt_pred,
                           "adagrad_samples_per_s": n / float(np.min(opt.epoch_seconds)), "adagrad_fit_wall_s": dt,
@@ -202,6 +216,15 @@ def main():
             orc.ffm_loss_grad(csr, y, m.P, m.w, 0.0, "logistic", row_end=nn, mini_batch_size=nn)
             line["cpu_samples_per_s"] = nn / (time.perf_counter() - t0)
             line["cpu_kind"] = "oracle port of sgd_ffm.predictWithGrad + scatter, 1 thread"
+            # the config's solver on the CPU: Hogwild FFM AdaGrad (adagrad_ffm_multi.nim:16-104), T = 2*cores
+            cores = os.cpu_count() or 1
+            T = min(2 * cores, 256)
+            nh = min(n, 20_000)
+            Pf = np.ascontiguousarray(m.P)
+            t0 = time.perf_counter()
+            orc.hogwild_adagrad_epoch(csr, y, Pf, m.w.copy(), 0.0, 2, T, is_ffm=True, loss_kind="logistic", n_rows=nh)
+            line[f"cpu_hogwild_adagrad_samples_per_s_T{T}"] = nh / (time.perf_counter() - t0)
+            line["cpu_hogwild_kind"] = f"oracle port of adagrad_ffm_multi.nim (Hogwild, racy), first {nh} rows, host cores={cores}"
         print(json.dumps(line), flush=True)
 
 
