@@ -85,8 +85,7 @@ static __global__ void adagrad_count_kernel(const int32_t *indices, const int64_
 }
 
 // The two per-minibatch AdaGrad passes below visit ONLY the features the batch touches (cnt[j] != 0):
-// a warp reads 32 counts at a time, then walks the touched ones with all lanes on the feature's
-// SB8 contiguous elements.  Untouched features carry zero deltas by construction, so skipping them is
+// (see the block-level scheme below); every touched feature's SB8 contiguous elements are handled by one warp.  Untouched features carry zero deltas by construction, so skipping them is
 // exact; for FFM (nFields*k = 312 elements per feature, P = 2.5 GB) a dense pass per minibatch cost
 // more than the row kernel itself.
 //
@@ -95,35 +94,69 @@ static __global__ void adagrad_count_kernel(const int32_t *indices, const int64_
 // same |P_old - theta| once per row containing j, and 0 for every later row of the batch -- with the
 // snapshot semantics of the synchronous minibatch every incidence sees the pre-batch P).
 // partials: [gridDim][4], column 3 = viol.
+// Both passes: a block reads 256 counts (coalesced), lists its touched features in shared memory in index
+// order, and its warps take them round-robin; a feature's SB8 elements are handled 4 x 32 at a time with
+// all loads of a batch issued before the first is used (ncu on the first form -- 32 features per warp,
+// one dependent round trip per 32 elements -- showed 12 ms per call at 4 % DRAM: pure load latency).
+#define ADA_UNROLL 4
 static __global__ void adagrad_refresh_kernel(double *P, const double *gsP, const double *gnP, int64_t dd, int SB8,
                                               const double *cnt, double *w, const double *gsw, const double *gnw,
                                               int64_t d, int fitLinear, double eta0, double tIt, double alpha,
                                               double beta, double *partials) {
   __shared__ double red[8];
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t nWarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  __shared__ int sList[256];
+  __shared__ double sCnt[256];
+  __shared__ int sN;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const double tmpP = eta0 * tIt * beta;
   const double denW = tIt * eta0 * alpha;
   double viol = 0.0;
-  for (int64_t base = warp * 32; base < dd; base += nWarps * 32) {
-    const int64_t jm = base + lane;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < dd; base += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t jm = base + threadIdx.x;
     const double cm = jm < dd ? cnt[jm] : 0.0;
     if (fitLinear && cm != 0.0 && jm < d) {
       const double wn = -eta0 * gsw[jm] / (denW + sqrt(gnw[jm]));   // fitLinearAdaGrad, fit_linear.nim:50-57
       viol += cm * fabs(w[jm] - wn);
       w[jm] = wn;
     }
-    unsigned mask = __ballot_sync(0xffffffffu, cm != 0.0);
-    while (mask) {
-      const int src = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const double c = __shfl_sync(0xffffffffu, cm, src);
-      const int64_t e0 = (base + src) * SB8;
-      for (int e = lane; e < SB8; e += 32) {
-        const double pn = -(eta0 * gsP[e0 + e]) / (tmpP + sqrt(gnP[e0 + e]));
-        viol += c * fabs(P[e0 + e] - pn);
-        P[e0 + e] = pn;
+    __syncthreads();
+    if (threadIdx.x == 0) sN = 0;
+    __syncthreads();
+    // ordered compaction of this block's touched features (deterministic: warp order, then lane order)
+    const unsigned mask = __ballot_sync(0xffffffffu, cm != 0.0);
+    for (int ww = 0; ww < nw; ++ww) {
+      if (wid == ww && cm != 0.0) {
+        const int pos = sN + __popc(mask & ((1u << lane) - 1));
+        sList[pos] = threadIdx.x;
+        sCnt[pos] = cm;
+      }
+      __syncthreads();
+      if (threadIdx.x == ww * 32) sN += __popc(mask);
+      __syncthreads();
+    }
+    const int nT = sN;
+    for (int t = wid; t < nT; t += nw) {
+      const double c = sCnt[t];
+      const int64_t e0 = (base + sList[t]) * SB8;
+      for (int eb = 0; eb < SB8; eb += 32 * ADA_UNROLL) {
+        double g[ADA_UNROLL], nn[ADA_UNROLL], p[ADA_UNROLL];
+#pragma unroll
+        for (int i = 0; i < ADA_UNROLL; ++i) {
+          const int e = eb + lane + 32 * i;
+          const bool ok = e < SB8;
+          g[i] = ok ? gsP[e0 + e] : 0.0;
+          nn[i] = ok ? gnP[e0 + e] : 1.0;
+          p[i] = ok ? P[e0 + e] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < ADA_UNROLL; ++i) {
+          const int e = eb + lane + 32 * i;
+          if (e < SB8) {
+            const double pn = -(eta0 * g[i]) / (tmpP + sqrt(nn[i]));
+            viol += c * fabs(p[i] - pn);
+            P[e0 + e] = pn;
+          }
+        }
       }
     }
   }
@@ -141,12 +174,12 @@ static __global__ void adagrad_refresh_kernel(double *P, const double *gsP, cons
 static __global__ void adagrad_apply_kernel(double *gsP, double *gnP, double *dGsP, double *dGnP, int64_t nP,
                                             double *gsw, double *gnw, double *dGsw, double *dGnw, int64_t d,
                                             int fitLinear, double *cnt, int64_t dd) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t nWarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  __shared__ int sList[256];
+  __shared__ int sN;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int SB8 = (int)(nP / dd);
-  for (int64_t base = warp * 32; base < dd; base += nWarps * 32) {
-    const int64_t jm = base + lane;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < dd; base += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t jm = base + threadIdx.x;
     const double cm = jm < dd ? cnt[jm] : 0.0;
     if (cm != 0.0) {
       if (jm < d) {
@@ -159,16 +192,35 @@ static __global__ void adagrad_apply_kernel(double *gsP, double *gnP, double *dG
       }
       cnt[jm] = 0.0;
     }
-    unsigned mask = __ballot_sync(0xffffffffu, cm != 0.0);
-    while (mask) {
-      const int src = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const int64_t e0 = (base + src) * SB8;
-      for (int e = lane; e < SB8; e += 32) {
-        gsP[e0 + e] += dGsP[e0 + e];
-        gnP[e0 + e] += dGnP[e0 + e];
-        dGsP[e0 + e] = 0.0;
-        dGnP[e0 + e] = 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) sN = 0;
+    __syncthreads();
+    if (cm != 0.0) sList[atomicAdd(&sN, 1)] = threadIdx.x;   // order is irrelevant here: features are independent
+    __syncthreads();
+    const int nT = sN;
+    for (int t = wid; t < nT; t += nw) {
+      const int64_t e0 = (base + sList[t]) * SB8;
+      for (int eb = 0; eb < SB8; eb += 32 * ADA_UNROLL) {
+        double gs[ADA_UNROLL], gn[ADA_UNROLL], ds[ADA_UNROLL], dn[ADA_UNROLL];
+#pragma unroll
+        for (int i = 0; i < ADA_UNROLL; ++i) {
+          const int e = eb + lane + 32 * i;
+          const bool ok = e < SB8;
+          gs[i] = ok ? gsP[e0 + e] : 0.0;
+          gn[i] = ok ? gnP[e0 + e] : 0.0;
+          ds[i] = ok ? dGsP[e0 + e] : 0.0;
+          dn[i] = ok ? dGnP[e0 + e] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < ADA_UNROLL; ++i) {
+          const int e = eb + lane + 32 * i;
+          if (e < SB8) {
+            gsP[e0 + e] = gs[i] + ds[i];
+            gnP[e0 + e] = gn[i] + dn[i];
+            dGsP[e0 + e] = 0.0;
+            dGnP[e0 + e] = 0.0;
+          }
+        }
       }
     }
   }

@@ -224,18 +224,34 @@ struct FfmPlan {
 };
 
 // pair-streaming kernel when k is 4/8/16/32, else nullptr
-template <int KT>
+template <int KT, bool TABLE>
 static FfmKernel ffm_pairs_mode(int mode) {
-  return mode == FFM_PREDICT ? ffm_pairs_kernel<FFM_PAIRS_PREDICT, KT, FfmArgs>
-         : mode == FFM_GRAD  ? ffm_pairs_kernel<FFM_PAIRS_GRAD, KT, FfmArgs>
-                             : ffm_pairs_kernel<FFM_PAIRS_ADAGRAD, KT, FfmArgs>;
+  return mode == FFM_PREDICT ? ffm_pairs_kernel<FFM_PAIRS_PREDICT, KT, TABLE, FfmArgs>
+         : mode == FFM_GRAD  ? ffm_pairs_kernel<FFM_PAIRS_GRAD, KT, TABLE, FfmArgs>
+                             : ffm_pairs_kernel<FFM_PAIRS_ADAGRAD, KT, TABLE, FfmArgs>;
 }
-static FfmKernel ffm_pairs_pick(int k, int mode) {
+static FfmKernel ffm_pairs_pick(int k, int mode, bool table) {
   switch (k) {
-    case 4: return ffm_pairs_mode<4>(mode);
-    case 8: return ffm_pairs_mode<8>(mode);
-    case 16: return ffm_pairs_mode<16>(mode);
-    case 32: return ffm_pairs_mode<32>(mode);
+    case 4: return table ? ffm_pairs_mode<4, true>(mode) : ffm_pairs_mode<4, false>(mode);
+    case 8: return table ? ffm_pairs_mode<8, true>(mode) : ffm_pairs_mode<8, false>(mode);
+    case 16: return table ? ffm_pairs_mode<16, true>(mode) : ffm_pairs_mode<16, false>(mode);
+    case 32: return table ? ffm_pairs_mode<32, true>(mode) : ffm_pairs_mode<32, false>(mode);
+    default: return nullptr;
+  }
+}
+
+template <int KT>
+static FfmKernel ffm_pairs_block_mode(int mode) {
+  return mode == FFM_PREDICT ? ffm_pairs_block_kernel<FFM_PAIRS_PREDICT, KT, FfmArgs>
+         : mode == FFM_GRAD  ? ffm_pairs_block_kernel<FFM_PAIRS_GRAD, KT, FfmArgs>
+                             : ffm_pairs_block_kernel<FFM_PAIRS_ADAGRAD, KT, FfmArgs>;
+}
+static FfmKernel ffm_pairs_block_pick(int k, int mode) {
+  switch (k) {
+    case 4: return ffm_pairs_block_mode<4>(mode);
+    case 8: return ffm_pairs_block_mode<8>(mode);
+    case 16: return ffm_pairs_block_mode<16>(mode);
+    case 32: return ffm_pairs_block_mode<32>(mode);
     default: return nullptr;
   }
 }
@@ -264,14 +280,18 @@ static int ffm_has_field_dups(nimfm_ctx *ctx, const nimfm_dataset *X, bool *dups
 static int ffm_plan(nimfm_ctx *ctx, const nimfm_ffm *m, const nimfm_dataset *X, int64_t nRows, FfmKernel kern,
                     FfmPlan *pl);
 
-// Every mode chooses the pair kernel when one exists for k (NIMFM_FFM_KERNEL=block forces the
-// block-per-row kernel); FFM_ADAGRAD additionally needs a dataset without repeated fields in a row.
+// Every mode chooses a pair kernel when one exists for k (NIMFM_FFM_KERNEL=block forces the staged
+// block-per-row kernel ffm_rows_kernel); FFM_ADAGRAD additionally needs a dataset without repeated
+// fields in a row.
 static int ffm_plan_mode(nimfm_ctx *ctx, const nimfm_ffm *m, const nimfm_dataset *X, int64_t nRows, int mode,
                          FfmPlan *pl) {
   const char *env = getenv("NIMFM_FFM_KERNEL");
   const bool forceBlock = env && !strcmp(env, "block");
   const int CH = (int)std::max<int64_t>(X->maxSegNnz, 1);
-  FfmKernel pk = (forceBlock || CH > 1024) ? nullptr : ffm_pairs_pick(m->k, mode);
+  const bool table = CH <= FFM_PAIRS_TABLE_MAXZ;
+  // the pair kernel addresses P through 32-bit (j*nFields + f): needs d*nFields < 2^31
+  FfmKernel pk = (forceBlock || CH > 1024 || m->d * m->nFields >= (int64_t)2147483647)
+                     ? nullptr : ffm_pairs_pick(m->k, mode, table);
   if (pk && mode == FFM_ADAGRAD) {
     // the pair kernel squares per-pair contributions, which equals the per-sample gradient entry
     // (adagrad.nim:119-124) only when no row has two nonzeros of one field
@@ -280,9 +300,30 @@ static int ffm_plan_mode(nimfm_ctx *ctx, const nimfm_ffm *m, const nimfm_dataset
     if (rc) return rc;
     if (dups) pk = nullptr;
   }
+  // rows up to FFM_PAIRS_TABLE_MAXZ nonzeros: the block-per-row form of the pair loop (grad 15.1 -> 22.7 M
+  // rows/s on C5); NIMFM_FFM_KERNEL=pairwarp keeps the warp-per-row form for A/B
+  const bool wantPairWarp = env && !strcmp(env, "pairwarp");
+  if (pk && table && !wantPairWarp) {
+    FfmKernel bk = ffm_pairs_block_pick(m->k, mode);
+    const int block = 256;
+    const size_t smem = ffm_pairs_warp_smem(CH, true);
+    CK(cudaFuncSetAttribute(bk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bk, block, smem));
+    if (occ < 1) return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "FFM pair-block kernel does not fit on an SM");
+    int64_t grid = std::min<int64_t>(nRows, (int64_t)occ * ctx->numSMs);
+    if (grid < 1) grid = 1;
+    pl->CH = CH;
+    pl->grid = (int)grid;
+    pl->smem = smem;
+    pl->kern = bk;
+    pl->block = block;
+    pl->partialRows = grid;
+    return NIMFM_OK;
+  }
   if (pk) {
     const int block = 256, wpb = block / 32;
-    const size_t smem = (size_t)wpb * CH * sizeof(FfmRec);
+    const size_t smem = (size_t)wpb * ffm_pairs_warp_smem(CH, table);
     CK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pk, block, smem));

@@ -23,11 +23,12 @@ struct FfmArgs;   // defined in ffm.cu
 
 struct __align__(16) FfmRec {
   double x;
-  int32_t j;
+  int32_t jb;   // j * nFields: (jb + f) * k is the element offset of P[j][f][0]  (d * nFields < 2^31 is required)
   int32_t f;
 };
 
 enum { FFM_PAIRS_PREDICT = 0, FFM_PAIRS_GRAD = 1, FFM_PAIRS_ADAGRAD = 2 };
+#define FFM_PAIRS_TABLE_MAXZ 64   // rows up to this length enumerate their pairs through a shared-memory table
 
 // advance the pair cursor (u, v), u < v < z, by `step` positions of the row-major pair order
 __device__ __forceinline__ void ffm_pair_advance(int &u, int &v, int step, int z) {
@@ -38,7 +39,16 @@ __device__ __forceinline__ void ffm_pair_advance(int &u, int &v, int step, int z
   }
 }
 
-template <int MODE, int KT, class Args>
+// bytes of shared memory one warp needs: the row's records + (TABLE) the pair table of the longest row
+__host__ __device__ inline size_t ffm_pairs_warp_smem(int CH, bool table) {
+  size_t b = (size_t)CH * sizeof(FfmRec) + (table ? (size_t)CH * (CH - 1) / 2 * sizeof(uint16_t) : 0);
+  return (b + 15) & ~(size_t)15;
+}
+
+// TABLE: the (u, v) of pair p comes from a per-warp table (u | v << 8) that depends only on the row
+// length z and is rebuilt when z changes (never, for one-feature-per-field data); ncu on the cursor
+// form (r01i): 26 K warp instructions per 39-nonzero row, most of them cursor and address arithmetic.
+template <int MODE, int KT, bool TABLE, class Args>
 __global__ void __launch_bounds__(256, 2) ffm_pairs_kernel(const Args a) {
   constexpr int SLOTS = 32 / KT;
   constexpr int PB = 8;   // pairs in flight per slot (2*PB gathers per lane)
@@ -48,11 +58,14 @@ __global__ void __launch_bounds__(256, 2) ffm_pairs_kernel(const Args a) {
   const int s = lane & (KT - 1);
   const int slot = lane / KT;
   const int CH = a.CH;
-  FfmRec *rec = reinterpret_cast<FfmRec *>(smem_raw) + (size_t)warpInBlock * CH;
+  unsigned char *wbase = smem_raw + (size_t)warpInBlock * ffm_pairs_warp_smem(CH, TABLE);
+  FfmRec *rec = reinterpret_cast<FfmRec *>(wbase);
+  uint16_t *tab = reinterpret_cast<uint16_t *>(wbase + (size_t)CH * sizeof(FfmRec));
+  int zTab = -1;
   const int warpsPerBlock = blockDim.x >> 5;
   const int64_t warpGlobal = (int64_t)blockIdx.x * warpsPerBlock + warpInBlock;
   const int64_t nWarps = (int64_t)gridDim.x * warpsPerBlock;
-  const int64_t SB8 = (int64_t)a.nFields * KT;
+  const int nF = a.nFields;
   double bias = a.b[0];
   if (MODE == FFM_PAIRS_ADAGRAD && !a.first && a.fitIntercept)   // adagrad.nim:101-105 (batch snapshot)
     bias = -a.eta0 * a.adaScal[0] / (sqrt(a.adaScal[1]) + a.eta0 * a.tIt * a.alpha0);
@@ -67,20 +80,30 @@ __global__ void __launch_bounds__(256, 2) ffm_pairs_kernel(const Args a) {
     double lin = 0.0;
     for (int u = lane; u < z; u += 32) {
       FfmRec m;
-      m.j = a.indices[rb + u];
+      const int32_t j = a.indices[rb + u];
+      m.jb = j * nF;
       m.f = a.fields[rb + u];
       m.x = a.data[rb + u];
       rec[u] = m;
-      lin += a.w[m.j] * m.x;
+      lin += a.w[j] * m.x;
+    }
+    const int nPairs = z * (z - 1) / 2;
+    if (TABLE && z != zTab) {
+      int u = 0, v = 1;
+      ffm_pair_advance(u, v, lane, z);
+      for (int p = lane; p < nPairs; p += 32) {
+        tab[p] = (uint16_t)(u | (v << 8));
+        ffm_pair_advance(u, v, 32, z);
+      }
+      zTab = z;
     }
     __syncwarp();
-    const int nPairs = z * (z - 1) / 2;
 
     // ---- forward: running dot over this slot's pairs
     double acc = 0.0;
     {
       int u = 0, v = 1;
-      ffm_pair_advance(u, v, slot, z);
+      if (!TABLE) ffm_pair_advance(u, v, slot, z);
       for (int p = slot; p < nPairs; p += SLOTS * PB) {
         double a1[PB], a2[PB], xx[PB];
 #pragma unroll
@@ -88,14 +111,19 @@ __global__ void __launch_bounds__(256, 2) ffm_pairs_kernel(const Args a) {
           const bool ok = p + i * SLOTS < nPairs;
           a1[i] = 0.0; a2[i] = 0.0; xx[i] = 0.0;
           if (ok) {
+            if (TABLE) {
+              const unsigned uv = tab[p + i * SLOTS];
+              u = uv & 0xff;
+              v = uv >> 8;
+            }
             const FfmRec mu = rec[u], mv = rec[v];
-            if (mv.j != mu.j) {                                                  // the reference pairs j1 < j2 only
-              a1[i] = __ldg(Pg + (int64_t)mu.j * SB8 + mv.f * KT);               // P[j_u][f_v][s]
-              a2[i] = __ldg(Pg + (int64_t)mv.j * SB8 + mu.f * KT);               // P[j_v][f_u][s]
+            if (mv.jb != mu.jb) {                                               // the reference pairs j1 < j2 only
+              a1[i] = __ldg(Pg + (int64_t)(mu.jb + mv.f) * KT);                 // P[j_u][f_v][s]
+              a2[i] = __ldg(Pg + (int64_t)(mv.jb + mu.f) * KT);                 // P[j_v][f_u][s]
               xx[i] = mu.x * mv.x;
             }
           }
-          ffm_pair_advance(u, v, SLOTS, z);
+          if (!TABLE) ffm_pair_advance(u, v, SLOTS, z);
         }
 #pragma unroll
         for (int i = 0; i < PB; ++i) acc += xx[i] * (a1[i] * a2[i]);
@@ -118,35 +146,40 @@ __global__ void __launch_bounds__(256, 2) ffm_pairs_kernel(const Args a) {
     double *__restrict__ gNg = (MODE == FFM_PAIRS_ADAGRAD) ? a.dGnP + s : nullptr;
     {
       int u = 0, v = 1;
-      ffm_pair_advance(u, v, slot, z);
+      if (!TABLE) ffm_pair_advance(u, v, slot, z);
       for (int p = slot; p < nPairs; p += SLOTS * PB) {
         double a1[PB], a2[PB], cx[PB];
-        int64_t e1[PB], e2[PB];
+        int32_t e1[PB], e2[PB];   // (j*nFields + f): element offset / KT
 #pragma unroll
         for (int i = 0; i < PB; ++i) {
           const bool ok = p + i * SLOTS < nPairs;
           e1[i] = -1; e2[i] = 0; a1[i] = 0.0; a2[i] = 0.0; cx[i] = 0.0;
           if (ok) {
+            if (TABLE) {
+              const unsigned uv = tab[p + i * SLOTS];
+              u = uv & 0xff;
+              v = uv >> 8;
+            }
             const FfmRec mu = rec[u], mv = rec[v];
-            if (mv.j != mu.j) {
-              e1[i] = (int64_t)mu.j * SB8 + mv.f * KT;       // entry (j_u, f_v)
-              e2[i] = (int64_t)mv.j * SB8 + mu.f * KT;       // entry (j_v, f_u)
-              a1[i] = __ldg(Pg + e1[i]);
-              a2[i] = __ldg(Pg + e2[i]);
+            if (mv.jb != mu.jb) {
+              e1[i] = mu.jb + mv.f;                        // entry (j_u, f_v)
+              e2[i] = mv.jb + mu.f;                        // entry (j_v, f_u)
+              a1[i] = __ldg(Pg + (int64_t)e1[i] * KT);
+              a2[i] = __ldg(Pg + (int64_t)e2[i] * KT);
               cx[i] = coef * (mu.x * mv.x);
             }
           }
-          ffm_pair_advance(u, v, SLOTS, z);
+          if (!TABLE) ffm_pair_advance(u, v, SLOTS, z);
         }
 #pragma unroll
         for (int i = 0; i < PB; ++i) {
           if (e1[i] >= 0) {
             const double g1 = cx[i] * a2[i], g2 = cx[i] * a1[i];
-            atomicAdd(gPg + e1[i], g1);
-            atomicAdd(gPg + e2[i], g2);
+            atomicAdd(gPg + (int64_t)e1[i] * KT, g1);
+            atomicAdd(gPg + (int64_t)e2[i] * KT, g2);
             if (MODE == FFM_PAIRS_ADAGRAD) {
-              atomicAdd(gNg + e1[i], g1 * g1);
-              atomicAdd(gNg + e2[i], g2 * g2);
+              atomicAdd(gNg + (int64_t)e1[i] * KT, g1 * g1);
+              atomicAdd(gNg + (int64_t)e2[i] * KT, g2 * g2);
             }
           }
         }
@@ -155,8 +188,9 @@ __global__ void __launch_bounds__(256, 2) ffm_pairs_kernel(const Args a) {
     if (a.fitLinear)
       for (int u = lane; u < z; u += 32) {
         const double gx = coef * rec[u].x;
-        atomicAdd(a.gw + rec[u].j, gx);
-        if (MODE == FFM_PAIRS_ADAGRAD) atomicAdd(a.dGnw + rec[u].j, gx * gx);
+        const int32_t j = a.indices[rb + u];
+        atomicAdd(a.gw + j, gx);
+        if (MODE == FFM_PAIRS_ADAGRAD) atomicAdd(a.dGnw + j, gx * gx);
       }
   }
   if (MODE != FFM_PAIRS_PREDICT) {
@@ -169,6 +203,154 @@ __global__ void __launch_bounds__(256, 2) ffm_pairs_kernel(const Args a) {
       a.partials[warpGlobal * 4 + 2] = accB2;
       a.partials[warpGlobal * 4 + 3] = 0.0;
     }
+  }
+}
+
+// ------------------------------------------------------------------ block-per-row form of the same loop
+// ONE THREAD BLOCK PER ROW: the row's pairs are dealt to all (blockDim/32)*SLOTS pair slots of the block,
+// so a 39-nonzero row is 3 batches of 8 pairs per slot instead of 24.  Only gridDim rows are in flight
+// on the chip (296 x 95 KB of gathered parameters ~ 28 MB), so the backward pass's re-read of the row's
+// vectors and the second half of every 128-byte line (the neighbouring field's vector) hit L2; with a
+// warp per row 2 368 rows x 95 KB = 225 MB are in flight, more than the 126 MB L2 (ncu r01i: 130 KB/row of
+// DRAM reads for 95 KB of algorithmic gathers, DRAM the only unit above 30 %).
+// Requires z <= FFM_PAIRS_TABLE_MAXZ (the shared pair table); summation order differs from the warp
+// form only by association.
+template <int MODE, int KT, class Args>
+__global__ void __launch_bounds__(256, 2) ffm_pairs_block_kernel(const Args a) {
+  constexpr int SLOTS = 32 / KT;
+  constexpr int PB = 8;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double red[32];
+  const int lane = threadIdx.x & 31;
+  const int warpInBlock = threadIdx.x >> 5;
+  const int nWarpsB = blockDim.x >> 5;
+  const int s = lane & (KT - 1);
+  const int gslot = warpInBlock * SLOTS + lane / KT;
+  const int nSlots = nWarpsB * SLOTS;
+  const int CH = a.CH;
+  FfmRec *rec = reinterpret_cast<FfmRec *>(smem_raw);
+  uint16_t *tab = reinterpret_cast<uint16_t *>(smem_raw + (size_t)CH * sizeof(FfmRec));
+  int zTab = -1;
+  const int nF = a.nFields;
+  double bias = a.b[0];
+  if (MODE == FFM_PAIRS_ADAGRAD && !a.first && a.fitIntercept)
+    bias = -a.eta0 * a.adaScal[0] / (sqrt(a.adaScal[1]) + a.eta0 * a.tIt * a.alpha0);
+  const double *__restrict__ Pg = a.P + s;
+  double accLoss = 0.0, accB1 = 0.0, accB2 = 0.0;
+
+  for (int64_t q = blockIdx.x; q < a.nRows; q += gridDim.x) {
+    const int64_t r = a.rowIdx ? (int64_t)a.rowIdx[q] : (a.rowBegin + q) % a.n;
+    const int64_t rb = a.indptr[r];
+    const int z = (int)(a.indptr[r + 1] - rb);
+    __syncthreads();                                   // the previous row's records are no longer read
+    double lin = 0.0;
+    for (int u = threadIdx.x; u < z; u += blockDim.x) {
+      FfmRec m;
+      const int32_t j = a.indices[rb + u];
+      m.jb = j * nF;
+      m.f = a.fields[rb + u];
+      m.x = a.data[rb + u];
+      rec[u] = m;
+      lin += a.w[j] * m.x;
+    }
+    const int nPairs = z * (z - 1) / 2;
+    if (z != zTab) {
+      int u = 0, v = 1;
+      ffm_pair_advance(u, v, threadIdx.x, z);
+      for (int p = threadIdx.x; p < nPairs; p += blockDim.x) {
+        tab[p] = (uint16_t)(u | (v << 8));
+        ffm_pair_advance(u, v, blockDim.x, z);
+      }
+      zTab = z;
+    }
+    __syncthreads();
+
+    // ---- forward
+    double acc = 0.0;
+    for (int p = gslot; p < nPairs; p += nSlots * PB) {
+      double a1[PB], a2[PB], xx[PB];
+#pragma unroll
+      for (int i = 0; i < PB; ++i) {
+        const int pi = p + i * nSlots;
+        a1[i] = 0.0; a2[i] = 0.0; xx[i] = 0.0;
+        if (pi < nPairs) {
+          const unsigned uv = tab[pi];
+          const FfmRec mu = rec[uv & 0xff], mv = rec[uv >> 8];
+          if (mv.jb != mu.jb) {
+            a1[i] = __ldg(Pg + (int64_t)(mu.jb + mv.f) * KT);
+            a2[i] = __ldg(Pg + (int64_t)(mv.jb + mu.f) * KT);
+            xx[i] = mu.x * mv.x;
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < PB; ++i) acc += xx[i] * (a1[i] * a2[i]);
+    }
+    double part = warp_sum(lin + acc);
+    if (lane == 0) red[warpInBlock] = part;
+    __syncthreads();
+    double tot = 0.0;
+    for (int wq = 0; wq < nWarpsB; ++wq) tot += red[wq];   // fixed order, identical in every thread
+    const double yhat = bias + tot;
+    if (threadIdx.x == 0 && a.yOut) a.yOut[q] = yhat;
+    if (MODE == FFM_PAIRS_PREDICT) continue;
+
+    const double yi = a.y[r];
+    const double dL = dev_dloss(a.loss, a.thr, yi, yhat);
+    const double coef = (MODE == FFM_PAIRS_GRAD) ? dL / a.mb : dL;
+    if (threadIdx.x == 0) {
+      accLoss += dev_loss(a.loss, a.thr, yi, yhat);
+      accB1 += coef;
+      accB2 += dL * dL;
+    }
+    // ---- backward
+    double *__restrict__ gPg = a.gP + s;
+    double *__restrict__ gNg = (MODE == FFM_PAIRS_ADAGRAD) ? a.dGnP + s : nullptr;
+    for (int p = gslot; p < nPairs; p += nSlots * PB) {
+      double a1[PB], a2[PB], cx[PB];
+      int32_t e1[PB], e2[PB];
+#pragma unroll
+      for (int i = 0; i < PB; ++i) {
+        const int pi = p + i * nSlots;
+        e1[i] = -1; e2[i] = 0; a1[i] = 0.0; a2[i] = 0.0; cx[i] = 0.0;
+        if (pi < nPairs) {
+          const unsigned uv = tab[pi];
+          const FfmRec mu = rec[uv & 0xff], mv = rec[uv >> 8];
+          if (mv.jb != mu.jb) {
+            e1[i] = mu.jb + mv.f;
+            e2[i] = mv.jb + mu.f;
+            a1[i] = __ldg(Pg + (int64_t)e1[i] * KT);
+            a2[i] = __ldg(Pg + (int64_t)e2[i] * KT);
+            cx[i] = coef * (mu.x * mv.x);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < PB; ++i) {
+        if (e1[i] >= 0) {
+          const double g1 = cx[i] * a2[i], g2 = cx[i] * a1[i];
+          atomicAdd(gPg + (int64_t)e1[i] * KT, g1);
+          atomicAdd(gPg + (int64_t)e2[i] * KT, g2);
+          if (MODE == FFM_PAIRS_ADAGRAD) {
+            atomicAdd(gNg + (int64_t)e1[i] * KT, g1 * g1);
+            atomicAdd(gNg + (int64_t)e2[i] * KT, g2 * g2);
+          }
+        }
+      }
+    }
+    if (a.fitLinear)
+      for (int u = threadIdx.x; u < z; u += blockDim.x) {
+        const double gx = coef * rec[u].x;
+        const int32_t j = a.indices[rb + u];
+        atomicAdd(a.gw + j, gx);
+        if (MODE == FFM_PAIRS_ADAGRAD) atomicAdd(a.dGnw + j, gx * gx);
+      }
+  }
+  if (MODE != FFM_PAIRS_PREDICT && threadIdx.x == 0) {
+    a.partials[blockIdx.x * 4 + 0] = accLoss;
+    a.partials[blockIdx.x * 4 + 1] = accB1;
+    a.partials[blockIdx.x * 4 + 2] = accB2;
+    a.partials[blockIdx.x * 4 + 3] = 0.0;
   }
 }
 

@@ -247,7 +247,7 @@ class SGD(_Base):
                                  C.byref(viol), C.byref(lossSum)))
                 self.epoch_seconds.append(time.perf_counter() - t0)
                 self.it = it.value
-                runningLoss = lossSum.value / (n * world)      # the loss sum is all-reduced; shards are even
+                runningLoss = lossSum.value / n
                 self.history.append((viol.value, runningLoss))
                 if callback is not None:
                     # finalize + transpose back before the user sees the model (sgd.nim:310-316)
