@@ -293,3 +293,94 @@ def prox_l21_row(p, lam):
     p = np.asarray(p, dtype=np.float64)
     nrm = np.sqrt(np.sum(p * p))
     return p * (1.0 - lam / nrm) if nrm > lam else np.zeros_like(p)
+
+
+def prox_squaredl12_slow(p, lam):
+    """proxSquaredL12Slow, tests/regularizer/squaredl12_slow.nim:10-25 (the reference's own test definition)"""
+    p = np.asarray(p, dtype=np.float64).copy()
+    n = len(p)
+    absp = np.sort(np.abs(p))[::-1]
+    S = 2.0 * lam * np.cumsum(absp)
+    for i in range(n):
+        S[i] /= 1.0 + 2.0 * lam * (i + 1.0)
+    theta = 0
+    for i in range(n):
+        if absp[i] - S[i] < 0:
+            break
+        theta += 1
+    for i in range(n):
+        if abs(p[i]) < absp[theta - 1]:
+            p[i] = 0.0
+        else:
+            p[i] = np.sign(p[i]) * max(abs(p[i]) - S[theta - 1], 0.0)
+    return p
+
+
+def pcd_slow_fit(X, y, P, w, intercept, degree, fit_linear, fit_intercept, loss, max_iter, alpha0,
+                 alpha, beta, gamma, reg):
+    """PCDSlow.fit (tests/optimizer/pcd_slow.nim:27-113): the naive dense solver the reference tests
+    pcd.nim against -- gradient step on one coordinate, then the regulariser's coordinate prox
+    (tests/regularizer/l1_slow.nim:28-31, squaredl12_slow.nim:43-56), full re-prediction after every
+    update.  reg in l1 / squaredl12 (transpose=true) / squaredl12_rows."""
+    n, d = X.shape
+    nO, k, dd = P.shape
+    P = P.copy()
+    w = w.copy()
+    alpha0, alpha, beta, gamma = alpha0 * n, alpha * n, beta * n, gamma * n
+    mu = MU[loss]
+    col_norm_sq = (X ** 2).sum(axis=0)
+    y_pred = fm_decision_function(X, P, w, intercept, degree)
+    for _ in range(max_iter):
+        if fit_intercept:
+            upd = alpha0 * intercept + sum(dloss_val(loss, y[i], y_pred[i]) for i in range(n))
+            upd /= mu * n + alpha0
+            intercept -= upd
+            y_pred = fm_decision_function(X, P, w, intercept, degree)
+        if fit_linear:
+            for j in range(d):
+                upd = alpha * w[j]
+                for i in range(n):
+                    upd += dloss_val(loss, y[i], y_pred[i]) * X[i, j]
+                inv = mu * col_norm_sq[j] + alpha
+                if inv < 1e-12:
+                    continue
+                upd /= inv
+                w[j] -= upd
+                for i in range(n):
+                    y_pred[i] -= upd * X[i, j]
+            y_pred = fm_decision_function(X, P, w, intercept, degree)
+        for o in range(nO):
+            deg = degree - o
+            for s in range(k):
+                for j in range(dd):
+                    dA = np.zeros(n)
+                    others = [q for q in range(dd) if q != j]
+                    for i in range(n):
+                        acc = 1.0 if deg - 1 == 0 else 0.0
+                        if deg - 1 > 0:
+                            for idx in combinations(others, deg - 1):
+                                prod = 1.0
+                                for j2 in idx:
+                                    prod *= P[o, s, j2]
+                                    if j2 < d:
+                                        prod *= X[i, j2]
+                                acc += prod
+                        if j < d:
+                            acc *= X[i, j]
+                        dA[i] = acc
+                    inv = float((dA ** 2).sum()) * mu + beta
+                    if inv < 1e-12:
+                        continue
+                    g = beta * P[o, s, j]
+                    for i in range(n):
+                        g += dloss_val(loss, y[i], y_pred[i]) * dA[i]
+                    P[o, s, j] -= g / inv
+                    lam = gamma / inv
+                    psj = P[o, s, j]
+                    if reg == "l1":
+                        P[o, s, j] = np.sign(psj) * max(abs(psj) - lam, 0.0)
+                    else:
+                        strength = (np.abs(P[o, s, :]).sum() if reg == "squaredl12" else np.abs(P[o, :, j]).sum()) - abs(psj)
+                        P[o, s, j] = np.sign(psj / (1 + 2 * lam)) * max(abs(psj / (1 + 2 * lam)) - 2 * lam * strength / (1 + 2 * lam), 0.0)
+                    y_pred = fm_decision_function(X, P, w, intercept, degree)
+    return P, w, intercept

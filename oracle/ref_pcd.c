@@ -3,9 +3,11 @@
  * with the per-coordinate prox / cache protocol of the regularisers it accepts:
  *   L1          regularizer/l1.nim:22-24,57-59        softthreshold(psj - update, lam)
  *   SquaredL12  regularizer/squaredl12.nim:108-114,161-185 (transpose = true | false)
- * TEST INFRASTRUCTURE ONLY (see ref_cpu.c header).  Pinned against oracle/bruteforce.py's
- * definition-level check (pcd with gamma = 0 == cd with the PCD guard; the coordinate prox minimises
- * the coordinate's quadratic model) in tests/test_oracle.py.
+ * TEST INFRASTRUCTURE ONLY (see ref_cpu.c header).  Pinned the way the reference pins pcd.nim
+ * (tests/test_pcd_l1.nim, tests/test_pcd_squaredl12.nim): against the naive dense solver PCDSlow
+ * (tests/optimizer/pcd_slow.nim + tests/regularizer/{l1,squaredl12}_slow.nim) restated in
+ * oracle/bruteforce.py, plus pcd(gamma = 0) == cd and monotone decrease of the regularised objective
+ * (tests/test_oracle.py).
  */
 #include <math.h>
 #include <stdint.h>

@@ -261,3 +261,35 @@ def test_pcd_oracle_reduces_to_cd_and_minimises_coordinate_model(oracle):
         obj = r["loss"] + r["reg"]
         assert np.all(np.diff(obj) <= 1e-12), (reg, obj)
         assert np.count_nonzero(r["P"] == 0.0) > 0
+
+
+@pytest.mark.parametrize("degree,fit_lower,reg", [(2, "explicit", "squaredl12"), (2, "augment", "squaredl12"),
+                                                  (2, "none", "squaredl12_rows"), (2, "explicit", "l1"),
+                                                  (3, "explicit", "l1")])
+def test_pcd_oracle_matches_reference_slow_solver(oracle, degree, fit_lower, reg):
+    """tests/test_pcd_squaredl12.nim / test_pcd_l1.nim compare pcd.nim with PCDSlow (pcd_slow.nim) at
+    n=50, d=6, k=4; the same comparison pins the restatement (rtol 1e-6 / atol 1e-9 there)."""
+    n, d, k = 30, 6, 3
+    X = make_dense(n, d, 77, density=0.7, positive=False)
+    y = np.random.default_rng(8).standard_normal(n)
+    csc = oracle.csr_to_csc(CSR.from_dense(X))
+    for fit_linear, fit_intercept in ((True, True), (False, False)):
+        P, w, _ = make_fm_params(d, degree, k, fit_lower, fit_linear, 13, scale=0.3)
+        kw = dict(alpha0=1e-6, alpha=1e-3, beta=1e-3, gamma=3e-2)
+        r = oracle.pcd_fit(csc, y, P, w, 0.0, degree, "squared", fit_linear, fit_intercept, max_iter=2, reg=reg, **kw)
+        Ps, ws, bs = bf.pcd_slow_fit(X, y, P, w, 0.0, degree, fit_linear, fit_intercept, "squared", 2, reg=reg, **kw)
+        np.testing.assert_allclose(r["P"], Ps, rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(r["w"], ws, rtol=1e-6, atol=1e-9)
+        assert abs(r["intercept"] - bs) < 1e-8
+        assert np.count_nonzero(Ps == 0.0) > 0 and np.array_equal(r["P"] == 0.0, Ps == 0.0)
+
+
+def test_prox_squaredl12_matches_reference_slow_definition(oracle):
+    """tests/test_squaredl12.nim: proxSquaredL12 vs proxSquaredL12Slow, d = 100, values in [-2, 2], the
+    reference's own lambda grid, tolerance 1e-10"""
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        q = rng.integers(0, 401, 100) / 100 - 2.0
+        for lam in [0.001, 0.002, 0.005, 0.01, 0.02, 0.05, 0.1, 0.2, 0.5, 1, 2, 3, 4]:
+            p1 = oracle.prox_matrix(q.reshape(-1, 1), lam, "squaredl12").ravel()
+            assert np.max(np.abs(p1 - bf.prox_squaredl12_slow(q, lam))) < 1e-10
