@@ -192,3 +192,82 @@ def test_fm_sgd_reset_scaling_and_perms(oracle):
     np.testing.assert_allclose([h[1] for h in opt.history], ref["loss"], rtol=OBJ_TOL)
     np.testing.assert_allclose(fm.P, ref["P"], rtol=1e-8, atol=1e-13)
     np.testing.assert_allclose(fm.w, ref["w"], rtol=1e-8, atol=1e-13)
+
+
+# ---------------------------------------------------------------- kernel-variant coverage
+def ragged_field_csr(n, d, n_fields, seed, max_nnz):
+    """rows with 0..max_nnz nonzeros (every 6th row empty, one row of length 1), random fields"""
+    rng = np.random.default_rng(seed)
+    data, indices, fields, indptr = [], [], [], [0]
+    for i in range(n):
+        z = 0 if i % 6 == 0 else (1 if i == 1 else int(rng.integers(2, max_nnz + 1)))
+        cols = np.sort(rng.choice(d, size=min(z, d), replace=False))
+        indices.extend(cols.tolist())
+        data.extend((rng.standard_normal(len(cols)) * 0.7).tolist())
+        fields.extend(rng.integers(0, n_fields, len(cols)).tolist())
+        indptr.append(len(indices))
+    return CSR(data, indices, indptr, n, d, fields=np.array(fields, np.int64), n_fields=n_fields)
+
+
+@pytest.mark.parametrize("k", [4, 8, 16, 32])
+@pytest.mark.parametrize("max_nnz", [9, 64, 90])
+@pytest.mark.parametrize("variant", ["default", "pairwarp", "block"])
+def test_ffm_kernel_variants_ragged(oracle, monkeypatch, k, max_nnz, variant):
+    """every compiled rank instance x the three kernel forms (pair-block with the shared pair table for
+    rows <= 64 nonzeros, warp-per-row pair cursor beyond, staged block-per-row fallback) on ragged rows
+    with empty rows and repeated fields: forward + gradient equal the oracle"""
+    if variant == "block" and max_nnz * 6 * k * 8 > 200_000:
+        pytest.skip("staged block kernel: slices do not fit shared memory")
+    if variant != "default":
+        monkeypatch.setenv("NIMFM_FFM_KERNEL", variant)
+    n, d, nF = 60, 120, 6
+    csr = ragged_field_csr(n, d, nF, 100 + max_nnz, max_nnz)
+    rng = np.random.default_rng(k)
+    P = rng.standard_normal((nF, d, k)) * 0.2
+    w = rng.standard_normal(d) * 0.1
+    y = rng.standard_normal(n)
+    m = make_ffm(P, w, 0.05)
+    got = m.decisionFunction(field_ds(csr))
+    assert max_rel(got, oracle.ffm_decision_function(csr, P, w, 0.05)) <= DEC_TOL
+    ls, gP, gw, gb = ffm_dev_loss_grad(m, field_ds(csr), y, nf.Squared())
+    ref = oracle.ffm_loss_grad(csr, y, P, w, 0.05, "squared")
+    assert abs(ls - ref["loss"]) <= 1e-10 * max(1.0, abs(ref["loss"]))
+    assert max_rel(gP, ref["gP"]) <= 1e-9 and max_rel(gw, ref["gw"]) <= 1e-9
+
+
+@pytest.mark.parametrize("mb", [1, 16, 200])
+@pytest.mark.parametrize("variant", ["default", "pairwarp", "block"])
+def test_ffm_adagrad_one_feature_per_field(oracle, monkeypatch, mb, variant):
+    """C5 row shape (one feature per field): the AdaGrad route runs on the pair kernels, which square
+    per-pair contributions -- equal to the oracle's per-sample squares; the staged kernel must agree"""
+    if variant != "default":
+        monkeypatch.setenv("NIMFM_FFM_KERNEL", variant)
+    csr = one_per_field_csr(200, 13, 20, 15)
+    k = 8
+    rng = np.random.default_rng(4)
+    P = rng.standard_normal((13, csr.d, k)) * 0.1
+    w = np.zeros(csr.d)
+    y = np.sign(rng.standard_normal(200))
+    ref = oracle.ffm_adagrad_fit(csr, y, P, w, 0.0, "logistic", max_iter=3, mini_batch_size=mb)
+    m = make_ffm(P, w, 0.0, task=nf.classification)
+    opt = nf.newAdaGrad(maxIter=3, loss=nf.Logistic(), verbose=0, tol=0.0, shuffle=False, miniBatchSize=mb)
+    opt.fit(field_ds(csr), y, m)
+    np.testing.assert_allclose([h[1] for h in opt.history], ref["loss"], rtol=OBJ_TOL)
+    np.testing.assert_allclose([h[0] for h in opt.history], ref["viol"], rtol=1e-8)
+    np.testing.assert_allclose(m.P, ref["P"], rtol=1e-8, atol=1e-13)
+    assert abs(m.intercept - ref["intercept"]) <= 1e-9
+
+
+def test_ffm_adagrad_repeated_fields_falls_back(oracle):
+    """rows with two nonzeros of one field: per-sample squares need the field-bucketed kernel (the pair
+    kernel would square each pair's share separately); the dispatcher must notice"""
+    csr = ragged_field_csr(60, 40, 3, 7, 10)
+    rng = np.random.default_rng(5)
+    P = rng.standard_normal((3, 40, 4)) * 0.1
+    y = rng.standard_normal(60)
+    ref = oracle.ffm_adagrad_fit(csr, y, P, np.zeros(40), 0.0, "squared", max_iter=2, mini_batch_size=8)
+    m = make_ffm(P, np.zeros(40), 0.0)
+    opt = nf.newAdaGrad(maxIter=2, verbose=0, tol=0.0, shuffle=False, miniBatchSize=8)
+    opt.fit(field_ds(csr), y, m)
+    np.testing.assert_allclose(m.P, ref["P"], rtol=1e-8, atol=1e-13)
+    np.testing.assert_allclose([h[1] for h in opt.history], ref["loss"], rtol=OBJ_TOL)
