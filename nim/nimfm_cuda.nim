@@ -121,6 +121,30 @@ proc nimfm_ffm_sgd_begin(ctx: Ctx, m: DeviceFFM): int32
 proc nimfm_ffm_sgd_epoch(ctx: Ctx, m: DeviceFFM, X: DeviceDataset, cfg: ptr SgdCfg, it: ptr int64,
                          perm: ptr int64, nRows: int64, viol, lossSum: ptr cdouble): int32
 proc nimfm_ffm_sgd_end(ctx: Ctx, m: DeviceFFM): int32
+# ---- the remaining entry points of include/nimfm_cuda.h (diagnostics, state transfer, measurement hooks)
+proc nimfm_version(): int32
+proc nimfm_launch_count(ctx: Ctx): int64
+proc nimfm_comm_size(ctx: Ctx): int32
+proc nimfm_dataset_info(ds: DeviceDataset, n, d, nnz: ptr int64, kind: ptr int32, nFields, maxRowNnz: ptr int64): int32
+proc nimfm_dataset_download(ctx: Ctx, ds: DeviceDataset, data: ptr cdouble, indices, indptr, fields: ptr int64): int32
+proc nimfm_fm_loss_grad_host(ctx: Ctx, fm: DeviceFM, nRows, d: int64, data: ptr cdouble, indices, indptr: ptr int64,
+                             y: ptr cdouble, loss: int32, huberThreshold: cdouble, miniBatchSize, chunkRows: int64,
+                             zeroGrads, allreduce: int32, lossSum: ptr cdouble): int32
+proc nimfm_fm_get_grads(ctx: Ctx, fm: DeviceFM, gP, gw, gb: ptr cdouble): int32
+proc nimfm_fm_adagrad_get_state(ctx: Ctx, fm: DeviceFM, gsP, gnP, gsw, gnw, gsb, gnb: ptr cdouble): int32
+proc nimfm_fm_adagrad_set_state(ctx: Ctx, fm: DeviceFM, gsP, gnP, gsw, gnw: ptr cdouble, gsb, gnb: cdouble): int32
+proc nimfm_fm_cd_get_ypred(ctx: Ctx, fm: DeviceFM, yPred: ptr cdouble): int32
+proc nimfm_ffm_loss_grad(ctx: Ctx, m: DeviceFFM, X: DeviceDataset, loss: int32, huberThreshold: cdouble,
+                         rowBegin, nRows: int64, rowIdx: ptr int64, miniBatchSize: int64,
+                         zeroGrads, allreduce: int32, lossSum: ptr cdouble): int32
+proc nimfm_ffm_get_grads(ctx: Ctx, m: DeviceFFM, gP, gw, gb: ptr cdouble): int32
+proc nimfm_fm_time_loss_grad(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, loss: int32, nRows, miniBatchSize: int64,
+                             reps, gradToo: int32, msPerLaunch: ptr cfloat): int32
+proc nimfm_ffm_time_loss_grad(ctx: Ctx, m: DeviceFFM, X: DeviceDataset, loss: int32, nRows, miniBatchSize: int64,
+                              reps, gradToo: int32, msPerLaunch: ptr cfloat): int32
+proc nimfm_timer_start(ctx: Ctx): int32
+proc nimfm_timer_stop(ctx: Ctx, ms: ptr cfloat): int32
+proc nimfm_fm_grad_device_ptr(fm: DeviceFM, p: ptr pointer, nDoubles: ptr int64): int32
 {.pop.}
 
 # ---------------------------------------------------------------- thin Nim layer (sketch)

@@ -130,3 +130,12 @@ def test_oracle_vstack_matches_dense_definition():
     whole = orc.csr_to_csc(st)
     assert np.array_equal(cst.indptr, whole.indptr) and np.array_equal(cst.indices, whole.indices)
     assert np.array_equal(cst.data, whole.data)
+
+
+def test_nim_binding_declares_every_header_symbol():
+    """nim/nimfm_cuda.nim (the {.importc, dynlib.} stub a nimfm maintainer adds) binds
+    exactly the symbols include/nimfm_cuda.h declares"""
+    nim = open(os.path.join(ROOT, "nim", "nimfm_cuda.nim")).read()
+    bound = set(re.findall(r"proc (nimfm_\w+)", nim))
+    assert sorted(bound) == header_symbols()
+    assert '{.push importc, dynlib: libName, cdecl.}' in nim
