@@ -396,6 +396,23 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = ne * world * args.e2e_steps / float(te.item())
 
+    # end-to-end batched decisionFunction from the same host buffers (predictions read back)
+    pred_host = torch.empty(ne, dtype=torch.float64).pin_memory()
+
+    def e2e_predict():
+        _lib.check(lib.nimfm_fm_decision_function_host(ctx, h, ne, D_FEATURES, hp[0], hp[1], hp[2], 0,
+                                                       C.c_void_p(pred_host.data_ptr())))
+    e2e_predict()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_predict()
+    torch.cuda.synchronize()
+    tp = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+    e2e_predict_value = ne * world * args.e2e_steps / float(tp.item())
+
     line = {
         "metric": "samples/sec FM/HOFM predict+grad", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -405,6 +422,9 @@ def main():
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
                 "rows_per_step": ne, "note": "nimfm_fm_loss_grad_host: pinned host CSR (f64 data, i64 indices/indptr, "
                 "f64 y) -> chunked H2D overlapped with the kernel -> loss read back"},
+        "e2e_predict": {"value": e2e_predict_value, "unit": "samples/s", "what": "nimfm_fm_decision_function_host: the "
+                        "same pinned host CSR -> chunked H2D overlapped with the forward kernel -> predictions copied "
+                        "back", "h2d_bytes_per_step": int(h2d - ne * 8), "d2h_bytes_per_step": int(ne * 8)},
         "roofline": roofline,
         "loss_sum": loss_sum, "setup_seconds": t_gen,
     }

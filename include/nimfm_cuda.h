@@ -148,6 +148,10 @@ int32_t nimfm_fm_loss_grad_host(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int
                                 const int64_t *indices, const int64_t *indptr, const double *y,
                                 int32_t loss, double huberThreshold, int64_t miniBatchSize,
                                 int64_t chunkRows, int32_t zeroGrads, int32_t allreduce, double *lossSum);
+/* decisionFunction fed from HOST buffers the same way (out[nRows] on the host): the serving-side call */
+int32_t nimfm_fm_decision_function_host(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t d,
+                                        const double *data, const int64_t *indices, const int64_t *indptr,
+                                        int64_t chunkRows, double *out);
 /* read the gradient buffers back in the reference layout (gP[order][s][j], gw[d], gb) */
 int32_t nimfm_fm_get_grads(nimfm_ctx *ctx, nimfm_fm *fm, double *gP, double *gw, double *gb);
 

@@ -130,6 +130,8 @@ proc nimfm_dataset_download(ctx: Ctx, ds: DeviceDataset, data: ptr cdouble, indi
 proc nimfm_fm_loss_grad_host(ctx: Ctx, fm: DeviceFM, nRows, d: int64, data: ptr cdouble, indices, indptr: ptr int64,
                              y: ptr cdouble, loss: int32, huberThreshold: cdouble, miniBatchSize, chunkRows: int64,
                              zeroGrads, allreduce: int32, lossSum: ptr cdouble): int32
+proc nimfm_fm_decision_function_host(ctx: Ctx, fm: DeviceFM, nRows, d: int64, data: ptr cdouble,
+                                     indices, indptr: ptr int64, chunkRows: int64, outY: ptr cdouble): int32
 proc nimfm_fm_get_grads(ctx: Ctx, fm: DeviceFM, gP, gw, gb: ptr cdouble): int32
 proc nimfm_fm_adagrad_get_state(ctx: Ctx, fm: DeviceFM, gsP, gnP, gsw, gnw, gsb, gnb: ptr cdouble): int32
 proc nimfm_fm_adagrad_set_state(ctx: Ctx, fm: DeviceFM, gsP, gnP, gsw, gnw: ptr cdouble, gsb, gnb: cdouble): int32

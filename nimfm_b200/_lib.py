@@ -85,6 +85,7 @@ SYMBOLS = {
     "nimfm_fm_loss_grad": (c_i32, [VP, VP, VP, c_i32, c_dbl, c_i64, c_i64, VP, c_i64, c_i32, c_i32, PD]),
     "nimfm_fm_loss_grad_host": (c_i32, [VP, VP, c_i64, c_i64, VP, VP, VP, VP, c_i32, c_dbl, c_i64, c_i64, c_i32,
                                         c_i32, PD]),
+    "nimfm_fm_decision_function_host": (c_i32, [VP, VP, c_i64, c_i64, VP, VP, VP, c_i64, VP]),
     "nimfm_fm_get_grads": (c_i32, [VP, VP, VP, VP, PD]),
     "nimfm_fm_mbpsgd_epoch": (c_i32, [VP, VP, VP, C.POINTER(MbpsgdCfg), c_i64, PI64, PI64, VP, PD]),
     "nimfm_fm_adagrad_init": (c_i32, [VP, VP, c_dbl, c_i32]),

@@ -328,6 +328,25 @@ int nimfm_fm_predict_device(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X
   return NIMFM_OK;
 }
 
+// decisionFunction's forward (lams applied, factorization_machine.nim:120) into a device buffer
+static int nimfm_fm_predict_device_lams(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *Xcsr, double *dOut) {
+  int rc = check_fm_ds(ctx, fm, Xcsr, false);
+  if (rc) return rc;
+  if (Xcsr->n == 0) return NIMFM_OK;
+  RowPlan pl;
+  if ((rc = plan_rows(ctx, fm, Xcsr, Xcsr->n, MODE_PREDICT, &pl))) return rc;
+  RowArgs a;
+  fill_row_args(a, fm, Xcsr);
+  a.nRows = Xcsr->n;
+  a.yOut = dOut;
+  a.G = pl.G;
+  a.CH = pl.CH;
+  pl.kern<<<pl.grid, pl.block, pl.smem, ctx->stream>>>(a);
+  LAUNCHED(ctx);
+  CK(cudaGetLastError());
+  return NIMFM_OK;
+}
+
 extern "C" {
 
 int32_t nimfm_fm_decision_function(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, double *out) {
@@ -809,19 +828,22 @@ static int ensure_stage(nimfm_ctx *ctx, nimfm_ctx::Stage &st, size_t rows, size_
   return NIMFM_OK;
 }
 
-extern "C" int32_t nimfm_fm_loss_grad_host(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t d,
-                                           const double *data, const int64_t *indices, const int64_t *indptr,
-                                           const double *y, int32_t loss, double huberThreshold,
-                                           int64_t miniBatchSize, int64_t chunkRows, int32_t zeroGrads,
-                                           int32_t allreduce, double *lossSum) {
+// Rows [0,nRows) of a HOST CSR streamed through the row kernel in chunks, the H2D copy of chunk c+1
+// overlapping the kernel of chunk c.  predOut == NULL: predict+grad (K2) into the model's gradient
+// buffers; predOut != NULL: decisionFunction (K1), each chunk's predictions copied back as it finishes.
+static int stream_host_rows(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t d, const double *data,
+                            const int64_t *indices, const int64_t *indptr, const double *y, int32_t loss,
+                            double huberThreshold, int64_t miniBatchSize, int64_t chunkRows, int32_t zeroGrads,
+                            int32_t allreduce, double *lossSum, double *predOut) {
   if (!ctx) return NIMFM_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
-  REQUIRE(fm && indptr && y, "NULL argument");
+  const bool predict = predOut != nullptr;
+  REQUIRE(fm && indptr && (y || predict), "NULL argument");
   REQUIRE(d == fm->d, "Invalid nFeatures. (batch %lld, model %lld)", (long long)d, (long long)fm->d);
   REQUIRE(nRows >= 0 && miniBatchSize >= 1, "bad nRows / miniBatchSize");
   if (chunkRows <= 0) chunkRows = 1 << 17;   // 84 MB per chunk at 39 nnz/row: short pipeline ramp and tail
   const int64_t nG = fm->nP() + fm->d + 2;
-  if (zeroGrads) CK(cudaMemsetAsync(fm->grad, 0, (size_t)nG * 8, ctx->stream));
+  if (zeroGrads && !predict) CK(cudaMemsetAsync(fm->grad, 0, (size_t)nG * 8, ctx->stream));
   int *bad = reinterpret_cast<int *>(ctx->scalars + 60);
   CK(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
   // size the two staging sets for the largest chunk (indptr is sampled at chunk boundaries only)
@@ -854,9 +876,9 @@ extern "C" int32_t nimfm_fm_loss_grad_host(nimfm_ctx *ctx, nimfm_fm *fm, int64_t
     CK(cudaMemcpyAsync(st.data, data + base, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->copyStream));
     CK(cudaMemcpyAsync(st.idx64, indices + base, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->copyStream));
     CK(cudaMemcpyAsync(st.indptr, indptr + r0, (size_t)(rows + 1) * 8, cudaMemcpyHostToDevice, ctx->copyStream));
-    CK(cudaMemcpyAsync(st.y, y + r0, (size_t)rows * 8, cudaMemcpyHostToDevice, ctx->copyStream));
+    if (!predict) CK(cudaMemcpyAsync(st.y, y + r0, (size_t)rows * 8, cudaMemcpyHostToDevice, ctx->copyStream));
     CK(cudaEventRecord(ctx->evCopied[c & 1], ctx->copyStream));
-    if (c == 0) {
+    if (c == 0 && !predict) {
       // hot columns of this batch (row sample on the host; see nimfm_find_hot): the previous call's
       // entries are cleared and the new ones set by one tiny kernel on the persistent table
       std::vector<int32_t> hot;
@@ -900,19 +922,44 @@ extern "C" int32_t nimfm_fm_loss_grad_host(nimfm_ctx *ctx, nimfm_fm *fm, int64_t
     tmp.hotSlot = ctx->stageHotSlot;
     tmp.hotList = ctx->stageHotList;
     tmp.nHot = nHot;
-    if ((rc = launch_loss_grad(ctx, fm, &tmp, loss, huberThreshold, 0, rows, nullptr, (double)miniBatchSize, nullptr)))
-      return rc;
-    add_tail_kernel<<<1, 1, 0, ctx->stream>>>(fm->grad + nG - 2, ctx->scalars + 8);
-    LAUNCHED(ctx);
+    if (predict) {
+      // the stage's target buffer doubles as the chunk's output; it travels back behind the kernel
+      if ((rc = nimfm_fm_predict_device_lams(ctx, fm, &tmp, st.y))) return rc;
+      CK(cudaMemcpyAsync(predOut + r0, st.y, (size_t)rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+      if ((rc = launch_loss_grad(ctx, fm, &tmp, loss, huberThreshold, 0, rows, nullptr, (double)miniBatchSize, nullptr)))
+        return rc;
+      add_tail_kernel<<<1, 1, 0, ctx->stream>>>(fm->grad + nG - 2, ctx->scalars + 8);
+      LAUNCHED(ctx);
+    }
     CK(cudaEventRecord(ctx->evComputed[c & 1], ctx->stream));
   }
-  if (allreduce && (rc = nimfm_allreduce_sum(ctx, fm->grad, nG))) return rc;
+  if (!predict && allreduce && (rc = nimfm_allreduce_sum(ctx, fm->grad, nG))) return rc;
   int hbad = 0;
   CK(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  if (lossSum) CK(cudaMemcpyAsync(lossSum, fm->grad + nG - 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (lossSum && !predict) CK(cudaMemcpyAsync(lossSum, fm->grad + nG - 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaStreamSynchronize(ctx->copyStream));
   CK(cudaGetLastError());
   if (hbad) return nimfm_fail(ctx, NIMFM_ERR_INVALID, "column index out of range [0,%lld)", (long long)d);
   return NIMFM_OK;
+}
+
+extern "C" int32_t nimfm_fm_loss_grad_host(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t d,
+                                           const double *data, const int64_t *indices, const int64_t *indptr,
+                                           const double *y, int32_t loss, double huberThreshold,
+                                           int64_t miniBatchSize, int64_t chunkRows, int32_t zeroGrads,
+                                           int32_t allreduce, double *lossSum) {
+  if (ctx && !y) return nimfm_fail(ctx, NIMFM_ERR_INVALID, "y is NULL");
+  return stream_host_rows(ctx, fm, nRows, d, data, indices, indptr, y, loss, huberThreshold, miniBatchSize, chunkRows,
+                          zeroGrads, allreduce, lossSum, nullptr);
+}
+
+// decisionFunction (model/factorization_machine.nim:100-122) fed from HOST buffers: the serving-side twin
+// of nimfm_fm_loss_grad_host (out[nRows] on the host; pinned memory gives full PCIe bandwidth)
+extern "C" int32_t nimfm_fm_decision_function_host(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t d,
+                                                   const double *data, const int64_t *indices,
+                                                   const int64_t *indptr, int64_t chunkRows, double *out) {
+  if (ctx && !out) return nimfm_fail(ctx, NIMFM_ERR_INVALID, "out is NULL");
+  return stream_host_rows(ctx, fm, nRows, d, data, indices, indptr, nullptr, 0, 1.0, 1, chunkRows, 0, 0, nullptr, out);
 }

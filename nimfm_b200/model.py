@@ -112,7 +112,15 @@ class FactorizationMachine(_FMBase):
         h = self._to_device(X.nFeatures)
         try:
             out = np.zeros(X.nSamples)
-            _lib.check(_lib.load().nimfm_fm_decision_function(_lib.ctx(), h, X.handle(), _lib.ptr(out)))
+            lib = _lib.load()
+            if X._handle is None and not isinstance(X, CSCDataset):
+                # no device twin yet: stream the host CSR through the row kernel (copy of chunk c+1
+                # overlaps the kernel of chunk c) instead of uploading a dataset first
+                _lib.check(lib.nimfm_fm_decision_function_host(
+                    _lib.ctx(), h, X.nSamples, X.nFeatures, _lib.ptr(X.data), _lib.ptr(X.indices),
+                    _lib.ptr(X.indptr), 0, _lib.ptr(out)))
+            else:
+                _lib.check(lib.nimfm_fm_decision_function(_lib.ctx(), h, X.handle(), _lib.ptr(out)))
         finally:
             _lib.load().nimfm_fm_free(_lib.ctx(), h)
         return out

@@ -89,6 +89,39 @@ def test_decision_function_ragged_and_wide(oracle, k, degree, fit_lower):
     assert max_rel(got, expect) <= DEC_TOL
 
 
+def test_decision_function_host_streaming(oracle):
+    """nimfm_fm_decision_function_host: the host CSR is streamed in chunks (ragged rows, empty rows, a
+    chunk size that does not divide n); identical to the resident-dataset call and to the oracle"""
+    n, d, k, degree = 700, 40, 8, 3
+    csr = ragged_csr(n, d, 77, 15)
+    P, w, _ = make_fm_params(d, degree, k, "augment", True, seed=3)
+    fm = make_fm(degree, k, "augment", True, True, P, w, 0.2)
+    fm.lams = np.random.default_rng(1).random(k) + 0.5
+    ref = oracle.fm_decision_function(csr, P, w, 0.2, degree, lams=fm.lams)
+    ds = csr_ds(csr)
+    assert ds._handle is None
+    got_host = fm.decisionFunction(ds)                       # no device twin -> streaming path
+    assert ds._handle is None
+    ds.handle()
+    got_dev = fm.decisionFunction(ds)                        # resident path
+    assert max_rel(got_host, ref) <= DEC_TOL and max_rel(got_dev, ref) <= DEC_TOL
+    lib, ctx = _lib.load(), _lib.ctx()
+    h = fm._to_device(d)
+    try:
+        out = np.zeros(n)
+        _lib.check(lib.nimfm_fm_decision_function_host(ctx, h, n, d, _lib.ptr(csr.data), _lib.ptr(csr.indices),
+                                                       _lib.ptr(csr.indptr), 97, _lib.ptr(out)))
+        assert np.array_equal(out, got_host)                 # chunking does not change a single bit
+        _lib.check(lib.nimfm_fm_decision_function_host(ctx, h, 0, d, None, None, _lib.ptr(csr.indptr), 0, _lib.ptr(out)))
+        bad = csr.indices.copy()
+        bad[5] = d
+        with pytest.raises(ValueError, match="out of range"):
+            _lib.check(lib.nimfm_fm_decision_function_host(ctx, h, n, d, _lib.ptr(csr.data), _lib.ptr(bad),
+                                                           _lib.ptr(csr.indptr), 0, _lib.ptr(out)))
+    finally:
+        lib.nimfm_fm_free(ctx, h)
+
+
 def test_decision_function_errors():
     X = make_dense(5, 6, 1)
     csr = CSR.from_dense(X)
