@@ -214,6 +214,24 @@ int32_t nimfm_fm_sgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X,
                            int64_t *it, const int64_t *perm, int64_t nRows, double *viol, double *lossSum);
 int32_t nimfm_fm_sgd_end(nimfm_ctx *ctx, nimfm_fm *fm);
 
+/* ---------------------------------------------------------------- PSGD (optimizer/psgd.nim) */
+typedef struct {
+  int32_t loss;
+  double huberThreshold;
+  double eta0, alpha0, alpha, beta, gamma;      /* newPSGD, psgd.nim:22-25 */
+  int32_t reg;             /* NIMFM_REG_L1 | _L21 (lazy protocols, l1.nim:84-136 / l21.nim:36-112) |
+                              _SQUAREDL12 | _SQUAREDL12_ROWS (dense step + full prox, squaredl12.nim:199-230) */
+  int32_t scheduling;
+  double power;
+} nimfm_psgd_cfg;
+/* Sequential per sample like SGD ("replicas only").  begin == reg.initSGD + the scaling caches
+ * (psgd.nim:98-112); epoch == the sample loop over perm (NULL: 0..nRows-1) (:118-176), lossSum its loss
+ * sum; end == finalize (:58-75). */
+int32_t nimfm_fm_psgd_begin(nimfm_ctx *ctx, nimfm_fm *fm);
+int32_t nimfm_fm_psgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, const nimfm_psgd_cfg *cfg,
+                            int64_t *it, const int64_t *perm, int64_t nRows, double *lossSum);
+int32_t nimfm_fm_psgd_end(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_psgd_cfg *cfg);
+
 /* ---------------------------------------------------------------- CD (optimizer/cd.nim) */
 typedef struct {
   int32_t loss;

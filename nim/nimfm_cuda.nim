@@ -56,6 +56,15 @@ type
     alpha0*, alpha*, beta*, gamma*: cdouble
     reg*: int32                   # 1 = L1, 2 = SquaredL12(transpose=true), 3 = SquaredL12(transpose=false)
 
+type
+  PsgdCfg* {.bycopy.} = object    # nimfm_psgd_cfg
+    loss*: int32
+    huberThreshold*: cdouble
+    eta0*, alpha0*, alpha*, beta*, gamma*: cdouble
+    reg*: int32
+    scheduling*: int32
+    power*: cdouble
+
 {.push importc, dynlib: libName, cdecl.}
 proc nimfm_ctx_create(device: int32, outCtx: ptr Ctx): int32
 proc nimfm_ctx_destroy(ctx: Ctx): int32
@@ -107,6 +116,10 @@ proc nimfm_fm_cd_epoch(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr CdCfg,
 proc nimfm_fm_pcd_epoch(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr PcdCfg,
                         viol, lossMean, regOverN: ptr cdouble): int32   # pcd.nim:156-172
 proc nimfm_fm_cd_end(ctx: Ctx, fm: DeviceFM): int32
+proc nimfm_fm_psgd_begin(ctx: Ctx, fm: DeviceFM): int32                      # psgd.nim:98-112
+proc nimfm_fm_psgd_epoch(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr PsgdCfg, it: ptr int64,
+                         perm: ptr int64, nRows: int64, lossSum: ptr cdouble): int32   # psgd.nim:118-176
+proc nimfm_fm_psgd_end(ctx: Ctx, fm: DeviceFM, cfg: ptr PsgdCfg): int32      # finalize, psgd.nim:58-75
 proc nimfm_ffm_create(ctx: Ctx, nComponents: int32, nFields, nFeatures: int64, fitLinear, fitIntercept: int32,
                       outM: ptr DeviceFFM): int32
 proc nimfm_ffm_set_params(ctx: Ctx, m: DeviceFFM, P, w: ptr cdouble, intercept: cdouble): int32

@@ -12,7 +12,7 @@ from .loss import (Huber, Logistic, Squared, SquaredHinge, newHuber, newLogistic
 from .model import (FactorizationMachine, FieldAwareFactorizationMachine, NotFittedError, augment,
                     classification, explicit, newFactorizationMachine,
                     newFieldAwareFactorizationMachine, none, regression)
-from .optimizers import (CD, L1, L21, MBPSGD, PCD, SGD, AdaGrad, SquaredL12, constant, invscaling, newAdaGrad, newCD,
-                         newL1, newL21, newMBPSGD, newPCD, newSGD, newSquaredL12, optimal, pegasos, regularization)
+from .optimizers import (CD, L1, L21, MBPSGD, PCD, PSGD, SGD, AdaGrad, SquaredL12, constant, invscaling, newAdaGrad, newCD,
+                         newL1, newL21, newMBPSGD, newPCD, newPSGD, newSGD, newSquaredL12, optimal, pegasos, regularization)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -47,6 +47,12 @@ class CdCfg(C.Structure):
                 ("beta", c_dbl)]
 
 
+class PsgdCfg(C.Structure):
+    _fields_ = [("loss", c_i32), ("huberThreshold", c_dbl), ("eta0", c_dbl), ("alpha0", c_dbl),
+                ("alpha", c_dbl), ("beta", c_dbl), ("gamma", c_dbl), ("reg", c_i32),
+                ("scheduling", c_i32), ("power", c_dbl)]
+
+
 class PcdCfg(C.Structure):
     _fields_ = [("loss", c_i32), ("huberThreshold", c_dbl), ("alpha0", c_dbl), ("alpha", c_dbl),
                 ("beta", c_dbl), ("gamma", c_dbl), ("reg", c_i32)]
@@ -96,6 +102,9 @@ SYMBOLS = {
     "nimfm_fm_sgd_begin": (c_i32, [VP, VP]),
     "nimfm_fm_sgd_epoch": (c_i32, [VP, VP, VP, C.POINTER(SgdCfg), PI64, VP, c_i64, PD, PD]),
     "nimfm_fm_sgd_end": (c_i32, [VP, VP]),
+    "nimfm_fm_psgd_begin": (c_i32, [VP, VP]),
+    "nimfm_fm_psgd_epoch": (c_i32, [VP, VP, VP, C.POINTER(PsgdCfg), PI64, VP, c_i64, PD]),
+    "nimfm_fm_psgd_end": (c_i32, [VP, VP, C.POINTER(PsgdCfg)]),
     "nimfm_fm_cd_begin": (c_i32, [VP, VP, VP, C.POINTER(CdCfg)]),
     "nimfm_fm_cd_epoch": (c_i32, [VP, VP, VP, C.POINTER(CdCfg), PD, PD, PD]),
     "nimfm_fm_pcd_epoch": (c_i32, [VP, VP, VP, C.POINTER(PcdCfg), PD, PD, PD]),

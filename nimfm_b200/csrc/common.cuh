@@ -91,6 +91,8 @@ struct nimfm_fm {
   // SGD lazy-scaling caches
   double *scalingsP = nullptr, *scalingsW = nullptr, *sgdScal = nullptr;  // sgdScal: [scaling_P, scaling_w, viol, loss]
   bool sgdReady = false;
+  double *psgdThr = nullptr;   // PSGD: per-feature accumulated thresholds of the lazy L1 / L21 protocol (psgd.cu)
+  bool psgdReady = false;
   // CD caches
   double *Pcm = nullptr;       // component-major copy P[o][s][j] used by the column kernels
   double *yPred = nullptr, *Acache = nullptr, *colNormSq = nullptr, *cdScal = nullptr;

@@ -229,7 +229,7 @@ int32_t nimfm_fm_free(nimfm_ctx *ctx, nimfm_fm *fm) {
   if (ctx) cudaSetDevice(ctx->device);
   for (double *p : {fm->P, fm->w, fm->lams, fm->b, fm->grad, fm->gsP, fm->gnP, fm->gsw, fm->gnw, fm->dG,
                     fm->adaScal, fm->scalingsP, fm->scalingsW, fm->sgdScal, fm->Pcm, fm->yPred, fm->Acache,
-                    fm->colNormSq, fm->cdScal, fm->proxState})
+                    fm->colNormSq, fm->cdScal, fm->proxState, fm->psgdThr})
     cudaFree(p);
   delete fm;
   return NIMFM_OK;
@@ -537,6 +537,17 @@ static int apply_prox(nimfm_ctx *ctx, nimfm_fm *fm, int reg, double lam) {
   }
   if (!done) return nimfm_fail(ctx, NIMFM_ERR_STATE, "SquaredL12 prox did not reach its fixed point");
   sql12_apply_kernel<<<grid, block, 0, ctx->stream>>>(fm->P, dd, SB8, R, fm->proxState);
+  LAUNCHED(ctx);
+  return NIMFM_OK;
+}
+
+// entry points for psgd.cu (the SquaredL12 route of PSGD reuses the row kernel and the prox kernels)
+int nimfm_fm_apply_prox(nimfm_ctx *ctx, nimfm_fm *fm, int reg, double lam) { return apply_prox(ctx, fm, reg, lam); }
+int nimfm_fm_loss_grad_one_row(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, int loss, double thr,
+                               int64_t row) {
+  int rc = launch_loss_grad(ctx, fm, X, loss, thr, row, 1, nullptr, 1.0, nullptr);
+  if (rc) return rc;
+  add_tail_kernel<<<1, 1, 0, ctx->stream>>>(fm->grad + fm->nP() + fm->d, ctx->scalars + 8);
   LAUNCHED(ctx);
   return NIMFM_OK;
 }

@@ -1,0 +1,464 @@
+// psgd.cu -- proximal SGD for FM (optimizer/psgd.nim:76-215), SURVEY 8f.2.
+//
+// PSGD is strictly sequential per sample, like SGD ("replicas only" for multi-GPU).  Two device routes:
+//  * L1 / L21 (regularizer/l1.nim:84-136, l21.nim:36-112): the reference keeps the parameters of
+//    untouched features stale and catches them up lazily (a global scaling / accumulated threshold and
+//    the per-feature values they had at the last touch).  That bookkeeping is NOT algebraically equal to
+//    an eager prox per step (e.g. l21.nim:86 accumulates eta*scaling with the pre-update scaling), so it
+//    is reproduced literally: ONE persistent thread block runs the sample loop with the row's P slice
+//    staged in shared memory (as sgd_fm_staged_kernel), applying lazyUpdate on the way in, the
+//    regulariser's step() in place, and updateCacheSGD / resetCacheSGD after it.
+//  * SquaredL12 (squaredl12.nim:199-230) is dense in the reference too ("sparsity is not leveraged"):
+//    every sample updates ALL parameters and runs the full prox.  Here: row kernel on the one sample
+//    (K2, coef = dloss) -> dense step kernel -> the MBPSGD prox kernels (prox_kernels.cuh).
+#include <math.h>
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "dense_kernels.cuh"
+
+#define PSGD_THREADS 256
+
+extern "C" {   // library-internal helpers defined in fm_api.cu (inside its extern "C" block)
+int nimfm_fm_loss_grad_one_row(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, int loss, double thr,
+                               int64_t row);
+int nimfm_fm_apply_prox(nimfm_ctx *ctx, nimfm_fm *fm, int reg, double lam);
+}
+
+__device__ __forceinline__ double psgd_eta(int sched, double eta0, double power, double reg, int64_t it) {
+  switch (sched) {  // getEta, sgd.nim:60-69
+    case NIMFM_SCHED_CONSTANT: return eta0;
+    case NIMFM_SCHED_OPTIMAL: return eta0 / pow(1.0 + eta0 * reg * (double)it, power);
+    case NIMFM_SCHED_INVSCALING: return eta0 / pow((double)it, power);
+    default: return 1.0 / (reg * (double)it);
+  }
+}
+static double host_eta(int sched, double eta0, double power, double reg, int64_t it) {
+  switch (sched) {
+    case NIMFM_SCHED_CONSTANT: return eta0;
+    case NIMFM_SCHED_OPTIMAL: return eta0 / pow(1.0 + eta0 * reg * (double)it, power);
+    case NIMFM_SCHED_INVSCALING: return eta0 / pow((double)it, power);
+    default: return 1.0 / (reg * (double)it);
+  }
+}
+
+__device__ __forceinline__ double psgd_soft(double x, double a) {   // softthreshold, regularizer/utils.nim:4-5
+  const double m = fabs(x) - a;
+  return (x > 0 ? 1.0 : (x < 0 ? -1.0 : 0.0)) * (m > 0.0 ? m : 0.0);
+}
+
+struct PsgdArgs {
+  const double *data;
+  const int32_t *indices;
+  const int64_t *indptr;
+  const double *y;
+  const int32_t *perm;
+  int64_t nRows, d, dd;
+  int degree, k, nOrders, nAug;
+  int fitLinear, fitIntercept;
+  double *P, *w, *b;
+  double *regScalings, *regThresholds, *scalingsW;   // [dd], [dd], [d]
+  double *scal;                                      // [reg scaling, reg threshold, scaling_w, loss sum]
+  nimfm_psgd_cfg cfg;
+  int64_t it0;
+  int zmax;
+};
+
+// L21.prox of the k-vector at v (l21.nim:25-29) by one warp; every lane of the warp must call
+__device__ __forceinline__ void psgd_l21_prox_warp(double *v, int k, double lam, double post) {
+  const int lane = threadIdx.x & 31;
+  double ss = 0.0;
+  for (int s = lane; s < k; s += 32) ss += v[s] * v[s];
+  const double nrm = sqrt(warp_sum(ss));
+  const double f = nrm > lam ? 1.0 - lam / nrm : 0.0;
+  for (int s = lane; s < k; s += 32) {
+    double p = nrm > lam ? v[s] * f : 0.0;
+    v[s] = p * post;
+  }
+}
+
+// dynamic smem: sP[zmax*SB8] | sX | sW | sSc | sTh (zmax doubles each) | sJ[zmax] (int64)
+__global__ void __launch_bounds__(PSGD_THREADS, 1) psgd_lazy_kernel(const PsgdArgs a) {
+  extern __shared__ __align__(16) unsigned char psgd_smem[];
+  __shared__ double red[PSGD_THREADS / 32];
+  __shared__ double sh[8];   // 0 yhat, 1 reg scaling, 2 reg threshold, 3 scaling_w, 4 dL
+  const int k = a.k, NO = a.nOrders, SB8 = NO * k, zmax = a.zmax;
+  double *sP = reinterpret_cast<double *>(psgd_smem);
+  double *sX = sP + (size_t)zmax * SB8;
+  double *sW = sX + zmax;
+  double *sSc = sW + zmax;
+  double *sTh = sSc + zmax;
+  int64_t *sJ = reinterpret_cast<int64_t *>(sTh + zmax);
+  const int tid = threadIdx.x, nth = blockDim.x, wid = tid >> 5, nw = nth >> 5;
+  const bool isL1 = a.cfg.reg == NIMFM_REG_L1;
+  const double alpha0 = a.cfg.alpha0, alpha = a.cfg.alpha, beta = a.cfg.beta, gamma = a.cfg.gamma;
+  double lossAcc = 0.0;
+  if (tid == 0) {
+    sh[1] = a.scal[0];
+    sh[2] = a.scal[1];
+    sh[3] = a.scal[2];
+  }
+  __syncthreads();
+  for (int64_t q = 0; q < a.nRows; ++q) {
+    const int64_t i = a.perm ? (int64_t)a.perm[q] : q;
+    const int64_t it = a.it0 + q;
+    const int64_t rb = a.indptr[i];
+    const int zReal = (int)(a.indptr[i + 1] - rb);
+    const int z = zReal + a.nAug;
+    const double rSc = sh[1], rTh = sh[2], scW = sh[3];
+    // ---- records + the lazy factors of every row feature incl. dummies (psgd.nim:121-127)
+    for (int u = tid; u < z; u += nth) {
+      const int64_t j = u < zReal ? (int64_t)a.indices[rb + u] : a.d + (u - zReal);
+      sJ[u] = j;
+      sX[u] = u < zReal ? a.data[rb + u] : 1.0;
+      sW[u] = u < zReal ? a.w[j] * (scW / a.scalingsW[j]) : 0.0;       // sfm.w[j] *= scaling_w / scalings_w[j]
+      const double sj = a.regScalings[j], tj = a.regThresholds[j];
+      sSc[u] = rSc / sj;
+      sTh[u] = isL1 ? gamma * rSc * (rTh - tj)                         // l1.nim:89-90
+                    : ((rTh - tj) / sj) * gamma;                       // l21.nim:62-63
+    }
+    __syncthreads();
+    for (int e = tid; e < z * SB8; e += nth) {
+      const int u = e / SB8, off = e - u * SB8;
+      double p = a.P[sJ[u] * SB8 + off];
+      if (isL1) {                                                      // l1.nim:86-90
+        p *= sSc[u];
+        p = psgd_soft(p, sTh[u]);
+      }
+      sP[e] = p;
+    }
+    __syncthreads();
+    if (!isL1) {                                                       // l21.nim:60-65: prox, then scale
+      for (int v = wid; v < z * NO; v += nw) {
+        const int u = v / NO;
+        psgd_l21_prox_warp(sP + (size_t)v * k, k, sTh[u], sSc[u]);     // vector (u, o) = sP[u*SB8 + o*k ..]
+      }
+      __syncthreads();
+    }
+    // ---- predictWithGrad forward (thread <-> (order, component)); A stays in registers
+    double part = 0.0;
+    for (int u = tid; u < zReal; u += nth) part += sW[u] * sX[u];
+    double A[NIMFM_MAX_DEGREE + 1];
+    const int os = tid;
+    const int o = os < SB8 ? os / k : 0, sc = os - o * k;
+    const int M = a.degree - o;
+    if (os < SB8) {
+      A[0] = 1.0;
+      for (int t = 1; t <= M; t++) A[t] = 0.0;
+      for (int u = 0; u < z; u++) {
+        const double tv = sP[u * SB8 + o * k + sc] * sX[u];
+        if (M == 2) {
+          A[1] += tv;
+          A[2] += tv * tv;
+        } else {
+          for (int t = M; t >= 1; t--) A[t] += A[t - 1] * tv;
+        }
+      }
+      part += M == 2 ? (A[1] * A[1] - A[2]) / 2.0 : A[M];
+    }
+    double yhat = block_sum(part, red);
+    if (tid == 0) {
+      yhat += a.b[0];
+      sh[0] = yhat;
+      const double yi = a.y[i];
+      lossAcc += dev_loss(a.cfg.loss, a.cfg.huberThreshold, yi, yhat);
+      sh[4] = dev_dloss(a.cfg.loss, a.cfg.huberThreshold, yi, yhat);
+    }
+    __syncthreads();
+    const double dL = sh[4];
+    const double etaW = psgd_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, alpha, it);
+    const double etaP = psgd_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, beta, it);
+    const double etaS = etaP / (1.0 + etaP * beta);                     // psgd.nim:134
+    // ---- reg.step (l1.nim:127-136 / l21.nim:102-112)
+    if (os < SB8) {
+      for (int u = 0; u < z; u++) {
+        const double x = sX[u];
+        const int e = u * SB8 + o * k + sc;
+        const double p = sP[e];
+        double g;
+        if (M == 2) g = x * (A[1] - p * x);
+        else {
+          g = x;
+          for (int t = 1; t < M; t++) g = x * (A[t] - p * g);
+        }
+        const double upd = etaS * (dL * g + beta * p);
+        sP[e] = isL1 ? psgd_soft(p - upd, gamma * etaS) : p - upd;
+      }
+    }
+    __syncthreads();
+    if (!isL1) {
+      for (int v = wid; v < z * NO; v += nw) psgd_l21_prox_warp(sP + (size_t)v * k, k, etaS * gamma, 1.0);
+      __syncthreads();
+    }
+    for (int e = tid; e < z * SB8; e += nth) {
+      const int u = e / SB8, off = e - u * SB8;
+      a.P[sJ[u] * SB8 + off] = sP[e];
+    }
+    // ---- reg.updateCacheSGD (l1.nim:106-113 / l21.nim:84-90), w, intercept, caches
+    double nSc, nTh;
+    if (isL1) {
+      nTh = rTh + etaS / rSc;
+      nSc = rSc * (1 - etaS * beta);
+    } else {
+      nTh = rTh + etaP * rSc;
+      nSc = rSc / (1 + etaP * beta);
+    }
+    const double nScW = scW / (1.0 + etaW * alpha);                     // psgd.nim:153
+    for (int u = tid; u < z; u += nth) {
+      const int64_t j = sJ[u];
+      a.regScalings[j] = nSc;
+      a.regThresholds[j] = nTh;
+      if (u < zReal) {
+        if (a.fitLinear) {                                              // fitLinearSGD with eta_w/(1+eta_w*alpha)
+          const double eta = etaW / (1.0 + etaW * alpha);
+          a.w[j] = sW[u] - eta * (dL * sX[u] + alpha * sW[u]);
+        }
+        a.scalingsW[j] = nScW;
+      }
+    }
+    if (tid == 0) {
+      if (a.fitIntercept) {                                             // psgd.nim:146-148
+        const double e0 = psgd_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, alpha0, it);
+        const double upd = e0 * (dL + alpha0 * a.b[0]);
+        a.b[0] -= upd / (1.0 + e0 * alpha0);
+      }
+      sh[1] = nSc;
+      sh[2] = nTh;
+      sh[3] = nScW;
+    }
+    __syncthreads();
+    // ---- resets against underflow (psgd.nim:158-163; l1.nim:116-124 and l21.nim:93-104 as written)
+    if (a.fitLinear && nScW < 1e-9) {
+      for (int64_t j = tid; j < a.d; j += nth) {
+        double v = a.w[j] * nScW;
+        a.w[j] = v / a.scalingsW[j];
+        a.scalingsW[j] = 1.0;
+      }
+      __syncthreads();
+      if (tid == 0) sh[3] = 1.0;
+      __syncthreads();
+    }
+    if (nSc < 1e-8) {
+      if (isL1) {
+        for (int64_t e = tid; e < a.dd * SB8; e += nth) {
+          const int64_t j = e / SB8;
+          double p = a.P[e] / a.regScalings[j];
+          p = psgd_soft(p, gamma * nTh - a.regThresholds[j]);
+          a.P[e] = p * nTh;
+        }
+      } else {
+        for (int64_t v = wid; v < a.dd * NO; v += nw) {
+          const int64_t j = v / NO;
+          const double thr = (nTh - a.regThresholds[j]) / a.regScalings[j];
+          psgd_l21_prox_warp(a.P + v * k, k, thr * gamma, nSc / a.regScalings[j]);
+        }
+      }
+      __syncthreads();
+      for (int64_t j = tid; j < a.dd; j += nth) {
+        a.regScalings[j] = 1.0;
+        a.regThresholds[j] = 0.0;
+      }
+      if (tid == 0) {
+        sh[1] = 1.0;
+        sh[2] = 0.0;
+      }
+      __syncthreads();
+    }
+  }
+  lossAcc = block_sum(lossAcc, red);
+  if (tid == 0) {
+    a.scal[0] = sh[1];
+    a.scal[1] = sh[2];
+    a.scal[2] = sh[3];
+    a.scal[3] = lossAcc;
+  }
+}
+
+// finalize (psgd.nim:58-75): w catch-up, reg.lazyUpdateFinal (l1.nim:93-103 resets its caches,
+// l21.nim:68-75 does not)
+__global__ void __launch_bounds__(PSGD_THREADS, 1) psgd_finalize_kernel(const PsgdArgs a) {
+  const int k = a.k, NO = a.nOrders, SB8 = NO * k;
+  const int tid = threadIdx.x, nth = blockDim.x, wid = tid >> 5, nw = nth >> 5;
+  const double rSc = a.scal[0], rTh = a.scal[1], scW = a.scal[2], gamma = a.cfg.gamma;
+  __syncthreads();
+  if (a.fitLinear)
+    for (int64_t j = tid; j < a.d; j += nth) {
+      double v = a.w[j] * scW;
+      a.w[j] = v / a.scalingsW[j];
+      a.scalingsW[j] = scW;
+    }
+  if (a.cfg.reg == NIMFM_REG_L1) {
+    for (int64_t e = tid; e < a.dd * SB8; e += nth) {
+      const int64_t j = e / SB8;
+      double p = a.P[e] * (rSc / a.regScalings[j]);
+      a.P[e] = psgd_soft(p, gamma * rSc * (rTh - a.regThresholds[j]));
+    }
+    __syncthreads();
+    for (int64_t j = tid; j < a.dd; j += nth) {
+      a.regScalings[j] = 1.0;
+      a.regThresholds[j] = 0.0;
+    }
+    if (tid == 0) {
+      a.scal[0] = 1.0;
+      a.scal[1] = 0.0;
+    }
+  } else if (a.cfg.reg == NIMFM_REG_L21) {
+    for (int64_t v = wid; v < a.dd * NO; v += nw) {
+      const int64_t j = v / NO;
+      const double thr = (rTh - a.regThresholds[j]) / a.regScalings[j];
+      psgd_l21_prox_warp(a.P + v * k, k, thr * gamma, rSc / a.regScalings[j]);
+    }
+  }
+}
+
+// dense step of the SquaredL12 route (squaredl12.nim:224-228 for P; the eager equivalent of the lazily
+// scaled w of psgd.nim:122-155; the intercept of :146-148).  g = dL*dA scattered by the row kernel; tail = [dL, loss]
+static __global__ void psgd_dense_step_kernel(double *P, double *gP, int64_t nP, double etaS, double beta, double *w,
+                                              double *gw, int64_t d, double etaW, double alpha, int fitLinear,
+                                              double *b, double *tail, double eta0v, double alpha0,
+                                              int fitIntercept, double *lossAcc) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (int64_t e = tid; e < nP; e += stride) {
+    const double p = P[e];
+    P[e] = p - etaS * (gP[e] + beta * p);
+    gP[e] = 0.0;
+  }
+  const double etaWs = etaW / (1.0 + etaW * alpha), rW = 1.0 / (1.0 + etaW * alpha);
+  for (int64_t j = tid; j < d; j += stride) {
+    if (fitLinear) {
+      const double g = gw[j], wv = w[j];
+      // touched: w - eta'(dL x + alpha w); untouched: only the lazy scaling 1/(1+eta_w alpha) (== 1 - eta' alpha)
+      w[j] = g != 0.0 ? wv - etaWs * (g + alpha * wv) : wv * rW;
+    }
+    gw[j] = 0.0;
+  }
+  if (tid == 0) {
+    if (fitIntercept) {
+      const double upd = eta0v * (tail[0] + alpha0 * b[0]);
+      b[0] -= upd / (1.0 + eta0v * alpha0);
+    }
+    lossAcc[0] += tail[1];
+    tail[0] = 0.0;
+    tail[1] = 0.0;
+  }
+}
+
+static void psgd_fill(nimfm_ctx *ctx, double *p, int64_t n, double v) {
+  fill_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(p, n, v);
+  LAUNCHED(ctx);
+}
+
+extern "C" {
+
+// reg.initSGD + the scaling caches of PSGD.fit (psgd.nim:98-112)
+int32_t nimfm_fm_psgd_begin(nimfm_ctx *ctx, nimfm_fm *fm) {
+  if (!ctx || !fm) return NIMFM_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  const int64_t dd = fm->dd(), d = fm->d;
+  if (!fm->scalingsP) {
+    CK(cudaMalloc(&fm->scalingsP, (size_t)dd * 8));
+    CK(cudaMalloc(&fm->scalingsW, (size_t)d * 8));
+    CK(cudaMalloc(&fm->sgdScal, 8 * 8));
+  }
+  if (!fm->psgdThr) CK(cudaMalloc(&fm->psgdThr, (size_t)dd * 8));
+  psgd_fill(ctx, fm->scalingsP, dd, 1.0);
+  psgd_fill(ctx, fm->scalingsW, d, 1.0);
+  psgd_fill(ctx, fm->psgdThr, dd, 0.0);
+  const double sc[4] = {1.0, 0.0, 1.0, 0.0};   // reg scaling, reg threshold, scaling_w, loss
+  CK(cudaMemcpyAsync(fm->sgdScal, sc, 32, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(fm->grad, 0, (size_t)(fm->nP() + d + 2) * 8, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  fm->psgdReady = true;
+  return NIMFM_OK;
+}
+
+int32_t nimfm_fm_psgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, const nimfm_psgd_cfg *cfg,
+                            int64_t *it, const int64_t *perm, int64_t nRows, double *lossSum) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  REQUIRE(fm && X && cfg && it, "NULL argument");
+  if (!fm->psgdReady) return nimfm_fail(ctx, NIMFM_ERR_STATE, "nimfm_fm_psgd_begin was not called");
+  REQUIRE(X->kind != NIMFM_DS_CSC, "a CSR dataset is required");
+  REQUIRE(X->d == fm->d, "Invalid nFeatures.");
+  REQUIRE(X->y != nullptr, "dataset has no targets");
+  REQUIRE(nRows >= 0 && (perm || nRows <= X->n), "bad nRows");
+  REQUIRE(cfg->reg >= NIMFM_REG_L1 && cfg->reg <= NIMFM_REG_L21, "unsupported regulariser");
+  const bool sq = cfg->reg == NIMFM_REG_SQUAREDL12 || cfg->reg == NIMFM_REG_SQUAREDL12_ROWS;
+  REQUIRE(!(sq && fm->degree != 2), "SquaredL12 supports only degree=2.");      // squaredl12.nim:103-106
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  const int64_t nP = fm->nP(), d = fm->d, nG = nP + d + 2;
+  CK(cudaMemsetAsync(fm->sgdScal + 3, 0, 8, ctx->stream));
+  if (!sq) {
+    const int32_t *permDev = nullptr;
+    if (perm && nRows > 0) {
+      if ((rc = nimfm_stage_row_ids(ctx, perm, nRows, X->n))) return rc;
+      permDev = ctx->idx32Scratch;
+    }
+    const int SB8 = fm->nOrders * fm->k;
+    const int zmax = (int)std::max<int64_t>(X->maxSegNnz + fm->nAug, 1);
+    const size_t smem = ((size_t)zmax * SB8 + 4 * (size_t)zmax) * 8 + (size_t)zmax * 8;
+    if (SB8 > PSGD_THREADS || smem > (size_t)ctx->smemOptin - 2048)
+      return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED,
+                        "PSGD: nOrders*nComponents=%d (max %d) or a %d-nonzero row's slice (%zu B) does not fit", SB8,
+                        PSGD_THREADS, zmax, smem);
+    PsgdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.data = X->data; a.indices = X->indices; a.indptr = X->indptr; a.y = X->y; a.perm = permDev;
+    a.nRows = nRows; a.d = d; a.dd = fm->dd();
+    a.degree = fm->degree; a.k = fm->k; a.nOrders = fm->nOrders; a.nAug = fm->nAug;
+    a.fitLinear = fm->fitLinear; a.fitIntercept = fm->fitIntercept;
+    a.P = fm->P; a.w = fm->w; a.b = fm->b;
+    a.regScalings = fm->scalingsP; a.regThresholds = fm->psgdThr; a.scalingsW = fm->scalingsW; a.scal = fm->sgdScal;
+    a.cfg = *cfg; a.it0 = *it; a.zmax = zmax;
+    CK(cudaFuncSetAttribute(psgd_lazy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    psgd_lazy_kernel<<<1, PSGD_THREADS, smem, ctx->stream>>>(a);
+    LAUNCHED(ctx);
+  } else {
+    for (int64_t q = 0; q < nRows; q++) {
+      const int64_t i = perm ? perm[q] : q;
+      REQUIRE(i >= 0 && i < X->n, "row id %lld out of range", (long long)i);
+      const int64_t itq = *it + q;
+      if ((rc = nimfm_fm_loss_grad_one_row(ctx, fm, X, cfg->loss, cfg->huberThreshold, i))) return rc;
+      const double etaW = host_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->alpha, itq);
+      const double etaP = host_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->beta, itq);
+      const double eta0v = host_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->alpha0, itq);
+      const double etaS = etaP / (1.0 + etaP * cfg->beta);
+      psgd_dense_step_kernel<<<ew_grid(ctx, nP), 256, 0, ctx->stream>>>(
+          fm->P, fm->grad, nP, etaS, cfg->beta, fm->w, fm->grad + nP, d, etaW, cfg->alpha, fm->fitLinear, fm->b,
+          fm->grad + nG - 2, eta0v, cfg->alpha0, fm->fitIntercept, fm->sgdScal + 3);
+      LAUNCHED(ctx);
+      if ((rc = nimfm_fm_apply_prox(ctx, fm, cfg->reg, cfg->gamma * etaS))) return rc;
+    }
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctx->hostScalars, fm->sgdScal, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *it += nRows;
+  if (lossSum) *lossSum = ctx->hostScalars[3];
+  return NIMFM_OK;
+}
+
+// finalize(self, sfm, P, scaling_w, scalings_w) (psgd.nim:58-75); a no-op for the eager SquaredL12 route
+int32_t nimfm_fm_psgd_end(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_psgd_cfg *cfg) {
+  if (!ctx || !fm || !cfg) return NIMFM_ERR_INVALID;
+  if (!fm->psgdReady) return nimfm_fail(ctx, NIMFM_ERR_STATE, "nimfm_fm_psgd_begin was not called");
+  CK(cudaSetDevice(ctx->device));
+  if (cfg->reg == NIMFM_REG_L1 || cfg->reg == NIMFM_REG_L21) {
+    PsgdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.d = fm->d; a.dd = fm->dd(); a.k = fm->k; a.nOrders = fm->nOrders; a.fitLinear = fm->fitLinear;
+    a.P = fm->P; a.w = fm->w;
+    a.regScalings = fm->scalingsP; a.regThresholds = fm->psgdThr; a.scalingsW = fm->scalingsW; a.scal = fm->sgdScal;
+    a.cfg = *cfg;
+    psgd_finalize_kernel<<<1, PSGD_THREADS, 0, ctx->stream>>>(a);
+    LAUNCHED(ctx);
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  return NIMFM_OK;
+}
+
+}  // extern "C"

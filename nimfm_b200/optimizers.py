@@ -371,6 +371,92 @@ def newAdaGrad(maxIter=100, eta0=0.1, alpha0=1e-6, alpha=1e-3, beta=1e-3, loss=N
     return AdaGrad(maxIter, eta0, alpha0, alpha, beta, loss, eps, verbose, tol, shuffle, nCalls, miniBatchSize)
 
 
+# ================================================================ PSGD
+class PSGD(_Base):
+    """Proximal SGD (optimizer/psgd.nim:10-215).  Strictly sequential per sample like SGD; reg: L1 / L21
+    (the reference's lazy protocols, reproduced on the device) or SquaredL12 (default; dense step + full
+    prox every sample, as in the reference)."""
+
+    def __init__(self, maxIter=100, eta0=0.01, alpha0=1e-6, alpha=1e-3, beta=1e-4, gamma=1e-4, loss=None,
+                 reg=None, scheduling=optimal, power=1.0, verbose=1, tol=1e-3, shuffle=True, nCalls=-1):
+        self.maxIter, self.eta0, self.alpha0, self.alpha, self.beta, self.gamma = maxIter, eta0, alpha0, alpha, beta, gamma
+        self.loss = loss if loss is not None else Squared()
+        self.reg = reg if reg is not None else SquaredL12()
+        self.scheduling, self.power, self.verbose, self.tol = scheduling, power, verbose, tol
+        self.shuffle, self.nCalls = shuffle, nCalls
+        self.it = 1
+
+    def fit(self, X, y, sfm, callback=None, perms=None):
+        """psgd.nim:76-215 (nCalls > 0, a callback inside the sample loop, is not supported: one library
+        call runs a whole epoch)"""
+        if not isinstance(X, CSRDataset):
+            raise TypeError("PSGD.fit needs a CSRDataset")
+        sfm.init(X)
+        y = sfm.checkTarget(y)
+        lib, ctx = _lib.load(), _lib.ctx()
+        X.set_targets(y)
+        n = X.nSamples
+        h = sfm._to_device(X.nFeatures)
+        if not sfm.warmStart:
+            self.it = 1                        # :104-105
+        cfg = _lib.PsgdCfg(self.loss.kind, self.loss.threshold, self.eta0, self.alpha0, self.alpha, self.beta,
+                           self.gamma, self.reg.kind, _lib.SCHED[self.scheduling], self.power)
+        rng = self._rng(sfm)
+        indices = np.arange(n, dtype=np.int64)
+        self.history = []
+        self.epoch_seconds = []
+        converged = False
+        runningLossOld = 0.0                   # :103
+        try:
+            self.reg.initSGD(sfm.degree, X.nFeatures + sfm.nAugments, sfm.nComponents)   # :111
+            _lib.check(lib.nimfm_fm_psgd_begin(ctx, h))
+            if self.verbose > 0:
+                echoHeader(self.maxIter, viol=False)
+            for ep in range(self.maxIter):
+                if perms is not None:
+                    indices = _lib.i64(perms[ep])
+                elif self.shuffle:
+                    rng.shuffle(indices)
+                itc, ls = C.c_int64(self.it), C.c_double()
+                t0 = time.perf_counter()
+                _lib.check(lib.nimfm_fm_psgd_epoch(ctx, h, X.handle(), C.byref(cfg), C.byref(itc),
+                                                   _lib.ptr(indices), n, C.byref(ls)))
+                self.epoch_seconds.append(time.perf_counter() - t0)
+                self.it = itc.value
+                runningLoss = ls.value / n
+                self.history.append(runningLoss)
+                if callback is not None and self.nCalls <= 0:      # :181-183 (finalize, then callback)
+                    _lib.check(lib.nimfm_fm_psgd_end(ctx, h, C.byref(cfg)))
+                    sfm._from_device(h)
+                    callback(self, sfm)
+                if math.isnan(runningLoss):
+                    print("Loss is NaN. Use smaller learning rate.")
+                    break
+                if abs(runningLoss - runningLossOld) < self.tol:   # :189-192
+                    if self.verbose > 0:
+                        print("Converged at epoch ", ep, ".")
+                    converged = True
+                    break
+                if self.verbose > 0:                                # :194-198 (stale P, as the reference prints it)
+                    sfm._from_device(h)
+                    regVal = regularization(sfm.P, sfm.w, sfm.intercept, self.alpha0, self.alpha, self.beta)
+                    for order in range(sfm.nOrders):
+                        regVal += self.gamma * self.reg.eval(np.asarray(sfm.P[order]).T, sfm.degree - order)
+                    echoInfo(ep + 1, self.maxIter, -1, runningLoss, regVal)
+                runningLossOld = runningLoss
+            if not converged and self.verbose > 0:
+                print("Objective did not converge. Increase maxIter.")
+            _lib.check(lib.nimfm_fm_psgd_end(ctx, h, C.byref(cfg)))   # finalize, :204
+            sfm._from_device(h)
+        finally:
+            lib.nimfm_fm_free(ctx, h)
+
+
+def newPSGD(maxIter=100, eta0=0.01, alpha0=1e-6, alpha=1e-3, beta=1e-4, gamma=1e-4, loss=None, reg=None,
+            scheduling=optimal, power=1.0, verbose=1, tol=1e-3, shuffle=True, nCalls=-1):
+    return PSGD(maxIter, eta0, alpha0, alpha, beta, gamma, loss, reg, scheduling, power, verbose, tol, shuffle, nCalls)
+
+
 # ================================================================ MBPSGD
 class L1:                                      # regularizer/l1.nim
     kind = _lib.REG_L1

@@ -384,3 +384,49 @@ def pcd_slow_fit(X, y, P, w, intercept, degree, fit_linear, fit_intercept, loss,
                         P[o, s, j] = np.sign(psj / (1 + 2 * lam)) * max(abs(psj / (1 + 2 * lam)) - 2 * lam * strength / (1 + 2 * lam), 0.0)
                     y_pred = fm_decision_function(X, P, w, intercept, degree)
     return P, w, intercept
+
+
+def psgd_slow_fit(X, y, P, w, intercept, degree, fit_linear, fit_intercept, loss, max_iter, eta0, alpha0,
+                  alpha, beta, gamma, reg, it=1):
+    """PSGDSlow.fit (tests/optimizer/psgd_slow.nim:42-99), shuffle=false, scheduling=optimal, power=1:
+    dense gradient step on every parameter, then the regulariser's full prox, every sample.
+    P model layout [nOrders, k, d+nAug]; reg in l1 / l21 / squaredl12 / squaredl12_rows."""
+    n, d = X.shape
+    nO, k, dd = P.shape
+    P = P.copy()
+    w = w.copy()
+
+    def eta(r):
+        return eta0 / (1.0 + eta0 * r * it)
+
+    for _ in range(max_iter):
+        for i in range(n):
+            y_pred = fm_decision_function(X[i:i + 1], P, w, intercept, degree)[0]
+            dL = dloss_val(loss, y[i], y_pred)
+            grad = np.zeros_like(P)
+            fm_grad(X, i, P, degree, dL, grad)
+            eta_w, eta_P = eta(alpha), eta(beta)
+            eta_s = eta_P / (1.0 + eta_P * beta)
+            if fit_intercept:
+                upd = eta(alpha0) * (dL + alpha0 * intercept)
+                intercept -= upd / (1.0 + eta(alpha0) * alpha0)
+            if fit_linear:
+                for j in range(d):
+                    upd = eta_w * (dL * X[i, j] + alpha * w[j])
+                    w[j] -= upd / (1.0 + eta_w * alpha)
+            for o in range(nO):
+                P[o] -= eta_s * (grad[o] + beta * P[o])
+                lam = gamma * eta_s
+                if reg == "l1":
+                    P[o] = np.sign(P[o]) * np.maximum(np.abs(P[o]) - lam, 0.0)
+                elif reg == "l21":
+                    for j in range(dd):
+                        P[o][:, j] = prox_l21_row(P[o][:, j], lam)
+                elif reg == "squaredl12":
+                    for s in range(k):
+                        P[o][s] = prox_squaredl12_slow(P[o][s], lam)
+                else:
+                    for j in range(dd):
+                        P[o][:, j] = prox_squaredl12_slow(P[o][:, j], lam)
+            it += 1
+    return P, w, intercept

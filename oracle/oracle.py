@@ -24,7 +24,7 @@ PI = C.POINTER(C.c_int64)
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("ref_cpu.c", "ref_hogwild.c", "ref_pcd.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("ref_cpu.c", "ref_hogwild.c", "ref_pcd.c", "ref_psgd.c")]
     if (not force and os.path.exists(_SO)
             and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs)):
         return _SO
@@ -359,6 +359,27 @@ def pcd_fit(Xc, y, P, w, intercept, degree, loss_kind="squared", fit_linear=True
         _d(viol), _d(ls), _d(rg), _d(yp))
     return dict(P=P, w=w, intercept=b.value, viol=viol[:ni], loss=ls[:ni], reg=rg[:ni], iters=ni,
                 y_pred=yp)
+
+
+def psgd_fit(X, y, P, w, intercept, degree, loss_kind="squared", fit_linear=True, fit_intercept=True,
+             max_iter=10, eta0=0.01, alpha0=1e-6, alpha=1e-3, beta=1e-4, gamma=1e-4, reg="squaredl12",
+             scheduling="optimal", power=1.0, tol=0.0, perms=None, it=1, thr=1.0):
+    """PSGD.fit (optimizer/psgd.nim:76-215), X CSR; reg in l1 / l21 / squaredl12 / squaredl12_rows."""
+    P = f64(P).copy()
+    w = f64(w).copy()
+    nO, k, dd = P.shape
+    b, itc = C.c_double(intercept), C.c_int64(it)
+    el = np.zeros(max_iter)
+    if perms is not None:
+        perms = i64(perms).reshape(-1, X.n)
+        assert perms.shape[0] >= max_iter
+    ne = lib().ref_psgd_fit(
+        c_i64(X.n), c_i64(X.d), _d(X.data), _i(X.indices), _i(X.indptr), _d(f64(y)), c_int(degree),
+        c_int(k), c_int(nO), c_int(dd - X.d), c_int(int(fit_linear)), c_int(int(fit_intercept)),
+        _d(P), _d(w), C.byref(b), c_int(LOSS[loss_kind]), c_dbl(thr), c_int(max_iter), c_dbl(eta0),
+        c_dbl(alpha0), c_dbl(alpha), c_dbl(beta), c_dbl(gamma), c_int(REG[reg]), c_int(SCHED[scheduling]),
+        c_dbl(power), c_dbl(tol), _i(perms), C.byref(itc), _d(el))
+    return dict(P=P, w=w, intercept=b.value, it=itc.value, epoch_loss=el[:ne], epochs=ne)
 
 
 def regularization(P, w, intercept, alpha0, alpha, beta):

@@ -271,3 +271,69 @@ def test_ffm_adagrad_repeated_fields_falls_back(oracle):
     opt.fit(field_ds(csr), y, m)
     np.testing.assert_allclose(m.P, ref["P"], rtol=1e-8, atol=1e-13)
     np.testing.assert_allclose([h[1] for h in opt.history], ref["loss"], rtol=OBJ_TOL)
+
+
+# ---------------------------------------------------------------- PSGD (optimizer/psgd.nim)
+def make_sgd_reg(reg):
+    return {"l1": nf.newL1, "l21": nf.newL21, "squaredl12": nf.newSquaredL12,
+            "squaredl12_rows": lambda: nf.newSquaredL12(transpose=False)}[reg]()
+
+
+@pytest.mark.parametrize("degree,fit_lower,reg", [(2, "explicit", "l1"), (3, "explicit", "l1"), (4, "augment", "l1"),
+                                                  (2, "none", "l21"), (3, "augment", "l21"), (3, "explicit", "l21"),
+                                                  (2, "explicit", "squaredl12"), (2, "augment", "squaredl12"),
+                                                  (2, "none", "squaredl12_rows")])
+@pytest.mark.parametrize("fit_linear,fit_intercept", [(True, True), (False, False)])
+def test_psgd_matches_oracle(oracle, degree, fit_lower, reg, fit_linear, fit_intercept):
+    """tests/test_psgd_{l1,l21,squaredl12}.nim shapes (n=80, d=8, k=4): the device's PSGD against the
+    literal restatement of psgd.nim (lazy L1 / L21 protocols, dense SquaredL12), shuffle=false"""
+    from oracle.oracle import CSR as _CSR
+    from helpers import make_dense, make_fm_params
+    n, d, k = 80, 8, 4
+    X = make_dense(n, d, 61 + degree, density=0.6, positive=False)
+    y = np.random.default_rng(degree).standard_normal(n)
+    csr = _CSR.from_dense(X)
+    P, w, nA = make_fm_params(d, degree, k, fit_lower, fit_linear, seed=23, scale=0.2)
+    kw = dict(eta0=0.05, alpha0=1e-6, alpha=1e-3, beta=1e-3, gamma=1.0 if reg == "l21" else 3e-2)
+    ref = oracle.psgd_fit(csr, y, P, w, 0.1, degree, "squared", fit_linear, fit_intercept, max_iter=3, reg=reg, **kw)
+    fm = nf.newFactorizationMachine(nf.regression, degree=degree, nComponents=k, fitLower=fit_lower,
+                                    fitLinear=fit_linear, fitIntercept=fit_intercept, warmStart=True)
+    fm.P, fm.w, fm.intercept, fm.isInitialized = P.copy(), w.copy(), 0.1, True
+    opt = nf.newPSGD(maxIter=3, reg=make_sgd_reg(reg), verbose=0, tol=0.0, shuffle=False, **kw)
+    opt.it = 1
+    ds = nf.newCSRDataset(csr.data, csr.indices, csr.indptr, n, d)
+    opt.fit(ds, y, fm)
+    np.testing.assert_allclose(opt.history, ref["epoch_loss"], rtol=OBJ_TOL)
+    np.testing.assert_allclose(fm.P, ref["P"], rtol=1e-8, atol=1e-13)
+    np.testing.assert_allclose(fm.w, ref["w"], rtol=1e-8, atol=1e-13)
+    assert abs(fm.intercept - ref["intercept"]) <= 1e-9
+    assert np.array_equal(fm.P == 0.0, ref["P"] == 0.0) and opt.it == ref["it"]
+    if reg in ("l1", "l21"):
+        assert np.count_nonzero(ref["P"] == 0.0) > 0                  # the prox really acted
+
+
+def test_psgd_permutation_logistic_and_rules(oracle):
+    """host-supplied permutations, logistic loss, invscaling schedule; the default regulariser
+    (SquaredL12) exists for degree 2 only"""
+    from oracle.oracle import CSR as _CSR
+    from helpers import make_dense, make_fm_params
+    n, d, k, degree = 60, 7, 3, 2
+    X = make_dense(n, d, 5, density=0.5, positive=False)
+    y = np.sign(np.random.default_rng(1).standard_normal(n))
+    csr = _CSR.from_dense(X)
+    P, w, _ = make_fm_params(d, degree, k, "explicit", True, seed=3, scale=0.2)
+    perms = np.array([np.random.default_rng(s).permutation(n) for s in range(2)])
+    kw = dict(eta0=0.1, alpha0=1e-6, alpha=1e-3, beta=1e-3, gamma=1e-2)
+    ref = oracle.psgd_fit(csr, y, P, w, 0.0, degree, "logistic", max_iter=2, reg="l1", scheduling="invscaling",
+                          power=0.5, perms=perms, **kw)
+    fm = nf.newFactorizationMachine(nf.classification, degree=degree, nComponents=k, warmStart=True)
+    fm.P, fm.w, fm.intercept, fm.isInitialized = P.copy(), w.copy(), 0.0, True
+    opt = nf.newPSGD(maxIter=2, loss=nf.Logistic(), reg=nf.newL1(), scheduling=nf.invscaling, power=0.5, verbose=0,
+                     tol=0.0, **kw)
+    opt.it = 1
+    opt.fit(nf.newCSRDataset(csr.data, csr.indices, csr.indptr, n, d), y, fm, perms=perms)
+    np.testing.assert_allclose(opt.history, ref["epoch_loss"], rtol=OBJ_TOL)
+    np.testing.assert_allclose(fm.P, ref["P"], rtol=1e-8, atol=1e-13)
+    fm3 = nf.newFactorizationMachine(nf.regression, degree=3, nComponents=2)
+    with pytest.raises(ValueError, match="SquaredL12 supports only degree=2"):
+        nf.newPSGD(maxIter=1, verbose=0).fit(nf.newCSRDataset(csr.data, csr.indices, csr.indptr, n, d), y, fm3)
