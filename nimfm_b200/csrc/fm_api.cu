@@ -122,9 +122,11 @@ static int plan_rows(nimfm_ctx *ctx, const nimfm_fm *fm, const nimfm_dataset *X,
   }
   if (!kern) return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "no row kernel for degree %d", fm->degree);
   int bestBlock = 0, bestOcc = 0, bestWarps = -1;
+  cudaFuncAttributes fattr;
+  CK(cudaFuncGetAttributes(&fattr, kern));
   for (int block : {256, 128, 64, 32}) {
     const size_t smem = (size_t)(block / 32) * gpw * perGroup;
-    if (smem > (size_t)ctx->smemOptin) continue;
+    if (smem > (size_t)ctx->smemOptin || block > fattr.maxThreadsPerBlock) continue;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem));
