@@ -14,6 +14,7 @@
 // order exactly like the reference's column sweep does.
 // P stays in the reference's component-major layout P[o][s][j] here (cd.fit does not transpose).
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -32,6 +33,14 @@ struct CdState {
   double alpha0 = 0, alpha = 0, beta = 0;  // already multiplied by nSamples (cd.nim:123-125)
   double *chain = nullptr;                 // PCD chained prox scratch: [a | c | u] x (d + nAug)
   int64_t chainCap = 0;
+  // one outer iteration is ~100-600 short kernels whose arguments do not change between iterations:
+  // it is captured once into a CUDA graph and replayed (the sweep is launch-latency-bound otherwise)
+  cudaGraphExec_t graph = nullptr;
+  int64_t graphKernels = 0;
+  struct Key {
+    int prox, loss;
+    double gammaRaw, thr, alpha0, alpha, beta;
+  } graphKey = {0, 0, 0, 0, 0, 0, 0};
 };
 
 // cdScal layout: [0] viol, [1] loss mean, [2] reg/n, [3] sum dloss, [4] |w|^2, [5] |P|^2
@@ -358,10 +367,11 @@ struct PcdProx {   // sparsity regulariser of a PCD sweep (zeros == plain CD)
   int k = 0, sIdx = 0;
 };
 
-static void cd_launch_cols(nimfm_ctx *ctx, const CdColArgs &a, bool blockPerCol) {
+// blockThreads: threads of a block-per-column launch (long columns), 0 = one warp per column
+static void cd_launch_cols(nimfm_ctx *ctx, const CdColArgs &a, int blockThreads) {
   const int64_t cols = a.j1 - a.j0;
-  if (blockPerCol) {
-    cd_col_kernel<true><<<(int)cols, 1024, 0, ctx->stream>>>(a);
+  if (blockThreads > 0) {
+    cd_col_kernel<true><<<(int)cols, blockThreads, 0, ctx->stream>>>(a);
   } else {
     const int64_t threads = cols * 32;
     cd_col_kernel<false><<<(int)((threads + 127) / 128), 128, 0, ctx->stream>>>(a);
@@ -370,12 +380,12 @@ static void cd_launch_cols(nimfm_ctx *ctx, const CdColArgs &a, bool blockPerCol)
 }
 
 static int cd_sweep(nimfm_ctx *ctx, CdState *st, const nimfm_dataset *X, nimfm_fm *fm, const nimfm_cd_cfg *cfg,
-                    double *Ps, int deg, double reg, double *updAbs, int64_t nCols, const PcdProx &px) {
+                    double *Ps, int deg, double reg, double *updAbs, int64_t nCols, const PcdProx &px, double *Abuf) {
   // nCols == d for the linear sweep (dummy features removed, cd.nim:159), d + nAug otherwise
   CdColArgs a;
   memset(&a, 0, sizeof(a));
   a.data = X->data; a.rows = X->indices; a.indptr = X->indptr; a.y = X->y;
-  a.yPred = fm->yPred; a.A = fm->Acache; a.Ps = Ps; a.updAbs = updAbs; a.colNormSq = fm->colNormSq;
+  a.yPred = fm->yPred; a.A = Abuf; a.Ps = Ps; a.updAbs = updAbs; a.colNormSq = fm->colNormSq;
   a.n = X->n; a.d = X->d; a.astride = fm->degree + 1; a.deg = deg;
   a.loss = cfg->loss; a.thr = cfg->huberThreshold; a.mu = loss_mu(cfg->loss); a.reg = reg;
   a.prox = deg == 0 ? 0 : px.prox; a.guardAll = px.guardAll; a.gamma = px.gamma;
@@ -387,7 +397,7 @@ static int cd_sweep(nimfm_ctx *ctx, CdState *st, const nimfm_dataset *X, nimfm_f
     pcd_abs_sum_kernel<<<1, 256, 0, ctx->stream>>>(Ps, nCols, cache);   // computeCacheCD (squaredl12.nim:173-179)
     LAUNCHED(ctx);
   }
-  auto run = [&](bool blockPerCol) {
+  auto run = [&](int blockPerCol) {
     if (!chained) {
       a.phase = 0;
       cd_launch_cols(ctx, a, blockPerCol);
@@ -404,18 +414,23 @@ static int cd_sweep(nimfm_ctx *ctx, CdState *st, const nimfm_dataset *X, nimfm_f
   for (size_t b = 0; b < nb; b++) {
     a.j0 = st->batchStart[b];
     a.j1 = st->batchStart[b + 1];
-    run(st->batchMaxLen[b] > 2048);
+    // column length decides the shape: a warp walks a 100-row column in 4 dependent round trips per pass,
+    // a 128-thread block in one (the sweep is latency-bound: ~100 short kernels per outer iteration)
+    const int64_t mx = st->batchMaxLen[b];
+    run(mx > 2048 ? 1024 : (mx > 256 ? 256 : (mx > 48 ? 128 : 0)));
   }
   for (int64_t j = X->d; j < nCols; j++) {   // dummy columns touch every row: one batch each
     a.j0 = j;
     a.j1 = j + 1;
-    run(true);
+    run(1024);
   }
   return NIMFM_OK;
 }
 
 static int cd_epoch_impl(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, const nimfm_cd_cfg *cfg, int prox,
                          double gammaRaw, double *viol, double *lossMean, double *regOverN);
+static int cd_enqueue_epoch(nimfm_ctx *ctx, CdState *st, nimfm_fm *fm, const nimfm_dataset *X, const nimfm_cd_cfg *cfg,
+                            int prox, double gammaRaw);
 
 extern "C" {
 
@@ -434,6 +449,8 @@ int32_t nimfm_fm_cd_begin(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, 
   int rc;
   if (st->csr) nimfm_dataset_free(ctx, st->csr);
   st->csr = nullptr;
+  if (st->graph) cudaGraphExecDestroy(st->graph);   // a new fit: buffers are reallocated below
+  st->graph = nullptr;
   if ((rc = nimfm_dataset_transpose(ctx, X, &st->csr))) return rc;
   // ---- batches of consecutive, pairwise row-disjoint columns
   {
@@ -464,7 +481,7 @@ int32_t nimfm_fm_cd_begin(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, 
   fm->Pcm = fm->yPred = fm->Acache = fm->colNormSq = fm->cdScal = nullptr;
   CK(cudaMalloc(&fm->Pcm, (size_t)std::max<int64_t>(nP, 1) * 8));
   CK(cudaMalloc(&fm->yPred, (size_t)std::max<int64_t>(n, 1) * 8));
-  CK(cudaMalloc(&fm->Acache, (size_t)std::max<int64_t>(n, 1) * (fm->degree + 1) * 8));
+  CK(cudaMalloc(&fm->Acache, (size_t)std::max<int64_t>(n, 1) * (fm->degree + 1) * 8 * 2));   // double buffer
   CK(cudaMalloc(&fm->colNormSq, (size_t)d * 8));
   CK(cudaMalloc(&fm->cdScal, 16 * 8));
   CK(cudaMemsetAsync(fm->cdScal, 0, 16 * 8, ctx->stream));
@@ -521,6 +538,64 @@ static int cd_epoch_impl(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, c
   CdState *st = cd_state(fm, false);
   REQUIRE(st && X->kind == NIMFM_DS_CSC && X->n == fm->cdN && X->d == fm->d, "dataset does not match cd_begin");
   CK(cudaSetDevice(ctx->device));
+  const int64_t n = X->n, dd = fm->dd();
+  int rc;
+  if ((rc = nimfm_ensure_partials(ctx, 1024))) return rc;            // no allocation inside a capture
+  if (prox == NIMFM_REG_SQUAREDL12 && st->chainCap < 3 * dd) {
+    cudaFree(st->chain);
+    st->chain = nullptr;
+    CK(cudaMalloc(&st->chain, (size_t)(3 * dd) * 8));
+    st->chainCap = 3 * dd;
+  }
+  const char *genv = getenv("NIMFM_CD_GRAPH");
+  const bool useGraph = !(genv && genv[0] == '0');
+  const CdState::Key key = {prox, cfg->loss, gammaRaw, cfg->huberThreshold, st->alpha0, st->alpha, st->beta};
+  if (!useGraph) {
+    if ((rc = cd_enqueue_epoch(ctx, st, fm, X, cfg, prox, gammaRaw))) return rc;
+  } else {
+    if (st->graph && memcmp(&key, &st->graphKey, sizeof(key)) != 0) {
+      cudaGraphExecDestroy(st->graph);
+      st->graph = nullptr;
+    }
+    if (!st->graph) {
+      const int64_t l0 = ctx->launches;
+      CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+      rc = cd_enqueue_epoch(ctx, st, fm, X, cfg, prox, gammaRaw);
+      cudaGraph_t g = nullptr;
+      cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+      st->graphKernels = ctx->launches - l0;
+      ctx->launches = l0;
+      if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+      if (ce != cudaSuccess) return nimfm_fail(ctx, NIMFM_ERR_CUDA, "CD graph capture: %s", cudaGetErrorString(ce));
+      ce = cudaGraphInstantiate(&st->graph, g, 0);
+      cudaGraphDestroy(g);
+      if (ce != cudaSuccess) return nimfm_fail(ctx, NIMFM_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+      st->graphKey = key;
+    }
+    CK(cudaGraphLaunch(st->graph, ctx->stream));
+    ctx->launches += st->graphKernels;
+  }
+  CK(cudaGetLastError());
+  double h[8];
+  CK(cudaMemcpyAsync(ctx->hostScalars, fm->cdScal, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->hostScalars + 8, fm->b, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  memcpy(h, ctx->hostScalars, 64);
+  const double hb = ctx->hostScalars[8];
+  if (viol) *viol = h[0];
+  if (lossMean) *lossMean = h[1] / (double)n;
+  if (regOverN) {
+    // regularization (optimizer/utils.nim:56-59): norm(.,2)^2 == sqrt(sum sq)^2
+    const double nw = sqrt(h[4]), np = sqrt(h[5]);
+    const double reg = 0.5 * st->alpha0 * (hb * hb) + 0.5 * st->alpha * (nw * nw) + 0.5 * st->beta * (np * np);
+    *regOverN = reg / (double)n;
+  }
+  return NIMFM_OK;
+}
+
+// every kernel of one outer iteration, enqueued on ctx->stream (no synchronisation, no allocation)
+static int cd_enqueue_epoch(nimfm_ctx *ctx, CdState *st, nimfm_fm *fm, const nimfm_dataset *X, const nimfm_cd_cfg *cfg,
+                            int prox, double gammaRaw) {
   const int64_t n = X->n, d = X->d, dd = fm->dd();
   const double mu = loss_mu(cfg->loss);
   const int64_t nUpd = 1 + d + (int64_t)fm->nOrders * fm->k * dd;
@@ -538,27 +613,40 @@ static int cd_epoch_impl(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, c
   px.guardAll = prox != 0;
   px.gamma = gammaRaw * (double)n;                                   // pcd.nim:121
   px.k = fm->k;
-  if (prox == NIMFM_REG_SQUAREDL12 && st->chainCap < 3 * dd) {
-    cudaFree(st->chain);
-    st->chain = nullptr;
-    CK(cudaMalloc(&st->chain, (size_t)(3 * dd) * 8));
-    st->chainCap = 3 * dd;
-  }
   if (fm->fitLinear)                                                 // fitLinearCD (dummy features removed)
-    if ((rc = cd_sweep(ctx, st, X, fm, cfg, fm->w, 0, st->alpha, st->updAbs + 1, d, px))) return rc;
+    if ((rc = cd_sweep(ctx, st, X, fm, cfg, fm->w, 0, st->alpha, st->updAbs + 1, d, px, fm->Acache))) return rc;
   const nimfm_dataset *R = st->csr;
-  for (int o = 0; o < fm->nOrders; o++) {
-    const int deg = fm->degree - o;
-    px.Po = fm->Pcm + (int64_t)o * fm->k * dd;
-    for (int s = 0; s < fm->k; s++) {
-      double *Ps = fm->Pcm + ((int64_t)o * fm->k + s) * dd;
-      px.sIdx = s;
-      cd_cache_kernel<<<rowGrid, 256, 0, ctx->stream>>>(R->data, R->indices, R->indptr, n, d, fm->nAug, Ps, deg,
-                                                        fm->Acache, fm->degree + 1);
-      LAUNCHED(ctx);
-      double *upd = st->updAbs + 1 + d + ((int64_t)o * fm->k + s) * dd;
-      if ((rc = cd_sweep(ctx, st, X, fm, cfg, Ps, deg, st->beta, upd, dd, px))) return rc;
+  // The A-cache of sweep t+1 depends only on P[t+1] and X, not on what sweep t writes, so it is built
+  // on a second stream into the other half of a double buffer WHILE sweep t runs (a fork/join inside the
+  // captured graph): one kernel of every three leaves the critical path.
+  const int T = fm->nOrders * fm->k;
+  const int astride = fm->degree + 1;
+  const size_t aHalf = (size_t)std::max<int64_t>(n, 1) * astride;
+  cudaStream_t side = ctx->copyStream;
+  auto build_cache = [&](int t, cudaStream_t strm) {
+    const int o = t / fm->k;
+    double *Ps = fm->Pcm + (int64_t)t * dd;
+    cd_cache_kernel<<<rowGrid, 256, 0, strm>>>(R->data, R->indices, R->indptr, n, d, fm->nAug, Ps, fm->degree - o,
+                                               fm->Acache + (size_t)(t & 1) * aHalf, astride);
+    LAUNCHED(ctx);
+  };
+  if (T > 0) build_cache(0, ctx->stream);
+  for (int t = 0; t < T; t++) {
+    const int o = t / fm->k, sIdx = t - o * fm->k;
+    if (t + 1 < T) {
+      CK(cudaEventRecord(ctx->evCopied[0], ctx->stream));      // sweep t-1 (last user of the other half) is done
+      CK(cudaStreamWaitEvent(side, ctx->evCopied[0], 0));
+      build_cache(t + 1, side);
+      CK(cudaEventRecord(ctx->evCopied[1], side));
     }
+    px.Po = fm->Pcm + (int64_t)o * fm->k * dd;
+    px.sIdx = sIdx;
+    double *Ps = fm->Pcm + (int64_t)t * dd;
+    double *upd = st->updAbs + 1 + d + (int64_t)t * dd;
+    if ((rc = cd_sweep(ctx, st, X, fm, cfg, Ps, fm->degree - o, st->beta, upd, dd, px,
+                       fm->Acache + (size_t)(t & 1) * aHalf)))
+      return rc;
+    if (t + 1 < T) CK(cudaStreamWaitEvent(ctx->stream, ctx->evCopied[1], 0));
   }
   // viol (fixed-order sum of |update|), mean loss, regularization / n (cd.nim:177-184)
   int grid = (int)std::min<int64_t>(1024, std::max<int64_t>(1, (nUpd + 255) / 256));
@@ -572,21 +660,6 @@ static int cd_epoch_impl(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, c
   // keep the feature-major copy current so get_params / callbacks see this epoch's parameters
   cd_permute_kernel<<<ew_grid(ctx, fm->nP()), 256, 0, ctx->stream>>>(fm->P, fm->Pcm, fm->nOrders, fm->k, dd, 0);
   LAUNCHED(ctx);
-  CK(cudaGetLastError());
-  double h[8];
-  CK(cudaMemcpyAsync(ctx->hostScalars, fm->cdScal, 64, cudaMemcpyDeviceToHost, ctx->stream));
-  double hb = 0.0;
-  CK(cudaMemcpyAsync(&hb, fm->b, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  memcpy(h, ctx->hostScalars, 64);
-  if (viol) *viol = h[0];
-  if (lossMean) *lossMean = h[1] / (double)n;
-  if (regOverN) {
-    // regularization (optimizer/utils.nim:56-59): norm(.,2)^2 == sqrt(sum sq)^2
-    const double nw = sqrt(h[4]), np = sqrt(h[5]);
-    const double reg = 0.5 * st->alpha0 * (hb * hb) + 0.5 * st->alpha * (nw * nw) + 0.5 * st->beta * (np * np);
-    *regOverN = reg / (double)n;
-  }
   return NIMFM_OK;
 }
 
@@ -613,6 +686,7 @@ int32_t nimfm_fm_cd_end(nimfm_ctx *ctx, nimfm_fm *fm) {
     nimfm_dataset_free(ctx, st->csr);
     cudaFree(st->updAbs);
     cudaFree(st->chain);
+    if (st->graph) cudaGraphExecDestroy(st->graph);
     for (size_t i = 0; i < g_cd.size(); i++)
       if (g_cd[i].first == fm) {
         delete g_cd[i].second;
