@@ -302,7 +302,15 @@ class AdaGrad(_Base):
         # data parallel (distributed.init_comm): X is this rank's shard and miniBatchSize the GLOBAL
         # synchronous minibatch; the library all-reduces the per-minibatch deltas
         world = _dist.world()
-        local = _dist.local_batch(self.miniBatchSize, _dist.rank(), world)
+        mbs = self.miniBatchSize
+        if maxThreads is not None and mbs == 1:
+            # fit(..., maxThreads) is the reference's Hogwild variant (adagrad_multi.nim:39-115: T lock-free
+            # threads, every sample sees parameters up to ~T updates stale, results nondeterministic).  Its
+            # deterministic device analogue is the synchronous minibatch of T samples; maxThreads < 0 means
+            # "as many as the machine runs at once" there (2 x cores, sgd_multi.nim:13-18) and here (4096
+            # resident rows).
+            mbs = 4096 if maxThreads < 0 else max(1, int(maxThreads))
+        local = _dist.local_batch(mbs, _dist.rank(), world)
         if local < 1:
             raise ValueError("miniBatchSize is smaller than the number of ranks")
         cfg = _lib.AdagradCfg(self.loss.kind, self.loss.threshold, self.eta0, self.alpha0, self.alpha,

@@ -349,6 +349,21 @@ def test_adagrad_matches_oracle(oracle, degree, fit_lower, mb):
     np.testing.assert_allclose(opt.g_norm["P"], ref["state"]["gnP"], rtol=1e-8, atol=1e-14)
 
 
+def test_adagrad_max_threads_maps_to_synchronous_minibatch(oracle):
+    """fit(..., maxThreads=T) (the reference's Hogwild entry point) runs the deterministic synchronous
+    minibatch of T samples"""
+    n, d, k, degree = 96, 9, 4, 2
+    X = make_dense(n, d, 3, density=0.5, positive=False)
+    y = np.random.default_rng(2).standard_normal(n)
+    csr = CSR.from_dense(X)
+    P, w, _ = make_fm_params(d, degree, k, "explicit", True, seed=4)
+    ref = oracle.adagrad_fit(csr, y, P, w, 0.0, degree, "squared", max_iter=2, mini_batch_size=8)
+    fm = make_fm(degree, k, "explicit", True, True, P, w, 0.0)
+    opt = nf.newAdaGrad(maxIter=2, verbose=0, tol=0.0, shuffle=False)
+    opt.fit(csr_ds(csr), y, fm, maxThreads=8)
+    assert max_rel(fm.P, ref["P"]) <= 1e-8 and max_rel(fm.w, ref["w"]) <= 1e-8
+
+
 def test_adagrad_warm_start_equals_cold(oracle):
     """tests/test_adagrad.nim:58-90: 2 x (warm-started) epochs == one run of the total length"""
     n, d, k, degree = 40, 8, 4, 3
