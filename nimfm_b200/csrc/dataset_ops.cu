@@ -15,6 +15,14 @@
 
 namespace {
 
+struct DsGuard {   // owns a dataset under construction: freed on every early return, released on success
+  nimfm_ctx *ctx;
+  nimfm_dataset *ds;
+  DsGuard(nimfm_ctx *c, nimfm_dataset *d) : ctx(c), ds(d) {}
+  ~DsGuard() { if (ds) nimfm_dataset_free(ctx, ds); }
+  nimfm_dataset *release() { nimfm_dataset *d = ds; ds = nullptr; return d; }
+};
+
 struct DevBuf {   // frees on scope exit so early returns do not leak
   void *p = nullptr;
   ~DevBuf() { cudaFree(p); }
@@ -221,12 +229,13 @@ int32_t nimfm_dataset_take_rows(nimfm_ctx *ctx, const nimfm_dataset *in, const i
   CK(cudaMalloc(&len.p, ((size_t)nIdx + 1) * 8));
   if (nIdx) CK(cudaMemcpyAsync(rows.p, rowIdx, (size_t)nIdx * 8, cudaMemcpyHostToDevice, ctx->stream));
   nimfm_dataset *o = new nimfm_dataset();
+  DsGuard guard(ctx, o);
   o->kind = in->kind; o->n = nIdx; o->d = in->d; o->nFields = in->nFields;
   CK(cudaMalloc(&o->indptr, ((size_t)nIdx + 1) * 8));
   seg_len_kernel<<<grid_for(ctx, nIdx), 256, 0, ctx->stream>>>(in->indptr, rows.as<int64_t>(), nIdx, len.as<int64_t>());
   LAUNCHED(ctx);
   int rc = exclusive_scan(ctx, len.as<int64_t>(), o->indptr, nIdx + 1);
-  if (rc) { nimfm_dataset_free(ctx, o); return rc; }
+  if (rc) return rc;
   int64_t nnz = 0;
   CK(cudaMemcpy(&nnz, o->indptr + nIdx, 8, cudaMemcpyDeviceToHost));
   o->nnz = nnz;
@@ -240,8 +249,8 @@ int32_t nimfm_dataset_take_rows(nimfm_ctx *ctx, const nimfm_dataset *in, const i
         o->fields, in->y, o->y);
     LAUNCHED(ctx);
   }
-  if ((rc = finish_dataset(ctx, o, in))) { nimfm_dataset_free(ctx, o); return rc; }
-  *out = o;
+  if ((rc = finish_dataset(ctx, o, in))) return rc;
+  *out = guard.release();
   return NIMFM_OK;
 }
 
@@ -272,8 +281,9 @@ int32_t nimfm_dataset_slice_rows(nimfm_ctx *ctx, const nimfm_dataset *in, int64_
   int64_t nnz = 0;
   CK(cudaMemcpy(&nnz, pos.as<int64_t>() + nnzIn, 8, cudaMemcpyDeviceToHost));
   nimfm_dataset *o = new nimfm_dataset();
+  DsGuard guard(ctx, o);
   o->kind = NIMFM_DS_CSC; o->n = last - first + 1; o->d = d; o->nnz = nnz;
-  if ((rc = alloc_arrays(ctx, o, d, nnz, false))) { nimfm_dataset_free(ctx, o); return rc; }
+  if ((rc = alloc_arrays(ctx, o, d, nnz, false))) return rc;
   remap_ptr_kernel<<<grid_for(ctx, d + 1), 256, 0, ctx->stream>>>(in->indptr, d, pos.as<int64_t>(), o->indptr);
   LAUNCHED(ctx);
   if (nnzIn) {
@@ -286,8 +296,8 @@ int32_t nimfm_dataset_slice_rows(nimfm_ctx *ctx, const nimfm_dataset *in, int64_
     CK(cudaMalloc(&o->y, (size_t)o->n * 8));
     CK(cudaMemcpyAsync(o->y, in->y + first, (size_t)o->n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   }
-  if ((rc = finish_dataset(ctx, o, nullptr))) { nimfm_dataset_free(ctx, o); return rc; }
-  *out = o;
+  if ((rc = finish_dataset(ctx, o, nullptr))) return rc;
+  *out = guard.release();
   return NIMFM_OK;
 }
 
@@ -311,11 +321,12 @@ int32_t nimfm_dataset_vstack(nimfm_ctx *ctx, const nimfm_dataset *const *parts, 
   REQUIRE(n < (int64_t)2147483647, "stacked row count does not fit int32");
   CK(cudaSetDevice(ctx->device));
   nimfm_dataset *o = new nimfm_dataset();
+  DsGuard guard(ctx, o);
   o->kind = p0->kind; o->n = n; o->d = p0->d; o->nnz = nnz; o->nFields = p0->nFields;
   const bool csc = p0->kind == NIMFM_DS_CSC;
   const int64_t nSeg = csc ? o->d : n;
   int rc = alloc_arrays(ctx, o, nSeg, nnz, p0->fields != nullptr);
-  if (rc) { nimfm_dataset_free(ctx, o); return rc; }
+  if (rc) return rc;
   if (haveY && n > 0) CK(cudaMalloc(&o->y, (size_t)n * 8));
   if (!csc) {
     CK(cudaMemsetAsync(o->indptr, 0, 8, ctx->stream));
@@ -348,7 +359,7 @@ int32_t nimfm_dataset_vstack(nimfm_ctx *ctx, const nimfm_dataset *const *parts, 
                                                                    offs.as<int64_t>() + (size_t)i * d);
       LAUNCHED(ctx);
     }
-    if ((rc = exclusive_scan(ctx, acc.as<int64_t>(), o->indptr, d + 1))) { nimfm_dataset_free(ctx, o); return rc; }
+    if ((rc = exclusive_scan(ctx, acc.as<int64_t>(), o->indptr, d + 1))) return rc;
     int64_t rowBase = 0;
     for (int i = 0; i < nParts; i++) {
       const nimfm_dataset *p = parts[i];
@@ -363,8 +374,8 @@ int32_t nimfm_dataset_vstack(nimfm_ctx *ctx, const nimfm_dataset *const *parts, 
     }
     CK(cudaStreamSynchronize(ctx->stream));
   }
-  if ((rc = finish_dataset(ctx, o, p0))) { nimfm_dataset_free(ctx, o); return rc; }
-  *out = o;
+  if ((rc = finish_dataset(ctx, o, p0))) return rc;
+  *out = guard.release();
   return NIMFM_OK;
 }
 
@@ -380,10 +391,11 @@ int32_t nimfm_dataset_transpose(nimfm_ctx *ctx, const nimfm_dataset *in, nimfm_d
   const bool toCsc = in->kind == NIMFM_DS_CSR;
   const int64_t nsIn = toCsc ? in->n : in->d, nsOut = toCsc ? in->d : in->n, nnz = in->nnz;
   nimfm_dataset *o = new nimfm_dataset();
+  DsGuard guard(ctx, o);
   o->kind = toCsc ? NIMFM_DS_CSC : NIMFM_DS_CSR;
   o->n = in->n; o->d = in->d; o->nnz = nnz;
   int rc = alloc_arrays(ctx, o, nsOut, nnz, false);
-  if (rc) { nimfm_dataset_free(ctx, o); return rc; }
+  if (rc) return rc;
   DevBuf segOf, keysOut, permIn, permOut, tmp;
   const size_t n4 = (size_t)std::max<int64_t>(nnz, 4) * 4;
   CK(cudaMalloc(&segOf.p, n4));
@@ -413,7 +425,7 @@ int32_t nimfm_dataset_transpose(nimfm_ctx *ctx, const nimfm_dataset *in, nimfm_d
     CK(cudaMemcpyAsync(o->y, in->y, (size_t)o->n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   }
   CK(cudaStreamSynchronize(ctx->stream));
-  if ((rc = finish_dataset(ctx, o, nullptr))) { nimfm_dataset_free(ctx, o); return rc; }
+  if ((rc = finish_dataset(ctx, o, nullptr))) return rc;
   if (o->kind == NIMFM_DS_CSR && nnz > 0) {
     // a CSR made on the device has no host copy to sample: find the hot columns from the CSC side
     // (column length >= n/16), the 16 longest
@@ -430,9 +442,9 @@ int32_t nimfm_dataset_transpose(nimfm_ctx *ctx, const nimfm_dataset *in, nimfm_d
     std::vector<int32_t> hot;
     for (size_t i = 0; i < cand.size() && i < 16; i++) hot.push_back((int32_t)cand[i].second);
     o->nHot = (int)hot.size();
-    if ((rc = nimfm_upload_hot(ctx, hot, o->d, &o->hotSlot, &o->hotList))) { nimfm_dataset_free(ctx, o); return rc; }
+    if ((rc = nimfm_upload_hot(ctx, hot, o->d, &o->hotSlot, &o->hotList))) return rc;
   }
-  *out = o;
+  *out = guard.release();
   return NIMFM_OK;
 }
 
