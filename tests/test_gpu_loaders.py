@@ -130,3 +130,38 @@ def test_user_item_rating_file(oracle, tmp_path):
     assert ds.nFeatures == (users.max() - 1 + 1) + (items.max() - 1 + 1)
     csc, _ = nf.loadUserItemRatingFile(p, kind="csc")
     same(csc, oracle.csr_to_csc(ref))
+
+
+def test_cli_train_dump_test_roundtrip(oracle, tmp_path, capsys):
+    """`nimfm train` / `nimfm test` (src/nimfm.nim:72-135) on the device path: svmlight in, CD fit, model
+    dump, a second process-level step reloading the model and writing the same predictions"""
+    from nimfm_b200.__main__ import main
+    rng = np.random.default_rng(5)
+    X = make_dense(90, 12, 4, density=0.5, positive=False)
+    csr = CSR.from_dense(X)
+    wtrue = rng.standard_normal(12)
+    y = X @ wtrue + 0.1 * rng.standard_normal(90)
+    tr, te = str(tmp_path / "tr.svm"), str(tmp_path / "te.svm")
+    write_svm(tr, csr, y)
+    write_svm(te, csr, y)
+    model, p1, p2 = str(tmp_path / "m.txt"), str(tmp_path / "p1.txt"), str(tmp_path / "p2.txt")
+    main(["train", "--task", "r", "--train", tr, "--test", te, "--degree", "2", "--nComponents", "3", "--solver", "cd",
+          "--maxIter", "5", "--dump", model, "--predict", p1, "--nFeatures", "12", "--verbose", "0"])
+    out = capsys.readouterr().out
+    assert "Test RMSE: " in out
+    rmse = float(out.split("Test RMSE: ")[1].split()[0])
+    main(["test", "--task", "r", "--test", te, "--load", model, "--predict", p2, "--nFeatures", "12", "--verbose", "0"])
+    out2 = capsys.readouterr().out
+    assert abs(float(out2.split("Test RMSE: ")[1].split()[0]) - rmse) < 1e-12
+    a, b = np.loadtxt(p1), np.loadtxt(p2)
+    assert np.array_equal(a, b) and len(a) == 90
+    # the CLI's fit equals the library's (CD, squared loss, the CLI's defaults) -- and the oracle's
+    fm = nf.FactorizationMachine.load(model, False)
+    csc = oracle.csr_to_csc(csr)
+    rngP = np.random.default_rng(1).standard_normal((1, 3, 12)) * 0.1     # init() of the mirror: seed=randomState, scale
+    ref = oracle.cd_fit(csc, y, rngP, np.zeros(12), 0.0, 2, "squared", max_iter=5, alpha0=1e-7, alpha=1e-5, beta=1e-3,
+                        tol=1e-5)
+    np.testing.assert_allclose(fm.P, ref["P"], rtol=1e-8, atol=1e-12)
+    for solver in ("sgd", "adagrad"):
+        main(["train", "--task", "c", "--train", tr, "--solver", solver, "--loss", "logistic", "--maxIter", "2",
+              "--nComponents", "2", "--verbose", "0"])
