@@ -112,6 +112,11 @@ int32_t nimfm_load_svmlight(nimfm_ctx *ctx, const char *path, int64_t nFeatures,
 int32_t nimfm_load_ffm(nimfm_ctx *ctx, const char *path, int64_t nFeatures, int64_t nFields,
                        nimfm_dataset **out);
 int32_t nimfm_load_user_item_rating(nimfm_ctx *ctx, const char *path, int32_t asCsc, nimfm_dataset **out);
+/* STREAMCSR / STREAMCSC binary files (tensor/sparse_stream.nim:3-33; written by convertSVMLightFile /
+ * transposeFile, dataset.nim:1017-1200) loaded WHOLE into a device CSR / CSC dataset (newStreamCSRDataset /
+ * newStreamCSCDataset, dataset.nim:170-179, without the window cache); pathY (nullable) is the raw float64
+ * label file of loadStreamLabel (dataset.nim:995-1014). */
+int32_t nimfm_load_stream(nimfm_ctx *ctx, const char *pathX, const char *pathY, nimfm_dataset **out);
 int32_t nimfm_dataset_get_targets(nimfm_ctx *ctx, const nimfm_dataset *ds, double *y);
 
 /* ---------------------------------------------------------------- FM model state

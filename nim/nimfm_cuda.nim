@@ -90,6 +90,7 @@ proc nimfm_load_ffm(ctx: Ctx, path: cstring, nFeatures, nFields: int64,
                     outDs: ptr DeviceDataset): int32             # loadFFMFile, dataset.nim:768-790
 proc nimfm_load_user_item_rating(ctx: Ctx, path: cstring, asCsc: int32,
                                  outDs: ptr DeviceDataset): int32  # loadUserItemRatingFile, dataset.nim:840-990
+proc nimfm_load_stream(ctx: Ctx, pathX, pathY: cstring, outDs: ptr DeviceDataset): int32   # newStreamCSR/CSCDataset
 proc nimfm_dataset_get_targets(ctx: Ctx, ds: DeviceDataset, y: ptr cdouble): int32
 proc nimfm_fm_create(ctx: Ctx, degree, nComponents, nOrders, nAugments: int32, nFeatures: int64,
                      fitLinear, fitIntercept: int32, outFm: ptr DeviceFM): int32

@@ -4,8 +4,9 @@ include/nimfm_cuda.h); this package is the thin host mirror a Nim program would 
 nim/nimfm_cuda.nim.  There is no CPU fallback."""
 from . import _lib
 from ._lib import NimfmCudaError
-from .dataset import (CSCDataset, CSRDataset, CSRFieldDataset, dumpFFMFile, dumpSVMLightFile, loadFFMFile,
-                      loadSVMLightFile, loadUserItemRatingFile, newCSCDataset, newCSRDataset,
+from .dataset import (CSCDataset, CSRDataset, CSRFieldDataset, convertSVMLightFile, dumpFFMFile,
+                      dumpSVMLightFile, loadFFMFile, loadStreamLabel, loadSVMLightFile,
+                      loadUserItemRatingFile, newStreamCSCDataset, newStreamCSRDataset, transposeFile, newCSCDataset, newCSRDataset,
                       newCSRFieldDataset, shuffle, toCSCDataset, toCSRDataset, vstack)
 from .loss import (Huber, Logistic, Squared, SquaredHinge, newHuber, newLogistic, newSquared,
                    newSquaredHinge)

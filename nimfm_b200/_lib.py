@@ -82,6 +82,7 @@ SYMBOLS = {
     "nimfm_load_svmlight": (c_i32, [VP, C.c_char_p, c_i64, c_i32, PVP]),
     "nimfm_load_ffm": (c_i32, [VP, C.c_char_p, c_i64, c_i64, PVP]),
     "nimfm_load_user_item_rating": (c_i32, [VP, C.c_char_p, c_i32, PVP]),
+    "nimfm_load_stream": (c_i32, [VP, C.c_char_p, C.c_char_p, PVP]),
     "nimfm_dataset_get_targets": (c_i32, [VP, VP, VP]),
     "nimfm_fm_create": (c_i32, [VP, c_i32, c_i32, c_i32, c_i32, c_i64, c_i32, c_i32, PVP]),
     "nimfm_fm_set_params": (c_i32, [VP, VP, VP, VP, c_dbl, VP]),

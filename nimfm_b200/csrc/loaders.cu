@@ -185,6 +185,36 @@ int finish_upload(nimfm_ctx *ctx, int64_t n, int64_t d, std::vector<double> &dat
 
 }  // namespace
 
+// ------------------------------------------------------------------ STREAMCSR / STREAMCSC binary files
+// (tensor/sparse_stream.nim:3-33, written by convertSVMLightFile / transposeFile, dataset.nim:1017-1200):
+//   magic "STREAMCSR" | "STREAMCSC" (9 bytes), header {nRows, nCols, nnz: int64; max, min: float64},
+//   then per row (CSR) / column (CSC): count int64, count x {val float64, id int64}.
+// The reference reads them through a window cache because they may exceed host memory; a B200 holds
+// 180 GB, so the file is loaded whole: the host only hops over the counts (O(segments)), the raw
+// payload is uploaded as it is and de-interleaved on the device.
+namespace {
+
+__global__ void stream_deinterleave_kernel(const unsigned char *payload, const int64_t *segByteOff,
+                                           const int64_t *indptr, int64_t nSeg, int64_t extent, double *data,
+                                           int32_t *idx, int *bad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nWarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t sgm = warp; sgm < nSeg; sgm += nWarps) {
+    const unsigned char *rec = payload + segByteOff[sgm];
+    const int64_t b = indptr[sgm], z = indptr[sgm + 1] - b;
+    for (int64_t t = lane; t < z; t += 32) {
+      const double v = *reinterpret_cast<const double *>(rec + 16 * t);
+      const int64_t id = *reinterpret_cast<const int64_t *>(rec + 16 * t + 8);
+      if (id < 0 || id >= extent) *bad = 1;
+      data[b + t] = v;
+      idx[b + t] = (int32_t)id;
+    }
+  }
+}
+
+}  // namespace
+
 extern "C" {
 
 int32_t nimfm_load_svmlight(nimfm_ctx *ctx, const char *path, int64_t nFeatures, int32_t asCsc, nimfm_dataset **out) {
@@ -275,6 +305,105 @@ int32_t nimfm_load_user_item_rating(nimfm_ctx *ctx, const char *path, int32_t as
     }
   for (int64_t i = 0; i <= n; i++) indptr[i] = 2 * i;
   return finish_upload(ctx, n, n > 0 ? nUsers + nItems : 0, data, indices, indptr, nullptr, 0, y, asCsc, out);
+}
+
+int32_t nimfm_load_stream(nimfm_ctx *ctx, const char *pathX, const char *pathY, nimfm_dataset **out) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  REQUIRE(out != nullptr && pathX != nullptr, "NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  Mapped m;
+  m.fd = open(pathX, O_RDONLY);
+  if (m.fd < 0) return nimfm_fail(ctx, NIMFM_ERR_INVALID, "%s cannot be opened.", pathX);      // sparse_stream.nim:103-104
+  struct stat st;
+  if (fstat(m.fd, &st) != 0) return nimfm_fail(ctx, NIMFM_ERR_INVALID, "cannot stat %s", pathX);
+  m.n = (size_t)st.st_size;
+  REQUIRE(m.n >= 49, "%s is not a StreamCSR / StreamCSC file.", pathX);
+  void *mp = mmap(nullptr, m.n, PROT_READ, MAP_PRIVATE, m.fd, 0);
+  if (mp == MAP_FAILED) { m.n = 0; return nimfm_fail(ctx, NIMFM_ERR_INVALID, "cannot map %s", pathX); }
+  m.p = static_cast<const char *>(mp);
+  const bool isCsr = memcmp(m.p, "STREAMCSR", 9) == 0, isCsc = memcmp(m.p, "STREAMCSC", 9) == 0;
+  REQUIRE(isCsr || isCsc, "%s is not a StreamCSR / StreamCSC file.", pathX);                    // :109-110,142-143
+  REQUIRE(!(m.n >= 14 && memcmp(m.p + 9, "FIELD", 5) == 0), "field stream files are not supported");
+  int64_t hdr[3];
+  memcpy(hdr, m.p + 9, 24);
+  const int64_t nRows = hdr[0], nCols = hdr[1], nnz = hdr[2];
+  REQUIRE(nRows >= 0 && nCols >= 0 && nnz >= 0, "corrupt header in %s", pathX);
+  const int64_t nSeg = isCsr ? nRows : nCols, extent = isCsr ? nCols : nRows;
+  REQUIRE(extent < (int64_t)2147483647, "index extent %lld does not fit int32", (long long)extent);
+  const size_t payloadBytes = m.n - 49;
+  std::vector<int64_t> segOff((size_t)nSeg), indptr((size_t)nSeg + 1, 0);
+  int64_t off = 0, maxSeg = 0;
+  for (int64_t sgm = 0; sgm < nSeg; sgm++) {
+    REQUIRE((size_t)off + 8 <= payloadBytes, "%s is truncated (segment %lld)", pathX, (long long)sgm);
+    int64_t cnt;
+    memcpy(&cnt, m.p + 49 + off, 8);
+    REQUIRE(cnt >= 0 && (size_t)off + 8 + 16 * (size_t)cnt <= payloadBytes, "%s is truncated (segment %lld)", pathX,
+            (long long)sgm);
+    segOff[(size_t)sgm] = off + 8;
+    indptr[(size_t)sgm + 1] = indptr[(size_t)sgm] + cnt;
+    maxSeg = std::max(maxSeg, cnt);
+    off += 8 + 16 * cnt;
+  }
+  REQUIRE(indptr[(size_t)nSeg] == nnz, "%s: header nnz %lld != %lld elements found", pathX, (long long)nnz,
+          (long long)indptr[(size_t)nSeg]);
+  nimfm_dataset *ds = new nimfm_dataset();
+  ds->kind = isCsr ? NIMFM_DS_CSR : NIMFM_DS_CSC;
+  ds->n = nRows; ds->d = nCols; ds->nnz = nnz; ds->maxSegNnz = maxSeg;
+  auto fail = [&](int rc) { nimfm_dataset_free(ctx, ds); return rc; };
+  unsigned char *dPayload = nullptr;
+  int64_t *dSegOff = nullptr;
+  int *dBad = nullptr;
+  cudaError_t ce = cudaSuccess;
+  auto ck = [&](cudaError_t e) { if (ce == cudaSuccess) ce = e; };
+  ck(cudaMalloc(&dPayload, std::max<size_t>(payloadBytes, 16)));
+  ck(cudaMalloc(&dSegOff, (size_t)std::max<int64_t>(nSeg, 1) * 8));
+  ck(cudaMalloc(&dBad, sizeof(int)));
+  ck(cudaMalloc(&ds->indptr, ((size_t)nSeg + 1) * 8));
+  ck(cudaMalloc(&ds->data, (size_t)std::max<int64_t>(nnz, 2) * 8));
+  ck(cudaMalloc(&ds->indices, (size_t)std::max<int64_t>(nnz, 4) * 4));
+  if (ce == cudaSuccess) {
+    ck(cudaMemcpyAsync(dPayload, m.p + 49, payloadBytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (nSeg) ck(cudaMemcpyAsync(dSegOff, segOff.data(), (size_t)nSeg * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ck(cudaMemcpyAsync(ds->indptr, indptr.data(), ((size_t)nSeg + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ck(cudaMemsetAsync(dBad, 0, sizeof(int), ctx->stream));
+    if (nSeg > 0 && nnz > 0) {
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nSeg * 32 + 255) / 256, (int64_t)ctx->numSMs * 16));
+      stream_deinterleave_kernel<<<grid, 256, 0, ctx->stream>>>(dPayload, dSegOff, ds->indptr, nSeg, extent, ds->data,
+                                                                ds->indices, dBad);
+      LAUNCHED(ctx);
+    }
+    int hbad = 0;
+    ck(cudaMemcpyAsync(&hbad, dBad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ck(cudaStreamSynchronize(ctx->stream));
+    ck(cudaGetLastError());
+    if (ce == cudaSuccess && hbad) {
+      cudaFree(dPayload); cudaFree(dSegOff); cudaFree(dBad);
+      nimfm_dataset_free(ctx, ds);
+      return nimfm_fail(ctx, NIMFM_ERR_INVALID, "%s: element id out of range [0,%lld)", pathX, (long long)extent);
+    }
+  }
+  cudaFree(dPayload); cudaFree(dSegOff); cudaFree(dBad);
+  if (ce != cudaSuccess) return fail(nimfm_fail(ctx, NIMFM_ERR_CUDA, "nimfm_load_stream: %s", cudaGetErrorString(ce)));
+  if (ds->kind == NIMFM_DS_CSR) {   // no hot columns known for a stream: all cold (bookkeeping only)
+    std::vector<int32_t> hot;
+    int rc = nimfm_upload_hot(ctx, hot, ds->d, &ds->hotSlot, &ds->hotList);
+    if (rc) return fail(rc);
+  }
+  if (pathY && pathY[0]) {            // loadStreamLabel (dataset.nim:995-1014): raw float64 targets
+    Mapped my;
+    my.fd = open(pathY, O_RDONLY);
+    if (my.fd < 0) return fail(nimfm_fail(ctx, NIMFM_ERR_INVALID, "%s cannot be opened.", pathY));
+    struct stat sy;
+    if (fstat(my.fd, &sy) != 0 || (int64_t)sy.st_size < nRows * 8)
+      return fail(nimfm_fail(ctx, NIMFM_ERR_INVALID, "%s holds fewer than %lld labels", pathY, (long long)nRows));
+    std::vector<double> y((size_t)nRows);
+    if (nRows && pread(my.fd, y.data(), (size_t)nRows * 8, 0) != (ssize_t)(nRows * 8))
+      return fail(nimfm_fail(ctx, NIMFM_ERR_INVALID, "cannot read %s", pathY));
+    int rc = nRows ? nimfm_dataset_set_targets(ctx, ds, y.data()) : NIMFM_OK;
+    if (rc) return fail(rc);
+  }
+  *out = ds;
+  return NIMFM_OK;
 }
 
 int32_t nimfm_dataset_get_targets(nimfm_ctx *ctx, const nimfm_dataset *ds, double *y) {

@@ -305,3 +305,95 @@ def dumpFFMFile(f, X, y):
                 f" {int(X.fields[q]) + 1}:{int(X.indices[q]) + 1}:{_num(X.data[q])}" for q in range(s, e)))
             if i + 1 != X.nSamples:
                 out.write("\n")
+
+
+# ---------------------------------------------------------------- binary stream files (dataset.nim:995-1200)
+_MAGIC = {"csr": b"STREAMCSR", "csc": b"STREAMCSC"}
+
+
+def _write_stream(f, kind, nRows, nCols, data, indices, indptr):
+    """magic | header {nRows, nCols, nnz: int64; max, min: float64} | per segment: count int64,
+    count x {val float64, id int64}  (tensor/sparse_stream.nim:3-33)"""
+    nnz = len(data)
+    mx = float(np.max(data)) if nnz else float(np.finfo(np.float64).min)      # low(float64) / high(float64)
+    mn = float(np.min(data)) if nnz else float(np.finfo(np.float64).max)
+    rec = np.zeros(nnz, dtype=[("val", "<f8"), ("id", "<i8")])
+    rec["val"], rec["id"] = data, indices
+    with open(os.path.expanduser(str(f)), "wb") as out:
+        out.write(_MAGIC[kind])
+        out.write(np.array([nRows, nCols, nnz], dtype="<i8").tobytes())
+        out.write(np.array([mx, mn], dtype="<f8").tobytes())
+        for s in range(len(indptr) - 1):
+            a, b = int(indptr[s]), int(indptr[s + 1])
+            out.write(np.int64(b - a).tobytes())
+            out.write(rec[a:b].tobytes())
+
+
+def convertSVMLightFile(fIn, fOutX, fOutY):
+    """convertSVMLightFile (dataset.nim:1017-1097): svmlight text -> STREAMCSR binary (0-based ids,
+    nFeatures = maxIndex - minIndex + 1 with minIndex starting at 1) + raw float64 labels"""
+    data, indices, indptr, y = [], [], [0], []
+    minIndex, maxIndex = 1, 0
+    for line in open(os.path.expanduser(str(fIn))).read().split("\n"):
+        tok = line.replace(":", " ").split()
+        if not tok:
+            continue
+        y.append(float(tok[0]))
+        for a in range(1, len(tok), 2):
+            j = int(tok[a])
+            minIndex, maxIndex = min(j, minIndex), max(j, maxIndex)
+            indices.append(j)
+            data.append(float(tok[a + 1]))
+        indptr.append(len(indices))
+    if minIndex < 0:
+        raise ValueError("Negative index is included.")
+    idx = np.array(indices, np.int64) - minIndex
+    _write_stream(fOutX, "csr", len(y), maxIndex - minIndex + 1, np.array(data, np.float64), idx, indptr)
+    np.array(y, dtype="<f8").tofile(os.path.expanduser(str(fOutY)))
+
+
+def transposeFile(fIn, fOut, cacheSize=200):
+    """transposeFile (dataset.nim:1100-1200): STREAMCSR <-> STREAMCSC (the header keeps [nRows, nCols]);
+    done with the library's stable device transpose instead of the reference's windowed file passes"""
+    X, _ = _load_stream(fIn, None)
+    T = _transposed(X, CSCDataset if isinstance(X, CSRDataset) else CSRDataset)
+    kind = "csc" if isinstance(T, CSCDataset) else "csr"
+    _write_stream(fOut, kind, T.nSamples, T.nFeatures, T.data, T.indices, T.indptr)
+
+
+def _load_stream(fX, fY):
+    h = C.c_void_p()
+    _lib.check(_lib.load().nimfm_load_stream(_lib.ctx(), _path(fX), None if fY is None else _path(fY), C.byref(h)))
+    probe = BaseDataset.__new__(BaseDataset)
+    probe._handle = h
+    cls = CSCDataset if BaseDataset.info(probe)["kind"] == _lib.DS_CSC else CSRDataset
+    probe._handle = None
+    out = _adopt(h, cls, None)
+    y = None
+    if fY is not None:
+        y = np.zeros(out.nSamples)
+        _lib.check(_lib.load().nimfm_dataset_get_targets(_lib.ctx(), h, _lib.ptr(y)))
+    return out, y
+
+
+def newStreamCSRDataset(f, cacheSize=200):
+    """newStreamCSRDataset (dataset.nim:170-173).  The reference windows the file through a cacheSize-MB
+    cache; here the whole matrix becomes resident in HBM (cacheSize is accepted and ignored)."""
+    X, _ = _load_stream(f, None)
+    if not isinstance(X, CSRDataset):
+        raise IOError(f"{f} is not a StreamCSR file.")
+    return X
+
+
+def newStreamCSCDataset(f, cacheSize=200):
+    """newStreamCSCDataset (dataset.nim:176-179)"""
+    X, _ = _load_stream(f, None)
+    if not isinstance(X, CSCDataset):
+        raise IOError(f"{f} is not a StreamCSC file.")
+    return X
+
+
+def loadStreamLabel(fIn, nSamples=None):
+    """loadStreamLabel (dataset.nim:995-1014): raw little-endian float64 targets"""
+    y = np.fromfile(os.path.expanduser(str(fIn)), dtype="<f8")
+    return y if nSamples is None else y[:nSamples].copy()

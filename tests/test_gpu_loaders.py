@@ -165,3 +165,46 @@ def test_cli_train_dump_test_roundtrip(oracle, tmp_path, capsys):
     for solver in ("sgd", "adagrad"):
         main(["train", "--task", "c", "--train", tr, "--solver", solver, "--loss", "logistic", "--maxIter", "2",
               "--nComponents", "2", "--verbose", "0"])
+
+
+def test_stream_binary_files(oracle, tmp_path):
+    """STREAMCSR / STREAMCSC binary files (tensor/sparse_stream.nim:3-33; convertSVMLightFile /
+    transposeFile / loadStreamLabel, dataset.nim:995-1200): converted from svmlight text, loaded whole
+    into device datasets (the payload is de-interleaved on the device), bit-exact with the text loader"""
+    X = make_dense(73, 21, 8, density=0.25, positive=False)
+    X[7] = 0.0
+    csr = CSR.from_dense(X)
+    y = np.random.default_rng(2).standard_normal(73)
+    txt, fx, fy, fxT = (str(tmp_path / n) for n in ("a.svm", "a.bin", "a.lab", "aT.bin"))
+    write_svm(txt, csr, y)
+    nf.convertSVMLightFile(txt, fx, fy)
+    raw = open(fx, "rb").read()
+    assert raw[:9] == b"STREAMCSR"
+    hdr = np.frombuffer(raw[9:33], dtype="<i8")
+    ref, yref = oracle.load_svmlight(txt)
+    assert hdr[0] == 73 and hdr[2] == len(ref.data)
+    ds = nf.newStreamCSRDataset(fx)
+    assert np.array_equal(ds.indptr, ref.indptr) and np.array_equal(ds.data, ref.data)
+    # both conventions subtract the minimum index (1 here), so the ids agree with the text loader
+    assert np.array_equal(ds.indices, ref.indices)
+    assert np.array_equal(nf.loadStreamLabel(fy), y) and np.array_equal(nf.loadStreamLabel(fy, 10), y[:10])
+    nf.transposeFile(fx, fxT)
+    assert open(fxT, "rb").read()[:9] == b"STREAMCSC"
+    csc = nf.newStreamCSCDataset(fxT)
+    cref = oracle.csr_to_csc(CSR(ds.data, ds.indices, ds.indptr, ds.nSamples, ds.nFeatures))
+    assert np.array_equal(csc.indptr, cref.indptr) and np.array_equal(csc.indices, cref.indices)
+    assert np.array_equal(csc.data, cref.data) and csc.shape == ds.shape
+    with pytest.raises(IOError):
+        nf.newStreamCSCDataset(fx)                         # wrong magic for the requested kind
+    open(str(tmp_path / "bad.bin"), "wb").write(raw[:200])
+    with pytest.raises(ValueError, match="truncated"):
+        nf.newStreamCSRDataset(str(tmp_path / "bad.bin"))
+    # the stream dataset drives the same kernels
+    rng = np.random.default_rng(3)
+    fm = nf.newFactorizationMachine(nf.regression, degree=2, nComponents=3, warmStart=True)
+    fm.P, fm.w, fm.intercept, fm.isInitialized = rng.standard_normal((1, 3, ds.nFeatures)) * 0.1, np.zeros(ds.nFeatures), 0.0, True
+    want = oracle.fm_decision_function(CSR(ds.data, ds.indices, ds.indptr, ds.nSamples, ds.nFeatures), fm.P, fm.w, 0.0, 2)
+    got = fm.decisionFunction(ds)
+    # (rows with one nonzero have an exactly-zero ANOVA term on the CPU; FMA contraction leaves ~1e-19 there)
+    from helpers import max_rel
+    assert max_rel(got, want) < 1e-10
