@@ -52,6 +52,7 @@ struct __align__(16) FfmMeta {
 };
 
 #include "ffm_pairs.cuh"
+#include "ffm_tma.cuh"
 
 static size_t ffm_smem_bytes(int CH, int SB8, int nFields) {
   size_t b = (((size_t)CH * SB8 * 8 + 15) & ~(size_t)15) + (size_t)CH * sizeof(FfmMeta) + (size_t)CH * 4 +
@@ -256,6 +257,22 @@ static FfmKernel ffm_pairs_block_pick(int k, int mode) {
   }
 }
 
+template <int KT>
+static FfmKernel ffm_tma_mode(int mode) {
+  return mode == FFM_PREDICT ? ffm_rows_tma_kernel<FFM_PAIRS_PREDICT, KT, FfmArgs>
+         : mode == FFM_GRAD  ? ffm_rows_tma_kernel<FFM_PAIRS_GRAD, KT, FfmArgs>
+                             : ffm_rows_tma_kernel<FFM_PAIRS_ADAGRAD, KT, FfmArgs>;
+}
+static FfmKernel ffm_tma_pick(int k, int mode) {
+  switch (k) {
+    case 4: return ffm_tma_mode<4>(mode);
+    case 8: return ffm_tma_mode<8>(mode);
+    case 16: return ffm_tma_mode<16>(mode);
+    case 32: return ffm_tma_mode<32>(mode);
+    default: return nullptr;
+  }
+}
+
 // does any row hold two nonzeros of one field?  (computed once per dataset, on the device)
 static int ffm_has_field_dups(nimfm_ctx *ctx, const nimfm_dataset *X, bool *dups) {
   if (X->fieldDup < 0) {
@@ -303,6 +320,29 @@ static int ffm_plan_mode(nimfm_ctx *ctx, const nimfm_ffm *m, const nimfm_dataset
   // rows up to FFM_PAIRS_TABLE_MAXZ nonzeros: the block-per-row form of the pair loop (grad 15.1 -> 22.7 M
   // rows/s on C5); NIMFM_FFM_KERNEL=pairwarp keeps the warp-per-row form for A/B
   const bool wantPairWarp = env && !strcmp(env, "pairwarp");
+  // NIMFM_FFM_KERNEL=tma: the TMA-staged form (ffm_tma.cuh) when two stages of the longest row fit
+  const bool wantTma = env && !strcmp(env, "tma");
+  if (pk && table && wantTma) {
+    const int SB8 = (int)(m->nFields * m->k);
+    const size_t smem = ffm_tma_smem(CH, SB8);
+    if (smem + 1024 <= (size_t)ctx->smemOptin && (SB8 & 1) == 0) {
+      FfmKernel tk = ffm_tma_pick(m->k, mode);
+      CK(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int occ = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tk, FFM_TMA_THREADS, smem));
+      if (occ >= 1) {
+        int64_t grid = std::min<int64_t>(nRows, (int64_t)occ * ctx->numSMs);
+        if (grid < 1) grid = 1;
+        pl->CH = CH;
+        pl->grid = (int)grid;
+        pl->smem = smem;
+        pl->kern = tk;
+        pl->block = FFM_TMA_THREADS;
+        pl->partialRows = grid;
+        return NIMFM_OK;
+      }
+    }
+  }
   if (pk && table && !wantPairWarp) {
     FfmKernel bk = ffm_pairs_block_pick(m->k, mode);
     const int block = 256;

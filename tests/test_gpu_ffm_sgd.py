@@ -211,10 +211,10 @@ def ragged_field_csr(n, d, n_fields, seed, max_nnz):
 
 @pytest.mark.parametrize("k", [4, 8, 16, 32])
 @pytest.mark.parametrize("max_nnz", [9, 64, 90])
-@pytest.mark.parametrize("variant", ["default", "pairwarp", "block"])
+@pytest.mark.parametrize("variant", ["default", "pairwarp", "block", "tma"])
 def test_ffm_kernel_variants_ragged(oracle, monkeypatch, k, max_nnz, variant):
     """every compiled rank instance x the three kernel forms (pair-block with the shared pair table for
-    rows <= 64 nonzeros, warp-per-row pair cursor beyond, staged block-per-row fallback) on ragged rows
+    rows <= 64 nonzeros, warp-per-row pair cursor beyond, staged block-per-row fallback, TMA-staged) on ragged rows
     with empty rows and repeated fields: forward + gradient equal the oracle"""
     if variant == "block" and max_nnz * 6 * k * 8 > 200_000:
         pytest.skip("staged block kernel: slices do not fit shared memory")
@@ -236,7 +236,7 @@ def test_ffm_kernel_variants_ragged(oracle, monkeypatch, k, max_nnz, variant):
 
 
 @pytest.mark.parametrize("mb", [1, 16, 200])
-@pytest.mark.parametrize("variant", ["default", "pairwarp", "block"])
+@pytest.mark.parametrize("variant", ["default", "pairwarp", "block", "tma"])
 def test_ffm_adagrad_one_feature_per_field(oracle, monkeypatch, mb, variant):
     """C5 row shape (one feature per field): the AdaGrad route runs on the pair kernels, which square
     per-pair contributions -- equal to the oracle's per-sample squares; the staged kernel must agree"""
