@@ -703,7 +703,10 @@ int32_t nimfm_ffm_adagrad_epoch(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_datase
     FfmArgs a;
     ffm_fill_args(a, m, X);
     a.rowBegin = start; a.nRows = cnt; a.rowIdx = rows;
-    a.gP = dGsP; a.gw = dGsw; a.dGnP = dGnP; a.dGnw = dGnw;
+    // one rank: accumulate straight into g_sum / g_norm (see nimfm_fm_adagrad_epoch)
+    const bool direct = ctx->nranks == 1;
+    a.gP = direct ? m->gsP : dGsP; a.gw = direct ? m->gsw : dGsw;
+    a.dGnP = direct ? m->gnP : dGnP; a.dGnw = direct ? m->gnw : dGnw;
     a.partials = ctx->partials;
     a.loss = cfg->loss; a.thr = cfg->huberThreshold;
     a.gsP = m->gsP; a.gnP = m->gnP; a.gsw = m->gsw; a.gnw = m->gnw; a.adaScal = m->adaScal;
@@ -718,9 +721,13 @@ int32_t nimfm_ffm_adagrad_epoch(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_datase
     adagrad_scalar_kernel<<<1, 1, 0, ctx->stream>>>(m->b, m->adaScal, part, violPart, ctx->scalars, m->fitIntercept,
                                                     cfg->eta0, tIt, cfg->alpha0, first);
     LAUNCHED(ctx);
-    adagrad_apply_kernel<<<ew_grid(ctx, nP), 256, 0, ctx->stream>>>(m->gsP, m->gnP, dGsP, dGnP, nP, m->gsw, m->gnw, dGsw,
-                                                                   dGnw, d, m->fitLinear, cntF, d);
-    LAUNCHED(ctx);
+    if (direct) {
+      CK(cudaMemsetAsync(cntF, 0, (size_t)d * 8, ctx->stream));
+    } else {
+      adagrad_apply_kernel<<<ew_grid(ctx, nP), 256, 0, ctx->stream>>>(m->gsP, m->gnP, dGsP, dGnP, nP, m->gsw, m->gnw,
+                                                                     dGsw, dGnw, d, m->fitLinear, cntF, d);
+      LAUNCHED(ctx);
+    }
     *it += cnt * (int64_t)ctx->nranks;
   }
   CK(cudaGetLastError());

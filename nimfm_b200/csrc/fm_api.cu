@@ -699,10 +699,13 @@ int32_t nimfm_fm_adagrad_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset
     a.rowBegin = start;
     a.nRows = cnt;
     a.rowIdx = rows;
-    a.gP = dGsP;
-    a.gw = dGsw;
-    a.dGnP = dGnP;
-    a.dGnw = dGnw;
+    // one rank: the gradients and their squares go straight into g_sum / g_norm (nothing reads them before
+    // the next minibatch's refresh), so the delta block and the apply pass are only needed for the all-reduce
+    const bool direct = ctx->nranks == 1;
+    a.gP = direct ? fm->gsP : dGsP;
+    a.gw = direct ? fm->gsw : dGsw;
+    a.dGnP = direct ? fm->gnP : dGnP;
+    a.dGnw = direct ? fm->gnw : dGnw;
     a.partials = ctx->partials;
     a.loss = cfg->loss;
     a.thr = cfg->huberThreshold;
@@ -720,9 +723,13 @@ int32_t nimfm_fm_adagrad_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset
     adagrad_scalar_kernel<<<1, 1, 0, ctx->stream>>>(fm->b, fm->adaScal, part, violPart, ctx->scalars, fm->fitIntercept,
                                                     cfg->eta0, tIt, cfg->alpha0, first);
     LAUNCHED(ctx);
-    adagrad_apply_kernel<<<ew_grid(ctx, nP), 256, 0, ctx->stream>>>(fm->gsP, fm->gnP, dGsP, dGnP, nP, fm->gsw, fm->gnw,
-                                                                   dGsw, dGnw, d, fm->fitLinear, cntF, dd);
-    LAUNCHED(ctx);
+    if (direct) {
+      CK(cudaMemsetAsync(cntF, 0, (size_t)dd * 8, ctx->stream));
+    } else {
+      adagrad_apply_kernel<<<ew_grid(ctx, nP), 256, 0, ctx->stream>>>(fm->gsP, fm->gnP, dGsP, dGnP, nP, fm->gsw, fm->gnw,
+                                                                     dGsw, dGnw, d, fm->fitLinear, cntF, dd);
+      LAUNCHED(ctx);
+    }
     *it += cnt * (int64_t)ctx->nranks;
   }
   CK(cudaGetLastError());
