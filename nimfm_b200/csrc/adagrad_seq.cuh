@@ -1,0 +1,174 @@
+// adagrad_seq.cuh -- AdaGrad with miniBatchSize = 1: the reference's strictly sequential per-sample loop
+// (optimizer/adagrad.nim:87-134,164-181) in ONE persistent thread block, the row's P / g_sum / g_norm
+// slices staged in shared memory (the minibatch pipeline costs six kernel launches per sample: 16 K
+// samples/s on the C4 shape).  Per sample, in the reference's order:
+//   update()   (it != 1): theta = -eta0*G/(eta0*(it-1)*reg + sqrt(N)) for the row's features (dummies
+//                         included), the intercept and w (fitLinearAdaGrad, fit_linear.nim:50-57); viol
+//   predictWithGrad, loss
+//   updateG()  G += dL*dA, N += (dL*dA)^2 (P, w, intercept);  it += 1
+#pragma once
+#include "common.cuh"
+
+#define ADASEQ_THREADS 256
+
+struct AdaSeqArgs {
+  const double *data;
+  const int32_t *indices;
+  const int64_t *indptr;
+  const double *y;
+  const int32_t *perm;
+  int64_t nRows, d;
+  int degree, k, nOrders, nAug, fitLinear, fitIntercept;
+  double *P, *gsP, *gnP, *w, *gsw, *gnw, *b, *adaScal;   // adaScal = [g_sum.intercept, g_norm.intercept]
+  double *scal;                                           // [loss sum, viol sum] (accumulated)
+  int loss;
+  double thr, eta0, alpha0, alpha, beta;
+  int64_t it0;
+  int zmax;
+};
+
+// dynamic smem: sP | sGs | sGn (zmax*SB8 each) | sX | sW (zmax each) | sJ (zmax int64)
+static __global__ void __launch_bounds__(ADASEQ_THREADS, 1) adagrad_fm_seq_kernel(const AdaSeqArgs a) {
+  extern __shared__ __align__(16) unsigned char ada_smem[];
+  __shared__ double red[ADASEQ_THREADS / 32];
+  __shared__ double sh[2];   // yhat, dL
+  const int k = a.k, NO = a.nOrders, SB8 = NO * k, zmax = a.zmax;
+  double *sP = reinterpret_cast<double *>(ada_smem);
+  double *sGs = sP + (size_t)zmax * SB8;
+  double *sGn = sGs + (size_t)zmax * SB8;
+  double *sX = sGn + (size_t)zmax * SB8;
+  double *sW = sX + zmax;
+  int64_t *sJ = reinterpret_cast<int64_t *>(sW + zmax);
+  const int tid = threadIdx.x, nth = blockDim.x;
+  double viol = 0.0, lossAcc = 0.0;
+  for (int64_t q = 0; q < a.nRows; ++q) {
+    const int64_t i = a.perm ? (int64_t)a.perm[q] : q;
+    const int64_t itq = a.it0 + q;
+    const bool refresh = itq != 1;
+    const double t = (double)(itq - 1);
+    const int64_t rb = a.indptr[i];
+    const int zReal = (int)(a.indptr[i + 1] - rb);
+    const int z = zReal + a.nAug;
+    __syncthreads();                                     // the previous sample's write-back has read the stage
+    // ---- records; update() of w for the row's real features
+    const double denW = t * a.eta0 * a.alpha;
+    for (int u = tid; u < z; u += nth) {
+      if (u < zReal) {
+        const int64_t j = a.indices[rb + u];
+        sJ[u] = j;
+        sX[u] = a.data[rb + u];
+        double wv = a.w[j];
+        if (a.fitLinear && refresh) {
+          const double wn = -a.eta0 * a.gsw[j] / (denW + sqrt(a.gnw[j]));
+          viol += fabs(wv - wn);
+          a.w[j] = wn;
+          wv = wn;
+        }
+        sW[u] = wv;
+      } else {
+        sJ[u] = a.d + (u - zReal);
+        sX[u] = 1.0;
+        sW[u] = 0.0;
+      }
+    }
+    if (tid == 0 && a.fitIntercept && refresh) {          // adagrad.nim:101-105
+      const double old = a.b[0];
+      const double den = sqrt(a.adaScal[1]) + a.eta0 * t * a.alpha0;
+      const double nb = -a.eta0 * a.adaScal[0] / den;
+      viol += fabs(old - nb);
+      a.b[0] = nb;
+    }
+    __syncthreads();
+    // ---- stage P / g_sum / g_norm of the row's features; update() of P (adagrad.nim:93-99)
+    const double tmpP = a.eta0 * t * a.beta;
+    for (int e = tid; e < z * SB8; e += nth) {
+      const int u = e / SB8, off = e - u * SB8;
+      const int64_t ge = sJ[u] * SB8 + off;
+      const double gs = a.gsP[ge], gn = a.gnP[ge];
+      double p = a.P[ge];
+      if (refresh) {
+        const double pn = -(a.eta0 * gs) / (tmpP + sqrt(gn));
+        viol += fabs(p - pn);
+        p = pn;
+      }
+      sP[e] = p;
+      sGs[e] = gs;
+      sGn[e] = gn;
+    }
+    __syncthreads();
+    // ---- predictWithGrad forward (thread <-> (order, component)); A stays in registers
+    double part = 0.0;
+    for (int u = tid; u < zReal; u += nth) part += sW[u] * sX[u];
+    double A[NIMFM_MAX_DEGREE + 1];
+    const int os = tid;
+    const int o = os < SB8 ? os / k : 0, sc = os - o * k;
+    const int M = a.degree - o;
+    if (os < SB8) {
+      A[0] = 1.0;
+      for (int tt = 1; tt <= M; tt++) A[tt] = 0.0;
+      for (int u = 0; u < z; u++) {
+        const double tv = sP[u * SB8 + o * k + sc] * sX[u];
+        if (M == 2) {
+          A[1] += tv;
+          A[2] += tv * tv;
+        } else {
+          for (int tt = M; tt >= 1; tt--) A[tt] += A[tt - 1] * tv;
+        }
+      }
+      part += M == 2 ? (A[1] * A[1] - A[2]) / 2.0 : A[M];
+    }
+    double yhat = block_sum(part, red);
+    if (tid == 0) {
+      yhat += a.b[0];
+      sh[0] = yhat;
+      const double yi = a.y[i];
+      lossAcc += dev_loss(a.loss, a.thr, yi, yhat);
+      sh[1] = dev_dloss(a.loss, a.thr, yi, yhat);
+    }
+    __syncthreads();
+    const double dL = sh[1];
+    // ---- updateG (adagrad.nim:113-134)
+    if (os < SB8) {
+      for (int u = 0; u < z; u++) {
+        const double x = sX[u];
+        const int e = u * SB8 + o * k + sc;
+        const double p = sP[e];
+        double g;
+        if (M == 2) g = x * (A[1] - p * x);
+        else {
+          g = x;
+          for (int tt = 1; tt < M; tt++) g = x * (A[tt] - p * g);
+        }
+        const double grad = dL * g;
+        sGs[e] += grad;
+        sGn[e] += grad * grad;
+      }
+    }
+    if (a.fitLinear)
+      for (int u = tid; u < zReal; u += nth) {
+        const int64_t j = sJ[u];
+        const double gx = dL * sX[u];
+        a.gsw[j] += gx;
+        a.gnw[j] += gx * gx;
+      }
+    if (tid == 0 && a.fitIntercept) {
+      a.adaScal[0] += dL;
+      a.adaScal[1] += dL * dL;
+    }
+    __syncthreads();
+    for (int e = tid; e < z * SB8; e += nth) {
+      const int u = e / SB8, off = e - u * SB8;
+      const int64_t ge = sJ[u] * SB8 + off;
+      if (refresh) a.P[ge] = sP[e];
+      a.gsP[ge] = sGs[e];
+      a.gnP[ge] = sGn[e];
+    }
+  }
+  viol = block_sum(viol, red);
+  __syncthreads();
+  lossAcc = block_sum(lossAcc, red);
+  if (tid == 0) {
+    a.scal[0] += lossAcc;
+    a.scal[1] += viol;
+  }
+}

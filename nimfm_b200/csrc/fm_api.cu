@@ -9,6 +9,7 @@
 #include "dense_kernels.cuh"
 #include "fm_rows_stream.cuh"
 #include "prox_kernels.cuh"
+#include "adagrad_seq.cuh"
 
 typedef void (*RowKernel)(const RowArgs);
 RowKernel nimfm_row_kernel_predict(int degree, bool explicitLower, int k);
@@ -665,6 +666,36 @@ int32_t nimfm_fm_adagrad_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset
   const int64_t nDelta = 2 * nP + 2 * d + 4;
   const int64_t mb = cfg->miniBatchSize;
   const int SB8 = fm->nOrders * fm->k;
+  // miniBatchSize = 1 on one rank: the reference's per-sample loop in one persistent block (adagrad_seq.cuh)
+  {
+    const int zmax = (int)std::max<int64_t>(X->maxSegNnz + fm->nAug, 1);
+    const size_t smem = (3 * (size_t)zmax * SB8 + 2 * (size_t)zmax) * 8 + (size_t)zmax * 8;
+    const char *env = getenv("NIMFM_ADAGRAD_SEQ");
+    if (mb == 1 && ctx->nranks == 1 && nRows > 0 && SB8 <= ADASEQ_THREADS && smem + 2048 <= (size_t)ctx->smemOptin &&
+        !(env && env[0] == '0')) {
+      AdaSeqArgs q;
+      memset(&q, 0, sizeof(q));
+      q.data = X->data; q.indices = X->indices; q.indptr = X->indptr; q.y = X->y; q.perm = idxDev;
+      q.nRows = nRows; q.d = d;
+      q.degree = fm->degree; q.k = fm->k; q.nOrders = fm->nOrders; q.nAug = fm->nAug;
+      q.fitLinear = fm->fitLinear; q.fitIntercept = fm->fitIntercept;
+      q.P = fm->P; q.gsP = fm->gsP; q.gnP = fm->gnP; q.w = fm->w; q.gsw = fm->gsw; q.gnw = fm->gnw;
+      q.b = fm->b; q.adaScal = fm->adaScal; q.scal = ctx->scalars;
+      q.loss = cfg->loss; q.thr = cfg->huberThreshold;
+      q.eta0 = cfg->eta0; q.alpha0 = cfg->alpha0; q.alpha = cfg->alpha; q.beta = cfg->beta;
+      q.it0 = *it; q.zmax = zmax;
+      CK(cudaFuncSetAttribute(adagrad_fm_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      adagrad_fm_seq_kernel<<<1, ADASEQ_THREADS, smem, ctx->stream>>>(q);
+      LAUNCHED(ctx);
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(ctx->hostScalars, ctx->scalars, 16, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      *it += nRows;
+      if (lossSum) *lossSum = ctx->hostScalars[0];
+      if (viol) *viol = ctx->hostScalars[1];
+      return NIMFM_OK;
+    }
+  }
   for (int64_t start = 0; start < nRows; start += mb) {
     const int64_t cnt = std::min<int64_t>(mb, nRows - start);
     const int32_t *rows = idxDev ? idxDev + start : nullptr;
