@@ -396,6 +396,12 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = ne * world * args.e2e_steps / float(te.item())
 
+    def link_stats():
+        a, b, t_ = C.c_int64(), C.c_int64(), C.c_int32()
+        _lib.check(lib.nimfm_stream_stats(ctx, C.byref(a), C.byref(b), C.byref(t_)))
+        return a.value, b.value, t_.value
+    e2e_h2d, e2e_d2h, e2e_threads = link_stats()
+
     # end-to-end batched decisionFunction from the same host buffers (predictions read back)
     pred_host = torch.empty(ne, dtype=torch.float64).pin_memory()
 
@@ -412,6 +418,7 @@ def main():
     if world > 1:
         dist.all_reduce(tp, op=dist.ReduceOp.MAX)
     e2e_predict_value = ne * world * args.e2e_steps / float(tp.item())
+    pred_h2d, pred_d2h, _ = link_stats()
 
     line = {
         "metric": "samples/sec FM/HOFM predict+grad", "value": value, "unit": "samples/s", "n_gpus": world,
@@ -419,12 +426,15 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, world, n),
         "clocks": clocks, "gpu_launches": int(launches),
-        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
-                "rows_per_step": ne, "note": "nimfm_fm_loss_grad_host: pinned host CSR (f64 data, i64 indices/indptr, "
-                "f64 y) -> chunked H2D overlapped with the kernel -> loss read back"},
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(e2e_h2d), "d2h_bytes_per_step": int(e2e_d2h),
+                "rows_per_step": ne, "host_bytes_per_step": int(h2d), "host_staging_threads": int(e2e_threads),
+                "note": "nimfm_fm_loss_grad_host: pinned host CSR (f64 data, i64 indices/indptr, f64 y) -> "
+                "[ids narrowed to int32 by the library's host staging threads when host_staging_threads > 0] -> chunked "
+                "H2D overlapped with the kernel -> loss read back; h2d/d2h bytes are what the library put on the "
+                "link (nimfm_stream_stats), host_bytes_per_step the size of the caller's arrays"},
         "e2e_predict": {"value": e2e_predict_value, "unit": "samples/s", "what": "nimfm_fm_decision_function_host: the "
                         "same pinned host CSR -> chunked H2D overlapped with the forward kernel -> predictions copied "
-                        "back", "h2d_bytes_per_step": int(h2d - ne * 8), "d2h_bytes_per_step": int(ne * 8)},
+                        "back", "h2d_bytes_per_step": int(pred_h2d), "d2h_bytes_per_step": int(pred_d2h)},
         "roofline": roofline,
         "loss_sum": loss_sum, "setup_seconds": t_gen,
     }

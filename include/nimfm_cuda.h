@@ -63,6 +63,9 @@ const char *nimfm_last_error(const nimfm_ctx *ctx);
 /* library/ABI version (major*100 + minor) and the number of kernels launched by this ctx so far */
 int32_t nimfm_version(void);
 int64_t nimfm_launch_count(const nimfm_ctx *ctx);
+/* what the last host-fed call (nimfm_fm_loss_grad_host / nimfm_fm_decision_function_host) moved over the link:
+ * bytes host->device, bytes device->host, and the host staging threads it used (0: ids narrowed on the device) */
+int32_t nimfm_stream_stats(const nimfm_ctx *ctx, int64_t *h2dBytes, int64_t *d2hBytes, int32_t *hostThreads);
 
 /* Multi-GPU (one process per GPU).  The reference has no distributed backend; this is
  * the synchronous data-parallel replacement of its Hogwild threads (sgd_multi.nim:86-95).

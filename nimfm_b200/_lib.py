@@ -66,6 +66,7 @@ SYMBOLS = {
     "nimfm_last_error": (C.c_char_p, [VP]),
     "nimfm_version": (c_i32, []),
     "nimfm_launch_count": (c_i64, [VP]),
+    "nimfm_stream_stats": (c_i32, [VP, VP, VP, VP]),
     "nimfm_comm_unique_id": (c_i32, [VP]),
     "nimfm_comm_init": (c_i32, [VP, c_i32, c_i32, VP]),
     "nimfm_comm_size": (c_i32, [VP]),

@@ -39,8 +39,15 @@ struct nimfm_ctx {
     double *data = nullptr, *y = nullptr;
     int64_t *idx64 = nullptr, *indptr = nullptr;
     int32_t *idx32 = nullptr;
-    size_t capNnz = 0, capRows = 0;
+    size_t capNnz = 0, capRows = 0, capIdx64 = 0;
   } stage[2];
+  // pinned slots of the host staging team (host_stage.h): narrowed ids + rebased indptr
+  int32_t *hostIdx[4] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t *hostPtr[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t evSlot[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t hostCapNnz = 0, hostCapRows = 0;
+  int64_t lastH2D = 0, lastD2H = 0;   // nimfm_stream_stats
+  int32_t lastHostThreads = 0;
   uint8_t *stageHotSlot = nullptr;   // persistent [stageHotD] table; only the <=16 hot entries change per call
   int32_t *stageHotList = nullptr;
   int64_t stageHotD = -1;

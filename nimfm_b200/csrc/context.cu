@@ -56,6 +56,13 @@ int32_t nimfm_version(void) { return 100; }
 const char *nimfm_last_error(const nimfm_ctx *ctx) { return ctx ? ctx->err.c_str() : g_noctx_err.c_str(); }
 
 int64_t nimfm_launch_count(const nimfm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int32_t nimfm_stream_stats(const nimfm_ctx *ctx, int64_t *h2dBytes, int64_t *d2hBytes, int32_t *hostThreads) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  if (h2dBytes) *h2dBytes = ctx->lastH2D;
+  if (d2hBytes) *d2hBytes = ctx->lastD2H;
+  if (hostThreads) *hostThreads = ctx->lastHostThreads;
+  return NIMFM_OK;
+}
 
 int32_t nimfm_ctx_create(int32_t device, nimfm_ctx **out) {
   nimfm_ctx *ctx = nullptr;
@@ -117,6 +124,11 @@ int32_t nimfm_ctx_destroy(nimfm_ctx *ctx) {
     cudaFree(ctx->stage[s].indptr); cudaFree(ctx->stage[s].idx32);
     if (ctx->evCopied[s]) cudaEventDestroy(ctx->evCopied[s]);
     if (ctx->evComputed[s]) cudaEventDestroy(ctx->evComputed[s]);
+  }
+  for (int s = 0; s < 4; s++) {
+    if (ctx->hostIdx[s]) cudaFreeHost(ctx->hostIdx[s]);
+    if (ctx->hostPtr[s]) cudaFreeHost(ctx->hostPtr[s]);
+    if (ctx->evSlot[s]) cudaEventDestroy(ctx->evSlot[s]);
   }
   cudaFree(ctx->stageHotSlot);
   cudaFree(ctx->stageHotList);

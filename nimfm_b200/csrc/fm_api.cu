@@ -5,11 +5,13 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <memory>
 
 #include "dense_kernels.cuh"
 #include "fm_rows_stream.cuh"
 #include "prox_kernels.cuh"
 #include "adagrad_seq.cuh"
+#include "host_stage.h"
 
 typedef void (*RowKernel)(const RowArgs);
 RowKernel nimfm_row_kernel_predict(int degree, bool explicitLower, int k);
@@ -859,7 +861,7 @@ static __global__ void set_hot_table_kernel(uint8_t *slot, const HotLists hl) {
   if (t >= 16 && hl.v[t] >= 0) slot[hl.v[t]] = (uint8_t)(t - 16);
 }
 
-static int ensure_stage(nimfm_ctx *ctx, nimfm_ctx::Stage &st, size_t rows, size_t nnz) {
+static int ensure_stage(nimfm_ctx *ctx, nimfm_ctx::Stage &st, size_t rows, size_t nnz, bool needIdx64) {
   if (st.capRows < rows) {
     if (st.y) CK(cudaFree(st.y));
     if (st.indptr) CK(cudaFree(st.indptr));
@@ -869,13 +871,38 @@ static int ensure_stage(nimfm_ctx *ctx, nimfm_ctx::Stage &st, size_t rows, size_
   }
   if (st.capNnz < nnz) {
     if (st.data) CK(cudaFree(st.data));
-    if (st.idx64) CK(cudaFree(st.idx64));
     if (st.idx32) CK(cudaFree(st.idx32));
     CK(cudaMalloc(&st.data, nnz * 8));
-    CK(cudaMalloc(&st.idx64, nnz * 8));
     CK(cudaMalloc(&st.idx32, nnz * 4));
     st.capNnz = nnz;
   }
+  if (needIdx64 && st.capIdx64 < nnz) {   // only the device-narrowing path stages 64-bit ids
+    if (st.idx64) CK(cudaFree(st.idx64));
+    st.idx64 = nullptr;
+    st.capIdx64 = 0;
+    CK(cudaMalloc(&st.idx64, nnz * 8));
+    st.capIdx64 = nnz;
+  }
+  return NIMFM_OK;
+}
+
+// pinned host slots of the staging team (host_stage.h): int32 ids + rebased indptr, kSlots deep
+static int ensure_host_slots(nimfm_ctx *ctx, size_t rows, size_t nnz) {
+  for (int s = 0; s < HostStageTeam::kSlots; s++) {
+    if (ctx->hostCapNnz < nnz) {
+      if (ctx->hostIdx[s]) CK(cudaFreeHost(ctx->hostIdx[s]));
+      ctx->hostIdx[s] = nullptr;
+      CK(cudaHostAlloc(&ctx->hostIdx[s], nnz * 4, cudaHostAllocDefault));
+    }
+    if (ctx->hostCapRows < rows) {
+      if (ctx->hostPtr[s]) CK(cudaFreeHost(ctx->hostPtr[s]));
+      ctx->hostPtr[s] = nullptr;
+      CK(cudaHostAlloc(&ctx->hostPtr[s], (rows + 1) * 8, cudaHostAllocDefault));
+    }
+    if (!ctx->evSlot[s]) CK(cudaEventCreateWithFlags(&ctx->evSlot[s], cudaEventDisableTiming));
+  }
+  ctx->hostCapNnz = std::max(ctx->hostCapNnz, nnz);
+  ctx->hostCapRows = std::max(ctx->hostCapRows, rows);
   return NIMFM_OK;
 }
 
@@ -897,16 +924,29 @@ static int stream_host_rows(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t
   if (zeroGrads && !predict) CK(cudaMemsetAsync(fm->grad, 0, (size_t)nG * 8, ctx->stream));
   int *bad = reinterpret_cast<int *>(ctx->scalars + 60);
   CK(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
-  // size the two staging sets for the largest chunk (indptr is sampled at chunk boundaries only)
+  // the chunk list; the two device staging sets are sized for the largest chunk
+  std::vector<HostChunk> chunks;
   size_t maxNnz = 1;
   for (int64_t r0 = 0; r0 < nRows; r0 += chunkRows) {
-    const int64_t r1 = std::min(nRows, r0 + chunkRows);
-    REQUIRE(indptr[r1] >= indptr[r0], "indptr is not monotone");
-    maxNnz = std::max(maxNnz, (size_t)(indptr[r1] - indptr[r0]));
+    HostChunk ch;
+    ch.r0 = r0;
+    ch.r1 = std::min(nRows, r0 + chunkRows);
+    REQUIRE(indptr[ch.r1] >= indptr[ch.r0], "indptr is not monotone");
+    ch.base = indptr[ch.r0];
+    ch.nnz = indptr[ch.r1] - ch.base;
+    maxNnz = std::max(maxNnz, (size_t)ch.nnz);
+    chunks.push_back(ch);
   }
+  const int64_t nChunks = (int64_t)chunks.size();
+  // host staging (host_stage.h): ids narrowed to int32 and indptr rebased by a thread team into pinned slots,
+  // 12 instead of 16 bytes per nonzero on the link; small calls and thread-starved ranks narrow on the device
+  const int64_t stageMinNnz = getenv("NIMFM_HOST_STAGE_MIN_NNZ") ? atoll(getenv("NIMFM_HOST_STAGE_MIN_NNZ")) : (1 << 20);
+  const int hostT = (indices && nRows > 0 && indptr[nRows] - indptr[0] >= stageMinNnz) ? HostStageTeam::default_threads(ctx->nranks) : 0;
   int rc;
+  const size_t capRows = (size_t)std::min(nRows, chunkRows) + 1;
   for (int s = 0; s < 2; s++)
-    if ((rc = ensure_stage(ctx, ctx->stage[s], (size_t)std::min(nRows, chunkRows) + 1, maxNnz))) return rc;
+    if ((rc = ensure_stage(ctx, ctx->stage[s], capRows, maxNnz, hostT == 0))) return rc;
+  if (hostT > 0 && (rc = ensure_host_slots(ctx, capRows, maxNnz))) return rc;
   if (!ctx->stageHotSlot || ctx->stageHotD != d) {   // persistent hot-column table, all cold
     if (ctx->stageHotSlot) CK(cudaFree(ctx->stageHotSlot));
     ctx->stageHotSlot = nullptr;
@@ -916,19 +956,47 @@ static int stream_host_rows(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t
     ctx->stageHotD = d;
     ctx->stageNHot = 0;
   }
+  std::unique_ptr<HostStageTeam> team;
+  if (hostT > 0) {
+    team.reset(new HostStageTeam(hostT, indices, indptr, d, chunks, ctx->hostIdx, ctx->hostPtr));
+    team->allow(std::min<int64_t>(nChunks, HostStageTeam::kSlots - 1));
+  }
+  // a failed check leaves with both streams drained (copies read the caller's buffers and our pinned slots)
+  auto drained = [&](int code) {
+    cudaStreamSynchronize(ctx->copyStream);
+    cudaStreamSynchronize(ctx->stream);
+    return code;
+  };
   int nHot = 0;
-  int c = 0;
-  for (int64_t r0 = 0; r0 < nRows; r0 += chunkRows, c++) {
-    const int64_t r1 = std::min(nRows, r0 + chunkRows), rows = r1 - r0;
-    const int64_t base = indptr[r0], nnz = indptr[r1] - base;
+  int64_t h2d = 0, d2h = 0;
+  for (int64_t c = 0; c < nChunks; c++) {
+    const int64_t r0 = chunks[c].r0, r1 = chunks[c].r1, rows = r1 - r0;
+    const int64_t base = chunks[c].base, nnz = chunks[c].nnz;
     nimfm_ctx::Stage &st = ctx->stage[c & 1];
+    const int hs = (int)(c % HostStageTeam::kSlots);
+    HostChunkInfo info;
+    if (team) {
+      info = team->wait(c);   // normally already staged: the team runs two chunks ahead of the copies
+      if (info.minSeg < 0)
+        return drained(nimfm_fail(ctx, NIMFM_ERR_INVALID, "indptr is not monotone in rows [%lld,%lld)", (long long)r0, (long long)r1));
+      if (info.bad)
+        return drained(nimfm_fail(ctx, NIMFM_ERR_INVALID, "column index out of range [0,%lld)", (long long)d));
+    }
     // the copies go out first; the host-side bookkeeping below overlaps with the DMA
     if (c >= 2) CK(cudaStreamWaitEvent(ctx->copyStream, ctx->evComputed[c & 1], 0));   // buffer is free again
     CK(cudaMemcpyAsync(st.data, data + base, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->copyStream));
-    CK(cudaMemcpyAsync(st.idx64, indices + base, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->copyStream));
-    CK(cudaMemcpyAsync(st.indptr, indptr + r0, (size_t)(rows + 1) * 8, cudaMemcpyHostToDevice, ctx->copyStream));
+    if (team) {
+      CK(cudaMemcpyAsync(st.idx32, ctx->hostIdx[hs], (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->copyStream));
+      CK(cudaMemcpyAsync(st.indptr, ctx->hostPtr[hs], (size_t)(rows + 1) * 8, cudaMemcpyHostToDevice, ctx->copyStream));
+    } else {
+      CK(cudaMemcpyAsync(st.idx64, indices + base, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->copyStream));
+      CK(cudaMemcpyAsync(st.indptr, indptr + r0, (size_t)(rows + 1) * 8, cudaMemcpyHostToDevice, ctx->copyStream));
+    }
     if (!predict) CK(cudaMemcpyAsync(st.y, y + r0, (size_t)rows * 8, cudaMemcpyHostToDevice, ctx->copyStream));
     CK(cudaEventRecord(ctx->evCopied[c & 1], ctx->copyStream));
+    if (team) CK(cudaEventRecord(ctx->evSlot[hs], ctx->copyStream));
+    h2d += nnz * (team ? 12 : 16) + (rows + 1) * 8 + (predict ? 0 : rows * 8);
+    d2h += predict ? rows * 8 : 0;
     if (c == 0 && !predict) {
       // hot columns of this batch (row sample on the host; see nimfm_find_hot): the previous call's
       // entries are cleared and the new ones set by one tiny kernel on the persistent table
@@ -945,27 +1013,27 @@ static int stream_host_rows(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t
       for (int i = 0; i < nHot; i++) ctx->stagePrevHot[i] = hot[i];
       ctx->stageNHot = nHot;
     }
-    int64_t maxSeg = 0, minSeg = 0;
-    for (int64_t r = r0; r < r1; r++) {
-      const int64_t len = indptr[r + 1] - indptr[r];
-      maxSeg = std::max(maxSeg, len);
-      minSeg = std::min(minSeg, len);
-    }
-    if (minSeg < 0) {
-      cudaStreamSynchronize(ctx->copyStream);
-      cudaStreamSynchronize(ctx->stream);
-      return nimfm_fail(ctx, NIMFM_ERR_INVALID, "indptr is not monotone in rows [%lld,%lld)", (long long)r0, (long long)r1);
+    if (!team) {
+      for (int64_t r = r0; r < r1; r++) {
+        const int64_t len = indptr[r + 1] - indptr[r];
+        info.maxSeg = std::max(info.maxSeg, len);
+        info.minSeg = std::min(info.minSeg, len);
+      }
+      if (info.minSeg < 0)
+        return drained(nimfm_fail(ctx, NIMFM_ERR_INVALID, "indptr is not monotone in rows [%lld,%lld)", (long long)r0, (long long)r1));
     }
     CK(cudaStreamWaitEvent(ctx->stream, ctx->evCopied[c & 1], 0));
-    narrow_rebase_kernel<<<ew_grid(ctx, nnz), 256, 0, ctx->stream>>>(st.idx64, st.idx32, nnz, st.indptr, rows + 1,
-                                                                     base, d, bad);
-    LAUNCHED(ctx);
+    if (!team) {
+      narrow_rebase_kernel<<<ew_grid(ctx, nnz), 256, 0, ctx->stream>>>(st.idx64, st.idx32, nnz, st.indptr, rows + 1,
+                                                                       base, d, bad);
+      LAUNCHED(ctx);
+    }
     nimfm_dataset tmp;
     tmp.kind = NIMFM_DS_CSR;
     tmp.n = rows;
     tmp.d = d;
     tmp.nnz = nnz;
-    tmp.maxSegNnz = maxSeg;
+    tmp.maxSegNnz = info.maxSeg;
     tmp.data = st.data;
     tmp.indices = st.idx32;
     tmp.indptr = st.indptr;
@@ -975,16 +1043,24 @@ static int stream_host_rows(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t
     tmp.nHot = nHot;
     if (predict) {
       // the stage's target buffer doubles as the chunk's output; it travels back behind the kernel
-      if ((rc = nimfm_fm_predict_device_lams(ctx, fm, &tmp, st.y))) return rc;
+      if ((rc = nimfm_fm_predict_device_lams(ctx, fm, &tmp, st.y))) return drained(rc);
       CK(cudaMemcpyAsync(predOut + r0, st.y, (size_t)rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
     } else {
       if ((rc = launch_loss_grad(ctx, fm, &tmp, loss, huberThreshold, 0, rows, nullptr, (double)miniBatchSize, nullptr)))
-        return rc;
+        return drained(rc);
       add_tail_kernel<<<1, 1, 0, ctx->stream>>>(fm->grad + nG - 2, ctx->scalars + 8);
       LAUNCHED(ctx);
     }
     CK(cudaEventRecord(ctx->evComputed[c & 1], ctx->stream));
+    if (team) {
+      // chunk c+2 reuses the pinned slot of chunk c-2: hand it to the team once that copy has left the host
+      if (c >= 2) CK(cudaEventSynchronize(ctx->evSlot[(c - 2) % HostStageTeam::kSlots]));
+      team->allow(c + 3);
+    }
   }
+  ctx->lastH2D = h2d;
+  ctx->lastD2H = d2h + (lossSum && !predict ? 8 : 0);
+  ctx->lastHostThreads = hostT;
   if (!predict && allreduce && (rc = nimfm_allreduce_sum(ctx, fm->grad, nG))) return rc;
   int hbad = 0;
   CK(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

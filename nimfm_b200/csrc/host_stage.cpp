@@ -1,0 +1,129 @@
+// host_stage.cpp -- see host_stage.h.  Plain C++ (g++), no CUDA.
+#include "host_stage.h"
+
+#include <immintrin.h>
+#include <stdlib.h>
+
+#include <algorithm>
+
+namespace {
+
+// int64 -> int32 with a range check; `dst` 32-byte aligned.  Returns nonzero if any id is outside [0,d).
+int narrow_scalar(const int64_t *src, int32_t *dst, int64_t n, int64_t d) {
+  int bad = 0;
+  for (int64_t i = 0; i < n; i++) {
+    const int64_t v = src[i];
+    bad |= (v < 0) | (v >= d);
+    dst[i] = (int32_t)v;
+  }
+  return bad;
+}
+
+// AVX2: 8 ids per iteration, non-temporal stores (the copy engine is the only reader of the slot).
+// Range check: ids are valid iff 0 <= v < d; with d <= 2^31 that is "high word zero and low word < d as
+// unsigned", folded into one OR-accumulator of (v | (d-1-v)) whose sign bit flags a violation.
+__attribute__((target("avx2"))) int narrow_avx2(const int64_t *src, int32_t *dst, int64_t n, int64_t d) {
+  const __m256i perm = _mm256_setr_epi32(0, 2, 4, 6, 0, 0, 0, 0);
+  const __m256i dm1 = _mm256_set1_epi64x(d - 1);
+  __m256i acc = _mm256_setzero_si256();
+  int64_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i));
+    const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 4));
+    acc = _mm256_or_si256(acc, _mm256_or_si256(a, _mm256_sub_epi64(dm1, a)));
+    acc = _mm256_or_si256(acc, _mm256_or_si256(b, _mm256_sub_epi64(dm1, b)));
+    const __m128i lo = _mm256_castsi256_si128(_mm256_permutevar8x32_epi32(a, perm));
+    const __m128i hi = _mm256_castsi256_si128(_mm256_permutevar8x32_epi32(b, perm));
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), _mm256_set_m128i(hi, lo));
+  }
+  alignas(32) int64_t t[4];
+  _mm256_store_si256(reinterpret_cast<__m256i *>(t), acc);
+  int bad = (t[0] | t[1] | t[2] | t[3]) < 0;
+  bad |= narrow_scalar(src + i, dst + i, n - i, d);
+  _mm_sfence();
+  return bad;
+}
+
+int narrow(const int64_t *src, int32_t *dst, int64_t n, int64_t d) {
+  static const bool haveAvx2 = __builtin_cpu_supports("avx2");
+  return haveAvx2 ? narrow_avx2(src, dst, n, d) : narrow_scalar(src, dst, n, d);
+}
+
+}  // namespace
+
+int HostStageTeam::default_threads(int nRanks) {
+  if (const char *e = getenv("NIMFM_HOST_THREADS")) return std::max(0, atoi(e));
+  const int hw = (int)std::thread::hardware_concurrency();
+  const int t = std::min(8, hw / std::max(1, nRanks));
+  return t >= 4 ? t : 0;   // fewer than 4 threads cannot keep up with a PCIe 5 x16 link
+}
+
+HostStageTeam::HostStageTeam(int nThreads, const int64_t *indices, const int64_t *indptr, int64_t d,
+                             const std::vector<HostChunk> &chunks, int32_t *const *idxSlot, int64_t *const *ptrSlot)
+    : T_(std::max(1, nThreads)), indices_(indices), indptr_(indptr), d_(d), chunks_(chunks), idxSlot_(idxSlot),
+      ptrSlot_(ptrSlot), done_(chunks.size(), 0), info_(chunks.size()) {
+  for (int t = 0; t < T_; t++) threads_.emplace_back([this, t] { work(t); });
+}
+
+HostStageTeam::~HostStageTeam() {
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    stop_ = true;
+  }
+  cv_.notify_all();
+  for (auto &th : threads_) th.join();
+}
+
+void HostStageTeam::allow(int64_t upTo) {
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    allowed_ = std::max(allowed_, upTo);
+  }
+  cv_.notify_all();
+}
+
+HostChunkInfo HostStageTeam::wait(int64_t c) {
+  std::unique_lock<std::mutex> g(mu_);
+  cv_.wait(g, [&] { return done_[c] == T_; });
+  return info_[c];
+}
+
+// thread t's share of chunk c: an 8-aligned slice of the nonzeros and a slice of the rows
+void HostStageTeam::part(int64_t c, int t, HostChunkInfo &info) {
+  const HostChunk &ch = chunks_[c];
+  const int s = (int)(c % kSlots);
+  const int64_t per = ((ch.nnz + T_ - 1) / T_ + 7) & ~(int64_t)7;
+  const int64_t a = std::min(ch.nnz, per * t), b = std::min(ch.nnz, per * (t + 1));
+  if (b > a) info.bad |= narrow(indices_ + ch.base + a, idxSlot_[s] + a, b - a, d_);
+  const int64_t rows = ch.r1 - ch.r0, rper = (rows + T_ - 1) / T_;
+  const int64_t ra = std::min(rows, rper * t), rb = std::min(rows, rper * (t + 1));
+  int64_t *op = ptrSlot_[s];
+  for (int64_t r = ra; r < rb; r++) {
+    const int64_t p0 = indptr_[ch.r0 + r], len = indptr_[ch.r0 + r + 1] - p0;
+    op[r] = p0 - ch.base;
+    info.maxSeg = std::max(info.maxSeg, len);
+    info.minSeg = std::min(info.minSeg, len);
+  }
+  if (t == T_ - 1) op[rows] = ch.nnz;
+}
+
+void HostStageTeam::work(int t) {
+  for (int64_t c = 0; c < (int64_t)chunks_.size(); c++) {
+    {
+      std::unique_lock<std::mutex> g(mu_);
+      cv_.wait(g, [&] { return stop_ || allowed_ > c; });
+      if (stop_) return;
+    }
+    HostChunkInfo mine;
+    part(c, t, mine);
+    bool last;
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      info_[c].bad |= mine.bad;
+      info_[c].maxSeg = std::max(info_[c].maxSeg, mine.maxSeg);
+      info_[c].minSeg = std::min(info_[c].minSeg, mine.minSeg);
+      last = ++done_[c] == T_;
+    }
+    if (last) cv_.notify_all();
+  }
+}

@@ -1,0 +1,53 @@
+// host_stage.h -- host-side preparation of streamed CSR chunks (the end-to-end path of fm_api.cu).
+//
+// The reference keeps column ids as Nim `int` (int64, tensor/sparse.nim:4-31); the device kernels read
+// int32.  Narrowing on the HOST, into pinned staging slots, before the H2D copy takes 4 of the 16 bytes a
+// nonzero costs on PCIe (the link is the bound of the end-to-end path).  A small team of threads runs
+// ahead of the copy engine: chunk c+1, c+2 are narrowed while chunk c is in flight.  The same pass checks
+// the index range, rebases the chunk's indptr to 0 and finds its longest / shortest row.
+#pragma once
+#include <stdint.h>
+
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+struct HostChunk {
+  int64_t r0 = 0, r1 = 0;     // rows [r0, r1) of the caller's CSR
+  int64_t base = 0, nnz = 0;  // indptr[r0], indptr[r1]-indptr[r0]
+};
+
+struct HostChunkInfo {
+  int64_t maxSeg = 0, minSeg = 0;
+  int bad = 0;                // some column id outside [0,d)
+};
+
+class HostStageTeam {
+ public:
+  static constexpr int kSlots = 4;
+  // idxSlot[s] (int32, >= max chunk nnz) and ptrSlot[s] (int64, >= max chunk rows + 1): pinned, 32-byte aligned
+  HostStageTeam(int nThreads, const int64_t *indices, const int64_t *indptr, int64_t d,
+                const std::vector<HostChunk> &chunks, int32_t *const *idxSlot, int64_t *const *ptrSlot);
+  ~HostStageTeam();                       // stops and joins the workers
+  void allow(int64_t upTo);               // chunks < upTo may be written (their slot's last copy has completed)
+  HostChunkInfo wait(int64_t c);          // blocks until chunk c is staged in slot c % kSlots
+  static int default_threads(int nRanks); // 0: not enough host threads for this rank -> narrow on the device
+
+ private:
+  void work(int t);
+  void part(int64_t c, int t, HostChunkInfo &info);
+  const int T_;
+  const int64_t *indices_, *indptr_;
+  const int64_t d_;
+  const std::vector<HostChunk> &chunks_;
+  int32_t *const *idxSlot_;
+  int64_t *const *ptrSlot_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  int64_t allowed_ = 0;
+  bool stop_ = false;
+  std::vector<int> done_;
+  std::vector<HostChunkInfo> info_;
+  std::vector<std::thread> threads_;
+};

@@ -122,6 +122,57 @@ def test_decision_function_host_streaming(oracle):
         lib.nimfm_fm_free(ctx, h)
 
 
+@pytest.mark.parametrize("host_threads", ["0", "1", "3", "8"])
+@pytest.mark.parametrize("chunk", [0, 97, 256])
+def test_loss_grad_host_streaming(oracle, monkeypatch, host_threads, chunk):
+    """nimfm_fm_loss_grad_host / nimfm_fm_decision_function_host (the end-to-end calls bench.py times): host
+    CSR in the reference dtypes -> chunks -> row kernel.  Both index-narrowing routes -- on the device
+    (NIMFM_HOST_THREADS=0) and by the host staging team into pinned int32 slots (host_stage.h) -- against the
+    oracle's updateGradient (minibatch_psgd.nim:67-88) and bit-identical to each other in the predictions."""
+    monkeypatch.setenv("NIMFM_HOST_THREADS", host_threads)
+    monkeypatch.setenv("NIMFM_HOST_STAGE_MIN_NNZ", "0")
+    n, d, k, degree = 1500, 60, 8, 3
+    csr = ragged_csr(n, d, 5, 17)
+    rng = np.random.default_rng(8)
+    y = np.where(rng.random(n) < 0.5, -1.0, 1.0)
+    P, w, _ = make_fm_params(d, degree, k, "explicit", True, seed=4)
+    fm = make_fm(degree, k, "explicit", True, True, P, w, -0.1, task=nf.classification)
+    ref = oracle.fm_loss_grad(csr, y, P, w, -0.1, degree, "logistic", mini_batch_size=n)
+    lib, ctx = _lib.load(), _lib.ctx()
+    h = fm._to_device(d)
+    try:
+        ls = C.c_double()
+        _lib.check(lib.nimfm_fm_loss_grad_host(ctx, h, n, d, _lib.ptr(csr.data), _lib.ptr(csr.indices), _lib.ptr(csr.indptr),
+                                               _lib.ptr(y), 2, 1.0, n, chunk, 1, 0, C.byref(ls)))
+        gP, gw, gb = np.zeros_like(P), np.zeros(d), C.c_double()
+        _lib.check(lib.nimfm_fm_get_grads(ctx, h, _lib.ptr(gP), _lib.ptr(gw), C.byref(gb)))
+        assert abs(ls.value - ref["loss"]) <= DEC_TOL * abs(ref["loss"])
+        assert max_rel(gP, ref["gP"]) <= 1e-9 and max_rel(gw, ref["gw"]) <= 1e-9
+        assert abs(gb.value - ref["gb"]) <= 1e-9 * max(abs(ref["gb"]), 1e-3)
+        out = np.zeros(n)
+        _lib.check(lib.nimfm_fm_decision_function_host(ctx, h, n, d, _lib.ptr(csr.data), _lib.ptr(csr.indices),
+                                                       _lib.ptr(csr.indptr), chunk, _lib.ptr(out)))
+        assert np.array_equal(out, fm.decisionFunction(csr_ds(csr)))
+        # a column id outside [0,d) and a negative one, in different chunks; a decreasing indptr
+        for pos, val in ((len(csr.indices) - 2, d), (3, -1)):
+            bad = csr.indices.copy()
+            bad[pos] = val
+            with pytest.raises(ValueError, match="out of range"):
+                _lib.check(lib.nimfm_fm_loss_grad_host(ctx, h, n, d, _lib.ptr(csr.data), _lib.ptr(bad), _lib.ptr(csr.indptr),
+                                                       _lib.ptr(y), 2, 1.0, n, chunk, 1, 0, C.byref(ls)))
+        ptr = csr.indptr.copy()
+        ptr[700] = ptr[699] - 1 if ptr[699] > 0 else ptr[701] + 1
+        with pytest.raises(ValueError, match="monotone"):
+            _lib.check(lib.nimfm_fm_loss_grad_host(ctx, h, n, d, _lib.ptr(csr.data), _lib.ptr(csr.indices), _lib.ptr(ptr),
+                                                   _lib.ptr(y), 2, 1.0, n, chunk, 1, 0, C.byref(ls)))
+        # and the library is still usable afterwards
+        _lib.check(lib.nimfm_fm_loss_grad_host(ctx, h, n, d, _lib.ptr(csr.data), _lib.ptr(csr.indices), _lib.ptr(csr.indptr),
+                                               _lib.ptr(y), 2, 1.0, n, chunk, 1, 0, C.byref(ls)))
+        assert abs(ls.value - ref["loss"]) <= DEC_TOL * abs(ref["loss"])
+    finally:
+        lib.nimfm_fm_free(ctx, h)
+
+
 def test_decision_function_errors():
     X = make_dense(5, 6, 1)
     csr = CSR.from_dense(X)
