@@ -90,6 +90,9 @@ struct nimfm_fm {
   // gradient buffer: [gP (nP) | gw (d) | gb, lossSum] contiguous for a single all-reduce
   double *grad = nullptr;
   double *proxState = nullptr;   // SquaredL12 column prox: [tau | prevCnt | done] (prox_kernels.cuh)
+  // lazy MBPSGD epoch: per-feature {1/cumP, 1/cumW} at the feature's last update, touched flags
+  double2 *lazyInv = nullptr;
+  uint8_t *lazyFlag = nullptr;
   // AdaGrad state (same layouts): g_sum, g_norm, and per-minibatch deltas
   double *gsP = nullptr, *gnP = nullptr, *gsw = nullptr, *gnw = nullptr;
   double *dG = nullptr;    // [dGsP (nP) | dGnP (nP) | dGsw (d) | dGnw (d) | touched (d+nAug) | loss, sum dL, sum dL^2, viol]

@@ -67,6 +67,95 @@ static __global__ void mbpsgd_step_kernel(double *P, double *gP, int64_t nP, dou
   }
 }
 
+// ------------------------------------------------------------------ MBPSGD lazy step (K3b)
+// The dense step above moves all of P, w and the gradient buffer every minibatch; with the reference's
+// default minibatch (25 641 rows of the Criteo shape) a minibatch touches ~1/5 of the features and the
+// dense pass costs as much as the row kernel.  An untouched feature only shrinks: p <- p / (1 + eta_t beta).
+// The lazy epoch applies that shrink when the feature is next touched: with cum[t] = prod_{s<t} r_s the
+// pending factor of feature j is cum[t] * inv[j] (inv[j] = 1 / cum at j's last update); the row kernel
+// folds it into x (fm_rows_stream.cuh), so the gradient it scatters is the true one times the same
+// factor.  Two flat kernels then update the touched features only: the P rows (one thread per element,
+// flag-gated, no synchronisation) and the per-feature state (w, inv, flag; block 0 also folds the row
+// kernel's partials into the intercept step and the epoch's loss sum, i.e. reduce_partials + add_tail +
+// the tid == 0 branch of mbpsgd_step_kernel).  SB8 = 1 << shift.
+static __global__ void __launch_bounds__(256) mbpsgd_lazy_P_kernel(double *__restrict__ P, double *__restrict__ gP,
+                                                                   int shift, int64_t nP,
+                                                                   const uint8_t *__restrict__ flag,
+                                                                   const double2 *__restrict__ inv, double cumPt,
+                                                                   double negEtaP, double rP) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (int64_t e0 = tid; e0 < nP; e0 += 4 * stride) {
+    bool on[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int64_t e = e0 + i * stride;
+      on[i] = e < nP && flag[e >> shift] != 0;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (!on[i]) continue;
+      const int64_t e = e0 + i * stride;
+      const double fac = cumPt * inv[e >> shift].x;
+      const double p = P[e] * fac + negEtaP * (gP[e] / fac);
+      P[e] = p * rP;
+      gP[e] = 0.0;
+    }
+  }
+}
+
+static __global__ void __launch_bounds__(256) mbpsgd_lazy_feat_kernel(
+    int64_t dd, int64_t d, double *w, double *gw, uint8_t *flag, double2 *inv, double cumPt, double cumWt,
+    double invPnext, double invWnext, double negEtaW, double rW, int fitLinear, double *b, const double *partials,
+    int64_t partialRows, double negEtaB, double rB, int fitIntercept, double *scal) {
+  __shared__ double red[8];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < dd; j += stride) {
+    if (!flag[j]) continue;
+    const double2 iv = inv[j];
+    if (j < d) {
+      if (fitLinear) {
+        const double v = w[j] * (cumWt * iv.y) + negEtaW * (gw[j] / (cumPt * iv.x));
+        w[j] = v * rW;
+      }
+      gw[j] = 0.0;
+    }
+    inv[j] = make_double2(invPnext, invWnext);
+    flag[j] = 0;
+  }
+  if (blockIdx.x == 0) {
+    double acc0 = 0.0, acc1 = 0.0;
+    for (int64_t r = threadIdx.x; r < partialRows; r += 256) {
+      acc0 += partials[r * 4 + 0];
+      acc1 += partials[r * 4 + 1];
+    }
+    const double lossSum = block_sum(acc0, red);
+    __syncthreads();
+    const double gb = block_sum(acc1, red);
+    if (threadIdx.x == 0) {
+      double bb = b[0];
+      if (fitIntercept && fitLinear) bb += negEtaB * gb;   // params.nim:47
+      if (fitIntercept) bb *= rB;                          // params.nim:65-66
+      b[0] = bb;
+      scal[0] += lossSum;
+    }
+  }
+}
+
+// end of a lazy epoch: every feature receives the shrink it still owes (P here, w + the reset of inv below)
+static __global__ void mbpsgd_lazy_flush_P_kernel(double *P, int shift, int64_t nP, const double2 *inv, double cumPT) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nP; e += stride) P[e] *= cumPT * inv[e >> shift].x;
+}
+static __global__ void mbpsgd_lazy_flush_feat_kernel(double *w, int64_t d, int fitLinear, double2 *inv, int64_t dd,
+                                                     double cumWT) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < dd; j += stride) {
+    if (fitLinear && j < d) w[j] *= cumWT * inv[j].y;
+    inv[j] = make_double2(1.0, 1.0);
+  }
+}
+
 // ------------------------------------------------------------------ AdaGrad dense kernels (K5)
 // A minibatch runs: count -> [all-reduce counts] -> refresh -> row kernel (reads P, scatters the
 // deltas) -> [all-reduce deltas] -> scalar + apply.

@@ -58,7 +58,7 @@ __global__ void permute_solver_dev(const double *S, double *D, int nO, int k, in
 // ------------------------------------------------------------------ launch planning
 struct RowPlan {
   RowKernel kern;
-  bool fast;
+  bool fast, stream;
   int G, CH, block, grid;
   size_t smem;
   int64_t nWarps;
@@ -144,6 +144,7 @@ static int plan_rows(nimfm_ctx *ctx, const nimfm_fm *fm, const nimfm_dataset *X,
     return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "row kernel does not fit on an SM (perGroup=%zu B)", perGroup);
   pl->kern = kern;
   pl->fast = fast != nullptr;
+  pl->stream = stream;
   pl->G = G;
   pl->CH = (int)CH;
   pl->block = bestBlock;
@@ -236,6 +237,8 @@ int32_t nimfm_fm_free(nimfm_ctx *ctx, nimfm_fm *fm) {
                     fm->adaScal, fm->scalingsP, fm->scalingsW, fm->sgdScal, fm->Pcm, fm->yPred, fm->Acache,
                     fm->colNormSq, fm->cdScal, fm->proxState, fm->psgdThr})
     cudaFree(p);
+  cudaFree(fm->lazyInv);
+  cudaFree(fm->lazyFlag);
   delete fm;
   return NIMFM_OK;
 }
@@ -394,12 +397,20 @@ int32_t nimfm_fm_decision_function(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dat
 }
 
 // ================================================================== K2: predict + grad
+// the lazy MBPSGD epoch's view of the pending shrink (RowArgs::lazy*); partialRows returns the number of
+// partial rows the kernel wrote (the lazy step reduces them itself: no reduce_partials launch)
+struct LazyView {
+  double cumPt = 1.0, cumWt = 1.0;
+  int64_t partialRows = 0;
+};
+
 static int launch_loss_grad(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, int loss, double thr,
                             int64_t rowBegin, int64_t nRows, const int32_t *rowIdxDev, double mb,
-                            double *yOutDev) {
+                            double *yOutDev, LazyView *lazy = nullptr) {
   RowPlan pl;
   int rc = plan_rows(ctx, fm, X, nRows, MODE_GRAD, &pl);
   if (rc) return rc;
+  if (lazy && !pl.stream) return nimfm_fail(ctx, NIMFM_ERR_STATE, "lazy step without the streaming row kernel");
   RowKernel kern = pl.kern;
   if ((rc = nimfm_ensure_partials(ctx, (size_t)pl.nWarps * 4))) return rc;
   RowArgs a;
@@ -416,8 +427,16 @@ static int launch_loss_grad(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X
   a.mb = mb;
   a.G = pl.G;
   a.CH = pl.CH;
+  if (lazy) {
+    a.lazyInv = fm->lazyInv;
+    a.lazyFlag = fm->lazyFlag;
+    a.lazyCumPt = lazy->cumPt;
+    a.lazyCumWt = lazy->cumWt;
+    lazy->partialRows = pl.nWarps;
+  }
   kern<<<pl.grid, pl.block, pl.smem, ctx->stream>>>(a);
   LAUNCHED(ctx);
+  if (lazy) return NIMFM_OK;
   // tail += [sum coef, sum loss]: partial columns are (loss, coef, dL^2, viol) -> reorder via scratch
   reduce_partials_kernel<<<1, 256, 0, ctx->stream>>>(ctx->partials, pl.nWarps, ctx->scalars + 8, 0);
   LAUNCHED(ctx);
@@ -582,6 +601,78 @@ int32_t nimfm_fm_mbpsgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset 
   CK(cudaMemsetAsync(fm->grad, 0, (size_t)nG * 8, ctx->stream));       // grads <- 0 (:99)
   CK(cudaMemsetAsync(ctx->scalars, 0, 8, ctx->stream));
   int64_t cur = *ii;
+  // ---- lazy epoch (dense_kernels.cuh, K3b): one rank, no prox, minibatches that touch a minority of the
+  // features.  Same iterates as the dense step up to the rounding of the accumulated shrink factors.
+  {
+    const int64_t T = cfg->maxIterInner;
+    const bool noProx = cfg->reg == NIMFM_REG_IDENTITY || cfg->gamma == 0.0;   // lam = 0: every prox is the identity
+    const char *env = getenv("NIMFM_MBPSGD_LAZY");
+    const double touchedUpper = (double)localBatch * ((double)X->nnz / (double)X->n + fm->nAug);
+    bool lazy = ctx->nranks == 1 && noProx && T >= 2 && T < (1 << 30) && touchedUpper <= 2.0 * (double)fm->dd();   // measured crossover on the C3 shape: between 1.3 and 5 nnz per feature
+    if (env) lazy = env[0] == '1' && ctx->nranks == 1 && noProx && T < (1 << 30);
+    RowPlan plq;
+    if (lazy && (plan_rows(ctx, fm, X, localBatch, MODE_GRAD, &plq) != NIMFM_OK || !plq.stream)) lazy = false;
+    { const int sb = fm->nOrders * fm->k; if (sb & (sb - 1)) lazy = false; }   // the flat step shifts by log2(SB8)
+    std::vector<double> cum;
+    if (lazy) {   // cumulative shrink tables cum[t] = prod_{s<t} 1 / (1 + eta_s * reg); too small a product: dense
+      cum.assign(2 * (size_t)(T + 1), 1.0);
+      for (int64_t t = 0; t < T; t++) {
+        const double etaP = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->beta, *it + t);
+        const double etaW = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->alpha, *it + t);
+        cum[t + 1] = cum[t] * (1.0 / (1.0 + etaP * cfg->beta));
+        cum[T + 1 + t + 1] = cum[T + 1 + t] * (1.0 / (1.0 + etaW * cfg->alpha));
+      }
+      if (!(cum[T] > 1e-100) || !(cum[2 * T + 1] > 1e-100)) lazy = false;
+    }
+    if (lazy) {
+      const int64_t dd = fm->dd();
+      const int SB8 = fm->nOrders * fm->k;
+      int shift = 0;
+      while ((1 << shift) < SB8) shift++;
+      if (!fm->lazyInv) {
+        CK(cudaMalloc(&fm->lazyInv, (size_t)dd * sizeof(double2)));
+        CK(cudaMalloc(&fm->lazyFlag, (size_t)dd));
+        CK(cudaMemsetAsync(fm->lazyFlag, 0, (size_t)dd, ctx->stream));
+        mbpsgd_lazy_flush_feat_kernel<<<ew_grid(ctx, dd), 256, 0, ctx->stream>>>(nullptr, 0, 0, fm->lazyInv, dd, 1.0);
+        LAUNCHED(ctx);
+      }
+      const int grid = ctx->numSMs * 8;
+      for (int64_t inner = 0; inner < T; inner++) {
+        LazyView lv;
+        lv.cumPt = cum[inner];
+        lv.cumWt = cum[T + 1 + inner];
+        if ((rc = launch_loss_grad(ctx, fm, X, cfg->loss, cfg->huberThreshold, cur, localBatch,
+                                   idxDev ? idxDev + inner * localBatch : nullptr, (double)cfg->miniBatchSize, nullptr, &lv)))
+          return rc;
+        const double etaP = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->beta, *it);
+        const double etaW = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->alpha, *it);
+        const double etaB = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->alpha0, *it);
+        const double rP = 1.0 / (1.0 + etaP * cfg->beta), rW = 1.0 / (1.0 + etaW * cfg->alpha),
+                     rB = 1.0 / (1.0 + etaB * cfg->alpha0);
+        mbpsgd_lazy_P_kernel<<<grid, 256, 0, ctx->stream>>>(fm->P, fm->grad, shift, nP, fm->lazyFlag, fm->lazyInv, lv.cumPt,
+                                                            -etaP, rP);
+        LAUNCHED(ctx);
+        mbpsgd_lazy_feat_kernel<<<(int)std::min<int64_t>((dd + 255) / 256, grid), 256, 0, ctx->stream>>>(
+            dd, d, fm->w, fm->grad + nP, fm->lazyFlag, fm->lazyInv, lv.cumPt, lv.cumWt, 1.0 / cum[inner + 1],
+            1.0 / cum[T + 1 + inner + 1], -etaW, rW, fm->fitLinear, fm->b, ctx->partials, lv.partialRows, -etaB, rB,
+            fm->fitIntercept, ctx->scalars);
+        LAUNCHED(ctx);
+        *it += 1;
+        cur = (cur + localBatch) % X->n;
+      }
+      mbpsgd_lazy_flush_P_kernel<<<ew_grid(ctx, nP), 256, 0, ctx->stream>>>(fm->P, shift, nP, fm->lazyInv, cum[T]);
+      LAUNCHED(ctx);
+      mbpsgd_lazy_flush_feat_kernel<<<ew_grid(ctx, dd), 256, 0, ctx->stream>>>(fm->w, d, fm->fitLinear, fm->lazyInv, dd,
+                                                                             cum[2 * T + 1]);
+      LAUNCHED(ctx);
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(ctx->hostScalars, ctx->scalars, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      *ii = cur;
+      if (runningLoss) *runningLoss = ctx->hostScalars[0] / (double)(cfg->miniBatchSize * cfg->maxIterInner);
+      return NIMFM_OK;
+    }
+  }
   for (int64_t inner = 0; inner < cfg->maxIterInner; inner++) {
     if ((rc = launch_loss_grad(ctx, fm, X, cfg->loss, cfg->huberThreshold, cur, localBatch,
                                idxDev ? idxDev + inner * localBatch : nullptr, (double)cfg->miniBatchSize, nullptr)))

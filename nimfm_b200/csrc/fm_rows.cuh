@@ -56,6 +56,12 @@ struct RowArgs {
   const uint8_t *hotSlot;   // [d], 255 = cold
   const int32_t *hotList;   // [nHot] feature id of each slot
   int nHot;
+  // lazy L2 shrink of MBPSGD (fm_api.cu, "lazy" epoch): feature j was last brought up to date at inner
+  // step l(j); its effective parameters are the stored ones times cum[t] / cum[l(j)], with
+  // lazyInv[j] = {1 / cumP[l(j)], 1 / cumW[l(j)]}
+  const double2 *lazyInv;           // nullptr: parameters are current (every other caller)
+  double lazyCumPt, lazyCumWt;      // cum[t] of the current inner step
+  uint8_t *lazyFlag;                // [d+nAug] set for every feature this minibatch touches
   // geometry
   int G, CH;
 };

@@ -77,7 +77,19 @@ __global__ void __launch_bounds__(256, 2) fm_rows_stream_kernel(const RowArgs a)
       if (u < zReal) {
         m.j = a.indices[rb + u];
         m.x = a.data[rb + u];
-        lin += a.w[m.j] * m.x;
+        double wj = a.w[m.j];
+        const double xo = m.x;
+        if constexpr (MODE == MODE_GRAD) {
+          if (a.lazyInv) {
+            // the shrink this feature has not received yet goes into x (ANOVA sees only p*x); the
+            // gradient then comes out times the same factor and the lazy step divides it back
+            const double2 iv = a.lazyInv[m.j];
+            wj *= a.lazyCumWt * iv.y;
+            m.x *= a.lazyCumPt * iv.x;
+            a.lazyFlag[m.j] = 1;
+          }
+        }
+        lin += wj * xo;
         m.acc = -1;
         if (MODE != MODE_PREDICT && a.hotSlot) {
           const int slot = a.hotSlot[m.j];
@@ -86,6 +98,12 @@ __global__ void __launch_bounds__(256, 2) fm_rows_stream_kernel(const RowArgs a)
       } else {
         m.j = (int32_t)(a.d + (u - zReal));
         m.x = 1.0;
+        if constexpr (MODE == MODE_GRAD) {
+          if (a.lazyInv) {
+            m.x = a.lazyCumPt * a.lazyInv[m.j].x;
+            a.lazyFlag[m.j] = 1;
+          }
+        }
         m.acc = (MODE != MODE_PREDICT) ? (a.nHot + (u - zReal)) * ASTR : -1;
       }
       sMeta[u] = m;

@@ -318,6 +318,49 @@ def test_mbpsgd_objective_matches_oracle(oracle, degree, fit_lower, reg, fit_lin
     assert opt.it == ref["it"]
 
 
+@pytest.mark.parametrize("degree,fit_lower", [(2, "explicit"), (3, "explicit"), (3, "augment"), (2, "none")])
+@pytest.mark.parametrize("k", [8, 32])
+@pytest.mark.parametrize("fit_linear,fit_intercept,shuffle", [(True, True, False), (False, True, True), (True, False, True)])
+def test_mbpsgd_lazy_epoch_matches_oracle(oracle, monkeypatch, degree, fit_lower, k, fit_linear, fit_intercept, shuffle):
+    """the lazy epoch (touched features only; pending L2 shrink folded into x by the row kernel, K3b) gives
+    the reference's iterates (minibatch_psgd.nim:91-124): sparse ragged rows so that most features sit out
+    most minibatches, strong L2 so that the skipped shrink steps are visible; the "optimal" schedule gives
+    every step its own eta, hence its own shrink factor"""
+    n, d = 240, 150
+    csr = ragged_csr(n, d, 23, 6)
+    y = np.sign(np.random.default_rng(6).standard_normal(n))
+    P, w, _ = make_fm_params(d, degree, k, fit_lower, fit_linear, seed=12, scale=0.1)
+    kw = dict(eta0=0.3, alpha0=1e-3, alpha=5e-2, beta=8e-2, gamma=0.0)
+    perms = None
+    if shuffle:   # the permutations the host mirror will draw (initial shuffle + one per wrap-around)
+        fm0 = make_fm(degree, k, fit_lower, fit_linear, fit_intercept, P, w, 0.1, task=nf.classification)
+        rng = np.random.default_rng(fm0.randomState)
+        idx = np.arange(n)
+        perms = []
+        for _ in range(9):
+            rng.shuffle(idx)
+            perms.append(idx.copy())
+        perms = np.array(perms)
+    ref = oracle.mbpsgd_fit(csr, y, P, w, 0.1, degree, "logistic", fit_linear, fit_intercept, max_iter=4,
+                            reg="identity", mini_batch_size=9, it=0, perms=perms, **kw)
+    got = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NIMFM_MBPSGD_LAZY", mode)
+        fm = make_fm(degree, k, fit_lower, fit_linear, fit_intercept, P, w, 0.1, task=nf.classification)
+        opt = nf.newMBPSGD(maxIter=4, loss=nf.Logistic(), reg=nf.L1(), miniBatchSize=9, verbose=0, tol=0.0,
+                           shuffle=shuffle, **kw)
+        before = _lib.launch_count()
+        opt.fit(csr_ds(csr), y, fm)
+        got[mode] = (fm, opt, _lib.launch_count() - before)
+        np.testing.assert_allclose(opt.history, ref["epoch_loss"], rtol=OBJ_TOL)
+        assert max_rel(fm.P, ref["P"]) <= 1e-9 and max_rel(fm.w, ref["w"]) <= 1e-9
+        assert abs(fm.intercept - ref["intercept"]) <= 1e-9 * max(abs(ref["intercept"]), 1e-3)
+        assert opt.it == ref["it"]
+    # the lazy epoch really ran: 2 launches per minibatch instead of 4
+    assert got["1"][2] < got["0"][2]
+    assert max_rel(got["1"][0].P, got["0"][0].P) <= 1e-11
+
+
 def test_mbpsgd_default_regulariser_is_degree2_only():
     """newMBPSGD's default reg is SquaredL12 (minibatch_psgd.nim:26-27) whose initSGD raises for any
     other degree (squaredl12.nim:103-106), whatever gamma is"""
