@@ -267,7 +267,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=10_000_000, help="rows per GPU (weak scaling)")
-    ap.add_argument("--e2e-rows", type=int, default=2_000_000, help="rows per end-to-end step (host buffers)")
+    ap.add_argument("--e2e-rows", type=int, default=10_000_000,
+                    help="rows per end-to-end step (host buffers); default: the same batch as the device-resident step")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bounded CPU-baseline sample")
     ap.add_argument("--ref-rows", type=int, default=100_000)
