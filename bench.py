@@ -267,8 +267,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=10_000_000, help="rows per GPU (weak scaling)")
-    ap.add_argument("--e2e-rows", type=int, default=10_000_000,
-                    help="rows per end-to-end step (host buffers); default: the same batch as the device-resident step")
+    ap.add_argument("--e2e-rows", type=int, default=0,
+                    help="rows per end-to-end step (host buffers); default: the whole 10 M-row batch of the "
+                         "device-resident step on one GPU, 2 M rows per rank under torchrun (pinned host memory "
+                         "of 8 ranks on one box)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bounded CPU-baseline sample")
     ap.add_argument("--ref-rows", type=int, default=100_000)
@@ -375,7 +377,7 @@ def main():
                                  "frac": B_FWD * n / (fms.value / 1e3) / 1e9 / peak}}
 
     # ---- end to end through the C ABI with HOST buffers (pinned), H2D inside the timed region
-    ne = min(args.e2e_rows, n)
+    ne = min(args.e2e_rows if args.e2e_rows > 0 else (10_000_000 if world == 1 else 2_000_000), n)
     hb = [torch.from_numpy(a).pin_memory() for a in (data[:ne * Z], indices[:ne * Z], indptr[:ne + 1], y[:ne])]
     hp = [C.c_void_p(t_.data_ptr()) for t_ in hb]
     h2d = sum(t_.numel() * t_.element_size() for t_ in hb)
