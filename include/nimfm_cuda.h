@@ -65,6 +65,8 @@ int32_t nimfm_version(void);
 int64_t nimfm_launch_count(const nimfm_ctx *ctx);
 /* what the last host-fed call (nimfm_fm_loss_grad_host / nimfm_fm_decision_function_host) moved over the link:
  * bytes host->device, bytes device->host, and the host staging threads it used (0: ids narrowed on the device) */
+/* free / total bytes of the context's device (cudaMemGetInfo) */
+int32_t nimfm_mem_info(nimfm_ctx *ctx, int64_t *freeBytes, int64_t *totalBytes);
 int32_t nimfm_stream_stats(const nimfm_ctx *ctx, int64_t *h2dBytes, int64_t *d2hBytes, int32_t *hostThreads);
 
 /* Multi-GPU (one process per GPU).  The reference has no distributed backend; this is
@@ -120,6 +122,19 @@ int32_t nimfm_load_user_item_rating(nimfm_ctx *ctx, const char *path, int32_t as
  * newStreamCSCDataset, dataset.nim:170-179, without the window cache); pathY (nullable) is the raw float64
  * label file of loadStreamLabel (dataset.nim:995-1014). */
 int32_t nimfm_load_stream(nimfm_ctx *ctx, const char *pathX, const char *pathY, nimfm_dataset **out);
+/* The window cache (tensor/sparse_stream.nim:232-270; StreamCSRDataset, dataset.nim:1017-1402) with HBM as the
+ * cache: an open handle indexes the file's segments once, nimfm_stream_window_end sizes a window of at most
+ * maxBytes of file payload (>= 1 row), nimfm_stream_load_window makes rows [segBegin, segEnd) a resident CSR
+ * dataset (indptr rebased, labels attached when pathY was given).  A file larger than device memory is
+ * processed window by window; StreamCSC files load whole only (a window of columns is another matrix). */
+typedef struct nimfm_stream nimfm_stream;
+int32_t nimfm_stream_open(nimfm_ctx *ctx, const char *pathX, const char *pathY, nimfm_stream **out);
+int32_t nimfm_stream_info(const nimfm_stream *sh, int32_t *kind, int64_t *nRows, int64_t *nCols, int64_t *nnz,
+                          int64_t *maxSegNnz, int64_t *payloadBytes);
+int64_t nimfm_stream_window_end(const nimfm_stream *sh, int64_t segBegin, int64_t maxBytes);
+int32_t nimfm_stream_load_window(nimfm_ctx *ctx, nimfm_stream *sh, int64_t segBegin, int64_t segEnd,
+                                 nimfm_dataset **out);
+int32_t nimfm_stream_close(nimfm_stream *sh);
 int32_t nimfm_dataset_get_targets(nimfm_ctx *ctx, const nimfm_dataset *ds, double *y);
 
 /* ---------------------------------------------------------------- FM model state

@@ -138,6 +138,12 @@ proc nimfm_ffm_sgd_end(ctx: Ctx, m: DeviceFFM): int32
 # ---- the remaining entry points of include/nimfm_cuda.h (diagnostics, state transfer, measurement hooks)
 proc nimfm_version(): int32
 proc nimfm_launch_count(ctx: Ctx): int64
+proc nimfm_stream_open(ctx: Ctx, pathX, pathY: cstring, sh: ptr pointer): int32
+proc nimfm_stream_info(sh: pointer, kind: ptr int32, nRows, nCols, nnz, maxSegNnz, payloadBytes: ptr int64): int32
+proc nimfm_stream_window_end(sh: pointer, segBegin, maxBytes: int64): int64
+proc nimfm_stream_load_window(ctx: Ctx, sh: pointer, segBegin, segEnd: int64, ds: ptr DeviceDataset): int32
+proc nimfm_stream_close(sh: pointer): int32
+proc nimfm_mem_info(ctx: Ctx, freeBytes, totalBytes: ptr int64): int32
 proc nimfm_stream_stats(ctx: Ctx, h2dBytes, d2hBytes: ptr int64, hostThreads: ptr int32): int32
 proc nimfm_comm_size(ctx: Ctx): int32
 proc nimfm_dataset_info(ds: DeviceDataset, n, d, nnz: ptr int64, kind: ptr int32, nFields, maxRowNnz: ptr int64): int32

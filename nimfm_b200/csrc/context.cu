@@ -56,6 +56,15 @@ int32_t nimfm_version(void) { return 100; }
 const char *nimfm_last_error(const nimfm_ctx *ctx) { return ctx ? ctx->err.c_str() : g_noctx_err.c_str(); }
 
 int64_t nimfm_launch_count(const nimfm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int32_t nimfm_mem_info(nimfm_ctx *ctx, int64_t *freeBytes, int64_t *totalBytes) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  size_t f = 0, t = 0;
+  CK(cudaMemGetInfo(&f, &t));
+  if (freeBytes) *freeBytes = (int64_t)f;
+  if (totalBytes) *totalBytes = (int64_t)t;
+  return NIMFM_OK;
+}
 int32_t nimfm_stream_stats(const nimfm_ctx *ctx, int64_t *h2dBytes, int64_t *d2hBytes, int32_t *hostThreads) {
   if (!ctx) return NIMFM_ERR_INVALID;
   if (h2dBytes) *h2dBytes = ctx->lastH2D;

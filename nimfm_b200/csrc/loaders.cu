@@ -192,6 +192,14 @@ int finish_upload(nimfm_ctx *ctx, int64_t n, int64_t d, std::vector<double> &dat
 // The reference reads them through a window cache because they may exceed host memory; a B200 holds
 // 180 GB, so the file is loaded whole: the host only hops over the counts (O(segments)), the raw
 // payload is uploaded as it is and de-interleaved on the device.
+struct nimfm_stream {
+  Mapped mx, my;
+  bool isCsr = true, hasY = false;
+  int64_t nRows = 0, nCols = 0, nnz = 0, nSeg = 0, extent = 0, maxSeg = 0, payloadEnd = 0;
+  std::vector<int64_t> segOff;   // byte offset (within the payload) of each segment's first record
+  std::vector<int64_t> indptr;
+};
+
 namespace {
 
 __global__ void stream_deinterleave_kernel(const unsigned char *payload, const int64_t *segByteOff,
@@ -307,11 +315,14 @@ int32_t nimfm_load_user_item_rating(nimfm_ctx *ctx, const char *path, int32_t as
   return finish_upload(ctx, n, n > 0 ? nUsers + nItems : 0, data, indices, indptr, nullptr, 0, y, asCsc, out);
 }
 
-int32_t nimfm_load_stream(nimfm_ctx *ctx, const char *pathX, const char *pathY, nimfm_dataset **out) {
+// ---- STREAMCSR / STREAMCSC files: an open handle indexes the segments once; windows of segments become
+// resident datasets on demand (the reference's cacheSize window, tensor/sparse_stream.nim:232-270, with HBM
+// as the cache), so a file larger than device memory is processed window by window.
+int32_t nimfm_stream_open(nimfm_ctx *ctx, const char *pathX, const char *pathY, nimfm_stream **out) {
   if (!ctx) return NIMFM_ERR_INVALID;
   REQUIRE(out != nullptr && pathX != nullptr, "NULL argument");
-  CK(cudaSetDevice(ctx->device));
-  Mapped m;
+  std::unique_ptr<nimfm_stream> sh(new nimfm_stream());
+  Mapped &m = sh->mx;
   m.fd = open(pathX, O_RDONLY);
   if (m.fd < 0) return nimfm_fail(ctx, NIMFM_ERR_INVALID, "%s cannot be opened.", pathX);      // sparse_stream.nim:103-104
   struct stat st;
@@ -326,29 +337,95 @@ int32_t nimfm_load_stream(nimfm_ctx *ctx, const char *pathX, const char *pathY, 
   REQUIRE(!(m.n >= 14 && memcmp(m.p + 9, "FIELD", 5) == 0), "field stream files are not supported");
   int64_t hdr[3];
   memcpy(hdr, m.p + 9, 24);
-  const int64_t nRows = hdr[0], nCols = hdr[1], nnz = hdr[2];
-  REQUIRE(nRows >= 0 && nCols >= 0 && nnz >= 0, "corrupt header in %s", pathX);
-  const int64_t nSeg = isCsr ? nRows : nCols, extent = isCsr ? nCols : nRows;
-  REQUIRE(extent < (int64_t)2147483647, "index extent %lld does not fit int32", (long long)extent);
+  sh->isCsr = isCsr;
+  sh->nRows = hdr[0]; sh->nCols = hdr[1]; sh->nnz = hdr[2];
+  REQUIRE(sh->nRows >= 0 && sh->nCols >= 0 && sh->nnz >= 0, "corrupt header in %s", pathX);
+  sh->nSeg = isCsr ? sh->nRows : sh->nCols;
+  sh->extent = isCsr ? sh->nCols : sh->nRows;
+  REQUIRE(sh->extent < (int64_t)2147483647, "index extent %lld does not fit int32", (long long)sh->extent);
   const size_t payloadBytes = m.n - 49;
-  std::vector<int64_t> segOff((size_t)nSeg), indptr((size_t)nSeg + 1, 0);
-  int64_t off = 0, maxSeg = 0;
-  for (int64_t sgm = 0; sgm < nSeg; sgm++) {
+  sh->segOff.resize((size_t)sh->nSeg);
+  sh->indptr.assign((size_t)sh->nSeg + 1, 0);
+  int64_t off = 0;
+  for (int64_t sgm = 0; sgm < sh->nSeg; sgm++) {
     REQUIRE((size_t)off + 8 <= payloadBytes, "%s is truncated (segment %lld)", pathX, (long long)sgm);
     int64_t cnt;
     memcpy(&cnt, m.p + 49 + off, 8);
     REQUIRE(cnt >= 0 && (size_t)off + 8 + 16 * (size_t)cnt <= payloadBytes, "%s is truncated (segment %lld)", pathX,
             (long long)sgm);
-    segOff[(size_t)sgm] = off + 8;
-    indptr[(size_t)sgm + 1] = indptr[(size_t)sgm] + cnt;
-    maxSeg = std::max(maxSeg, cnt);
+    sh->segOff[(size_t)sgm] = off + 8;
+    sh->indptr[(size_t)sgm + 1] = sh->indptr[(size_t)sgm] + cnt;
+    sh->maxSeg = std::max(sh->maxSeg, cnt);
     off += 8 + 16 * cnt;
   }
-  REQUIRE(indptr[(size_t)nSeg] == nnz, "%s: header nnz %lld != %lld elements found", pathX, (long long)nnz,
-          (long long)indptr[(size_t)nSeg]);
+  sh->payloadEnd = off;
+  REQUIRE(sh->indptr[(size_t)sh->nSeg] == sh->nnz, "%s: header nnz %lld != %lld elements found", pathX,
+          (long long)sh->nnz, (long long)sh->indptr[(size_t)sh->nSeg]);
+  if (pathY && pathY[0]) {            // loadStreamLabel (dataset.nim:995-1014): raw float64 targets
+    Mapped &my = sh->my;
+    my.fd = open(pathY, O_RDONLY);
+    if (my.fd < 0) return nimfm_fail(ctx, NIMFM_ERR_INVALID, "%s cannot be opened.", pathY);
+    struct stat sy;
+    if (fstat(my.fd, &sy) != 0 || (int64_t)sy.st_size < sh->nRows * 8)
+      return nimfm_fail(ctx, NIMFM_ERR_INVALID, "%s holds fewer than %lld labels", pathY, (long long)sh->nRows);
+    sh->hasY = true;
+  }
+  *out = sh.release();
+  return NIMFM_OK;
+}
+
+int32_t nimfm_stream_info(const nimfm_stream *sh, int32_t *kind, int64_t *nRows, int64_t *nCols, int64_t *nnz,
+                          int64_t *maxSegNnz, int64_t *payloadBytes) {
+  if (!sh) return NIMFM_ERR_INVALID;
+  if (kind) *kind = sh->isCsr ? NIMFM_DS_CSR : NIMFM_DS_CSC;
+  if (nRows) *nRows = sh->nRows;
+  if (nCols) *nCols = sh->nCols;
+  if (nnz) *nnz = sh->nnz;
+  if (maxSegNnz) *maxSegNnz = sh->maxSeg;
+  if (payloadBytes) *payloadBytes = sh->payloadEnd;
+  return NIMFM_OK;
+}
+
+// the largest segEnd such that segments [segBegin, segEnd) hold at most maxBytes of file payload (always at
+// least one segment): how the reference sizes a cache window (sparse_stream.nim:232-270, cacheSize in bytes)
+int64_t nimfm_stream_window_end(const nimfm_stream *sh, int64_t segBegin, int64_t maxBytes) {
+  if (!sh || segBegin < 0 || segBegin >= sh->nSeg) return sh ? sh->nSeg : 0;
+  const int64_t start = sh->segOff[(size_t)segBegin] - 8;
+  // segOff is increasing: first segment whose end offset exceeds start + maxBytes
+  int64_t lo = segBegin + 1, hi = sh->nSeg;
+  while (lo < hi) {
+    const int64_t mid = lo + (hi - lo + 1) / 2;
+    const int64_t endOff = mid < sh->nSeg ? sh->segOff[(size_t)mid] - 8 : sh->payloadEnd;
+    if (endOff - start <= maxBytes) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+int32_t nimfm_stream_load_window(nimfm_ctx *ctx, nimfm_stream *sh, int64_t segBegin, int64_t segEnd,
+                                 nimfm_dataset **out) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  REQUIRE(sh != nullptr && out != nullptr, "NULL argument");
+  REQUIRE(segBegin >= 0 && segBegin <= segEnd && segEnd <= sh->nSeg, "window [%lld,%lld) outside [0,%lld)",
+          (long long)segBegin, (long long)segEnd, (long long)sh->nSeg);
+  // a window of columns would be a matrix with other column ids: only rows can be windowed
+  REQUIRE(sh->isCsr || (segBegin == 0 && segEnd == sh->nSeg), "a StreamCSC file is loaded whole");
+  CK(cudaSetDevice(ctx->device));
+  const int64_t nSeg = segEnd - segBegin;
+  const int64_t nnz = sh->indptr[(size_t)segEnd] - sh->indptr[(size_t)segBegin];
+  const int64_t byteBegin = nSeg ? sh->segOff[(size_t)segBegin] - 8 : 0;
+  const int64_t byteEnd = nSeg ? (segEnd < sh->nSeg ? sh->segOff[(size_t)segEnd] - 8 : sh->payloadEnd) : 0;
+  const size_t payloadBytes = (size_t)(byteEnd - byteBegin);
+  std::vector<int64_t> segOff((size_t)nSeg), indptr((size_t)nSeg + 1, 0);
+  int64_t maxSeg = 0;
+  for (int64_t g = 0; g < nSeg; g++) {
+    segOff[(size_t)g] = sh->segOff[(size_t)(segBegin + g)] - byteBegin;
+    indptr[(size_t)g + 1] = sh->indptr[(size_t)(segBegin + g + 1)] - sh->indptr[(size_t)segBegin];
+    maxSeg = std::max(maxSeg, indptr[(size_t)g + 1] - indptr[(size_t)g]);
+  }
   nimfm_dataset *ds = new nimfm_dataset();
-  ds->kind = isCsr ? NIMFM_DS_CSR : NIMFM_DS_CSC;
-  ds->n = nRows; ds->d = nCols; ds->nnz = nnz; ds->maxSegNnz = maxSeg;
+  ds->kind = sh->isCsr ? NIMFM_DS_CSR : NIMFM_DS_CSC;
+  ds->n = sh->isCsr ? nSeg : sh->nRows;
+  ds->d = sh->nCols; ds->nnz = nnz; ds->maxSegNnz = maxSeg;
   auto fail = [&](int rc) { nimfm_dataset_free(ctx, ds); return rc; };
   unsigned char *dPayload = nullptr;
   int64_t *dSegOff = nullptr;
@@ -362,13 +439,14 @@ int32_t nimfm_load_stream(nimfm_ctx *ctx, const char *pathX, const char *pathY, 
   ck(cudaMalloc(&ds->data, (size_t)std::max<int64_t>(nnz, 2) * 8));
   ck(cudaMalloc(&ds->indices, (size_t)std::max<int64_t>(nnz, 4) * 4));
   if (ce == cudaSuccess) {
-    ck(cudaMemcpyAsync(dPayload, m.p + 49, payloadBytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (payloadBytes)
+      ck(cudaMemcpyAsync(dPayload, sh->mx.p + 49 + byteBegin, payloadBytes, cudaMemcpyHostToDevice, ctx->stream));
     if (nSeg) ck(cudaMemcpyAsync(dSegOff, segOff.data(), (size_t)nSeg * 8, cudaMemcpyHostToDevice, ctx->stream));
     ck(cudaMemcpyAsync(ds->indptr, indptr.data(), ((size_t)nSeg + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     ck(cudaMemsetAsync(dBad, 0, sizeof(int), ctx->stream));
     if (nSeg > 0 && nnz > 0) {
       const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nSeg * 32 + 255) / 256, (int64_t)ctx->numSMs * 16));
-      stream_deinterleave_kernel<<<grid, 256, 0, ctx->stream>>>(dPayload, dSegOff, ds->indptr, nSeg, extent, ds->data,
+      stream_deinterleave_kernel<<<grid, 256, 0, ctx->stream>>>(dPayload, dSegOff, ds->indptr, nSeg, sh->extent, ds->data,
                                                                 ds->indices, dBad);
       LAUNCHED(ctx);
     }
@@ -379,31 +457,47 @@ int32_t nimfm_load_stream(nimfm_ctx *ctx, const char *pathX, const char *pathY, 
     if (ce == cudaSuccess && hbad) {
       cudaFree(dPayload); cudaFree(dSegOff); cudaFree(dBad);
       nimfm_dataset_free(ctx, ds);
-      return nimfm_fail(ctx, NIMFM_ERR_INVALID, "%s: element id out of range [0,%lld)", pathX, (long long)extent);
+      return nimfm_fail(ctx, NIMFM_ERR_INVALID, "stream file: element id out of range [0,%lld)", (long long)sh->extent);
     }
   }
   cudaFree(dPayload); cudaFree(dSegOff); cudaFree(dBad);
-  if (ce != cudaSuccess) return fail(nimfm_fail(ctx, NIMFM_ERR_CUDA, "nimfm_load_stream: %s", cudaGetErrorString(ce)));
+  if (ce != cudaSuccess) return fail(nimfm_fail(ctx, NIMFM_ERR_CUDA, "nimfm_stream_load_window: %s", cudaGetErrorString(ce)));
   if (ds->kind == NIMFM_DS_CSR) {   // no hot columns known for a stream: all cold (bookkeeping only)
     std::vector<int32_t> hot;
     int rc = nimfm_upload_hot(ctx, hot, ds->d, &ds->hotSlot, &ds->hotList);
     if (rc) return fail(rc);
   }
-  if (pathY && pathY[0]) {            // loadStreamLabel (dataset.nim:995-1014): raw float64 targets
-    Mapped my;
-    my.fd = open(pathY, O_RDONLY);
-    if (my.fd < 0) return fail(nimfm_fail(ctx, NIMFM_ERR_INVALID, "%s cannot be opened.", pathY));
-    struct stat sy;
-    if (fstat(my.fd, &sy) != 0 || (int64_t)sy.st_size < nRows * 8)
-      return fail(nimfm_fail(ctx, NIMFM_ERR_INVALID, "%s holds fewer than %lld labels", pathY, (long long)nRows));
-    std::vector<double> y((size_t)nRows);
-    if (nRows && pread(my.fd, y.data(), (size_t)nRows * 8, 0) != (ssize_t)(nRows * 8))
-      return fail(nimfm_fail(ctx, NIMFM_ERR_INVALID, "cannot read %s", pathY));
-    int rc = nRows ? nimfm_dataset_set_targets(ctx, ds, y.data()) : NIMFM_OK;
+  if (sh->hasY && sh->isCsr && nSeg > 0) {
+    std::vector<double> y((size_t)nSeg);
+    if (pread(sh->my.fd, y.data(), (size_t)nSeg * 8, (off_t)(segBegin * 8)) != (ssize_t)(nSeg * 8))
+      return fail(nimfm_fail(ctx, NIMFM_ERR_INVALID, "cannot read the label file"));
+    int rc = nimfm_dataset_set_targets(ctx, ds, y.data());
+    if (rc) return fail(rc);
+  } else if (sh->hasY && !sh->isCsr && sh->nRows > 0) {
+    std::vector<double> y((size_t)sh->nRows);
+    if (pread(sh->my.fd, y.data(), (size_t)sh->nRows * 8, 0) != (ssize_t)(sh->nRows * 8))
+      return fail(nimfm_fail(ctx, NIMFM_ERR_INVALID, "cannot read the label file"));
+    int rc = nimfm_dataset_set_targets(ctx, ds, y.data());
     if (rc) return fail(rc);
   }
   *out = ds;
   return NIMFM_OK;
+}
+
+int32_t nimfm_stream_close(nimfm_stream *sh) {
+  delete sh;
+  return NIMFM_OK;
+}
+
+int32_t nimfm_load_stream(nimfm_ctx *ctx, const char *pathX, const char *pathY, nimfm_dataset **out) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  REQUIRE(out != nullptr && pathX != nullptr, "NULL argument");
+  nimfm_stream *sh = nullptr;
+  int rc = nimfm_stream_open(ctx, pathX, pathY, &sh);
+  if (rc) return rc;
+  rc = nimfm_stream_load_window(ctx, sh, 0, sh->nSeg, out);
+  nimfm_stream_close(sh);
+  return rc;
 }
 
 int32_t nimfm_dataset_get_targets(nimfm_ctx *ctx, const nimfm_dataset *ds, double *y) {

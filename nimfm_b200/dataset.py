@@ -15,6 +15,7 @@ from . import _lib
 
 class BaseDataset:
     kind = _lib.DS_CSR
+    windowed = False      # True: a StreamCSRDataset kept on disk and walked window by window
 
     def __init__(self, data, indices, indptr, nSamples, nFeatures, fields=None, nFields=0):
         self.data = _lib.f64(data)
@@ -376,9 +377,129 @@ def _load_stream(fX, fY):
     return out, y
 
 
-def newStreamCSRDataset(f, cacheSize=200):
+class _DeviceCSRDataset(CSRDataset):
+    """A library-made CSR dataset that stays on the device: the host arrays are read back only if somebody
+    asks for them (a window of a stream file is used once and freed)."""
+
+    def __init__(self, h):
+        self._handle = h
+        self._y_id = None
+        inf = BaseDataset.info(self)
+        self._n, self._d, self._nFields, self._nnz = inf["n"], inf["d"], inf["nFields"], inf["nnz"]
+        self.fields = None
+
+    @property
+    def nnz(self):
+        return self._nnz
+
+    def __getattr__(self, name):
+        if name in ("data", "indices", "indptr"):
+            self.data, self.indices, self.indptr, _ = BaseDataset.download(self)
+            return self.__dict__[name]
+        raise AttributeError(name)
+
+
+class StreamCSRDataset(CSRDataset):
+    """newStreamCSRDataset (dataset.nim:170-173; StreamCSRDataset, dataset.nim:1017-1402) in its windowed
+    form: the file stays on disk, `windows()` yields one resident window of rows after another (HBM is the
+    cache; cacheSize MB of file payload per window, as in the reference).  decisionFunction and the
+    SGD / AdaGrad / MBPSGD fits walk the windows in file order; like the reference with nCached < nSamples
+    they do not shuffle (sgd.nim:297, minibatch_psgd.nim:110-111)."""
+    windowed = True
+
+    def __init__(self, f, cacheSize=200, fY=None):
+        self._path = _path(f)
+        self._sh = C.c_void_p()
+        lib = _lib.load()
+        _lib.check(lib.nimfm_stream_open(_lib.ctx(), self._path, None if fY is None else _path(fY), C.byref(self._sh)))
+        kind, n, d, nnz, mx, pay = C.c_int32(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(lib.nimfm_stream_info(self._sh, C.byref(kind), C.byref(n), C.byref(d), C.byref(nnz), C.byref(mx),
+                                         C.byref(pay)))
+        if kind.value != _lib.DS_CSR:
+            self.close()
+            raise IOError(f"{f} is not a StreamCSR file.")
+        self._n, self._d, self._nnz, self._nFields = n.value, d.value, nnz.value, 0
+        self.payloadBytes = pay.value
+        self.cacheBytes = max(int(cacheSize * 1024 * 1024), 1)
+        self._handle = None
+        self._y = None
+        self.fields = None
+
+    @property
+    def nnz(self):
+        return self._nnz
+
+    @property
+    def nCached(self):
+        """rows of the first window (dataset.nim's nCached: == nSamples iff the file fits the cache)"""
+        return self.window_end(0) if self._n else 0
+
+    def window_end(self, rowBegin, cacheBytes=None):
+        return int(_lib.load().nimfm_stream_window_end(self._sh, int(rowBegin),
+                                                       int(self.cacheBytes if cacheBytes is None else cacheBytes)))
+
+    def set_targets(self, y):
+        y = _lib.f64(y)
+        if len(y) != self._n:
+            raise ValueError("len(y) != nSamples")
+        self._y = y
+
+    def load_rows(self, a, b):
+        """rows [a, b) as a resident dataset (targets attached when set_targets was called)"""
+        h = C.c_void_p()
+        _lib.check(_lib.load().nimfm_stream_load_window(_lib.ctx(), self._sh, int(a), int(b), C.byref(h)))
+        win = _DeviceCSRDataset(h)
+        if self._y is not None and b > a:
+            win.set_targets(self._y[a:b])
+        return win
+
+    def windows(self, multiple=1, start=0):
+        """(rowBegin, rowEnd, dataset) over [start, nSamples) in file order; every window but the last holds
+        a multiple of `multiple` rows (minibatches never straddle a window)"""
+        a = int(start)
+        while a < self._n:
+            b = self.window_end(a)
+            if multiple > 1 and b < self._n:
+                b = a + max((b - a) // multiple, 1) * multiple
+                b = min(b, self._n)
+            win = self.load_rows(a, b)
+            try:
+                yield a, b, win
+            finally:
+                win.free()
+            a = b
+
+    def handle(self):
+        raise ValueError("a windowed StreamCSRDataset has no single device twin; iterate windows()")
+
+    def __getitem__(self, key):
+        raise ValueError("row access on a windowed StreamCSRDataset is not supported; use load_rows(a, b)")
+
+    def close(self):
+        if getattr(self, "_sh", None):
+            _lib.load().nimfm_stream_close(self._sh)
+            self._sh = None
+
+    free = close
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def newStreamCSRDataset(f, cacheSize=200, resident=None):
     """newStreamCSRDataset (dataset.nim:170-173).  The reference windows the file through a cacheSize-MB
-    cache; here the whole matrix becomes resident in HBM (cacheSize is accepted and ignored)."""
+    cache.  Here HBM is the cache: resident=True loads the whole matrix onto the device, resident=False
+    keeps the file on disk and walks cacheSize-MB windows of rows (StreamCSRDataset), resident=None picks
+    the resident form whenever the file's payload is at most a third of the free device memory."""
+    if resident is None:
+        free = C.c_int64()
+        _lib.check(_lib.load().nimfm_mem_info(_lib.ctx(), C.byref(free), None))
+        resident = os.path.getsize(_path(f)) * 3 <= free.value
+    if not resident:
+        return StreamCSRDataset(f, cacheSize)
     X, _ = _load_stream(f, None)
     if not isinstance(X, CSRDataset):
         raise IOError(f"{f} is not a StreamCSR file.")

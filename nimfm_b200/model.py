@@ -113,7 +113,11 @@ class FactorizationMachine(_FMBase):
         try:
             out = np.zeros(X.nSamples)
             lib = _lib.load()
-            if X._handle is None and not isinstance(X, CSCDataset):
+            if X.windowed:
+                # a stream file kept on disk: one resident window of rows after another
+                for a, b, win in X.windows():
+                    _lib.check(lib.nimfm_fm_decision_function(_lib.ctx(), h, win.handle(), _lib.ptr(out[a:b])))
+            elif X._handle is None and not isinstance(X, CSCDataset):
                 # no device twin yet: stream the host CSR through the row kernel (copy of chunk c+1
                 # overlaps the kernel of chunk c) instead of uploading a dataset first
                 _lib.check(lib.nimfm_fm_decision_function_host(

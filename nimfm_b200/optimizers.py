@@ -194,6 +194,18 @@ def newPCD(maxIter=100, alpha0=1e-6, alpha=1e-3, beta=1e-4, gamma=1e-4, loss=Non
     return PCD(maxIter, alpha0, alpha, beta, gamma, loss, reg, verbose, tol)
 
 
+def _windowed_epoch(epoch, ctx, h, X, cfg, it, viol, lossSum, multiple):
+    """One SGD / AdaGrad epoch over a StreamCSRDataset kept on disk: the per-sample (or per-minibatch) loop
+    runs over one resident window of rows after another, in file order, with the iteration counter and the
+    optimizer state carried across windows; viol and the loss sum add up (sgd.nim:298-307)."""
+    v, ls = C.c_double(), C.c_double()
+    viol.value, lossSum.value = 0.0, 0.0
+    for a, b, win in X.windows(multiple=multiple):
+        _lib.check(epoch(ctx, h, win.handle(), C.byref(cfg), C.byref(it), None, b - a, C.byref(v), C.byref(ls)))
+        viol.value += v.value
+        lossSum.value += ls.value
+
+
 # ================================================================ SGD
 class SGD(_Base):
     def __init__(self, maxIter=100, eta0=0.01, alpha0=1e-6, alpha=1e-3, beta=1e-3, loss=None,
@@ -214,6 +226,8 @@ class SGD(_Base):
         sgd_multi.nim:40) is accepted and ignored: the device path keeps the exact sequential
         semantics."""
         is_ffm = isinstance(fm, FieldAwareFactorizationMachine)
+        if X.windowed and is_ffm:
+            raise TypeError("field stream files are not supported")
         fm.init(X)
         y = fm.checkTarget(y)
         lib, ctx = _lib.load(), _lib.ctx()
@@ -238,13 +252,16 @@ class SGD(_Base):
             for ep in range(self.maxIter):
                 if perms is not None:
                     indices = _lib.i64(perms[ep])
-                elif self.shuffle:
+                elif self.shuffle and not X.windowed:      # sgd.nim:297: only a fully cached dataset is shuffled
                     rng.shuffle(indices)
                 it = C.c_int64(self.it)
                 viol, lossSum = C.c_double(), C.c_double()
                 t0 = time.perf_counter()
-                _lib.check(epoch(ctx, h, X.handle(), C.byref(cfg), C.byref(it), _lib.ptr(indices), n,
-                                 C.byref(viol), C.byref(lossSum)))
+                if X.windowed:
+                    _windowed_epoch(epoch, ctx, h, X, cfg, it, viol, lossSum, 1)
+                else:
+                    _lib.check(epoch(ctx, h, X.handle(), C.byref(cfg), C.byref(it), _lib.ptr(indices), n,
+                                     C.byref(viol), C.byref(lossSum)))
                 self.epoch_seconds.append(time.perf_counter() - t0)
                 self.it = it.value
                 runningLoss = lossSum.value / n
@@ -289,6 +306,8 @@ class AdaGrad(_Base):
     def fit(self, X, y, fm, maxThreads=None, callback=None, perms=None):
         """adagrad.nim:137-203 / adagrad_ffm.nim:11-66 (maxThreads of adagrad_multi.nim:39 is ignored)."""
         is_ffm = isinstance(fm, FieldAwareFactorizationMachine)
+        if X.windowed and is_ffm:
+            raise TypeError("field stream files are not supported")
         fm.init(X)
         y = fm.checkTarget(y)
         lib, ctx = _lib.load(), _lib.ctx()
@@ -338,13 +357,16 @@ class AdaGrad(_Base):
             for ep in range(self.maxIter):
                 if perms is not None:
                     indices = _lib.i64(perms[ep])
-                elif self.shuffle:
+                elif self.shuffle and not X.windowed:      # adagrad.nim:168: only a fully cached dataset is shuffled
                     rng.shuffle(indices)
                 it = C.c_int64(self.it)
                 viol, lossSum = C.c_double(), C.c_double()
                 t0 = time.perf_counter()
-                _lib.check(epoch(ctx, h, X.handle(), C.byref(cfg), C.byref(it), _lib.ptr(indices), n,
-                                 C.byref(viol), C.byref(lossSum)))
+                if X.windowed:
+                    _windowed_epoch(epoch, ctx, h, X, cfg, it, viol, lossSum, local)
+                else:
+                    _lib.check(epoch(ctx, h, X.handle(), C.byref(cfg), C.byref(it), _lib.ptr(indices), n,
+                                     C.byref(viol), C.byref(lossSum)))
                 self.epoch_seconds.append(time.perf_counter() - t0)
                 self.it = it.value
                 runningLoss = lossSum.value / (n * world)      # the loss sum is all-reduced; shards are even
@@ -567,6 +589,10 @@ class MBPSGD(_Base):
                              self.gamma, self.reg.kind, _lib.SCHED[self.scheduling], self.power, mb, inner)
         rng = self._rng(sfm)
         indices = np.arange(n, dtype=np.int64)
+        if X.windowed:
+            if _dist.world() > 1:
+                raise ValueError("a windowed StreamCSRDataset is not sharded across ranks")
+            self_shuffle, self.shuffle = self.shuffle, False    # :110-111,169: nCached < nSamples never shuffles
         if self.shuffle:
             rng.shuffle(indices)               # :169-170
         if self.verbose > 0:
@@ -596,8 +622,12 @@ class MBPSGD(_Base):
                             rng.shuffle(indices)
                 itc, iic, rl = C.c_int64(self.it), C.c_int64(ii), C.c_double()
                 t0 = time.perf_counter()
-                _lib.check(lib.nimfm_fm_mbpsgd_epoch(ctx, h, X.handle(), C.byref(cfg), local, C.byref(itc),
-                                                     C.byref(iic), _lib.ptr(sample), C.byref(rl)))
+                if X.windowed:
+                    rl.value, ii = self._windowed_epoch(lib, ctx, h, X, cfg, mb, inner, itc, ii)
+                    iic.value = ii
+                else:
+                    _lib.check(lib.nimfm_fm_mbpsgd_epoch(ctx, h, X.handle(), C.byref(cfg), local, C.byref(itc),
+                                                         C.byref(iic), _lib.ptr(sample), C.byref(rl)))
                 self.epoch_seconds.append(time.perf_counter() - t0)
                 self.it = itc.value
                 if not self.shuffle:
@@ -627,6 +657,52 @@ class MBPSGD(_Base):
             sfm._from_device(h)
         finally:
             lib.nimfm_fm_free(ctx, h)
+            if X.windowed:
+                self.shuffle = self_shuffle
+
+    @staticmethod
+    def _windowed_epoch(lib, ctx, h, X, cfg, mb, inner, itc, ii):
+        """epoch() (minibatch_psgd.nim:91-124) over a StreamCSRDataset kept on disk: the `inner` minibatches
+        are taken from resident windows of whole minibatches starting at the row cursor ii, wrapping to the
+        top of the file like the reference's cursor; returns (runningLoss, new cursor)."""
+        n = X.nSamples
+        total, left = 0.0, inner
+        while left > 0:
+            # as many whole minibatches as one cache window holds (at least one), without wrapping twice
+            b = X.window_end(ii)
+            k = max((b - ii) // mb, 1)
+            k = min(k, left, max((n - ii + mb - 1) // mb, 1))
+            rows = k * mb
+            parts = [X.load_rows(ii, min(n, ii + rows))]
+            rest = rows - (min(n, ii + rows) - ii)
+            while rest > 0:                     # the cursor wrapped (n < mb wraps more than once)
+                take = min(rest, n)
+                parts.append(X.load_rows(0, take))
+                rest -= take
+            win = parts[0]
+            if len(parts) > 1:
+                arr = (C.c_void_p * len(parts))(*[p_.handle() for p_ in parts])
+                hv = C.c_void_p()
+                _lib.check(lib.nimfm_dataset_vstack(ctx, arr, len(parts), C.byref(hv)))
+                from .dataset import _DeviceCSRDataset
+                win = _DeviceCSRDataset(hv)
+                win.set_targets(np.concatenate([X._y[ii:min(n, ii + rows)]] +
+                                               [X._y[:p_.nSamples] for p_ in parts[1:]]))
+            try:
+                sub = _lib.MbpsgdCfg.from_buffer_copy(cfg)
+                sub.maxIterInner = k
+                cur, rl = C.c_int64(0), C.c_double()
+                _lib.check(lib.nimfm_fm_mbpsgd_epoch(ctx, h, win.handle(), C.byref(sub), mb, C.byref(itc),
+                                                     C.byref(cur), None, C.byref(rl)))
+                total += rl.value * mb * k
+            finally:
+                for p_ in parts:
+                    p_.free()
+                if win is not parts[0]:
+                    win.free()
+            ii = (ii + rows) % n
+            left -= k
+        return total / (mb * inner), ii
 
 
 def newMBPSGD(maxIter=100, eta0=0.1, alpha0=1e-6, alpha=1e-3, beta=1e-4, gamma=1e-4, loss=None, reg=None,

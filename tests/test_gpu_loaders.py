@@ -208,3 +208,77 @@ def test_stream_binary_files(oracle, tmp_path):
     # (rows with one nonzero have an exactly-zero ANOVA term on the CPU; FMA contraction leaves ~1e-19 there)
     from helpers import max_rel
     assert max_rel(got, want) < 1e-10
+
+
+@pytest.mark.parametrize("cache_kb", [1.5, 9.0, 10_000.0])
+def test_stream_windowed_dataset(oracle, tmp_path, cache_kb):
+    """StreamCSRDataset in its windowed form (the reference's cacheSize window with HBM as the cache,
+    sparse_stream.nim:232-270): the file stays on disk and decisionFunction / SGD / AdaGrad / MBPSGD walk
+    resident windows of rows in file order -- same results as the whole matrix resident (no shuffling, as
+    the reference with nCached < nSamples) and as the oracle.  cache_kb: windows of ~5 rows, ~30 rows, one."""
+    import ctypes as C
+    from nimfm_b200 import _lib
+    from helpers import max_rel, make_fm_params
+    n, d, k = 157, 40, 8
+    rng = np.random.default_rng(21)
+    X = make_dense(n, d, 4, density=0.3, positive=False)
+    X[11] = 0.0
+    csr = CSR.from_dense(X)
+    y = np.sign(rng.standard_normal(n))
+    txt, fx, fy = (str(tmp_path / f) for f in ("w.svm", "w.bin", "w.lab"))
+    write_svm(txt, csr, y)
+    nf.convertSVMLightFile(txt, fx, fy)
+    whole = nf.newStreamCSRDataset(fx, resident=True)
+    ref = CSR(whole.data, whole.indices, whole.indptr, whole.nSamples, whole.nFeatures)
+    dd = whole.nFeatures
+    win = nf.newStreamCSRDataset(fx, cacheSize=cache_kb / 1024.0, resident=False)
+    assert win.windowed and win.shape == whole.shape and win.nnz == whole.nnz
+    # windows tile the rows, each within the cache budget (or a single row), bit-exact content
+    spans = []
+    for a, b, w_ in win.windows():
+        spans.append((a, b))
+        sub = oracle.csr_take_rows(ref, np.arange(a, b))
+        assert np.array_equal(w_.indptr, sub.indptr) and np.array_equal(w_.indices, sub.indices)
+        assert np.array_equal(w_.data, sub.data)
+        payload = 8 * (b - a) + 16 * len(sub.data)
+        assert payload <= cache_kb * 1024 or b - a == 1
+    assert spans[0][0] == 0 and spans[-1][1] == n and all(spans[i][1] == spans[i + 1][0] for i in range(len(spans) - 1))
+    assert (len(spans) == 1) == (cache_kb > 1000) and win.nCached == spans[0][1]
+    with pytest.raises(ValueError, match="windows"):
+        win.handle()
+
+    def model(degree=3):
+        P, w, _ = make_fm_params(dd, degree, k, "explicit", True, seed=3, scale=0.1)
+        fm = nf.newFactorizationMachine(nf.classification, degree=degree, nComponents=k, warmStart=True)
+        fm.P, fm.w, fm.intercept, fm.isInitialized = P.copy(), w.copy(), 0.05, True
+        return fm, P, w
+    fm, P, w = model()
+    assert np.array_equal(fm.decisionFunction(win), fm.decisionFunction(whole))
+    assert max_rel(fm.decisionFunction(win), oracle.fm_decision_function(ref, P, w, 0.05, 3)) <= 1e-10
+
+    # per-sample solvers: the sequential loop simply continues across windows
+    for make in (lambda: nf.newSGD(maxIter=3, eta0=0.05, verbose=0, tol=0.0, shuffle=True, loss=nf.Logistic()),
+                 lambda: nf.newAdaGrad(maxIter=3, eta0=0.1, verbose=0, tol=0.0, shuffle=True, loss=nf.Logistic()),
+                 lambda: nf.newAdaGrad(maxIter=3, eta0=0.1, verbose=0, tol=0.0, shuffle=True, loss=nf.Logistic(),
+                                       miniBatchSize=8)):
+        fa, _, _ = model()
+        oa = make()
+        oa.fit(win, y, fa)
+        fb, _, _ = model()
+        ob = make()
+        ob.shuffle = False
+        ob.fit(whole, y, fb)
+        assert np.allclose(oa.history, ob.history, rtol=1e-10, atol=0) and oa.it == ob.it
+        assert max_rel(fa.P, fb.P) <= 1e-10 and max_rel(fa.w, fb.w) <= 1e-10
+
+    # MBPSGD: minibatches of 7 rows (157 = 22*7 + 3: the cursor wraps and every epoch starts elsewhere)
+    kw = dict(eta0=0.2, alpha0=1e-6, alpha=1e-3, beta=1e-3, gamma=0.0)
+    fa, P2, w2 = model(2)
+    oa = nf.newMBPSGD(maxIter=4, loss=nf.Logistic(), miniBatchSize=7, verbose=0, tol=0.0, shuffle=True, **kw)
+    oa.fit(win, y, fa)
+    assert oa.shuffle is True
+    oref = oracle.mbpsgd_fit(ref, y, P2, w2, 0.05, 2, "logistic", True, True, max_iter=4, reg="identity",
+                             mini_batch_size=7, it=0, **kw)
+    np.testing.assert_allclose(oa.history, oref["epoch_loss"], rtol=1e-8)
+    assert max_rel(fa.P, oref["P"]) <= 1e-8 and max_rel(fa.w, oref["w"]) <= 1e-8 and oa.it == oref["it"]
+    win.close()
