@@ -46,6 +46,11 @@ struct nimfm_ctx {
   int64_t *hostPtr[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t evSlot[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t hostCapNnz = 0, hostCapRows = 0;
+  // pinned pieces of the file -> device copy (loaders.cu, staged_h2d): kPinPieces x kPinPieceBytes
+  static constexpr int kPinPieces = 16;
+  static constexpr size_t kPinPieceBytes = 8u << 20;
+  unsigned char *pinPiece[kPinPieces] = {nullptr};
+  cudaEvent_t evPiece[kPinPieces] = {nullptr};
   int64_t lastH2D = 0, lastD2H = 0;   // nimfm_stream_stats
   int32_t lastHostThreads = 0;
   uint8_t *stageHotSlot = nullptr;   // persistent [stageHotD] table; only the <=16 hot entries change per call
@@ -151,6 +156,8 @@ int nimfm_allreduce_sum(nimfm_ctx *ctx, double *buf, int64_t n);
 
 // hot-column table upload (dataset.cu)
 int nimfm_upload_hot(nimfm_ctx *ctx, const std::vector<int32_t> &hot, int64_t d, uint8_t **hotSlot, int32_t **hotList);
+int nimfm_find_hot(const int64_t *indices, const int64_t *indptr, int64_t rowBegin, int64_t rowEnd,
+                   std::vector<int32_t> &hot, int64_t maxSample);
 
 // upload host int64 row ids into ctx->idx32Scratch as int32 (validated against n)
 int nimfm_stage_row_ids(nimfm_ctx *ctx, const int64_t *ids, int64_t count, int64_t n);

@@ -134,6 +134,10 @@ int32_t nimfm_ctx_destroy(nimfm_ctx *ctx) {
     if (ctx->evCopied[s]) cudaEventDestroy(ctx->evCopied[s]);
     if (ctx->evComputed[s]) cudaEventDestroy(ctx->evComputed[s]);
   }
+  for (int s = 0; s < nimfm_ctx::kPinPieces; s++) {
+    if (ctx->pinPiece[s]) cudaFreeHost(ctx->pinPiece[s]);
+    if (ctx->evPiece[s]) cudaEventDestroy(ctx->evPiece[s]);
+  }
   for (int s = 0; s < 4; s++) {
     if (ctx->hostIdx[s]) cudaFreeHost(ctx->hostIdx[s]);
     if (ctx->hostPtr[s]) cudaFreeHost(ctx->hostPtr[s]);

@@ -14,6 +14,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <charconv>
 #include <thread>
 
@@ -192,6 +193,53 @@ int finish_upload(nimfm_ctx *ctx, int64_t n, int64_t d, std::vector<double> &dat
 // The reference reads them through a window cache because they may exceed host memory; a B200 holds
 // 180 GB, so the file is loaded whole: the host only hops over the counts (O(segments)), the raw
 // payload is uploaded as it is and de-interleaved on the device.
+// Pageable (mmap'ed file) memory -> device.  cudaMemcpy from pageable memory runs at ~4.5 GB/s here (the
+// driver stages it through one pinned bounce buffer on one thread); a team of threads copying 8 MB pieces
+// into the context's pinned pieces, each thread issuing the async copy of the piece it just filled, keeps
+// the link busy instead.  The caller's stream waits for the last piece.
+static int staged_h2d(nimfm_ctx *ctx, void *dDst, const char *src, size_t bytes) {
+  if (bytes == 0) return NIMFM_OK;
+  const size_t piece = nimfm_ctx::kPinPieceBytes;
+  const int64_t nPieces = (int64_t)((bytes + piece - 1) / piece);
+  const int hw = (int)std::thread::hardware_concurrency();
+  int T = std::min<int64_t>(std::min(8, std::max(1, hw / std::max(1, ctx->nranks))), nPieces);
+  if (const char *e = getenv("NIMFM_HOST_THREADS")) T = std::max(1, std::min(atoi(e), 8));
+  if (nPieces < 4 || T < 2) {
+    CK(cudaMemcpyAsync(dDst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return NIMFM_OK;
+  }
+  for (int i = 0; i < nimfm_ctx::kPinPieces; i++) {
+    if (!ctx->pinPiece[i]) CK(cudaHostAlloc(&ctx->pinPiece[i], piece, cudaHostAllocDefault));
+    if (!ctx->evPiece[i]) CK(cudaEventCreateWithFlags(&ctx->evPiece[i], cudaEventDisableTiming));
+  }
+  std::atomic<int64_t> next(0);
+  std::atomic<int> err((int)cudaSuccess);
+  auto work = [&](int t) {
+    if (cudaSetDevice(ctx->device) != cudaSuccess) { err = (int)cudaErrorInvalidDevice; return; }
+    int use = 0;   // thread t owns pieces 2t and 2t+1 of the pinned set
+    for (;;) {
+      const int64_t i = next.fetch_add(1);
+      if (i >= nPieces || err.load() != (int)cudaSuccess) return;
+      const int slot = 2 * t + (use++ & 1);
+      const size_t off = (size_t)i * piece, len = std::min(piece, bytes - off);
+      cudaError_t e = cudaEventSynchronize(ctx->evPiece[slot]);   // the slot's previous copy has left the host
+      memcpy(ctx->pinPiece[slot], src + off, len);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(static_cast<char *>(dDst) + off, ctx->pinPiece[slot], len, cudaMemcpyHostToDevice, ctx->copyStream);
+      if (e == cudaSuccess) e = cudaEventRecord(ctx->evPiece[slot], ctx->copyStream);
+      if (e != cudaSuccess) { err = (int)e; return; }
+    }
+  };
+  std::vector<std::thread> team;
+  for (int t = 0; t < T; t++) team.emplace_back(work, t);
+  for (auto &th : team) th.join();
+  if (err.load() != (int)cudaSuccess)
+    return nimfm_fail(ctx, NIMFM_ERR_CUDA, "staged_h2d: %s", cudaGetErrorString((cudaError_t)err.load()));
+  CK(cudaEventRecord(ctx->evCopied[0], ctx->copyStream));
+  CK(cudaStreamWaitEvent(ctx->stream, ctx->evCopied[0], 0));
+  return NIMFM_OK;
+}
+
 struct nimfm_stream {
   Mapped mx, my;
   bool isCsr = true, hasY = false;
@@ -439,8 +487,8 @@ int32_t nimfm_stream_load_window(nimfm_ctx *ctx, nimfm_stream *sh, int64_t segBe
   ck(cudaMalloc(&ds->data, (size_t)std::max<int64_t>(nnz, 2) * 8));
   ck(cudaMalloc(&ds->indices, (size_t)std::max<int64_t>(nnz, 4) * 4));
   if (ce == cudaSuccess) {
-    if (payloadBytes)
-      ck(cudaMemcpyAsync(dPayload, sh->mx.p + 49 + byteBegin, payloadBytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (payloadBytes && staged_h2d(ctx, dPayload, sh->mx.p + 49 + byteBegin, payloadBytes) != NIMFM_OK)
+      ck(cudaErrorUnknown);
     if (nSeg) ck(cudaMemcpyAsync(dSegOff, segOff.data(), (size_t)nSeg * 8, cudaMemcpyHostToDevice, ctx->stream));
     ck(cudaMemcpyAsync(ds->indptr, indptr.data(), ((size_t)nSeg + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     ck(cudaMemsetAsync(dBad, 0, sizeof(int), ctx->stream));
@@ -462,10 +510,28 @@ int32_t nimfm_stream_load_window(nimfm_ctx *ctx, nimfm_stream *sh, int64_t segBe
   }
   cudaFree(dPayload); cudaFree(dSegOff); cudaFree(dBad);
   if (ce != cudaSuccess) return fail(nimfm_fail(ctx, NIMFM_ERR_CUDA, "nimfm_stream_load_window: %s", cudaGetErrorString(ce)));
-  if (ds->kind == NIMFM_DS_CSR) {   // no hot columns known for a stream: all cold (bookkeeping only)
+  if (ds->kind == NIMFM_DS_CSR) {
+    // hot columns from a row sample, as for uploaded datasets (nimfm_find_hot): the sampled rows' ids are
+    // gathered out of the interleaved payload into a small CSR first
     std::vector<int32_t> hot;
+    if (nSeg > 0) {
+      const int64_t stride = std::max<int64_t>(1, nSeg / 2048);
+      std::vector<int64_t> sIdx, sPtr(1, 0);
+      for (int64_t g = 0; g < nSeg; g += stride) {
+        const char *rec = sh->mx.p + 49 + sh->segOff[(size_t)(segBegin + g)];
+        const int64_t z = indptr[(size_t)g + 1] - indptr[(size_t)g];
+        for (int64_t t = 0; t < z; t++) {
+          int64_t id;
+          memcpy(&id, rec + 16 * t + 8, 8);
+          sIdx.push_back(id);
+        }
+        sPtr.push_back((int64_t)sIdx.size());
+      }
+      nimfm_find_hot(sIdx.data(), sPtr.data(), 0, (int64_t)sPtr.size() - 1, hot, 2048);
+    }
     int rc = nimfm_upload_hot(ctx, hot, ds->d, &ds->hotSlot, &ds->hotList);
     if (rc) return fail(rc);
+    ds->nHot = (int)hot.size();
   }
   if (sh->hasY && sh->isCsr && nSeg > 0) {
     std::vector<double> y((size_t)nSeg);

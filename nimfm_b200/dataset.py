@@ -367,9 +367,9 @@ def _load_stream(fX, fY):
     _lib.check(_lib.load().nimfm_load_stream(_lib.ctx(), _path(fX), None if fY is None else _path(fY), C.byref(h)))
     probe = BaseDataset.__new__(BaseDataset)
     probe._handle = h
-    cls = CSCDataset if BaseDataset.info(probe)["kind"] == _lib.DS_CSC else CSRDataset
+    cls = _DeviceCSCDataset if BaseDataset.info(probe)["kind"] == _lib.DS_CSC else _DeviceCSRDataset
     probe._handle = None
-    out = _adopt(h, cls, None)
+    out = cls(h)
     y = None
     if fY is not None:
         y = np.zeros(out.nSamples)
@@ -377,9 +377,9 @@ def _load_stream(fX, fY):
     return out, y
 
 
-class _DeviceCSRDataset(CSRDataset):
-    """A library-made CSR dataset that stays on the device: the host arrays are read back only if somebody
-    asks for them (a window of a stream file is used once and freed)."""
+class _DeviceMixin:
+    """A library-made dataset that stays on the device: the host arrays are read back only if somebody asks
+    for them (a window of a stream file is used once and freed; a 100 GB file is not mirrored on the host)."""
 
     def __init__(self, h):
         self._handle = h
@@ -397,6 +397,14 @@ class _DeviceCSRDataset(CSRDataset):
             self.data, self.indices, self.indptr, _ = BaseDataset.download(self)
             return self.__dict__[name]
         raise AttributeError(name)
+
+
+class _DeviceCSRDataset(_DeviceMixin, CSRDataset):
+    pass
+
+
+class _DeviceCSCDataset(_DeviceMixin, CSCDataset):
+    pass
 
 
 class StreamCSRDataset(CSRDataset):
