@@ -54,8 +54,12 @@ int narrow(const int64_t *src, int32_t *dst, int64_t n, int64_t d) {
 int HostStageTeam::default_threads(int nRanks) {
   if (const char *e = getenv("NIMFM_HOST_THREADS")) return std::max(0, atoi(e));
   const int hw = (int)std::thread::hardware_concurrency();
-  const int t = std::min(8, hw / std::max(1, nRanks));
-  return t >= 4 ? t : 0;   // fewer than 4 threads cannot keep up with a PCIe 5 x16 link
+  // Staging pays while the rank's own PCIe link is the bound (1-2 ranks on this box: 81 -> 102 M rows/s).
+  // With every GPU of the box fed at once the host's memory system is the bound and the extra pass over
+  // the ids costs more than the 25 % of link bytes it saves (8 ranks, measured: 285 M rows/s narrowing on the
+  // device, 188-196 M with 2-4 staging threads per rank): only ranks with 8 hardware threads to themselves stage.
+  const int t = hw / std::max(1, nRanks);
+  return t >= 8 ? 8 : 0;
 }
 
 HostStageTeam::HostStageTeam(int nThreads, const int64_t *indices, const int64_t *indptr, int64_t d,
