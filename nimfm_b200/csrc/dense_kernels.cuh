@@ -161,15 +161,29 @@ static __global__ void mbpsgd_lazy_flush_feat_kernel(double *w, int64_t d, int f
 // deltas) -> [all-reduce deltas] -> scalar + apply.
 //
 // cnt[j] += number of rows of the batch that contain feature j (dummy features: every row).
+// Columns of the dataset's hot table (present in >= 1/16 of the rows) are counted in shared memory and
+// flushed once per block: 1 Mi Criteo-shaped rows put 1 Mi REDs on each of 13 addresses otherwise (4.3 ms
+// of a 14 ms minibatch).  Counts are small integers held in doubles: exact in any order.
 static __global__ void adagrad_count_kernel(const int32_t *indices, const int64_t *indptr, int64_t n, int64_t rowBegin,
-                                            int64_t nRows, const int32_t *rowIdx, int64_t d, int nAug, double *cnt) {
+                                            int64_t nRows, const int32_t *rowIdx, int64_t d, int nAug, double *cnt,
+                                            const uint8_t *hotSlot, const int32_t *hotList, int nHot) {
+  __shared__ int hotCnt[16];
+  if (threadIdx.x < 16) hotCnt[threadIdx.x] = 0;
+  __syncthreads();
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nWarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int lane = threadIdx.x & 31;
   for (int64_t q = warp; q < nRows; q += nWarps) {
     const int64_t r = rowIdx ? (int64_t)rowIdx[q] : (rowBegin + q) % n;
-    for (int64_t e = indptr[r] + lane; e < indptr[r + 1]; e += 32) atomicAdd(cnt + indices[e], 1.0);
+    for (int64_t e = indptr[r] + lane; e < indptr[r + 1]; e += 32) {
+      const int32_t j = indices[e];
+      const int slot = (hotSlot && nHot > 0) ? hotSlot[j] : 255;
+      if (slot != 255) atomicAdd(&hotCnt[slot], 1);
+      else atomicAdd(cnt + j, 1.0);
+    }
   }
+  __syncthreads();
+  if ((int)threadIdx.x < nHot && hotCnt[threadIdx.x] > 0) atomicAdd(cnt + hotList[threadIdx.x], (double)hotCnt[threadIdx.x]);
   if (warp == 0 && lane < nAug) cnt[d + lane] += (double)nRows;   // augmentation: one dummy per row
 }
 

@@ -682,7 +682,7 @@ int32_t nimfm_ffm_adagrad_epoch(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_datase
       // per-feature row counts of the batch (all ranks): viol weights + the touched-feature set
       const int cgrid = (int)std::min<int64_t>((cnt * 32 + 255) / 256, (int64_t)ctx->numSMs * 16);
       adagrad_count_kernel<<<cgrid < 1 ? 1 : cgrid, 256, 0, ctx->stream>>>(X->indices, X->indptr, X->n, start, cnt, rows,
-                                                                          d, 0, cntF);
+                                                                          d, 0, cntF, X->hotSlot, X->hotList, X->nHot);
       LAUNCHED(ctx);
       if ((rc = nimfm_allreduce_sum(ctx, cntF, d))) return rc;
     }

@@ -799,7 +799,7 @@ int32_t nimfm_fm_adagrad_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset
       // the refresh / apply passes which features the batch touches
       const int cgrid = (int)std::min<int64_t>((cnt * 32 + 255) / 256, (int64_t)ctx->numSMs * 16);
       adagrad_count_kernel<<<cgrid < 1 ? 1 : cgrid, 256, 0, ctx->stream>>>(X->indices, X->indptr, X->n, start, cnt, rows,
-                                                                          d, fm->nAug, cntF);
+                                                                          d, fm->nAug, cntF, X->hotSlot, X->hotList, X->nHot);
       LAUNCHED(ctx);
       if ((rc = nimfm_allreduce_sum(ctx, cntF, dd))) return rc;
     }
