@@ -156,6 +156,8 @@ int nimfm_allreduce_sum(nimfm_ctx *ctx, double *buf, int64_t n);
 
 // hot-column table upload (dataset.cu)
 int nimfm_upload_hot(nimfm_ctx *ctx, const std::vector<int32_t> &hot, int64_t d, uint8_t **hotSlot, int32_t **hotList);
+int nimfm_staged_h2d(nimfm_ctx *ctx, void *dDst, const void *src, size_t bytes, int64_t narrowD = 0, int *bad = nullptr);
+int nimfm_staged_d2h(nimfm_ctx *ctx, void *hostDst, const void *dSrc, size_t bytes);
 int nimfm_find_hot(const int64_t *indices, const int64_t *indptr, int64_t rowBegin, int64_t rowEnd,
                    std::vector<int32_t> &hot, int64_t maxSample);
 

@@ -3,7 +3,11 @@
 #include <dlfcn.h>
 #include <stdarg.h>
 
+#include <atomic>
+#include <thread>
+
 #include "common.cuh"
+#include "host_stage.h"
 
 // minimal NCCL surface (types as in nccl.h 2.27/2.28; resolved at run time)
 typedef struct { char internal[128]; } nimfm_ncclUniqueId;
@@ -261,5 +265,112 @@ int nimfm_stage_row_ids(nimfm_ctx *ctx, const int64_t *ids, int64_t count, int64
   CK(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (hbad) return nimfm_fail(ctx, NIMFM_ERR_INVALID, "row index out of range [0,%lld)", (long long)n);
+  return NIMFM_OK;
+}
+
+// Pageable host memory (a caller's numpy / Nim seq arrays, an mmap'ed file) -> device.  cudaMemcpy from
+// pageable memory runs at ~4 GB/s here (the driver stages it through one pinned bounce buffer on one
+// thread); a team of threads copying 8 MB pieces into the context's pinned pieces, each thread issuing the
+// async copy of the piece it just filled, keeps the link busy instead.  With narrowD > 0 the source is
+// int64 ids and the pieces are filled with their int32 narrowing (range-checked against [0, narrowD):
+// *bad is set, the caller reports).  The context's stream waits for the last piece.
+int nimfm_staged_h2d(nimfm_ctx *ctx, void *dDst, const void *srcv, size_t bytes, int64_t narrowD, int *bad) {
+  if (bad) *bad = 0;
+  if (bytes == 0) return NIMFM_OK;
+  const char *src = static_cast<const char *>(srcv);
+  const bool narrowing = narrowD > 0;
+  const size_t piece = nimfm_ctx::kPinPieceBytes;            // bytes of DESTINATION per piece
+  const size_t dstBytes = narrowing ? bytes / 2 : bytes;
+  const int64_t nPieces = (int64_t)((dstBytes + piece - 1) / piece);
+  const int hw = (int)std::thread::hardware_concurrency();
+  int T = (int)std::min<int64_t>(std::min(8, std::max(1, hw / std::max(1, ctx->nranks))), nPieces);
+  if (const char *e = getenv("NIMFM_HOST_THREADS")) T = std::max(1, std::min(atoi(e), 8));
+  for (int i = 0; i < nimfm_ctx::kPinPieces; i++) {
+    if (!ctx->pinPiece[i]) CK(cudaHostAlloc(&ctx->pinPiece[i], piece, cudaHostAllocDefault));
+    if (!ctx->evPiece[i]) CK(cudaEventCreateWithFlags(&ctx->evPiece[i], cudaEventDisableTiming));
+  }
+  std::atomic<int64_t> next(0);
+  std::atomic<int> err((int)cudaSuccess), anyBad(0);
+  auto work = [&](int t) {
+    if (cudaSetDevice(ctx->device) != cudaSuccess) { err = (int)cudaErrorInvalidDevice; return; }
+    int use = 0;   // thread t owns pieces 2t and 2t+1 of the pinned set
+    for (;;) {
+      const int64_t i = next.fetch_add(1);
+      if (i >= nPieces || err.load() != (int)cudaSuccess) return;
+      const int slot = 2 * t + (use++ & 1);
+      const size_t off = (size_t)i * piece, len = std::min(piece, dstBytes - off);
+      cudaError_t e = cudaEventSynchronize(ctx->evPiece[slot]);   // the slot's previous copy has left the host
+      if (narrowing) {
+        if (nimfm_host_narrow(reinterpret_cast<const int64_t *>(src) + off / 4,
+                              reinterpret_cast<int32_t *>(ctx->pinPiece[slot]), (int64_t)(len / 4), narrowD))
+          anyBad = 1;
+      } else {
+        memcpy(ctx->pinPiece[slot], src + off, len);
+      }
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(static_cast<char *>(dDst) + off, ctx->pinPiece[slot], len, cudaMemcpyHostToDevice, ctx->copyStream);
+      if (e == cudaSuccess) e = cudaEventRecord(ctx->evPiece[slot], ctx->copyStream);
+      if (e != cudaSuccess) { err = (int)e; return; }
+    }
+  };
+  if (T < 2 || nPieces < 2) {
+    work(0);
+  } else {
+    std::vector<std::thread> team;
+    for (int t = 0; t < T; t++) team.emplace_back(work, t);
+    for (auto &th : team) th.join();
+  }
+  if (err.load() != (int)cudaSuccess)
+    return nimfm_fail(ctx, NIMFM_ERR_CUDA, "staged_h2d: %s", cudaGetErrorString((cudaError_t)err.load()));
+  if (bad) *bad = anyBad.load();
+  CK(cudaEventRecord(ctx->evCopied[0], ctx->copyStream));
+  CK(cudaStreamWaitEvent(ctx->stream, ctx->evCopied[0], 0));
+  return NIMFM_OK;
+}
+
+// Device -> pageable host memory, the same way round: every thread queues the async copy of a piece into
+// one of its pinned slots, waits for it, and copies it out while the other threads' pieces are on the link.
+// Everything queued on the context's stream before the call is waited for; the call returns with the data
+// in place.
+int nimfm_staged_d2h(nimfm_ctx *ctx, void *hostDst, const void *dSrc, size_t bytes) {
+  if (bytes == 0) return NIMFM_OK;
+  const size_t piece = nimfm_ctx::kPinPieceBytes;
+  const int64_t nPieces = (int64_t)((bytes + piece - 1) / piece);
+  const int hw = (int)std::thread::hardware_concurrency();
+  int T = (int)std::min<int64_t>(std::min(8, std::max(1, hw / std::max(1, ctx->nranks))), nPieces);
+  if (const char *e = getenv("NIMFM_HOST_THREADS")) T = std::max(1, std::min(atoi(e), 8));
+  for (int i = 0; i < nimfm_ctx::kPinPieces; i++) {
+    if (!ctx->pinPiece[i]) CK(cudaHostAlloc(&ctx->pinPiece[i], piece, cudaHostAllocDefault));
+    if (!ctx->evPiece[i]) CK(cudaEventCreateWithFlags(&ctx->evPiece[i], cudaEventDisableTiming));
+  }
+  CK(cudaEventRecord(ctx->evComputed[0], ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->copyStream, ctx->evComputed[0], 0));
+  std::atomic<int64_t> next(0);
+  std::atomic<int> err((int)cudaSuccess);
+  auto work = [&](int t) {
+    if (cudaSetDevice(ctx->device) != cudaSuccess) { err = (int)cudaErrorInvalidDevice; return; }
+    const int slot = 2 * t;
+    for (;;) {
+      const int64_t i = next.fetch_add(1);
+      if (i >= nPieces || err.load() != (int)cudaSuccess) return;
+      const size_t off = (size_t)i * piece, len = std::min(piece, bytes - off);
+      cudaError_t e = cudaEventSynchronize(ctx->evPiece[slot]);   // an earlier H2D out of this slot has left
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(ctx->pinPiece[slot], static_cast<const char *>(dSrc) + off, len, cudaMemcpyDeviceToHost, ctx->copyStream);
+      if (e == cudaSuccess) e = cudaEventRecord(ctx->evPiece[slot], ctx->copyStream);
+      if (e == cudaSuccess) e = cudaEventSynchronize(ctx->evPiece[slot]);
+      if (e != cudaSuccess) { err = (int)e; return; }
+      memcpy(static_cast<char *>(hostDst) + off, ctx->pinPiece[slot], len);
+    }
+  };
+  if (T < 2 || nPieces < 2) {
+    work(0);
+  } else {
+    std::vector<std::thread> team;
+    for (int t = 0; t < T; t++) team.emplace_back(work, t);
+    for (auto &th : team) th.join();
+  }
+  if (err.load() != (int)cudaSuccess)
+    return nimfm_fail(ctx, NIMFM_ERR_CUDA, "staged_d2h: %s", cudaGetErrorString((cudaError_t)err.load()));
   return NIMFM_OK;
 }

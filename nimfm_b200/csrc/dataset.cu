@@ -75,22 +75,6 @@ static int upload_common(nimfm_ctx *ctx, int kind, int64_t nSeg, int64_t nOther,
       maxSeg = std::max(maxSeg, len);
     }
   }
-  std::vector<int32_t> idx32((size_t)nnz);
-  for (int64_t q = 0; q < nnz; q++) {
-    int64_t v = indices[base + q];
-    REQUIRE(v >= 0 && v < nOther, "index %lld out of range [0,%lld) at nnz %lld", (long long)v,
-            (long long)nOther, (long long)(base + q));
-    idx32[q] = (int32_t)v;
-  }
-  std::vector<int32_t> f32;
-  if (fields) {
-    f32.resize((size_t)nnz);
-    for (int64_t q = 0; q < nnz; q++) {
-      int64_t v = fields[base + q];
-      REQUIRE(v >= 0 && v < nFields, "field %lld out of range [0,%lld)", (long long)v, (long long)nFields);
-      f32[q] = (int32_t)v;
-    }
-  }
   nimfm_dataset *ds = new nimfm_dataset();
   ds->kind = kind;
   ds->n = (kind == NIMFM_DS_CSC) ? n : ns;
@@ -98,11 +82,38 @@ static int upload_common(nimfm_ctx *ctx, int kind, int64_t nSeg, int64_t nOther,
   ds->nnz = nnz;
   ds->nFields = fields ? nFields : 0;
   ds->maxSegNnz = maxSeg;
-  int rc;
-  if ((rc = alloc_copy(ctx, (void **)&ds->data, data ? data + base : nullptr, (size_t)nnz * 8))) return rc;
-  if ((rc = alloc_copy(ctx, (void **)&ds->indices, idx32.data(), (size_t)nnz * 4))) return rc;
-  if ((rc = alloc_copy(ctx, (void **)&ds->indptr, ptr.data(), ((size_t)ns + 1) * 8))) return rc;
-  if (fields && (rc = alloc_copy(ctx, (void **)&ds->fields, f32.data(), (size_t)nnz * 4))) return rc;
+  // values, ids and field ids reach the device through the pinned-piece thread team (the ids narrowed to
+  // int32 and range-checked on the way): 2 M Criteo-shaped rows 0.33 s -> the link's rate
+  int rc, bad = 0;
+  auto fail = [&](int code) { nimfm_dataset_free(ctx, ds); return code; };
+  CK(cudaMalloc(&ds->data, (size_t)std::max<int64_t>(nnz, 2) * 8));
+  CK(cudaMalloc(&ds->indices, (size_t)std::max<int64_t>(nnz, 4) * 4));
+  if (fields) CK(cudaMalloc(&ds->fields, (size_t)std::max<int64_t>(nnz, 4) * 4));
+  if (nnz > 0) {
+    if ((rc = nimfm_staged_h2d(ctx, ds->data, data + base, (size_t)nnz * 8))) return fail(rc);
+    if ((rc = nimfm_staged_h2d(ctx, ds->indices, indices + base, (size_t)nnz * 8, nOther > 0 ? nOther : 1, &bad))) return fail(rc);
+    if (bad) {   // error path only: name the first offender like the sequential check did
+      CK(cudaStreamSynchronize(ctx->stream));
+      for (int64_t q = 0; q < nnz; q++) {
+        const int64_t v = indices[base + q];
+        if (v < 0 || v >= nOther)
+          return fail(nimfm_fail(ctx, NIMFM_ERR_INVALID, "index %lld out of range [0,%lld) at nnz %lld", (long long)v,
+                                 (long long)nOther, (long long)(base + q)));
+      }
+    }
+    if (fields) {
+      if ((rc = nimfm_staged_h2d(ctx, ds->fields, fields + base, (size_t)nnz * 8, nFields > 0 ? nFields : 1, &bad))) return fail(rc);
+      if (bad) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int64_t q = 0; q < nnz; q++) {
+          const int64_t v = fields[base + q];
+          if (v < 0 || v >= nFields)
+            return fail(nimfm_fail(ctx, NIMFM_ERR_INVALID, "field %lld out of range [0,%lld)", (long long)v, (long long)nFields));
+        }
+      }
+    }
+  }
+  if ((rc = alloc_copy(ctx, (void **)&ds->indptr, ptr.data(), ((size_t)ns + 1) * 8))) return fail(rc);
   if (kind != NIMFM_DS_CSC) {
     std::vector<int32_t> hot;
     ds->nHot = nimfm_find_hot(indices, indptr, segBegin, segEnd, hot, 16384);

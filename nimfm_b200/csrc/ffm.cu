@@ -469,10 +469,10 @@ static int ffm_permute(nimfm_ctx *ctx, nimfm_ffm *m, double *host, double *dev, 
   const int64_t nP = m->nP();
   double *tmp = nullptr;
   CK(cudaMalloc(&tmp, (size_t)nP * 8));
-  if (toDev) CK(cudaMemcpyAsync(tmp, host, (size_t)nP * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (toDev) { int rcs = nimfm_staged_h2d(ctx, tmp, host, (size_t)nP * 8); if (rcs) { cudaFree(tmp); return rcs; } }
   ffm_permute_kernel<<<ew_grid(ctx, nP), 256, 0, ctx->stream>>>(tmp, dev, m->nFields, m->d, m->k, toDev);
   LAUNCHED(ctx);
-  if (!toDev) CK(cudaMemcpyAsync(host, tmp, (size_t)nP * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (!toDev) { int rcs = nimfm_staged_d2h(ctx, host, tmp, (size_t)nP * 8); if (rcs) { cudaFree(tmp); return rcs; } }
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaFree(tmp));
   CK(cudaGetLastError());

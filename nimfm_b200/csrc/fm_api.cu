@@ -251,7 +251,7 @@ int32_t nimfm_fm_set_params(nimfm_ctx *ctx, nimfm_fm *fm, const double *P, const
   const int64_t nP = fm->nP();
   double *tmp = nullptr;
   CK(cudaMalloc(&tmp, (size_t)nP * 8));
-  CK(cudaMemcpyAsync(tmp, P, (size_t)nP * 8, cudaMemcpyHostToDevice, ctx->stream));
+  { int rcs = nimfm_staged_h2d(ctx, tmp, P, (size_t)nP * 8); if (rcs) { cudaFree(tmp); return rcs; } }
   permute_model_to_dev<<<ew_grid(ctx, nP), 256, 0, ctx->stream>>>(tmp, fm->P, fm->nOrders, fm->k, fm->dd());
   LAUNCHED(ctx);
   CK(cudaMemcpyAsync(fm->w, w, (size_t)fm->d * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -274,7 +274,7 @@ static int get_permuted(nimfm_ctx *ctx, nimfm_fm *fm, const double *dev, double 
   CK(cudaMalloc(&tmp, (size_t)nP * 8));
   permute_dev_to_model<<<ew_grid(ctx, nP), 256, 0, ctx->stream>>>(dev, tmp, fm->nOrders, fm->k, fm->dd());
   LAUNCHED(ctx);
-  CK(cudaMemcpyAsync(host, tmp, (size_t)nP * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  { int rcs = nimfm_staged_d2h(ctx, host, tmp, (size_t)nP * 8); if (rcs) { cudaFree(tmp); return rcs; } }
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaFree(tmp));
   CK(cudaGetLastError());

@@ -51,6 +51,8 @@ int narrow(const int64_t *src, int32_t *dst, int64_t n, int64_t d) {
 
 }  // namespace
 
+int nimfm_host_narrow(const int64_t *src, int32_t *dst, int64_t n, int64_t d) { return narrow(src, dst, n, d); }
+
 int HostStageTeam::default_threads(int nRanks) {
   if (const char *e = getenv("NIMFM_HOST_THREADS")) return std::max(0, atoi(e));
   const int hw = (int)std::thread::hardware_concurrency();

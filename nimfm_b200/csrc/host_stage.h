@@ -13,6 +13,9 @@
 #include <thread>
 #include <vector>
 
+// int64 -> int32 (AVX2 when the CPU has it); dst 32-byte aligned; nonzero if any id is outside [0, d)
+int nimfm_host_narrow(const int64_t *src, int32_t *dst, int64_t n, int64_t d);
+
 struct HostChunk {
   int64_t r0 = 0, r1 = 0;     // rows [r0, r1) of the caller's CSR
   int64_t base = 0, nnz = 0;  // indptr[r0], indptr[r1]-indptr[r0]

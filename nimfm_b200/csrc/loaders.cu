@@ -193,53 +193,6 @@ int finish_upload(nimfm_ctx *ctx, int64_t n, int64_t d, std::vector<double> &dat
 // The reference reads them through a window cache because they may exceed host memory; a B200 holds
 // 180 GB, so the file is loaded whole: the host only hops over the counts (O(segments)), the raw
 // payload is uploaded as it is and de-interleaved on the device.
-// Pageable (mmap'ed file) memory -> device.  cudaMemcpy from pageable memory runs at ~4.5 GB/s here (the
-// driver stages it through one pinned bounce buffer on one thread); a team of threads copying 8 MB pieces
-// into the context's pinned pieces, each thread issuing the async copy of the piece it just filled, keeps
-// the link busy instead.  The caller's stream waits for the last piece.
-static int staged_h2d(nimfm_ctx *ctx, void *dDst, const char *src, size_t bytes) {
-  if (bytes == 0) return NIMFM_OK;
-  const size_t piece = nimfm_ctx::kPinPieceBytes;
-  const int64_t nPieces = (int64_t)((bytes + piece - 1) / piece);
-  const int hw = (int)std::thread::hardware_concurrency();
-  int T = std::min<int64_t>(std::min(8, std::max(1, hw / std::max(1, ctx->nranks))), nPieces);
-  if (const char *e = getenv("NIMFM_HOST_THREADS")) T = std::max(1, std::min(atoi(e), 8));
-  if (nPieces < 4 || T < 2) {
-    CK(cudaMemcpyAsync(dDst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    return NIMFM_OK;
-  }
-  for (int i = 0; i < nimfm_ctx::kPinPieces; i++) {
-    if (!ctx->pinPiece[i]) CK(cudaHostAlloc(&ctx->pinPiece[i], piece, cudaHostAllocDefault));
-    if (!ctx->evPiece[i]) CK(cudaEventCreateWithFlags(&ctx->evPiece[i], cudaEventDisableTiming));
-  }
-  std::atomic<int64_t> next(0);
-  std::atomic<int> err((int)cudaSuccess);
-  auto work = [&](int t) {
-    if (cudaSetDevice(ctx->device) != cudaSuccess) { err = (int)cudaErrorInvalidDevice; return; }
-    int use = 0;   // thread t owns pieces 2t and 2t+1 of the pinned set
-    for (;;) {
-      const int64_t i = next.fetch_add(1);
-      if (i >= nPieces || err.load() != (int)cudaSuccess) return;
-      const int slot = 2 * t + (use++ & 1);
-      const size_t off = (size_t)i * piece, len = std::min(piece, bytes - off);
-      cudaError_t e = cudaEventSynchronize(ctx->evPiece[slot]);   // the slot's previous copy has left the host
-      memcpy(ctx->pinPiece[slot], src + off, len);
-      if (e == cudaSuccess)
-        e = cudaMemcpyAsync(static_cast<char *>(dDst) + off, ctx->pinPiece[slot], len, cudaMemcpyHostToDevice, ctx->copyStream);
-      if (e == cudaSuccess) e = cudaEventRecord(ctx->evPiece[slot], ctx->copyStream);
-      if (e != cudaSuccess) { err = (int)e; return; }
-    }
-  };
-  std::vector<std::thread> team;
-  for (int t = 0; t < T; t++) team.emplace_back(work, t);
-  for (auto &th : team) th.join();
-  if (err.load() != (int)cudaSuccess)
-    return nimfm_fail(ctx, NIMFM_ERR_CUDA, "staged_h2d: %s", cudaGetErrorString((cudaError_t)err.load()));
-  CK(cudaEventRecord(ctx->evCopied[0], ctx->copyStream));
-  CK(cudaStreamWaitEvent(ctx->stream, ctx->evCopied[0], 0));
-  return NIMFM_OK;
-}
-
 struct nimfm_stream {
   Mapped mx, my;
   bool isCsr = true, hasY = false;
@@ -487,7 +440,7 @@ int32_t nimfm_stream_load_window(nimfm_ctx *ctx, nimfm_stream *sh, int64_t segBe
   ck(cudaMalloc(&ds->data, (size_t)std::max<int64_t>(nnz, 2) * 8));
   ck(cudaMalloc(&ds->indices, (size_t)std::max<int64_t>(nnz, 4) * 4));
   if (ce == cudaSuccess) {
-    if (payloadBytes && staged_h2d(ctx, dPayload, sh->mx.p + 49 + byteBegin, payloadBytes) != NIMFM_OK)
+    if (payloadBytes && nimfm_staged_h2d(ctx, dPayload, sh->mx.p + 49 + byteBegin, payloadBytes) != NIMFM_OK)
       ck(cudaErrorUnknown);
     if (nSeg) ck(cudaMemcpyAsync(dSegOff, segOff.data(), (size_t)nSeg * 8, cudaMemcpyHostToDevice, ctx->stream));
     ck(cudaMemcpyAsync(ds->indptr, indptr.data(), ((size_t)nSeg + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
