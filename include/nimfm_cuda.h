@@ -302,6 +302,18 @@ int32_t nimfm_ffm_adagrad_epoch(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_datase
                                 const nimfm_adagrad_cfg *cfg, int64_t *it, const int64_t *perm,
                                 int64_t nRows, double *viol, double *lossSum);
 int32_t nimfm_ffm_adagrad_finalize(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_adagrad_cfg *cfg, int64_t it);
+/* Synchronous-minibatch SGD: the deterministic device analogue of the Hogwild variants fit(..., maxThreads)
+ * (optimizer/sgd_multi.nim:40-120, sgd_ffm_multi.nim:31-103).  The miniBatchSize samples of a minibatch are
+ * evaluated at the same parameters and their updates applied at once with the step sizes of the minibatch's
+ * first iteration: touched features p <- (1-eta beta)^B p - eta sum_i dL_i dA_i (viol += |p_new - p|),
+ * untouched features p <- (1-eta beta)^B p, it += B.  miniBatchSize = 1 is step() itself (sgd.nim:205-258).
+ * No begin / end: the parameters stay canonical between calls.  perm (nullable): sample order. */
+int32_t nimfm_fm_sgd_minibatch_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, const nimfm_sgd_cfg *cfg,
+                                     int64_t miniBatchSize, int64_t *it, const int64_t *perm, int64_t nRows,
+                                     double *viol, double *lossSum);
+int32_t nimfm_ffm_sgd_minibatch_epoch(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_dataset *X,
+                                      const nimfm_sgd_cfg *cfg, int64_t miniBatchSize, int64_t *it,
+                                      const int64_t *perm, int64_t nRows, double *viol, double *lossSum);
 /* SGD for FFM (optimizer/sgd_ffm.nim:33-106), sequential like nimfm_fm_sgd_* */
 int32_t nimfm_ffm_sgd_begin(nimfm_ctx *ctx, nimfm_ffm *m);
 int32_t nimfm_ffm_sgd_epoch(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_dataset *X, const nimfm_sgd_cfg *cfg,

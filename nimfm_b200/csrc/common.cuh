@@ -106,6 +106,7 @@ struct nimfm_fm {
   // SGD lazy-scaling caches
   double *scalingsP = nullptr, *scalingsW = nullptr, *sgdScal = nullptr;  // sgdScal: [scaling_P, scaling_w, viol, loss]
   bool sgdReady = false;
+  double *sgdCnt = nullptr;    // minibatch SGD (sgd_mb.cu): per-feature touch counts of the current minibatch
   double *psgdThr = nullptr;   // PSGD: per-feature accumulated thresholds of the lazy L1 / L21 protocol (psgd.cu)
   bool psgdReady = false;
   // CD caches
@@ -126,6 +127,7 @@ struct nimfm_ffm {
   double *P = nullptr, *w = nullptr, *b = nullptr;
   double *grad = nullptr;      // [gP | gw | gb, lossSum]
   double *gsP = nullptr, *gnP = nullptr, *gsw = nullptr, *gnw = nullptr, *dG = nullptr, *adaScal = nullptr;
+  double *sgdCnt = nullptr;    // minibatch SGD (sgd_mb.cu)
   bool adaReady = false;
   double *scalingsP = nullptr, *scalingsW = nullptr, *sgdScal = nullptr;
   bool sgdReady = false;

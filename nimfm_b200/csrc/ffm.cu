@@ -461,6 +461,7 @@ int32_t nimfm_ffm_free(nimfm_ctx *ctx, nimfm_ffm *m) {
   for (double *p : {m->P, m->w, m->b, m->grad, m->gsP, m->gnP, m->gsw, m->gnw, m->dG, m->adaScal, m->scalingsP,
                     m->scalingsW, m->sgdScal})
     cudaFree(p);
+  cudaFree(m->sgdCnt);
   delete m;
   return NIMFM_OK;
 }
@@ -553,6 +554,12 @@ static int ffm_launch_grad(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_dataset *X,
   reduce_partials_kernel<<<1, 256, 0, ctx->stream>>>(ctx->partials, pl.partialRows, ctx->scalars + 8, 0);
   LAUNCHED(ctx);
   return NIMFM_OK;
+}
+
+// the pair kernel over rows of a resident dataset into m->grad (+ red4 at ctx->scalars+8), for sgd_mb.cu
+int nimfm_ffm_launch_grad_rows(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_dataset *X, int loss, double thr,
+                               int64_t rowBegin, int64_t nRows, const int32_t *rowIdxDev, double mb) {
+  return ffm_launch_grad(ctx, m, X, loss, thr, rowBegin, nRows, rowIdxDev, mb);
 }
 
 int32_t nimfm_ffm_loss_grad(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_dataset *X, int32_t loss,

@@ -237,6 +237,7 @@ int32_t nimfm_fm_free(nimfm_ctx *ctx, nimfm_fm *fm) {
                     fm->adaScal, fm->scalingsP, fm->scalingsW, fm->sgdScal, fm->Pcm, fm->yPred, fm->Acache,
                     fm->colNormSq, fm->cdScal, fm->proxState, fm->psgdThr})
     cudaFree(p);
+  cudaFree(fm->sgdCnt);
   cudaFree(fm->lazyInv);
   cudaFree(fm->lazyFlag);
   delete fm;
@@ -567,6 +568,12 @@ static int apply_prox(nimfm_ctx *ctx, nimfm_fm *fm, int reg, double lam) {
 
 // entry points for psgd.cu (the SquaredL12 route of PSGD reuses the row kernel and the prox kernels)
 int nimfm_fm_apply_prox(nimfm_ctx *ctx, nimfm_fm *fm, int reg, double lam) { return apply_prox(ctx, fm, reg, lam); }
+// the row kernel over rows of a resident dataset into fm->grad (+ red4 at ctx->scalars+8), for sgd_mb.cu
+int nimfm_fm_launch_grad_rows(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, int loss, double thr,
+                              int64_t rowBegin, int64_t nRows, const int32_t *rowIdxDev, double mb) {
+  return launch_loss_grad(ctx, fm, X, loss, thr, rowBegin, nRows, rowIdxDev, mb, nullptr);
+}
+double nimfm_get_eta(int sched, double eta0, double power, double reg, int64_t it) { return get_eta(sched, eta0, power, reg, it); }
 int nimfm_fm_loss_grad_one_row(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, int loss, double thr,
                                int64_t row) {
   int rc = launch_loss_grad(ctx, fm, X, loss, thr, row, 1, nullptr, 1.0, nullptr);

@@ -209,11 +209,15 @@ def _windowed_epoch(epoch, ctx, h, X, cfg, it, viol, lossSum, multiple):
 # ================================================================ SGD
 class SGD(_Base):
     def __init__(self, maxIter=100, eta0=0.01, alpha0=1e-6, alpha=1e-3, beta=1e-3, loss=None,
-                 scheduling=optimal, power=1.0, verbose=1, tol=1e-3, shuffle=True, nCalls=-1):
+                 scheduling=optimal, power=1.0, verbose=1, tol=1e-3, shuffle=True, nCalls=-1, miniBatchSize=1):
+        """newSGD (sgd.nim:23-52).  miniBatchSize is this implementation's extra knob: 1 is the reference's
+        strictly sequential semantics; >1 is the synchronous-minibatch variant (the deterministic analogue of
+        the Hogwild fit(..., maxThreads))."""
         self.maxIter, self.eta0, self.alpha0, self.alpha, self.beta = maxIter, eta0, alpha0, alpha, beta
         self.loss = loss if loss is not None else Squared()
         self.scheduling, self.power = scheduling, power
         self.verbose, self.tol, self.shuffle, self.nCalls = verbose, tol, shuffle, nCalls
+        self.miniBatchSize = int(miniBatchSize)
         self.it = 1
 
     def init(self):                            # sgd.nim:55-57
@@ -222,9 +226,12 @@ class SGD(_Base):
             echoHeader(self.maxIter)
 
     def fit(self, X, y, fm, maxThreads=None, callback=None, perms=None):
-        """sgd.nim:261-328 / sgd_ffm.nim:49-106.  maxThreads (the Hogwild variants' argument,
-        sgd_multi.nim:40) is accepted and ignored: the device path keeps the exact sequential
-        semantics."""
+        """sgd.nim:261-328 / sgd_ffm.nim:49-106.  fit(..., maxThreads) is the reference's Hogwild variant
+        (sgd_multi.nim:40-120, sgd_ffm_multi.nim:31-103: T lock-free threads, every sample sees parameters up
+        to ~T updates stale, results nondeterministic); its deterministic device analogue is the synchronous
+        minibatch of T samples (nimfm_*_sgd_minibatch_epoch).  maxThreads < 0 means "as many as the machine
+        runs at once" there (2 x cores, sgd_multi.nim:13-18) and here (4096 resident rows).  Without
+        maxThreads (and miniBatchSize = 1) the device keeps the exact sequential semantics."""
         is_ffm = isinstance(fm, FieldAwareFactorizationMachine)
         if X.windowed and is_ffm:
             raise TypeError("field stream files are not supported")
@@ -240,6 +247,15 @@ class SGD(_Base):
                                     lib.nimfm_fm_free))
         cfg = _lib.SgdCfg(self.loss.kind, self.loss.threshold, self.eta0, self.alpha0, self.alpha, self.beta,
                           _lib.SCHED[self.scheduling], self.power)
+        mbs = self.miniBatchSize
+        if maxThreads is not None and mbs == 1:
+            mbs = 4096 if maxThreads < 0 else max(1, int(maxThreads))
+        if mbs > 1:
+            if X.windowed:
+                raise ValueError("minibatch SGD needs a resident dataset")
+            mb_epoch = lib.nimfm_ffm_sgd_minibatch_epoch if is_ffm else lib.nimfm_fm_sgd_minibatch_epoch
+            begin = end = lambda *_: 0          # parameters stay canonical: no scaling caches to set up / fold in
+            epoch = lambda c_, h_, x_, cfg_, it_, idx_, n_, v_, l_: mb_epoch(c_, h_, x_, cfg_, mbs, it_, idx_, n_, v_, l_)
         if not fm.warmStart:
             self.init()
         rng = self._rng(fm)
@@ -284,8 +300,9 @@ class SGD(_Base):
 
 
 def newSGD(maxIter=100, eta0=0.01, alpha0=1e-6, alpha=1e-3, beta=1e-3, loss=None, scheduling=optimal,
-           power=1.0, verbose=1, tol=1e-3, shuffle=True, nCalls=-1):
-    return SGD(maxIter, eta0, alpha0, alpha, beta, loss, scheduling, power, verbose, tol, shuffle, nCalls)
+           power=1.0, verbose=1, tol=1e-3, shuffle=True, nCalls=-1, miniBatchSize=1):
+    return SGD(maxIter, eta0, alpha0, alpha, beta, loss, scheduling, power, verbose, tol, shuffle, nCalls,
+               miniBatchSize)
 
 
 # ================================================================ AdaGrad

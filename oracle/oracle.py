@@ -559,3 +559,91 @@ def load_user_item_rating(path):
     idx[0::2] = np.array(users, np.int64) - min_user
     idx[1::2] = np.array(items, np.int64) + n_users - min_item
     return CSR(np.ones(2 * n), idx, np.arange(n + 1) * 2, n, n_users + n_items if n else 0), f64(y)
+
+
+# ---------------------------------------------------------------- synchronous-minibatch SGD
+def get_eta(scheduling, eta0, power, reg, it):
+    """getEta (optimizer/sgd.nim:60-69)"""
+    if scheduling == "constant":
+        return eta0
+    if scheduling == "optimal":
+        return eta0 / (1.0 + eta0 * reg * float(it)) ** power
+    if scheduling == "invscaling":
+        return eta0 / float(it) ** power
+    return 1.0 / (reg * float(it))      # pegasos
+
+
+def _shrink_pow(base, B):
+    s = 1.0
+    for _ in range(B):
+        s *= base
+    return s
+
+
+def sgd_minibatch_fit(X, y, P, w, intercept, degree=2, loss_kind="squared", B=1, max_iter=3, eta0=0.01, alpha0=1e-6,
+                      alpha=1e-3, beta=1e-3, scheduling="optimal", power=1.0, it=1, perms=None, fit_linear=True,
+                      fit_intercept=True, ffm=False, thr=1.0):
+    """The deterministic device analogue of the reference's Hogwild SGD (sgd_multi.nim:40-120,
+    sgd_ffm_multi.nim:31-103), restated: the B samples of a minibatch see the same parameters (predictWithGrad,
+    sgd.nim:191-202 / sgd_ffm.nim:11-30, summed with coef = dloss), then
+        touched features (those occurring in the minibatch; all orders / fields, as update() sgd.nim:214-222):
+            p <- (1 - eta_P beta)^B p - eta_P sum_i dL_i dA_i,   viol += |p_new - p|
+        untouched:  p <- (1 - eta_P beta)^B p                    (the lazy scaling of sgd.nim:231-239)
+        w likewise with (eta_w, alpha); b <- (1 - eta_b alpha0)^B b - eta_b sum_i dL_i;   it += B
+    with the step sizes of the minibatch's first iteration.  B = 1 is step() itself.
+    P: model layout ([nOrders, k, d+aug] for FM, [nFields, d, k] for FFM).  Returns P, w, intercept, it and the
+    per-epoch viol / mean loss."""
+    P, w, b = f64(P).copy(), f64(w).copy(), float(intercept)
+    y = f64(y)
+    n, d = X.n, X.d
+    viols, losses = [], []
+    order = np.arange(n)
+    for ep in range(max_iter):
+        if perms is not None:
+            order = i64(perms[ep])
+        viol, loss_sum = 0.0, 0.0
+        for q0 in range(0, n, B):
+            rows = order[q0:q0 + B]
+            Bm = len(rows)
+            sub = csr_take_rows(X, rows)
+            if ffm:
+                sub.fields = np.concatenate([X.fields[X.indptr[r]:X.indptr[r + 1]] for r in rows]).astype(np.int64) \
+                    if Bm else np.zeros(0, np.int64)
+                sub.n_fields = X.n_fields
+                g = ffm_loss_grad(sub, y[rows], P, w, b, loss_kind, mini_batch_size=1, thr=thr)
+            else:
+                g = fm_loss_grad(sub, y[rows], P, w, b, degree, loss_kind, mini_batch_size=1, thr=thr)
+            loss_sum += g["loss"]
+            etaP, etaW, etaB = (get_eta(scheduling, eta0, power, r_, it) for r_ in (beta, alpha, alpha0))
+            sP, sW, sB = _shrink_pow(1.0 - etaP * beta, Bm), _shrink_pow(1.0 - etaW * alpha, Bm), \
+                _shrink_pow(1.0 - etaB * alpha0, Bm)
+            touched = np.zeros(P.shape[1] if ffm else P.shape[2], bool)
+            touched[np.unique(sub.indices)] = True
+            if not ffm:
+                touched[d:] = True                      # dummy features occur in every row (dataset.nim:182-189)
+            if ffm:
+                Pn = sP * P
+                upd = sP * P[:, touched, :] - etaP * g["gP"][:, touched, :]
+                viol += float(np.abs(upd - P[:, touched, :]).sum())
+                Pn[:, touched, :] = upd
+            else:
+                Pn = sP * P
+                upd = sP * P[:, :, touched] - etaP * g["gP"][:, :, touched]
+                viol += float(np.abs(upd - P[:, :, touched]).sum())
+                Pn[:, :, touched] = upd
+            P = Pn
+            if fit_linear:
+                tw = touched[:d]
+                wn = sW * w
+                updw = sW * w[tw] - etaW * g["gw"][tw]
+                viol += float(np.abs(updw - w[tw]).sum())
+                wn[tw] = updw
+                w = wn
+            if fit_intercept:
+                bn = sB * b - etaB * g["gb"]
+                viol += abs(bn - b)
+                b = bn
+            it += Bm
+        viols.append(viol)
+        losses.append(loss_sum / n)
+    return dict(P=P, w=w, intercept=b, it=it, viol=np.array(viols), loss=np.array(losses))

@@ -337,3 +337,97 @@ def test_psgd_permutation_logistic_and_rules(oracle):
     fm3 = nf.newFactorizationMachine(nf.regression, degree=3, nComponents=2)
     with pytest.raises(ValueError, match="SquaredL12 supports only degree=2"):
         nf.newPSGD(maxIter=1, verbose=0).fit(nf.newCSRDataset(csr.data, csr.indices, csr.indptr, n, d), y, fm3)
+
+
+# ---------------------------------------------------------------- synchronous-minibatch SGD (Hogwild's device analogue)
+@pytest.mark.parametrize("B", [1, 5, 64])
+@pytest.mark.parametrize("degree,fit_lower,k", [(2, "explicit", 8), (3, "explicit", 4), (3, "augment", 16), (2, "none", 30)])
+@pytest.mark.parametrize("fit_linear,fit_intercept", [(True, True), (False, True), (True, False)])
+def test_fm_sgd_minibatch(oracle, B, degree, fit_lower, k, fit_linear, fit_intercept):
+    """nimfm_fm_sgd_minibatch_epoch against oracle.sgd_minibatch_fit (which, at B = 1, test_oracle.py holds to
+    the line-by-line restatement of SGD.fit): ragged rows so that most features sit out most minibatches,
+    strong L2 so that their shrink is visible, a shuffled sample order, a partial last minibatch."""
+    n, d = 203, 60
+    rng = np.random.default_rng(31)
+    X = make_dense(n, d, 8, density=0.12, positive=False)
+    X[5] = 0.0
+    csr = CSR.from_dense(X)
+    y = np.sign(rng.standard_normal(n))
+    P, w, _ = make_fm_params(d, degree, k, fit_lower, fit_linear, seed=9, scale=0.1)
+    kw = dict(eta0=0.03, alpha0=1e-3, alpha=2e-2, beta=3e-2)
+    perms = np.array([np.random.default_rng(70 + e).permutation(n) for e in range(3)])
+    ref = oracle.sgd_minibatch_fit(csr, y, P, w, 0.1, degree, "logistic", B=B, max_iter=3, perms=perms, it=1,
+                                   fit_linear=fit_linear, fit_intercept=fit_intercept, **kw)
+    fm = nf.newFactorizationMachine(nf.classification, degree=degree, nComponents=k, fitLower=fit_lower,
+                                    fitLinear=fit_linear, fitIntercept=fit_intercept, warmStart=True)
+    fm.P, fm.w, fm.intercept, fm.isInitialized = P.copy(), w.copy(), 0.1, True
+    opt = nf.newSGD(maxIter=3, loss=nf.Logistic(), verbose=0, tol=0.0, miniBatchSize=B if B > 1 else 1, **kw)
+    ds = nf.newCSRDataset(csr.data, csr.indices, csr.indptr, n, d)
+    opt.fit(ds, y, fm, perms=perms)        # B == 1: the sequential kernel, i.e. the reference's own loop
+    np.testing.assert_allclose([h[1] for h in opt.history], ref["loss"], rtol=OBJ_TOL)
+    np.testing.assert_allclose([h[0] for h in opt.history], ref["viol"], rtol=1e-8)
+    assert max_rel(fm.P, ref["P"]) <= 1e-9 and max_rel(fm.w, ref["w"]) <= 1e-9
+    assert abs(fm.intercept - ref["intercept"]) <= 1e-10 and opt.it == ref["it"]
+
+
+def test_fm_sgd_minibatch_of_one_and_max_threads(oracle):
+    """the minibatch entry point with miniBatchSize = 1 reproduces the sequential solver; fit(..., maxThreads=T)
+    (the reference's Hogwild entry point, sgd_multi.nim:40) runs the synchronous minibatch of T samples"""
+    n, d, k = 90, 25, 8
+    X = make_dense(n, d, 3, density=0.3, positive=False)
+    csr = CSR.from_dense(X)
+    y = np.random.default_rng(2).standard_normal(n)
+    P, w, _ = make_fm_params(d, 2, k, "explicit", True, seed=1, scale=0.1)
+    kw = dict(eta0=0.02, alpha0=1e-4, alpha=1e-2, beta=1e-2)
+    seq = oracle.sgd_fit(csr, y, P, w, 0.0, 2, "squared", max_iter=2, it=1, **kw)
+    lib, ctx = _lib.load(), _lib.ctx()
+    fm = nf.newFactorizationMachine(nf.regression, degree=2, nComponents=k, warmStart=True)
+    fm.P, fm.w, fm.intercept, fm.isInitialized = P.copy(), w.copy(), 0.0, True
+    ds = nf.newCSRDataset(csr.data, csr.indices, csr.indptr, n, d)
+    ds.set_targets(y)
+    h = fm._to_device(d)
+    try:
+        cfg = _lib.SgdCfg(0, 1.0, kw["eta0"], kw["alpha0"], kw["alpha"], kw["beta"], _lib.SCHED[nf.optimal], 1.0)
+        it = C.c_int64(1)
+        for ep in range(2):
+            viol, ls = C.c_double(), C.c_double()
+            _lib.check(lib.nimfm_fm_sgd_minibatch_epoch(ctx, h, ds.handle(), C.byref(cfg), 1, C.byref(it), None, n,
+                                                        C.byref(viol), C.byref(ls)))
+            assert abs(viol.value - seq["viol"][ep]) <= 1e-8 * seq["viol"][ep]
+            assert abs(ls.value / n - seq["loss"][ep]) <= OBJ_TOL * abs(seq["loss"][ep])
+        fm._from_device(h)
+        assert it.value == seq["it"] and max_rel(fm.P, seq["P"]) <= 1e-9 and max_rel(fm.w, seq["w"]) <= 1e-9
+        with pytest.raises(ValueError, match="miniBatchSize"):
+            _lib.check(lib.nimfm_fm_sgd_minibatch_epoch(ctx, h, ds.handle(), C.byref(cfg), 0, C.byref(it), None, n, None, None))
+    finally:
+        lib.nimfm_fm_free(ctx, h)
+    ref = oracle.sgd_minibatch_fit(csr, y, P, w, 0.0, 2, "squared", B=7, max_iter=2, it=1, **kw)
+    fm2 = nf.newFactorizationMachine(nf.regression, degree=2, nComponents=k, warmStart=True)
+    fm2.P, fm2.w, fm2.intercept, fm2.isInitialized = P.copy(), w.copy(), 0.0, True
+    opt = nf.newSGD(maxIter=2, verbose=0, tol=0.0, shuffle=False, **kw)
+    opt.fit(ds, y, fm2, maxThreads=7)
+    assert max_rel(fm2.P, ref["P"]) <= 1e-9 and opt.it == ref["it"]
+    np.testing.assert_allclose([h_[0] for h_ in opt.history], ref["viol"], rtol=1e-8)
+
+
+@pytest.mark.parametrize("B", [1, 6, 50])
+def test_ffm_sgd_minibatch(oracle, B):
+    X, csr, _ = make_field_csr(83, 24, 4, 19, density=0.3)
+    k = 4
+    rng = np.random.default_rng(6)
+    P, w = rng.standard_normal((4, 24, k)) * 0.1, rng.standard_normal(24) * 0.1
+    y = np.sign(rng.standard_normal(83))
+    kw = dict(eta0=0.03, alpha0=1e-3, alpha=2e-2, beta=3e-2)
+    perms = np.array([np.random.default_rng(11 + e).permutation(83) for e in range(3)])
+    ref = oracle.sgd_minibatch_fit(csr, y, P, w, -0.1, loss_kind="logistic", B=B, max_iter=3, perms=perms, it=1,
+                                   ffm=True, **kw)
+    m = make_ffm(P, w, -0.1, task=nf.classification)
+    opt = nf.newSGD(maxIter=3, loss=nf.Logistic(), verbose=0, tol=0.0, **kw)
+    opt.fit(field_ds(csr), y, m, maxThreads=B, perms=perms)
+    if B == 1:   # maxThreads = 1 is the sequential solver, i.e. the reference itself
+        seq = oracle.ffm_sgd_fit(csr, y, P, w, -0.1, "logistic", max_iter=3, perms=perms, it=1, **kw)
+        np.testing.assert_allclose(m.P, seq["P"], rtol=1e-8, atol=1e-13)
+    np.testing.assert_allclose([h[1] for h in opt.history], ref["loss"], rtol=OBJ_TOL)
+    np.testing.assert_allclose([h[0] for h in opt.history], ref["viol"], rtol=1e-8)
+    assert max_rel(m.P, ref["P"]) <= 1e-9 and max_rel(m.w, ref["w"]) <= 1e-9
+    assert abs(m.intercept - ref["intercept"]) <= 1e-10 and opt.it == ref["it"]

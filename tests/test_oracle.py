@@ -320,3 +320,43 @@ def test_psgd_oracle_vs_reference_slow_solver(oracle, degree, fit_lower, reg):
     # the prox acts: a larger gamma zeroes parameters
     r = oracle.psgd_fit(csr, y, P, w, 0.0, degree, "squared", max_iter=2, reg=reg, eta0=0.05, gamma=0.5)
     assert np.count_nonzero(r["P"] == 0.0) > 0
+
+
+@pytest.mark.parametrize("degree,fit_lower", [(2, "explicit"), (3, "explicit"), (3, "augment"), (2, "none")])
+@pytest.mark.parametrize("fit_linear,fit_intercept", [(True, True), (False, True), (True, False)])
+def test_minibatch_sgd_restatement_with_one_sample_is_the_sequential_step(oracle, degree, fit_lower, fit_linear, fit_intercept):
+    """sgd_minibatch_fit (the rule the device's synchronous-minibatch SGD follows) with B = 1 is step()
+    (sgd.nim:205-258): same iterates, viol and loss as the line-by-line restatement of SGD.fit, up to the
+    rounding of eager vs lazy scaling of the untouched features."""
+    n, d, k = 60, 9, 4
+    X = make_dense(n, d, 21, density=0.4, positive=False)
+    y = np.random.default_rng(1).standard_normal(n)
+    csr = CSR.from_dense(X)
+    P, w, _ = make_fm_params(d, degree, k, fit_lower, fit_linear, seed=3, scale=0.1)
+    kw = dict(eta0=0.05, alpha0=1e-3, alpha=1e-2, beta=2e-2, scheduling="optimal", power=1.0)
+    perms = np.array([np.random.default_rng(5 + e).permutation(n) for e in range(3)])
+    ref = oracle.sgd_fit(csr, y, P, w, 0.2, degree, "squared", fit_linear, fit_intercept, max_iter=3, perms=perms,
+                         it=1, **kw)
+    got = oracle.sgd_minibatch_fit(csr, y, P, w, 0.2, degree, "squared", B=1, max_iter=3, perms=perms, it=1,
+                                   fit_linear=fit_linear, fit_intercept=fit_intercept, **kw)
+    assert got["it"] == ref["it"]
+    np.testing.assert_allclose(got["P"], ref["P"], rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(got["w"], ref["w"], rtol=1e-10, atol=1e-14)
+    assert abs(got["intercept"] - ref["intercept"]) <= 1e-12
+    np.testing.assert_allclose(got["viol"], ref["viol"], rtol=1e-9)
+    np.testing.assert_allclose(got["loss"], ref["loss"], rtol=1e-10)
+
+
+def test_minibatch_sgd_restatement_ffm_with_one_sample(oracle):
+    n, d, nf, k = 40, 12, 3, 3
+    _, csr, _ = make_field_csr(n, d, nf, 4)
+    y = np.random.default_rng(2).standard_normal(n)
+    rng = np.random.default_rng(7)
+    P, w = rng.standard_normal((nf, d, k)) * 0.1, rng.standard_normal(d) * 0.1
+    kw = dict(eta0=0.05, alpha0=1e-3, alpha=1e-2, beta=2e-2, scheduling="optimal", power=1.0)
+    ref = oracle.ffm_sgd_fit(csr, y, P, w, 0.1, "squared", True, True, max_iter=2, it=1, **kw)
+    got = oracle.sgd_minibatch_fit(csr, y, P, w, 0.1, loss_kind="squared", B=1, max_iter=2, it=1, ffm=True, **kw)
+    np.testing.assert_allclose(got["P"], ref["P"], rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(got["w"], ref["w"], rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(got["viol"], ref["viol"], rtol=1e-9)
+    np.testing.assert_allclose(got["loss"], ref["loss"], rtol=1e-10)
