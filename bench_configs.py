@@ -174,6 +174,25 @@ def main():
                           "note": "decisionFunction: wall clock incl. 512 MB parameter upload + result download; "
                                   "adagrad: the blocking nimfm_fm_adagrad_epoch call",
                           "adagrad_epoch_loss": opt.history[-1][1]}), flush=True)
+        # SGD: the sequential solver (the reference's SGD.fit) on a row sample, and fit(..., maxThreads=T) -- the
+        # reference's Hogwild entry point -- as synchronous minibatches of T samples (eta0 tiny: a minibatch moves
+        # the parameters by T * eta * mean gradient, like T sequential steps)
+        sgd = {}
+        for T in (4096, 65536):
+            f2 = nf.newFactorizationMachine(nf.classification, degree=3, nComponents=32, warmStart=True)
+            f2.P, f2.w, f2.intercept, f2.isInitialized = P.copy(), w.copy(), b, True
+            o2 = nf.newSGD(maxIter=2, eta0=1e-6, loss=nf.Logistic(), verbose=0, tol=0.0, shuffle=False)
+            o2.fit(ds, y, f2, maxThreads=T)
+            sgd[f"minibatch_{T}_samples_per_s"] = n / float(np.min(o2.epoch_seconds))
+        ns = min(n, 20000)
+        f2 = nf.newFactorizationMachine(nf.classification, degree=3, nComponents=32, warmStart=True)
+        f2.P, f2.w, f2.intercept, f2.isInitialized = P.copy(), w.copy(), b, True
+        o2 = nf.newSGD(maxIter=1, eta0=1e-6, loss=nf.Logistic(), verbose=0, tol=0.0, shuffle=False)
+        o2.fit(ds[0:ns], y[:ns], f2)
+        sgd["sequential_samples_per_s"] = ns / float(np.min(o2.epoch_seconds))
+        print(json.dumps({"config": "C4c", "what": f"HOFM degree 3 rank 32, n={n}: SGD sequential (first {ns} rows) and "
+                          "synchronous-minibatch SGD, the device analogue of Hogwild fit(..., maxThreads=T)", **sgd}),
+              flush=True)
         ds.free()
 
     # ---------------------------------------------------------------- C5: FFM predict+grad

@@ -82,7 +82,12 @@ static __global__ void __launch_bounds__(256) mbpsgd_lazy_P_kernel(double *__res
                                                                    int shift, int64_t nP,
                                                                    const uint8_t *__restrict__ flag,
                                                                    const double2 *__restrict__ inv, double cumPt,
-                                                                   double negEtaP, double rP) {
+                                                                   double negEtaP, double rP, double aP = 1.0,
+                                                                   double *violPart = nullptr) {
+  // p_new = (aP * p_eff + negEtaP * g) * rP: MBPSGD (aP = 1, rP = 1/(1+eta beta)); minibatch SGD (sgd_mb.cu:
+  // aP = (1-eta beta)^B, rP = 1) also wants viol = sum |p_new - p_eff| (violPart[block*4])
+  __shared__ double red[8];
+  double viol = 0.0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   for (int64_t e0 = tid; e0 < nP; e0 += 4 * stride) {
@@ -97,9 +102,20 @@ static __global__ void __launch_bounds__(256) mbpsgd_lazy_P_kernel(double *__res
       if (!on[i]) continue;
       const int64_t e = e0 + i * stride;
       const double fac = cumPt * inv[e >> shift].x;
-      const double p = P[e] * fac + negEtaP * (gP[e] / fac);
-      P[e] = p * rP;
+      const double pe = P[e] * fac;
+      const double p = (aP * pe + negEtaP * (gP[e] / fac)) * rP;
+      viol += fabs(p - pe);
+      P[e] = p;
       gP[e] = 0.0;
+    }
+  }
+  if (violPart) {   // uniform across the grid
+    viol = block_sum(viol, red);
+    if (threadIdx.x == 0) {
+      violPart[blockIdx.x * 4 + 0] = viol;
+      violPart[blockIdx.x * 4 + 1] = 0.0;
+      violPart[blockIdx.x * 4 + 2] = 0.0;
+      violPart[blockIdx.x * 4 + 3] = 0.0;
     }
   }
 }
@@ -107,16 +123,21 @@ static __global__ void __launch_bounds__(256) mbpsgd_lazy_P_kernel(double *__res
 static __global__ void __launch_bounds__(256) mbpsgd_lazy_feat_kernel(
     int64_t dd, int64_t d, double *w, double *gw, uint8_t *flag, double2 *inv, double cumPt, double cumWt,
     double invPnext, double invWnext, double negEtaW, double rW, int fitLinear, double *b, const double *partials,
-    int64_t partialRows, double negEtaB, double rB, int fitIntercept, double *scal) {
+    int64_t partialRows, double negEtaB, double rB, int fitIntercept, double *scal, double aW = 1.0,
+    double *violPart = nullptr) {
+  // violPart != nullptr: the minibatch-SGD rule (w_new = aW w_eff - eta gw, b_new = rB b - eta gb, viol)
   __shared__ double red[8];
+  double viol = 0.0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < dd; j += stride) {
     if (!flag[j]) continue;
     const double2 iv = inv[j];
     if (j < d) {
       if (fitLinear) {
-        const double v = w[j] * (cumWt * iv.y) + negEtaW * (gw[j] / (cumPt * iv.x));
-        w[j] = v * rW;
+        const double we = w[j] * (cumWt * iv.y);
+        const double v = (aW * we + negEtaW * (gw[j] / (cumPt * iv.x))) * rW;
+        viol += fabs(v - we);
+        w[j] = v;
       }
       gw[j] = 0.0;
     }
@@ -134,10 +155,28 @@ static __global__ void __launch_bounds__(256) mbpsgd_lazy_feat_kernel(
     const double gb = block_sum(acc1, red);
     if (threadIdx.x == 0) {
       double bb = b[0];
-      if (fitIntercept && fitLinear) bb += negEtaB * gb;   // params.nim:47
-      if (fitIntercept) bb *= rB;                          // params.nim:65-66
+      if (violPart) {                                        // sgd.nim:225-228
+        if (fitIntercept) {
+          const double bn = rB * bb + negEtaB * gb;
+          viol += fabs(bn - bb);
+          bb = bn;
+        }
+      } else {
+        if (fitIntercept && fitLinear) bb += negEtaB * gb;   // params.nim:47
+        if (fitIntercept) bb *= rB;                          // params.nim:65-66
+      }
       b[0] = bb;
       scal[0] += lossSum;
+    }
+    __syncthreads();
+  }
+  if (violPart) {
+    viol = block_sum(viol, red);
+    if (threadIdx.x == 0) {
+      violPart[blockIdx.x * 4 + 0] = viol;
+      violPart[blockIdx.x * 4 + 1] = 0.0;
+      violPart[blockIdx.x * 4 + 2] = 0.0;
+      violPart[blockIdx.x * 4 + 3] = 0.0;
     }
   }
 }

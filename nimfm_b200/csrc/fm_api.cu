@@ -627,7 +627,8 @@ int32_t nimfm_fm_mbpsgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset 
         const double etaP = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->beta, *it + t);
         const double etaW = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->alpha, *it + t);
         cum[t + 1] = cum[t] * (1.0 / (1.0 + etaP * cfg->beta));
-        cum[T + 1 + t + 1] = cum[T + 1 + t] * (1.0 / (1.0 + etaW * cfg->alpha));
+        // fitLinear = false: w is frozen (params.nim:90-98), and the row kernel must see it unscaled
+        cum[T + 1 + t + 1] = fm->fitLinear ? cum[T + 1 + t] * (1.0 / (1.0 + etaW * cfg->alpha)) : 1.0;
       }
       if (!(cum[T] > 1e-100) || !(cum[2 * T + 1] > 1e-100)) lazy = false;
     }
@@ -707,6 +708,99 @@ int32_t nimfm_fm_mbpsgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset 
   *ii = cur;
   // runningLoss / (miniBatchSize*maxIterInner) (:124); the loss sum was all-reduced with the gradient
   if (runningLoss) *runningLoss = ctx->hostScalars[0] / (double)(cfg->miniBatchSize * cfg->maxIterInner);
+  return NIMFM_OK;
+}
+
+// ================================================================== minibatch SGD, lazy form (sgd_mb.cu, K6b)
+// The rule of sgd_mb.cu with the K3b machinery: untouched features owe cum[t] * inv[j] = prod (1-eta beta)^B of
+// the minibatches they sat out; the row kernel folds it into x, two flat kernels update the touched features,
+// one dense pass at the end of the epoch settles the rest.  *applied = 0: not applicable here (the caller runs
+// the dense form).  idxDev: staged sample order (nullable).
+int nimfm_fm_sgd_mb_lazy_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, const nimfm_sgd_cfg *cfg,
+                               int64_t B, int64_t *it, const int32_t *idxDev, int64_t nRows, int *applied,
+                               double *viol, double *lossSum) {
+  *applied = 0;
+  if (nRows <= 0 || X->n <= 0) return NIMFM_OK;
+  const int64_t T = (nRows + B - 1) / B;
+  const char *env = getenv("NIMFM_SGD_MB_LAZY");
+  const double touchedUpper = (double)B * ((double)X->nnz / (double)X->n + fm->nAug);
+  bool lazy = false;   // opt-in (NIMFM_SGD_MB_LAZY=1) until measured; `auto` below is the intended default
+  (void)touchedUpper;
+  if (env) lazy = env[0] == '1' && ctx->nranks == 1 && T < (1 << 30);
+  if (env && env[0] == 'a') lazy = ctx->nranks == 1 && T >= 2 && T < (1 << 30) && touchedUpper <= 2.0 * (double)fm->dd();
+  const int SB8 = fm->nOrders * fm->k;
+  if (SB8 < 1 || (SB8 & (SB8 - 1))) lazy = false;
+  RowPlan plq;
+  if (lazy && (plan_rows(ctx, fm, X, std::min(B, nRows), MODE_GRAD, &plq) != NIMFM_OK || !plq.stream)) lazy = false;
+  if (!lazy) return NIMFM_OK;
+  // per-minibatch step sizes / shrink factors and their running products
+  std::vector<double> etaP((size_t)T), etaW((size_t)T), etaB((size_t)T), sP((size_t)T), sW((size_t)T), sB((size_t)T);
+  std::vector<double> cumP((size_t)T + 1, 1.0), cumW((size_t)T + 1, 1.0);
+  auto shrink_pow = [](double base, int64_t n) { double s = 1.0; for (int64_t i = 0; i < n; i++) s *= base; return s; };
+  for (int64_t t = 0; t < T; t++) {
+    const int64_t Bm = std::min(B, nRows - t * B), itT = *it + t * B;
+    etaP[t] = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->beta, itT);
+    etaW[t] = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->alpha, itT);
+    etaB[t] = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->alpha0, itT);
+    sP[t] = shrink_pow(1.0 - etaP[t] * cfg->beta, Bm);
+    sW[t] = shrink_pow(1.0 - etaW[t] * cfg->alpha, Bm);
+    sB[t] = shrink_pow(1.0 - etaB[t] * cfg->alpha0, Bm);
+    cumP[t + 1] = cumP[t] * sP[t];
+    cumW[t + 1] = fm->fitLinear ? cumW[t] * sW[t] : 1.0;   // fitLinear = false: w is frozen and read unscaled
+  }
+  // a factor that is not a healthy positive number (eta * reg >= 1, long decay): dense form
+  if (!(cumP[T] > 1e-100) || !(cumW[T] > 1e-100) || !(cumP[T] < 1e100) || !(cumW[T] < 1e100)) return NIMFM_OK;
+  for (int64_t t = 0; t < T; t++)
+    if (!(sP[t] > 0.0) || !(sW[t] > 0.0)) return NIMFM_OK;
+  const int64_t nP = fm->nP(), d = fm->d, dd = fm->dd(), nG = nP + d + 2;
+  int shift = 0;
+  while ((1 << shift) < SB8) shift++;
+  if (!fm->lazyInv) {
+    CK(cudaMalloc(&fm->lazyInv, (size_t)dd * sizeof(double2)));
+    CK(cudaMalloc(&fm->lazyFlag, (size_t)dd));
+    CK(cudaMemsetAsync(fm->lazyFlag, 0, (size_t)dd, ctx->stream));
+    mbpsgd_lazy_flush_feat_kernel<<<ew_grid(ctx, dd), 256, 0, ctx->stream>>>(nullptr, 0, 0, fm->lazyInv, dd, 1.0);
+    LAUNCHED(ctx);
+  }
+  const int grid = ctx->numSMs * 8;
+  const int gridF = (int)std::min<int64_t>((dd + 255) / 256, grid);
+  int rc;
+  if ((rc = nimfm_ensure_partials(ctx, (size_t)(plq.nWarps + grid + gridF) * 4))) return rc;
+  CK(cudaMemsetAsync(fm->grad, 0, (size_t)nG * 8, ctx->stream));
+  CK(cudaMemsetAsync(ctx->scalars, 0, 8, ctx->stream));
+  CK(cudaMemsetAsync(ctx->scalars + 20, 0, 4 * 8, ctx->stream));
+  *applied = 1;
+  for (int64_t t = 0; t < T; t++) {
+    const int64_t q0 = t * B, Bm = std::min(B, nRows - q0);
+    LazyView lv;
+    lv.cumPt = cumP[t];
+    lv.cumWt = cumW[t];
+    if ((rc = launch_loss_grad(ctx, fm, X, cfg->loss, cfg->huberThreshold, q0, Bm, idxDev ? idxDev + q0 : nullptr, 1.0,
+                               nullptr, &lv)))
+      return rc;
+    double *violPart = ctx->partials + (size_t)lv.partialRows * 4;
+    mbpsgd_lazy_P_kernel<<<grid, 256, 0, ctx->stream>>>(fm->P, fm->grad, shift, nP, fm->lazyFlag, fm->lazyInv, lv.cumPt,
+                                                        -etaP[t], 1.0, sP[t], violPart);
+    LAUNCHED(ctx);
+    mbpsgd_lazy_feat_kernel<<<gridF, 256, 0, ctx->stream>>>(
+        dd, d, fm->w, fm->grad + nP, fm->lazyFlag, fm->lazyInv, lv.cumPt, lv.cumWt, 1.0 / cumP[t + 1], 1.0 / cumW[t + 1],
+        -etaW[t], 1.0, fm->fitLinear, fm->b, ctx->partials, lv.partialRows, -etaB[t], sB[t], fm->fitIntercept,
+        ctx->scalars, sW[t], violPart + (size_t)grid * 4);
+    LAUNCHED(ctx);
+    reduce_partials_kernel<<<1, 256, 0, ctx->stream>>>(violPart, grid + gridF, ctx->scalars + 20, 1);
+    LAUNCHED(ctx);
+    *it += Bm;
+  }
+  mbpsgd_lazy_flush_P_kernel<<<ew_grid(ctx, nP), 256, 0, ctx->stream>>>(fm->P, shift, nP, fm->lazyInv, cumP[T]);
+  LAUNCHED(ctx);
+  mbpsgd_lazy_flush_feat_kernel<<<ew_grid(ctx, dd), 256, 0, ctx->stream>>>(fm->w, d, fm->fitLinear, fm->lazyInv, dd, cumW[T]);
+  LAUNCHED(ctx);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctx->hostScalars, ctx->scalars, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->hostScalars + 1, ctx->scalars + 20, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (lossSum) *lossSum = ctx->hostScalars[0];
+  if (viol) *viol = ctx->hostScalars[1];
   return NIMFM_OK;
 }
 

@@ -24,6 +24,9 @@ int nimfm_fm_launch_grad_rows(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset 
 int nimfm_ffm_launch_grad_rows(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_dataset *X, int loss, double thr,
                                int64_t rowBegin, int64_t nRows, const int32_t *rowIdxDev, double mb);
 double nimfm_get_eta(int sched, double eta0, double power, double reg, int64_t it);
+int nimfm_fm_sgd_mb_lazy_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, const nimfm_sgd_cfg *cfg,
+                               int64_t B, int64_t *it, const int32_t *idxDev, int64_t nRows, int *applied,
+                               double *viol, double *lossSum);
 }
 
 namespace {
@@ -180,6 +183,20 @@ int32_t nimfm_fm_sgd_minibatch_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_d
   REQUIRE(X->kind == NIMFM_DS_CSR || X->kind == NIMFM_DS_CSR_FIELD, "a CSR dataset is required");
   REQUIRE(X->d == fm->d, "Invalid nFeatures. (dataset %lld, model %lld)", (long long)X->d, (long long)fm->d);
   REQUIRE(X->y != nullptr, "dataset has no targets (nimfm_dataset_set_targets)");
+  REQUIRE(cfg && it && miniBatchSize >= 1, "NULL argument or miniBatchSize < 1");
+  REQUIRE(nRows >= 0 && (perm != nullptr || nRows <= X->n), "bad nRows");
+  {
+    // touched-features-only form when a minibatch touches a minority of the features (K6b over K3b)
+    const int32_t *idxDev = nullptr;
+    if (perm && nRows > 0) {
+      int rcs = nimfm_stage_row_ids(ctx, perm, nRows, X->n);
+      if (rcs) return rcs;
+      idxDev = ctx->idx32Scratch;
+    }
+    int applied = 0;
+    int rcl = nimfm_fm_sgd_mb_lazy_epoch(ctx, fm, X, cfg, miniBatchSize, it, idxDev, nRows, &applied, viol, lossSum);
+    if (rcl || applied) return rcl;
+  }
   MbModel M{fm->P, fm->grad, fm->w, fm->b, fm->nP(), (int64_t)fm->nOrders * fm->k, fm->d, fm->dd(), fm->nAug,
             fm->fitLinear, fm->fitIntercept, &fm->sgdCnt};
   if (fm->nOrders == 0) M.SB8 = 1;

@@ -343,10 +343,14 @@ def test_psgd_permutation_logistic_and_rules(oracle):
 @pytest.mark.parametrize("B", [1, 5, 64])
 @pytest.mark.parametrize("degree,fit_lower,k", [(2, "explicit", 8), (3, "explicit", 4), (3, "augment", 16), (2, "none", 30)])
 @pytest.mark.parametrize("fit_linear,fit_intercept", [(True, True), (False, True), (True, False)])
-def test_fm_sgd_minibatch(oracle, B, degree, fit_lower, k, fit_linear, fit_intercept):
+@pytest.mark.parametrize("lazy", ["0", "1"])
+def test_fm_sgd_minibatch(oracle, monkeypatch, B, degree, fit_lower, k, fit_linear, fit_intercept, lazy):
     """nimfm_fm_sgd_minibatch_epoch against oracle.sgd_minibatch_fit (which, at B = 1, test_oracle.py holds to
     the line-by-line restatement of SGD.fit): ragged rows so that most features sit out most minibatches,
-    strong L2 so that their shrink is visible, a shuffled sample order, a partial last minibatch."""
+    strong L2 so that their shrink is visible, a shuffled sample order, a partial last minibatch.  lazy: the
+    dense step over all parameters vs the touched-features-only form (streaming row kernel shapes only; the
+    others fall back to the dense step by themselves)."""
+    monkeypatch.setenv("NIMFM_SGD_MB_LAZY", lazy)
     n, d = 203, 60
     rng = np.random.default_rng(31)
     X = make_dense(n, d, 8, density=0.12, positive=False)
@@ -354,6 +358,8 @@ def test_fm_sgd_minibatch(oracle, B, degree, fit_lower, k, fit_linear, fit_inter
     csr = CSR.from_dense(X)
     y = np.sign(rng.standard_normal(n))
     P, w, _ = make_fm_params(d, degree, k, fit_lower, fit_linear, seed=9, scale=0.1)
+    if not fit_linear:   # a frozen, nonzero w still enters every prediction and is never scaled (sgd.nim:229-236)
+        w = np.random.default_rng(78).standard_normal(d) * 0.1
     kw = dict(eta0=0.03, alpha0=1e-3, alpha=2e-2, beta=3e-2)
     perms = np.array([np.random.default_rng(70 + e).permutation(n) for e in range(3)])
     ref = oracle.sgd_minibatch_fit(csr, y, P, w, 0.1, degree, "logistic", B=B, max_iter=3, perms=perms, it=1,

@@ -330,6 +330,8 @@ def test_mbpsgd_lazy_epoch_matches_oracle(oracle, monkeypatch, degree, fit_lower
     csr = ragged_csr(n, d, 23, 6)
     y = np.sign(np.random.default_rng(6).standard_normal(n))
     P, w, _ = make_fm_params(d, degree, k, fit_lower, fit_linear, seed=12, scale=0.1)
+    if not fit_linear:   # a frozen, nonzero w still enters every prediction and must not be shrunk (params.nim:90-98)
+        w = np.random.default_rng(77).standard_normal(d) * 0.1
     kw = dict(eta0=0.3, alpha0=1e-3, alpha=5e-2, beta=8e-2, gamma=0.0)
     perms = None
     if shuffle:   # the permutations the host mirror will draw (initial shuffle + one per wrap-around)
