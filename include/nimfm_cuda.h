@@ -307,13 +307,17 @@ int32_t nimfm_ffm_adagrad_finalize(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_ada
  * evaluated at the same parameters and their updates applied at once with the step sizes of the minibatch's
  * first iteration: touched features p <- (1-eta beta)^B p - eta sum_i dL_i dA_i (viol += |p_new - p|),
  * untouched features p <- (1-eta beta)^B p, it += B.  miniBatchSize = 1 is step() itself (sgd.nim:205-258).
- * No begin / end: the parameters stay canonical between calls.  perm (nullable): sample order. */
+ * No begin / end: the parameters stay canonical between calls.  perm (nullable): sample order.
+ * Data parallel like nimfm_fm_mbpsgd_epoch: with a communicator X is this rank's shard, localBatch (<= 0: =
+ * miniBatchSize) the rows this rank feeds per minibatch, miniBatchSize = localBatch x ranks the global one;
+ * touch counts and gradients are all-reduced, every rank applies the identical step. */
 int32_t nimfm_fm_sgd_minibatch_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, const nimfm_sgd_cfg *cfg,
-                                     int64_t miniBatchSize, int64_t *it, const int64_t *perm, int64_t nRows,
-                                     double *viol, double *lossSum);
+                                     int64_t miniBatchSize, int64_t localBatch, int64_t *it, const int64_t *perm,
+                                     int64_t nRows, double *viol, double *lossSum);
 int32_t nimfm_ffm_sgd_minibatch_epoch(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_dataset *X,
-                                      const nimfm_sgd_cfg *cfg, int64_t miniBatchSize, int64_t *it,
-                                      const int64_t *perm, int64_t nRows, double *viol, double *lossSum);
+                                      const nimfm_sgd_cfg *cfg, int64_t miniBatchSize, int64_t localBatch,
+                                      int64_t *it, const int64_t *perm, int64_t nRows, double *viol,
+                                      double *lossSum);
 /* SGD for FFM (optimizer/sgd_ffm.nim:33-106), sequential like nimfm_fm_sgd_* */
 int32_t nimfm_ffm_sgd_begin(nimfm_ctx *ctx, nimfm_ffm *m);
 int32_t nimfm_ffm_sgd_epoch(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_dataset *X, const nimfm_sgd_cfg *cfg,

@@ -132,9 +132,9 @@ proc nimfm_ffm_adagrad_epoch(ctx: Ctx, m: DeviceFFM, X: DeviceDataset, cfg: ptr 
                              perm: ptr int64, nRows: int64, viol, lossSum: ptr cdouble): int32
 proc nimfm_ffm_adagrad_finalize(ctx: Ctx, m: DeviceFFM, cfg: ptr AdagradCfg, it: int64): int32
 proc nimfm_ffm_sgd_begin(ctx: Ctx, m: DeviceFFM): int32
-proc nimfm_fm_sgd_minibatch_epoch(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr SgdCfg, miniBatchSize: int64,
+proc nimfm_fm_sgd_minibatch_epoch(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr SgdCfg, miniBatchSize, localBatch: int64,
                                   it: ptr int64, perm: ptr int64, nRows: int64, viol, lossSum: ptr cdouble): int32
-proc nimfm_ffm_sgd_minibatch_epoch(ctx: Ctx, m: DeviceFFM, X: DeviceDataset, cfg: ptr SgdCfg, miniBatchSize: int64,
+proc nimfm_ffm_sgd_minibatch_epoch(ctx: Ctx, m: DeviceFFM, X: DeviceDataset, cfg: ptr SgdCfg, miniBatchSize, localBatch: int64,
                                    it: ptr int64, perm: ptr int64, nRows: int64, viol, lossSum: ptr cdouble): int32
 proc nimfm_ffm_sgd_epoch(ctx: Ctx, m: DeviceFFM, X: DeviceDataset, cfg: ptr SgdCfg, it: ptr int64,
                          perm: ptr int64, nRows: int64, viol, lossSum: ptr cdouble): int32

@@ -130,8 +130,8 @@ SYMBOLS = {
     "nimfm_ffm_adagrad_finalize": (c_i32, [VP, VP, C.POINTER(AdagradCfg), c_i64]),
     "nimfm_ffm_sgd_begin": (c_i32, [VP, VP]),
     "nimfm_ffm_sgd_epoch": (c_i32, [VP, VP, VP, C.POINTER(SgdCfg), PI64, VP, c_i64, PD, PD]),
-    "nimfm_fm_sgd_minibatch_epoch": (c_i32, [VP, VP, VP, C.POINTER(SgdCfg), c_i64, PI64, VP, c_i64, PD, PD]),
-    "nimfm_ffm_sgd_minibatch_epoch": (c_i32, [VP, VP, VP, C.POINTER(SgdCfg), c_i64, PI64, VP, c_i64, PD, PD]),
+    "nimfm_fm_sgd_minibatch_epoch": (c_i32, [VP, VP, VP, C.POINTER(SgdCfg), c_i64, c_i64, PI64, VP, c_i64, PD, PD]),
+    "nimfm_ffm_sgd_minibatch_epoch": (c_i32, [VP, VP, VP, C.POINTER(SgdCfg), c_i64, c_i64, PI64, VP, c_i64, PD, PD]),
     "nimfm_ffm_sgd_end": (c_i32, [VP, VP]),
     "nimfm_fm_time_loss_grad": (c_i32, [VP, VP, VP, c_i32, c_i64, c_i64, c_i32, c_i32, C.POINTER(C.c_float)]),
     "nimfm_ffm_time_loss_grad": (c_i32, [VP, VP, VP, c_i32, c_i64, c_i64, c_i32, c_i32, C.POINTER(C.c_float)]),

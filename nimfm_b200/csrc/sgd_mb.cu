@@ -12,7 +12,9 @@
 //     it += B
 // With B = 1 this is step() itself (p - eta (dL dA + beta p), viol = |update|), which the tests hold against
 // the sequential oracle; for B > 1 the oracle restates the rule above (oracle.sgd_minibatch_fit).
-// One rank only (the sequential and Hogwild forms of the reference have no distributed counterpart).
+// Data parallel like MBPSGD / AdaGrad: with a communicator, X is this rank's shard, every rank feeds localBatch
+// rows of each minibatch, the touch counts and the gradient buffer ([gP | gw | sum dL, loss]) are all-reduced
+// and every rank applies the identical step (shards must be even: B = localBatch * ranks).
 #include <algorithm>
 
 #include "common.cuh"
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(256) sgd_mb_P_kernel(double *__restrict__ P, d
 // red4 = [loss sum, sum dL, ...] of the minibatch (reduce_partials of the row kernel's partials).
 __global__ void __launch_bounds__(256) sgd_mb_feat_kernel(double *w, double *gw, int64_t d, double *cnt, int64_t dd,
                                                           double sW, double negEtaW, int fitLinear, double *b,
-                                                          const double *red4, double sB, double negEtaB,
+                                                          const double *red4, double *tail, double sB, double negEtaB,
                                                           int fitIntercept, double *scal, double *violPart) {
   __shared__ double red[8];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -92,12 +94,15 @@ __global__ void __launch_bounds__(256) sgd_mb_feat_kernel(double *w, double *gw,
     if (touched) cnt[j] = 0.0;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
+    // one rank: red4 = [loss, sum dL] of the minibatch; several: the all-reduced tail [sum dL, loss] of the buffer
+    const double gb = tail ? tail[0] : red4[1], ls = tail ? tail[1] : red4[0];
     if (fitIntercept) {
-      const double bb = b[0], bn = sB * bb + negEtaB * red4[1];
+      const double bb = b[0], bn = sB * bb + negEtaB * gb;
       viol += fabs(bn - bb);
       b[0] = bn;
     }
-    scal[0] += red4[0];
+    scal[0] += ls;
+    if (tail) tail[0] = tail[1] = 0.0;
   }
   viol = block_sum(viol, red);
   if (threadIdx.x == 0) {
@@ -117,10 +122,13 @@ struct MbModel {
 
 template <class LaunchGrad>
 int sgd_mb_epoch(nimfm_ctx *ctx, const MbModel &M, const nimfm_dataset *X, const nimfm_sgd_cfg *cfg, int64_t B,
-                 int64_t *it, const int64_t *perm, int64_t nRows, double *viol, double *lossSum, LaunchGrad launch) {
+                 int64_t localBatch, int64_t *it, const int64_t *perm, int64_t nRows, double *viol, double *lossSum,
+                 LaunchGrad launch) {
   REQUIRE(cfg && it, "NULL argument");
   REQUIRE(B >= 1, "miniBatchSize < 1");
-  REQUIRE(ctx->nranks == 1, "minibatch SGD runs on one rank");
+  const int R = ctx->nranks;
+  if (localBatch <= 0) localBatch = B;
+  REQUIRE(R == 1 ? localBatch == B : localBatch * R == B, "miniBatchSize must be localBatch x ranks (even shards)");
   REQUIRE(nRows >= 0 && (perm != nullptr || nRows <= X->n), "bad nRows");
   int rc;
   const int32_t *idxDev = nullptr;
@@ -138,13 +146,19 @@ int sgd_mb_epoch(nimfm_ctx *ctx, const MbModel &M, const nimfm_dataset *X, const
   CK(cudaMemsetAsync(ctx->scalars, 0, 8, ctx->stream));          // [0]: loss sum of the epoch
   CK(cudaMemsetAsync(ctx->scalars + 20, 0, 4 * 8, ctx->stream)); // [20]: viol of the epoch
   const int gridP = ew_grid(ctx, M.nP), gridF = ew_grid(ctx, M.dd);
-  for (int64_t q0 = 0; q0 < nRows; q0 += B) {
-    const int64_t Bm = std::min(B, nRows - q0);
-    const int cgrid = (int)std::max<int64_t>(1, std::min<int64_t>((Bm * 32 + 255) / 256, (int64_t)ctx->numSMs * 16));
-    adagrad_count_kernel<<<cgrid, 256, 0, ctx->stream>>>(X->indices, X->indptr, X->n, q0, Bm, idxDev ? idxDev + q0 : nullptr,
+  for (int64_t q0 = 0; q0 < nRows; q0 += localBatch) {
+    const int64_t Bl = std::min(localBatch, nRows - q0), Bm = Bl * R;   // rows of this rank / of the whole minibatch
+    const int cgrid = (int)std::max<int64_t>(1, std::min<int64_t>((Bl * 32 + 255) / 256, (int64_t)ctx->numSMs * 16));
+    adagrad_count_kernel<<<cgrid, 256, 0, ctx->stream>>>(X->indices, X->indptr, X->n, q0, Bl, idxDev ? idxDev + q0 : nullptr,
                                                         M.d, M.nAug, cnt, X->hotSlot, X->hotList, X->nHot);
     LAUNCHED(ctx);
-    if ((rc = launch(q0, Bm, idxDev ? idxDev + q0 : nullptr))) return rc;     // G += sum_i dL_i dA_i; red4 at scalars+8
+    if ((rc = launch(q0, Bl, idxDev ? idxDev + q0 : nullptr))) return rc;     // G += sum_i dL_i dA_i; red4 at scalars+8
+    if (R > 1) {
+      add_tail_kernel<<<1, 1, 0, ctx->stream>>>(M.grad + nG - 2, ctx->scalars + 8);
+      LAUNCHED(ctx);
+      if ((rc = nimfm_allreduce_sum(ctx, cnt, M.dd))) return rc;
+      if ((rc = nimfm_allreduce_sum(ctx, M.grad, nG))) return rc;
+    }
     const double etaP = nimfm_get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->beta, *it);
     const double etaW = nimfm_get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->alpha, *it);
     const double etaB = nimfm_get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->alpha0, *it);
@@ -154,8 +168,8 @@ int sgd_mb_epoch(nimfm_ctx *ctx, const MbModel &M, const nimfm_dataset *X, const
     sgd_mb_P_kernel<<<gridP, 256, 0, ctx->stream>>>(M.P, M.grad, M.SB8, M.nP, cnt, sP, -etaP, ctx->partials);
     LAUNCHED(ctx);
     sgd_mb_feat_kernel<<<gridF, 256, 0, ctx->stream>>>(M.w, M.grad + M.nP, M.d, cnt, M.dd, sW, -etaW, M.fitLinear, M.b,
-                                                      ctx->scalars + 8, sB, -etaB, M.fitIntercept, ctx->scalars,
-                                                      ctx->partials + (size_t)gridP * 4);
+                                                      ctx->scalars + 8, R > 1 ? M.grad + nG - 2 : nullptr, sB, -etaB,
+                                                      M.fitIntercept, ctx->scalars, ctx->partials + (size_t)gridP * 4);
     LAUNCHED(ctx);
     reduce_partials_kernel<<<1, 256, 0, ctx->stream>>>(ctx->partials, gridP + gridF, ctx->scalars + 20, 1);
     LAUNCHED(ctx);
@@ -175,8 +189,8 @@ int sgd_mb_epoch(nimfm_ctx *ctx, const MbModel &M, const nimfm_dataset *X, const
 extern "C" {
 
 int32_t nimfm_fm_sgd_minibatch_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, const nimfm_sgd_cfg *cfg,
-                                     int64_t miniBatchSize, int64_t *it, const int64_t *perm, int64_t nRows,
-                                     double *viol, double *lossSum) {
+                                     int64_t miniBatchSize, int64_t localBatch, int64_t *it, const int64_t *perm,
+                                     int64_t nRows, double *viol, double *lossSum) {
   if (!ctx) return NIMFM_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
   REQUIRE(fm && X, "NULL handle");
@@ -200,15 +214,15 @@ int32_t nimfm_fm_sgd_minibatch_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_d
   MbModel M{fm->P, fm->grad, fm->w, fm->b, fm->nP(), (int64_t)fm->nOrders * fm->k, fm->d, fm->dd(), fm->nAug,
             fm->fitLinear, fm->fitIntercept, &fm->sgdCnt};
   if (fm->nOrders == 0) M.SB8 = 1;
-  return sgd_mb_epoch(ctx, M, X, cfg, miniBatchSize, it, perm, nRows, viol, lossSum,
+  return sgd_mb_epoch(ctx, M, X, cfg, miniBatchSize, localBatch, it, perm, nRows, viol, lossSum,
                       [&](int64_t q0, int64_t Bm, const int32_t *idx) {
                         return nimfm_fm_launch_grad_rows(ctx, fm, X, cfg->loss, cfg->huberThreshold, q0, Bm, idx, 1.0);
                       });
 }
 
 int32_t nimfm_ffm_sgd_minibatch_epoch(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_dataset *X, const nimfm_sgd_cfg *cfg,
-                                      int64_t miniBatchSize, int64_t *it, const int64_t *perm, int64_t nRows,
-                                      double *viol, double *lossSum) {
+                                      int64_t miniBatchSize, int64_t localBatch, int64_t *it, const int64_t *perm,
+                                      int64_t nRows, double *viol, double *lossSum) {
   if (!ctx) return NIMFM_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
   REQUIRE(m && X, "NULL handle");
@@ -217,7 +231,7 @@ int32_t nimfm_ffm_sgd_minibatch_epoch(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_
   REQUIRE(X->y != nullptr, "dataset has no targets (nimfm_dataset_set_targets)");
   MbModel M{m->P, m->grad, m->w, m->b, m->nP(), m->nFields * m->k, m->d, m->d, 0, m->fitLinear, m->fitIntercept,
             &m->sgdCnt};
-  return sgd_mb_epoch(ctx, M, X, cfg, miniBatchSize, it, perm, nRows, viol, lossSum,
+  return sgd_mb_epoch(ctx, M, X, cfg, miniBatchSize, localBatch, it, perm, nRows, viol, lossSum,
                       [&](int64_t q0, int64_t Bm, const int32_t *idx) {
                         return nimfm_ffm_launch_grad_rows(ctx, m, X, cfg->loss, cfg->huberThreshold, q0, Bm, idx, 1.0);
                       });

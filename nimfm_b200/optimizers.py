@@ -248,14 +248,21 @@ class SGD(_Base):
         cfg = _lib.SgdCfg(self.loss.kind, self.loss.threshold, self.eta0, self.alpha0, self.alpha, self.beta,
                           _lib.SCHED[self.scheduling], self.power)
         mbs = self.miniBatchSize
+        world = 1
         if maxThreads is not None and mbs == 1:
             mbs = 4096 if maxThreads < 0 else max(1, int(maxThreads))
         if mbs > 1:
             if X.windowed:
                 raise ValueError("minibatch SGD needs a resident dataset")
             mb_epoch = lib.nimfm_ffm_sgd_minibatch_epoch if is_ffm else lib.nimfm_fm_sgd_minibatch_epoch
+            # data parallel (distributed.init_comm): X is this rank's shard, mbs the GLOBAL minibatch
+            world = _dist.world()
+            if mbs % world:
+                raise ValueError("miniBatchSize must be a multiple of the number of ranks")
+            local = mbs // world
             begin = end = lambda *_: 0          # parameters stay canonical: no scaling caches to set up / fold in
-            epoch = lambda c_, h_, x_, cfg_, it_, idx_, n_, v_, l_: mb_epoch(c_, h_, x_, cfg_, mbs, it_, idx_, n_, v_, l_)
+            epoch = lambda c_, h_, x_, cfg_, it_, idx_, n_, v_, l_: mb_epoch(c_, h_, x_, cfg_, mbs, local, it_, idx_, n_,
+                                                                            v_, l_)
         if not fm.warmStart:
             self.init()
         rng = self._rng(fm)
@@ -280,7 +287,7 @@ class SGD(_Base):
                                      C.byref(viol), C.byref(lossSum)))
                 self.epoch_seconds.append(time.perf_counter() - t0)
                 self.it = it.value
-                runningLoss = lossSum.value / n
+                runningLoss = lossSum.value / (n * world)      # minibatch form: the loss sum is all-reduced
                 self.history.append((viol.value, runningLoss))
                 if callback is not None:
                     # finalize + transpose back before the user sees the model (sgd.nim:310-316)

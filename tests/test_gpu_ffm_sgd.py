@@ -397,14 +397,14 @@ def test_fm_sgd_minibatch_of_one_and_max_threads(oracle):
         it = C.c_int64(1)
         for ep in range(2):
             viol, ls = C.c_double(), C.c_double()
-            _lib.check(lib.nimfm_fm_sgd_minibatch_epoch(ctx, h, ds.handle(), C.byref(cfg), 1, C.byref(it), None, n,
+            _lib.check(lib.nimfm_fm_sgd_minibatch_epoch(ctx, h, ds.handle(), C.byref(cfg), 1, 0, C.byref(it), None, n,
                                                         C.byref(viol), C.byref(ls)))
             assert abs(viol.value - seq["viol"][ep]) <= 1e-8 * seq["viol"][ep]
             assert abs(ls.value / n - seq["loss"][ep]) <= OBJ_TOL * abs(seq["loss"][ep])
         fm._from_device(h)
         assert it.value == seq["it"] and max_rel(fm.P, seq["P"]) <= 1e-9 and max_rel(fm.w, seq["w"]) <= 1e-9
         with pytest.raises(ValueError, match="miniBatchSize"):
-            _lib.check(lib.nimfm_fm_sgd_minibatch_epoch(ctx, h, ds.handle(), C.byref(cfg), 0, C.byref(it), None, n, None, None))
+            _lib.check(lib.nimfm_fm_sgd_minibatch_epoch(ctx, h, ds.handle(), C.byref(cfg), 0, 0, C.byref(it), None, n, None, None))
     finally:
         lib.nimfm_fm_free(ctx, h)
     ref = oracle.sgd_minibatch_fit(csr, y, P, w, 0.0, 2, "squared", B=7, max_iter=2, it=1, **kw)

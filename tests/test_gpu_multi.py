@@ -85,6 +85,17 @@ def _worker(rank, world, port, out_dir):
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     assert torch.equal(t, tmax)                       # bit-identical replicas
 
+    # 3b. SGD, synchronous minibatch (global 16; the device analogue of Hogwild fit(..., maxThreads)): touch
+    # counts and gradients all-reduced, identical step on every rank == the restated rule on the interleaved order
+    kws = dict(eta0=0.02, alpha0=1e-4, alpha=1e-2, beta=2e-2)
+    r3b = orc.sgd_minibatch_fit(perm_csr, y[order], P, w, 0.05, degree, "logistic", B=mb, max_iter=2, it=1, **kws)
+    fm = fm_new()
+    opt = nf.newSGD(maxIter=2, loss=nf.Logistic(), miniBatchSize=mb, verbose=0, tol=0.0, shuffle=False, **kws)
+    opt.fit(ds, y[b:e], fm)
+    assert max_rel(fm.P, r3b["P"]) <= 1e-9 and max_rel(fm.w, r3b["w"]) <= 1e-9 and opt.it == r3b["it"]
+    np.testing.assert_allclose([h_[0] for h_ in opt.history], r3b["viol"], rtol=1e-8)
+    np.testing.assert_allclose([h_[1] for h_ in opt.history], r3b["loss"], rtol=1e-8)
+
     # 4. FFM predict+grad with the gradient all-reduce == full-batch oracle gradient
     Xf, fcsr, _ = make_field_csr(n, 12, 4, 9)
     Pf = np.random.default_rng(3).standard_normal((4, 12, 4)) * 0.1
