@@ -272,6 +272,49 @@ def sgd_slow_fit(X, y, P, w, intercept, degree, fit_linear, fit_intercept, loss,
     return P, w, intercept
 
 
+def sgd_minibatch_slow_fit(X, y, P, w, intercept, degree, fit_linear, fit_intercept, loss, B, max_iter, eta0,
+                           alpha0, alpha, beta, power=1.0):
+    """The synchronous-minibatch generalisation of SGDSlow.fit (sgd_slow.nim:38-91: dense updates, the L2 shrink
+    applied to every parameter at every step): the B samples of a minibatch are evaluated at the same
+    parameters, then their B dense updates are applied at once with the step sizes of the minibatch's first
+    iteration -- theta <- (1 - eta reg)^B theta - eta sum_i grad_i.  B = 1 is sgd_slow_fit.  Independent of
+    oracle.sgd_minibatch_fit (which works on touched / untouched feature sets) and of the device code."""
+    n, d = X.shape
+    P = P.copy()
+    w = w.copy()
+    it = 1
+
+    def eta(reg):
+        return eta0 / (1.0 + eta0 * reg * it) ** power
+
+    def spow(base, m):
+        s = 1.0
+        for _ in range(m):
+            s *= base
+        return s
+
+    for _ in range(max_iter):
+        for q0 in range(0, n, B):
+            rows = range(q0, min(n, q0 + B))
+            m = len(rows)
+            y_pred = fm_decision_function(X[q0:q0 + m], P, w, intercept, degree)
+            grad = np.zeros_like(P)
+            gw, gb = np.zeros(d), 0.0
+            for t, i in enumerate(rows):
+                dL = dloss_val(loss, y[i], y_pred[t])
+                fm_grad(X, i, P, degree, dL, grad)
+                gw += dL * X[i]
+                gb += dL
+            eP, eW, eB = eta(beta), eta(alpha), eta(alpha0)
+            P = spow(1.0 - eP * beta, m) * P - eP * grad
+            if fit_linear:
+                w = spow(1.0 - eW * alpha, m) * w - eW * gw
+            if fit_intercept:
+                intercept = spow(1.0 - eB * alpha0, m) * intercept - eB * gb
+            it += m
+    return P, w, intercept
+
+
 # ---------------------------------------------------------------- proximal operators (definitions)
 def prox_squaredl12_sorted(p, lam):
     """argmin_q 0.5*||q - p||^2 + lam * ||q||_1^2 in closed form: with a = sort(|p|, descending) and

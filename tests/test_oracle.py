@@ -360,3 +360,27 @@ def test_minibatch_sgd_restatement_ffm_with_one_sample(oracle):
     np.testing.assert_allclose(got["w"], ref["w"], rtol=1e-10, atol=1e-14)
     np.testing.assert_allclose(got["viol"], ref["viol"], rtol=1e-9)
     np.testing.assert_allclose(got["loss"], ref["loss"], rtol=1e-10)
+
+
+@pytest.mark.parametrize("degree,fit_lower", [(2, "explicit"), (3, "explicit"), (3, "augment")])
+@pytest.mark.parametrize("B", [1, 3, 16])
+def test_minibatch_sgd_restatement_vs_naive_dense_definition(oracle, degree, fit_lower, B):
+    """oracle.sgd_minibatch_fit (touched / untouched feature sets, CSR) against the naive dense generalisation of
+    the reference's SGDSlow (bruteforce.sgd_minibatch_slow_fit: every parameter shrunk at every step); at B = 1
+    the latter is sgd_slow_fit itself (tests/optimizer/sgd_slow.nim:38-91)."""
+    n, d, k = 37, 6, 3
+    X = make_dense(n, d, 33, density=0.5, positive=False)
+    y = np.random.default_rng(8).standard_normal(n)
+    csr = CSR.from_dense(X)
+    P, w, _ = make_fm_params(d, degree, k, fit_lower, True, seed=4, scale=0.1)
+    kw = dict(eta0=0.05, alpha0=1e-3, alpha=1e-2, beta=2e-2)
+    got = oracle.sgd_minibatch_fit(csr, y, P, w, 0.1, degree, "squared", B=B, max_iter=3, it=1, **kw)
+    sP, sw, sb = bf.sgd_minibatch_slow_fit(X, y, P, w, 0.1, degree, True, True, "squared", B, 3, kw["eta0"],
+                                           kw["alpha0"], kw["alpha"], kw["beta"])
+    np.testing.assert_allclose(got["P"], sP, rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(got["w"], sw, rtol=1e-9, atol=1e-13)
+    assert abs(got["intercept"] - sb) <= 1e-12
+    if B == 1:
+        qP, qw, qb = bf.sgd_slow_fit(X, y, P, w, 0.1, degree, True, True, "squared", 3, kw["eta0"], kw["alpha0"],
+                                     kw["alpha"], kw["beta"])
+        np.testing.assert_allclose(sP, qP, rtol=1e-10, atol=1e-14)
