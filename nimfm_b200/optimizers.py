@@ -328,7 +328,8 @@ class AdaGrad(_Base):
         self.g_norm = None
 
     def fit(self, X, y, fm, maxThreads=None, callback=None, perms=None):
-        """adagrad.nim:137-203 / adagrad_ffm.nim:11-66 (maxThreads of adagrad_multi.nim:39 is ignored)."""
+        """adagrad.nim:137-203 / adagrad_ffm.nim:11-66; fit(..., maxThreads=T) (adagrad_multi.nim:39) runs the
+        synchronous minibatch of T samples, see below."""
         is_ffm = isinstance(fm, FieldAwareFactorizationMachine)
         if X.windowed and is_ffm:
             raise TypeError("field stream files are not supported")
