@@ -74,6 +74,10 @@ def solver_cases():
         cdP, cdw, cdb = bf.cd_slow_fit(X, y, P, w, 0.0, degree, True, True, "squared", 2, 1e-6, 1e-3, 1e-3)
         agP, agw, agb = bf.adagrad_slow_fit(X, y, P, w * 0, 0.0, degree, True, True, "squared", 2, 0.1, 1e-6, 1e-3, 1e-3, 1e-10)
         sgP, sgw, sgb = bf.sgd_slow_fit(X, y, P, w, 0.0, degree, True, True, "squared", 2, 0.01, 1e-6, 1e-3, 1e-3)
+        # synchronous minibatches of 5 samples (the device analogue of Hogwild fit(..., maxThreads=5))
+        mbP, mbw, mbb = bf.sgd_minibatch_slow_fit(X, y, P, w, 0.0, degree, True, True, "squared", 5, 2, 0.01, 1e-6,
+                                                  1e-3, 1e-3)
+        out.update({f"{tag}_mbP": mbP, f"{tag}_mbw": mbw, f"{tag}_mbb": mbb})
         out.update({f"{tag}_degree": degree, f"{tag}_fit_lower": fit_lower, f"{tag}_P0": P, f"{tag}_w0": w,
                     f"{tag}_cdP": cdP, f"{tag}_cdw": cdw, f"{tag}_cdb": cdb,
                     f"{tag}_agP": agP, f"{tag}_agw": agw, f"{tag}_agb": agb,
