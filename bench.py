@@ -1,15 +1,27 @@
 #!/usr/bin/env python
-"""bench.py -- the headline measurement: FP64 HOFM degree-3 (rank 32, explicit lower orders)
-predict + gradient over a synthetic Criteo-shaped CSR (39 nnz/row, 1M hashed features), BASELINE.json
-config 4 / SURVEY 8d "C4", in samples/s.
+"""bench.py -- the headline measurement and, as extra keys on the same JSON line, every other BASELINE.json
+config at its BASELINE size (10 M rows per GPU), at every N.
 
   python bench.py --gpus N --steps K --warmup W          (N>1: launched by torch.distributed.run)
   python bench.py --impl reference ...                   (the reference's CPU path, oracle port)
 
-A "step" is one predict+grad pass (zero grads -> fused forward + dloss + gradient scatter ->
-loss/gb reduction [-> NCCL all-reduce of grad P/w when N>1]) over this rank's resident shard of
-`--rows` rows (weak scaling: every rank holds its own 10M-row shard).  One JSON line is printed by
-rank 0.  See DESIGN.md "Measurement" for the byte accounting behind `roofline`.
+Headline (`value`, `roofline`, `e2e`): FP64 HOFM degree-3 (rank 32, explicit lower orders) predict + gradient
+over a synthetic Criteo-shaped CSR (39 nnz/row, 1M hashed features) -- BASELINE.json config 4 / SURVEY 8d "C4" --
+in samples/s.  A "step" is one predict+grad pass (zero grads -> fused forward + dloss + gradient scatter ->
+loss/gb reduction [-> NCCL all-reduce of grad P/w when N>1]) over this rank's resident shard of `--rows` rows
+(weak scaling: every rank holds its own 10M-row shard).
+
+Extra keys (each measured in the same process, device time on the library's stream, MAX over ranks):
+  parity_check   N>1 only, BEFORE any timing: the sharded MBPSGD / AdaGrad / minibatch-SGD / FFM paths on small
+                 uneven shards against the CPU oracle (tests/sharded_parity.py); a failure exits non-zero
+  c4_decision_function, c4_adagrad   the other two C4 paths (batched prediction; AdaGrad synchronous minibatch)
+  c3_mbpsgd      FM degree 2 rank 16, MBPSGD logistic, epochs at three minibatch sizes
+  c5_ffm         FFM rank 8, 39 fields: forward / predict+grad kernels, the all-reduced step, an AdaGrad epoch
+  cd_epoch_s     C1 / C2 CD epochs on rank 0 (CD does not shard)
+  uniform        N=1: the headline kernel on uniform-random columns (no cache help: the DRAM-bound case)
+  e2e.pageable   the end-to-end call fed from PAGEABLE caller arrays (what a Nim seq is)
+  cpu_baseline   N=1: the oracle port timed on the host cores, per config
+See DESIGN.md "Measurement" for the byte accounting behind every `roofline`.
 """
 import argparse
 import ctypes as C
@@ -33,6 +45,14 @@ DEGREE, K, N_ORDERS = 3, 32, 2
 # scattered parameter element once, no cache credit)
 B_FWD = Z * (8 + 4 + 8 + 8 * K * N_ORDERS) + 8 + 8
 B_GRAD = B_FWD + 8 + Z * (8 * K * N_ORDERS + 8)
+B_ADA = Z * (8 + 4 + 40 + 40 * K * N_ORDERS) + 24
+K3 = 16           # C3: FM degree 2 rank 16, one order
+B3_FWD = Z * (8 + 4 + 8 + 8 * K3) + 16
+B3_GRAD = B3_FWD + 8 + Z * (8 * K3 + 8)
+N_FIELDS, K5 = 39, 8
+B5_FWD = N_FIELDS * (8 + 4 + 4 + 8) + N_FIELDS * (N_FIELDS - 1) * 8 * K5 + 16
+B5_GRAD = B5_FWD + 8 + N_FIELDS * (N_FIELDS - 1) * 8 * K5 + N_FIELDS * 8
+B5_ADA = N_FIELDS * N_FIELDS * K5 * 40      # reference semantics: all fields x row features x k
 
 
 def gen_criteo_rows(n, seed, d=D_FEATURES, dist="criteo"):
@@ -70,6 +90,37 @@ def gen_criteo_rows(n, seed, d=D_FEATURES, dist="criteo"):
     return data.reshape(-1), indices.reshape(-1), indptr, y
 
 
+def gen_ffm_rows(n, seed, n_fields=N_FIELDS, d=D_FEATURES):
+    """libffm-shaped field CSR: one feature per field, field f owns its own contiguous id range with a
+    Zipf(1.05)-like rank distribution; two thirds of the values are 1.0, the rest U(0,1); y = +-1."""
+    rng = np.random.default_rng(seed)
+    R = d // n_fields
+    s = 1.05
+    idx = np.empty((n, n_fields), dtype=np.int64)
+    data = np.empty((n, n_fields), dtype=np.float64)
+    step = 1 << 20
+    for a in range(0, n, step):
+        b = min(n, a + step)
+        u = rng.random((b - a, n_fields))
+        rank = np.floor(((R ** (1.0 - s) - 1.0) * u + 1.0) ** (1.0 / (1.0 - s))).astype(np.int64) - 1
+        np.clip(rank, 0, R - 1, out=rank)
+        idx[a:b] = np.arange(n_fields)[None, :] * R + rank
+        v = rng.random((b - a, n_fields))
+        data[a:b] = np.where(rng.random((b - a, n_fields)) < 0.66, 1.0, v)
+    fields = np.tile(np.arange(n_fields, dtype=np.int64), n)
+    y = np.where(rng.random(n) < 0.5, -1.0, 1.0)
+    return data.reshape(-1), idx.reshape(-1), np.arange(n + 1, dtype=np.int64) * n_fields, fields, y
+
+
+def gen_ml100k(n=100_000, n_users=943, n_items=1682, seed=5):
+    rng = np.random.default_rng(seed)
+    u = rng.integers(0, n_users, n)
+    v = rng.integers(0, n_items, n) + n_users
+    idx = np.stack([u, v], axis=1).astype(np.int64)
+    y = rng.integers(1, 6, n).astype(np.float64)
+    return np.ones(2 * n), idx.reshape(-1), np.arange(n + 1, dtype=np.int64) * 2, y, n_users + n_items
+
+
 def model_params(seed, d=D_FEATURES):
     rng = np.random.default_rng(seed)
     P = rng.standard_normal((N_ORDERS, K, d)) * 0.01      # newFactorizationMachine scale=0.01
@@ -87,15 +138,16 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, or None"""
+def ncu_profile():
+    """per-row counters of the dominant kernels from the committed `ncu --set full` captures (profiles/traffic.json:
+    DRAM / L2 bytes per row and the capture each comes from), or {}"""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("fm_rows_grad_dram_bytes_per_row")
+            return json.load(open(p))
         except Exception:
-            return None
-    return None
+            return {}
+    return {}
 
 
 class ClockSampler:
@@ -147,6 +199,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ====================================================================== CPU legs (oracle port, timed only)
 def cpu_port_rate(orc, rows, seed, min_seconds, threads_note=True):
     """Time the oracle port of updateGradient (minibatch_psgd.nim:67-88 + sgd.nim:191-202), 1 thread,
     on `rows` rows of the same workload; returns (samples/s, rows used, seconds)."""
@@ -210,6 +263,46 @@ def hogwild_threads():
     return min(2 * (os.cpu_count() or 1), 256)
 
 
+def cpu_config_baselines(orc, budget_s=4.0):
+    """The reference's own solvers for the other configs (oracle port, release flags), each on a bounded sample of
+    the same synthetic workload: C1/C2 CD and C3 MBPSGD single-threaded (as the reference runs them), C5 FFM
+    AdaGrad as Hogwild on 2 x cores threads (sgd_multi.nim:13-18)."""
+    from oracle.oracle import CSR
+    out = {}
+    # C1 / C2: CD epochs (cd.nim:110-194), 1 thread
+    data, idx, ptr, y, d = gen_ml100k()
+    n = len(y)
+    csc = orc.csr_to_csc(CSR(data, idx, ptr, n, d))
+    for tag, degree in (("c1_cd_epoch_s", 2), ("c2_cd_epoch_s", 3)):
+        P = np.random.default_rng(1).standard_normal((degree - 1, 30, d)) * 0.01
+        t0 = time.perf_counter()
+        orc.cd_fit(csc, y, P, np.zeros(d), 0.0, degree, "squared", max_iter=2, alpha0=1e-10, alpha=1e-10, beta=1e-3)
+        out[tag] = (time.perf_counter() - t0) / 2
+    # C3: one MBPSGD epoch (minibatch_psgd.nim:91-124) at the reference-default minibatch, 1 thread
+    rows = 200_000
+    data, idx, ptr, y = gen_criteo_rows(rows, 2000)
+    csr = CSR(data, idx, ptr, rows, D_FEATURES)
+    P = np.random.default_rng(2).standard_normal((1, K3, D_FEATURES)) * 0.01
+    t0 = time.perf_counter()
+    orc.mbpsgd_fit(csr, y, P, np.zeros(D_FEATURES), 0.0, 2, "logistic", max_iter=1, gamma=0.0, reg="identity", it=1)
+    dt = time.perf_counter() - t0
+    out["c3_mbpsgd_samples_per_s"] = rows / dt
+    out["c3_sample"] = (f"{rows} rows, one epoch at the reference-default minibatch ({D_FEATURES * rows // (rows * Z)} rows: "
+                        "the dense passes over P dominate, as in the reference)")
+    # C5: Hogwild FFM AdaGrad (adagrad_ffm_multi.nim:16-104)
+    rows = 20_000
+    data, idx, ptr, fields, y = gen_ffm_rows(rows, 4000)
+    csr = CSR(data, idx, ptr, rows, D_FEATURES, fields=fields, n_fields=N_FIELDS)
+    Pf = np.ascontiguousarray(np.random.default_rng(3).standard_normal((N_FIELDS, D_FEATURES, K5)) * 0.01)
+    T = hogwild_threads()
+    t0 = time.perf_counter()
+    orc.hogwild_adagrad_epoch(csr, y, Pf, np.zeros(D_FEATURES), 0.0, 2, T, is_ffm=True, loss_kind="logistic", n_rows=rows)
+    out["c5_hogwild_adagrad_samples_per_s"] = rows / (time.perf_counter() - t0)
+    out["c5_threads"] = T
+    out["kind"] = "port (oracle restatement; Nim toolchain unavailable)"
+    return out
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path.  The Nim toolchain is not
     in this image, so this is the oracle PORT of MBPSGD.updateGradient, which the reference runs on ONE
@@ -238,6 +331,8 @@ def run_reference(args, rank, world):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_row * per_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, world, per_step),
+        "value_is": ("hogwild_adagrad (predict+grad AND the update, all host threads)" if hog >= single
+                     else "single_thread_update_gradient (the same op as the GPU arm)"),
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": T if hog >= single else 1, "kind": "port",
                          "sample": f"the faster of (a) {per_step} rows/step through the oracle port of "
                                    "minibatch_psgd.updateGradient on 1 thread (the reference's MBPSGD is "
@@ -260,6 +355,413 @@ def workload_config(args, world, rows_per_step):
             "l2": "inputs larger than L2 (no flush needed)"}
 
 
+# ====================================================================== the GPU arm
+class Bench:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        import nimfm_b200 as nf
+        from nimfm_b200 import _lib, distributed as nd
+        self.args, self.torch, self.dist, self.nf, self._lib, self.nd = args, torch, dist, nf, _lib, nd
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        self.lib = _lib.load()
+        self.ctx = _lib.ctx(self.local_rank)
+        nd.init_comm(self.rank, self.world)   # library-owned NCCL communicator (the id travels over torch.distributed)
+        self.peak, self.peak_src = measured_peak()
+        self.skip = set(x for x in args.skip.split(",") if x)
+
+    # ---- plumbing
+    def on(self, tag):
+        return tag not in self.skip
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def maxr(self, v):
+        t = self.torch.tensor([float(v)], device="cuda", dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, reps=1):
+        """device time (ms) of `reps` calls of fn on the library's stream (CUDA events), MAX over ranks"""
+        ms = C.c_float()
+        self.barrier()
+        self._lib.check(self.lib.nimfm_timer_start(self.ctx))
+        for _ in range(reps):
+            fn()
+        self._lib.check(self.lib.nimfm_timer_stop(self.ctx, C.byref(ms)))
+        return self.maxr(ms.value) / reps
+
+    def frac(self, bytes_per_row, rows_per_s_per_gpu):
+        return bytes_per_row * rows_per_s_per_gpu / 1e9 / self.peak
+
+    # ---- parity of the sharded paths, before anything is timed (N > 1)
+    def parity_check(self):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from oracle import oracle as orc
+        if self.rank == 0:
+            orc.build()
+        self.barrier()
+        import sharded_parity
+        try:
+            res = sharded_parity.run_checks(self.rank, self.world)
+        except Exception as exc:   # a crash on one rank must not leave the others in a collective
+            res = {"ok": False, "max_rel": float("inf"), "ranks": self.world, "failed": [repr(exc)], "cases": {}}
+        ok = self.torch.tensor([1.0 if res["ok"] else 0.0, -res["max_rel"] if np.isfinite(res["max_rel"]) else -1e300],
+                               device="cuda", dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN)
+        res["ok"] = bool(ok[0].item() == 1.0)
+        res["max_rel"] = float(-ok[1].item())
+        res["what"] = ("tests/sharded_parity.py: decisionFunction, MBPSGD (L1 / L21: reduce-scatter + sharded step + "
+                       "all-gather; SquaredL12: all-reduce), AdaGrad, minibatch SGD, FFM grad + AdaGrad on uneven "
+                       "shards vs the CPU oracle; ok = every rank passed, max_rel = worst over ranks")
+        return res
+
+    # ---- C4: the headline + e2e + the other C4 paths
+    def run_c4(self, line):
+        args, lib, ctx, _lib, nf, world = self.args, self.lib, self.ctx, self._lib, self.nf, self.world
+        n = args.rows
+        t_gen = time.perf_counter()
+        data, indices, indptr, y = gen_criteo_rows(n, 1000 + self.rank, dist=args.dist)
+        ds = nf.newCSRDataset(data, indices, indptr, n, D_FEATURES)
+        ds.set_targets(y)
+        ds.handle()
+        P, w, b = model_params(7)
+        fm = nf.newFactorizationMachine(nf.classification, degree=DEGREE, nComponents=K, fitLower=nf.explicit)
+        fm.P, fm.w, fm.intercept, fm.isInitialized = P, w, b, True
+        h = fm._to_device(D_FEATURES)
+        t_gen = time.perf_counter() - t_gen
+        loss_kind = nf.Logistic().kind
+        mb_global = n * world
+
+        def step():
+            ls = C.c_double()
+            _lib.check(lib.nimfm_fm_loss_grad(ctx, h, ds.handle(), loss_kind, 1.0, 0, n, None, mb_global, 1,
+                                              int(world > 1), C.byref(ls)))
+            return ls.value
+
+        for _ in range(args.warmup):
+            step()
+        sampler = ClockSampler(self.local_rank)
+        self.barrier()
+        sampler.start()
+        l0 = _lib.launch_count()
+        _lib.check(lib.nimfm_timer_start(ctx))
+        for _ in range(args.steps):
+            loss_sum = step()
+        ms = C.c_float()
+        _lib.check(lib.nimfm_timer_stop(ctx, C.byref(ms)))
+        launches = _lib.launch_count() - l0
+        self.barrier()
+        clocks = sampler.stop()
+        ms_per_step = self.maxr(ms.value) / args.steps
+        value = n * world / (ms_per_step / 1e3)
+
+        # ---- dominant kernel alone (CUDA events on the launching stream inside the library)
+        kms, fms = C.c_float(), C.c_float()
+        _lib.check(lib.nimfm_fm_time_loss_grad(ctx, h, ds.handle(), loss_kind, n, mb_global, max(args.steps, 3), 1, C.byref(kms)))
+        _lib.check(lib.nimfm_fm_time_loss_grad(ctx, h, ds.handle(), loss_kind, n, mb_global, max(args.steps, 3), 0, C.byref(fms)))
+        achieved = B_GRAD * n / (kms.value / 1e3) / 1e9
+        prof = ncu_profile()
+        dram_row = prof.get("fm_rows_grad_dram_bytes_per_row")
+        l2_row = prof.get("fm_rows_grad_l2_bytes_per_row")
+        # NOTE on frac > 1: `achieved` counts ALGORITHMIC bytes (every gathered / scattered parameter element once, no
+        # cache credit, SURVEY 8d).  On the Zipf-shaped workload ~2/3 of those sectors hit L2, so the figure can
+        # exceed the DRAM copy peak; `dram_frac` is the same launch's real DRAM traffic (ncu) over the peak, and the
+        # `uniform` key below is the cache-free case where the two coincide.
+        roofline = {"bound": "hbm", "kernel": "fm_rows_stream_kernel<3,true,MODE_GRAD,32>", "achieved": achieved,
+                    "peak": self.peak, "unit": "GB/s", "frac": achieved / self.peak, "peak_source": self.peak_src,
+                    "traffic": None if dram_row is None else dram_row * n,
+                    "traffic_source": prof.get("fm_rows_grad_source"),
+                    "dram_frac": None if dram_row is None else dram_row * n / (kms.value / 1e3) / 1e9 / self.peak,
+                    "l2_bytes_per_row": l2_row,
+                    "l2_GBs": None if l2_row is None else l2_row * n / (kms.value / 1e3) / 1e9,
+                    "what_bounds_it": prof.get("fm_rows_grad_bound"),
+                    "algorithmic_bytes_per_row": B_GRAD, "kernel_ms": kms.value,
+                    "kernel_share_of_step": kms.value / ms_per_step, "frac_of_nominal_8TBs": achieved / 8000.0,
+                    "forward_only": {"kernel": "fm_rows_stream_kernel<3,true,MODE_PREDICT,32>", "kernel_ms": fms.value,
+                                     "samples_per_s": n / (fms.value / 1e3), "algorithmic_bytes_per_row": B_FWD,
+                                     "achieved": B_FWD * n / (fms.value / 1e3) / 1e9,
+                                     "frac": B_FWD * n / (fms.value / 1e3) / 1e9 / self.peak}}
+        line.update({"value": value, "ms_per_step": ms_per_step, "clocks": clocks, "gpu_launches": int(launches),
+                     "roofline": roofline, "loss_sum": loss_sum, "setup_seconds": t_gen})
+        fwd_ms = self.maxr(fms.value)
+        line["c4_decision_function"] = {"samples_per_s": n * world / (fwd_ms / 1e3), "kernel_ms": fwd_ms, "rows_per_gpu": n,
+                                        "what": "batched decisionFunction kernel over the resident shards (no collective)",
+                                        "frac": self.frac(B_FWD, n / (fwd_ms / 1e3))}
+        if self.on("e2e"):
+            self.run_e2e(line, h, data, indices, indptr, y, n, loss_kind)
+        if self.on("c4_adagrad"):
+            self.run_c4_adagrad(line, h, ds, n, loss_kind)
+        lib.nimfm_fm_free(ctx, h)
+        del fm, P, w
+        if self.on("c3"):
+            self.run_c3(line, ds, n, loss_kind)
+        ds.free()
+
+    def run_e2e(self, line, h, data, indices, indptr, y, n, loss_kind):
+        """end to end through the C ABI with HOST buffers, H2D inside the timed region: caller-pinned arrays,
+        PAGEABLE arrays (numpy == a Nim seq), and pageable arrays page-locked once (nimfm_host_register)"""
+        args, lib, ctx, _lib, world, torch = self.args, self.lib, self.ctx, self._lib, self.world, self.torch
+        ne = min(args.e2e_rows if args.e2e_rows > 0 else (10_000_000 if world == 1 else 2_000_000), n)
+        host = [data[:ne * Z], indices[:ne * Z], indptr[:ne + 1], y[:ne]]
+        nbytes = sum(a.nbytes for a in host)
+
+        def run(ptrs, steps, predict_out=None):
+            def one():
+                if predict_out is not None:
+                    _lib.check(lib.nimfm_fm_decision_function_host(ctx, h, ne, D_FEATURES, ptrs[0], ptrs[1], ptrs[2], 0,
+                                                                   predict_out))
+                    return 0.0
+                ls = C.c_double()
+                _lib.check(lib.nimfm_fm_loss_grad_host(ctx, h, ne, D_FEATURES, ptrs[0], ptrs[1], ptrs[2], ptrs[3], loss_kind,
+                                                       1.0, ne * world, 0, 1, int(world > 1), C.byref(ls)))
+                return ls.value
+            one()
+            self.barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                one()
+            torch.cuda.synchronize()
+            dt = self.maxr(time.perf_counter() - t0)
+            a, b_, t_ = C.c_int64(), C.c_int64(), C.c_int32()
+            _lib.check(lib.nimfm_stream_stats(ctx, C.byref(a), C.byref(b_), C.byref(t_)))
+            return ne * world * steps / dt, a.value, b_.value, t_.value
+
+        # (1) caller-pinned
+        hb = [torch.from_numpy(a).pin_memory() for a in host]
+        hp = [C.c_void_p(t_.data_ptr()) for t_ in hb]
+        v, h2d, d2h, thr = run(hp, args.e2e_steps)
+        pred_host = torch.empty(ne, dtype=torch.float64).pin_memory()
+        vp, ph2d, pd2h, _ = run(hp, args.e2e_steps, C.c_void_p(pred_host.data_ptr()))
+        del hb, hp, pred_host
+        # (2) pageable: the caller's numpy arrays as they are
+        pp = [_lib.ptr(a) for a in host]
+        vg, gh2d, gd2h, gthr = run(pp, args.e2e_steps)
+        pred_pg = np.empty(ne)
+        vgp, _, _, _ = run(pp, args.e2e_steps, _lib.ptr(pred_pg))
+        # (3) pageable arrays page-locked once per dataset by the host layer
+        t0 = time.perf_counter()
+        for a in host:
+            _lib.check(lib.nimfm_host_register(ctx, _lib.ptr(a), a.nbytes))
+        t_reg = time.perf_counter() - t0
+        vr, _, _, _ = run(pp, args.e2e_steps)
+        for a in host:
+            _lib.check(lib.nimfm_host_unregister(ctx, _lib.ptr(a)))
+        line["e2e"] = {
+            "value": v, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "rows_per_step": ne, "host_bytes_per_step": int(nbytes), "host_staging_threads": int(thr),
+            "host_memory": "caller-pinned arrays (the base contract's e2e); `pageable` is what a Nim seq gives",
+            "pageable": {"value": vg, "h2d_bytes_per_step": int(gh2d), "d2h_bytes_per_step": int(gd2h),
+                         "host_staging_threads": int(gthr),
+                         "what": "the same call on PAGEABLE arrays (numpy == a Nim seq): values, ids and targets all go "
+                                 "through the library's host staging threads into pinned slots"},
+            "registered": {"value": vr, "register_seconds_once": t_reg,
+                           "what": "the same pageable arrays after nimfm_host_register (page-locked once per dataset)"},
+            "d2h_note": "the result read back per step is the loss sum (8 B); the gradient stays on the device for the "
+                        "solver step",
+            "note": "nimfm_fm_loss_grad_host: host CSR in the reference dtypes (f64 data, i64 indices/indptr, f64 y) -> "
+                    "ids narrowed to int32 by the host staging threads -> chunked H2D overlapped with the kernel -> loss "
+                    "read back; h2d/d2h bytes are what the library put on the link (nimfm_stream_stats)"}
+        line["e2e_predict"] = {"value": vp, "unit": "samples/s", "h2d_bytes_per_step": int(ph2d), "d2h_bytes_per_step": int(pd2h),
+                               "pageable": {"value": vgp, "what": "pageable arrays in, pageable result array out"},
+                               "what": "nimfm_fm_decision_function_host: the same host CSR -> chunked H2D overlapped "
+                                       "with the forward kernel -> predictions copied back"}
+
+    def run_c4_adagrad(self, line, h, ds, n, loss_kind):
+        lib, ctx, _lib, world = self.lib, self.ctx, self._lib, self.world
+        local = min(self.args.adagrad_mb, n)
+        # eta0 small: the synchronous variant accumulates SUMS over the minibatch (adagrad.nim:119-124 per sample),
+        # so its first dual-averaging step scales like eta0 * sqrt(minibatch)
+        cfg = _lib.AdagradCfg(loss_kind, 1.0, 1e-4, 1e-6, 1e-3, 1e-3, 1e-10, local)
+        _lib.check(lib.nimfm_fm_adagrad_init(ctx, h, 1e-10, 1))
+        it = C.c_int64(1)
+        viol, ls = C.c_double(), C.c_double()
+
+        def epoch():
+            _lib.check(lib.nimfm_fm_adagrad_epoch(ctx, h, ds.handle(), C.byref(cfg), C.byref(it), None, n,
+                                                  C.byref(viol), C.byref(ls)))
+        epoch()                                        # the first epoch has no refresh pass on its first minibatch
+        l0 = _lib.launch_count()
+        ms = min(self.timed(epoch), self.timed(epoch))
+        rate = n * world / (ms / 1e3)
+        line["c4_adagrad"] = {"samples_per_s": rate, "s_per_epoch": ms / 1e3, "rows_per_gpu": n,
+                              "minibatch_rows_per_gpu": local, "global_minibatch": local * world,
+                              "epoch_loss": ls.value / (n * world), "gpu_launches_2_epochs": int(_lib.launch_count() - l0),
+                              "algorithmic_bytes_per_row": B_ADA, "frac": self.frac(B_ADA, rate / world),
+                              "what": "AdaGrad synchronous-minibatch epoch (count -> refresh -> row kernel -> "
+                                      "[all-reduce of the delta block -> apply]), HOFM degree 3 rank 32, logistic"}
+
+    def run_c3(self, line, ds, n, loss_kind):
+        """C3: FM degree 2 rank 16, MBPSGD logistic (gamma = 0), epochs over the same Criteo-shaped shards"""
+        lib, ctx, _lib, nf, world = self.lib, self.ctx, self._lib, self.nf, self.world
+        rng = np.random.default_rng(2)
+        P3 = rng.standard_normal((1, K3, D_FEATURES)) * 0.01
+        w3 = np.zeros(D_FEATURES)
+        fm = nf.newFactorizationMachine(nf.classification, degree=2, nComponents=K3, warmStart=True)
+        fm.P, fm.w, fm.intercept, fm.isInitialized = P3, w3, 0.0, True
+        h = fm._to_device(D_FEATURES)
+        n_glob, nnz_glob = n * world, n * world * Z
+        default_mb = max(D_FEATURES * n_glob // nnz_glob, 1)              # minibatch_psgd.nim:157-160
+        out = {"what": "MBPSGD epoch (K2 per minibatch -> [reduce-scatter] -> step (+prox) -> [all-gather]), FM degree 2 "
+                       "rank 16, logistic, gamma = 0; samples/s over all ranks", "rows_per_gpu": n,
+               "algorithmic_bytes_per_row_sparse": B3_GRAD, "dense_step_bytes_per_minibatch": 4 * 8 * (K3 + 1) * D_FEATURES}
+        variants = [("reference_default", default_mb, 400), ("256Ki_per_gpu", (1 << 18) * world, None),
+                    ("1Mi_per_gpu", (1 << 20) * world, None)]
+        for tag, mb, cap in variants:
+            local = self.nd.local_batch(mb, self.rank, world)
+            inner = max((n_glob - 1) // mb + 1, 1)                         # :161-164
+            capped = cap is not None and inner > cap
+            if capped:
+                inner = cap
+            _lib.check(lib.nimfm_fm_set_params(ctx, h, _lib.ptr(P3), _lib.ptr(w3), 0.0, None))
+            cfg = _lib.MbpsgdCfg(loss_kind, 1.0, 0.1, 1e-6, 1e-3, 1e-4, 0.0, _lib.REG_L1, _lib.SCHED["optimal"], 1.0, mb, inner)
+            it, ii, rl = C.c_int64(1), C.c_int64(0), C.c_double()
+
+            def epoch():
+                _lib.check(lib.nimfm_fm_mbpsgd_epoch(ctx, h, ds.handle(), C.byref(cfg), local, C.byref(it), C.byref(ii),
+                                                     None, C.byref(rl)))
+            epoch()
+            l0 = _lib.launch_count()
+            ms = min(self.timed(epoch), self.timed(epoch))
+            rate = mb * inner / (ms / 1e3)
+            out[tag] = {"global_minibatch": mb, "rows_per_gpu_per_minibatch": local, "inner_iterations": inner,
+                        "inner_capped": capped, "s_per_epoch": ms / 1e3, "samples_per_s": rate,
+                        "us_per_minibatch": ms * 1e3 / inner, "epoch_loss": rl.value,
+                        "gpu_launches_2_epochs": int(_lib.launch_count() - l0),
+                        "frac_sparse": self.frac(B3_GRAD, rate / world)}
+        lib.nimfm_fm_free(ctx, h)
+        line["c3_mbpsgd"] = out
+
+    # ---- C5: FFM
+    def run_c5(self, line):
+        args, lib, ctx, _lib, nf, world = self.args, self.lib, self.ctx, self._lib, self.nf, self.world
+        n = args.ffm_rows
+        t0 = time.perf_counter()
+        data, idx, ptr, fields, y = gen_ffm_rows(n, 6000 + self.rank)
+        ds = nf.newCSRFieldDataset(data, idx, ptr, fields, n, D_FEATURES, N_FIELDS)
+        ds.set_targets(y)
+        ds.handle()
+        del data, idx, fields
+        base = np.random.default_rng(3).standard_normal((D_FEATURES, K5)) * 0.01
+        P = np.empty((N_FIELDS, D_FEATURES, K5))
+        for f in range(N_FIELDS):                       # distinct per field without 312 M normal draws
+            np.multiply(base, 1.0 + 0.01 * f, out=P[f])
+        m = nf.newFieldAwareFactorizationMachine(nf.classification, nComponents=K5, warmStart=True)
+        m.P, m.w, m.intercept, m.isInitialized = P, np.zeros(D_FEATURES), 0.0, True
+        h = m._to_device(ds)
+        setup = time.perf_counter() - t0
+        out = {"what": f"FFM {N_FIELDS} fields rank {K5}, one feature per field, d={D_FEATURES}, logistic; samples/s over "
+                       "all ranks", "rows_per_gpu": n, "setup_seconds": setup}
+        for tag, grad, bts in (("forward", 0, B5_FWD), ("predict_grad", 1, B5_GRAD)):
+            ms = C.c_float()
+            _lib.check(lib.nimfm_ffm_time_loss_grad(ctx, h, ds.handle(), 2, n, n * world, 2, grad, C.byref(ms)))
+            t = self.maxr(ms.value)
+            out[tag] = {"kernel_ms": t, "samples_per_s": n * world / (t / 1e3), "algorithmic_bytes_per_row": bts,
+                        "frac": self.frac(bts, n / (t / 1e3))}
+        ls = C.c_double()
+
+        def step():
+            _lib.check(lib.nimfm_ffm_loss_grad(ctx, h, ds.handle(), 2, 1.0, 0, n, None, n * world, 1, int(world > 1),
+                                               C.byref(ls)))
+        step()
+        ms = self.timed(step, 2)
+        out["step"] = {"ms_per_step": ms, "samples_per_s": n * world / (ms / 1e3),
+                       "what": "zero grads + pair kernel + all-reduce of [gP | gw | gb, loss] (2.5 GB)",
+                       "frac": self.frac(B5_GRAD, n / (ms / 1e3))}
+        local = min(args.adagrad_mb, n)
+        cfg = _lib.AdagradCfg(2, 1.0, 1e-4, 1e-6, 1e-3, 1e-3, 1e-10, local)
+        _lib.check(lib.nimfm_ffm_adagrad_init(ctx, h, 1e-10, 1))
+        it, viol = C.c_int64(1), C.c_double()
+
+        def epoch():
+            _lib.check(lib.nimfm_ffm_adagrad_epoch(ctx, h, ds.handle(), C.byref(cfg), C.byref(it), None, n, C.byref(viol),
+                                                   C.byref(ls)))
+        epoch()
+        ms = self.timed(epoch)
+        rate = n * world / (ms / 1e3)
+        out["adagrad"] = {"samples_per_s": rate, "s_per_epoch": ms / 1e3, "minibatch_rows_per_gpu": local,
+                          "epoch_loss": ls.value / (n * world), "algorithmic_bytes_per_row": B5_ADA,
+                          "frac": self.frac(B5_ADA, rate / world),
+                          "what": "AdaGrad synchronous-minibatch epoch (count -> refresh -> pair kernel -> [all-reduce of "
+                                  "the 5 GB delta block -> apply])"}
+        lib.nimfm_ffm_free(ctx, h)
+        ds.free()
+        line["c5_ffm"] = out
+
+    # ---- C1 / C2: CD on rank 0 (the coordinate loop is sequential: it does not shard)
+    def run_cd(self, line):
+        nf, _lib = self.nf, self._lib
+        if self.rank == 0:
+            data, idx, ptr, y, d = gen_ml100k()
+            n = len(y)
+            order = np.argsort(idx, kind="stable")          # CSC of the 2-nnz-per-row CSR (columns ascending, rows stable)
+            csc_idx = (order // 2).astype(np.int64)
+            csc_ptr = np.concatenate([[0], np.cumsum(np.bincount(idx, minlength=d))]).astype(np.int64)
+            ds = nf.newCSCDataset(np.ones(2 * n), csc_idx, csc_ptr, n, d)
+            out = {"what": f"CD epoch seconds, ML-100K shape n={n} d={d} nnz={2 * n}, rank 30, squared loss (rank 0 only: "
+                           "CD stays single-GPU)"}
+            for tag, degree in (("c1", 2), ("c2", 3)):
+                P = np.random.default_rng(1).standard_normal((degree - 1, 30, d)) * 0.01
+                kw = dict(alpha0=1e-10, alpha=1e-10, beta=1e-3)
+                fm = nf.newFactorizationMachine(nf.regression, degree=degree, nComponents=30, warmStart=True)
+                fm.P, fm.w, fm.intercept, fm.isInitialized = P.copy(), np.zeros(d), 0.0, True
+                nf.newCD(maxIter=1, verbose=0, tol=0.0, **kw).fit(ds, y, fm)       # warm-up (batches, graph capture)
+                fm.P, fm.w, fm.intercept = P.copy(), np.zeros(d), 0.0
+                opt = nf.newCD(maxIter=5, verbose=0, tol=0.0, **kw)
+                l0 = _lib.launch_count()
+                opt.fit(ds, y, fm)
+                ep = float(np.median(opt.epoch_seconds))
+                steps = (degree - 1) * 30 * d + d + 1
+                out[tag] = {"degree": degree, "epoch_s": ep, "coordinate_steps_per_epoch": steps,
+                            "us_per_coordinate_step": ep / steps * 1e6,
+                            "objective_after_5_epochs": opt.history[-1][1] + opt.history[-1][2],
+                            "kernel_launches_per_epoch": (_lib.launch_count() - l0) / 5}
+            ds.free()
+            line["cd_epoch_s"] = out["c2"]["epoch_s"]
+            line["cd"] = out
+        self.barrier()
+
+    # ---- the headline kernel without cache help
+    def run_uniform(self, line):
+        args, lib, ctx, _lib, nf = self.args, self.lib, self.ctx, self._lib, self.nf
+        n = min(args.uniform_rows, args.rows)
+        data, indices, indptr, y = gen_criteo_rows(n, 77, dist="uniform")
+        ds = nf.newCSRDataset(data, indices, indptr, n, D_FEATURES)
+        ds.set_targets(y)
+        P, w, b = model_params(7)
+        fm = nf.newFactorizationMachine(nf.classification, degree=DEGREE, nComponents=K, fitLower=nf.explicit)
+        fm.P, fm.w, fm.intercept, fm.isInitialized = P, w, b, True
+        h = fm._to_device(D_FEATURES)
+        kms, fms = C.c_float(), C.c_float()
+        _lib.check(lib.nimfm_fm_time_loss_grad(ctx, h, ds.handle(), 2, n, n, 3, 1, C.byref(kms)))
+        _lib.check(lib.nimfm_fm_time_loss_grad(ctx, h, ds.handle(), 2, n, n, 3, 1, C.byref(kms)))
+        _lib.check(lib.nimfm_fm_time_loss_grad(ctx, h, ds.handle(), 2, n, n, 3, 0, C.byref(fms)))
+        prof = ncu_profile()
+        dram_row = prof.get("fm_rows_grad_uniform_dram_bytes_per_row")
+        g = B_GRAD * n / (kms.value / 1e3) / 1e9
+        line["uniform"] = {"what": "the headline kernels on uniform-random column ids (every slot uniform over its own id "
+                                   "range: no hot features, no L2 reuse) -- the DRAM-bound case", "rows": n,
+                           "grad": {"kernel_ms": kms.value, "samples_per_s": n / (kms.value / 1e3), "achieved": g,
+                                    "frac": g / self.peak, "dram_bytes_per_row": dram_row,
+                                    "dram_frac": None if dram_row is None else dram_row * n / (kms.value / 1e3) / 1e9 / self.peak,
+                                    "traffic_source": prof.get("fm_rows_grad_uniform_source")},
+                           "forward": {"kernel_ms": fms.value, "samples_per_s": n / (fms.value / 1e3),
+                                       "frac": B_FWD * n / (fms.value / 1e3) / 1e9 / self.peak}}
+        lib.nimfm_fm_free(ctx, h)
+        ds.free()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -267,6 +769,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=10_000_000, help="rows per GPU (weak scaling)")
+    ap.add_argument("--ffm-rows", type=int, default=10_000_000, help="FFM rows per GPU")
+    ap.add_argument("--uniform-rows", type=int, default=4_000_000)
+    ap.add_argument("--adagrad-mb", type=int, default=1 << 19, help="AdaGrad rows per GPU per synchronous minibatch")
     ap.add_argument("--e2e-rows", type=int, default=0,
                     help="rows per end-to-end step (host buffers); default: the whole 10 M-row batch of the "
                          "device-resident step on one GPU, 2 M rows per rank under torchrun (pinned host memory "
@@ -275,174 +780,41 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bounded CPU-baseline sample")
     ap.add_argument("--ref-rows", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip", default="", help="comma list of sections to skip: parity,e2e,c4_adagrad,c3,c5,cd,uniform")
     ap.add_argument("--dist", default="criteo", choices=["criteo", "uniform", "zipfall"],
                     help="index distribution; anything but 'criteo' is an experiment, not the reported workload")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
 
-    import torch
-    import torch.distributed as dist
-    import nimfm_b200 as nf
-    from nimfm_b200 import _lib
-
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    lib = _lib.load()
-    ctx = _lib.ctx(local_rank)
-    if world > 1:   # library-owned NCCL communicator; the 128-byte id travels over torch.distributed
-        uid = (C.c_char * 128)()
-        if rank == 0:
-            _lib.check(lib.nimfm_comm_unique_id(uid))
-        box = [bytes(uid)]
-        dist.broadcast_object_list(box, src=0)
-        uid = (C.c_char * 128).from_buffer_copy(box[0])
-        _lib.check(lib.nimfm_comm_init(ctx, rank, world, uid))
-
-    n = args.rows
-    t_gen = time.perf_counter()
-    data, indices, indptr, y = gen_criteo_rows(n, 1000 + rank, dist=args.dist)
-    ds = nf.newCSRDataset(data, indices, indptr, n, D_FEATURES)
-    ds.set_targets(y)
-    P, w, b = model_params(7)
-    fm = nf.newFactorizationMachine(nf.classification, degree=DEGREE, nComponents=K, fitLower=nf.explicit)
-    fm.P, fm.w, fm.intercept, fm.isInitialized = P, w, b, True
-    h = fm._to_device(D_FEATURES)
-    t_gen = time.perf_counter() - t_gen
-    loss_kind = nf.Logistic().kind
-    mb_global = n * world
-
-    def step():
-        ls = C.c_double()
-        _lib.check(lib.nimfm_fm_loss_grad(ctx, h, ds.handle(), loss_kind, 1.0, 0, n, None, mb_global, 1,
-                                          int(world > 1), C.byref(ls)))
-        return ls.value
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step()
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    l0 = _lib.launch_count()
-    _lib.check(lib.nimfm_timer_start(ctx))
-    for _ in range(args.steps):
-        loss_sum = step()
-    ms = C.c_float()
-    _lib.check(lib.nimfm_timer_stop(ctx, C.byref(ms)))
-    launches = _lib.launch_count() - l0
-    barrier()
-    clocks = sampler.stop()
-    t = torch.tensor([ms.value], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_per_step = ms_total / args.steps
-    value = n * world / (ms_per_step / 1e3)
-
-    # ---- dominant kernel alone (CUDA events on the launching stream inside the library)
-    kms = C.c_float()
-    _lib.check(lib.nimfm_fm_time_loss_grad(ctx, h, ds.handle(), loss_kind, n, mb_global, max(args.steps, 3), 1,
-                                           C.byref(kms)))
-    fms = C.c_float()
-    _lib.check(lib.nimfm_fm_time_loss_grad(ctx, h, ds.handle(), loss_kind, n, mb_global, max(args.steps, 3), 0,
-                                           C.byref(fms)))
-    peak, peak_src = measured_peak()
-    achieved = B_GRAD * n / (kms.value / 1e3) / 1e9
-    traffic_row = ncu_traffic()
-    # NOTE on frac > 1: `achieved` counts ALGORITHMIC bytes (every gathered / scattered parameter element
-    # once, no cache credit).  On the Zipf-shaped workload ~2/3 of those sectors hit L2
-    # (ncu: 11.9 KB/row of DRAM traffic vs 41 KB algorithmic), so the figure can exceed the DRAM copy peak.
-    roofline = {"bound": "hbm", "kernel": "fm_rows_stream_kernel<3,true,MODE_GRAD,32>", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": None if traffic_row is None else traffic_row * n,
-                "algorithmic_bytes_per_row": B_GRAD, "kernel_ms": kms.value,
-                "kernel_share_of_step": kms.value / ms_per_step,
-                "frac_of_nominal_8TBs": achieved / 8000.0,
-                "forward_only": {"kernel": "fm_rows_stream_kernel<3,true,MODE_PREDICT,32>", "kernel_ms": fms.value,
-                                 "samples_per_s": n / (fms.value / 1e3), "algorithmic_bytes_per_row": B_FWD,
-                                 "achieved": B_FWD * n / (fms.value / 1e3) / 1e9,
-                                 "frac": B_FWD * n / (fms.value / 1e3) / 1e9 / peak}}
-
-    # ---- end to end through the C ABI with HOST buffers (pinned), H2D inside the timed region
-    ne = min(args.e2e_rows if args.e2e_rows > 0 else (10_000_000 if world == 1 else 2_000_000), n)
-    hb = [torch.from_numpy(a).pin_memory() for a in (data[:ne * Z], indices[:ne * Z], indptr[:ne + 1], y[:ne])]
-    hp = [C.c_void_p(t_.data_ptr()) for t_ in hb]
-    h2d = sum(t_.numel() * t_.element_size() for t_ in hb)
-
-    def e2e_step():
-        ls = C.c_double()
-        _lib.check(lib.nimfm_fm_loss_grad_host(ctx, h, ne, D_FEATURES, hp[0], hp[1], hp[2], hp[3], loss_kind, 1.0,
-                                               ne * world, 0, 1, int(world > 1), C.byref(ls)))
-        return ls.value
-
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        e2e_loss = e2e_step()
-    torch.cuda.synchronize()
-    te = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = ne * world * args.e2e_steps / float(te.item())
-
-    def link_stats():
-        a, b, t_ = C.c_int64(), C.c_int64(), C.c_int32()
-        _lib.check(lib.nimfm_stream_stats(ctx, C.byref(a), C.byref(b), C.byref(t_)))
-        return a.value, b.value, t_.value
-    e2e_h2d, e2e_d2h, e2e_threads = link_stats()
-
-    # end-to-end batched decisionFunction from the same host buffers (predictions read back)
-    pred_host = torch.empty(ne, dtype=torch.float64).pin_memory()
-
-    def e2e_predict():
-        _lib.check(lib.nimfm_fm_decision_function_host(ctx, h, ne, D_FEATURES, hp[0], hp[1], hp[2], 0,
-                                                       C.c_void_p(pred_host.data_ptr())))
-    e2e_predict()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        e2e_predict()
-    torch.cuda.synchronize()
-    tp = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
-    e2e_predict_value = ne * world * args.e2e_steps / float(tp.item())
-    pred_h2d, pred_d2h, _ = link_stats()
-
+    B = Bench(args)
     line = {
-        "metric": "samples/sec FM/HOFM predict+grad", "value": value, "unit": "samples/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "metric": "samples/sec FM/HOFM predict+grad", "value": None, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, world, n),
-        "clocks": clocks, "gpu_launches": int(launches),
-        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(e2e_h2d), "d2h_bytes_per_step": int(e2e_d2h),
-                "rows_per_step": ne, "host_bytes_per_step": int(h2d), "host_staging_threads": int(e2e_threads),
-                "note": "nimfm_fm_loss_grad_host: pinned host CSR (f64 data, i64 indices/indptr, f64 y) -> "
-                "[ids narrowed to int32 by the library's host staging threads when host_staging_threads > 0] -> chunked "
-                "H2D overlapped with the kernel -> loss read back; h2d/d2h bytes are what the library put on the "
-                "link (nimfm_stream_stats), host_bytes_per_step the size of the caller's arrays"},
-        "e2e_predict": {"value": e2e_predict_value, "unit": "samples/s", "what": "nimfm_fm_decision_function_host: the "
-                        "same pinned host CSR -> chunked H2D overlapped with the forward kernel -> predictions copied "
-                        "back", "h2d_bytes_per_step": int(pred_h2d), "d2h_bytes_per_step": int(pred_d2h)},
-        "roofline": roofline,
-        "loss_sum": loss_sum, "setup_seconds": t_gen,
+        "config": workload_config(args, world, args.rows),
     }
     if args.dist != "criteo":
         line["config"]["experiment_dist"] = args.dist
+    if world > 1 and B.on("parity"):
+        line["parity_check"] = B.parity_check()
+        if not line["parity_check"]["ok"]:
+            if rank == 0:
+                print(json.dumps(line), flush=True)
+            B.barrier()
+            sys.exit(3)
+    B.run_c4(line)
+    if B.on("c5"):
+        B.run_c5(line)
+    if B.on("cd"):
+        B.run_cd(line)
+    if world == 1 and B.on("uniform"):
+        B.run_uniform(line)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
         orc.build()
@@ -455,12 +827,17 @@ def main():
                                                             "multithreaded path), racy by design, timed only"},
                                 "sample": f"first {used} rows of the same workload in {dt:.1f} s, oracle port of "
                                           "minibatch_psgd.updateGradient + sgd.predictWithGrad (the reference "
-                                          "runs MBPSGD on one thread)", "host_cores": os.cpu_count()}
+                                          "runs MBPSGD on one thread)", "host_cores": os.cpu_count(),
+                                "configs": cpu_config_baselines(orc)}
+        # the two ratios side by side: the same op on one thread, and the reference's all-threads solver
+        line["vs_cpu"] = {"predict_grad_vs_single_thread_update_gradient": line["value"] / rate,
+                          "e2e_vs_single_thread_update_gradient": line["e2e"]["value"] / rate if "e2e" in line else None,
+                          "c4_adagrad_vs_hogwild_adagrad": (line["c4_adagrad"]["samples_per_s"] / hog
+                                                            if "c4_adagrad" in line else None)}
     if rank == 0:
         print(json.dumps(line), flush=True)
-    lib.nimfm_fm_free(ctx, h)
     if world > 1:
-        dist.destroy_process_group()
+        B.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

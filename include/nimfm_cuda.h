@@ -68,6 +68,11 @@ int64_t nimfm_launch_count(const nimfm_ctx *ctx);
 /* free / total bytes of the context's device (cudaMemGetInfo) */
 int32_t nimfm_mem_info(nimfm_ctx *ctx, int64_t *freeBytes, int64_t *totalBytes);
 int32_t nimfm_stream_stats(const nimfm_ctx *ctx, int64_t *h2dBytes, int64_t *d2hBytes, int32_t *hostThreads);
+/* Page-lock / release a caller-owned host array (cudaHostRegister) for as long as its owner -- the dataset object
+ * holding the seqs of tensor/sparse.nim:4-31 -- lives: the host-fed calls then copy straight out of it at link
+ * rate.  Unregistered (pageable) arrays still work: the host staging team copies them through pinned slots. */
+int32_t nimfm_host_register(nimfm_ctx *ctx, const void *ptr, int64_t bytes);
+int32_t nimfm_host_unregister(nimfm_ctx *ctx, const void *ptr);
 
 /* Multi-GPU (one process per GPU).  The reference has no distributed backend; this is
  * the synchronous data-parallel replacement of its Hogwild threads (sgd_multi.nim:86-95).
@@ -75,6 +80,10 @@ int32_t nimfm_stream_stats(const nimfm_ctx *ctx, int64_t *h2dBytes, int64_t *d2h
 int32_t nimfm_comm_unique_id(void *uid128);
 int32_t nimfm_comm_init(nimfm_ctx *ctx, int32_t rank, int32_t nranks, const void *uid128);
 int32_t nimfm_comm_size(const nimfm_ctx *ctx);
+/* `count` int64 values of every rank, rank-major (all[r*count + i]), on every host: what the host side needs to
+ * agree on before a sharded fit() -- global nSamples / nnz behind MBPSGD's default minibatch
+ * (minibatch_psgd.nim:157-165), shard lengths.  One rank: a copy.  count <= 4096. */
+int32_t nimfm_comm_allgather_i64(nimfm_ctx *ctx, const int64_t *mine, int32_t count, int64_t *all);
 
 /* ---------------------------------------------------------------- datasets
  * newCSRDataset / newCSCDataset / newCSRFieldDataset (dataset.nim:116-153).  indices are narrowed to
@@ -165,8 +174,11 @@ int32_t nimfm_fm_loss_grad(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X,
 /* The same predict+grad step fed from HOST buffers (the end-to-end path): rows [0,nRows) of a host
  * CSR in the reference dtypes (f64 data, i64 indices / indptr, f64 y) are streamed to the device in
  * chunks of chunkRows rows (<=0: library default), the host->device copy of chunk c+1 overlapping
- * the kernel of chunk c on a second stream; indices are narrowed and indptr rebased on the device.
- * Pinned host memory gives full PCIe bandwidth; pageable memory works but is slower. */
+ * the kernel of chunk c on a second stream; ids are narrowed to int32 and indptr rebased by the library's
+ * host staging threads (or on the device when a rank has too few host threads to itself).  Page-locked
+ * arrays (nimfm_host_register, cudaHostAlloc) are read by the copy engine directly; PAGEABLE arrays -- a Nim
+ * seq -- are detected (cudaPointerGetAttributes) and their values / targets go through the same staging
+ * threads into pinned slots, so no copy is left to the driver's single-threaded pageable path. */
 int32_t nimfm_fm_loss_grad_host(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t d, const double *data,
                                 const int64_t *indices, const int64_t *indptr, const double *y,
                                 int32_t loss, double huberThreshold, int64_t miniBatchSize,
@@ -192,8 +204,12 @@ typedef struct {
 /* One epoch() (:91-124).  *it is MBPSGD.it (in/out), *ii the sample cursor (in/out).  sampleIdx is
  * NULL for cyclic order from *ii (shuffle=false) or the miniBatchSize*maxIterInner row ids the
  * host's cursor+shuffle logic (:102-111) yields for this epoch.  With a communicator every rank
- * passes its own shard and the per-minibatch gradient is all-reduced (miniBatchSize is the GLOBAL
- * size used in coef; each rank processes localBatch rows per inner iteration). */
+ * passes its own shard (miniBatchSize is the GLOBAL size used in coef; each rank processes localBatch
+ * rows per inner iteration; the shares may differ but must add up to miniBatchSize, and miniBatchSize,
+ * maxIterInner and *it must agree across ranks -- checked).  Per minibatch the gradient pool is
+ * reduce-scattered, every rank runs Params.step (params.nim:90-98) and the prox on its 1/N slice of
+ * [P | w | b], and the parameters are all-gathered (the column-wise SquaredL12 prox, which sums over all
+ * features, keeps an all-reduce followed by the identical dense step on every rank). */
 int32_t nimfm_fm_mbpsgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X,
                               const nimfm_mbpsgd_cfg *cfg, int64_t localBatch, int64_t *it,
                               int64_t *ii, const int64_t *sampleIdx, double *runningLoss);
@@ -310,7 +326,9 @@ int32_t nimfm_ffm_adagrad_finalize(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_ada
  * No begin / end: the parameters stay canonical between calls.  perm (nullable): sample order.
  * Data parallel like nimfm_fm_mbpsgd_epoch: with a communicator X is this rank's shard, localBatch (<= 0: =
  * miniBatchSize) the rows this rank feeds per minibatch, miniBatchSize = localBatch x ranks the global one;
- * touch counts and gradients are all-reduced, every rank applies the identical step. */
+ * touch counts and gradients are all-reduced, every rank applies the identical step.  Shards and shares may be
+ * uneven: every rank runs max_r ceil(nRows_r / localBatch_r) minibatches (feeding 0 rows once its shard is used
+ * up) and `it` advances by the global row count of each minibatch; the same holds for the AdaGrad epochs. */
 int32_t nimfm_fm_sgd_minibatch_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, const nimfm_sgd_cfg *cfg,
                                      int64_t miniBatchSize, int64_t localBatch, int64_t *it, const int64_t *perm,
                                      int64_t nRows, double *viol, double *lossSum);

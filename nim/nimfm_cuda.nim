@@ -150,6 +150,9 @@ proc nimfm_stream_close(sh: pointer): int32
 proc nimfm_mem_info(ctx: Ctx, freeBytes, totalBytes: ptr int64): int32
 proc nimfm_stream_stats(ctx: Ctx, h2dBytes, d2hBytes: ptr int64, hostThreads: ptr int32): int32
 proc nimfm_comm_size(ctx: Ctx): int32
+proc nimfm_comm_allgather_i64(ctx: Ctx, mine: ptr int64, count: int32, all: ptr int64): int32
+proc nimfm_host_register(ctx: Ctx, p: pointer, bytes: int64): int32      # page-lock a dataset's seqs once
+proc nimfm_host_unregister(ctx: Ctx, p: pointer): int32
 proc nimfm_dataset_info(ds: DeviceDataset, n, d, nnz: ptr int64, kind: ptr int32, nFields, maxRowNnz: ptr int64): int32
 proc nimfm_dataset_download(ctx: Ctx, ds: DeviceDataset, data: ptr cdouble, indices, indptr, fields: ptr int64): int32
 proc nimfm_fm_loss_grad_host(ctx: Ctx, fm: DeviceFM, nRows, d: int64, data: ptr cdouble, indices, indptr: ptr int64,

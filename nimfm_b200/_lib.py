@@ -68,6 +68,8 @@ SYMBOLS = {
     "nimfm_launch_count": (c_i64, [VP]),
     "nimfm_stream_stats": (c_i32, [VP, VP, VP, VP]),
     "nimfm_mem_info": (c_i32, [VP, VP, VP]),
+    "nimfm_host_register": (c_i32, [VP, VP, c_i64]),
+    "nimfm_host_unregister": (c_i32, [VP, VP]),
     "nimfm_stream_open": (c_i32, [VP, C.c_char_p, C.c_char_p, PVP]),
     "nimfm_stream_info": (c_i32, [VP, VP, VP, VP, VP, VP, VP]),
     "nimfm_stream_window_end": (c_i64, [VP, c_i64, c_i64]),
@@ -76,6 +78,7 @@ SYMBOLS = {
     "nimfm_comm_unique_id": (c_i32, [VP]),
     "nimfm_comm_init": (c_i32, [VP, c_i32, c_i32, VP]),
     "nimfm_comm_size": (c_i32, [VP]),
+    "nimfm_comm_allgather_i64": (c_i32, [VP, VP, c_i32, VP]),
     "nimfm_csr_upload": (c_i32, [VP, c_i64, c_i64, VP, VP, VP, VP, c_i64, c_i64, c_i64, PVP]),
     "nimfm_csc_upload": (c_i32, [VP, c_i64, c_i64, VP, VP, VP, PVP]),
     "nimfm_dataset_transpose": (c_i32, [VP, VP, PVP]),

@@ -44,6 +44,10 @@ struct nimfm_ctx {
   // pinned slots of the host staging team (host_stage.h): narrowed ids + rebased indptr
   int32_t *hostIdx[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t *hostPtr[4] = {nullptr, nullptr, nullptr, nullptr};
+  double *hostData[4] = {nullptr, nullptr, nullptr, nullptr};   // pageable callers only: values / targets
+  double *hostY[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t hostCapData = 0, hostCapY = 0;
+  int32_t lastPageable = 0;          // nimfm_stream_stats: the last host-fed call staged pageable values
   cudaEvent_t evSlot[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t hostCapNnz = 0, hostCapRows = 0;
   // pinned pieces of the file -> device copy (loaders.cu, staged_h2d): kPinPieces x kPinPieceBytes
@@ -61,6 +65,8 @@ struct nimfm_ctx {
   // communicator
   ncclComm *comm = nullptr;
   int rank = 0, nranks = 1;
+  struct CommBuf { void *ptr, *win; };
+  std::vector<CommBuf> commBufs;     // ncclMemAlloc'ed / window-registered buffers (nimfm_comm_alloc)
 };
 
 struct nimfm_dataset {
@@ -88,11 +94,16 @@ struct nimfm_fm {
   int fitLinear = 1, fitIntercept = 1;
   int64_t dd() const { return d + nAug; }
   int64_t nP() const { return (int64_t)nOrders * dd() * k; }
-  // device parameters, layout P[j][o][s] ("feature-major": one feature's nOrders*k doubles contiguous)
+  // device parameters, layout P[j][o][s] ("feature-major": one feature's nOrders*k doubles contiguous).
+  // P, w and the scalar block b live in ONE allocation, pool = [P (nP) | w (d) | b (8) | slack], in the same flat
+  // element order as the gradient buffer, so that a multi-rank step can reduce-scatter the gradients, update
+  // its flat slice of the parameters and all-gather the pool in place (fm_api.cu, sharded MBPSGD step).
+  double *pool = nullptr;
+  int64_t poolCap = 0;     // doubles allocated in pool and in grad (>= nP + d + 8, plus slice-alignment slack)
   double *P = nullptr, *w = nullptr, *lams = nullptr;
-  double *b = nullptr;     // device scalar block: [0]=intercept
+  double *b = nullptr;     // device scalar block inside pool: [0]=intercept, [1]=epoch loss of the sharded step
   bool lamsAreOnes = true;
-  // gradient buffer: [gP (nP) | gw (d) | gb, lossSum] contiguous for a single all-reduce
+  // gradient buffer: [gP (nP) | gw (d) | gb, lossSum | slack] contiguous for a single collective
   double *grad = nullptr;
   double *proxState = nullptr;   // SquaredL12 column prox: [tau | prevCnt | done] (prox_kernels.cuh)
   // lazy MBPSGD epoch: per-feature {1/cumP, 1/cumW} at the feature's last update, touched flags
@@ -155,13 +166,39 @@ int nimfm_fail(nimfm_ctx *ctx, int code, const char *fmt, ...);
 int nimfm_ensure_partials(nimfm_ctx *ctx, size_t nDoubles);
 int nimfm_ensure_idx(nimfm_ctx *ctx, size_t n);
 int nimfm_allreduce_sum(nimfm_ctx *ctx, double *buf, int64_t n);
+int nimfm_reduce_scatter_sum(nimfm_ctx *ctx, double *buf, int64_t count);
+int nimfm_allgather_inplace(nimfm_ctx *ctx, double *buf, int64_t count);
+int nimfm_allgather_host_i64(nimfm_ctx *ctx, const int64_t *mine, int count, int64_t *all);
+// Minibatch schedule shared by the ranks of a synchronous epoch.  Every rank feeds up to `mb` of its own
+// `nRows` rows per minibatch; shards and shares may be uneven, so all ranks run T = max_r ceil(nRows_r / mb_r)
+// minibatches (a rank that has run out feeds 0 rows but still joins the collectives) and the iteration
+// counter advances by the GLOBAL number of rows of the minibatch.
+struct MbSchedule {
+  int64_t T = 0;
+  int rank = 0;
+  std::vector<int64_t> nRows, mb;
+  int64_t rows_of(int r, int64_t t) const {
+    const int64_t left = nRows[(size_t)r] - t * mb[(size_t)r];
+    return left <= 0 ? 0 : (left < mb[(size_t)r] ? left : mb[(size_t)r]);
+  }
+  int64_t local(int64_t t) const { return rows_of(rank, t); }
+  int64_t global(int64_t t) const {
+    int64_t g = 0;
+    for (size_t r = 0; r < nRows.size(); r++) g += rows_of((int)r, t);
+    return g;
+  }
+};
+// gathers (nRows, mb, it) of every rank; fails when the ranks disagree on `it` (their replicas have diverged)
+int nimfm_mb_schedule(nimfm_ctx *ctx, int64_t nRows, int64_t mb, int64_t it, MbSchedule *out);
+int nimfm_comm_alloc(nimfm_ctx *ctx, double **out, size_t nDoubles);
+void nimfm_comm_free(nimfm_ctx *ctx, double *p);
 
 // hot-column table upload (dataset.cu)
 int nimfm_upload_hot(nimfm_ctx *ctx, const std::vector<int32_t> &hot, int64_t d, uint8_t **hotSlot, int32_t **hotList);
 int nimfm_staged_h2d(nimfm_ctx *ctx, void *dDst, const void *src, size_t bytes, int64_t narrowD = 0, int *bad = nullptr);
 int nimfm_staged_d2h(nimfm_ctx *ctx, void *hostDst, const void *dSrc, size_t bytes);
 int nimfm_find_hot(const int64_t *indices, const int64_t *indptr, int64_t rowBegin, int64_t rowEnd,
-                   std::vector<int32_t> &hot, int64_t maxSample);
+                   std::vector<int32_t> &hot, int64_t maxSample, int64_t d);
 
 // upload host int64 row ids into ctx->idx32Scratch as int32 (validated against n)
 int nimfm_stage_row_ids(nimfm_ctx *ctx, const int64_t *ids, int64_t count, int64_t n);

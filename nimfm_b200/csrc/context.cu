@@ -3,6 +3,7 @@
 #include <dlfcn.h>
 #include <stdarg.h>
 
+#include <algorithm>
 #include <atomic>
 #include <thread>
 
@@ -14,6 +15,12 @@ typedef struct { char internal[128]; } nimfm_ncclUniqueId;
 typedef int (*fn_ncclGetUniqueId)(nimfm_ncclUniqueId *);
 typedef int (*fn_ncclCommInitRank)(ncclComm **, int, nimfm_ncclUniqueId, int);
 typedef int (*fn_ncclAllReduce)(const void *, void *, size_t, int, int, ncclComm *, cudaStream_t);
+typedef int (*fn_ncclReduceScatter)(const void *, void *, size_t, int, int, ncclComm *, cudaStream_t);
+typedef int (*fn_ncclAllGather)(const void *, void *, size_t, int, ncclComm *, cudaStream_t);
+typedef int (*fn_ncclMemAlloc)(void **, size_t);
+typedef int (*fn_ncclMemFree)(void *);
+typedef int (*fn_ncclCommWindowRegister)(ncclComm *, void *, size_t, void **, int);
+typedef int (*fn_ncclCommWindowDeregister)(ncclComm *, void *);
 typedef int (*fn_ncclCommDestroy)(ncclComm *);
 typedef const char *(*fn_ncclGetErrorString)(int);
 static struct {
@@ -21,6 +28,12 @@ static struct {
   fn_ncclGetUniqueId getUniqueId;
   fn_ncclCommInitRank commInitRank;
   fn_ncclAllReduce allReduce;
+  fn_ncclReduceScatter reduceScatter;
+  fn_ncclAllGather allGather;
+  fn_ncclMemAlloc memAlloc;                      // optional (NCCL >= 2.19)
+  fn_ncclMemFree memFree;
+  fn_ncclCommWindowRegister windowRegister;      // optional (NCCL >= 2.27): symmetric-memory collectives
+  fn_ncclCommWindowDeregister windowDeregister;
   fn_ncclCommDestroy commDestroy;
   fn_ncclGetErrorString errStr;
 } g_nccl;
@@ -33,6 +46,12 @@ static int load_nccl() {
   g_nccl.getUniqueId = (fn_ncclGetUniqueId)dlsym(h, "ncclGetUniqueId");
   g_nccl.commInitRank = (fn_ncclCommInitRank)dlsym(h, "ncclCommInitRank");
   g_nccl.allReduce = (fn_ncclAllReduce)dlsym(h, "ncclAllReduce");
+  g_nccl.reduceScatter = (fn_ncclReduceScatter)dlsym(h, "ncclReduceScatter");
+  g_nccl.allGather = (fn_ncclAllGather)dlsym(h, "ncclAllGather");
+  g_nccl.memAlloc = (fn_ncclMemAlloc)dlsym(h, "ncclMemAlloc");
+  g_nccl.memFree = (fn_ncclMemFree)dlsym(h, "ncclMemFree");
+  g_nccl.windowRegister = (fn_ncclCommWindowRegister)dlsym(h, "ncclCommWindowRegister");
+  g_nccl.windowDeregister = (fn_ncclCommWindowDeregister)dlsym(h, "ncclCommWindowDeregister");
   g_nccl.commDestroy = (fn_ncclCommDestroy)dlsym(h, "ncclCommDestroy");
   g_nccl.errStr = (fn_ncclGetErrorString)dlsym(h, "ncclGetErrorString");
   if (!g_nccl.getUniqueId || !g_nccl.commInitRank || !g_nccl.allReduce || !g_nccl.commDestroy) return -1;
@@ -51,6 +70,23 @@ int nimfm_fail(nimfm_ctx *ctx, int code, const char *fmt, ...) {
   if (ctx) ctx->err = buf;
   else g_noctx_err = buf;
   return code;
+}
+
+static int ctx_init_resources(nimfm_ctx *ctx) {
+  CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&ctx->ev0));
+  CK(cudaEventCreate(&ctx->ev1));
+  CK(cudaEventCreate(&ctx->tev0));
+  CK(cudaEventCreate(&ctx->tev1));
+  CK(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+  for (int s = 0; s < 2; s++) {
+    CK(cudaEventCreateWithFlags(&ctx->evCopied[s], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->evComputed[s], cudaEventDisableTiming));
+  }
+  CK(cudaMalloc(&ctx->scalars, 64 * sizeof(double)));
+  CK(cudaMemset(ctx->scalars, 0, 64 * sizeof(double)));
+  CK(cudaMallocHost(&ctx->hostScalars, 64 * sizeof(double)));
+  return NIMFM_OK;
 }
 
 extern "C" {
@@ -105,19 +141,12 @@ int32_t nimfm_ctx_create(int32_t device, nimfm_ctx **out) {
   ctx->numSMs = prop.multiProcessorCount;
   ctx->smemOptin = (int)prop.sharedMemPerBlockOptin;
   ctx->smemPerSM = (int)prop.sharedMemPerMultiprocessor;
-  CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  CK(cudaEventCreate(&ctx->ev0));
-  CK(cudaEventCreate(&ctx->ev1));
-  CK(cudaEventCreate(&ctx->tev0));
-  CK(cudaEventCreate(&ctx->tev1));
-  CK(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
-  for (int s = 0; s < 2; s++) {
-    CK(cudaEventCreateWithFlags(&ctx->evCopied[s], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&ctx->evComputed[s], cudaEventDisableTiming));
+  const int rc = ctx_init_resources(ctx);
+  if (rc != NIMFM_OK) {   // the half-built context is released; its message moves to the no-context slot
+    const std::string msg = ctx->err;
+    nimfm_ctx_destroy(ctx);
+    return nimfm_fail(nullptr, rc, "%s", msg.c_str());
   }
-  CK(cudaMalloc(&ctx->scalars, 64 * sizeof(double)));
-  CK(cudaMemset(ctx->scalars, 0, 64 * sizeof(double)));
-  CK(cudaMallocHost(&ctx->hostScalars, 64 * sizeof(double)));
   *out = ctx;
   return NIMFM_OK;
 }
@@ -145,6 +174,8 @@ int32_t nimfm_ctx_destroy(nimfm_ctx *ctx) {
   for (int s = 0; s < 4; s++) {
     if (ctx->hostIdx[s]) cudaFreeHost(ctx->hostIdx[s]);
     if (ctx->hostPtr[s]) cudaFreeHost(ctx->hostPtr[s]);
+    if (ctx->hostData[s]) cudaFreeHost(ctx->hostData[s]);
+    if (ctx->hostY[s]) cudaFreeHost(ctx->hostY[s]);
     if (ctx->evSlot[s]) cudaEventDestroy(ctx->evSlot[s]);
   }
   cudaFree(ctx->stageHotSlot);
@@ -156,6 +187,35 @@ int32_t nimfm_ctx_destroy(nimfm_ctx *ctx) {
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
+  return NIMFM_OK;
+}
+
+// Page-lock a caller-owned host array for the lifetime of the data set it belongs to (the Nim dataset object
+// owns its seqs, so the lifetime is known there): host-fed calls then DMA straight out of it at link rate.
+// Unregister before the array is freed or resized.
+int32_t nimfm_host_register(nimfm_ctx *ctx, const void *ptr, int64_t bytes) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  REQUIRE(ptr != nullptr && bytes > 0, "bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  cudaError_t e = cudaHostRegister(const_cast<void *>(ptr), (size_t)bytes, cudaHostRegisterDefault);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    cudaGetLastError();
+    return NIMFM_OK;
+  }
+  if (e != cudaSuccess) return nimfm_fail(ctx, NIMFM_ERR_CUDA, "cudaHostRegister(%lld bytes): %s", (long long)bytes, cudaGetErrorString(e));
+  return NIMFM_OK;
+}
+
+int32_t nimfm_host_unregister(nimfm_ctx *ctx, const void *ptr) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  REQUIRE(ptr != nullptr, "ptr is NULL");
+  CK(cudaSetDevice(ctx->device));
+  cudaError_t e = cudaHostUnregister(const_cast<void *>(ptr));
+  if (e == cudaErrorHostMemoryNotRegistered) {
+    cudaGetLastError();
+    return NIMFM_OK;
+  }
+  if (e != cudaSuccess) return nimfm_fail(ctx, NIMFM_ERR_CUDA, "cudaHostUnregister: %s", cudaGetErrorString(e));
   return NIMFM_OK;
 }
 
@@ -187,6 +247,13 @@ int32_t nimfm_comm_init(nimfm_ctx *ctx, int32_t rank, int32_t nranks, const void
 
 int32_t nimfm_comm_size(const nimfm_ctx *ctx) { return ctx ? ctx->nranks : 0; }
 
+int32_t nimfm_comm_allgather_i64(nimfm_ctx *ctx, const int64_t *mine, int32_t count, int64_t *all) {
+  if (!ctx) return NIMFM_ERR_INVALID;
+  REQUIRE(mine && all && count >= 1 && count <= 4096, "bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  return nimfm_allgather_host_i64(ctx, mine, count, all);
+}
+
 int32_t nimfm_timer_start(nimfm_ctx *ctx) {
   if (!ctx) return NIMFM_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
@@ -211,6 +278,104 @@ int nimfm_allreduce_sum(nimfm_ctx *ctx, double *buf, int64_t n) {
   int rc = g_nccl.allReduce(buf, buf, (size_t)n, /*ncclDouble*/ 8, /*ncclSum*/ 0, ctx->comm, ctx->stream);
   if (rc != 0) return nimfm_fail(ctx, NIMFM_ERR_NCCL, "ncclAllReduce: %s", g_nccl.errStr ? g_nccl.errStr(rc) : "?");
   return NIMFM_OK;
+}
+
+// rank r receives the sum of elements [r*count, (r+1)*count) of every rank's buf, in place (at buf + r*count)
+int nimfm_reduce_scatter_sum(nimfm_ctx *ctx, double *buf, int64_t count) {
+  if (ctx->nranks == 1) return NIMFM_OK;
+  if (!ctx->comm || !g_nccl.reduceScatter) return nimfm_fail(ctx, NIMFM_ERR_NCCL, "communicator not initialised (nimfm_comm_init)");
+  int rc = g_nccl.reduceScatter(buf, buf + (int64_t)ctx->rank * count, (size_t)count, 8, 0, ctx->comm, ctx->stream);
+  if (rc != 0) return nimfm_fail(ctx, NIMFM_ERR_NCCL, "ncclReduceScatter: %s", g_nccl.errStr ? g_nccl.errStr(rc) : "?");
+  return NIMFM_OK;
+}
+
+// every rank's slice [r*count, (r+1)*count) of buf is distributed to all ranks, in place
+int nimfm_allgather_inplace(nimfm_ctx *ctx, double *buf, int64_t count) {
+  if (ctx->nranks == 1) return NIMFM_OK;
+  if (!ctx->comm || !g_nccl.allGather) return nimfm_fail(ctx, NIMFM_ERR_NCCL, "communicator not initialised (nimfm_comm_init)");
+  int rc = g_nccl.allGather(buf + (int64_t)ctx->rank * count, buf, (size_t)count, 8, ctx->comm, ctx->stream);
+  if (rc != 0) return nimfm_fail(ctx, NIMFM_ERR_NCCL, "ncclAllGather: %s", g_nccl.errStr ? g_nccl.errStr(rc) : "?");
+  return NIMFM_OK;
+}
+
+// `count` int64 values of every rank, rank-major, on every host (sizes the ranks must agree on before a
+// sharded epoch: shard lengths, minibatch shares).  One rank: a copy.
+int nimfm_allgather_host_i64(nimfm_ctx *ctx, const int64_t *mine, int count, int64_t *all) {
+  if (ctx->nranks == 1) {
+    memcpy(all, mine, (size_t)count * 8);
+    return NIMFM_OK;
+  }
+  if (!ctx->comm || !g_nccl.allGather) return nimfm_fail(ctx, NIMFM_ERR_NCCL, "communicator not initialised (nimfm_comm_init)");
+  int rc = nimfm_ensure_idx(ctx, (size_t)count * (ctx->nranks + 1));
+  if (rc) return rc;
+  int64_t *dAll = ctx->idxScratch, *dMine = ctx->idxScratch + (size_t)count * ctx->nranks;
+  CK(cudaMemcpyAsync(dMine, mine, (size_t)count * 8, cudaMemcpyHostToDevice, ctx->stream));
+  rc = g_nccl.allGather(dMine, dAll, (size_t)count, /*ncclInt64*/ 4, ctx->comm, ctx->stream);
+  if (rc != 0) return nimfm_fail(ctx, NIMFM_ERR_NCCL, "ncclAllGather: %s", g_nccl.errStr ? g_nccl.errStr(rc) : "?");
+  CK(cudaMemcpyAsync(all, dAll, (size_t)count * ctx->nranks * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return NIMFM_OK;
+}
+
+int nimfm_mb_schedule(nimfm_ctx *ctx, int64_t nRows, int64_t mb, int64_t it, MbSchedule *out) {
+  const int R = ctx->nranks;
+  out->rank = ctx->rank;
+  out->nRows.assign((size_t)R, nRows);
+  out->mb.assign((size_t)R, mb);
+  if (R > 1) {
+    const int64_t mine[3] = {nRows, mb, it};
+    std::vector<int64_t> all((size_t)3 * R);
+    int rc = nimfm_allgather_host_i64(ctx, mine, 3, all.data());
+    if (rc) return rc;
+    for (int r = 0; r < R; r++) {
+      out->nRows[(size_t)r] = all[(size_t)3 * r];
+      out->mb[(size_t)r] = all[(size_t)3 * r + 1];
+      if (all[(size_t)3 * r + 2] != it)
+        return nimfm_fail(ctx, NIMFM_ERR_STATE, "rank %d is at iteration %lld, rank %d at %lld: the replicas have diverged",
+                          r, (long long)all[(size_t)3 * r + 2], ctx->rank, (long long)it);
+      if (out->mb[(size_t)r] < 1) return nimfm_fail(ctx, NIMFM_ERR_INVALID, "rank %d has miniBatchSize < 1", r);
+    }
+  }
+  out->T = 0;
+  for (int r = 0; r < R; r++)
+    out->T = std::max(out->T, (out->nRows[(size_t)r] + out->mb[(size_t)r] - 1) / out->mb[(size_t)r]);
+  return NIMFM_OK;
+}
+
+// Buffers that take part in collectives.  With NIMFM_NCCL_SYMMETRIC=1 (and an NCCL that has it) they come from
+// ncclMemAlloc and are registered as symmetric windows on the communicator, which lets NCCL run its
+// symmetric-memory / NVLS kernels without staging copies; otherwise plain cudaMalloc.  Collective: when the
+// symmetric route is on, every rank must allocate the same sequence of buffers (the solvers do).
+int nimfm_comm_alloc(nimfm_ctx *ctx, double **out, size_t nDoubles) {
+  *out = nullptr;
+  const char *env = getenv("NIMFM_NCCL_SYMMETRIC");
+  const bool sym = env && env[0] == '1' && ctx->comm && g_nccl.memAlloc && g_nccl.memFree;
+  if (sym) {
+    void *p = nullptr;
+    if (g_nccl.memAlloc(&p, nDoubles * 8) == 0 && p) {
+      void *win = nullptr;
+      if (g_nccl.windowRegister && g_nccl.windowRegister(ctx->comm, p, nDoubles * 8, &win, /*NCCL_WIN_COLL_SYMMETRIC*/ 1) != 0)
+        win = nullptr;
+      ctx->commBufs.push_back({p, win});
+      *out = static_cast<double *>(p);
+      return NIMFM_OK;
+    }
+  }
+  CK(cudaMalloc(out, nDoubles * 8));
+  return NIMFM_OK;
+}
+
+void nimfm_comm_free(nimfm_ctx *ctx, double *p) {
+  if (!p) return;
+  if (ctx)
+    for (size_t i = 0; i < ctx->commBufs.size(); i++)
+      if (ctx->commBufs[i].ptr == p) {
+        if (ctx->commBufs[i].win && g_nccl.windowDeregister && ctx->comm) g_nccl.windowDeregister(ctx->comm, ctx->commBufs[i].win);
+        if (g_nccl.memFree) g_nccl.memFree(p);
+        ctx->commBufs.erase(ctx->commBufs.begin() + (long)i);
+        return;
+      }
+  cudaFree(p);
 }
 
 int nimfm_ensure_partials(nimfm_ctx *ctx, size_t nDoubles) {

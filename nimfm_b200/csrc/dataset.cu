@@ -15,16 +15,27 @@ static int alloc_copy(nimfm_ctx *ctx, void **dst, const void *src, size_t bytes)
 // Find the "hot" columns of a CSR from an evenly spaced sample of at most 16384 rows: present in at
 // least 1/16 of the sampled rows, the 16 most frequent.  Pure bookkeeping; it only changes where the
 // kernels ACCUMULATE the gradients of those columns, never a result.
+// The sample runs BEFORE the caller's arrays are fully validated (the host-fed calls check chunk by chunk),
+// so it trusts nothing: rows whose indptr pair is not a sane range inside [lo, hi) are skipped and ids outside
+// [0, d) are ignored -- the validation that follows rejects the call; the sample must only not crash on it
+// or hand an out-of-range id to the hot table.
 int nimfm_find_hot(const int64_t *indices, const int64_t *indptr, int64_t rowBegin, int64_t rowEnd,
-                   std::vector<int32_t> &hot, int64_t maxSample) {
+                   std::vector<int32_t> &hot, int64_t maxSample, int64_t d) {
   hot.clear();
   const int64_t ns = rowEnd - rowBegin;
   if (ns <= 0) return 0;
   const int64_t stride = std::max<int64_t>(1, ns / maxSample);
+  const int64_t lo = indptr[rowBegin], hi = indptr[rowEnd];
   std::unordered_map<int64_t, int> cnt;
   int64_t sampled = 0;
-  for (int64_t r = rowBegin; r < rowEnd; r += stride, ++sampled)
-    for (int64_t q = indptr[r]; q < indptr[r + 1]; q++) cnt[indices[q]] += 1;
+  for (int64_t r = rowBegin; r < rowEnd; r += stride, ++sampled) {
+    const int64_t q0 = indptr[r], q1 = indptr[r + 1];
+    if (q0 < lo || q1 > hi || q1 < q0) continue;
+    for (int64_t q = q0; q < q1; q++) {
+      const int64_t j = indices[q];
+      if (j >= 0 && j < d) cnt[j] += 1;
+    }
+  }
   std::vector<std::pair<int, int64_t>> cand;
   for (auto &kv : cnt)
     if ((int64_t)kv.second * 16 >= sampled && kv.second >= 2) cand.push_back({kv.second, kv.first});
@@ -76,6 +87,12 @@ static int upload_common(nimfm_ctx *ctx, int kind, int64_t nSeg, int64_t nOther,
     }
   }
   nimfm_dataset *ds = new nimfm_dataset();
+  // every early return below (CK / REQUIRE included) releases the half-built dataset and its device buffers
+  struct Guard {
+    nimfm_ctx *ctx;
+    nimfm_dataset *ds;
+    ~Guard() { if (ds) nimfm_dataset_free(ctx, ds); }
+  } guard{ctx, ds};
   ds->kind = kind;
   ds->n = (kind == NIMFM_DS_CSC) ? n : ns;
   ds->d = (kind == NIMFM_DS_CSC) ? ns : d;
@@ -85,7 +102,7 @@ static int upload_common(nimfm_ctx *ctx, int kind, int64_t nSeg, int64_t nOther,
   // values, ids and field ids reach the device through the pinned-piece thread team (the ids narrowed to
   // int32 and range-checked on the way): 2 M Criteo-shaped rows 0.33 s -> the link's rate
   int rc, bad = 0;
-  auto fail = [&](int code) { nimfm_dataset_free(ctx, ds); return code; };
+  auto fail = [&](int code) { return code; };   // the guard frees
   CK(cudaMalloc(&ds->data, (size_t)std::max<int64_t>(nnz, 2) * 8));
   CK(cudaMalloc(&ds->indices, (size_t)std::max<int64_t>(nnz, 4) * 4));
   if (fields) CK(cudaMalloc(&ds->fields, (size_t)std::max<int64_t>(nnz, 4) * 4));
@@ -116,10 +133,11 @@ static int upload_common(nimfm_ctx *ctx, int kind, int64_t nSeg, int64_t nOther,
   if ((rc = alloc_copy(ctx, (void **)&ds->indptr, ptr.data(), ((size_t)ns + 1) * 8))) return fail(rc);
   if (kind != NIMFM_DS_CSC) {
     std::vector<int32_t> hot;
-    ds->nHot = nimfm_find_hot(indices, indptr, segBegin, segEnd, hot, 16384);
+    ds->nHot = nimfm_find_hot(indices, indptr, segBegin, segEnd, hot, 16384, d);
     if ((rc = nimfm_upload_hot(ctx, hot, d, &ds->hotSlot, &ds->hotList))) return rc;
   }
   CK(cudaStreamSynchronize(ctx->stream));
+  guard.ds = nullptr;
   *out = ds;
   return NIMFM_OK;
 }

@@ -67,6 +67,37 @@ static __global__ void mbpsgd_step_kernel(double *P, double *gP, int64_t nP, dou
   }
 }
 
+// The same step on ONE RANK'S FLAT SLICE [lo, hi) of the pools (multi-rank: reduce-scatter of the gradient pool
+// -> this kernel on 1/N of the elements -> all-gather of the parameter pool).  par = [P | w | b, epochLoss],
+// g = [gP | gw | gb, lossSum], both in the same flat element order; the slice may straddle the P / w / tail
+// boundaries.  The gradient pool is cleared by the caller (every rank holds partial sums outside its slice).
+static __global__ void mbpsgd_step_flat_kernel(double *par, const double *g, int64_t lo, int64_t hi, int64_t nP,
+                                               int64_t d, double negEtaP, double rP, int reg, double lam,
+                                               double negEtaW, double rW, int fitLinear, double negEtaB, double rB,
+                                               int fitIntercept) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < hi; e += stride) {
+    if (e < nP) {
+      double p = par[e] + negEtaP * g[e];
+      p *= rP;
+      if (reg == NIMFM_REG_L1) {
+        const double m = fabs(p) - lam;
+        p = (p > 0 ? 1.0 : (p < 0 ? -1.0 : 0.0)) * (m > 0.0 ? m : 0.0);
+      }
+      par[e] = p;
+    } else if (e < nP + d) {
+      if (fitLinear) par[e] = (par[e] + negEtaW * g[e]) * rW;
+    } else if (e == nP + d) {
+      double bb = par[e];
+      if (fitIntercept && fitLinear) bb += negEtaB * g[e];   // params.nim:47
+      if (fitIntercept) bb *= rB;                            // params.nim:65-66
+      par[e] = bb;
+    } else if (e == nP + d + 1) {
+      par[e] += g[e];                                        // the epoch's loss sum (minibatch_psgd.nim:84,124)
+    }
+  }
+}
+
 // ------------------------------------------------------------------ MBPSGD lazy step (K3b)
 // The dense step above moves all of P, w and the gradient buffer every minibatch; with the reference's
 // default minibatch (25 641 rows of the Criteo shape) a minibatch touches ~1/5 of the features and the

@@ -680,8 +680,11 @@ int32_t nimfm_ffm_adagrad_epoch(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_datase
   double *violPart = cntF + d;
   const int64_t nDelta = 2 * nP + 2 * d + 4;
   const int64_t mb = cfg->miniBatchSize;
-  for (int64_t start = 0; start < nRows; start += mb) {
-    const int64_t cnt = std::min<int64_t>(mb, nRows - start);
+  MbSchedule sch;
+  if ((rc = nimfm_mb_schedule(ctx, nRows, mb, *it, &sch))) return rc;
+  for (int64_t t = 0; t < sch.T; t++) {
+    const int64_t start = std::min(t * mb, nRows);
+    const int64_t cnt = sch.local(t);   // 0 once this rank's (shorter) shard is used up: it still joins the collectives
     const int32_t *rows = idxDev ? idxDev + start : nullptr;
     const double tIt = (double)(*it - 1);
     const int first = (*it == 1);
@@ -735,7 +738,7 @@ int32_t nimfm_ffm_adagrad_epoch(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_datase
                                                                      dGsw, dGnw, d, m->fitLinear, cntF, d);
       LAUNCHED(ctx);
     }
-    *it += cnt * (int64_t)ctx->nranks;
+    *it += sch.global(t);
   }
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(ctx->hostScalars, ctx->scalars, 16, cudaMemcpyDeviceToHost, ctx->stream));

@@ -216,16 +216,25 @@ int32_t nimfm_fm_create(nimfm_ctx *ctx, int32_t degree, int32_t nComponents, int
   fm->fitLinear = fitLinear != 0;
   fm->fitIntercept = fitIntercept != 0;
   const int64_t nP = fm->nP(), d = fm->d;
-  CK(cudaMalloc(&fm->P, (size_t)nP * 8));
-  CK(cudaMalloc(&fm->w, (size_t)d * 8));
-  CK(cudaMalloc(&fm->lams, (size_t)fm->k * 8));
-  CK(cudaMalloc(&fm->b, 8 * 8));
-  CK(cudaMalloc(&fm->grad, (size_t)(nP + d + 2) * 8));
-  CK(cudaMemsetAsync(fm->P, 0, (size_t)nP * 8, ctx->stream));
-  CK(cudaMemsetAsync(fm->w, 0, (size_t)d * 8, ctx->stream));
-  CK(cudaMemsetAsync(fm->b, 0, 8 * 8, ctx->stream));
-  CK(cudaMemsetAsync(fm->grad, 0, (size_t)(nP + d + 2) * 8, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  // slack: room to round a rank's flat slice up to whole (feature, order-block) vectors for up to 64 ranks
+  const int64_t SB8 = (int64_t)fm->nOrders * fm->k;
+  fm->poolCap = nP + d + 8 + 64 * ((SB8 & 1) ? 2 * SB8 : SB8);
+  int rc;
+  if ((rc = nimfm_comm_alloc(ctx, &fm->pool, (size_t)fm->poolCap)) || (rc = nimfm_comm_alloc(ctx, &fm->grad, (size_t)fm->poolCap))) {
+    nimfm_fm_free(ctx, fm);
+    return rc;
+  }
+  fm->P = fm->pool;
+  fm->w = fm->pool + nP;
+  fm->b = fm->pool + nP + d;
+  cudaError_t ce = cudaMalloc(&fm->lams, (size_t)fm->k * 8);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(fm->pool, 0, (size_t)fm->poolCap * 8, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(fm->grad, 0, (size_t)fm->poolCap * 8, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+  if (ce != cudaSuccess) {
+    nimfm_fm_free(ctx, fm);
+    return nimfm_fail(ctx, NIMFM_ERR_CUDA, "nimfm_fm_create: %s", cudaGetErrorString(ce));
+  }
   *out = fm;
   return NIMFM_OK;
 }
@@ -233,7 +242,9 @@ int32_t nimfm_fm_create(nimfm_ctx *ctx, int32_t degree, int32_t nComponents, int
 int32_t nimfm_fm_free(nimfm_ctx *ctx, nimfm_fm *fm) {
   if (!fm) return NIMFM_OK;
   if (ctx) cudaSetDevice(ctx->device);
-  for (double *p : {fm->P, fm->w, fm->lams, fm->b, fm->grad, fm->gsP, fm->gnP, fm->gsw, fm->gnw, fm->dG,
+  nimfm_comm_free(ctx, fm->pool);   // P, w, b
+  nimfm_comm_free(ctx, fm->grad);
+  for (double *p : {fm->lams, fm->gsP, fm->gnP, fm->gsw, fm->gnw, fm->dG,
                     fm->adaScal, fm->scalingsP, fm->scalingsW, fm->sgdScal, fm->Pcm, fm->yPred, fm->Acache,
                     fm->colNormSq, fm->cdScal, fm->proxState, fm->psgdThr})
     cudaFree(p);
@@ -598,6 +609,23 @@ int32_t nimfm_fm_mbpsgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset 
           "SquaredL12 supports only degree=2.");
   if (localBatch <= 0) localBatch = cfg->miniBatchSize;
   REQUIRE(X->n > 0, "empty dataset");
+  if (ctx->nranks > 1) {
+    // every rank must run the same number of minibatches with the same divisor and step sizes, and the shares
+    // must add up to the global minibatch -- otherwise the collectives deadlock or the replicas drift apart
+    const int64_t mine[4] = {cfg->miniBatchSize, cfg->maxIterInner, localBatch, *it};
+    std::vector<int64_t> all((size_t)4 * ctx->nranks);
+    if ((rc = nimfm_allgather_host_i64(ctx, mine, 4, all.data()))) return rc;
+    int64_t share = 0;
+    for (int r = 0; r < ctx->nranks; r++) {
+      const int64_t *q = all.data() + 4 * r;
+      REQUIRE(q[0] == mine[0] && q[1] == mine[1] && q[3] == mine[3],
+              "rank %d disagrees on miniBatchSize / maxIterInner / it (%lld, %lld, %lld vs %lld, %lld, %lld)", r,
+              (long long)q[0], (long long)q[1], (long long)q[3], (long long)mine[0], (long long)mine[1], (long long)mine[3]);
+      share += q[2];
+    }
+    REQUIRE(share == cfg->miniBatchSize, "the ranks' localBatch add up to %lld, not miniBatchSize %lld", (long long)share,
+            (long long)cfg->miniBatchSize);
+  }
   const int64_t nP = fm->nP(), d = fm->d, nG = nP + d + 2;
   const int64_t total = localBatch * cfg->maxIterInner;
   const int32_t *idxDev = nullptr;
@@ -681,12 +709,54 @@ int32_t nimfm_fm_mbpsgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset 
       return NIMFM_OK;
     }
   }
+  // ---- multi-rank, sharded step (the alternative to "identical dense step on every GPU"): the
+  // gradient pool is reduce-scattered, every rank steps (and proxes) its flat 1/N slice of [P | w | b], and the
+  // parameter pool is all-gathered in place.  Same bytes on the fabric as the all-reduce, 1/N of the dense pass.
+  // The column-wise SquaredL12 prox needs sums over all features and keeps the all-reduce route.
+  int64_t sliceC = 0;
+  {
+    const char *env = getenv("NIMFM_MBPSGD_SHARDED");
+    const int64_t SB8 = (int64_t)fm->nOrders * fm->k, align = (SB8 & 1) ? 2 * SB8 : SB8;
+    const int64_t c = ((nG + ctx->nranks - 1) / ctx->nranks + align - 1) / align * align;
+    if (ctx->nranks > 1 && cfg->reg != NIMFM_REG_SQUAREDL12 && !(env && env[0] == '0') && c * ctx->nranks <= fm->poolCap)
+      sliceC = c;
+  }
+  if (sliceC) CK(cudaMemsetAsync(fm->b + 1, 0, 8, ctx->stream));   // epoch loss slot of the parameter pool
   for (int64_t inner = 0; inner < cfg->maxIterInner; inner++) {
     if ((rc = launch_loss_grad(ctx, fm, X, cfg->loss, cfg->huberThreshold, cur, localBatch,
                                idxDev ? idxDev + inner * localBatch : nullptr, (double)cfg->miniBatchSize, nullptr)))
       return rc;
     add_tail_kernel<<<1, 1, 0, ctx->stream>>>(fm->grad + nG - 2, ctx->scalars + 8);
     LAUNCHED(ctx);
+    if (sliceC) {
+      if ((rc = nimfm_reduce_scatter_sum(ctx, fm->grad, sliceC))) return rc;
+      const double etaP = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->beta, *it);
+      const double etaW = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->alpha, *it);
+      const double etaB = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->alpha0, *it);
+      const double rP = 1.0 / (1.0 + etaP * cfg->beta), rW = 1.0 / (1.0 + etaW * cfg->alpha),
+                   rB = 1.0 / (1.0 + etaB * cfg->alpha0);
+      const double lam = cfg->gamma * etaP / (1.0 + etaP * cfg->beta);
+      const int64_t lo = (int64_t)ctx->rank * sliceC, hi = std::min(lo + sliceC, nG);
+      if (hi > lo) {
+        mbpsgd_step_flat_kernel<<<ew_grid(ctx, hi - lo), 256, 0, ctx->stream>>>(
+            fm->pool, fm->grad, lo, hi, nP, d, -etaP, rP, cfg->reg, lam, -etaW, rW, fm->fitLinear, -etaB, rB,
+            fm->fitIntercept);
+        LAUNCHED(ctx);
+        // row-wise prox on the slice's whole (feature, order) vectors (slices start at multiples of nOrders*k)
+        if ((cfg->reg == NIMFM_REG_L21 || cfg->reg == NIMFM_REG_SQUAREDL12_ROWS) && lam != 0.0 && lo < nP) {
+          if (fm->k > 32 * NIMFM_PROX_MAXE)
+            return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "row-wise prox supports nComponents <= %d", 32 * NIMFM_PROX_MAXE);
+          const int64_t vecs = (std::min(hi, nP) - lo) / fm->k;
+          prox_rows_kernel<<<ew_grid(ctx, vecs * 32), 256, 0, ctx->stream>>>(fm->pool + lo, vecs, fm->k, lam, cfg->reg);
+          LAUNCHED(ctx);
+        }
+      }
+      if ((rc = nimfm_allgather_inplace(ctx, fm->pool, sliceC))) return rc;
+      CK(cudaMemsetAsync(fm->grad, 0, (size_t)(sliceC * ctx->nranks) * 8, ctx->stream));
+      *it += 1;
+      cur = (cur + localBatch) % X->n;
+      continue;
+    }
     if ((rc = nimfm_allreduce_sum(ctx, fm->grad, nG))) return rc;
     const double etaP = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->beta, *it);     // :114-116
     const double etaW = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->alpha, *it);
@@ -703,10 +773,10 @@ int32_t nimfm_fm_mbpsgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset 
     cur = (cur + localBatch) % X->n;
   }
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(ctx->hostScalars, ctx->scalars, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->hostScalars, sliceC ? fm->b + 1 : ctx->scalars, 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   *ii = cur;
-  // runningLoss / (miniBatchSize*maxIterInner) (:124); the loss sum was all-reduced with the gradient
+  // runningLoss / (miniBatchSize*maxIterInner) (:124); the loss sum was reduced with the gradient
   if (runningLoss) *runningLoss = ctx->hostScalars[0] / (double)(cfg->miniBatchSize * cfg->maxIterInner);
   return NIMFM_OK;
 }
@@ -889,8 +959,11 @@ int32_t nimfm_fm_adagrad_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset
       return NIMFM_OK;
     }
   }
-  for (int64_t start = 0; start < nRows; start += mb) {
-    const int64_t cnt = std::min<int64_t>(mb, nRows - start);
+  MbSchedule sch;
+  if ((rc = nimfm_mb_schedule(ctx, nRows, mb, *it, &sch))) return rc;
+  for (int64_t t = 0; t < sch.T; t++) {
+    const int64_t start = std::min(t * mb, nRows);
+    const int64_t cnt = sch.local(t);   // 0 once this rank's (shorter) shard is used up: it still joins the collectives
     const int32_t *rows = idxDev ? idxDev + start : nullptr;
     const double tIt = (double)(*it - 1);
     const int first = (*it == 1);
@@ -954,7 +1027,7 @@ int32_t nimfm_fm_adagrad_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset
                                                                      dGsw, dGnw, d, fm->fitLinear, cntF, dd);
       LAUNCHED(ctx);
     }
-    *it += cnt * (int64_t)ctx->nranks;
+    *it += sch.global(t);
   }
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(ctx->hostScalars, ctx->scalars, 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1039,10 +1112,6 @@ __global__ void narrow_rebase_kernel(const int64_t *idx64, int32_t *idx32, int64
   for (int64_t r = tid; r < nRowsPlus1; r += stride) indptr[r] -= base;
 }
 
-int nimfm_find_hot(const int64_t *indices, const int64_t *indptr, int64_t rowBegin, int64_t rowEnd,
-                   std::vector<int32_t> &hot, int64_t maxSample);
-int nimfm_upload_hot(nimfm_ctx *ctx, const std::vector<int32_t> &hot, int64_t d, uint8_t **hotSlot,
-                     int32_t **hotList);
 
 struct HotLists { int32_t v[32]; };   // [0,16): entries to clear, [16,32): entries to set (-1 = none)
 static __global__ void set_hot_table_kernel(uint8_t *slot, const HotLists hl) {
@@ -1079,22 +1148,60 @@ static int ensure_stage(nimfm_ctx *ctx, nimfm_ctx::Stage &st, size_t rows, size_
 
 // pinned host slots of the staging team (host_stage.h): int32 ids + rebased indptr, kSlots deep
 static int ensure_host_slots(nimfm_ctx *ctx, size_t rows, size_t nnz) {
+  // a capacity is only recorded once ALL slots have it: a failed allocation half way leaves it at 0, so the
+  // next call reallocates every slot instead of copying from a null one
+  const bool growNnz = ctx->hostCapNnz < nnz, growRows = ctx->hostCapRows < rows;
+  if (growNnz) ctx->hostCapNnz = 0;
+  if (growRows) ctx->hostCapRows = 0;
   for (int s = 0; s < HostStageTeam::kSlots; s++) {
-    if (ctx->hostCapNnz < nnz) {
+    if (growNnz) {
       if (ctx->hostIdx[s]) CK(cudaFreeHost(ctx->hostIdx[s]));
       ctx->hostIdx[s] = nullptr;
       CK(cudaHostAlloc(&ctx->hostIdx[s], nnz * 4, cudaHostAllocDefault));
     }
-    if (ctx->hostCapRows < rows) {
+    if (growRows) {
       if (ctx->hostPtr[s]) CK(cudaFreeHost(ctx->hostPtr[s]));
       ctx->hostPtr[s] = nullptr;
       CK(cudaHostAlloc(&ctx->hostPtr[s], (rows + 1) * 8, cudaHostAllocDefault));
     }
     if (!ctx->evSlot[s]) CK(cudaEventCreateWithFlags(&ctx->evSlot[s], cudaEventDisableTiming));
   }
-  ctx->hostCapNnz = std::max(ctx->hostCapNnz, nnz);
-  ctx->hostCapRows = std::max(ctx->hostCapRows, rows);
+  if (growNnz) ctx->hostCapNnz = nnz;
+  if (growRows) ctx->hostCapRows = rows;
   return NIMFM_OK;
+}
+
+// pinned value / target slots for PAGEABLE callers (same all-or-nothing capacity rule)
+static int ensure_host_value_slots(nimfm_ctx *ctx, size_t rows, size_t nnz) {
+  const bool growD = ctx->hostCapData < nnz, growY = ctx->hostCapY < rows;
+  if (growD) ctx->hostCapData = 0;
+  if (growY) ctx->hostCapY = 0;
+  for (int s = 0; s < HostStageTeam::kSlots; s++) {
+    if (growD) {
+      if (ctx->hostData[s]) CK(cudaFreeHost(ctx->hostData[s]));
+      ctx->hostData[s] = nullptr;
+      CK(cudaHostAlloc(&ctx->hostData[s], nnz * 8, cudaHostAllocDefault));
+    }
+    if (growY) {
+      if (ctx->hostY[s]) CK(cudaFreeHost(ctx->hostY[s]));
+      ctx->hostY[s] = nullptr;
+      CK(cudaHostAlloc(&ctx->hostY[s], (rows + 1) * 8, cudaHostAllocDefault));
+    }
+  }
+  if (growD) ctx->hostCapData = nnz;
+  if (growY) ctx->hostCapY = rows;
+  return NIMFM_OK;
+}
+
+// is this host pointer outside every page-locked allocation CUDA knows (a plain malloc / Nim seq / numpy array)?
+static bool is_pageable(const void *p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return at.type == cudaMemoryTypeUnregistered;
 }
 
 // Rows [0,nRows) of a HOST CSR streamed through the row kernel in chunks, the H2D copy of chunk c+1
@@ -1148,8 +1255,12 @@ static int stream_host_rows(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t
     ctx->stageNHot = 0;
   }
   std::unique_ptr<HostStageTeam> team;
+  // pageable caller arrays: their values (and targets) travel through the team's pinned slots as well
+  const bool stageValues = hostT > 0 && is_pageable(data);
+  if (stageValues && (rc = ensure_host_value_slots(ctx, capRows, maxNnz))) return rc;
   if (hostT > 0) {
     team.reset(new HostStageTeam(hostT, indices, indptr, d, chunks, ctx->hostIdx, ctx->hostPtr));
+    if (stageValues) team->stage_values(data, predict ? nullptr : y, ctx->hostData, ctx->hostY);
     team->allow(std::min<int64_t>(nChunks, HostStageTeam::kSlots - 1));
   }
   // a failed check leaves with both streams drained (copies read the caller's buffers and our pinned slots)
@@ -1160,6 +1271,12 @@ static int stream_host_rows(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t
   };
   int nHot = 0;
   int64_t h2d = 0, d2h = 0;
+  double *dOutAll = nullptr;
+  if (predict && nRows > 0 && is_pageable(predOut)) CK(cudaMalloc(&dOutAll, (size_t)nRows * 8));
+  struct OutGuard {
+    double *&p;
+    ~OutGuard() { if (p) cudaFree(p); }
+  } outGuard{dOutAll};
   for (int64_t c = 0; c < nChunks; c++) {
     const int64_t r0 = chunks[c].r0, r1 = chunks[c].r1, rows = r1 - r0;
     const int64_t base = chunks[c].base, nnz = chunks[c].nnz;
@@ -1175,7 +1292,8 @@ static int stream_host_rows(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t
     }
     // the copies go out first; the host-side bookkeeping below overlaps with the DMA
     if (c >= 2) CK(cudaStreamWaitEvent(ctx->copyStream, ctx->evComputed[c & 1], 0));   // buffer is free again
-    CK(cudaMemcpyAsync(st.data, data + base, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->copyStream));
+    CK(cudaMemcpyAsync(st.data, stageValues ? ctx->hostData[hs] : data + base, (size_t)nnz * 8, cudaMemcpyHostToDevice,
+                       ctx->copyStream));
     if (team) {
       CK(cudaMemcpyAsync(st.idx32, ctx->hostIdx[hs], (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->copyStream));
       CK(cudaMemcpyAsync(st.indptr, ctx->hostPtr[hs], (size_t)(rows + 1) * 8, cudaMemcpyHostToDevice, ctx->copyStream));
@@ -1183,7 +1301,8 @@ static int stream_host_rows(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t
       CK(cudaMemcpyAsync(st.idx64, indices + base, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->copyStream));
       CK(cudaMemcpyAsync(st.indptr, indptr + r0, (size_t)(rows + 1) * 8, cudaMemcpyHostToDevice, ctx->copyStream));
     }
-    if (!predict) CK(cudaMemcpyAsync(st.y, y + r0, (size_t)rows * 8, cudaMemcpyHostToDevice, ctx->copyStream));
+    if (!predict)
+      CK(cudaMemcpyAsync(st.y, stageValues ? ctx->hostY[hs] : y + r0, (size_t)rows * 8, cudaMemcpyHostToDevice, ctx->copyStream));
     CK(cudaEventRecord(ctx->evCopied[c & 1], ctx->copyStream));
     if (team) CK(cudaEventRecord(ctx->evSlot[hs], ctx->copyStream));
     h2d += nnz * (team ? 12 : 16) + (rows + 1) * 8 + (predict ? 0 : rows * 8);
@@ -1192,7 +1311,7 @@ static int stream_host_rows(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t
       // hot columns of this batch (row sample on the host; see nimfm_find_hot): the previous call's
       // entries are cleared and the new ones set by one tiny kernel on the persistent table
       std::vector<int32_t> hot;
-      nHot = (indices && nRows > 0) ? nimfm_find_hot(indices, indptr, 0, nRows, hot, 2048) : 0;
+      nHot = (indices && nRows > 0) ? nimfm_find_hot(indices, indptr, 0, nRows, hot, 2048, d) : 0;
       int32_t lists[32];
       for (int i = 0; i < 16; i++) lists[i] = i < ctx->stageNHot ? ctx->stagePrevHot[i] : -1;
       for (int i = 0; i < 16; i++) lists[16 + i] = i < nHot ? hot[i] : -1;
@@ -1232,7 +1351,11 @@ static int stream_host_rows(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t
     tmp.hotSlot = ctx->stageHotSlot;
     tmp.hotList = ctx->stageHotList;
     tmp.nHot = nHot;
-    if (predict) {
+    if (predict && dOutAll) {
+      // pageable result array: a device->pageable copy blocks the host until the kernel is done and would
+      // serialise the pipeline, so the chunks' predictions collect on the device and leave in one staged copy
+      if ((rc = nimfm_fm_predict_device_lams(ctx, fm, &tmp, dOutAll + r0))) return drained(rc);
+    } else if (predict) {
       // the stage's target buffer doubles as the chunk's output; it travels back behind the kernel
       if ((rc = nimfm_fm_predict_device_lams(ctx, fm, &tmp, st.y))) return drained(rc);
       CK(cudaMemcpyAsync(predOut + r0, st.y, (size_t)rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1252,7 +1375,9 @@ static int stream_host_rows(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t
   ctx->lastH2D = h2d;
   ctx->lastD2H = d2h + (lossSum && !predict ? 8 : 0);
   ctx->lastHostThreads = hostT;
+  ctx->lastPageable = stageValues ? 1 : 0;
   if (!predict && allreduce && (rc = nimfm_allreduce_sum(ctx, fm->grad, nG))) return rc;
+  if (dOutAll && (rc = nimfm_staged_d2h(ctx, predOut, dOutAll, (size_t)nRows * 8))) return drained(rc);
   int hbad = 0;
   CK(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   if (lossSum && !predict) CK(cudaMemcpyAsync(lossSum, fm->grad + nG - 1, 8, cudaMemcpyDeviceToHost, ctx->stream));

@@ -216,6 +216,13 @@ __global__ void __launch_bounds__(256, 2) fm_rows_stream_kernel(const RowArgs a)
 #pragma unroll
               for (int o = 0; o < NO; ++o) an[o * KT] += gr[o] * gr[o];
             }
+            // linear-term gradient of a hot column: element SB8 of the slot is owned by the group's lane 0
+            // (plain adds in nonzero order; a shared-memory FP64 atomicAdd is a CAS spin loop)
+            if (gl == 0 && a.fitLinear && c + i < zReal) {
+              const double gx = coef * m.x;
+              sAcc[m.acc + SB8] += gx;
+              if (MODE == MODE_ADAGRAD) sAccN[m.acc + SB8] += gx * gx;
+            }
           } else {
             const int64_t eo = (int64_t)m.j * SB8;
 #pragma unroll
@@ -228,18 +235,14 @@ __global__ void __launch_bounds__(256, 2) fm_rows_stream_kernel(const RowArgs a)
         }
       }
     }
-    // ---- linear-term gradient (real features only): one lane per nonzero
+    // ---- linear-term gradient of the cold real features: one lane per nonzero (hot columns: above)
     if (a.fitLinear) {
       for (int u = gl; u < zReal; u += G) {
         const NnzMeta m = sMeta[u];
+        if (m.acc >= 0) continue;
         const double gx = coef * m.x;
-        if (m.acc >= 0) {
-          atomicAdd(sAcc + m.acc + SB8, gx);
-          if (MODE == MODE_ADAGRAD) atomicAdd(sAccN + m.acc + SB8, gx * gx);
-        } else {
-          atomicAdd(a.gw + m.j, gx);
-          if (MODE == MODE_ADAGRAD) atomicAdd(a.dGnw + m.j, gx * gx);
-        }
+        atomicAdd(a.gw + m.j, gx);
+        if (MODE == MODE_ADAGRAD) atomicAdd(a.dGnw + m.j, gx * gx);
       }
     }
   }

@@ -3,6 +3,7 @@
 
 #include <immintrin.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -80,6 +81,14 @@ HostStageTeam::~HostStageTeam() {
   for (auto &th : threads_) th.join();
 }
 
+void HostStageTeam::stage_values(const double *data, const double *y, double *const *dataSlot, double *const *ySlot) {
+  std::lock_guard<std::mutex> g(mu_);
+  data_ = data;
+  y_ = y;
+  dataSlot_ = dataSlot;
+  ySlot_ = ySlot;
+}
+
 void HostStageTeam::allow(int64_t upTo) {
   {
     std::lock_guard<std::mutex> g(mu_);
@@ -101,8 +110,10 @@ void HostStageTeam::part(int64_t c, int t, HostChunkInfo &info) {
   const int64_t per = ((ch.nnz + T_ - 1) / T_ + 7) & ~(int64_t)7;
   const int64_t a = std::min(ch.nnz, per * t), b = std::min(ch.nnz, per * (t + 1));
   if (b > a) info.bad |= narrow(indices_ + ch.base + a, idxSlot_[s] + a, b - a, d_);
+  if (b > a && data_) memcpy(dataSlot_[s] + a, data_ + ch.base + a, (size_t)(b - a) * sizeof(double));
   const int64_t rows = ch.r1 - ch.r0, rper = (rows + T_ - 1) / T_;
   const int64_t ra = std::min(rows, rper * t), rb = std::min(rows, rper * (t + 1));
+  if (rb > ra && y_) memcpy(ySlot_[s] + ra, y_ + ch.r0 + ra, (size_t)(rb - ra) * sizeof(double));
   int64_t *op = ptrSlot_[s];
   for (int64_t r = ra; r < rb; r++) {
     const int64_t p0 = indptr_[ch.r0 + r], len = indptr_[ch.r0 + r + 1] - p0;

@@ -32,6 +32,10 @@ class HostStageTeam {
   // idxSlot[s] (int32, >= max chunk nnz) and ptrSlot[s] (int64, >= max chunk rows + 1): pinned, 32-byte aligned
   HostStageTeam(int nThreads, const int64_t *indices, const int64_t *indptr, int64_t d,
                 const std::vector<HostChunk> &chunks, int32_t *const *idxSlot, int64_t *const *ptrSlot);
+  // PAGEABLE caller arrays (a Nim seq, a numpy array): the team also copies each chunk's values (and targets,
+  // when y != nullptr) into pinned slots, so that every byte the copy engine reads is page-locked -- a
+  // cudaMemcpyAsync from pageable memory is staged by the driver on one thread at ~4 GB/s.  Call before allow().
+  void stage_values(const double *data, const double *y, double *const *dataSlot, double *const *ySlot);
   ~HostStageTeam();                       // stops and joins the workers
   void allow(int64_t upTo);               // chunks < upTo may be written (their slot's last copy has completed)
   HostChunkInfo wait(int64_t c);          // blocks until chunk c is staged in slot c % kSlots
@@ -46,6 +50,9 @@ class HostStageTeam {
   const std::vector<HostChunk> &chunks_;
   int32_t *const *idxSlot_;
   int64_t *const *ptrSlot_;
+  const double *data_ = nullptr, *y_ = nullptr;
+  double *const *dataSlot_ = nullptr;
+  double *const *ySlot_ = nullptr;
   std::mutex mu_;
   std::condition_variable cv_;
   int64_t allowed_ = 0;

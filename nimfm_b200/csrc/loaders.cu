@@ -480,7 +480,7 @@ int32_t nimfm_stream_load_window(nimfm_ctx *ctx, nimfm_stream *sh, int64_t segBe
         }
         sPtr.push_back((int64_t)sIdx.size());
       }
-      nimfm_find_hot(sIdx.data(), sPtr.data(), 0, (int64_t)sPtr.size() - 1, hot, 2048);
+      nimfm_find_hot(sIdx.data(), sPtr.data(), 0, (int64_t)sPtr.size() - 1, hot, 2048, ds->d);
     }
     int rc = nimfm_upload_hot(ctx, hot, ds->d, &ds->hotSlot, &ds->hotList);
     if (rc) return fail(rc);

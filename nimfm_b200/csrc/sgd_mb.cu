@@ -128,7 +128,7 @@ int sgd_mb_epoch(nimfm_ctx *ctx, const MbModel &M, const nimfm_dataset *X, const
   REQUIRE(B >= 1, "miniBatchSize < 1");
   const int R = ctx->nranks;
   if (localBatch <= 0) localBatch = B;
-  REQUIRE(R == 1 ? localBatch == B : localBatch * R == B, "miniBatchSize must be localBatch x ranks (even shards)");
+  REQUIRE(R > 1 || localBatch == B, "one rank: localBatch must equal miniBatchSize");
   REQUIRE(nRows >= 0 && (perm != nullptr || nRows <= X->n), "bad nRows");
   int rc;
   const int32_t *idxDev = nullptr;
@@ -146,13 +146,21 @@ int sgd_mb_epoch(nimfm_ctx *ctx, const MbModel &M, const nimfm_dataset *X, const
   CK(cudaMemsetAsync(ctx->scalars, 0, 8, ctx->stream));          // [0]: loss sum of the epoch
   CK(cudaMemsetAsync(ctx->scalars + 20, 0, 4 * 8, ctx->stream)); // [20]: viol of the epoch
   const int gridP = ew_grid(ctx, M.nP), gridF = ew_grid(ctx, M.dd);
-  for (int64_t q0 = 0; q0 < nRows; q0 += localBatch) {
-    const int64_t Bl = std::min(localBatch, nRows - q0), Bm = Bl * R;   // rows of this rank / of the whole minibatch
+  // shards and shares may be uneven: all ranks run the same number of minibatches and use the GLOBAL row count
+  MbSchedule sch;
+  if ((rc = nimfm_mb_schedule(ctx, nRows, localBatch, *it, &sch))) return rc;
+  for (int64_t t = 0; t < sch.T; t++) {
+    const int64_t q0 = std::min(t * localBatch, nRows);
+    const int64_t Bl = sch.local(t), Bm = sch.global(t);   // rows of this rank / of the whole minibatch
     const int cgrid = (int)std::max<int64_t>(1, std::min<int64_t>((Bl * 32 + 255) / 256, (int64_t)ctx->numSMs * 16));
     adagrad_count_kernel<<<cgrid, 256, 0, ctx->stream>>>(X->indices, X->indptr, X->n, q0, Bl, idxDev ? idxDev + q0 : nullptr,
                                                         M.d, M.nAug, cnt, X->hotSlot, X->hotList, X->nHot);
     LAUNCHED(ctx);
-    if ((rc = launch(q0, Bl, idxDev ? idxDev + q0 : nullptr))) return rc;     // G += sum_i dL_i dA_i; red4 at scalars+8
+    if (Bl > 0) {
+      if ((rc = launch(q0, Bl, idxDev ? idxDev + q0 : nullptr))) return rc;   // G += sum_i dL_i dA_i; red4 at scalars+8
+    } else {
+      CK(cudaMemsetAsync(ctx->scalars + 8, 0, 4 * 8, ctx->stream));           // this rank's shard is used up
+    }
     if (R > 1) {
       add_tail_kernel<<<1, 1, 0, ctx->stream>>>(M.grad + nG - 2, ctx->scalars + 8);
       LAUNCHED(ctx);

@@ -57,6 +57,24 @@ def init_comm(rank, world):
     _lib.check(_lib.load().nimfm_comm_init(_lib.ctx(), rank, world, uid))
 
 
+def allgather_i64(values):
+    """[world, len(values)] int64 array of every rank's `values` (the library's communicator carries it)."""
+    import numpy as np
+    mine = np.ascontiguousarray(values, dtype=np.int64)
+    out = np.empty((world(), mine.size), dtype=np.int64)
+    _lib.check(_lib.load().nimfm_comm_allgather_i64(_lib.ctx(), _lib.ptr(mine), int(mine.size), _lib.ptr(out)))
+    return out
+
+
+def global_shape(X):
+    """(nSamples, nnz) summed over the ranks' shards -- what the reference's size rules
+    (minibatch_psgd.nim:157-165) see when X is the whole dataset."""
+    if world() == 1:
+        return int(X.nSamples), int(X.nnz)
+    g = allgather_i64([X.nSamples, X.nnz]).sum(axis=0)
+    return int(g[0]), int(g[1])
+
+
 def local_batch(mini_batch_size, rank, world):
     """Rows of a global minibatch processed by this rank (the global size is what coef divides by,
     minibatch_psgd.nim:73)."""

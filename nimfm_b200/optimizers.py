@@ -249,22 +249,30 @@ class SGD(_Base):
                           _lib.SCHED[self.scheduling], self.power)
         mbs = self.miniBatchSize
         world = 1
+        if self.nCalls > 0 and callback is not None:
+            raise NotImplementedError("nCalls > 0 (a callback inside the sample loop, sgd.nim:300-305) is not "
+                                      "supported: one library call runs a whole epoch; use nCalls <= 0")
         if maxThreads is not None and mbs == 1:
             mbs = 4096 if maxThreads < 0 else max(1, int(maxThreads))
+        if mbs == 1 and _dist.world() > 1:
+            raise ValueError("per-sample SGD is sequential and does not shard across ranks (replicas only); "
+                             "pass miniBatchSize > 1 or fit(..., maxThreads) for the synchronous-minibatch form")
         if mbs > 1:
             if X.windowed:
                 raise ValueError("minibatch SGD needs a resident dataset")
             mb_epoch = lib.nimfm_ffm_sgd_minibatch_epoch if is_ffm else lib.nimfm_fm_sgd_minibatch_epoch
-            # data parallel (distributed.init_comm): X is this rank's shard, mbs the GLOBAL minibatch
+            # data parallel (distributed.init_comm): X is this rank's shard, mbs the GLOBAL minibatch; the shares
+            # (and the shards) may be uneven -- the library agrees the schedule across ranks
             world = _dist.world()
-            if mbs % world:
-                raise ValueError("miniBatchSize must be a multiple of the number of ranks")
-            local = mbs // world
+            local = _dist.local_batch(mbs, _dist.rank(), world)
+            if local < 1:
+                raise ValueError("miniBatchSize is smaller than the number of ranks")
             begin = end = lambda *_: 0          # parameters stay canonical: no scaling caches to set up / fold in
             epoch = lambda c_, h_, x_, cfg_, it_, idx_, n_, v_, l_: mb_epoch(c_, h_, x_, cfg_, mbs, local, it_, idx_, n_,
                                                                             v_, l_)
         if not fm.warmStart:
             self.init()
+        n_glob = _dist.global_shape(X)[0] if world > 1 else n
         rng = self._rng(fm)
         indices = np.arange(n, dtype=np.int64)
         self._converged = False
@@ -287,7 +295,7 @@ class SGD(_Base):
                                      C.byref(viol), C.byref(lossSum)))
                 self.epoch_seconds.append(time.perf_counter() - t0)
                 self.it = it.value
-                runningLoss = lossSum.value / (n * world)      # minibatch form: the loss sum is all-reduced
+                runningLoss = lossSum.value / n_glob           # minibatch form: the loss sum is all-reduced
                 self.history.append((viol.value, runningLoss))
                 if callback is not None:
                     # finalize + transpose back before the user sees the model (sgd.nim:310-316)
@@ -347,6 +355,9 @@ class AdaGrad(_Base):
         # synchronous minibatch; the library all-reduces the per-minibatch deltas
         world = _dist.world()
         mbs = self.miniBatchSize
+        if self.nCalls > 0 and callback is not None:
+            raise NotImplementedError("nCalls > 0 (a callback inside the sample loop, adagrad.nim:170-181) is not "
+                                      "supported: one library call runs a whole epoch; use nCalls <= 0")
         if maxThreads is not None and mbs == 1:
             # fit(..., maxThreads) is the reference's Hogwild variant (adagrad_multi.nim:39-115: T lock-free
             # threads, every sample sees parameters up to ~T updates stale, results nondeterministic).  Its
@@ -357,6 +368,10 @@ class AdaGrad(_Base):
         local = _dist.local_batch(mbs, _dist.rank(), world)
         if local < 1:
             raise ValueError("miniBatchSize is smaller than the number of ranks")
+        if mbs == 1 and world > 1:
+            raise ValueError("per-sample AdaGrad is sequential and does not shard across ranks (replicas only); "
+                             "pass miniBatchSize > 1 or fit(..., maxThreads) for the synchronous-minibatch form")
+        n_glob = _dist.global_shape(X)[0] if world > 1 else n
         cfg = _lib.AdagradCfg(self.loss.kind, self.loss.threshold, self.eta0, self.alpha0, self.alpha,
                               self.beta, self.eps, local)
         if not fm.warmStart:                   # AdaGrad.init, adagrad.nim:47-62
@@ -394,7 +409,7 @@ class AdaGrad(_Base):
                                      C.byref(viol), C.byref(lossSum)))
                 self.epoch_seconds.append(time.perf_counter() - t0)
                 self.it = it.value
-                runningLoss = lossSum.value / (n * world)      # the loss sum is all-reduced; shards are even
+                runningLoss = lossSum.value / n_glob           # the loss sum is all-reduced over the shards
                 self.history.append((viol.value, runningLoss))
                 if callback is not None:
                     _lib.check(fin(ctx, h, C.byref(cfg), self.it))
@@ -579,13 +594,15 @@ class MBPSGD(_Base):
         self.it = 0                            # minibatch_psgd.nim:62
 
     def resolve_sizes(self, X):
-        """minibatch_psgd.nim:157-165"""
+        """minibatch_psgd.nim:157-165, on the GLOBAL shape: with a communicator X is this rank's shard and the
+        rule sees the sum of the shards, so every rank resolves the same sizes whatever its own share is"""
+        n, nnz = _dist.global_shape(X)
         mb = self.miniBatchSize
         if mb <= 0:
-            mb = max((X.nFeatures * X.nSamples) // X.nnz, 1)
+            mb = max((X.nFeatures * n) // nnz, 1)
         inner = self.maxIterInner
         if inner <= 0:
-            inner = max((X.nSamples - 1) // mb + 1, 1)
+            inner = max((n - 1) // mb + 1, 1)
         return mb, inner
 
     def fit(self, X, y, sfm, callback=None):
@@ -602,11 +619,8 @@ class MBPSGD(_Base):
         # data parallel (distributed.init_comm): X is this rank's shard, mb the GLOBAL minibatch; every
         # rank feeds its share of each minibatch and the library all-reduces grad P / w / b / loss
         local = _dist.local_batch(mb, _dist.rank(), _dist.world())
-        if _dist.world() > 1:
-            if local < 1:
-                raise ValueError("miniBatchSize is smaller than the number of ranks")
-            if self.maxIterInner <= 0:
-                inner = max((n - 1) // local + 1, 1)
+        if _dist.world() > 1 and local < 1:
+            raise ValueError("miniBatchSize is smaller than the number of ranks")
         # self.reg.initSGD(degree, nFeatures+nAugments, nComponents) (:172): SquaredL12 -- the default --
         # raises for degree != 2 whatever gamma is (squaredl12.nim:103-106)
         self.reg.initSGD(sfm.degree, X.nFeatures + sfm.nAugments, sfm.nComponents)
