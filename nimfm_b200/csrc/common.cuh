@@ -13,6 +13,7 @@
 struct ncclComm;
 
 #define NIMFM_MAX_DEGREE 6   // device row kernels are instantiated for degree 2..6
+#define NIMFM_MAX_RANKS 8    // ranks the peer-memory exchange is instantiated for (one NVSwitch box)
 
 struct nimfm_ctx {
   int device = 0;
@@ -65,8 +66,19 @@ struct nimfm_ctx {
   // communicator
   ncclComm *comm = nullptr;
   int rank = 0, nranks = 1;
-  struct CommBuf { void *ptr, *win; };
-  std::vector<CommBuf> commBufs;     // ncclMemAlloc'ed / window-registered buffers (nimfm_comm_alloc)
+  // NVLink peer memory (peer.cu): buffers that take part in the gradient exchange live in arenas whose IPC
+  // handles every rank has opened; arenas are recycled by size and released with the context
+  struct PeerArena {
+    double *base = nullptr;
+    size_t nDoubles = 0;
+    bool inUse = false;
+    double *peer[NIMFM_MAX_RANKS] = {nullptr};   // peer[rank] == base
+  };
+  std::vector<PeerArena> arenas;
+  bool peerOK = false;
+  uint32_t *peerFlags = nullptr;                 // [NIMFM_MAX_RANKS] arrival counters written by the peers
+  uint32_t *peerFlagsOf[NIMFM_MAX_RANKS] = {nullptr};
+  uint32_t barrierEpoch = 0;
 };
 
 struct nimfm_dataset {
@@ -190,8 +202,23 @@ struct MbSchedule {
 };
 // gathers (nRows, mb, it) of every rank; fails when the ranks disagree on `it` (their replicas have diverged)
 int nimfm_mb_schedule(nimfm_ctx *ctx, int64_t nRows, int64_t mb, int64_t it, MbSchedule *out);
-int nimfm_comm_alloc(nimfm_ctx *ctx, double **out, size_t nDoubles);
+// peer.cu
+int nimfm_peer_init(nimfm_ctx *ctx);
+void nimfm_peer_shutdown(nimfm_ctx *ctx);
+int nimfm_comm_alloc(nimfm_ctx *ctx, double **out, size_t nDoubles);   // COLLECTIVE when peer memory is on
 void nimfm_comm_free(nimfm_ctx *ctx, double *p);
+int nimfm_peer_allreduce_sum(nimfm_ctx *ctx, double *buf, int64_t n, int *done);
+struct MbpsgdStepArgs {   // Params.step (params.nim:90-98) + L1 prox on a flat slice of [P | w | b, epochLoss]
+  int64_t nP, d;
+  double negEtaP, rP, lam, negEtaW, rW, negEtaB, rB;
+  int reg, fitLinear, fitIntercept;
+};
+// reduce this rank's slice [lo, hi) of `grad` over all ranks, step `pool` there, write the slice into every
+// rank's pool (broadcast != 0) or only the local one; *done = 0 when the buffers are not peer-mapped
+int nimfm_peer_mbpsgd_step(nimfm_ctx *ctx, double *pool, double *grad, int64_t lo, int64_t hi, const MbpsgdStepArgs &sa,
+                           int broadcast, int *done);
+int nimfm_peer_broadcast_slice(nimfm_ctx *ctx, double *buf, int64_t lo, int64_t hi);
+int nimfm_peer_barrier(nimfm_ctx *ctx);
 
 // hot-column table upload (dataset.cu)
 int nimfm_upload_hot(nimfm_ctx *ctx, const std::vector<int32_t> &hot, int64_t d, uint8_t **hotSlot, int32_t **hotList);

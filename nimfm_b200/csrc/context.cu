@@ -17,10 +17,6 @@ typedef int (*fn_ncclCommInitRank)(ncclComm **, int, nimfm_ncclUniqueId, int);
 typedef int (*fn_ncclAllReduce)(const void *, void *, size_t, int, int, ncclComm *, cudaStream_t);
 typedef int (*fn_ncclReduceScatter)(const void *, void *, size_t, int, int, ncclComm *, cudaStream_t);
 typedef int (*fn_ncclAllGather)(const void *, void *, size_t, int, ncclComm *, cudaStream_t);
-typedef int (*fn_ncclMemAlloc)(void **, size_t);
-typedef int (*fn_ncclMemFree)(void *);
-typedef int (*fn_ncclCommWindowRegister)(ncclComm *, void *, size_t, void **, int);
-typedef int (*fn_ncclCommWindowDeregister)(ncclComm *, void *);
 typedef int (*fn_ncclCommDestroy)(ncclComm *);
 typedef const char *(*fn_ncclGetErrorString)(int);
 static struct {
@@ -30,10 +26,6 @@ static struct {
   fn_ncclAllReduce allReduce;
   fn_ncclReduceScatter reduceScatter;
   fn_ncclAllGather allGather;
-  fn_ncclMemAlloc memAlloc;                      // optional (NCCL >= 2.19)
-  fn_ncclMemFree memFree;
-  fn_ncclCommWindowRegister windowRegister;      // optional (NCCL >= 2.27): symmetric-memory collectives
-  fn_ncclCommWindowDeregister windowDeregister;
   fn_ncclCommDestroy commDestroy;
   fn_ncclGetErrorString errStr;
 } g_nccl;
@@ -48,10 +40,6 @@ static int load_nccl() {
   g_nccl.allReduce = (fn_ncclAllReduce)dlsym(h, "ncclAllReduce");
   g_nccl.reduceScatter = (fn_ncclReduceScatter)dlsym(h, "ncclReduceScatter");
   g_nccl.allGather = (fn_ncclAllGather)dlsym(h, "ncclAllGather");
-  g_nccl.memAlloc = (fn_ncclMemAlloc)dlsym(h, "ncclMemAlloc");
-  g_nccl.memFree = (fn_ncclMemFree)dlsym(h, "ncclMemFree");
-  g_nccl.windowRegister = (fn_ncclCommWindowRegister)dlsym(h, "ncclCommWindowRegister");
-  g_nccl.windowDeregister = (fn_ncclCommWindowDeregister)dlsym(h, "ncclCommWindowDeregister");
   g_nccl.commDestroy = (fn_ncclCommDestroy)dlsym(h, "ncclCommDestroy");
   g_nccl.errStr = (fn_ncclGetErrorString)dlsym(h, "ncclGetErrorString");
   if (!g_nccl.getUniqueId || !g_nccl.commInitRank || !g_nccl.allReduce || !g_nccl.commDestroy) return -1;
@@ -154,8 +142,9 @@ int32_t nimfm_ctx_create(int32_t device, nimfm_ctx **out) {
 int32_t nimfm_ctx_destroy(nimfm_ctx *ctx) {
   if (!ctx) return NIMFM_OK;
   cudaSetDevice(ctx->device);
-  if (ctx->comm && g_nccl.commDestroy) g_nccl.commDestroy(ctx->comm);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  nimfm_peer_shutdown(ctx);
+  if (ctx->comm && g_nccl.commDestroy) g_nccl.commDestroy(ctx->comm);
   cudaFree(ctx->partials);
   cudaFree(ctx->scalars);
   cudaFree(ctx->idxScratch);
@@ -242,7 +231,7 @@ int32_t nimfm_comm_init(nimfm_ctx *ctx, int32_t rank, int32_t nranks, const void
   memcpy(&id, uid128, 128);
   int rc = g_nccl.commInitRank(&ctx->comm, nranks, id, rank);
   if (rc != 0) return nimfm_fail(ctx, NIMFM_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.errStr ? g_nccl.errStr(rc) : "?");
-  return NIMFM_OK;
+  return nimfm_peer_init(ctx);   // NVLink peer-memory exchange (falls back to NCCL when the GPUs cannot map each other)
 }
 
 int32_t nimfm_comm_size(const nimfm_ctx *ctx) { return ctx ? ctx->nranks : 0; }
@@ -274,6 +263,11 @@ int32_t nimfm_timer_stop(nimfm_ctx *ctx, float *ms) {
 
 int nimfm_allreduce_sum(nimfm_ctx *ctx, double *buf, int64_t n) {
   if (ctx->nranks == 1) return NIMFM_OK;
+  {   // buffers that live in a peer-mapped arena are reduced over NVLink peer memory (peer.cu), in a fixed rank order
+    int done = 0;
+    int rc = nimfm_peer_allreduce_sum(ctx, buf, n, &done);
+    if (rc || done) return rc;
+  }
   if (!ctx->comm) return nimfm_fail(ctx, NIMFM_ERR_NCCL, "communicator not initialised (nimfm_comm_init)");
   int rc = g_nccl.allReduce(buf, buf, (size_t)n, /*ncclDouble*/ 8, /*ncclSum*/ 0, ctx->comm, ctx->stream);
   if (rc != 0) return nimfm_fail(ctx, NIMFM_ERR_NCCL, "ncclAllReduce: %s", g_nccl.errStr ? g_nccl.errStr(rc) : "?");
@@ -340,42 +334,6 @@ int nimfm_mb_schedule(nimfm_ctx *ctx, int64_t nRows, int64_t mb, int64_t it, MbS
   for (int r = 0; r < R; r++)
     out->T = std::max(out->T, (out->nRows[(size_t)r] + out->mb[(size_t)r] - 1) / out->mb[(size_t)r]);
   return NIMFM_OK;
-}
-
-// Buffers that take part in collectives.  With NIMFM_NCCL_SYMMETRIC=1 (and an NCCL that has it) they come from
-// ncclMemAlloc and are registered as symmetric windows on the communicator, which lets NCCL run its
-// symmetric-memory / NVLS kernels without staging copies; otherwise plain cudaMalloc.  Collective: when the
-// symmetric route is on, every rank must allocate the same sequence of buffers (the solvers do).
-int nimfm_comm_alloc(nimfm_ctx *ctx, double **out, size_t nDoubles) {
-  *out = nullptr;
-  const char *env = getenv("NIMFM_NCCL_SYMMETRIC");
-  const bool sym = env && env[0] == '1' && ctx->comm && g_nccl.memAlloc && g_nccl.memFree;
-  if (sym) {
-    void *p = nullptr;
-    if (g_nccl.memAlloc(&p, nDoubles * 8) == 0 && p) {
-      void *win = nullptr;
-      if (g_nccl.windowRegister && g_nccl.windowRegister(ctx->comm, p, nDoubles * 8, &win, /*NCCL_WIN_COLL_SYMMETRIC*/ 1) != 0)
-        win = nullptr;
-      ctx->commBufs.push_back({p, win});
-      *out = static_cast<double *>(p);
-      return NIMFM_OK;
-    }
-  }
-  CK(cudaMalloc(out, nDoubles * 8));
-  return NIMFM_OK;
-}
-
-void nimfm_comm_free(nimfm_ctx *ctx, double *p) {
-  if (!p) return;
-  if (ctx)
-    for (size_t i = 0; i < ctx->commBufs.size(); i++)
-      if (ctx->commBufs[i].ptr == p) {
-        if (ctx->commBufs[i].win && g_nccl.windowDeregister && ctx->comm) g_nccl.windowDeregister(ctx->comm, ctx->commBufs[i].win);
-        if (g_nccl.memFree) g_nccl.memFree(p);
-        ctx->commBufs.erase(ctx->commBufs.begin() + (long)i);
-        return;
-      }
-  cudaFree(p);
 }
 
 int nimfm_ensure_partials(nimfm_ctx *ctx, size_t nDoubles) {

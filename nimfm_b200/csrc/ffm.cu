@@ -445,7 +445,7 @@ int32_t nimfm_ffm_create(nimfm_ctx *ctx, int32_t nComponents, int64_t nFields, i
   CK(cudaMalloc(&m->P, (size_t)nP * 8));
   CK(cudaMalloc(&m->w, (size_t)m->d * 8));
   CK(cudaMalloc(&m->b, 8 * 8));
-  CK(cudaMalloc(&m->grad, (size_t)(nP + m->d + 2) * 8));
+  { int rca = nimfm_comm_alloc(ctx, &m->grad, (size_t)(nP + m->d + 2)); if (rca) { nimfm_ffm_free(ctx, m); return rca; } }
   CK(cudaMemsetAsync(m->P, 0, (size_t)nP * 8, ctx->stream));
   CK(cudaMemsetAsync(m->w, 0, (size_t)m->d * 8, ctx->stream));
   CK(cudaMemsetAsync(m->b, 0, 64, ctx->stream));
@@ -458,10 +458,12 @@ int32_t nimfm_ffm_create(nimfm_ctx *ctx, int32_t nComponents, int64_t nFields, i
 int32_t nimfm_ffm_free(nimfm_ctx *ctx, nimfm_ffm *m) {
   if (!m) return NIMFM_OK;
   if (ctx) cudaSetDevice(ctx->device);
-  for (double *p : {m->P, m->w, m->b, m->grad, m->gsP, m->gnP, m->gsw, m->gnw, m->dG, m->adaScal, m->scalingsP,
+  nimfm_comm_free(ctx, m->grad);
+  nimfm_comm_free(ctx, m->dG);
+  nimfm_comm_free(ctx, m->sgdCnt);
+  for (double *p : {m->P, m->w, m->b, m->gsP, m->gnP, m->gsw, m->gnw, m->adaScal, m->scalingsP,
                     m->scalingsW, m->sgdScal})
     cudaFree(p);
-  cudaFree(m->sgdCnt);
   delete m;
   return NIMFM_OK;
 }
@@ -635,7 +637,7 @@ int32_t nimfm_ffm_adagrad_init(nimfm_ctx *ctx, nimfm_ffm *m, double eps, int32_t
     CK(cudaMalloc(&m->gnP, (size_t)nP * 8));
     CK(cudaMalloc(&m->gsw, (size_t)d * 8));
     CK(cudaMalloc(&m->gnw, (size_t)d * 8));
-    CK(cudaMalloc(&m->dG, (size_t)(2 * nP + 3 * d + 8) * 8));
+    { int rca = nimfm_comm_alloc(ctx, &m->dG, (size_t)(2 * nP + 3 * d + 8)); if (rca) return rca; }
     CK(cudaMalloc(&m->adaScal, 64));
   }
   if (fresh || reset) {

@@ -244,11 +244,12 @@ int32_t nimfm_fm_free(nimfm_ctx *ctx, nimfm_fm *fm) {
   if (ctx) cudaSetDevice(ctx->device);
   nimfm_comm_free(ctx, fm->pool);   // P, w, b
   nimfm_comm_free(ctx, fm->grad);
-  for (double *p : {fm->lams, fm->gsP, fm->gnP, fm->gsw, fm->gnw, fm->dG,
+  nimfm_comm_free(ctx, fm->dG);
+  nimfm_comm_free(ctx, fm->sgdCnt);
+  for (double *p : {fm->lams, fm->gsP, fm->gnP, fm->gsw, fm->gnw,
                     fm->adaScal, fm->scalingsP, fm->scalingsW, fm->sgdScal, fm->Pcm, fm->yPred, fm->Acache,
                     fm->colNormSq, fm->cdScal, fm->proxState, fm->psgdThr})
     cudaFree(p);
-  cudaFree(fm->sgdCnt);
   cudaFree(fm->lazyInv);
   cudaFree(fm->lazyFlag);
   delete fm;
@@ -709,17 +710,22 @@ int32_t nimfm_fm_mbpsgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset 
       return NIMFM_OK;
     }
   }
-  // ---- multi-rank, sharded step (the alternative to "identical dense step on every GPU"): the
-  // gradient pool is reduce-scattered, every rank steps (and proxes) its flat 1/N slice of [P | w | b], and the
-  // parameter pool is all-gathered in place.  Same bytes on the fabric as the all-reduce, 1/N of the dense pass.
-  // The column-wise SquaredL12 prox needs sums over all features and keeps the all-reduce route.
+  // ---- multi-rank, sharded step (the alternative to "identical dense step on every GPU"): every rank
+  // owns a flat 1/N slice of [P | w | b]; the gradient pool is reduced slice-wise, the owner steps (and proxes) its
+  // slice, and the slice is distributed to all ranks.  Over NVLink peer memory (peer.cu) that is ONE kernel between
+  // two flag barriers -- reduce out of every peer's gradient pool, Params.step + L1 prox, stores into every peer's
+  // parameter pool -- in a fixed rank order; without peer mapping (NIMFM_PEER=0, no P2P) NCCL carries it as an
+  // all-reduce + the dense step everywhere, or (NIMFM_MBPSGD_SHARDED=1) reduce-scatter -> slice step -> all-gather.
+  // The column-wise SquaredL12 prox needs sums over all features and keeps the all-reduce + dense step.
   int64_t sliceC = 0;
+  bool viaPeer = false;
   {
-    const char *env = getenv("NIMFM_MBPSGD_SHARDED");
+    const char *envS = getenv("NIMFM_MBPSGD_SHARDED");
     const int64_t SB8 = (int64_t)fm->nOrders * fm->k, align = (SB8 & 1) ? 2 * SB8 : SB8;
     const int64_t c = ((nG + ctx->nranks - 1) / ctx->nranks + align - 1) / align * align;
-    if (ctx->nranks > 1 && cfg->reg != NIMFM_REG_SQUAREDL12 && !(env && env[0] == '0') && c * ctx->nranks <= fm->poolCap)
-      sliceC = c;
+    const bool fits = ctx->nranks > 1 && cfg->reg != NIMFM_REG_SQUAREDL12 && c * ctx->nranks <= fm->poolCap;
+    viaPeer = fits && ctx->peerOK && !(envS && envS[0] == '0');
+    if (viaPeer || (fits && envS && envS[0] == '1')) sliceC = c;
   }
   if (sliceC) CK(cudaMemsetAsync(fm->b + 1, 0, 8, ctx->stream));   // epoch loss slot of the parameter pool
   for (int64_t inner = 0; inner < cfg->maxIterInner; inner++) {
@@ -729,30 +735,48 @@ int32_t nimfm_fm_mbpsgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset 
     add_tail_kernel<<<1, 1, 0, ctx->stream>>>(fm->grad + nG - 2, ctx->scalars + 8);
     LAUNCHED(ctx);
     if (sliceC) {
-      if ((rc = nimfm_reduce_scatter_sum(ctx, fm->grad, sliceC))) return rc;
       const double etaP = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->beta, *it);
       const double etaW = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->alpha, *it);
       const double etaB = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->alpha0, *it);
       const double rP = 1.0 / (1.0 + etaP * cfg->beta), rW = 1.0 / (1.0 + etaW * cfg->alpha),
                    rB = 1.0 / (1.0 + etaB * cfg->alpha0);
       const double lam = cfg->gamma * etaP / (1.0 + etaP * cfg->beta);
-      const int64_t lo = (int64_t)ctx->rank * sliceC, hi = std::min(lo + sliceC, nG);
-      if (hi > lo) {
-        mbpsgd_step_flat_kernel<<<ew_grid(ctx, hi - lo), 256, 0, ctx->stream>>>(
-            fm->pool, fm->grad, lo, hi, nP, d, -etaP, rP, cfg->reg, lam, -etaW, rW, fm->fitLinear, -etaB, rB,
-            fm->fitIntercept);
+      const int64_t lo = std::min(nG, (int64_t)ctx->rank * sliceC), hi = std::min(lo + sliceC, nG);
+      const bool rowProx = (cfg->reg == NIMFM_REG_L21 || cfg->reg == NIMFM_REG_SQUAREDL12_ROWS) && lam != 0.0;
+      if (rowProx && fm->k > 32 * NIMFM_PROX_MAXE)
+        return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "row-wise prox supports nComponents <= %d", 32 * NIMFM_PROX_MAXE);
+      auto prox_slice = [&]() {   // whole (feature, order) vectors: slices start at multiples of nOrders*k
+        if (!rowProx || lo >= nP) return;
+        const int64_t vecs = (std::min(hi, nP) - lo) / fm->k;
+        prox_rows_kernel<<<ew_grid(ctx, vecs * 32), 256, 0, ctx->stream>>>(fm->pool + lo, vecs, fm->k, lam, cfg->reg);
         LAUNCHED(ctx);
-        // row-wise prox on the slice's whole (feature, order) vectors (slices start at multiples of nOrders*k)
-        if ((cfg->reg == NIMFM_REG_L21 || cfg->reg == NIMFM_REG_SQUAREDL12_ROWS) && lam != 0.0 && lo < nP) {
-          if (fm->k > 32 * NIMFM_PROX_MAXE)
-            return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "row-wise prox supports nComponents <= %d", 32 * NIMFM_PROX_MAXE);
-          const int64_t vecs = (std::min(hi, nP) - lo) / fm->k;
-          prox_rows_kernel<<<ew_grid(ctx, vecs * 32), 256, 0, ctx->stream>>>(fm->pool + lo, vecs, fm->k, lam, cfg->reg);
-          LAUNCHED(ctx);
+      };
+      int done = 0;
+      if (viaPeer) {
+        MbpsgdStepArgs sa{nP, d, -etaP, rP, lam, -etaW, rW, -etaB, rB, cfg->reg, fm->fitLinear, fm->fitIntercept};
+        if ((rc = nimfm_peer_mbpsgd_step(ctx, fm->pool, fm->grad, lo, hi, sa, rowProx ? 0 : 1, &done))) return rc;
+        if (done) {
+          if (rowProx) {
+            prox_slice();
+            if ((rc = nimfm_peer_broadcast_slice(ctx, fm->pool, lo, hi))) return rc;
+          }
+          if ((rc = nimfm_peer_barrier(ctx))) return rc;   // all slices have landed; all peers are done reading my gradients
         }
       }
-      if ((rc = nimfm_allgather_inplace(ctx, fm->pool, sliceC))) return rc;
-      CK(cudaMemsetAsync(fm->grad, 0, (size_t)(sliceC * ctx->nranks) * 8, ctx->stream));
+      if (!done) {
+        if ((rc = nimfm_reduce_scatter_sum(ctx, fm->grad, sliceC))) return rc;
+        if (hi > lo) {
+          mbpsgd_step_flat_kernel<<<ew_grid(ctx, hi - lo), 256, 0, ctx->stream>>>(
+              fm->pool, fm->grad, lo, hi, nP, d, -etaP, rP, cfg->reg, lam, -etaW, rW, fm->fitLinear, -etaB, rB,
+              fm->fitIntercept);
+          LAUNCHED(ctx);
+          prox_slice();
+        }
+        if ((rc = nimfm_allgather_inplace(ctx, fm->pool, sliceC))) return rc;
+      }
+      // grads <- 0 by a kernel, not a memset: its stores leave the lines in L2 for the next minibatch's REDs
+      fill_kernel<<<ew_grid(ctx, sliceC * ctx->nranks), 256, 0, ctx->stream>>>(fm->grad, sliceC * ctx->nranks, 0.0);
+      LAUNCHED(ctx);
       *it += 1;
       cur = (cur + localBatch) % X->n;
       continue;
@@ -884,7 +908,7 @@ int32_t nimfm_fm_adagrad_init(nimfm_ctx *ctx, nimfm_fm *fm, double eps, int32_t 
     CK(cudaMalloc(&fm->gnP, (size_t)nP * 8));
     CK(cudaMalloc(&fm->gsw, (size_t)d * 8));
     CK(cudaMalloc(&fm->gnw, (size_t)d * 8));
-    CK(cudaMalloc(&fm->dG, (size_t)(2 * nP + 2 * d + dd + 8) * 8));
+    { int rca = nimfm_comm_alloc(ctx, &fm->dG, (size_t)(2 * nP + 2 * d + dd + 8)); if (rca) return rca; }
     CK(cudaMalloc(&fm->adaScal, 8 * 8));
   }
   if (fresh || reset) {   // AdaGrad.init, :47-55

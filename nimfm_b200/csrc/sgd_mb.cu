@@ -137,7 +137,7 @@ int sgd_mb_epoch(nimfm_ctx *ctx, const MbModel &M, const nimfm_dataset *X, const
     idxDev = ctx->idx32Scratch;
   }
   if (!*M.cnt) {
-    CK(cudaMalloc(M.cnt, (size_t)std::max<int64_t>(M.dd, 1) * 8));
+    if ((rc = nimfm_comm_alloc(ctx, M.cnt, (size_t)std::max<int64_t>(M.dd, 2)))) return rc;
     CK(cudaMemsetAsync(*M.cnt, 0, (size_t)std::max<int64_t>(M.dd, 1) * 8, ctx->stream));
   }
   double *cnt = *M.cnt;
