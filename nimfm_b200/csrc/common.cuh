@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <initializer_list>
 #include <string>
 #include <vector>
 
@@ -71,10 +72,22 @@ struct nimfm_ctx {
   struct PeerArena {
     double *base = nullptr;
     size_t nDoubles = 0;
-    bool inUse = false;
-    double *peer[NIMFM_MAX_RANKS] = {nullptr};   // peer[rank] == base
+    bool inUse = false, haveHandle = false;
+    int64_t handle[8] = {0};                     // cudaIpcMemHandle_t of base
+  };
+  struct PeerOpened {                            // a peer's arena this rank has mapped (cached by handle)
+    int rank = 0;
+    int64_t handle[8] = {0};
+    double *ptr = nullptr;
+  };
+  struct PeerMap {                               // one buffer of the running epoch call: every rank's copy
+    double *local = nullptr;
+    int64_t nDoubles = 0;
+    double *peer[NIMFM_MAX_RANKS] = {nullptr};
   };
   std::vector<PeerArena> arenas;
+  std::vector<PeerOpened> peerOpened;
+  std::vector<PeerMap> peerMaps;
   bool peerOK = false;
   uint32_t *peerFlags = nullptr;                 // [NIMFM_MAX_RANKS] arrival counters written by the peers
   uint32_t *peerFlagsOf[NIMFM_MAX_RANKS] = {nullptr};
@@ -205,8 +218,20 @@ int nimfm_mb_schedule(nimfm_ctx *ctx, int64_t nRows, int64_t mb, int64_t it, MbS
 // peer.cu
 int nimfm_peer_init(nimfm_ctx *ctx);
 void nimfm_peer_shutdown(nimfm_ctx *ctx);
-int nimfm_comm_alloc(nimfm_ctx *ctx, double **out, size_t nDoubles);   // COLLECTIVE when peer memory is on
+int nimfm_comm_alloc(nimfm_ctx *ctx, double **out, size_t nDoubles);   // local; arena memory when peer memory is on
 void nimfm_comm_free(nimfm_ctx *ctx, double *p);
+int nimfm_peer_prepare(nimfm_ctx *ctx, const double *const *bufs, int nb);   // COLLECTIVE, per epoch-level call
+void nimfm_peer_release(nimfm_ctx *ctx);
+struct PeerScope {   // prepare on entry, release on every exit path
+  nimfm_ctx *ctx;
+  int rc;
+  PeerScope(nimfm_ctx *c, std::initializer_list<const double *> bufs) : ctx(c), rc(0) {
+    bool any = false;   // no buffer to exchange (e.g. allreduce = 0): not a collective call, nothing to prepare
+    for (const double *b : bufs) any = any || b != nullptr;
+    if (c->nranks > 1 && any) rc = nimfm_peer_prepare(c, bufs.begin(), (int)bufs.size());
+  }
+  ~PeerScope() { nimfm_peer_release(ctx); }
+};
 int nimfm_peer_allreduce_sum(nimfm_ctx *ctx, double *buf, int64_t n, int *done);
 struct MbpsgdStepArgs {   // Params.step (params.nim:90-98) + L1 prox on a flat slice of [P | w | b, epochLoss]
   int64_t nP, d;

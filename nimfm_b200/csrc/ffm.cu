@@ -574,6 +574,8 @@ int32_t nimfm_ffm_loss_grad(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_dataset *X
   REQUIRE(nRows >= 0 && miniBatchSize >= 1, "bad nRows / miniBatchSize");
   REQUIRE(rowIdx != nullptr || (rowBegin >= 0 && (rowBegin < X->n || nRows == 0)), "rowBegin out of range");
   const int64_t nG = m->nP() + m->d + 2;
+  PeerScope peers(ctx, {allreduce ? m->grad : nullptr});
+  if (peers.rc) return peers.rc;
   if (zeroGrads) CK(cudaMemsetAsync(m->grad, 0, (size_t)nG * 8, ctx->stream));
   const int32_t *idxDev = nullptr;
   if (rowIdx && nRows > 0) {
@@ -684,6 +686,8 @@ int32_t nimfm_ffm_adagrad_epoch(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_datase
   const int64_t mb = cfg->miniBatchSize;
   MbSchedule sch;
   if ((rc = nimfm_mb_schedule(ctx, nRows, mb, *it, &sch))) return rc;
+  PeerScope peers(ctx, {m->dG});
+  if (peers.rc) return peers.rc;
   for (int64_t t = 0; t < sch.T; t++) {
     const int64_t start = std::min(t * mb, nRows);
     const int64_t cnt = sch.local(t);   // 0 once this rank's (shorter) shard is used up: it still joins the collectives

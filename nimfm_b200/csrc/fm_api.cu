@@ -467,6 +467,8 @@ int32_t nimfm_fm_loss_grad(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X,
   REQUIRE(nRows >= 0 && miniBatchSize >= 1, "bad nRows / miniBatchSize");
   REQUIRE(rowIdx != nullptr || (rowBegin >= 0 && (rowBegin < X->n || nRows == 0)), "rowBegin out of range");
   const int64_t nG = fm->nP() + fm->d + 2;
+  PeerScope peers(ctx, {allreduce ? fm->grad : nullptr});   // collective when a communicator exists: all ranks call together
+  if (peers.rc) return peers.rc;
   if (zeroGrads) CK(cudaMemsetAsync(fm->grad, 0, (size_t)nG * 8, ctx->stream));
   const int32_t *idxDev = nullptr;
   if (rowIdx && nRows > 0) {
@@ -628,6 +630,8 @@ int32_t nimfm_fm_mbpsgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset 
             (long long)cfg->miniBatchSize);
   }
   const int64_t nP = fm->nP(), d = fm->d, nG = nP + d + 2;
+  PeerScope peers(ctx, {fm->grad, fm->pool});
+  if (peers.rc) return peers.rc;
   const int64_t total = localBatch * cfg->maxIterInner;
   const int32_t *idxDev = nullptr;
   if (sampleIdx) {
@@ -985,6 +989,8 @@ int32_t nimfm_fm_adagrad_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset
   }
   MbSchedule sch;
   if ((rc = nimfm_mb_schedule(ctx, nRows, mb, *it, &sch))) return rc;
+  PeerScope peers(ctx, {fm->dG});
+  if (peers.rc) return peers.rc;
   for (int64_t t = 0; t < sch.T; t++) {
     const int64_t start = std::min(t * mb, nRows);
     const int64_t cnt = sch.local(t);   // 0 once this rank's (shorter) shard is used up: it still joins the collectives
@@ -1243,6 +1249,8 @@ static int stream_host_rows(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t
   REQUIRE(nRows >= 0 && miniBatchSize >= 1, "bad nRows / miniBatchSize");
   if (chunkRows <= 0) chunkRows = 1 << 17;   // 84 MB per chunk at 39 nnz/row: short pipeline ramp and tail
   const int64_t nG = fm->nP() + fm->d + 2;
+  PeerScope peers(ctx, {(!predict && allreduce) ? fm->grad : nullptr});
+  if (peers.rc) return peers.rc;
   if (zeroGrads && !predict) CK(cudaMemsetAsync(fm->grad, 0, (size_t)nG * 8, ctx->stream));
   int *bad = reinterpret_cast<int *>(ctx->scalars + 60);
   CK(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));

@@ -3,8 +3,9 @@
 // "ncclAllReduce, then the identical dense step on every GPU" schedule of SURVEY 8e).
 //
 // Every buffer that takes part in the exchange (gradient pool, parameter pool, AdaGrad delta block, touch
-// counts) lives in an ARENA whose CUDA IPC handle every rank has opened, so a kernel on rank r can read and
-// write the same buffer of every peer directly.  One exchange is
+// counts) lives in an ARENA; at the start of an epoch-level call the ranks swap the CUDA IPC handles of the
+// arenas the call will exchange (nimfm_peer_prepare: one small gather, mappings cached), so a kernel on rank r
+// can read and write the corresponding buffer of every peer directly.  One exchange is
 //     barrier  ->  reduce kernel  ->  barrier
 // where the reduce kernel, on rank r, walks ITS 1/N slice of the buffer: 16-byte loads of the slice out of all
 // N ranks' buffers (N loads in flight per element pair), a sum in rank order 0..N-1 (so the result is
@@ -139,61 +140,36 @@ __global__ void __launch_bounds__(256) peer_broadcast_kernel(const double *src, 
   }
 }
 
+// the prepared table of the running epoch call: local range -> every rank's pointer to ITS buffer of that role
 bool lookup(const nimfm_ctx *ctx, const double *ptr, int64_t n, PeerPtrs *out) {
-  for (const auto &a : ctx->arenas) {
-    if (ptr >= a.base && ptr + n <= a.base + a.nDoubles) {
-      const int64_t off = ptr - a.base;
-      for (int r = 0; r < ctx->nranks; r++) out->p[r] = a.peer[r] + off;
+  for (const auto &m : ctx->peerMaps) {
+    if (ptr >= m.local && ptr + n <= m.local + m.nDoubles) {
+      const int64_t off = ptr - m.local;
+      for (int r = 0; r < ctx->nranks; r++) out->p[r] = m.peer[r] + off;
       return true;
     }
   }
   return false;
 }
 
-// every rank's handle for `base` -> peer pointers; ok = 0 on ANY rank makes the whole call fail on every rank
-int exchange_open(nimfm_ctx *ctx, void *base, int ok, void **peerOut, bool *allOk) {
-  const int R = ctx->nranks;
-  int64_t mine[9] = {0};
-  cudaIpcMemHandle_t h;
-  if (ok && cudaIpcGetMemHandle(&h, base) != cudaSuccess) {
-    cudaGetLastError();
-    ok = 0;
-  }
-  if (ok) memcpy(mine, &h, sizeof(h));
+// open (or find in the cache) rank r's allocation with this IPC handle
+double *open_peer(nimfm_ctx *ctx, int r, const int64_t *handle8) {
+  for (const auto &o : ctx->peerOpened)
+    if (o.rank == r && !memcmp(o.handle, handle8, 64)) return o.ptr;
+  cudaIpcMemHandle_t hp;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-  mine[8] = ok;
-  std::vector<int64_t> all((size_t)9 * R);
-  int rc = nimfm_allgather_host_i64(ctx, mine, 9, all.data());
-  if (rc) return rc;
-  bool good = true;
-  for (int r = 0; r < R; r++) good = good && all[(size_t)9 * r + 8] != 0;
-  int opened = good ? 1 : 0;
-  if (good) {
-    for (int r = 0; r < R; r++) {
-      if (r == ctx->rank) { peerOut[r] = base; continue; }
-      cudaIpcMemHandle_t hp;
-      memcpy(&hp, &all[(size_t)9 * r], sizeof(hp));
-      if (cudaIpcOpenMemHandle(&peerOut[r], hp, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-        cudaGetLastError();
-        peerOut[r] = nullptr;
-        opened = 0;
-      }
-    }
+  memcpy(&hp, handle8, sizeof(hp));
+  void *p = nullptr;
+  if (cudaIpcOpenMemHandle(&p, hp, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
   }
-  // second round: did every rank manage to map every peer?
-  const int64_t st[1] = {opened};
-  std::vector<int64_t> sts((size_t)R);
-  if ((rc = nimfm_allgather_host_i64(ctx, st, 1, sts.data()))) return rc;
-  bool every = true;
-  for (int r = 0; r < R; r++) every = every && sts[(size_t)r] != 0;
-  if (!every)
-    for (int r = 0; r < R; r++)
-      if (r != ctx->rank && good && peerOut[r]) {
-        cudaIpcCloseMemHandle(peerOut[r]);
-        peerOut[r] = nullptr;
-      }
-  *allOk = every;
-  return NIMFM_OK;
+  nimfm_ctx::PeerOpened o;
+  o.rank = r;
+  memcpy(o.handle, handle8, 64);
+  o.ptr = static_cast<double *>(p);
+  ctx->peerOpened.push_back(o);
+  return o.ptr;
 }
 
 template <class F>
@@ -233,46 +209,50 @@ int nimfm_peer_init(nimfm_ctx *ctx) {
   ctx->peerOK = false;
   const char *env = getenv("NIMFM_PEER");
   if (ctx->nranks < 2 || ctx->nranks > NIMFM_MAX_RANKS || (env && env[0] == '0')) return NIMFM_OK;
-  int ok = 1;
-  if (cudaMalloc(&ctx->peerFlags, 4096) != cudaSuccess || cudaMemset(ctx->peerFlags, 0, 4096) != cudaSuccess ||
-      cudaDeviceSynchronize() != cudaSuccess) {
+  // the flag array: exchanged once, here (comm_init is collective by definition)
+  int64_t mine[9] = {0};
+  cudaIpcMemHandle_t h;
+  if (cudaMalloc(&ctx->peerFlags, 4096) == cudaSuccess && cudaMemset(ctx->peerFlags, 0, 4096) == cudaSuccess &&
+      cudaDeviceSynchronize() == cudaSuccess && cudaIpcGetMemHandle(&h, ctx->peerFlags) == cudaSuccess) {
+    memcpy(mine, &h, sizeof(h));
+    mine[8] = 1;
+  } else {
     cudaGetLastError();
-    ok = 0;
   }
-  void *peers[NIMFM_MAX_RANKS] = {nullptr};
-  bool all = false;
-  int rc = exchange_open(ctx, ctx->peerFlags, ok, peers, &all);
+  const int R = ctx->nranks;
+  std::vector<int64_t> all((size_t)9 * R);
+  int rc = nimfm_allgather_host_i64(ctx, mine, 9, all.data());
   if (rc) return rc;
-  if (!all) {   // e.g. no P2P between the GPUs of this box: the NCCL route stays in charge
-    cudaFree(ctx->peerFlags);
-    ctx->peerFlags = nullptr;
-    return NIMFM_OK;
-  }
-  for (int r = 0; r < ctx->nranks; r++) ctx->peerFlagsOf[r] = static_cast<uint32_t *>(peers[r]);
-  ctx->peerOK = true;
+  int64_t opened = 1;
+  for (int r = 0; r < R; r++) opened = opened && all[(size_t)9 * r + 8];
+  if (opened)
+    for (int r = 0; r < R; r++) {
+      ctx->peerFlagsOf[r] = r == ctx->rank ? ctx->peerFlags : reinterpret_cast<uint32_t *>(open_peer(ctx, r, &all[(size_t)9 * r]));
+      if (!ctx->peerFlagsOf[r]) opened = 0;
+    }
+  std::vector<int64_t> sts((size_t)R);
+  if ((rc = nimfm_allgather_host_i64(ctx, &opened, 1, sts.data()))) return rc;   // did EVERY rank map every peer?
+  bool every = true;
+  for (int r = 0; r < R; r++) every = every && sts[(size_t)r] != 0;
+  ctx->peerOK = every;   // false: e.g. no P2P between the GPUs of this box -- the NCCL route stays in charge
   ctx->barrierEpoch = 0;
   return NIMFM_OK;
 }
 
 void nimfm_peer_shutdown(nimfm_ctx *ctx) {
-  for (auto &a : ctx->arenas) {
-    for (int r = 0; r < ctx->nranks; r++)
-      if (r != ctx->rank && a.peer[r]) cudaIpcCloseMemHandle(a.peer[r]);
-    cudaFree(a.base);
-  }
+  for (auto &o : ctx->peerOpened) cudaIpcCloseMemHandle(o.ptr);
+  ctx->peerOpened.clear();
+  ctx->peerMaps.clear();
+  for (auto &a : ctx->arenas) cudaFree(a.base);
   ctx->arenas.clear();
-  if (ctx->peerFlags) {
-    for (int r = 0; r < ctx->nranks; r++)
-      if (r != ctx->rank && ctx->peerFlagsOf[r]) cudaIpcCloseMemHandle(ctx->peerFlagsOf[r]);
-    cudaFree(ctx->peerFlags);
-    ctx->peerFlags = nullptr;
-  }
+  if (ctx->peerFlags) cudaFree(ctx->peerFlags);
+  ctx->peerFlags = nullptr;
   ctx->peerOK = false;
 }
 
-// Buffers that take part in the exchange.  With peer memory on this is COLLECTIVE: every rank must allocate the
-// same sequence of sizes (the solvers do -- they run the same code on every rank).  Freed arenas are kept and
-// recycled by size: an exporter must not free memory its peers still have mapped.
+// Buffers that may take part in an exchange.  LOCAL (not collective: a rank may create models the others do not,
+// e.g. CD on rank 0).  With peer memory on, the memory comes from arenas that are recycled by size and released
+// only with the context: an exporter must not free memory a peer may still have mapped.
 int nimfm_comm_alloc(nimfm_ctx *ctx, double **out, size_t nDoubles) {
   *out = nullptr;
   if (!ctx->peerOK) {
@@ -287,21 +267,7 @@ int nimfm_comm_alloc(nimfm_ctx *ctx, double **out, size_t nDoubles) {
     }
   nimfm_ctx::PeerArena a;
   a.nDoubles = nDoubles;
-  int ok = 1;
-  if (cudaMalloc(&a.base, nDoubles * 8) != cudaSuccess) {
-    cudaGetLastError();
-    a.base = nullptr;
-    ok = 0;
-  }
-  void *peers[NIMFM_MAX_RANKS] = {nullptr};
-  bool all = false;
-  int rc = exchange_open(ctx, a.base, ok, peers, &all);
-  if (rc) { cudaFree(a.base); return rc; }
-  if (!all) {
-    cudaFree(a.base);
-    return nimfm_fail(ctx, NIMFM_ERR_CUDA, "peer-mapped allocation of %zu bytes failed on some rank", nDoubles * 8);
-  }
-  for (int r = 0; r < ctx->nranks; r++) a.peer[r] = static_cast<double *>(peers[r]);
+  CK(cudaMalloc(&a.base, nDoubles * 8));
   a.inUse = true;
   ctx->arenas.push_back(a);
   *out = a.base;
@@ -318,6 +284,65 @@ void nimfm_comm_free(nimfm_ctx *ctx, double *p) {
       }
   cudaFree(p);
 }
+
+// COLLECTIVE, once per epoch-level library call: every rank names the buffers the call will exchange (same
+// roles in the same order on every rank); the ranks swap the IPC handles of the arenas those buffers live in and
+// (re)open what they have not mapped yet.  A buffer that is not arena memory on some rank, or that some rank
+// cannot map, is left to NCCL by ALL ranks (everybody sees the same gathered table).  The table is valid until
+// nimfm_peer_release -- the exchanges below find their peers' pointers in it.
+int nimfm_peer_prepare(nimfm_ctx *ctx, const double *const *bufs, int nb) {
+  ctx->peerMaps.clear();
+  if (!ctx->peerOK || nb <= 0) return NIMFM_OK;
+  const int R = ctx->nranks;
+  const int W = 11;   // per buffer: handle (8) | offset in the arena | doubles available from the offset | ok
+  std::vector<int64_t> mine((size_t)W * nb, 0), all((size_t)W * nb * R);
+  for (int i = 0; i < nb; i++) {
+    for (auto &a : ctx->arenas)
+      if (bufs[i] && bufs[i] >= a.base && bufs[i] < a.base + a.nDoubles) {
+        if (!a.haveHandle) {
+          cudaIpcMemHandle_t h;
+          if (cudaIpcGetMemHandle(&h, a.base) != cudaSuccess) { cudaGetLastError(); break; }
+          memcpy(a.handle, &h, 64);
+          a.haveHandle = true;
+        }
+        memcpy(&mine[(size_t)W * i], a.handle, 64);
+        mine[(size_t)W * i + 8] = bufs[i] - a.base;
+        mine[(size_t)W * i + 9] = (int64_t)a.nDoubles - (bufs[i] - a.base);
+        mine[(size_t)W * i + 10] = 1;
+        break;
+      }
+  }
+  int rc = nimfm_allgather_host_i64(ctx, mine.data(), W * nb, all.data());
+  if (rc) return rc;
+  std::vector<nimfm_ctx::PeerMap> maps;
+  std::vector<int64_t> good((size_t)nb, 1);
+  for (int i = 0; i < nb; i++) {
+    nimfm_ctx::PeerMap m;
+    m.local = const_cast<double *>(bufs[i]);
+    m.nDoubles = mine[(size_t)W * i + 9];
+    for (int r = 0; r < R && good[(size_t)i]; r++) {
+      const int64_t *q = &all[((size_t)r * nb + i) * W];
+      if (!q[10]) { good[(size_t)i] = 0; break; }
+      m.nDoubles = std::min(m.nDoubles, q[9]);
+      if (r == ctx->rank) { m.peer[r] = m.local; continue; }
+      double *base = open_peer(ctx, r, q);
+      if (!base) { good[(size_t)i] = 0; break; }
+      m.peer[r] = base + q[8];
+    }
+    maps.push_back(m);
+  }
+  // second round: a buffer is exchanged over peer memory only if EVERY rank mapped every peer's copy
+  std::vector<int64_t> goodAll((size_t)nb * R);
+  if ((rc = nimfm_allgather_host_i64(ctx, good.data(), nb, goodAll.data()))) return rc;
+  for (int i = 0; i < nb; i++) {
+    bool every = true;
+    for (int r = 0; r < R; r++) every = every && goodAll[(size_t)r * nb + i] != 0;
+    if (every) ctx->peerMaps.push_back(maps[(size_t)i]);
+  }
+  return NIMFM_OK;
+}
+
+void nimfm_peer_release(nimfm_ctx *ctx) { ctx->peerMaps.clear(); }
 
 int nimfm_peer_allreduce_sum(nimfm_ctx *ctx, double *buf, int64_t n, int *done) {
   *done = 0;
