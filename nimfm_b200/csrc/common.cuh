@@ -92,7 +92,15 @@ struct nimfm_ctx {
   uint32_t *peerFlags = nullptr;                 // [NIMFM_MAX_RANKS] arrival counters written by the peers
   uint32_t *peerFlagsOf[NIMFM_MAX_RANKS] = {nullptr};
   uint32_t barrierEpoch = 0;
+  // NIMFM_TRACE=1: device time per phase of the multi-rank epochs (CUDA events on the stream, summed per tag and
+  // printed to stderr by nimfm_trace_report) -- a measurement aid, off by default
+  struct TraceSpan { const char *tag; cudaEvent_t e0, e1; };
+  std::vector<TraceSpan> trace;
+  int traceOn = -1;
 };
+void nimfm_trace_begin(nimfm_ctx *ctx, const char *tag);
+void nimfm_trace_end(nimfm_ctx *ctx);
+void nimfm_trace_report(nimfm_ctx *ctx, const char *what);
 
 struct nimfm_dataset {
   int kind = NIMFM_DS_CSR;
@@ -238,11 +246,12 @@ struct MbpsgdStepArgs {   // Params.step (params.nim:90-98) + L1 prox on a flat 
   double negEtaP, rP, lam, negEtaW, rW, negEtaB, rB;
   int reg, fitLinear, fitIntercept;
 };
-// reduce this rank's slice [lo, hi) of `grad` over all ranks, step `pool` there, write the slice into every
-// rank's pool (broadcast != 0) or only the local one; *done = 0 when the buffers are not peer-mapped
+// barrier, then reduce this rank's slice [lo, hi) of `grad` over all ranks (rank order) and step the local `pool`
+// there; the caller follows with [prox on the slice,] barrier, nimfm_peer_pull_slices(pool).  *done = 0 when the
+// buffers are not peer-mapped (nothing was launched)
 int nimfm_peer_mbpsgd_step(nimfm_ctx *ctx, double *pool, double *grad, int64_t lo, int64_t hi, const MbpsgdStepArgs &sa,
-                           int broadcast, int *done);
-int nimfm_peer_broadcast_slice(nimfm_ctx *ctx, double *buf, int64_t lo, int64_t hi);
+                           int *done);
+int nimfm_peer_pull_slices(nimfm_ctx *ctx, double *buf, int64_t c, int64_t n);
 int nimfm_peer_barrier(nimfm_ctx *ctx);
 
 // hot-column table upload (dataset.cu)

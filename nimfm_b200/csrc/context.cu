@@ -336,6 +336,43 @@ int nimfm_mb_schedule(nimfm_ctx *ctx, int64_t nRows, int64_t mb, int64_t it, MbS
   return NIMFM_OK;
 }
 
+void nimfm_trace_begin(nimfm_ctx *ctx, const char *tag) {
+  if (ctx->traceOn < 0) { const char *e = getenv("NIMFM_TRACE"); ctx->traceOn = e && e[0] == '1'; }
+  if (!ctx->traceOn) return;
+  nimfm_ctx::TraceSpan sp{tag, nullptr, nullptr};
+  cudaEventCreate(&sp.e0);
+  cudaEventCreate(&sp.e1);
+  cudaEventRecord(sp.e0, ctx->stream);
+  ctx->trace.push_back(sp);
+}
+void nimfm_trace_end(nimfm_ctx *ctx) {
+  if (ctx->traceOn != 1 || ctx->trace.empty()) return;
+  cudaEventRecord(ctx->trace.back().e1, ctx->stream);
+}
+void nimfm_trace_report(nimfm_ctx *ctx, const char *what) {
+  if (ctx->traceOn != 1 || ctx->trace.empty()) return;
+  cudaStreamSynchronize(ctx->stream);
+  struct Acc { const char *tag; double ms; int n; };
+  std::vector<Acc> acc;
+  for (auto &sp : ctx->trace) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, sp.e0, sp.e1);
+    cudaEventDestroy(sp.e0);
+    cudaEventDestroy(sp.e1);
+    bool found = false;
+    for (auto &a : acc) if (!strcmp(a.tag, sp.tag)) { a.ms += ms; a.n++; found = true; }
+    if (!found) acc.push_back({sp.tag, ms, 1});
+  }
+  ctx->trace.clear();
+  std::string line = std::string("[nimfm trace] rank ") + std::to_string(ctx->rank) + " " + what + ":";
+  for (auto &a : acc) {
+    char buf[128];
+    snprintf(buf, sizeof(buf), "  %s %.1f us x %d", a.tag, a.ms * 1e3 / a.n, a.n);
+    line += buf;
+  }
+  fprintf(stderr, "%s\n", line.c_str());
+}
+
 int nimfm_ensure_partials(nimfm_ctx *ctx, size_t nDoubles) {
   if (ctx->partialsCap >= nDoubles) return NIMFM_OK;
   if (ctx->partials) {

@@ -733,11 +733,13 @@ int32_t nimfm_fm_mbpsgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset 
   }
   if (sliceC) CK(cudaMemsetAsync(fm->b + 1, 0, 8, ctx->stream));   // epoch loss slot of the parameter pool
   for (int64_t inner = 0; inner < cfg->maxIterInner; inner++) {
+    nimfm_trace_begin(ctx, "K2");
     if ((rc = launch_loss_grad(ctx, fm, X, cfg->loss, cfg->huberThreshold, cur, localBatch,
                                idxDev ? idxDev + inner * localBatch : nullptr, (double)cfg->miniBatchSize, nullptr)))
       return rc;
     add_tail_kernel<<<1, 1, 0, ctx->stream>>>(fm->grad + nG - 2, ctx->scalars + 8);
     LAUNCHED(ctx);
+    nimfm_trace_end(ctx);
     if (sliceC) {
       const double etaP = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->beta, *it);
       const double etaW = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->alpha, *it);
@@ -758,13 +760,28 @@ int32_t nimfm_fm_mbpsgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset 
       int done = 0;
       if (viaPeer) {
         MbpsgdStepArgs sa{nP, d, -etaP, rP, lam, -etaW, rW, -etaB, rB, cfg->reg, fm->fitLinear, fm->fitIntercept};
-        if ((rc = nimfm_peer_mbpsgd_step(ctx, fm->pool, fm->grad, lo, hi, sa, rowProx ? 0 : 1, &done))) return rc;
+        nimfm_trace_begin(ctx, "barrier+reduce+step");
+        if ((rc = nimfm_peer_mbpsgd_step(ctx, fm->pool, fm->grad, lo, hi, sa, &done))) return rc;
+        nimfm_trace_end(ctx);
         if (done) {
-          if (rowProx) {
-            prox_slice();
-            if ((rc = nimfm_peer_broadcast_slice(ctx, fm->pool, lo, hi))) return rc;
-          }
-          if ((rc = nimfm_peer_barrier(ctx))) return rc;   // all slices have landed; all peers are done reading my gradients
+          prox_slice();
+          nimfm_trace_begin(ctx, "barrier2");
+          if ((rc = nimfm_peer_barrier(ctx))) return rc;   // every slice is final; all peers are done reading my gradients
+          nimfm_trace_end(ctx);
+          // the pull first, grads <- 0 last.  Measured on 2 GPUs (C3, 256 Ki rows per rank per minibatch,
+          // profiles/r02_peer_exchange.md): with the pull last, the rank whose pulled slice holds the always-present
+          // columns' parameter rows ran the next row kernel at 740 us against 598 us on the other rank (freshly
+          // written hot lines, whoever wrote them); with the zero-fill last both ranks run it at 630-646 us
+          nimfm_trace_begin(ctx, "pull");
+          if ((rc = nimfm_peer_pull_slices(ctx, fm->pool, sliceC, nG))) return rc;
+          nimfm_trace_end(ctx);
+          nimfm_trace_begin(ctx, "zero grads");
+          fill_kernel<<<ew_grid(ctx, nG), 256, 0, ctx->stream>>>(fm->grad, nG, 0.0);
+          LAUNCHED(ctx);
+          nimfm_trace_end(ctx);
+          *it += 1;
+          cur = (cur + localBatch) % X->n;
+          continue;
         }
       }
       if (!done) {
@@ -779,13 +796,19 @@ int32_t nimfm_fm_mbpsgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset 
         if ((rc = nimfm_allgather_inplace(ctx, fm->pool, sliceC))) return rc;
       }
       // grads <- 0 by a kernel, not a memset: its stores leave the lines in L2 for the next minibatch's REDs
+      nimfm_trace_begin(ctx, "zero grads");
       fill_kernel<<<ew_grid(ctx, sliceC * ctx->nranks), 256, 0, ctx->stream>>>(fm->grad, sliceC * ctx->nranks, 0.0);
       LAUNCHED(ctx);
+      nimfm_trace_end(ctx);
       *it += 1;
       cur = (cur + localBatch) % X->n;
       continue;
     }
+    nimfm_trace_begin(ctx, "allreduce");
     if ((rc = nimfm_allreduce_sum(ctx, fm->grad, nG))) return rc;
+    nimfm_trace_end(ctx);
+    nimfm_trace_begin(ctx, "dense step");
+    struct TraceEnd { nimfm_ctx *c; ~TraceEnd() { nimfm_trace_end(c); } } traceEnd{ctx};
     const double etaP = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->beta, *it);     // :114-116
     const double etaW = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->alpha, *it);
     const double etaB = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->alpha0, *it);
@@ -800,7 +823,9 @@ int32_t nimfm_fm_mbpsgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset 
     *it += 1;
     cur = (cur + localBatch) % X->n;
   }
+  if (viaPeer && (rc = nimfm_peer_barrier(ctx))) return rc;   // no peer still pulls my slice when the call returns
   CK(cudaGetLastError());
+  nimfm_trace_report(ctx, "mbpsgd epoch");
   CK(cudaMemcpyAsync(ctx->hostScalars, sliceC ? fm->b + 1 : ctx->scalars, 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   *ii = cur;

@@ -7,13 +7,16 @@
 // arenas the call will exchange (nimfm_peer_prepare: one small gather, mappings cached), so a kernel on rank r
 // can read and write the corresponding buffer of every peer directly.  One exchange is
 //     barrier  ->  reduce kernel  ->  barrier
-// where the reduce kernel, on rank r, walks ITS 1/N slice of the buffer: 16-byte loads of the slice out of all
-// N ranks' buffers (N loads in flight per element pair), a sum in rank order 0..N-1 (so the result is
-// bit-identical on every rank and from run to run), an element-wise functor -- identity for a plain
-// all-reduce; Params.step + the L1 prox for MBPSGD, which turns reduce-scatter + sharded step + all-gather
-// into ONE pass -- and 16-byte stores of the result into all N ranks' output buffers.  Per rank that moves
-// (N-1)/N of the buffer in and out over NVLink once, the same bytes as an all-reduce, without NCCL's
-// staging copies, and 1/N of the dense step instead of all of it on every GPU.
+// followed by  pull -> [barrier],  where the reduce kernel, on rank r, walks ITS 1/N slice of the buffer: 16-byte
+// loads of the slice out of all N ranks' buffers (N loads in flight per element pair), a sum in rank order
+// 0..N-1 (so the result is bit-identical on every rank and from run to run), an element-wise functor -- identity
+// for a plain all-reduce; Params.step + the L1 prox for MBPSGD, which turns reduce-scatter + sharded step into
+// ONE pass over 1/N of the parameters -- and a LOCAL store; the pull kernel then copies every peer's finished
+// slice into the local buffer (remote loads, local stores).  Per rank that reads (N-1)/N of the buffer twice over
+// NVLink, the bytes of a reduce-scatter + all-gather, with no staging copies and 1/N of the dense step.
+// Pull (remote loads, local stores) rather than push: both were built and measured on 2 GPUs
+// (profiles/r02_peer_exchange.md) -- the exchange costs the same either way (~590-620 GB/s of NVLink reads),
+// and with every store local no rank's memory is written behind its back while it computes.
 //
 // The barrier is a one-block kernel: rank r stores the barrier's sequence number into slot r of every peer's
 // flag array (st.release.sys) and spins until its own slots hold it (ld.acquire.sys).  Counters only grow and
@@ -127,16 +130,6 @@ __global__ void __launch_bounds__(256) peer_reduce_kernel(PeerPtrs in, PeerPtrs 
     for (int r = 1; r < R; r++) s += __ldcg(in.p[r] + e);
     const double o = f(e, s);
     for (int r = 0; r < nOut; r++) out.p[r][e] = o;
-  }
-}
-
-__global__ void __launch_bounds__(256) peer_broadcast_kernel(const double *src, PeerPtrs out, int R, int self, int64_t lo,
-                                                           int64_t hi) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t e = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < hi; e += stride) {
-    const double v = src[e];
-    for (int r = 0; r < R; r++)
-      if (r != self) out.p[r][e] = v;
   }
 }
 
@@ -344,6 +337,8 @@ int nimfm_peer_prepare(nimfm_ctx *ctx, const double *const *bufs, int nb) {
 
 void nimfm_peer_release(nimfm_ctx *ctx) { ctx->peerMaps.clear(); }
 
+int nimfm_peer_pull_slices(nimfm_ctx *ctx, double *buf, int64_t c, int64_t n);
+
 int nimfm_peer_allreduce_sum(nimfm_ctx *ctx, double *buf, int64_t n, int *done) {
   *done = 0;
   PeerPtrs pp;
@@ -354,34 +349,61 @@ int nimfm_peer_allreduce_sum(nimfm_ctx *ctx, double *buf, int64_t n, int *done) 
   const int64_t lo = std::min<int64_t>(n, (int64_t)ctx->rank * c), hi = std::min<int64_t>(n, lo + c);
   int rc;
   if ((rc = nimfm_peer_barrier(ctx))) return rc;        // every rank's contribution is complete
-  if ((rc = launch_reduce(ctx, pp, pp, R, lo, hi, IdentityF()))) return rc;
-  if ((rc = nimfm_peer_barrier(ctx))) return rc;        // every slice has landed everywhere
+  PeerPtrs out = pp;
+  out.p[0] = buf;
+  if ((rc = launch_reduce(ctx, pp, out, 1, lo, hi, IdentityF()))) return rc;   // my slice, summed in rank order, in place
+  if ((rc = nimfm_peer_barrier(ctx))) return rc;        // every slice is final
+  if ((rc = nimfm_peer_pull_slices(ctx, buf, c, n))) return rc;
+  if ((rc = nimfm_peer_barrier(ctx))) return rc;        // nobody still reads my slice: the caller may overwrite the buffer
   *done = 1;
   return NIMFM_OK;
 }
 
 int nimfm_peer_mbpsgd_step(nimfm_ctx *ctx, double *pool, double *grad, int64_t lo, int64_t hi, const MbpsgdStepArgs &sa,
-                           int broadcast, int *done) {
+                           int *done) {
   *done = 0;
   PeerPtrs pg, pp;
   const int64_t span = sa.nP + sa.d + 2;
   if (!ctx->peerOK || (lo & 1) || !lookup(ctx, grad, span, &pg) || !lookup(ctx, pool, span, &pp)) return NIMFM_OK;
   int rc;
-  if ((rc = nimfm_peer_barrier(ctx))) return rc;
+  if ((rc = nimfm_peer_barrier(ctx))) return rc;   // every rank's gradients are complete (and its last pull has finished)
   MbpsgdStepF f{pool, sa};
   PeerPtrs out = pp;
-  if (!broadcast) out.p[0] = pool;                      // a prox follows on the local slice: broadcast afterwards
-  if ((rc = launch_reduce(ctx, pg, out, broadcast ? ctx->nranks : 1, lo, hi, f))) return rc;
+  out.p[0] = pool;
+  if ((rc = launch_reduce(ctx, pg, out, 1, lo, hi, f))) return rc;
   *done = 1;
   return NIMFM_OK;
 }
 
-int nimfm_peer_broadcast_slice(nimfm_ctx *ctx, double *buf, int64_t lo, int64_t hi) {
+// all-gather by PULLING: copy every peer's slice [r*c, (r+1)*c) of its buffer into the local buffer (remote
+// 16-byte loads, local stores), the peers in a rotated order so that the ranks do not all read the same GPU
+__global__ void __launch_bounds__(256) peer_pull_kernel(PeerPtrs in, double *dst, int R, int self, int64_t c, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (int q = 1; q < R; q++) {
+    const int r = (self + q) % R;
+    const int64_t lo = r * c, hi = lo + c < n ? lo + c : n;      // c even, n may be odd
+    const double2 *src = reinterpret_cast<const double2 *>(in.p[r]);
+    double2 *d2 = reinterpret_cast<double2 *>(dst);
+    const int64_t p0 = lo >> 1, p1 = hi >> 1;
+    for (int64_t i = p0 + tid; i < p1; i += 4 * stride) {
+      double2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (i + u * stride < p1) v[u] = __ldcg(src + i + u * stride);
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (i + u * stride < p1) d2[i + u * stride] = v[u];
+    }
+    if ((hi & 1) && hi > lo && tid == 0) dst[hi - 1] = __ldcg(in.p[r] + hi - 1);
+  }
+}
+
+int nimfm_peer_pull_slices(nimfm_ctx *ctx, double *buf, int64_t c, int64_t n) {
   PeerPtrs pp;
-  if (!ctx->peerOK || !lookup(ctx, buf, hi, &pp)) return nimfm_fail(ctx, NIMFM_ERR_STATE, "buffer is not peer-mapped");
-  if (hi <= lo) return NIMFM_OK;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((hi - lo + 255) / 256, (int64_t)ctx->numSMs * 4));
-  peer_broadcast_kernel<<<grid, 256, 0, ctx->stream>>>(buf, pp, ctx->nranks, ctx->rank, lo, hi);
+  if (!ctx->peerOK || !lookup(ctx, buf, n, &pp)) return nimfm_fail(ctx, NIMFM_ERR_STATE, "buffer is not peer-mapped");
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((c / 2 + 1023) / 1024, (int64_t)ctx->numSMs * 4));
+  peer_pull_kernel<<<grid, 256, 0, ctx->stream>>>(pp, buf, ctx->nranks, ctx->rank, c, n);
   LAUNCHED(ctx);
   CK(cudaGetLastError());
   return NIMFM_OK;
