@@ -495,6 +495,23 @@ class Bench:
                                      "frac": B_FWD * n / (fms.value / 1e3) / 1e9 / self.peak}}
         line.update({"value": value, "ms_per_step": ms_per_step, "clocks": clocks, "gpu_launches": int(launches),
                      "roofline": roofline, "loss_sum": loss_sum, "setup_seconds": t_gen})
+        if self.on("det"):
+            # the atomic-free route (csrc/fm_cols.cu) on the same step, timed beside the RED route
+            os.environ["NIMFM_DETERMINISTIC"] = "1"
+            try:
+                t0 = time.perf_counter()
+                det_loss = step()                          # first call builds the CSC twin + column segments
+                first = time.perf_counter() - t0
+                det_ms = self.timed(step, 2)
+                det_loss2 = step()
+            finally:
+                del os.environ["NIMFM_DETERMINISTIC"]
+            line["deterministic"] = {
+                "samples_per_s": n * world / (det_ms / 1e3), "ms_per_step": det_ms, "first_call_seconds": first,
+                "vs_red_route": ms_per_step / det_ms, "loss_sum": det_loss, "repeat_bit_identical": det_loss == det_loss2,
+                "loss_sum_rel_diff_vs_red": abs(det_loss - loss_sum) / abs(loss_sum),
+                "what": "NIMFM_DETERMINISTIC=1: stash-forward row kernel + column kernel over the CSC twin (every "
+                        "gradient element summed in ascending row order, plain stores, no atomics), same step"}
         fwd_ms = self.maxr(fms.value)
         line["c4_decision_function"] = {"samples_per_s": n * world / (fwd_ms / 1e3), "kernel_ms": fwd_ms, "rows_per_gpu": n,
                                         "what": "batched decisionFunction kernel over the resident shards (no collective)",
@@ -780,7 +797,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bounded CPU-baseline sample")
     ap.add_argument("--ref-rows", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--skip", default="", help="comma list of sections to skip: parity,e2e,c4_adagrad,c3,c5,cd,uniform")
+    ap.add_argument("--skip", default="", help="comma list of sections to skip: parity,det,e2e,c4_adagrad,c3,c5,cd,uniform")
     ap.add_argument("--dist", default="criteo", choices=["criteo", "uniform", "zipfall"],
                     help="index distribution; anything but 'criteo' is an experiment, not the reported workload")
     args = ap.parse_args()

@@ -28,6 +28,8 @@ struct nimfm_ctx {
   // scratch (grown on demand)
   double *partials = nullptr;  // per-group partial sums written by the row kernels
   size_t partialsCap = 0;
+  double *stash = nullptr;     // deterministic gradient (fm_cols.cu): per-row stash records + segment partials
+  size_t stashCap = 0;
   double *scalars = nullptr;   // small device scalar block (64 doubles)
   double *hostScalars = nullptr;  // pinned mirror
   int64_t *idxScratch = nullptr;  // device copy of host-provided row ids
@@ -102,8 +104,23 @@ void nimfm_trace_begin(nimfm_ctx *ctx, const char *tag);
 void nimfm_trace_end(nimfm_ctx *ctx);
 void nimfm_trace_report(nimfm_ctx *ctx, const char *what);
 
+struct nimfm_dataset;
+// fm_cols.cu: the CSC twin of a CSR dataset (stable transpose: rows ascending inside a column) and its columns cut
+// into segments of at most 512 entries -- the work list of the column-wise (atomic-free) gradient kernels
+struct nimfm_det_twin {
+  nimfm_dataset *csc = nullptr;
+  int32_t *taskCol = nullptr, *taskLen = nullptr, *taskSlot = nullptr;   // per segment: column, length, partial slot (-1: whole column)
+  int64_t *taskBeg = nullptr;
+  int32_t *multiCol = nullptr, *multiFirst = nullptr, *multiCount = nullptr;   // columns with several segments
+  int64_t nTasks = 0, nMulti = 0, nSlots = 0;
+  int nAug = -1;
+};
+void nimfm_det_twin_free(nimfm_ctx *ctx, nimfm_det_twin *t);
+int nimfm_det_twin_get(nimfm_ctx *ctx, const nimfm_dataset *X, int nAug, nimfm_det_twin **out);
+
 struct nimfm_dataset {
   int kind = NIMFM_DS_CSR;
+  mutable nimfm_det_twin *detTwin = nullptr;
   int64_t n = 0, d = 0, nnz = 0;     // n rows (samples), d columns (features) of the LOGICAL matrix
   int64_t nFields = 0;
   int64_t maxSegNnz = 0;             // longest row (CSR) / column (CSC)

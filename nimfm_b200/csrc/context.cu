@@ -146,6 +146,7 @@ int32_t nimfm_ctx_destroy(nimfm_ctx *ctx) {
   nimfm_peer_shutdown(ctx);
   if (ctx->comm && g_nccl.commDestroy) g_nccl.commDestroy(ctx->comm);
   cudaFree(ctx->partials);
+  cudaFree(ctx->stash);
   cudaFree(ctx->scalars);
   cudaFree(ctx->idxScratch);
   cudaFree(ctx->idx32Scratch);

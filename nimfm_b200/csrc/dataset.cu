@@ -206,6 +206,7 @@ int32_t nimfm_dataset_download(nimfm_ctx *ctx, const nimfm_dataset *ds, double *
 int32_t nimfm_dataset_free(nimfm_ctx *ctx, nimfm_dataset *ds) {
   if (!ds) return NIMFM_OK;
   if (ctx) cudaSetDevice(ctx->device);
+  if (ds->detTwin) nimfm_det_twin_free(ctx, ds->detTwin);
   cudaFree(ds->data);
   cudaFree(ds->indices);
   cudaFree(ds->indptr);

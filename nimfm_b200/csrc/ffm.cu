@@ -53,6 +53,7 @@ struct __align__(16) FfmMeta {
 
 #include "ffm_pairs.cuh"
 #include "ffm_tma.cuh"
+#include "ffm_cols.cuh"
 
 static size_t ffm_smem_bytes(int CH, int SB8, int nFields) {
   size_t b = (((size_t)CH * SB8 * 8 + 15) & ~(size_t)15) + (size_t)CH * sizeof(FfmMeta) + (size_t)CH * 4 +
@@ -540,10 +541,106 @@ int32_t nimfm_ffm_decision_function(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_da
   return NIMFM_OK;
 }
 
+// which route by default: decided by measurement; the RED route until the column route is shown to win
+static bool ffm_cols_default(int64_t nRows) { (void)nRows; return false; }
+
+// The atomic-free route (ffm_cols.cuh).  *taken = 0: the shape is outside what it supports (the caller runs the
+// RED route) unless `must` is set (NIMFM_DETERMINISTIC=1), in which case that is an error.
+static int ffm_launch_grad_cols(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_dataset *X, int loss, double thr,
+                                int64_t rowBegin, int64_t nRows, const int32_t *rowIdxDev, double mb, bool must,
+                                int *taken) {
+  *taken = 0;
+  typedef void (*ColKern)(const FfmColArgs);
+  constexpr int E = 8;
+  ColKern ck = m->k == 4 ? ffm_cols_grad_kernel<4, E> : m->k == 8 ? ffm_cols_grad_kernel<8, E>
+               : m->k == 16 ? ffm_cols_grad_kernel<16, E> : (ColKern) nullptr;
+  const int CH = (int)std::max<int64_t>(X->maxSegNnz, 1);
+  bool dups = true;
+  int rc;
+  const bool shapeOk = ck && !rowIdxDev && rowBegin >= 0 && rowBegin + nRows <= X->n && CH <= 64 && m->nFields <= 64 &&
+                       m->d * m->nFields < (int64_t)2147483647;
+  if (shapeOk && (rc = ffm_has_field_dups(ctx, X, &dups))) return rc;
+  if (!shapeOk || dups) {
+    if (must)
+      return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "the deterministic FFM gradient needs a contiguous row range, rows of at "
+                        "most 64 nonzeros with one nonzero per field, nFields <= 64 and nComponents in {4,8,16}");
+    return NIMFM_OK;
+  }
+  nimfm_det_twin *tw = nullptr;
+  if ((rc = nimfm_det_twin_get(ctx, X, 0, &tw))) return rc;
+  const int SB8 = (int)(m->nFields * m->k);
+  const size_t need = (size_t)std::max<int64_t>(nRows, 1) + (size_t)tw->nSlots * (SB8 + 1) + 16;
+  if (ctx->stashCap < need) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->stash) CK(cudaFree(ctx->stash));
+    ctx->stash = nullptr;
+    ctx->stashCap = 0;
+    CK(cudaMalloc(&ctx->stash, need * 8));
+    ctx->stashCap = need;
+  }
+  // pass 1: the forward pair kernel leaves yhat per row, then coef = dloss / mb in place + the loss partials
+  FfmPlan pl;
+  if ((rc = ffm_plan_mode(ctx, m, X, nRows, FFM_PREDICT, &pl))) return rc;
+  FfmArgs a;
+  ffm_fill_args(a, m, X);
+  a.rowBegin = rowBegin; a.nRows = nRows; a.yOut = ctx->stash; a.CH = pl.CH;
+  pl.kern<<<pl.grid, pl.block, pl.smem, ctx->stream>>>(a);
+  LAUNCHED(ctx);
+  const int cgrid = (int)std::max<int64_t>(1, std::min<int64_t>((nRows + 255) / 256, (int64_t)ctx->numSMs * 4));
+  if ((rc = nimfm_ensure_partials(ctx, (size_t)cgrid * 4))) return rc;
+  ffm_coef_kernel<<<cgrid, 256, 0, ctx->stream>>>(ctx->stash, X->y, rowBegin, nRows, loss, thr, mb, ctx->partials);
+  LAUNCHED(ctx);
+  reduce_partials_kernel<<<1, 256, 0, ctx->stream>>>(ctx->partials, cgrid, ctx->scalars + 8, 0);
+  LAUNCHED(ctx);
+  // pass 2: the column kernel
+  FfmColArgs c;
+  c.cdata = tw->csc->data; c.crow = tw->csc->indices;
+  c.taskCol = tw->taskCol; c.taskLen = tw->taskLen; c.taskSlot = tw->taskSlot; c.taskBeg = tw->taskBeg;
+  c.nTasks = tw->nTasks;
+  c.data = X->data; c.indices = X->indices; c.fields = X->fields; c.indptr = X->indptr;
+  c.coef = ctx->stash;
+  c.rowBegin = rowBegin; c.rowEnd = rowBegin + nRows;
+  c.nFields = (int)m->nFields; c.CH = CH;
+  c.P = m->P; c.gP = m->grad; c.gw = m->grad + m->nP();
+  c.partial = ctx->stash + std::max<int64_t>(nRows, 1);
+  c.fitLinear = m->fitLinear;
+  if (tw->nTasks > 0) {
+    const int perWarp = 32 / m->k;
+    const int NS = (int)((m->nFields + perWarp - 1) / perWarp * perWarp);   // slots: one per field, whole warps
+    const int block = NS * m->k;
+    const size_t smem = (size_t)E * CH * sizeof(FfmRec) + (size_t)E * sizeof(FfmColMeta) + (size_t)E * NS + 16;
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ck, block, smem));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tw->nTasks, (int64_t)std::max(occ, 1) * ctx->numSMs));
+    ck<<<grid, block, smem, ctx->stream>>>(c);
+    LAUNCHED(ctx);
+  }
+  if (tw->nMulti > 0) {
+    ffm_cols_combine_kernel<<<(unsigned)tw->nMulti, 128, 0, ctx->stream>>>(tw->multiCol, tw->multiFirst, tw->multiCount,
+                                                                          tw->nMulti, c.partial, SB8, c.gP, c.gw, m->fitLinear);
+    LAUNCHED(ctx);
+  }
+  CK(cudaGetLastError());
+  *taken = 1;
+  return NIMFM_OK;
+}
+
 static int ffm_launch_grad(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_dataset *X, int loss, double thr,
                            int64_t rowBegin, int64_t nRows, const int32_t *rowIdxDev, double mb) {
   FfmPlan pl;
-  int rc = ffm_plan_mode(ctx, m, X, nRows, FFM_GRAD, &pl);
+  int rc;
+  {
+    // NIMFM_FFM_GRAD = cols | red | unset (automatic); NIMFM_DETERMINISTIC=1 insists on the atomic-free route
+    const char *envG = getenv("NIMFM_FFM_GRAD"), *envD = getenv("NIMFM_DETERMINISTIC");
+    const bool must = envD && envD[0] == '1';
+    const bool want = must || (envG ? !strcmp(envG, "cols") : ffm_cols_default(nRows));
+    if (want && nRows > 0) {
+      int taken = 0;
+      if ((rc = ffm_launch_grad_cols(ctx, m, X, loss, thr, rowBegin, nRows, rowIdxDev, mb, must, &taken))) return rc;
+      if (taken) return NIMFM_OK;
+    }
+  }
+  rc = ffm_plan_mode(ctx, m, X, nRows, FFM_GRAD, &pl);
   if (rc) return rc;
   if ((rc = nimfm_ensure_partials(ctx, (size_t)pl.partialRows * 4))) return rc;
   FfmArgs a;

@@ -69,6 +69,10 @@ RowKernel nimfm_row_stream_kernel_predict(int degree, bool explicitLower, int k)
 RowKernel nimfm_row_stream_kernel_grad(int degree, bool explicitLower, int k);
 RowKernel nimfm_row_stream_kernel_adagrad(int degree, bool explicitLower, int k);
 RowKernel nimfm_row_fast_kernel_grad(int degree, bool explicitLower, int k);
+RowKernel nimfm_row_stream_kernel_stash(int degree, bool explicitLower, int k);
+int nimfm_fm_det_loss_grad(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X, RowKernel stashKern, int G, int CH,
+                           int grid, int block, size_t smem, int64_t nWarps, int loss, double thr, int64_t rowBegin,
+                           int64_t nRows, double mb, double *yOutDev, const RowArgs &base);
 
 static bool is_explicit(const nimfm_fm *fm) { return fm->degree > 2 && fm->nOrders == fm->degree - 1; }
 
@@ -77,7 +81,7 @@ static bool is_explicit(const nimfm_fm *fm) { return fm->degree > 2 && fm->nOrde
 // warps under the shared-memory budget, and a persistent grid of occupancy x numSMs blocks.
 static int plan_rows(nimfm_ctx *ctx, const nimfm_fm *fm, const nimfm_dataset *X, int64_t nRows, int mode,
                      RowPlan *pl) {
-  const int nAcc = mode == MODE_PREDICT ? 0 : (mode == MODE_GRAD ? 1 : 2);
+  const int nAcc = (mode == MODE_PREDICT || mode == MODE_STASH) ? 0 : (mode == MODE_GRAD ? 1 : 2);
   const int nHotTot = nAcc ? (X->hotSlot ? X->nHot : 0) + fm->nAug : 0;
   const int k = fm->k;
   const int G = k <= 8 ? 8 : (k <= 16 ? 16 : 32);
@@ -94,12 +98,16 @@ static int plan_rows(nimfm_ctx *ctx, const nimfm_fm *fm, const nimfm_dataset *X,
   RowKernel fast = nullptr;
   bool stream = false;
   if (!wantGeneric) {
-    if (!wantFast && z <= 512) {
+    if ((!wantFast || mode == MODE_STASH) && z <= 512) {
       fast = mode == MODE_PREDICT ? nimfm_row_stream_kernel_predict(fm->degree, expl, k)
              : mode == MODE_GRAD  ? nimfm_row_stream_kernel_grad(fm->degree, expl, k)
+             : mode == MODE_STASH ? nimfm_row_stream_kernel_stash(fm->degree, expl, k)
                                   : nimfm_row_stream_kernel_adagrad(fm->degree, expl, k);
       stream = fast != nullptr;
     }
+    if (mode == MODE_STASH && !fast)
+      return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "the deterministic gradient supports degree 2 / 3 with nComponents in "
+                        "{8,16,32} and rows of at most 512 nonzeros");
     if (!fast && mode != MODE_ADAGRAD) {
       fast = mode == MODE_PREDICT ? nimfm_row_fast_kernel_predict(fm->degree, expl, k)
                                   : nimfm_row_fast_kernel_grad(fm->degree, expl, k);
@@ -421,7 +429,17 @@ static int launch_loss_grad(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X
                             int64_t rowBegin, int64_t nRows, const int32_t *rowIdxDev, double mb,
                             double *yOutDev, LazyView *lazy = nullptr) {
   RowPlan pl;
-  int rc = plan_rows(ctx, fm, X, nRows, MODE_GRAD, &pl);
+  int rc;
+  // NIMFM_DETERMINISTIC=1: the atomic-free route (fm_cols.cu): stash-forward row kernel + column kernel over the CSC twin
+  if (const char *env = getenv("NIMFM_DETERMINISTIC"); env && env[0] == '1' && !lazy) {
+    if (rowIdxDev) return nimfm_fail(ctx, NIMFM_ERR_UNSUPPORTED, "the deterministic gradient needs a contiguous row range (no row list)");
+    if ((rc = plan_rows(ctx, fm, X, nRows, MODE_STASH, &pl))) return rc;
+    RowArgs base;
+    fill_row_args(base, fm, X);
+    return nimfm_fm_det_loss_grad(ctx, fm, X, pl.kern, pl.G, pl.CH, pl.grid, pl.block, pl.smem, pl.nWarps, loss, thr,
+                                  rowBegin, nRows, mb, yOutDev, base);
+  }
+  rc = plan_rows(ctx, fm, X, nRows, MODE_GRAD, &pl);
   if (rc) return rc;
   if (lazy && !pl.stream) return nimfm_fail(ctx, NIMFM_ERR_STATE, "lazy step without the streaming row kernel");
   RowKernel kern = pl.kern;
@@ -650,6 +668,7 @@ int32_t nimfm_fm_mbpsgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset 
     const double touchedUpper = (double)localBatch * ((double)X->nnz / (double)X->n + fm->nAug);
     bool lazy = ctx->nranks == 1 && noProx && T >= 2 && T < (1 << 30) && touchedUpper <= 2.0 * (double)fm->dd();   // measured crossover on the C3 shape: between 1.3 and 5 nnz per feature
     if (env) lazy = env[0] == '1' && ctx->nranks == 1 && noProx && T < (1 << 30);
+    if (const char *det = getenv("NIMFM_DETERMINISTIC"); det && det[0] == '1') lazy = false;   // the lazy step folds factors into x: RED route only
     RowPlan plq;
     if (lazy && (plan_rows(ctx, fm, X, localBatch, MODE_GRAD, &plq) != NIMFM_OK || !plq.stream)) lazy = false;
     { const int sb = fm->nOrders * fm->k; if (sb & (sb - 1)) lazy = false; }   // the flat step shifts by log2(SB8)
@@ -1296,7 +1315,9 @@ static int stream_host_rows(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t
   // host staging (host_stage.h): ids narrowed to int32 and indptr rebased by a thread team into pinned slots,
   // 12 instead of 16 bytes per nonzero on the link; small calls and thread-starved ranks narrow on the device
   const int64_t stageMinNnz = getenv("NIMFM_HOST_STAGE_MIN_NNZ") ? atoll(getenv("NIMFM_HOST_STAGE_MIN_NNZ")) : (1 << 20);
-  const int hostT = (indices && nRows > 0 && indptr[nRows] - indptr[0] >= stageMinNnz) ? HostStageTeam::default_threads(ctx->nranks) : 0;
+  const bool bigCall = indices && nRows > 0 && indptr[nRows] - indptr[0] >= stageMinNnz;
+  const int hostT = !bigCall ? 0 : (is_pageable(data) ? HostStageTeam::pageable_threads(ctx->nranks)
+                                                      : HostStageTeam::default_threads(ctx->nranks));
   int rc;
   const size_t capRows = (size_t)std::min(nRows, chunkRows) + 1;
   for (int s = 0; s < 2; s++)

@@ -23,7 +23,7 @@
 #pragma once
 #include "common.cuh"
 
-enum { MODE_PREDICT = 0, MODE_GRAD = 1, MODE_ADAGRAD = 2 };
+enum { MODE_PREDICT = 0, MODE_GRAD = 1, MODE_ADAGRAD = 2, MODE_STASH = 3 };
 
 struct RowArgs {
   // dataset (CSR)
@@ -62,6 +62,9 @@ struct RowArgs {
   const double2 *lazyInv;           // nullptr: parameters are current (every other caller)
   double lazyCumPt, lazyCumWt;      // cum[t] of the current inner step
   uint8_t *lazyFlag;                // [d+nAug] set for every feature this minibatch touches
+  // MODE_STASH (deterministic gradient, fm_cols.cu): per row [coef | A[o][1..M_o-1][s] ...], stashStride doubles
+  double *stash;
+  int stashStride;
   // geometry
   int G, CH;
 };

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256, 2) fm_rows_stream_kernel(const RowArgs a)
   const int gl = lane & (G - 1);
   const int gidInWarp = lane / G;
   const int CH = a.CH;
-  const int nHotTot = (MODE == MODE_PREDICT) ? 0 : a.nHot + a.nAug;
+  const int nHotTot = (MODE == MODE_PREDICT || MODE == MODE_STASH) ? 0 : a.nHot + a.nAug;
   const size_t perGroup = stream_group_smem(CH, SB8, nHotTot, NACC);
   unsigned char *base = smem_raw + (size_t)(warpInBlock * GPW + gidInWarp) * perGroup;
   NnzMeta *sMeta = reinterpret_cast<NnzMeta *>(base);
@@ -162,6 +162,34 @@ __global__ void __launch_bounds__(256, 2) fm_rows_stream_kernel(const RowArgs a)
       if (active && gl == 0 && a.yOut) a.yOut[q] = yhat;
       continue;
     }
+    if (MODE == MODE_STASH) {
+      // forward half of the deterministic gradient (fm_cols.cu): what the derivative recurrence of sgd.nim:176-188
+      // needs from this row -- coef and A[o][1 .. M_o-1] per component -- goes to the row's stash record
+      if (active) {
+        const double yi = a.y[r];
+        const double dL = dev_dloss(a.loss, a.thr, yi, yhat);
+        double *rec = a.stash + (size_t)q * a.stashStride;
+        if (gl == 0) {
+          if (a.yOut) a.yOut[q] = yhat;
+          accLoss += dev_loss(a.loss, a.thr, yi, yhat);
+          accB1 += dL / a.mb;
+          accB2 += dL * dL;
+          rec[0] = dL / a.mb;
+        }
+        int off = 1;
+#pragma unroll
+        for (int o = 0; o < NO; ++o) {
+          const int M = DEGREE - o;
+#pragma unroll
+          for (int t = 1; t < DEGREE; ++t)
+            if (t < M) {
+              rec[off + gl] = A[o][t];
+              off += KT;
+            }
+        }
+      }
+      continue;
+    }
 
     // ---- loss derivative (loss.nim) and backward (sgd.nim:176-188 + minibatch_psgd.nim:73-88)
     double coef = 0.0;
@@ -247,7 +275,7 @@ __global__ void __launch_bounds__(256, 2) fm_rows_stream_kernel(const RowArgs a)
     }
   }
 
-  if constexpr (MODE != MODE_PREDICT) {
+  if constexpr (MODE == MODE_GRAD || MODE == MODE_ADAGRAD) {
     // ---- flush the hot-column accumulators ONCE PER BLOCK: the block's groups are summed in a fixed
     // order by one thread per element, then one RED per element (per-group flushes made every group
     // of a small minibatch hammer the same few hundred addresses: 180 us for 25 641 rows)
@@ -269,6 +297,8 @@ __global__ void __launch_bounds__(256, 2) fm_rows_stream_kernel(const RowArgs a)
         atomicAdd((which ? a.dGnw : a.gw) + j, v);
       }
     }
+  }
+  if constexpr (MODE != MODE_PREDICT) {
     accLoss = warp_sum(accLoss);
     accB1 = warp_sum(accB1);
     accB2 = warp_sum(accB2);

@@ -45,6 +45,24 @@ __attribute__((target("avx2"))) int narrow_avx2(const int64_t *src, int32_t *dst
   return bad;
 }
 
+// doubles -> a pinned slot with non-temporal stores (the copy engine is the slot's only reader); dst 32-byte aligned
+__attribute__((target("avx2"))) void stream_copy_avx2(double *dst, const double *src, int64_t n) {
+  int64_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    const __m256d a = _mm256_loadu_pd(src + i), b = _mm256_loadu_pd(src + i + 4);
+    _mm256_stream_pd(dst + i, a);
+    _mm256_stream_pd(dst + i + 4, b);
+  }
+  for (; i < n; i++) dst[i] = src[i];
+  _mm_sfence();
+}
+
+void stream_copy(double *dst, const double *src, int64_t n) {
+  static const bool haveAvx2 = __builtin_cpu_supports("avx2");
+  if (haveAvx2 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0) stream_copy_avx2(dst, src, n);
+  else memcpy(dst, src, (size_t)n * sizeof(double));
+}
+
 int narrow(const int64_t *src, int32_t *dst, int64_t n, int64_t d) {
   static const bool haveAvx2 = __builtin_cpu_supports("avx2");
   return haveAvx2 ? narrow_avx2(src, dst, n, d) : narrow_scalar(src, dst, n, d);
@@ -63,6 +81,15 @@ int HostStageTeam::default_threads(int nRanks) {
   // device, 188-196 M with 2-4 staging threads per rank): only ranks with 8 hardware threads to themselves stage.
   const int t = hw / std::max(1, nRanks);
   return t >= 8 ? 8 : 0;
+}
+
+// pageable caller arrays add a copy of the values to the narrowing: the team is the bound then (8 threads: 32 GB/s
+// of link traffic against 52 GB/s from pinned arrays), so it takes what the rank has, less two for the caller
+int HostStageTeam::pageable_threads(int nRanks) {
+  if (const char *e = getenv("NIMFM_HOST_THREADS")) return std::max(0, atoi(e));
+  const int hw = (int)std::thread::hardware_concurrency();
+  const int t = hw / std::max(1, nRanks);
+  return t >= 8 ? std::min(t - 2, 24) : 0;
 }
 
 HostStageTeam::HostStageTeam(int nThreads, const int64_t *indices, const int64_t *indptr, int64_t d,
@@ -110,7 +137,7 @@ void HostStageTeam::part(int64_t c, int t, HostChunkInfo &info) {
   const int64_t per = ((ch.nnz + T_ - 1) / T_ + 7) & ~(int64_t)7;
   const int64_t a = std::min(ch.nnz, per * t), b = std::min(ch.nnz, per * (t + 1));
   if (b > a) info.bad |= narrow(indices_ + ch.base + a, idxSlot_[s] + a, b - a, d_);
-  if (b > a && data_) memcpy(dataSlot_[s] + a, data_ + ch.base + a, (size_t)(b - a) * sizeof(double));
+  if (b > a && data_) stream_copy(dataSlot_[s] + a, data_ + ch.base + a, b - a);
   const int64_t rows = ch.r1 - ch.r0, rper = (rows + T_ - 1) / T_;
   const int64_t ra = std::min(rows, rper * t), rb = std::min(rows, rper * (t + 1));
   if (rb > ra && y_) memcpy(ySlot_[s] + ra, y_ + ch.r0 + ra, (size_t)(rb - ra) * sizeof(double));

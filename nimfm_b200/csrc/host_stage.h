@@ -40,6 +40,7 @@ class HostStageTeam {
   void allow(int64_t upTo);               // chunks < upTo may be written (their slot's last copy has completed)
   HostChunkInfo wait(int64_t c);          // blocks until chunk c is staged in slot c % kSlots
   static int default_threads(int nRanks); // 0: not enough host threads for this rank -> narrow on the device
+  static int pageable_threads(int nRanks);   // team size when the values are staged too
 
  private:
   void work(int t);
