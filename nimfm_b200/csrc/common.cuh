@@ -186,6 +186,7 @@ struct nimfm_ffm {
   int64_t nP() const { return nFields * d * k; }
   // device layout P[j][f][s]: one feature's nFields*k doubles contiguous
   double *P = nullptr, *w = nullptr, *b = nullptr;
+  double *PT = nullptr;        // field-major copy PT[f][j][s], refreshed by the column gradient route (ffm_cols.cuh)
   double *grad = nullptr;      // [gP | gw | gb, lossSum]
   double *gsP = nullptr, *gnP = nullptr, *gsw = nullptr, *gnw = nullptr, *dG = nullptr, *adaScal = nullptr;
   double *sgdCnt = nullptr;    // minibatch SGD (sgd_mb.cu)

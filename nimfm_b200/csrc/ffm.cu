@@ -462,7 +462,7 @@ int32_t nimfm_ffm_free(nimfm_ctx *ctx, nimfm_ffm *m) {
   nimfm_comm_free(ctx, m->grad);
   nimfm_comm_free(ctx, m->dG);
   nimfm_comm_free(ctx, m->sgdCnt);
-  for (double *p : {m->P, m->w, m->b, m->gsP, m->gnP, m->gsw, m->gnw, m->adaScal, m->scalingsP,
+  for (double *p : {m->P, m->PT, m->w, m->b, m->gsP, m->gnP, m->gsw, m->gnw, m->adaScal, m->scalingsP,
                     m->scalingsW, m->sgdScal})
     cudaFree(p);
   delete m;
@@ -551,7 +551,7 @@ static int ffm_launch_grad_cols(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_datase
                                 int *taken) {
   *taken = 0;
   typedef void (*ColKern)(const FfmColArgs);
-  constexpr int E = 8;
+  constexpr int E = 4;   // column entries in flight per warp
   ColKern ck = m->k == 4 ? ffm_cols_grad_kernel<4, E> : m->k == 8 ? ffm_cols_grad_kernel<8, E>
                : m->k == 16 ? ffm_cols_grad_kernel<16, E> : (ColKern) nullptr;
   const int CH = (int)std::max<int64_t>(X->maxSegNnz, 1);
@@ -601,17 +601,21 @@ static int ffm_launch_grad_cols(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_datase
   c.coef = ctx->stash;
   c.rowBegin = rowBegin; c.rowEnd = rowBegin + nRows;
   c.nFields = (int)m->nFields; c.CH = CH;
-  c.P = m->P; c.gP = m->grad; c.gw = m->grad + m->nP();
+  c.d = m->d;
+  if (!m->PT) CK(cudaMalloc(&m->PT, (size_t)m->nP() * 8));
+  ffm_field_major_kernel<<<ew_grid(ctx, m->nP()), 256, 0, ctx->stream>>>(m->P, m->PT, m->d, (int)m->nFields, m->k);
+  LAUNCHED(ctx);
+  c.PT = m->PT; c.gP = m->grad; c.gw = m->grad + m->nP();
   c.partial = ctx->stash + std::max<int64_t>(nRows, 1);
   c.fitLinear = m->fitLinear;
   if (tw->nTasks > 0) {
-    const int perWarp = 32 / m->k;
-    const int NS = (int)((m->nFields + perWarp - 1) / perWarp * perWarp);   // slots: one per field, whole warps
-    const int block = NS * m->k;
-    const size_t smem = (size_t)E * CH * sizeof(FfmRec) + (size_t)E * sizeof(FfmColMeta) + (size_t)E * NS + 16;
+    const int block = 128;   // 143 registers at k = 8: three 4-warp blocks per SM
+    const size_t smem = (size_t)(block / 32) * ffm_cols_warp_smem(E);
+    CK(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ck, block, smem));
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tw->nTasks, (int64_t)std::max(occ, 1) * ctx->numSMs));
+    const int64_t wantBlocks = (tw->nTasks + block / 32 - 1) / (block / 32);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(wantBlocks, (int64_t)std::max(occ, 1) * ctx->numSMs));
     ck<<<grid, block, smem, ctx->stream>>>(c);
     LAUNCHED(ctx);
   }

@@ -27,7 +27,8 @@ struct FfmColArgs {
   const double *coef;        // [rowEnd - rowBegin] coef_i = dloss_i / mb (written by ffm_coef_kernel)
   int64_t rowBegin, rowEnd;
   int nFields, CH;
-  const double *P;
+  int64_t d;
+  const double *PT;          // the parameters in FIELD-major layout PT[f][j][s] (see ffm_field_major_kernel)
   double *gP, *gw, *partial;
   int fitLinear;
 };
@@ -83,88 +84,151 @@ static __global__ void ffm_coef_kernel(double *yhatCoef, const double *y, int64_
   }
 }
 
-struct FfmColMeta {
-  int64_t rb;
-  double cx;     // coef_i * x_ij
-  int z, fj;     // row length; field of feature j in this row
-};
+// P[j][f][s] (the row kernels' layout: one feature's fields contiguous) -> PT[f][j][s].  The column kernel gathers,
+// for a column of field f_j, the vectors P[j_u][f_j][:] of the partner features: in PT they all lie in ONE slab of
+// d*k doubles (64 MB for C5) that stays in L2 while the columns of that field are processed, where the row layout
+// scatters them over all of P (2.5 GB) -- 64-byte random DRAM accesses, measured at 21 % of the DRAM peak.
+static __global__ void ffm_field_major_kernel(const double *P, double *PT, int64_t d, int nF, int k) {
+  const int64_t total = d * nF * k;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(e % k);
+    const int64_t t = e / k;
+    const int64_t j = t % d;
+    const int f = (int)(t / d);
+    PT[e] = P[(j * nF + f) * k + s];
+  }
+}
 
+// bytes of shared scratch one warp needs for E entries in flight (must match WarpScratch below)
+static inline size_t ffm_cols_warp_smem(int E) {
+  const size_t b = (size_t)E * 64 * 8 + (size_t)E * 64 * 4 + (size_t)E * 64 + (size_t)E * 4;
+  return (b + 15) & ~(size_t)15;
+}
+
+// ONE WARP PER COLUMN SEGMENT, lane <-> field (two passes for nFields > 32), every lane owns the whole k-vector of
+// its field in registers.  Per batch of E column entries: lanes < E fetch the entries' row / row pointer / coef*x;
+// each entry's row is read with coalesced loads (lane <-> position) into the warp's shared scratch together with
+// the inverse table field -> position; then lane f gathers P[j_u][f_j][0..k) for all E entries -- E*k/2 16-byte
+// loads in flight per lane -- and accumulates.  No block-wide barrier anywhere: warps run independent segments.
+// (The first form -- a block per segment, thread <-> (field, component), three __syncthreads per batch -- ran the
+// C5 shape at 21 M rows/s against 60 M for the forward kernel gathering the same bytes: barrier- and latency-bound.)
 template <int KT, int E>
-__global__ void __launch_bounds__(512) ffm_cols_grad_kernel(const FfmColArgs a) {
+__global__ void __launch_bounds__(256) ffm_cols_grad_kernel(const FfmColArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int NS = blockDim.x / KT, CH = a.CH, nF = a.nFields;
-  FfmRec *recs = reinterpret_cast<FfmRec *>(smem_raw);                           // [E][CH]
-  FfmColMeta *meta = reinterpret_cast<FfmColMeta *>(recs + (size_t)E * CH);     // [E]
-  signed char *pos = reinterpret_cast<signed char *>(meta + E);                  // [E][NS]: position of field f in row e
-  const int tid = threadIdx.x, s = tid % KT, f = tid / KT;
+  constexpr int MAXZ = 64;
+  struct WarpScratch {
+    double x[E][MAXZ];
+    int32_t jb[E][MAXZ];
+    signed char inv[E][MAXZ];   // field -> position in the row, -1: the row has no nonzero of that field
+    int fj[E];
+  };
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem_raw)[wib];
+  const int nF = a.nFields;
   const int SB8 = nF * KT;
-  for (int64_t t = blockIdx.x; t < a.nTasks; t += gridDim.x) {
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  const int64_t nWarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t t = warp; t < a.nTasks; t += nWarps) {
     const int64_t j = a.taskCol[t];
     const int32_t jb = (int32_t)(j * nF);
     int64_t eb = a.taskBeg[t], ee = eb + a.taskLen[t];
     if ((int64_t)a.crow[eb] < a.rowBegin) eb = lower_bound_row_i32(a.crow, eb, ee, a.rowBegin);
     if (eb < ee && (int64_t)a.crow[ee - 1] >= a.rowEnd) ee = lower_bound_row_i32(a.crow, eb, ee, a.rowEnd);
-    double acc = 0.0, accW = 0.0;
+    double acc0[KT], acc1[KT], accW = 0.0;
+#pragma unroll
+    for (int c = 0; c < KT; ++c) acc0[c] = acc1[c] = 0.0;
     for (int64_t e0 = eb; e0 < ee; e0 += E) {
       const int nb = (int)(ee - e0 < E ? ee - e0 : E);
-      if (tid < nb) {
-        const int64_t e = e0 + tid, row = a.crow[e];
-        FfmColMeta m;
-        m.rb = a.indptr[row];
-        m.z = (int)(a.indptr[row + 1] - m.rb);
-        m.cx = a.coef[row - a.rowBegin] * a.cdata[e];
-        m.fj = 0;
-        meta[tid] = m;
+      int64_t rbL = 0;
+      int zL = 0;
+      double cxL = 0.0;
+      if (lane < nb) {
+        const int64_t e = e0 + lane, row = a.crow[e];
+        rbL = a.indptr[row];
+        zL = (int)(a.indptr[row + 1] - rbL);
+        cxL = a.coef[row - a.rowBegin] * a.cdata[e];
       }
-      for (int q = tid; q < E * NS; q += blockDim.x) pos[q] = -1;
-      __syncthreads();
-      for (int q = tid; q < nb * CH; q += blockDim.x) {
-        const int e = q / CH, u = q - e * CH;
-        if (u < meta[e].z) {
-          const int64_t at = meta[e].rb + u;
-          FfmRec r;
-          const int32_t idx = a.indices[at];
-          r.jb = idx * nF;
-          r.f = a.fields[at];
-          r.x = a.data[at];
-          recs[e * CH + u] = r;
-          pos[e * NS + r.f] = (signed char)u;
-          if (idx == (int32_t)j) meta[e].fj = r.f;
+      __syncwarp();   // the previous batch's readers are done with the scratch
+#pragma unroll
+      for (int i = 0; i < E; ++i) {
+        ws.inv[i][lane] = -1;
+        ws.inv[i][lane + 32] = -1;
+      }
+      __syncwarp();
+      double cx[E];
+#pragma unroll
+      for (int i = 0; i < E; ++i) {
+        const int64_t rb = __shfl_sync(0xffffffffu, rbL, i);
+        const int z = __shfl_sync(0xffffffffu, zL, i);
+        cx[i] = __shfl_sync(0xffffffffu, cxL, i);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int u = lane + 32 * half;
+          if (i < nb && u < z) {
+            const int32_t idx = a.indices[rb + u];
+            const int fld = a.fields[rb + u];
+            ws.x[i][u] = a.data[rb + u];
+            ws.jb[i][u] = idx;
+            ws.inv[i][fld] = (signed char)u;
+            if (idx == (int32_t)j) ws.fj[i] = fld;
+          }
         }
       }
-      __syncthreads();
-      if (f < nF) {
-        double v[E], sc[E];
+      __syncwarp();
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-          v[e] = 0.0;
-          sc[e] = 0.0;
-          if (e < nb) {
-            const int u = pos[e * NS + f];
-            if (u >= 0) {
-              const FfmRec r = recs[e * CH + u];
-              if (r.jb != jb) {   // the reference pairs distinct features only
-                v[e] = __ldg(a.P + (int64_t)(r.jb + meta[e].fj) * KT + s);   // P[j_u][f_j][s]
-                sc[e] = meta[e].cx * r.x;
+      for (int pass = 0; pass < 2; ++pass) {
+        const int f = lane + 32 * pass;
+        if (pass == 1 && nF <= 32) break;
+        double v[E][KT], sc[E];
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+          sc[i] = 0.0;
+#pragma unroll
+          for (int c = 0; c < KT; ++c) v[i][c] = 0.0;
+          if (i < nb && f < nF) {
+            const int u = ws.inv[i][f];
+            if (u >= 0 && ws.jb[i][u] != (int32_t)j) {   // the reference pairs distinct features only
+              const double2 *src = reinterpret_cast<const double2 *>(a.PT + ((int64_t)ws.fj[i] * a.d + ws.jb[i][u]) * KT);   // P[j_u][f_j][:]
+#pragma unroll
+              for (int c = 0; c < KT / 2; ++c) {
+                const double2 q = __ldg(src + c);
+                v[i][2 * c] = q.x;
+                v[i][2 * c + 1] = q.y;
               }
+              sc[i] = cx[i] * ws.x[i][u];
             }
           }
         }
 #pragma unroll
-        for (int e = 0; e < E; ++e) acc += sc[e] * v[e];   // entries in ascending row order
+        for (int i = 0; i < E; ++i)   // entries in ascending row order
+#pragma unroll
+          for (int c = 0; c < KT; ++c) {
+            if (pass == 0) acc0[c] += sc[i] * v[i][c];
+            else acc1[c] += sc[i] * v[i][c];
+          }
       }
-      if (tid == 0)
-        for (int e = 0; e < nb; ++e) accW += meta[e].cx;
-      __syncthreads();
+      if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < E; ++i)
+          if (i < nb) accW += cx[i];
     }
     const int slot = a.taskSlot[t];
-    if (slot < 0) {
-      if (f < nF) a.gP[(int64_t)(jb + f) * KT + s] += acc;
-      if (tid == 0 && a.fitLinear) a.gw[j] += accW;
-    } else {
-      double *ps = a.partial + (size_t)slot * (SB8 + 1);
-      if (f < nF) ps[f * KT + s] = acc;
-      if (tid == 0) ps[SB8] = accW;
+    double *dst = slot < 0 ? a.gP + (int64_t)jb * KT : a.partial + (size_t)slot * (SB8 + 1);
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int f = lane + 32 * pass;
+      if (f < nF) {
+#pragma unroll
+        for (int c = 0; c < KT; ++c) {
+          const double val = pass == 0 ? acc0[c] : acc1[c];
+          if (slot < 0) dst[f * KT + c] += val;
+          else dst[f * KT + c] = val;
+        }
+      }
+    }
+    if (lane == 0) {
+      if (slot < 0) { if (a.fitLinear) a.gw[j] += accW; }
+      else dst[SB8] = accW;
     }
   }
 }

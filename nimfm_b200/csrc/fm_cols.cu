@@ -195,7 +195,12 @@ void nimfm_det_twin_free(nimfm_ctx *ctx, nimfm_det_twin *t) {
 static int build_twin(nimfm_ctx *ctx, const nimfm_dataset *X, int nAug, nimfm_det_twin **out) {
   nimfm_det_twin *t = new nimfm_det_twin();
   struct Guard { nimfm_ctx *c; nimfm_det_twin *t; ~Guard() { if (t) nimfm_det_twin_free(c, t); } } guard{ctx, t};
-  int rc = nimfm_dataset_transpose(ctx, X, &t->csc);
+  nimfm_dataset view = *X;      // a plain-CSR view of the same device arrays (a field dataset's fields play no part here)
+  view.kind = NIMFM_DS_CSR;
+  view.fields = nullptr;
+  view.y = nullptr;
+  view.detTwin = nullptr;
+  int rc = nimfm_dataset_transpose(ctx, &view, &t->csc);
   if (rc) return rc;
   const int64_t d = X->d, n = X->n;
   std::vector<int64_t> ptr((size_t)d + 1);
