@@ -398,6 +398,198 @@ __global__ void __launch_bounds__(SGD_THREADS, 1) sgd_fm_staged_kernel(const Sgd
   }
 }
 
+// The FM sample loop, PIPELINED (the default): the staged kernel above spends most of a sample waiting on a chain of
+// dependent global loads (permutation -> indptr -> indices / values -> scalings, w -> P rows: 23 us per C4 sample,
+// 43 K samples/s -- slower than one host core on the same loop).  Here
+//   * the CSR side of the chain is read-only, so it is fetched AHEAD: the last warp loads sample q+2's row pointer
+//     and target and sample q+1's indices / values into a second set of shared buffers while sample q computes;
+//   * what depends on the previous update (scalings, w, the P rows) is one round of independent loads issued by all
+//     512 threads at once; eta (a pow()) is computed by one otherwise idle thread in that shadow;
+//   * the forward DP keeps the reference's order (thread <-> (order, component), nonzeros in row order), leaves
+//     A[.][1..M-1] in shared memory, and the derivative + update + write-back is spread over ALL threads
+//     (element <-> thread), straight from shared memory to global.
+// Same arithmetic per parameter element as sgd_epoch_kernel<false>; viol is summed in a different order.
+// dynamic smem: sP[zmax*SB8] | sA[SB8*(MAXDEG+1)] | sX[2][zmax] | sW[zmax] | sSc[zmax] | sJ[2][zmax] (int32)
+#define SGDP_THREADS 512
+struct SgdPipeMeta {
+  int64_t i, rb;
+  double y;
+  int z;
+};
+
+__global__ void __launch_bounds__(SGDP_THREADS, 1) sgd_fm_pipe_kernel(const SgdArgs a, int zmax) {
+  extern __shared__ __align__(16) unsigned char sgd_smem[];
+  __shared__ double red[SGDP_THREADS / 32];
+  __shared__ double sh[8];              // [1] scaling_P, [2] scaling_w, [3] dL, [4..6] eta_P, eta_w, eta_b of this sample
+  __shared__ SgdPipeMeta meta[3];       // ring: sample q lives in meta[q % 3]
+  const int k = a.k, NO = a.nOrders, SB8 = NO * k, AST = NIMFM_MAX_DEGREE + 1;
+  double *sP = reinterpret_cast<double *>(sgd_smem);
+  double *sA = sP + (size_t)zmax * SB8;
+  double *sXb = sA + (size_t)SB8 * AST;
+  double *sW = sXb + 2 * (size_t)zmax;
+  double *sSc = sW + zmax;
+  int32_t *sJb = reinterpret_cast<int32_t *>(sSc + zmax);
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int lastWarp0 = nth - 32;       // the prefetching warp
+  double viol = 0.0, lossAcc = 0.0;
+  const double alpha0 = a.cfg.alpha0, alpha = a.cfg.alpha, beta = a.cfg.beta;
+
+  auto load_meta = [&](int64_t q) {     // one thread: permutation -> row pointer, row length, target
+    SgdPipeMeta m;
+    m.i = a.perm ? (int64_t)a.perm[q] : q;
+    m.rb = a.indptr[m.i];
+    m.z = (int)(a.indptr[m.i + 1] - m.rb);
+    m.y = a.y[m.i];
+    meta[q % 3] = m;
+  };
+  auto load_row = [&](int64_t q, int lane0) {   // one warp: indices / values (+ dummy features) of sample q
+    const SgdPipeMeta m = meta[q % 3];
+    int32_t *J = sJb + (q & 1) * zmax;
+    double *X = sXb + (q & 1) * zmax;
+    for (int u = tid - lane0; u < m.z + a.nAug; u += 32) {
+      if (u < m.z) {
+        J[u] = a.indices[m.rb + u];
+        X[u] = a.data[m.rb + u];
+      } else {
+        J[u] = (int32_t)(a.d + (u - m.z));
+        X[u] = 1.0;
+      }
+    }
+  };
+  if (tid == 0) {
+    sh[1] = a.scal[0];
+    sh[2] = a.scal[1];
+    if (a.nRows > 0) load_meta(0);
+    if (a.nRows > 1) load_meta(1);
+  }
+  __syncthreads();
+  if (tid >= lastWarp0 && a.nRows > 0) load_row(0, lastWarp0);
+  __syncthreads();
+
+  for (int64_t q = 0; q < a.nRows; ++q) {
+    const int64_t it = a.it0 + q;
+    const SgdPipeMeta m = meta[q % 3];
+    const int zReal = m.z, z = zReal + a.nAug;
+    const int32_t *J = sJb + (q & 1) * zmax;
+    const double *X = sXb + (q & 1) * zmax;
+    const double scP = sh[1], scW = sh[2];
+    // ---- phase 1: everything that depends on the previous update, in one round of independent loads
+    if (tid < z) {
+      if (tid < zReal) {
+        const int64_t j = J[tid];
+        sSc[tid] = scP / a.scalingsP[j];                    // lazilyUpdate, sgd.nim:134-143 (real features only)
+        double wv = a.w[j];
+        if (a.fitLinear) wv *= scW / a.scalingsW[j];
+        sW[tid] = wv;
+      } else {
+        sSc[tid] = 1.0;
+        sW[tid] = 0.0;
+      }
+    }
+    for (int e = tid; e < z * SB8; e += nth) {
+      const int u = e / SB8, off = e - u * SB8;
+      sP[e] = a.P[(int64_t)J[u] * SB8 + off];
+    }
+    if (tid == nth - 33) {                                   // an idle thread of the second-to-last warp: the step sizes
+      sh[4] = dev_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, beta, it);
+      sh[5] = dev_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, alpha, it);
+      sh[6] = dev_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, alpha0, it);
+    }
+    if (tid == nth - 1 && q + 2 < a.nRows) load_meta(q + 2);           // read-only side of the chain, two samples ahead
+    if (tid >= lastWarp0 && q + 1 < a.nRows) load_row(q + 1, lastWarp0);   // ... and one sample ahead
+    __syncthreads();
+    for (int e = tid; e < zReal * SB8; e += nth) sP[e] *= sSc[e / SB8];
+    __syncthreads();
+    // ---- predictWithGrad: forward, thread <-> (order, component), nonzeros in row order (sgd.nim:146-173)
+    double part = 0.0;
+    for (int u = tid; u < zReal; u += nth) part += sW[u] * X[u];
+    if (tid < SB8) {
+      const int o = tid / k, sc = tid - o * k;
+      const int M = a.degree - o;
+      double A[NIMFM_MAX_DEGREE + 1];
+      A[0] = 1.0;
+      for (int t = 1; t <= M; t++) A[t] = 0.0;
+      for (int u = 0; u < z; u++) {
+        const double tv = sP[u * SB8 + o * k + sc] * X[u];
+        if (M == 2) {
+          A[1] += tv;
+          A[2] += tv * tv;
+        } else {
+          for (int t = M; t >= 1; t--) A[t] += A[t - 1] * tv;
+        }
+      }
+      part += M == 2 ? (A[1] * A[1] - A[2]) / 2.0 : A[M];
+      for (int t = 1; t < M; t++) sA[tid * AST + t] = A[t];
+    }
+    const double yh = block_sum(part, red);
+    if (tid == 0) {
+      const double yhat = yh + a.b[0];
+      lossAcc += dev_loss(a.cfg.loss, a.cfg.huberThreshold, m.y, yhat);
+      sh[3] = dev_dloss(a.cfg.loss, a.cfg.huberThreshold, m.y, yhat);
+    }
+    __syncthreads();
+    const double dL = sh[3], etaP = sh[4], etaW = sh[5];
+    // ---- update (sgd.nim:205-243): element <-> thread, derivative recurrence from the stored A (sgd.nim:176-188)
+    for (int e = tid; e < z * SB8; e += nth) {
+      const int u = e / SB8, os = e - u * SB8;
+      const int M = a.degree - os / k;
+      const double x = X[u], p = sP[e];
+      const double *A = sA + os * AST;
+      double g;
+      if (M == 2) g = x * (A[1] - p * x);
+      else {
+        g = x;
+        for (int t = 1; t < M; t++) g = x * (A[t] - p * g);
+      }
+      const double upd = etaP * (dL * g + beta * p);
+      viol += fabs(upd);
+      a.P[(int64_t)J[u] * SB8 + os] = p - upd;
+    }
+    const double nscP = scP * (1 - etaP * beta), nscW = scW * (1 - etaW * alpha);
+    if (tid < zReal) {
+      const int64_t j = J[tid];
+      if (a.fitLinear) {                                    // fitLinearSGD, fit_linear.nim:41-47
+        const double upd = etaW * (dL * X[tid] + alpha * sW[tid]);
+        a.w[j] = sW[tid] - upd;
+        viol += fabs(upd);
+      }
+      a.scalingsP[j] = nscP;
+      a.scalingsW[j] = nscW;
+    } else if (tid < z) {
+      a.scalingsP[a.d + (tid - zReal)] = nscP;
+    }
+    if (tid == 0) {
+      if (a.fitIntercept) {
+        const double upd = sh[6] * (dL + alpha0 * a.b[0]);
+        viol += fabs(upd);
+        a.b[0] -= upd;
+      }
+      sh[1] = nscP;
+      sh[2] = nscW;
+    }
+    __syncthreads();
+    // ---- resetScaling (sgd.nim:116-131)
+    const bool resetW = a.fitLinear && nscW < 1e-9, resetP = nscP < 1e-9;
+    if (resetW || resetP) {
+      sgd_materialize(a, SB8, a.d, resetW, resetP, nscP, nscW);
+      if (tid == 0) {
+        if (resetW) sh[2] = 1.0;
+        if (resetP) sh[1] = 1.0;
+      }
+      __syncthreads();
+    }
+  }
+  viol = block_sum(viol, red);
+  __syncthreads();
+  lossAcc = block_sum(lossAcc, red);
+  if (tid == 0) {
+    a.scal[0] = sh[1];
+    a.scal[1] = sh[2];
+    a.scal[2] = viol;
+    a.scal[3] = lossAcc;
+  }
+}
+
 // finalize (sgd.nim:99-113)
 template <bool FFM>
 __global__ void __launch_bounds__(SGD_THREADS, 1) sgd_finalize_kernel(const SgdArgs a) {
@@ -480,7 +672,11 @@ int32_t nimfm_fm_sgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X,
   const int zmax = (int)std::max<int64_t>(X->maxSegNnz + fm->nAug, 1);
   const size_t smem = ((size_t)zmax * SB8 + 3 * (size_t)zmax) * 8 + (size_t)zmax * 8;
   const char *env = getenv("NIMFM_SGD_KERNEL");
-  if (SB8 <= SGD_THREADS && smem <= (size_t)ctx->smemOptin - 2048 && !(env && !strcmp(env, "unstaged"))) {
+  const size_t smemPipe = ((size_t)zmax * SB8 + (size_t)SB8 * (NIMFM_MAX_DEGREE + 1) + 4 * (size_t)zmax) * 8 + 2 * (size_t)zmax * 4 + 16;
+  if (SB8 <= SGDP_THREADS - 64 && zmax <= SGDP_THREADS - 64 && smemPipe <= (size_t)ctx->smemOptin - 4096 && !env) {
+    CK(cudaFuncSetAttribute(sgd_fm_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemPipe));
+    sgd_fm_pipe_kernel<<<1, SGDP_THREADS, smemPipe, ctx->stream>>>(a, zmax);
+  } else if (SB8 <= SGD_THREADS && smem <= (size_t)ctx->smemOptin - 2048 && !(env && !strcmp(env, "unstaged"))) {
     CK(cudaFuncSetAttribute(sgd_fm_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     sgd_fm_staged_kernel<<<1, SGD_THREADS, smem, ctx->stream>>>(a, zmax);
   } else {
