@@ -81,41 +81,54 @@ static __global__ void __launch_bounds__(ADASEQ_THREADS, 1) adagrad_fm_seq_kerne
     __syncthreads();
     // ---- stage P / g_sum / g_norm of the row's features; update() of P (adagrad.nim:93-99)
     const double tmpP = a.eta0 * t * a.beta;
-    for (int e = tid; e < z * SB8; e += nth) {
-      const int u = e / SB8, off = e - u * SB8;
-      const int64_t ge = sJ[u] * SB8 + off;
-      const double gs = a.gsP[ge], gn = a.gnP[ge];
-      double p = a.P[ge];
-      if (refresh) {
-        const double pn = -(a.eta0 * gs) / (tmpP + sqrt(gn));
-        viol += fabs(p - pn);
-        p = pn;
+    for (int base = tid; base < z * SB8; base += 5 * nth) {   // all loads of a batch first: one memory latency per
+      double gsv[5], gnv[5], pv[5];                             // batch instead of one per element
+#pragma unroll
+      for (int r = 0; r < 5; ++r) {
+        const int e = base + r * nth;
+        const bool ok = e < z * SB8;
+        const int64_t ge = ok ? sJ[e / SB8] * SB8 + (e % SB8) : 0;
+        gsv[r] = ok ? a.gsP[ge] : 0.0;
+        gnv[r] = ok ? a.gnP[ge] : 1.0;
+        pv[r] = ok ? a.P[ge] : 0.0;
       }
-      sP[e] = p;
-      sGs[e] = gs;
-      sGn[e] = gn;
+#pragma unroll
+      for (int r = 0; r < 5; ++r) {
+        const int e = base + r * nth;
+        if (e < z * SB8) {
+          double p = pv[r];
+          if (refresh) {
+            const double pn = -(a.eta0 * gsv[r]) / (tmpP + sqrt(gnv[r]));
+            viol += fabs(p - pn);
+            p = pn;
+          }
+          sP[e] = p;
+          sGs[e] = gsv[r];
+          sGn[e] = gnv[r];
+        }
+      }
     }
     __syncthreads();
     // ---- predictWithGrad forward (thread <-> (order, component)); A stays in registers
     double part = 0.0;
     for (int u = tid; u < zReal; u += nth) part += sW[u] * sX[u];
-    double A[NIMFM_MAX_DEGREE + 1];
+    AnovaState A;
     const int os = tid;
     const int o = os < SB8 ? os / k : 0, sc = os - o * k;
     const int M = a.degree - o;
     if (os < SB8) {
-      A[0] = 1.0;
-      for (int tt = 1; tt <= M; tt++) A[tt] = 0.0;
+      anova_init(A);
+#pragma unroll 4
       for (int u = 0; u < z; u++) {
         const double tv = sP[u * SB8 + o * k + sc] * sX[u];
         if (M == 2) {
           A[1] += tv;
           A[2] += tv * tv;
         } else {
-          for (int tt = M; tt >= 1; tt--) A[tt] += A[tt - 1] * tv;
+          anova_step(A, M, tv);
         }
       }
-      part += M == 2 ? (A[1] * A[1] - A[2]) / 2.0 : A[M];
+      part += M == 2 ? (A[1] * A[1] - A[2]) / 2.0 : anova_at(A, M);
     }
     double yhat = block_sum(part, red);
     if (tid == 0) {
@@ -129,6 +142,7 @@ static __global__ void __launch_bounds__(ADASEQ_THREADS, 1) adagrad_fm_seq_kerne
     const double dL = sh[1];
     // ---- updateG (adagrad.nim:113-134)
     if (os < SB8) {
+#pragma unroll 4
       for (int u = 0; u < z; u++) {
         const double x = sX[u];
         const int e = u * SB8 + o * k + sc;
@@ -136,8 +150,7 @@ static __global__ void __launch_bounds__(ADASEQ_THREADS, 1) adagrad_fm_seq_kerne
         double g;
         if (M == 2) g = x * (A[1] - p * x);
         else {
-          g = x;
-          for (int tt = 1; tt < M; tt++) g = x * (A[tt] - p * g);
+          g = anova_deriv(A, M, x, p);
         }
         const double grad = dL * g;
         sGs[e] += grad;

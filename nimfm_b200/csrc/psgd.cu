@@ -139,23 +139,22 @@ __global__ void __launch_bounds__(PSGD_THREADS, 1) psgd_lazy_kernel(const PsgdAr
     // ---- predictWithGrad forward (thread <-> (order, component)); A stays in registers
     double part = 0.0;
     for (int u = tid; u < zReal; u += nth) part += sW[u] * sX[u];
-    double A[NIMFM_MAX_DEGREE + 1];
+    AnovaState A;
     const int os = tid;
     const int o = os < SB8 ? os / k : 0, sc = os - o * k;
     const int M = a.degree - o;
     if (os < SB8) {
-      A[0] = 1.0;
-      for (int t = 1; t <= M; t++) A[t] = 0.0;
+      anova_init(A);
       for (int u = 0; u < z; u++) {
         const double tv = sP[u * SB8 + o * k + sc] * sX[u];
         if (M == 2) {
           A[1] += tv;
           A[2] += tv * tv;
         } else {
-          for (int t = M; t >= 1; t--) A[t] += A[t - 1] * tv;
+          anova_step(A, M, tv);
         }
       }
-      part += M == 2 ? (A[1] * A[1] - A[2]) / 2.0 : A[M];
+      part += M == 2 ? (A[1] * A[1] - A[2]) / 2.0 : anova_at(A, M);
     }
     double yhat = block_sum(part, red);
     if (tid == 0) {
@@ -179,8 +178,7 @@ __global__ void __launch_bounds__(PSGD_THREADS, 1) psgd_lazy_kernel(const PsgdAr
         double g;
         if (M == 2) g = x * (A[1] - p * x);
         else {
-          g = x;
-          for (int t = 1; t < M; t++) g = x * (A[t] - p * g);
+          g = anova_deriv(A, M, x, p);
         }
         const double upd = etaS * (dL * g + beta * p);
         sP[e] = isL1 ? psgd_soft(p - upd, gamma * etaS) : p - upd;

@@ -101,9 +101,8 @@ __global__ void __launch_bounds__(SGD_THREADS, 1) sgd_epoch_kernel(const SgdArgs
       for (int os = tid; os < SB8; os += nth) {          // thread <-> (order, component)
         const int o = os / k, s = os - o * k;
         const int M = a.degree - o;
-        double A[NIMFM_MAX_DEGREE + 1];
-        A[0] = 1.0;
-        for (int t = 1; t <= M; t++) A[t] = 0.0;
+        AnovaState A;
+        anova_init(A);
         for (int u = 0; u < z; u++) {
           const int64_t j = u < zReal ? (int64_t)a.indices[rb + u] : a.d + (u - zReal);
           const double x = u < zReal ? a.data[rb + u] : 1.0;
@@ -112,11 +111,11 @@ __global__ void __launch_bounds__(SGD_THREADS, 1) sgd_epoch_kernel(const SgdArgs
             A[1] += tv;
             A[2] += tv * tv;
           } else {
-            for (int t = M; t >= 1; t--) A[t] += A[t - 1] * tv;
+            anova_step(A, M, tv);
           }
         }
         if (M == 2) A[2] = (A[1] * A[1] - A[2]) / 2.0;
-        part += A[M];
+        part += anova_at(A, M);
       }
     } else {
       // dA[u][f][s] = sum_{b != u, field_b == f} x_u x_b P[j_b][f_u][s]   (sgd_ffm.nim:18-30)
@@ -159,16 +158,15 @@ __global__ void __launch_bounds__(SGD_THREADS, 1) sgd_epoch_kernel(const SgdArgs
         const int o = os / k, s = os - o * k;
         const int M = a.degree - o;
         // recompute the DP state of this (order, component), then the derivative recurrence (sgd.nim:176-188)
-        double A[NIMFM_MAX_DEGREE + 1];
-        A[0] = 1.0;
-        for (int t = 1; t <= M; t++) A[t] = 0.0;
+        AnovaState A;
+        anova_init(A);
         for (int u = 0; u < z; u++) {
           const int64_t j = u < zReal ? (int64_t)a.indices[rb + u] : a.d + (u - zReal);
           const double x = u < zReal ? a.data[rb + u] : 1.0;
           const double tv = a.P[j * SB8 + o * k + s] * x;
           if (M == 2) A[1] += tv;
           else
-            for (int t = M; t >= 1; t--) A[t] += A[t - 1] * tv;
+            anova_step(A, M, tv);
         }
         for (int u = 0; u < z; u++) {
           const int64_t j = u < zReal ? (int64_t)a.indices[rb + u] : a.d + (u - zReal);
@@ -178,8 +176,7 @@ __global__ void __launch_bounds__(SGD_THREADS, 1) sgd_epoch_kernel(const SgdArgs
           double g;
           if (M == 2) g = x * (A[1] - p * x);
           else {
-            g = x;
-            for (int t = 1; t < M; t++) g = x * (A[t] - p * g);
+            g = anova_deriv(A, M, x, p);
           }
           const double upd = etaP * (dL * g + beta * p);
           viol += fabs(upd);
@@ -302,23 +299,22 @@ __global__ void __launch_bounds__(SGD_THREADS, 1) sgd_fm_staged_kernel(const Sgd
     // ---- predictWithGrad: forward (thread <-> (order, component)); A stays in registers for the update
     double part = 0.0;
     for (int u = tid; u < zReal; u += nth) part += sW[u] * sX[u];
-    double A[NIMFM_MAX_DEGREE + 1];
+    AnovaState A;
     const int os = tid;
     const int o = os < SB8 ? os / k : 0, sc = os - o * k;
     const int M = a.degree - o;
     if (os < SB8) {
-      A[0] = 1.0;
-      for (int t = 1; t <= M; t++) A[t] = 0.0;
+      anova_init(A);
       for (int u = 0; u < z; u++) {
         const double tv = sP[u * SB8 + o * k + sc] * sX[u];
         if (M == 2) {
           A[1] += tv;
           A[2] += tv * tv;
         } else {
-          for (int t = M; t >= 1; t--) A[t] += A[t - 1] * tv;
+          anova_step(A, M, tv);
         }
       }
-      part += M == 2 ? (A[1] * A[1] - A[2]) / 2.0 : A[M];
+      part += M == 2 ? (A[1] * A[1] - A[2]) / 2.0 : anova_at(A, M);
     }
     double yhat = block_sum(part, red);
     if (tid == 0) {
@@ -341,8 +337,7 @@ __global__ void __launch_bounds__(SGD_THREADS, 1) sgd_fm_staged_kernel(const Sgd
         double g;
         if (M == 2) g = x * (A[1] - p * x);
         else {
-          g = x;
-          for (int t = 1; t < M; t++) g = x * (A[t] - p * g);
+          g = anova_deriv(A, M, x, p);
         }
         const double upd = etaP * (dL * g + beta * p);
         viol += fabs(upd);
@@ -421,7 +416,7 @@ __global__ void __launch_bounds__(SGDP_THREADS, 1) sgd_fm_pipe_kernel(const SgdA
   extern __shared__ __align__(16) unsigned char sgd_smem[];
   __shared__ double red[SGDP_THREADS / 32];
   __shared__ double sh[8];              // [1] scaling_P, [2] scaling_w, [3] dL, [4..6] eta_P, eta_w, eta_b of this sample
-  __shared__ SgdPipeMeta meta[3];       // ring: sample q lives in meta[q % 3]
+  __shared__ SgdPipeMeta meta[4];       // ring: sample q lives in meta[q & 3]
   const int k = a.k, NO = a.nOrders, SB8 = NO * k, AST = NIMFM_MAX_DEGREE + 1;
   double *sP = reinterpret_cast<double *>(sgd_smem);
   double *sA = sP + (size_t)zmax * SB8;
@@ -432,47 +427,70 @@ __global__ void __launch_bounds__(SGDP_THREADS, 1) sgd_fm_pipe_kernel(const SgdA
   const int tid = threadIdx.x, nth = blockDim.x;
   const int lastWarp0 = nth - 32;       // the prefetching warp
   double viol = 0.0, lossAcc = 0.0;
+  long long prof[4] = {0, 0, 0, 0};
   const double alpha0 = a.cfg.alpha0, alpha = a.cfg.alpha, beta = a.cfg.beta;
 
-  auto load_meta = [&](int64_t q) {     // one thread: permutation -> row pointer, row length, target
-    SgdPipeMeta m;
-    m.i = a.perm ? (int64_t)a.perm[q] : q;
-    m.rb = a.indptr[m.i];
-    m.z = (int)(a.indptr[m.i + 1] - m.rb);
-    m.y = a.y[m.i];
-    meta[q % 3] = m;
-  };
-  auto load_row = [&](int64_t q, int lane0) {   // one warp: indices / values (+ dummy features) of sample q
-    const SgdPipeMeta m = meta[q % 3];
-    int32_t *J = sJb + (q & 1) * zmax;
-    double *X = sXb + (q & 1) * zmax;
-    for (int u = tid - lane0; u < m.z + a.nAug; u += 32) {
-      if (u < m.z) {
-        J[u] = a.indices[m.rb + u];
-        X[u] = a.data[m.rb + u];
-      } else {
-        J[u] = (int32_t)(a.d + (u - m.z));
-        X[u] = 1.0;
-      }
-    }
-  };
+  // prologue: the read-only chain of the first samples, loaded the plain way
   if (tid == 0) {
     sh[1] = a.scal[0];
     sh[2] = a.scal[1];
-    if (a.nRows > 0) load_meta(0);
-    if (a.nRows > 1) load_meta(1);
+    for (int64_t q = 0; q < 3 && q < a.nRows; ++q) {
+      SgdPipeMeta m;
+      m.i = a.perm ? (int64_t)a.perm[q] : q;
+      if (q < 2) {
+        m.rb = a.indptr[m.i];
+        m.z = (int)(a.indptr[m.i + 1] - m.rb);
+        m.y = a.y[m.i];
+      }
+      meta[q & 3] = m;
+    }
   }
   __syncthreads();
-  if (tid >= lastWarp0 && a.nRows > 0) load_row(0, lastWarp0);
+  if (tid >= lastWarp0 && a.nRows > 0) {
+    const SgdPipeMeta m = meta[0];
+    for (int u = tid - lastWarp0; u < m.z + a.nAug; u += 32) {
+      sJb[u] = u < m.z ? a.indices[m.rb + u] : (int32_t)(a.d + (u - m.z));
+      sXb[u] = u < m.z ? a.data[m.rb + u] : 1.0;
+    }
+  }
   __syncthreads();
 
   for (int64_t q = 0; q < a.nRows; ++q) {
     const int64_t it = a.it0 + q;
-    const SgdPipeMeta m = meta[q % 3];
+    const SgdPipeMeta m = meta[q & 3];
     const int zReal = m.z, z = zReal + a.nAug;
+    // ---- the read-only side of the chain, fetched AHEAD into registers by the last warp; each stage is a single
+    // level of loads issued here and parked in shared memory at the END of the iteration, so the warp never waits
+    // on them before the block's barriers: sample q+3's row id, q+2's row pointer / target, q+1's indices / values
+    int64_t pfI = 0, pfRb = 0, pfRe = 0;
+    double pfY = 0.0, pfX0 = 0.0, pfX1 = 0.0;
+    int32_t pfJ0 = 0, pfJ1 = 0;
+    if (tid == nth - 1) {
+      if (q + 3 < a.nRows) pfI = a.perm ? (int64_t)a.perm[q + 3] : q + 3;
+      if (q + 2 < a.nRows) {
+        const int64_t i2 = meta[(q + 2) & 3].i;
+        pfRb = a.indptr[i2];
+        pfRe = a.indptr[i2 + 1];
+        pfY = a.y[i2];
+      }
+    }
+    const SgdPipeMeta m1 = meta[(q + 1) & 3];
+    const int z1 = q + 1 < a.nRows ? m1.z + a.nAug : 0;
+    if (tid >= lastWarp0) {                                  // up to 64 nonzeros per row through this path
+      const int u0 = tid - lastWarp0, u1 = u0 + 32;
+      if (u0 < z1) {
+        pfJ0 = u0 < m1.z ? a.indices[m1.rb + u0] : (int32_t)(a.d + (u0 - m1.z));
+        pfX0 = u0 < m1.z ? a.data[m1.rb + u0] : 1.0;
+      }
+      if (u1 < z1) {
+        pfJ1 = u1 < m1.z ? a.indices[m1.rb + u1] : (int32_t)(a.d + (u1 - m1.z));
+        pfX1 = u1 < m1.z ? a.data[m1.rb + u1] : 1.0;
+      }
+    }
     const int32_t *J = sJb + (q & 1) * zmax;
     const double *X = sXb + (q & 1) * zmax;
     const double scP = sh[1], scW = sh[2];
+    long long c0 = clock64();
     // ---- phase 1: everything that depends on the previous update, in one round of independent loads
     if (tid < z) {
       if (tid < zReal) {
@@ -486,18 +504,26 @@ __global__ void __launch_bounds__(SGDP_THREADS, 1) sgd_fm_pipe_kernel(const SgdA
         sW[tid] = 0.0;
       }
     }
-    for (int e = tid; e < z * SB8; e += nth) {
-      const int u = e / SB8, off = e - u * SB8;
-      sP[e] = a.P[(int64_t)J[u] * SB8 + off];
+    for (int base = tid; base < z * SB8; base += 6 * nth) {   // all loads of a batch before the first store: one
+      double pr[6];                                            // memory latency per batch, not one per element
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        const int e = base + r * nth;
+        pr[r] = e < z * SB8 ? a.P[(int64_t)J[e / SB8] * SB8 + (e % SB8)] : 0.0;
+      }
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        const int e = base + r * nth;
+        if (e < z * SB8) sP[e] = pr[r];
+      }
     }
     if (tid == nth - 33) {                                   // an idle thread of the second-to-last warp: the step sizes
       sh[4] = dev_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, beta, it);
       sh[5] = dev_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, alpha, it);
       sh[6] = dev_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, alpha0, it);
     }
-    if (tid == nth - 1 && q + 2 < a.nRows) load_meta(q + 2);           // read-only side of the chain, two samples ahead
-    if (tid >= lastWarp0 && q + 1 < a.nRows) load_row(q + 1, lastWarp0);   // ... and one sample ahead
     __syncthreads();
+    long long c1 = clock64();
     for (int e = tid; e < zReal * SB8; e += nth) sP[e] *= sSc[e / SB8];
     __syncthreads();
     // ---- predictWithGrad: forward, thread <-> (order, component), nonzeros in row order (sgd.nim:146-173)
@@ -506,21 +532,24 @@ __global__ void __launch_bounds__(SGDP_THREADS, 1) sgd_fm_pipe_kernel(const SgdA
     if (tid < SB8) {
       const int o = tid / k, sc = tid - o * k;
       const int M = a.degree - o;
-      double A[NIMFM_MAX_DEGREE + 1];
-      A[0] = 1.0;
-      for (int t = 1; t <= M; t++) A[t] = 0.0;
+      AnovaState A;
+      anova_init(A);
+#pragma unroll 4
       for (int u = 0; u < z; u++) {
         const double tv = sP[u * SB8 + o * k + sc] * X[u];
         if (M == 2) {
           A[1] += tv;
           A[2] += tv * tv;
         } else {
-          for (int t = M; t >= 1; t--) A[t] += A[t - 1] * tv;
+          anova_step(A, M, tv);
         }
       }
-      part += M == 2 ? (A[1] * A[1] - A[2]) / 2.0 : A[M];
-      for (int t = 1; t < M; t++) sA[tid * AST + t] = A[t];
+      part += M == 2 ? (A[1] * A[1] - A[2]) / 2.0 : anova_at(A, M);
+#pragma unroll
+      for (int t = 1; t < NIMFM_MAX_DEGREE; ++t)
+        if (t < M) sA[tid * AST + t] = A[t];
     }
+    long long c2 = clock64();
     const double yh = block_sum(part, red);
     if (tid == 0) {
       const double yhat = yh + a.b[0];
@@ -529,7 +558,9 @@ __global__ void __launch_bounds__(SGDP_THREADS, 1) sgd_fm_pipe_kernel(const SgdA
     }
     __syncthreads();
     const double dL = sh[3], etaP = sh[4], etaW = sh[5];
+    long long c3 = clock64();
     // ---- update (sgd.nim:205-243): element <-> thread, derivative recurrence from the stored A (sgd.nim:176-188)
+#pragma unroll 2
     for (int e = tid; e < z * SB8; e += nth) {
       const int u = e / SB8, os = e - u * SB8;
       const int M = a.degree - os / k;
@@ -539,7 +570,7 @@ __global__ void __launch_bounds__(SGDP_THREADS, 1) sgd_fm_pipe_kernel(const SgdA
       if (M == 2) g = x * (A[1] - p * x);
       else {
         g = x;
-        for (int t = 1; t < M; t++) g = x * (A[t] - p * g);
+        for (int t = 1; t < M; t++) g = x * (A[t] - p * g);   // A in shared memory: dynamic indexing is fine here
       }
       const double upd = etaP * (dL * g + beta * p);
       viol += fabs(upd);
@@ -567,7 +598,28 @@ __global__ void __launch_bounds__(SGDP_THREADS, 1) sgd_fm_pipe_kernel(const SgdA
       sh[1] = nscP;
       sh[2] = nscW;
     }
+    // ---- park what was fetched ahead (the slots being written belong to samples q+1 .. q+3: nobody reads them now)
+    if (tid == nth - 1) {
+      if (q + 3 < a.nRows) meta[(q + 3) & 3].i = pfI;
+      if (q + 2 < a.nRows) {
+        SgdPipeMeta &m2 = meta[(q + 2) & 3];
+        m2.rb = pfRb;
+        m2.z = (int)(pfRe - pfRb);
+        m2.y = pfY;
+      }
+    }
+    if (tid >= lastWarp0) {
+      int32_t *Jn = sJb + ((q + 1) & 1) * zmax;
+      double *Xn = sXb + ((q + 1) & 1) * zmax;
+      const int u0 = tid - lastWarp0, u1 = u0 + 32;
+      if (u0 < z1) { Jn[u0] = pfJ0; Xn[u0] = pfX0; }
+      if (u1 < z1) { Jn[u1] = pfJ1; Xn[u1] = pfX1; }
+    }
     __syncthreads();
+    if (a.nFields == -7 && tid == 0) {   // phase profile (debug): cycles of this sample's phases
+      long long c4 = clock64();
+      prof[0] += c1 - c0; prof[1] += c2 - c1; prof[2] += c3 - c2; prof[3] += c4 - c3;
+    }
     // ---- resetScaling (sgd.nim:116-131)
     const bool resetW = a.fitLinear && nscW < 1e-9, resetP = nscP < 1e-9;
     if (resetW || resetP) {
@@ -579,6 +631,9 @@ __global__ void __launch_bounds__(SGDP_THREADS, 1) sgd_fm_pipe_kernel(const SgdA
       __syncthreads();
     }
   }
+  if (a.nFields == -7 && tid == 0)
+    printf("[sgd pipe profile] cycles/sample: loads %lld  scale+forward %lld  reduce+loss %lld  update+park %lld\n",
+           prof[0] / a.nRows, prof[1] / a.nRows, prof[2] / a.nRows, prof[3] / a.nRows);
   viol = block_sum(viol, red);
   __syncthreads();
   lossAcc = block_sum(lossAcc, red);
@@ -673,7 +728,8 @@ int32_t nimfm_fm_sgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X,
   const size_t smem = ((size_t)zmax * SB8 + 3 * (size_t)zmax) * 8 + (size_t)zmax * 8;
   const char *env = getenv("NIMFM_SGD_KERNEL");
   const size_t smemPipe = ((size_t)zmax * SB8 + (size_t)SB8 * (NIMFM_MAX_DEGREE + 1) + 4 * (size_t)zmax) * 8 + 2 * (size_t)zmax * 4 + 16;
-  if (SB8 <= SGDP_THREADS - 64 && zmax <= SGDP_THREADS - 64 && smemPipe <= (size_t)ctx->smemOptin - 4096 && !env) {
+  if (SB8 <= SGDP_THREADS - 64 && zmax <= 64 && smemPipe <= (size_t)ctx->smemOptin - 4096 && !env) {
+    if (getenv("NIMFM_SGD_PROFILE")) a.nFields = -7;
     CK(cudaFuncSetAttribute(sgd_fm_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemPipe));
     sgd_fm_pipe_kernel<<<1, SGDP_THREADS, smemPipe, ctx->stream>>>(a, zmax);
   } else if (SB8 <= SGD_THREADS && smem <= (size_t)ctx->smemOptin - 2048 && !(env && !strcmp(env, "unstaged"))) {
