@@ -1,6 +1,5 @@
-## nimfm_cuda.nim -- the Nim side of the drop-in boundary: {.importc, dynlib.} declarations of
-## include/nimfm_cuda.h plus thin procs that keep nimfm's own signatures, so that
-## `import nimfm/cuda/nimfm_cuda` can stand in for the CPU kernels / solvers on the hot path.
+## nimfm_cuda.nim -- the Nim side of the drop-in boundary: {.importc, dynlib.} declarations of every symbol of
+## include/nimfm_cuda.h.  The procs that keep nimfm's own signatures are in the files beside this one.
 ##
 ## NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Nim toolchain (SURVEY.md, probe table).
 ## The same symbols are exercised through the ctypes mirror (nimfm_b200/_lib.py), whose prototype
@@ -66,164 +65,117 @@ type
     power*: cdouble
 
 {.push importc, dynlib: libName, cdecl.}
-proc nimfm_ctx_create(device: int32, outCtx: ptr Ctx): int32
-proc nimfm_ctx_destroy(ctx: Ctx): int32
-proc nimfm_last_error(ctx: Ctx): cstring
-proc nimfm_comm_unique_id(uid: pointer): int32
-proc nimfm_comm_init(ctx: Ctx, rank, nranks: int32, uid: pointer): int32
-proc nimfm_csr_upload(ctx: Ctx, n, d: int64, data: ptr cdouble, indices, indptr, fields: ptr int64,
+proc nimfm_ctx_create*(device: int32, outCtx: ptr Ctx): int32
+proc nimfm_ctx_destroy*(ctx: Ctx): int32
+proc nimfm_last_error*(ctx: Ctx): cstring
+proc nimfm_comm_unique_id*(uid: pointer): int32
+proc nimfm_comm_init*(ctx: Ctx, rank, nranks: int32, uid: pointer): int32
+proc nimfm_csr_upload*(ctx: Ctx, n, d: int64, data: ptr cdouble, indices, indptr, fields: ptr int64,
                       nFields, rowBegin, rowEnd: int64, outDs: ptr DeviceDataset): int32
-proc nimfm_csc_upload(ctx: Ctx, n, d: int64, data: ptr cdouble, indices, indptr: ptr int64,
+proc nimfm_csc_upload*(ctx: Ctx, n, d: int64, data: ptr cdouble, indices, indptr: ptr int64,
                       outDs: ptr DeviceDataset): int32
-proc nimfm_dataset_transpose(ctx: Ctx, src: DeviceDataset, outDs: ptr DeviceDataset): int32
-proc nimfm_dataset_take_rows(ctx: Ctx, src: DeviceDataset, rowIdx: ptr int64, nIdx: int64,
+proc nimfm_dataset_transpose*(ctx: Ctx, src: DeviceDataset, outDs: ptr DeviceDataset): int32
+proc nimfm_dataset_take_rows*(ctx: Ctx, src: DeviceDataset, rowIdx: ptr int64, nIdx: int64,
                              outDs: ptr DeviceDataset): int32   # X[indicesRow], dataset.nim:319-367
-proc nimfm_dataset_slice_rows(ctx: Ctx, src: DeviceDataset, first, last: int64,
+proc nimfm_dataset_slice_rows*(ctx: Ctx, src: DeviceDataset, first, last: int64,
                               outDs: ptr DeviceDataset): int32  # X[a..b], dataset.nim:328-348
-proc nimfm_dataset_vstack(ctx: Ctx, parts: ptr DeviceDataset, nParts: int32,
+proc nimfm_dataset_vstack*(ctx: Ctx, parts: ptr DeviceDataset, nParts: int32,
                           outDs: ptr DeviceDataset): int32      # vstack, dataset.nim:452-483
-proc nimfm_dataset_set_targets(ctx: Ctx, ds: DeviceDataset, y: ptr cdouble): int32
-proc nimfm_dataset_free(ctx: Ctx, ds: DeviceDataset): int32
-proc nimfm_load_svmlight(ctx: Ctx, path: cstring, nFeatures: int64, asCsc: int32,
+proc nimfm_dataset_set_targets*(ctx: Ctx, ds: DeviceDataset, y: ptr cdouble): int32
+proc nimfm_dataset_free*(ctx: Ctx, ds: DeviceDataset): int32
+proc nimfm_load_svmlight*(ctx: Ctx, path: cstring, nFeatures: int64, asCsc: int32,
                          outDs: ptr DeviceDataset): int32        # loadSVMLightFile, dataset.nim:616-693
-proc nimfm_load_ffm(ctx: Ctx, path: cstring, nFeatures, nFields: int64,
+proc nimfm_load_ffm*(ctx: Ctx, path: cstring, nFeatures, nFields: int64,
                     outDs: ptr DeviceDataset): int32             # loadFFMFile, dataset.nim:768-790
-proc nimfm_load_user_item_rating(ctx: Ctx, path: cstring, asCsc: int32,
+proc nimfm_load_user_item_rating*(ctx: Ctx, path: cstring, asCsc: int32,
                                  outDs: ptr DeviceDataset): int32  # loadUserItemRatingFile, dataset.nim:840-990
-proc nimfm_load_stream(ctx: Ctx, pathX, pathY: cstring, outDs: ptr DeviceDataset): int32   # newStreamCSR/CSCDataset
-proc nimfm_dataset_get_targets(ctx: Ctx, ds: DeviceDataset, y: ptr cdouble): int32
-proc nimfm_fm_create(ctx: Ctx, degree, nComponents, nOrders, nAugments: int32, nFeatures: int64,
+proc nimfm_load_stream*(ctx: Ctx, pathX, pathY: cstring, outDs: ptr DeviceDataset): int32   # newStreamCSR/CSCDataset
+proc nimfm_dataset_get_targets*(ctx: Ctx, ds: DeviceDataset, y: ptr cdouble): int32
+proc nimfm_fm_create*(ctx: Ctx, degree, nComponents, nOrders, nAugments: int32, nFeatures: int64,
                      fitLinear, fitIntercept: int32, outFm: ptr DeviceFM): int32
-proc nimfm_fm_set_params(ctx: Ctx, fm: DeviceFM, P, w: ptr cdouble, intercept: cdouble, lams: ptr cdouble): int32
-proc nimfm_fm_get_params(ctx: Ctx, fm: DeviceFM, P, w: ptr cdouble, intercept: ptr cdouble): int32
-proc nimfm_fm_free(ctx: Ctx, fm: DeviceFM): int32
-proc nimfm_fm_decision_function(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, outY: ptr cdouble): int32
-proc nimfm_fm_loss_grad(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, loss: int32, huberThreshold: cdouble,
+proc nimfm_fm_set_params*(ctx: Ctx, fm: DeviceFM, P, w: ptr cdouble, intercept: cdouble, lams: ptr cdouble): int32
+proc nimfm_fm_get_params*(ctx: Ctx, fm: DeviceFM, P, w: ptr cdouble, intercept: ptr cdouble): int32
+proc nimfm_fm_free*(ctx: Ctx, fm: DeviceFM): int32
+proc nimfm_fm_decision_function*(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, outY: ptr cdouble): int32
+proc nimfm_fm_loss_grad*(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, loss: int32, huberThreshold: cdouble,
                         rowBegin, nRows: int64, rowIdx: ptr int64, miniBatchSize: int64,
                         zeroGrads, allreduce: int32, lossSum: ptr cdouble): int32
-proc nimfm_fm_mbpsgd_epoch(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr MbpsgdCfg, localBatch: int64,
+proc nimfm_fm_mbpsgd_epoch*(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr MbpsgdCfg, localBatch: int64,
                            it, ii: ptr int64, sampleIdx: ptr int64, runningLoss: ptr cdouble): int32
-proc nimfm_fm_adagrad_init(ctx: Ctx, fm: DeviceFM, eps: cdouble, reset: int32): int32
-proc nimfm_fm_adagrad_epoch(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr AdagradCfg, it: ptr int64,
+proc nimfm_fm_adagrad_init*(ctx: Ctx, fm: DeviceFM, eps: cdouble, reset: int32): int32
+proc nimfm_fm_adagrad_epoch*(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr AdagradCfg, it: ptr int64,
                             perm: ptr int64, nRows: int64, viol, lossSum: ptr cdouble): int32
-proc nimfm_fm_adagrad_finalize(ctx: Ctx, fm: DeviceFM, cfg: ptr AdagradCfg, it: int64): int32
-proc nimfm_fm_sgd_begin(ctx: Ctx, fm: DeviceFM): int32
-proc nimfm_fm_sgd_epoch(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr SgdCfg, it: ptr int64,
+proc nimfm_fm_adagrad_finalize*(ctx: Ctx, fm: DeviceFM, cfg: ptr AdagradCfg, it: int64): int32
+proc nimfm_fm_sgd_begin*(ctx: Ctx, fm: DeviceFM): int32
+proc nimfm_fm_sgd_epoch*(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr SgdCfg, it: ptr int64,
                         perm: ptr int64, nRows: int64, viol, lossSum: ptr cdouble): int32
-proc nimfm_fm_sgd_end(ctx: Ctx, fm: DeviceFM): int32
-proc nimfm_fm_cd_begin(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr CdCfg): int32
-proc nimfm_fm_cd_epoch(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr CdCfg,
+proc nimfm_fm_sgd_end*(ctx: Ctx, fm: DeviceFM): int32
+proc nimfm_fm_cd_begin*(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr CdCfg): int32
+proc nimfm_fm_cd_epoch*(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr CdCfg,
                        viol, lossMean, regOverN: ptr cdouble): int32
-proc nimfm_fm_pcd_epoch(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr PcdCfg,
+proc nimfm_fm_pcd_epoch*(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr PcdCfg,
                         viol, lossMean, regOverN: ptr cdouble): int32   # pcd.nim:156-172
-proc nimfm_fm_cd_end(ctx: Ctx, fm: DeviceFM): int32
-proc nimfm_fm_psgd_begin(ctx: Ctx, fm: DeviceFM): int32                      # psgd.nim:98-112
-proc nimfm_fm_psgd_epoch(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr PsgdCfg, it: ptr int64,
+proc nimfm_fm_cd_end*(ctx: Ctx, fm: DeviceFM): int32
+proc nimfm_fm_psgd_begin*(ctx: Ctx, fm: DeviceFM): int32                      # psgd.nim:98-112
+proc nimfm_fm_psgd_epoch*(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr PsgdCfg, it: ptr int64,
                          perm: ptr int64, nRows: int64, lossSum: ptr cdouble): int32   # psgd.nim:118-176
-proc nimfm_fm_psgd_end(ctx: Ctx, fm: DeviceFM, cfg: ptr PsgdCfg): int32      # finalize, psgd.nim:58-75
-proc nimfm_ffm_create(ctx: Ctx, nComponents: int32, nFields, nFeatures: int64, fitLinear, fitIntercept: int32,
+proc nimfm_fm_psgd_end*(ctx: Ctx, fm: DeviceFM, cfg: ptr PsgdCfg): int32      # finalize, psgd.nim:58-75
+proc nimfm_ffm_create*(ctx: Ctx, nComponents: int32, nFields, nFeatures: int64, fitLinear, fitIntercept: int32,
                       outM: ptr DeviceFFM): int32
-proc nimfm_ffm_set_params(ctx: Ctx, m: DeviceFFM, P, w: ptr cdouble, intercept: cdouble): int32
-proc nimfm_ffm_get_params(ctx: Ctx, m: DeviceFFM, P, w: ptr cdouble, intercept: ptr cdouble): int32
-proc nimfm_ffm_free(ctx: Ctx, m: DeviceFFM): int32
-proc nimfm_ffm_decision_function(ctx: Ctx, m: DeviceFFM, X: DeviceDataset, outY: ptr cdouble): int32
-proc nimfm_ffm_adagrad_init(ctx: Ctx, m: DeviceFFM, eps: cdouble, reset: int32): int32
-proc nimfm_ffm_adagrad_epoch(ctx: Ctx, m: DeviceFFM, X: DeviceDataset, cfg: ptr AdagradCfg, it: ptr int64,
+proc nimfm_ffm_set_params*(ctx: Ctx, m: DeviceFFM, P, w: ptr cdouble, intercept: cdouble): int32
+proc nimfm_ffm_get_params*(ctx: Ctx, m: DeviceFFM, P, w: ptr cdouble, intercept: ptr cdouble): int32
+proc nimfm_ffm_free*(ctx: Ctx, m: DeviceFFM): int32
+proc nimfm_ffm_decision_function*(ctx: Ctx, m: DeviceFFM, X: DeviceDataset, outY: ptr cdouble): int32
+proc nimfm_ffm_adagrad_init*(ctx: Ctx, m: DeviceFFM, eps: cdouble, reset: int32): int32
+proc nimfm_ffm_adagrad_epoch*(ctx: Ctx, m: DeviceFFM, X: DeviceDataset, cfg: ptr AdagradCfg, it: ptr int64,
                              perm: ptr int64, nRows: int64, viol, lossSum: ptr cdouble): int32
-proc nimfm_ffm_adagrad_finalize(ctx: Ctx, m: DeviceFFM, cfg: ptr AdagradCfg, it: int64): int32
-proc nimfm_ffm_sgd_begin(ctx: Ctx, m: DeviceFFM): int32
-proc nimfm_fm_sgd_minibatch_epoch(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr SgdCfg, miniBatchSize, localBatch: int64,
+proc nimfm_ffm_adagrad_finalize*(ctx: Ctx, m: DeviceFFM, cfg: ptr AdagradCfg, it: int64): int32
+proc nimfm_ffm_sgd_begin*(ctx: Ctx, m: DeviceFFM): int32
+proc nimfm_fm_sgd_minibatch_epoch*(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, cfg: ptr SgdCfg, miniBatchSize, localBatch: int64,
                                   it: ptr int64, perm: ptr int64, nRows: int64, viol, lossSum: ptr cdouble): int32
-proc nimfm_ffm_sgd_minibatch_epoch(ctx: Ctx, m: DeviceFFM, X: DeviceDataset, cfg: ptr SgdCfg, miniBatchSize, localBatch: int64,
+proc nimfm_ffm_sgd_minibatch_epoch*(ctx: Ctx, m: DeviceFFM, X: DeviceDataset, cfg: ptr SgdCfg, miniBatchSize, localBatch: int64,
                                    it: ptr int64, perm: ptr int64, nRows: int64, viol, lossSum: ptr cdouble): int32
-proc nimfm_ffm_sgd_epoch(ctx: Ctx, m: DeviceFFM, X: DeviceDataset, cfg: ptr SgdCfg, it: ptr int64,
+proc nimfm_ffm_sgd_epoch*(ctx: Ctx, m: DeviceFFM, X: DeviceDataset, cfg: ptr SgdCfg, it: ptr int64,
                          perm: ptr int64, nRows: int64, viol, lossSum: ptr cdouble): int32
-proc nimfm_ffm_sgd_end(ctx: Ctx, m: DeviceFFM): int32
+proc nimfm_ffm_sgd_end*(ctx: Ctx, m: DeviceFFM): int32
 # ---- the remaining entry points of include/nimfm_cuda.h (diagnostics, state transfer, measurement hooks)
-proc nimfm_version(): int32
-proc nimfm_launch_count(ctx: Ctx): int64
-proc nimfm_stream_open(ctx: Ctx, pathX, pathY: cstring, sh: ptr pointer): int32
-proc nimfm_stream_info(sh: pointer, kind: ptr int32, nRows, nCols, nnz, maxSegNnz, payloadBytes: ptr int64): int32
-proc nimfm_stream_window_end(sh: pointer, segBegin, maxBytes: int64): int64
-proc nimfm_stream_load_window(ctx: Ctx, sh: pointer, segBegin, segEnd: int64, ds: ptr DeviceDataset): int32
-proc nimfm_stream_close(sh: pointer): int32
-proc nimfm_mem_info(ctx: Ctx, freeBytes, totalBytes: ptr int64): int32
-proc nimfm_stream_stats(ctx: Ctx, h2dBytes, d2hBytes: ptr int64, hostThreads: ptr int32): int32
-proc nimfm_comm_size(ctx: Ctx): int32
-proc nimfm_comm_allgather_i64(ctx: Ctx, mine: ptr int64, count: int32, all: ptr int64): int32
-proc nimfm_host_register(ctx: Ctx, p: pointer, bytes: int64): int32      # page-lock a dataset's seqs once
-proc nimfm_host_unregister(ctx: Ctx, p: pointer): int32
-proc nimfm_dataset_info(ds: DeviceDataset, n, d, nnz: ptr int64, kind: ptr int32, nFields, maxRowNnz: ptr int64): int32
-proc nimfm_dataset_download(ctx: Ctx, ds: DeviceDataset, data: ptr cdouble, indices, indptr, fields: ptr int64): int32
-proc nimfm_fm_loss_grad_host(ctx: Ctx, fm: DeviceFM, nRows, d: int64, data: ptr cdouble, indices, indptr: ptr int64,
+proc nimfm_version*(): int32
+proc nimfm_launch_count*(ctx: Ctx): int64
+proc nimfm_stream_open*(ctx: Ctx, pathX, pathY: cstring, sh: ptr pointer): int32
+proc nimfm_stream_info*(sh: pointer, kind: ptr int32, nRows, nCols, nnz, maxSegNnz, payloadBytes: ptr int64): int32
+proc nimfm_stream_window_end*(sh: pointer, segBegin, maxBytes: int64): int64
+proc nimfm_stream_load_window*(ctx: Ctx, sh: pointer, segBegin, segEnd: int64, ds: ptr DeviceDataset): int32
+proc nimfm_stream_close*(sh: pointer): int32
+proc nimfm_mem_info*(ctx: Ctx, freeBytes, totalBytes: ptr int64): int32
+proc nimfm_stream_stats*(ctx: Ctx, h2dBytes, d2hBytes: ptr int64, hostThreads: ptr int32): int32
+proc nimfm_comm_size*(ctx: Ctx): int32
+proc nimfm_comm_allgather_i64*(ctx: Ctx, mine: ptr int64, count: int32, all: ptr int64): int32
+proc nimfm_host_register*(ctx: Ctx, p: pointer, bytes: int64): int32      # page-lock a dataset's seqs once
+proc nimfm_host_unregister*(ctx: Ctx, p: pointer): int32
+proc nimfm_dataset_info*(ds: DeviceDataset, n, d, nnz: ptr int64, kind: ptr int32, nFields, maxRowNnz: ptr int64): int32
+proc nimfm_dataset_download*(ctx: Ctx, ds: DeviceDataset, data: ptr cdouble, indices, indptr, fields: ptr int64): int32
+proc nimfm_fm_loss_grad_host*(ctx: Ctx, fm: DeviceFM, nRows, d: int64, data: ptr cdouble, indices, indptr: ptr int64,
                              y: ptr cdouble, loss: int32, huberThreshold: cdouble, miniBatchSize, chunkRows: int64,
                              zeroGrads, allreduce: int32, lossSum: ptr cdouble): int32
-proc nimfm_fm_decision_function_host(ctx: Ctx, fm: DeviceFM, nRows, d: int64, data: ptr cdouble,
+proc nimfm_fm_decision_function_host*(ctx: Ctx, fm: DeviceFM, nRows, d: int64, data: ptr cdouble,
                                      indices, indptr: ptr int64, chunkRows: int64, outY: ptr cdouble): int32
-proc nimfm_fm_get_grads(ctx: Ctx, fm: DeviceFM, gP, gw, gb: ptr cdouble): int32
-proc nimfm_fm_adagrad_get_state(ctx: Ctx, fm: DeviceFM, gsP, gnP, gsw, gnw, gsb, gnb: ptr cdouble): int32
-proc nimfm_fm_adagrad_set_state(ctx: Ctx, fm: DeviceFM, gsP, gnP, gsw, gnw: ptr cdouble, gsb, gnb: cdouble): int32
-proc nimfm_fm_cd_get_ypred(ctx: Ctx, fm: DeviceFM, yPred: ptr cdouble): int32
-proc nimfm_ffm_loss_grad(ctx: Ctx, m: DeviceFFM, X: DeviceDataset, loss: int32, huberThreshold: cdouble,
+proc nimfm_fm_get_grads*(ctx: Ctx, fm: DeviceFM, gP, gw, gb: ptr cdouble): int32
+proc nimfm_fm_adagrad_get_state*(ctx: Ctx, fm: DeviceFM, gsP, gnP, gsw, gnw, gsb, gnb: ptr cdouble): int32
+proc nimfm_fm_adagrad_set_state*(ctx: Ctx, fm: DeviceFM, gsP, gnP, gsw, gnw: ptr cdouble, gsb, gnb: cdouble): int32
+proc nimfm_fm_cd_get_ypred*(ctx: Ctx, fm: DeviceFM, yPred: ptr cdouble): int32
+proc nimfm_ffm_loss_grad*(ctx: Ctx, m: DeviceFFM, X: DeviceDataset, loss: int32, huberThreshold: cdouble,
                          rowBegin, nRows: int64, rowIdx: ptr int64, miniBatchSize: int64,
                          zeroGrads, allreduce: int32, lossSum: ptr cdouble): int32
-proc nimfm_ffm_get_grads(ctx: Ctx, m: DeviceFFM, gP, gw, gb: ptr cdouble): int32
-proc nimfm_fm_time_loss_grad(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, loss: int32, nRows, miniBatchSize: int64,
+proc nimfm_ffm_get_grads*(ctx: Ctx, m: DeviceFFM, gP, gw, gb: ptr cdouble): int32
+proc nimfm_fm_time_loss_grad*(ctx: Ctx, fm: DeviceFM, X: DeviceDataset, loss: int32, nRows, miniBatchSize: int64,
                              reps, gradToo: int32, msPerLaunch: ptr cfloat): int32
-proc nimfm_ffm_time_loss_grad(ctx: Ctx, m: DeviceFFM, X: DeviceDataset, loss: int32, nRows, miniBatchSize: int64,
+proc nimfm_ffm_time_loss_grad*(ctx: Ctx, m: DeviceFFM, X: DeviceDataset, loss: int32, nRows, miniBatchSize: int64,
                               reps, gradToo: int32, msPerLaunch: ptr cfloat): int32
-proc nimfm_timer_start(ctx: Ctx): int32
-proc nimfm_timer_stop(ctx: Ctx, ms: ptr cfloat): int32
-proc nimfm_fm_grad_device_ptr(fm: DeviceFM, p: ptr pointer, nDoubles: ptr int64): int32
+proc nimfm_timer_start*(ctx: Ctx): int32
+proc nimfm_timer_stop*(ctx: Ctx, ms: ptr cfloat): int32
+proc nimfm_fm_grad_device_ptr*(fm: DeviceFM, p: ptr pointer, nDoubles: ptr int64): int32
 {.pop.}
 
-# ---------------------------------------------------------------- thin Nim layer (sketch)
-# The procs below show how nimfm's own signatures are kept; they rely on nimfm's types
-# (dataset.nim, model/factorization_machine.nim, loss.nim, optimizer/*.nim).
-
-var gCtx: Ctx
-
-proc ctx*(): Ctx =
-  if gCtx.isNil:
-    if nimfm_ctx_create(0, addr gCtx) != 0:
-      raise newException(IOError, "libnimfm_cuda: no CUDA device (there is no CPU fallback)")
-  result = gCtx
-
-template check(rc: int32) =
-  if rc != 0:
-    # same exception style as factorization_machine.nim:114-115
-    raise newException(ValueError, $nimfm_last_error(ctx()))
-
-when false:  # compiled only inside nimfm's tree, where these types exist
-  import ../dataset, ../tensor/tensor, ../model/factorization_machine, ../model/fm_base, ../loss
-
-  proc p[T](s: var seq[T]): ptr T = (if s.len == 0: nil else: addr s[0])
-
-  proc upload*(X: CSRDataset): DeviceDataset =
-    ## newCSRDataset (dataset.nim:116-122): data/indices/indptr are the public seqs of tensor/sparse.nim:4-31
-    check nimfm_csr_upload(ctx(), X.nSamples, X.data.shape[1], cast[ptr cdouble](p(X.data.data)),
-                           cast[ptr int64](p(X.data.indices)), cast[ptr int64](p(X.data.indptr)), nil, 0,
-                           0, X.nSamples, addr result)
-
-  proc flatP(fm: FactorizationMachine): seq[float64] =
-    ## Tensor is seq[Matrix] of ragged rows (tensor.nim:8-17): flatten to [order][s][j]
-    for o in 0..<fm.P.shape[0]:
-      for s in 0..<fm.P.shape[1]:
-        for j in 0..<fm.P.shape[2]: result.add(fm.P[o, s, j])
-
-  proc toDevice*(fm: FactorizationMachine, nFeatures: int): DeviceFM =
-    var P = flatP(fm)
-    check nimfm_fm_create(ctx(), int32(fm.degree), int32(fm.nComponents), int32(fm.nOrders),
-                          int32(fm.nAugments), nFeatures, int32(fm.fitLinear), int32(fm.fitIntercept), addr result)
-    check nimfm_fm_set_params(ctx(), result, cast[ptr cdouble](p(P)), cast[ptr cdouble](p(fm.w)),
-                              fm.intercept, cast[ptr cdouble](p(fm.lams)))
-
-  proc decisionFunction*(self: FactorizationMachine, X: CSRDataset): seq[float64] =
-    ## drop-in for factorization_machine.nim:100-122
-    self.checkInitialized()
-    let ds = upload(X)
-    let h = toDevice(self, X.nFeatures)
-    result = newSeq[float64](X.nSamples)
-    check nimfm_fm_decision_function(ctx(), h, ds, cast[ptr cdouble](p(result)))
-    discard nimfm_fm_free(ctx(), h)
-    discard nimfm_dataset_free(ctx(), ds)
+# The Nim host layer over these symbols lives beside this file: device.nim (context, dataset / model twins),
+# fit_cd.nim, fit_mbpsgd.nim, fit_adagrad.nim, fit_sgd.nim, fit_ffm.nim (the replaced `fit` bodies) and
+# decision_function.nim -- see INTEGRATION.md for where each one plugs into nimfm's modules.
