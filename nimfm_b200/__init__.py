@@ -4,7 +4,8 @@ include/nimfm_cuda.h); this package is the thin host mirror a Nim program would 
 nim/nimfm_cuda.nim.  There is no CPU fallback."""
 from . import _lib
 from ._lib import NimfmCudaError
-from .dataset import (CSCDataset, CSRDataset, CSRFieldDataset, StreamCSRDataset, convertSVMLightFile, dumpFFMFile,
+from .dataset import (CSCDataset, CSRDataset, CSRFieldDataset, StreamCSRDataset, StreamCSRFieldDataset, convertFFMFile,
+                      convertSVMLightFile, dumpFFMFile, newStreamCSRFieldDataset, transposeFieldFile,
                       dumpSVMLightFile, loadFFMFile, loadStreamLabel, loadSVMLightFile,
                       loadUserItemRatingFile, newStreamCSCDataset, newStreamCSRDataset, transposeFile, newCSCDataset, newCSRDataset,
                       newCSRFieldDataset, shuffle, toCSCDataset, toCSRDataset, vstack)

@@ -196,6 +196,11 @@ int finish_upload(nimfm_ctx *ctx, int64_t n, int64_t d, std::vector<double> &dat
 struct nimfm_stream {
   Mapped mx, my;
   bool isCsr = true, hasY = false;
+  // field files (STREAMCSRFIELD, tensor/sparse_stream.nim:6-8,15-18,27-33): 14-byte magic, 48-byte header with
+  // nFields, 24-byte records {field, val, id}; plain files: 9 + 40 bytes, 16-byte records {val, id}
+  bool isField = false;
+  int64_t nFields = 0;
+  int hdrBytes = 49, recBytes = 16, valOff = 0, idOff = 8;
   int64_t nRows = 0, nCols = 0, nnz = 0, nSeg = 0, extent = 0, maxSeg = 0, payloadEnd = 0;
   std::vector<int64_t> segOff;   // byte offset (within the payload) of each segment's first record
   std::vector<int64_t> indptr;
@@ -205,7 +210,8 @@ namespace {
 
 __global__ void stream_deinterleave_kernel(const unsigned char *payload, const int64_t *segByteOff,
                                            const int64_t *indptr, int64_t nSeg, int64_t extent, double *data,
-                                           int32_t *idx, int *bad) {
+                                           int32_t *idx, int *bad, int recBytes, int valOff, int idOff,
+                                           int32_t *fields, int64_t nFields) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nWarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -213,11 +219,16 @@ __global__ void stream_deinterleave_kernel(const unsigned char *payload, const i
     const unsigned char *rec = payload + segByteOff[sgm];
     const int64_t b = indptr[sgm], z = indptr[sgm + 1] - b;
     for (int64_t t = lane; t < z; t += 32) {
-      const double v = *reinterpret_cast<const double *>(rec + 16 * t);
-      const int64_t id = *reinterpret_cast<const int64_t *>(rec + 16 * t + 8);
+      const double v = *reinterpret_cast<const double *>(rec + recBytes * t + valOff);
+      const int64_t id = *reinterpret_cast<const int64_t *>(rec + recBytes * t + idOff);
       if (id < 0 || id >= extent) *bad = 1;
       data[b + t] = v;
       idx[b + t] = (int32_t)id;
+      if (fields) {
+        const int64_t f = *reinterpret_cast<const int64_t *>(rec + recBytes * t);
+        if (f < 0 || f >= nFields) *bad = 2;
+        fields[b + t] = (int32_t)f;
+      }
     }
   }
 }
@@ -335,29 +346,38 @@ int32_t nimfm_stream_open(nimfm_ctx *ctx, const char *pathX, const char *pathY, 
   m.p = static_cast<const char *>(mp);
   const bool isCsr = memcmp(m.p, "STREAMCSR", 9) == 0, isCsc = memcmp(m.p, "STREAMCSC", 9) == 0;
   REQUIRE(isCsr || isCsc, "%s is not a StreamCSR / StreamCSC file.", pathX);                    // :109-110,142-143
-  REQUIRE(!(m.n >= 14 && memcmp(m.p + 9, "FIELD", 5) == 0), "field stream files are not supported");
-  int64_t hdr[3];
-  memcpy(hdr, m.p + 9, 24);
+  sh->isField = m.n >= 62 && memcmp(m.p + 9, "FIELD", 5) == 0;                                  // :164-196
+  REQUIRE(!(sh->isField && isCsc), "StreamCSCField files feed no solver on this path (FFM fits are row-wise)");
+  int64_t hdr[4] = {0, 0, 0, 0};
+  if (sh->isField) {
+    memcpy(hdr, m.p + 14, 32);
+    sh->nFields = hdr[3];
+    sh->hdrBytes = 62; sh->recBytes = 24; sh->valOff = 8; sh->idOff = 16;
+    REQUIRE(sh->nFields >= 1, "corrupt header in %s", pathX);
+  } else {
+    memcpy(hdr, m.p + 9, 24);
+  }
+  const int HB = sh->hdrBytes, RB = sh->recBytes;
   sh->isCsr = isCsr;
   sh->nRows = hdr[0]; sh->nCols = hdr[1]; sh->nnz = hdr[2];
   REQUIRE(sh->nRows >= 0 && sh->nCols >= 0 && sh->nnz >= 0, "corrupt header in %s", pathX);
   sh->nSeg = isCsr ? sh->nRows : sh->nCols;
   sh->extent = isCsr ? sh->nCols : sh->nRows;
   REQUIRE(sh->extent < (int64_t)2147483647, "index extent %lld does not fit int32", (long long)sh->extent);
-  const size_t payloadBytes = m.n - 49;
+  const size_t payloadBytes = m.n - (size_t)HB;
   sh->segOff.resize((size_t)sh->nSeg);
   sh->indptr.assign((size_t)sh->nSeg + 1, 0);
   int64_t off = 0;
   for (int64_t sgm = 0; sgm < sh->nSeg; sgm++) {
     REQUIRE((size_t)off + 8 <= payloadBytes, "%s is truncated (segment %lld)", pathX, (long long)sgm);
     int64_t cnt;
-    memcpy(&cnt, m.p + 49 + off, 8);
-    REQUIRE(cnt >= 0 && (size_t)off + 8 + 16 * (size_t)cnt <= payloadBytes, "%s is truncated (segment %lld)", pathX,
+    memcpy(&cnt, m.p + HB + off, 8);
+    REQUIRE(cnt >= 0 && (size_t)off + 8 + (size_t)RB * (size_t)cnt <= payloadBytes, "%s is truncated (segment %lld)", pathX,
             (long long)sgm);
     sh->segOff[(size_t)sgm] = off + 8;
     sh->indptr[(size_t)sgm + 1] = sh->indptr[(size_t)sgm] + cnt;
     sh->maxSeg = std::max(sh->maxSeg, cnt);
-    off += 8 + 16 * cnt;
+    off += 8 + (int64_t)RB * cnt;
   }
   sh->payloadEnd = off;
   REQUIRE(sh->indptr[(size_t)sh->nSeg] == sh->nnz, "%s: header nnz %lld != %lld elements found", pathX,
@@ -378,7 +398,7 @@ int32_t nimfm_stream_open(nimfm_ctx *ctx, const char *pathX, const char *pathY, 
 int32_t nimfm_stream_info(const nimfm_stream *sh, int32_t *kind, int64_t *nRows, int64_t *nCols, int64_t *nnz,
                           int64_t *maxSegNnz, int64_t *payloadBytes) {
   if (!sh) return NIMFM_ERR_INVALID;
-  if (kind) *kind = sh->isCsr ? NIMFM_DS_CSR : NIMFM_DS_CSC;
+  if (kind) *kind = sh->isField ? NIMFM_DS_CSR_FIELD : (sh->isCsr ? NIMFM_DS_CSR : NIMFM_DS_CSC);
   if (nRows) *nRows = sh->nRows;
   if (nCols) *nCols = sh->nCols;
   if (nnz) *nnz = sh->nnz;
@@ -424,7 +444,8 @@ int32_t nimfm_stream_load_window(nimfm_ctx *ctx, nimfm_stream *sh, int64_t segBe
     maxSeg = std::max(maxSeg, indptr[(size_t)g + 1] - indptr[(size_t)g]);
   }
   nimfm_dataset *ds = new nimfm_dataset();
-  ds->kind = sh->isCsr ? NIMFM_DS_CSR : NIMFM_DS_CSC;
+  ds->kind = sh->isField ? NIMFM_DS_CSR_FIELD : (sh->isCsr ? NIMFM_DS_CSR : NIMFM_DS_CSC);
+  ds->nFields = sh->isField ? sh->nFields : 0;
   ds->n = sh->isCsr ? nSeg : sh->nRows;
   ds->d = sh->nCols; ds->nnz = nnz; ds->maxSegNnz = maxSeg;
   auto fail = [&](int rc) { nimfm_dataset_free(ctx, ds); return rc; };
@@ -439,8 +460,9 @@ int32_t nimfm_stream_load_window(nimfm_ctx *ctx, nimfm_stream *sh, int64_t segBe
   ck(cudaMalloc(&ds->indptr, ((size_t)nSeg + 1) * 8));
   ck(cudaMalloc(&ds->data, (size_t)std::max<int64_t>(nnz, 2) * 8));
   ck(cudaMalloc(&ds->indices, (size_t)std::max<int64_t>(nnz, 4) * 4));
+  if (sh->isField) ck(cudaMalloc(&ds->fields, (size_t)std::max<int64_t>(nnz, 4) * 4));
   if (ce == cudaSuccess) {
-    if (payloadBytes && nimfm_staged_h2d(ctx, dPayload, sh->mx.p + 49 + byteBegin, payloadBytes) != NIMFM_OK)
+    if (payloadBytes && nimfm_staged_h2d(ctx, dPayload, sh->mx.p + sh->hdrBytes + byteBegin, payloadBytes) != NIMFM_OK)
       ck(cudaErrorUnknown);
     if (nSeg) ck(cudaMemcpyAsync(dSegOff, segOff.data(), (size_t)nSeg * 8, cudaMemcpyHostToDevice, ctx->stream));
     ck(cudaMemcpyAsync(ds->indptr, indptr.data(), ((size_t)nSeg + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -448,7 +470,8 @@ int32_t nimfm_stream_load_window(nimfm_ctx *ctx, nimfm_stream *sh, int64_t segBe
     if (nSeg > 0 && nnz > 0) {
       const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nSeg * 32 + 255) / 256, (int64_t)ctx->numSMs * 16));
       stream_deinterleave_kernel<<<grid, 256, 0, ctx->stream>>>(dPayload, dSegOff, ds->indptr, nSeg, sh->extent, ds->data,
-                                                                ds->indices, dBad);
+                                                                ds->indices, dBad, sh->recBytes, sh->valOff, sh->idOff,
+                                                                ds->fields, sh->nFields);
       LAUNCHED(ctx);
     }
     int hbad = 0;
@@ -458,12 +481,14 @@ int32_t nimfm_stream_load_window(nimfm_ctx *ctx, nimfm_stream *sh, int64_t segBe
     if (ce == cudaSuccess && hbad) {
       cudaFree(dPayload); cudaFree(dSegOff); cudaFree(dBad);
       nimfm_dataset_free(ctx, ds);
+      if (hbad == 2)
+        return nimfm_fail(ctx, NIMFM_ERR_INVALID, "stream file: field out of range [0,%lld)", (long long)sh->nFields);
       return nimfm_fail(ctx, NIMFM_ERR_INVALID, "stream file: element id out of range [0,%lld)", (long long)sh->extent);
     }
   }
   cudaFree(dPayload); cudaFree(dSegOff); cudaFree(dBad);
   if (ce != cudaSuccess) return fail(nimfm_fail(ctx, NIMFM_ERR_CUDA, "nimfm_stream_load_window: %s", cudaGetErrorString(ce)));
-  if (ds->kind == NIMFM_DS_CSR) {
+  if (ds->kind == NIMFM_DS_CSR || ds->kind == NIMFM_DS_CSR_FIELD) {
     // hot columns from a row sample, as for uploaded datasets (nimfm_find_hot): the sampled rows' ids are
     // gathered out of the interleaved payload into a small CSR first
     std::vector<int32_t> hot;
@@ -471,11 +496,11 @@ int32_t nimfm_stream_load_window(nimfm_ctx *ctx, nimfm_stream *sh, int64_t segBe
       const int64_t stride = std::max<int64_t>(1, nSeg / 2048);
       std::vector<int64_t> sIdx, sPtr(1, 0);
       for (int64_t g = 0; g < nSeg; g += stride) {
-        const char *rec = sh->mx.p + 49 + sh->segOff[(size_t)(segBegin + g)];
+        const char *rec = sh->mx.p + sh->hdrBytes + sh->segOff[(size_t)(segBegin + g)];
         const int64_t z = indptr[(size_t)g + 1] - indptr[(size_t)g];
         for (int64_t t = 0; t < z; t++) {
           int64_t id;
-          memcpy(&id, rec + 16 * t + 8, 8);
+          memcpy(&id, rec + sh->recBytes * t + sh->idOff, 8);
           sIdx.push_back(id);
         }
         sPtr.push_back((int64_t)sIdx.size());

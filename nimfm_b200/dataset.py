@@ -353,6 +353,92 @@ def convertSVMLightFile(fIn, fOutX, fOutY):
     np.array(y, dtype="<f8").tofile(os.path.expanduser(str(fOutY)))
 
 
+_MAGIC_FIELD = {"csr": b"STREAMCSRFIELD", "csc": b"STREAMCSCFIELD"}
+
+
+def _write_field_stream(f, kind, nRows, nCols, nFields, data, indices, fields, indptr):
+    """magic (14 bytes) | header {nRows, nCols, nnz, nFields: int64; max, min: float64} | per segment: count int64,
+    count x {field int64, val float64, id int64}  (tensor/sparse_stream.nim:6-8,15-18,27-33)"""
+    nnz = len(data)
+    mx = float(np.max(data)) if nnz else float(np.finfo(np.float64).min)
+    mn = float(np.min(data)) if nnz else float(np.finfo(np.float64).max)
+    rec = np.zeros(nnz, dtype=[("field", "<i8"), ("val", "<f8"), ("id", "<i8")])
+    rec["field"], rec["val"], rec["id"] = fields, data, indices
+    with open(os.path.expanduser(str(f)), "wb") as out:
+        out.write(_MAGIC_FIELD[kind])
+        out.write(np.array([nRows, nCols, nnz, nFields], dtype="<i8").tobytes())
+        out.write(np.array([mx, mn], dtype="<f8").tobytes())
+        for s in range(len(indptr) - 1):
+            a, b = int(indptr[s]), int(indptr[s + 1])
+            out.write(np.int64(b - a).tobytes())
+            out.write(rec[a:b].tobytes())
+
+
+def _read_field_stream(f):
+    """(kind, nRows, nCols, nFields, data, indices, fields, indptr) of a STREAMCSRFIELD / STREAMCSCFIELD file"""
+    raw = open(os.path.expanduser(str(f)), "rb").read()
+    kind = {v: k for k, v in _MAGIC_FIELD.items()}.get(raw[:14])
+    if kind is None:
+        raise IOError(f"{f} is not neither StreamCSCField nor StreamCSRField file.")     # dataset.nim:1320-1322
+    nRows, nCols, nnz, nFields = (int(v) for v in np.frombuffer(raw[14:46], dtype="<i8"))
+    nSeg = nRows if kind == "csr" else nCols
+    data, indices, fields, indptr = np.zeros(nnz), np.zeros(nnz, np.int64), np.zeros(nnz, np.int64), [0]
+    off, q = 62, 0
+    for _ in range(nSeg):
+        cnt = int(np.frombuffer(raw[off:off + 8], dtype="<i8")[0])
+        rec = np.frombuffer(raw[off + 8:off + 8 + 24 * cnt], dtype=[("field", "<i8"), ("val", "<f8"), ("id", "<i8")])
+        data[q:q + cnt], indices[q:q + cnt], fields[q:q + cnt] = rec["val"], rec["id"], rec["field"]
+        q += cnt
+        off += 8 + 24 * cnt
+        indptr.append(q)
+    return kind, nRows, nCols, nFields, data, indices, fields, np.array(indptr, np.int64)
+
+
+def convertFFMFile(fIn, fOutX, fOutY):
+    """convertFFMFile (dataset.nim:1202-1297): libffm text "label field:j:val ..." -> STREAMCSRFIELD binary + raw
+    float64 labels; nFeatures = maxIndex - minIndex + 1 and nFields = maxField - minField + 1 with both minima
+    starting at 1 (:1209-1212,1254-1255), ids rebased by minIndex (:1293).  The reference writes the FIELD
+    unrebased (:1288) and then uses it as a 0-based index -- out of range for a 1-based file -- so the field is
+    rebased by minField here, as loadFFMFile does (dataset.nim:768-790)."""
+    data, indices, fields, indptr, y = [], [], [], [0], []
+    minIndex, maxIndex, minField, maxField = 1, 0, 1, 0
+    for line in open(os.path.expanduser(str(fIn))).read().split("\n"):
+        tok = line.split()
+        if not tok:
+            continue
+        y.append(float(tok[0]))
+        for t in tok[1:]:
+            fld, j, v = t.split(":")
+            fld, j = int(fld), int(j)
+            minField, maxField = min(fld, minField), max(fld, maxField)
+            minIndex, maxIndex = min(j, minIndex), max(j, maxIndex)
+            fields.append(fld)
+            indices.append(j)
+            data.append(float(v))
+        indptr.append(len(indices))
+    if minField < 0:
+        raise ValueError("Negative field index is included.")
+    if minIndex < 0:
+        raise ValueError("Negative index is included.")
+    _write_field_stream(fOutX, "csr", len(y), maxIndex - minIndex + 1, maxField - minField + 1,
+                        np.array(data, np.float64), np.array(indices, np.int64) - minIndex,
+                        np.array(fields, np.int64) - minField, indptr)
+    np.array(y, dtype="<f8").tofile(os.path.expanduser(str(fOutY)))
+
+
+def transposeFieldFile(fIn, fOut, cacheSize=200):
+    """transposeFieldFile (dataset.nim:1302-1402): STREAMCSRFIELD <-> STREAMCSCFIELD, the header keeping
+    [nRows, nCols, nFields]; a stable sort by the other axis (entries of one output segment stay in input-segment
+    order, like the reference's counting passes), the field travelling with its element"""
+    kind, nRows, nCols, nFields, data, indices, fields, indptr = _read_field_stream(fIn)
+    nSegOut = nCols if kind == "csr" else nRows
+    seg = np.repeat(np.arange(len(indptr) - 1, dtype=np.int64), np.diff(indptr))
+    order = np.argsort(indices, kind="stable")
+    optr = np.concatenate([[0], np.cumsum(np.bincount(indices, minlength=nSegOut))]).astype(np.int64)
+    _write_field_stream(fOut, "csc" if kind == "csr" else "csr", nRows, nCols, nFields, data[order], seg[order],
+                        fields[order], optr)
+
+
 def transposeFile(fIn, fOut, cacheSize=200):
     """transposeFile (dataset.nim:1100-1200): STREAMCSR <-> STREAMCSC (the header keeps [nRows, nCols]);
     done with the library's stable device transpose instead of the reference's windowed file passes"""
@@ -367,7 +453,8 @@ def _load_stream(fX, fY):
     _lib.check(_lib.load().nimfm_load_stream(_lib.ctx(), _path(fX), None if fY is None else _path(fY), C.byref(h)))
     probe = BaseDataset.__new__(BaseDataset)
     probe._handle = h
-    cls = _DeviceCSCDataset if BaseDataset.info(probe)["kind"] == _lib.DS_CSC else _DeviceCSRDataset
+    kind = BaseDataset.info(probe)["kind"]
+    cls = {_lib.DS_CSC: _DeviceCSCDataset, _lib.DS_CSR_FIELD: _DeviceCSRFieldDataset}.get(kind, _DeviceCSRDataset)
     probe._handle = None
     out = cls(h)
     y = None
@@ -394,13 +481,21 @@ class _DeviceMixin:
 
     def __getattr__(self, name):
         if name in ("data", "indices", "indptr"):
-            self.data, self.indices, self.indptr, _ = BaseDataset.download(self)
+            self.data, self.indices, self.indptr, f = BaseDataset.download(self)
+            if f is not None:
+                self.fields = f
             return self.__dict__[name]
         raise AttributeError(name)
 
 
 class _DeviceCSRDataset(_DeviceMixin, CSRDataset):
     pass
+
+
+class _DeviceCSRFieldDataset(_DeviceMixin, CSRFieldDataset):
+    def __init__(self, h):
+        _DeviceMixin.__init__(self, h)
+        self.data, self.indices, self.indptr, self.fields = BaseDataset.download(self)
 
 
 class _DeviceCSCDataset(_DeviceMixin, CSCDataset):
@@ -423,9 +518,9 @@ class StreamCSRDataset(CSRDataset):
         kind, n, d, nnz, mx, pay = C.c_int32(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
         _lib.check(lib.nimfm_stream_info(self._sh, C.byref(kind), C.byref(n), C.byref(d), C.byref(nnz), C.byref(mx),
                                          C.byref(pay)))
-        if kind.value != _lib.DS_CSR:
+        if kind.value != self.kind:
             self.close()
-            raise IOError(f"{f} is not a StreamCSR file.")
+            raise IOError(f"{f} is not a {'StreamCSRField' if self.kind == _lib.DS_CSR_FIELD else 'StreamCSR'} file.")
         self._n, self._d, self._nnz, self._nFields = n.value, d.value, nnz.value, 0
         self.payloadBytes = pay.value
         self.cacheBytes = max(int(cacheSize * 1024 * 1024), 1)
@@ -456,10 +551,12 @@ class StreamCSRDataset(CSRDataset):
         """rows [a, b) as a resident dataset (targets attached when set_targets was called)"""
         h = C.c_void_p()
         _lib.check(_lib.load().nimfm_stream_load_window(_lib.ctx(), self._sh, int(a), int(b), C.byref(h)))
-        win = _DeviceCSRDataset(h)
+        win = self._window_cls(h)
         if self._y is not None and b > a:
             win.set_targets(self._y[a:b])
         return win
+
+    _window_cls = _DeviceCSRDataset
 
     def windows(self, multiple=1, start=0):
         """(rowBegin, rowEnd, dataset) over [start, nSamples) in file order; every window but the last holds
@@ -495,6 +592,35 @@ class StreamCSRDataset(CSRDataset):
             self.close()
         except Exception:
             pass
+
+
+class StreamCSRFieldDataset(StreamCSRDataset):
+    """newStreamCSRFieldDataset (dataset.nim:1402+; StreamCSRFieldMatrix, tensor/sparse_stream.nim:54-56,164-196): a
+    STREAMCSRFIELD file kept on disk and walked window by window, the FFM solvers' row dataset"""
+    kind = _lib.DS_CSR_FIELD
+
+    def __init__(self, f, cacheSize=200, fY=None):
+        StreamCSRDataset.__init__(self, f, cacheSize, fY)
+        with open(self._path.decode() if isinstance(self._path, bytes) else self._path, "rb") as fh:
+            fh.seek(14 + 24)
+            self._nFields = int(np.frombuffer(fh.read(8), dtype="<i8")[0])
+
+    _window_cls = _DeviceCSRFieldDataset
+
+
+def newStreamCSRFieldDataset(f, cacheSize=200, resident=None):
+    """newStreamCSRFieldDataset: resident (whole file on the device) whenever the payload is at most a third of
+    the free device memory, else windowed -- as newStreamCSRDataset"""
+    if resident is None:
+        free = C.c_int64()
+        _lib.check(_lib.load().nimfm_mem_info(_lib.ctx(), C.byref(free), None))
+        resident = os.path.getsize(_path(f)) * 3 <= free.value
+    if not resident:
+        return StreamCSRFieldDataset(f, cacheSize)
+    X, _ = _load_stream(f, None)
+    if not isinstance(X, CSRFieldDataset):
+        raise IOError(f"{f} is not a StreamCSRField file.")
+    return X
 
 
 def newStreamCSRDataset(f, cacheSize=200, resident=None):

@@ -261,7 +261,11 @@ class FieldAwareFactorizationMachine(_FMBase):
         h = self._to_device(X)
         try:
             out = np.zeros(X.nSamples)
-            _lib.check(_lib.load().nimfm_ffm_decision_function(_lib.ctx(), h, X.handle(), _lib.ptr(out)))
+            if X.windowed:      # a field stream file kept on disk: one resident window of rows after another
+                for a, b, win in X.windows():
+                    _lib.check(_lib.load().nimfm_ffm_decision_function(_lib.ctx(), h, win.handle(), _lib.ptr(out[a:b])))
+            else:
+                _lib.check(_lib.load().nimfm_ffm_decision_function(_lib.ctx(), h, X.handle(), _lib.ptr(out)))
         finally:
             _lib.load().nimfm_ffm_free(_lib.ctx(), h)
         return out

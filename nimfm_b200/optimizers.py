@@ -233,8 +233,6 @@ class SGD(_Base):
         runs at once" there (2 x cores, sgd_multi.nim:13-18) and here (4096 resident rows).  Without
         maxThreads (and miniBatchSize = 1) the device keeps the exact sequential semantics."""
         is_ffm = isinstance(fm, FieldAwareFactorizationMachine)
-        if X.windowed and is_ffm:
-            raise TypeError("field stream files are not supported")
         fm.init(X)
         y = fm.checkTarget(y)
         lib, ctx = _lib.load(), _lib.ctx()
@@ -339,8 +337,6 @@ class AdaGrad(_Base):
         """adagrad.nim:137-203 / adagrad_ffm.nim:11-66; fit(..., maxThreads=T) (adagrad_multi.nim:39) runs the
         synchronous minibatch of T samples, see below."""
         is_ffm = isinstance(fm, FieldAwareFactorizationMachine)
-        if X.windowed and is_ffm:
-            raise TypeError("field stream files are not supported")
         fm.init(X)
         y = fm.checkTarget(y)
         lib, ctx = _lib.load(), _lib.ctx()

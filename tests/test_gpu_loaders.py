@@ -282,3 +282,54 @@ def test_stream_windowed_dataset(oracle, tmp_path, cache_kb):
     np.testing.assert_allclose(oa.history, oref["epoch_loss"], rtol=1e-8)
     assert max_rel(fa.P, oref["P"]) <= 1e-8 and max_rel(fa.w, oref["w"]) <= 1e-8 and oa.it == oref["it"]
     win.close()
+
+
+@pytest.mark.parametrize("cache_kb", [1, 100000])
+def test_field_stream_files(oracle, tmp_path, cache_kb):
+    """STREAMCSRFIELD files (convertFFMFile dataset.nim:1202-1297, newStreamCSRFieldDataset, transposeFieldFile
+    :1302-1402): the binary file loads to exactly what loadFFMFile reads from the text (ids / fields / indptr bit for
+    bit), windows tile the rows, and the FFM paths -- decisionFunction, SGD, AdaGrad -- give the same results from
+    the windowed file as from the resident dataset"""
+    from helpers import max_rel
+    X, csr, field_of = make_field_csr(83, 14, 4, 9)
+    y = np.sign(np.random.default_rng(2).standard_normal(83))
+    ds0 = nf.newCSRFieldDataset(csr.data, csr.indices, csr.indptr, csr.fields, csr.n, csr.d, csr.n_fields)
+    txt, fx, fy, ft, fb = (str(tmp_path / f) for f in ("a.ffm", "a.bin", "a.lab", "a.csc", "a.back"))
+    nf.dumpFFMFile(txt, ds0, y)                        # 1-based text
+    nf.convertFFMFile(txt, fx, fy)
+    text_ds, text_y = nf.loadFFMFile(txt)
+    whole = nf.newStreamCSRFieldDataset(fx, resident=True)
+    assert whole.shape == text_ds.shape and whole.nFields == text_ds.nFields == 4
+    for name in ("indptr", "indices", "fields", "data"):
+        assert np.array_equal(getattr(whole, name), getattr(text_ds, name)), name
+    assert np.array_equal(nf.loadStreamLabel(fy), text_y)
+    # transpose there and back: stable both ways, so the round trip is the identity on the file
+    nf.transposeFieldFile(fx, ft)
+    nf.transposeFieldFile(ft, fb)
+    assert open(fb, "rb").read() == open(fx, "rb").read()
+    assert open(ft, "rb").read()[:14] == b"STREAMCSCFIELD"
+    win = nf.newStreamCSRFieldDataset(fx, cacheSize=cache_kb / 1024.0, resident=False)
+    assert win.windowed and win.nFields == 4 and win.shape == whole.shape
+    spans = [(a, b) for a, b, _ in win.windows()]
+    assert spans[0][0] == 0 and spans[-1][1] == 83 and all(spans[i][1] == spans[i + 1][0] for i in range(len(spans) - 1))
+    assert (len(spans) == 1) == (cache_kb > 1000)
+    rng = np.random.default_rng(3)
+    P0, w0 = rng.standard_normal((4, whole.nFeatures, 4)) * 0.1, rng.standard_normal(whole.nFeatures) * 0.1
+
+    def model():
+        m = nf.newFieldAwareFactorizationMachine(nf.classification, nComponents=4, warmStart=True)
+        m.P, m.w, m.intercept, m.isInitialized = P0.copy(), w0.copy(), 0.05, True
+        return m
+    ref = CSR(whole.data, whole.indices, whole.indptr, whole.nSamples, whole.nFeatures, fields=whole.fields, n_fields=4)
+    got = model().decisionFunction(win)
+    assert np.array_equal(got, model().decisionFunction(whole))
+    assert max_rel(got, oracle.ffm_decision_function(ref, P0, w0, 0.05)) <= 1e-10
+    for make in (lambda: nf.newSGD(maxIter=2, eta0=0.05, verbose=0, tol=0.0, shuffle=False, loss=nf.Logistic()),
+                 lambda: nf.newAdaGrad(maxIter=2, eta0=0.1, verbose=0, tol=0.0, shuffle=False, loss=nf.Logistic())):
+        ma, mb = model(), model()
+        oa, ob = make(), make()
+        oa.fit(win, y, ma)
+        ob.fit(whole, y, mb)
+        assert np.allclose(oa.history, ob.history, rtol=1e-10, atol=0) and oa.it == ob.it
+        assert max_rel(ma.P, mb.P) <= 1e-10 and max_rel(ma.w, mb.w) <= 1e-10
+    win.close()
