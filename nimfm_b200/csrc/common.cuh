@@ -40,6 +40,10 @@ struct nimfm_ctx {
   cudaEvent_t evCopied[2] = {nullptr, nullptr}, evComputed[2] = {nullptr, nullptr};
   cudaEvent_t tev0 = nullptr, tev1 = nullptr;   // nimfm_timer_*
   struct Stage {
+    double *packed = nullptr;      // packed transport of the values (host_stage.h, pack_values): expanded into data
+    uint64_t *mask = nullptr;
+    uint32_t *blk = nullptr;
+    size_t capPack = 0;
     double *data = nullptr, *y = nullptr;
     int64_t *idx64 = nullptr, *indptr = nullptr;
     int32_t *idx32 = nullptr;
@@ -48,6 +52,10 @@ struct nimfm_ctx {
   // pinned slots of the host staging team (host_stage.h): narrowed ids + rebased indptr
   int32_t *hostIdx[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t *hostPtr[4] = {nullptr, nullptr, nullptr, nullptr};
+  double *hostPack[4] = {nullptr, nullptr, nullptr, nullptr};   // packed values: pinned slots of the staging team
+  uint64_t *hostMask[4] = {nullptr, nullptr, nullptr, nullptr};
+  uint32_t *hostBlk[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t hostCapPack = 0;
   double *hostData[4] = {nullptr, nullptr, nullptr, nullptr};   // pageable callers only: values / targets
   double *hostY[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t hostCapData = 0, hostCapY = 0;

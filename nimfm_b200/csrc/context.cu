@@ -152,6 +152,7 @@ int32_t nimfm_ctx_destroy(nimfm_ctx *ctx) {
   cudaFree(ctx->idx32Scratch);
   cudaFreeHost(ctx->hostScalars);
   for (int s = 0; s < 2; s++) {
+    cudaFree(ctx->stage[s].packed); cudaFree(ctx->stage[s].mask); cudaFree(ctx->stage[s].blk);
     cudaFree(ctx->stage[s].data); cudaFree(ctx->stage[s].y); cudaFree(ctx->stage[s].idx64);
     cudaFree(ctx->stage[s].indptr); cudaFree(ctx->stage[s].idx32);
     if (ctx->evCopied[s]) cudaEventDestroy(ctx->evCopied[s]);
@@ -165,6 +166,9 @@ int32_t nimfm_ctx_destroy(nimfm_ctx *ctx) {
     if (ctx->hostIdx[s]) cudaFreeHost(ctx->hostIdx[s]);
     if (ctx->hostPtr[s]) cudaFreeHost(ctx->hostPtr[s]);
     if (ctx->hostData[s]) cudaFreeHost(ctx->hostData[s]);
+    if (ctx->hostPack[s]) cudaFreeHost(ctx->hostPack[s]);
+    if (ctx->hostMask[s]) cudaFreeHost(ctx->hostMask[s]);
+    if (ctx->hostBlk[s]) cudaFreeHost(ctx->hostBlk[s]);
     if (ctx->hostY[s]) cudaFreeHost(ctx->hostY[s]);
     if (ctx->evSlot[s]) cudaEventDestroy(ctx->evSlot[s]);
   }

@@ -1267,6 +1267,58 @@ static int ensure_host_value_slots(nimfm_ctx *ctx, size_t rows, size_t nnz) {
   return NIMFM_OK;
 }
 
+// pinned slots + device buffers of the packed value transport (host_stage.h, pack_values)
+static int ensure_pack_buffers(nimfm_ctx *ctx, size_t nnz) {
+  const size_t words = nnz / 64 + 8, blks = nnz / 256 + 8;
+  if (ctx->hostCapPack < nnz) {
+    ctx->hostCapPack = 0;
+    for (int s = 0; s < HostStageTeam::kSlots; s++) {
+      if (ctx->hostPack[s]) CK(cudaFreeHost(ctx->hostPack[s]));
+      if (ctx->hostMask[s]) CK(cudaFreeHost(ctx->hostMask[s]));
+      if (ctx->hostBlk[s]) CK(cudaFreeHost(ctx->hostBlk[s]));
+      ctx->hostPack[s] = nullptr; ctx->hostMask[s] = nullptr; ctx->hostBlk[s] = nullptr;
+      CK(cudaHostAlloc(&ctx->hostPack[s], (nnz + 8) * 8, cudaHostAllocDefault));
+      CK(cudaHostAlloc(&ctx->hostMask[s], words * 8, cudaHostAllocDefault));
+      CK(cudaHostAlloc(&ctx->hostBlk[s], blks * 4, cudaHostAllocDefault));
+    }
+    ctx->hostCapPack = nnz;
+  }
+  for (int s = 0; s < 2; s++) {
+    nimfm_ctx::Stage &st = ctx->stage[s];
+    if (st.capPack < nnz) {
+      if (st.packed) CK(cudaFree(st.packed));
+      if (st.mask) CK(cudaFree(st.mask));
+      if (st.blk) CK(cudaFree(st.blk));
+      st.packed = nullptr; st.mask = nullptr; st.blk = nullptr; st.capPack = 0;
+      CK(cudaMalloc(&st.packed, (nnz + 8) * 8));
+      CK(cudaMalloc(&st.mask, words * 8));
+      CK(cudaMalloc(&st.blk, blks * 4));
+      st.capPack = nnz;
+    }
+  }
+  return NIMFM_OK;
+}
+
+// values back from their packed transport: bit q of mask = "value q is exactly 1.0"; the others sit in `packed`,
+// blk[q / 256] = index of the first packed value of q's block of 256 nonzeros
+__global__ void expand_values_kernel(const uint64_t *__restrict__ mask, const uint32_t *__restrict__ blk,
+                                     const double *__restrict__ packed, double *__restrict__ out, int64_t nnz) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz; q += stride) {
+    const int64_t w = q >> 6;
+    const int bit = (int)(q & 63);
+    const uint64_t word = mask[w];
+    if ((word >> bit) & 1) {
+      out[q] = 1.0;
+    } else {
+      uint32_t idx = blk[q >> 8];
+      for (int64_t v = (q >> 8) << 2; v < w; v++) idx += __popcll(~mask[v]);
+      idx += __popcll(~word & ((1ull << bit) - 1ull));
+      out[q] = packed[idx];
+    }
+  }
+}
+
 // is this host pointer outside every page-locked allocation CUDA knows (a plain malloc / Nim seq / numpy array)?
 static bool is_pageable(const void *p) {
   if (!p) return false;
@@ -1334,13 +1386,29 @@ static int stream_host_rows(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t
   }
   std::unique_ptr<HostStageTeam> team;
   // pageable caller arrays: their values (and targets) travel through the team's pinned slots as well
-  const bool stageValues = hostT > 0 && is_pageable(data);
-  if (stageValues && (rc = ensure_host_value_slots(ctx, capRows, maxNnz))) return rc;
+  const bool pageable = hostT > 0 && is_pageable(data);
+  // packed transport of the values when at least a quarter of a sample of them is exactly 1.0 (one-hot data):
+  // lossless, 281 instead of 484 bytes per Criteo-shaped row on the link (NIMFM_HOST_PACK=0 / 1 forces it off / on)
+  bool packValues = false;
+  if (hostT > 0 && data && nRows > 0) {
+    const int64_t nnzAll = indptr[nRows] - indptr[0], sample = std::min<int64_t>(nnzAll, 1 << 16);
+    int64_t ones = 0;
+    for (int64_t q = 0; q < sample; q++) ones += data[indptr[0] + q * (nnzAll / sample)] == 1.0;
+    packValues = ones * 4 >= sample && sample > 0;
+    if (const char *e = getenv("NIMFM_HOST_PACK")) packValues = e[0] == '1';
+  }
+  const bool stageValues = pageable && !packValues;
+  if ((pageable || packValues) && (rc = ensure_host_value_slots(ctx, capRows, packValues ? 1 : maxNnz))) return rc;
+  if (packValues && (rc = ensure_pack_buffers(ctx, maxNnz))) return rc;
   if (hostT > 0) {
     team.reset(new HostStageTeam(hostT, indices, indptr, d, chunks, ctx->hostIdx, ctx->hostPtr));
-    if (stageValues) team->stage_values(data, predict ? nullptr : y, ctx->hostData, ctx->hostY);
+    if (packValues)
+      team->pack_values(data, (pageable && !predict) ? y : nullptr, ctx->hostPack, ctx->hostMask, ctx->hostBlk, ctx->hostY);
+    else if (stageValues)
+      team->stage_values(data, predict ? nullptr : y, ctx->hostData, ctx->hostY);
     team->allow(std::min<int64_t>(nChunks, HostStageTeam::kSlots - 1));
   }
+  const bool stageY = pageable;
   // a failed check leaves with both streams drained (copies read the caller's buffers and our pinned slots)
   auto drained = [&](int code) {
     cudaStreamSynchronize(ctx->copyStream);
@@ -1370,8 +1438,26 @@ static int stream_host_rows(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t
     }
     // the copies go out first; the host-side bookkeeping below overlaps with the DMA
     if (c >= 2) CK(cudaStreamWaitEvent(ctx->copyStream, ctx->evComputed[c & 1], 0));   // buffer is free again
-    CK(cudaMemcpyAsync(st.data, stageValues ? ctx->hostData[hs] : data + base, (size_t)nnz * 8, cudaMemcpyHostToDevice,
-                       ctx->copyStream));
+    int64_t valueBytes = nnz * 8;
+    if (packValues) {
+      const int64_t per = team->slice_len(nnz);
+      valueBytes = 0;
+      for (int t = 0; t < team->threads(); t++) {
+        const int64_t a0 = std::min(nnz, per * t), cnt = info.packed[t];
+        if (cnt > 0)
+          CK(cudaMemcpyAsync(st.packed + a0, ctx->hostPack[hs] + a0, (size_t)cnt * 8, cudaMemcpyHostToDevice, ctx->copyStream));
+        valueBytes += cnt * 8;
+      }
+      const int64_t words = (nnz + 63) / 64, blks = (nnz + 255) / 256;
+      if (nnz > 0) {
+        CK(cudaMemcpyAsync(st.mask, ctx->hostMask[hs], (size_t)words * 8, cudaMemcpyHostToDevice, ctx->copyStream));
+        CK(cudaMemcpyAsync(st.blk, ctx->hostBlk[hs], (size_t)blks * 4, cudaMemcpyHostToDevice, ctx->copyStream));
+      }
+      valueBytes += words * 8 + blks * 4;
+    } else {
+      CK(cudaMemcpyAsync(st.data, stageValues ? ctx->hostData[hs] : data + base, (size_t)nnz * 8, cudaMemcpyHostToDevice,
+                         ctx->copyStream));
+    }
     if (team) {
       CK(cudaMemcpyAsync(st.idx32, ctx->hostIdx[hs], (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->copyStream));
       CK(cudaMemcpyAsync(st.indptr, ctx->hostPtr[hs], (size_t)(rows + 1) * 8, cudaMemcpyHostToDevice, ctx->copyStream));
@@ -1380,10 +1466,10 @@ static int stream_host_rows(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t
       CK(cudaMemcpyAsync(st.indptr, indptr + r0, (size_t)(rows + 1) * 8, cudaMemcpyHostToDevice, ctx->copyStream));
     }
     if (!predict)
-      CK(cudaMemcpyAsync(st.y, stageValues ? ctx->hostY[hs] : y + r0, (size_t)rows * 8, cudaMemcpyHostToDevice, ctx->copyStream));
+      CK(cudaMemcpyAsync(st.y, stageY ? ctx->hostY[hs] : y + r0, (size_t)rows * 8, cudaMemcpyHostToDevice, ctx->copyStream));
     CK(cudaEventRecord(ctx->evCopied[c & 1], ctx->copyStream));
     if (team) CK(cudaEventRecord(ctx->evSlot[hs], ctx->copyStream));
-    h2d += nnz * (team ? 12 : 16) + (rows + 1) * 8 + (predict ? 0 : rows * 8);
+    h2d += valueBytes + nnz * (team ? 4 : 8) + (rows + 1) * 8 + (predict ? 0 : rows * 8);
     d2h += predict ? rows * 8 : 0;
     if (c == 0 && !predict) {
       // hot columns of this batch (row sample on the host; see nimfm_find_hot): the previous call's
@@ -1411,6 +1497,10 @@ static int stream_host_rows(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t
         return drained(nimfm_fail(ctx, NIMFM_ERR_INVALID, "indptr is not monotone in rows [%lld,%lld)", (long long)r0, (long long)r1));
     }
     CK(cudaStreamWaitEvent(ctx->stream, ctx->evCopied[c & 1], 0));
+    if (packValues && nnz > 0) {
+      expand_values_kernel<<<ew_grid(ctx, nnz), 256, 0, ctx->stream>>>(st.mask, st.blk, st.packed, st.data, nnz);
+      LAUNCHED(ctx);
+    }
     if (!team) {
       narrow_rebase_kernel<<<ew_grid(ctx, nnz), 256, 0, ctx->stream>>>(st.idx64, st.idx32, nnz, st.indptr, rows + 1,
                                                                        base, d, bad);
@@ -1453,7 +1543,7 @@ static int stream_host_rows(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t
   ctx->lastH2D = h2d;
   ctx->lastD2H = d2h + (lossSum && !predict ? 8 : 0);
   ctx->lastHostThreads = hostT;
-  ctx->lastPageable = stageValues ? 1 : 0;
+  ctx->lastPageable = pageable ? 1 : 0;
   if (!predict && allreduce && (rc = nimfm_allreduce_sum(ctx, fm->grad, nG))) return rc;
   if (dOutAll && (rc = nimfm_staged_d2h(ctx, predOut, dOutAll, (size_t)nRows * 8))) return drained(rc);
   int hbad = 0;

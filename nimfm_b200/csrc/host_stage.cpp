@@ -63,6 +63,56 @@ void stream_copy(double *dst, const double *src, int64_t n) {
   else memcpy(dst, src, (size_t)n * sizeof(double));
 }
 
+// Pack a slice of values (n a multiple of 256 except for the last slice of a chunk): mask bit = "value is exactly 1.0",
+// the other values appended to `out` (capacity n), blk[b] = outBase + number of packed values before block b of 256.
+// Returns the number of packed values.
+int64_t pack_scalar(const double *src, int64_t n, double *out, uint64_t *mask, uint32_t *blk, int64_t outBase, int64_t i0,
+                    int64_t cnt) {
+  for (int64_t i = i0; i < n; i++) {
+    if ((i & 255) == 0) blk[i >> 8] = (uint32_t)(outBase + cnt);
+    if ((i & 63) == 0) mask[i >> 6] = 0;
+    const double v = src[i];
+    const bool one = v == 1.0;
+    mask[i >> 6] |= (uint64_t)one << (i & 63);
+    out[cnt] = v;
+    cnt += !one;
+  }
+  return cnt;
+}
+
+__attribute__((target("avx2,popcnt"))) int64_t pack_avx2(const double *src, int64_t n, double *out, uint64_t *mask,
+                                                        uint32_t *blk, int64_t outBase) {
+  // left-compaction of 4 doubles by a 16-entry table of 32-bit lane permutations (keep bit i = value i is NOT 1.0)
+  alignas(32) static const int32_t lut[16][8] = {
+      {0, 1, 2, 3, 4, 5, 6, 7}, {0, 1, 2, 3, 4, 5, 6, 7}, {2, 3, 0, 1, 4, 5, 6, 7}, {0, 1, 2, 3, 4, 5, 6, 7},
+      {4, 5, 0, 1, 2, 3, 6, 7}, {0, 1, 4, 5, 2, 3, 6, 7}, {2, 3, 4, 5, 0, 1, 6, 7}, {0, 1, 2, 3, 4, 5, 6, 7},
+      {6, 7, 0, 1, 2, 3, 4, 5}, {0, 1, 6, 7, 2, 3, 4, 5}, {2, 3, 6, 7, 0, 1, 4, 5}, {0, 1, 2, 3, 6, 7, 4, 5},
+      {4, 5, 6, 7, 0, 1, 2, 3}, {0, 1, 4, 5, 6, 7, 2, 3}, {2, 3, 4, 5, 6, 7, 0, 1}, {0, 1, 2, 3, 4, 5, 6, 7}};
+  const __m256d ones = _mm256_set1_pd(1.0);
+  int64_t cnt = 0, i = 0;
+  const int64_t n64 = n & ~(int64_t)63;
+  for (; i < n64; i += 64) {
+    if ((i & 255) == 0) blk[i >> 8] = (uint32_t)(outBase + cnt);
+    uint64_t word = 0;
+    for (int g = 0; g < 16; g++) {
+      const __m256d v = _mm256_loadu_pd(src + i + 4 * g);
+      const int eq = _mm256_movemask_pd(_mm256_cmp_pd(v, ones, _CMP_EQ_OQ));
+      word |= (uint64_t)eq << (4 * g);
+      const int keep = ~eq & 15;
+      const __m256i perm = _mm256_load_si256(reinterpret_cast<const __m256i *>(lut[keep]));
+      _mm256_storeu_pd(out + cnt, _mm256_castsi256_pd(_mm256_permutevar8x32_epi32(_mm256_castpd_si256(v), perm)));
+      cnt += __builtin_popcount(keep);
+    }
+    mask[i >> 6] = word;
+  }
+  return pack_scalar(src, n, out, mask, blk, outBase, i, cnt);
+}
+
+int64_t pack(const double *src, int64_t n, double *out, uint64_t *mask, uint32_t *blk, int64_t outBase) {
+  static const bool haveAvx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("popcnt");
+  return haveAvx2 ? pack_avx2(src, n, out, mask, blk, outBase) : pack_scalar(src, n, out, mask, blk, outBase, 0, 0);
+}
+
 int narrow(const int64_t *src, int32_t *dst, int64_t n, int64_t d) {
   static const bool haveAvx2 = __builtin_cpu_supports("avx2");
   return haveAvx2 ? narrow_avx2(src, dst, n, d) : narrow_scalar(src, dst, n, d);
@@ -94,7 +144,7 @@ int HostStageTeam::pageable_threads(int nRanks) {
 
 HostStageTeam::HostStageTeam(int nThreads, const int64_t *indices, const int64_t *indptr, int64_t d,
                              const std::vector<HostChunk> &chunks, int32_t *const *idxSlot, int64_t *const *ptrSlot)
-    : T_(std::max(1, nThreads)), indices_(indices), indptr_(indptr), d_(d), chunks_(chunks), idxSlot_(idxSlot),
+    : T_(std::min(32, std::max(1, nThreads))), indices_(indices), indptr_(indptr), d_(d), chunks_(chunks), idxSlot_(idxSlot),
       ptrSlot_(ptrSlot), done_(chunks.size(), 0), info_(chunks.size()) {
   for (int t = 0; t < T_; t++) threads_.emplace_back([this, t] { work(t); });
 }
@@ -116,6 +166,18 @@ void HostStageTeam::stage_values(const double *data, const double *y, double *co
   ySlot_ = ySlot;
 }
 
+void HostStageTeam::pack_values(const double *data, const double *y, double *const *packSlot, uint64_t *const *maskSlot,
+                                uint32_t *const *blkSlot, double *const *ySlot) {
+  std::lock_guard<std::mutex> g(mu_);
+  data_ = data;
+  y_ = y;
+  dataSlot_ = nullptr;
+  packSlot_ = packSlot;
+  maskSlot_ = maskSlot;
+  blkSlot_ = blkSlot;
+  ySlot_ = ySlot;
+}
+
 void HostStageTeam::allow(int64_t upTo) {
   {
     std::lock_guard<std::mutex> g(mu_);
@@ -134,10 +196,13 @@ HostChunkInfo HostStageTeam::wait(int64_t c) {
 void HostStageTeam::part(int64_t c, int t, HostChunkInfo &info) {
   const HostChunk &ch = chunks_[c];
   const int s = (int)(c % kSlots);
-  const int64_t per = ((ch.nnz + T_ - 1) / T_ + 7) & ~(int64_t)7;
+  const int64_t per = slice_len(ch.nnz);
   const int64_t a = std::min(ch.nnz, per * t), b = std::min(ch.nnz, per * (t + 1));
   if (b > a) info.bad |= narrow(indices_ + ch.base + a, idxSlot_[s] + a, b - a, d_);
-  if (b > a && data_) stream_copy(dataSlot_[s] + a, data_ + ch.base + a, b - a);
+  if (b > a && data_ && packSlot_)
+    info.packed[t] = pack(data_ + ch.base + a, b - a, packSlot_[s] + a, maskSlot_[s] + (a >> 6), blkSlot_[s] + (a >> 8), a);
+  else if (b > a && data_)
+    stream_copy(dataSlot_[s] + a, data_ + ch.base + a, b - a);
   const int64_t rows = ch.r1 - ch.r0, rper = (rows + T_ - 1) / T_;
   const int64_t ra = std::min(rows, rper * t), rb = std::min(rows, rper * (t + 1));
   if (rb > ra && y_) memcpy(ySlot_[s] + ra, y_ + ch.r0 + ra, (size_t)(rb - ra) * sizeof(double));
@@ -164,6 +229,7 @@ void HostStageTeam::work(int t) {
     {
       std::lock_guard<std::mutex> g(mu_);
       info_[c].bad |= mine.bad;
+      info_[c].packed[t] = mine.packed[t];
       info_[c].maxSeg = std::max(info_[c].maxSeg, mine.maxSeg);
       info_[c].minSeg = std::min(info_[c].minSeg, mine.minSeg);
       last = ++done_[c] == T_;

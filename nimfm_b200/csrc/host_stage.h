@@ -24,6 +24,7 @@ struct HostChunk {
 struct HostChunkInfo {
   int64_t maxSeg = 0, minSeg = 0;
   int bad = 0;                // some column id outside [0,d)
+  int64_t packed[32] = {0};   // pack mode: values != 1.0 written by thread t at the start of its slice
 };
 
 class HostStageTeam {
@@ -36,6 +37,15 @@ class HostStageTeam {
   // when y != nullptr) into pinned slots, so that every byte the copy engine reads is page-locked -- a
   // cudaMemcpyAsync from pageable memory is staged by the driver on one thread at ~4 GB/s.  Call before allow().
   void stage_values(const double *data, const double *y, double *const *dataSlot, double *const *ySlot);
+  // LOSSLESS transport packing of the values: sparse FM data is mostly one-hot (26 of the 39 values of a
+  // Criteo-shaped row are exactly 1.0), so a chunk travels as a bit mask "value == 1.0" (1 bit per nonzero), the
+  // other values packed per thread slice, and one uint32 offset per 256 nonzeros that lets the device expand
+  // without a scan (fm_api.cu, expand_values_kernel).  Every double that is not bit-for-bit 1.0 crosses the link
+  // unchanged.  Call before allow(); slices are multiples of 256 nonzeros (slice_len()).
+  void pack_values(const double *data, const double *y, double *const *packSlot, uint64_t *const *maskSlot,
+                   uint32_t *const *blkSlot, double *const *ySlot);
+  int64_t slice_len(int64_t nnz) const { return ((nnz + T_ - 1) / T_ + 255) & ~(int64_t)255; }
+  int threads() const { return T_; }
   ~HostStageTeam();                       // stops and joins the workers
   void allow(int64_t upTo);               // chunks < upTo may be written (their slot's last copy has completed)
   HostChunkInfo wait(int64_t c);          // blocks until chunk c is staged in slot c % kSlots
@@ -54,6 +64,9 @@ class HostStageTeam {
   const double *data_ = nullptr, *y_ = nullptr;
   double *const *dataSlot_ = nullptr;
   double *const *ySlot_ = nullptr;
+  double *const *packSlot_ = nullptr;
+  uint64_t *const *maskSlot_ = nullptr;
+  uint32_t *const *blkSlot_ = nullptr;
   std::mutex mu_;
   std::condition_variable cv_;
   int64_t allowed_ = 0;

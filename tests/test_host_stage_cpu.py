@@ -52,6 +52,53 @@ extern "C" int run_team(int threads, const int64_t *indices, const int64_t *indp
   for (int s = 0; s < HostStageTeam::kSlots; s++) { free(idxSlot[s]); free(ptrSlot[s]); }
   return (int)nChunks;
 }
+// pack mode: the team packs the values of every chunk; the driver concatenates per chunk [mask words | blk offsets |
+// packed region of the whole slot] so that Python can expand them the way expand_values_kernel does
+extern "C" int run_pack(int threads, const double *data, const int64_t *indices, const int64_t *indptr, int64_t nRows,
+                        int64_t d, int64_t chunkRows, double *outPacked, uint64_t *outMask, uint32_t *outBlk,
+                        int64_t *outPackedCount) {
+  std::vector<HostChunk> chunks;
+  size_t maxNnz = 1;
+  for (int64_t r0 = 0; r0 < nRows; r0 += chunkRows) {
+    HostChunk ch; ch.r0 = r0; ch.r1 = std::min(nRows, r0 + chunkRows);
+    ch.base = indptr[ch.r0]; ch.nnz = indptr[ch.r1] - ch.base;
+    maxNnz = std::max(maxNnz, (size_t)ch.nnz);
+    chunks.push_back(ch);
+  }
+  int32_t *idxSlot[HostStageTeam::kSlots]; int64_t *ptrSlot[HostStageTeam::kSlots];
+  double *packSlot[HostStageTeam::kSlots]; uint64_t *maskSlot[HostStageTeam::kSlots]; uint32_t *blkSlot[HostStageTeam::kSlots];
+  for (int s = 0; s < HostStageTeam::kSlots; s++) {
+    idxSlot[s] = (int32_t *)aligned_alloc(64, ((maxNnz * 4 + 63) / 64) * 64);
+    ptrSlot[s] = (int64_t *)aligned_alloc(64, (((size_t)chunkRows + 1) * 8 + 63) / 64 * 64);
+    packSlot[s] = (double *)aligned_alloc(64, (((maxNnz + 8) * 8 + 63) / 64) * 64);
+    maskSlot[s] = (uint64_t *)aligned_alloc(64, ((maxNnz / 64 + 8) * 8 + 63) / 64 * 64);
+    blkSlot[s] = (uint32_t *)aligned_alloc(64, ((maxNnz / 256 + 8) * 4 + 63) / 64 * 64);
+  }
+  const int64_t nChunks = (int64_t)chunks.size();
+  {
+    HostStageTeam team(threads, indices, indptr, d, chunks, idxSlot, ptrSlot);
+    team.pack_values(data, nullptr, packSlot, maskSlot, blkSlot, nullptr);
+    team.allow(std::min<int64_t>(nChunks, HostStageTeam::kSlots - 1));
+    for (int64_t c = 0; c < nChunks; c++) {
+      HostChunkInfo info = team.wait(c);
+      const int s = (int)(c % HostStageTeam::kSlots);
+      const int64_t nnz = chunks[c].nnz, off = chunks[c].base - indptr[0], per = team.slice_len(nnz);
+      // what the library copies: every thread's packed region, the mask words, the block offsets
+      int64_t total = 0;
+      for (int t = 0; t < team.threads(); t++) {
+        const int64_t a0 = std::min(nnz, per * t);
+        memcpy(outPacked + off + a0, packSlot[s] + a0, (size_t)info.packed[t] * 8);
+        total += info.packed[t];
+      }
+      outPackedCount[c] = total;
+      memcpy(outMask + c * (maxNnz / 64 + 8), maskSlot[s], (size_t)((nnz + 63) / 64) * 8);
+      memcpy(outBlk + c * (maxNnz / 256 + 8), blkSlot[s], (size_t)((nnz + 255) / 256) * 4);
+      team.allow(c + 3);
+    }
+  }
+  for (int s = 0; s < HostStageTeam::kSlots; s++) { free(idxSlot[s]); free(ptrSlot[s]); free(packSlot[s]); free(maskSlot[s]); free(blkSlot[s]); }
+  return (int)nChunks;
+}
 extern "C" int narrow_only(const int64_t *src, int32_t *dst, int64_t n, int64_t d) { return nimfm_host_narrow(src, dst, n, d); }
 extern "C" int default_threads(int nRanks) { return HostStageTeam::default_threads(nRanks); }
 """
@@ -144,3 +191,46 @@ def test_default_threads_gate(lib, monkeypatch):
     assert lib.default_threads(max(hw, 1)) == 0                          # one core per rank: narrow on the device
     monkeypatch.setenv("NIMFM_HOST_THREADS", "3")
     assert lib.default_threads(64) == 3
+
+
+@pytest.mark.parametrize("threads", [1, 3, 8, 14])
+@pytest.mark.parametrize("chunk,frac_ones", [(5000, 0.66), (300, 0.3), (64, 1.0), (5000, 0.0)])
+def test_pack_values_roundtrip(lib, threads, chunk, frac_ones):
+    """the lossless packed transport of the values (bit mask "== 1.0" + the other values + one offset per 256 nonzeros):
+    expanding it the way expand_values_kernel does gives back every double bit for bit -- NaN, -0.0, denormals and
+    values next to 1.0 included"""
+    n, d = 2000, 100_000
+    indices, indptr = ragged(n, d, 11 + threads, 40)
+    nnz = int(indptr[-1])
+    rng = np.random.default_rng(chunk)
+    data = rng.standard_normal(nnz)
+    data[rng.random(nnz) < frac_ones] = 1.0
+    special = np.array([np.nan, -0.0, 5e-324, np.nextafter(1.0, 2.0), np.nextafter(1.0, 0.0), np.inf, -1.0])
+    data[rng.integers(0, nnz, 50)] = special[rng.integers(0, len(special), 50)]
+    nChunks = (n + chunk - 1) // chunk
+    maxNnz = max(int(indptr[min(n, (c + 1) * chunk)] - indptr[c * chunk]) for c in range(nChunks))
+    W, B = maxNnz // 64 + 8, maxNnz // 256 + 8
+    outPacked = np.zeros(nnz + 16)
+    outMask, outBlk = np.zeros(nChunks * W, np.uint64), np.zeros(nChunks * B, np.uint32)
+    counts = np.zeros(nChunks, np.int64)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    got = lib.run_pack(threads, P(data), P(indices), P(indptr), C.c_int64(n), C.c_int64(d), C.c_int64(chunk), P(outPacked),
+                       P(outMask), P(outBlk), P(counts))
+    assert got == nChunks
+    for c in range(nChunks):
+        a, b = int(indptr[c * chunk]), int(indptr[min(n, (c + 1) * chunk)])
+        want = data[a:b]
+        m = b - a
+        assert counts[c] == int(np.sum(~(want == 1.0)))
+        words = outMask[c * W: c * W + (m + 63) // 64]
+        bits = ((words[:, None] >> np.arange(64, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(bool).ravel()[:m]
+        assert np.array_equal(bits, want == 1.0)
+        # expand: index of packed value q = blk[q // 256] + number of non-ones before q inside its block
+        q = np.arange(m)
+        nonone = ~bits
+        before = np.cumsum(nonone) - nonone                   # non-ones before q in the chunk
+        blk_start = (q // 256) * 256
+        inblock = before - before[blk_start]                  # ... inside q's block (before[blk_start] counts up to the block)
+        idx = outBlk[c * B + q // 256].astype(np.int64) + inblock
+        out = np.where(bits, 1.0, outPacked[a + idx])
+        assert np.array_equal(out.view(np.uint64), want.view(np.uint64))
