@@ -1019,8 +1019,15 @@ int32_t nimfm_fm_adagrad_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset
       q.loss = cfg->loss; q.thr = cfg->huberThreshold;
       q.eta0 = cfg->eta0; q.alpha0 = cfg->alpha0; q.alpha = cfg->alpha; q.beta = cfg->beta;
       q.it0 = *it; q.zmax = zmax;
-      CK(cudaFuncSetAttribute(adagrad_fm_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      adagrad_fm_seq_kernel<<<1, ADASEQ_THREADS, smem, ctx->stream>>>(q);
+      const size_t smemPipe = (3 * (size_t)zmax * SB8 + (size_t)SB8 * (NIMFM_MAX_DEGREE + 1) + 3 * (size_t)zmax) * 8 +
+                              2 * (size_t)zmax * 4 + 16;
+      if (zmax <= 64 && smemPipe + 4096 <= (size_t)ctx->smemOptin && !(env && env[0] == 's')) {   // NIMFM_ADAGRAD_SEQ=staged
+        CK(cudaFuncSetAttribute(adagrad_fm_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemPipe));
+        adagrad_fm_pipe_kernel<<<1, ADAPIPE_THREADS, smemPipe, ctx->stream>>>(q);
+      } else {
+        CK(cudaFuncSetAttribute(adagrad_fm_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        adagrad_fm_seq_kernel<<<1, ADASEQ_THREADS, smem, ctx->stream>>>(q);
+      }
       LAUNCHED(ctx);
       CK(cudaGetLastError());
       CK(cudaMemcpyAsync(ctx->hostScalars, ctx->scalars, 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1368,8 +1375,22 @@ static int stream_host_rows(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t
   // 12 instead of 16 bytes per nonzero on the link; small calls and thread-starved ranks narrow on the device
   const int64_t stageMinNnz = getenv("NIMFM_HOST_STAGE_MIN_NNZ") ? atoll(getenv("NIMFM_HOST_STAGE_MIN_NNZ")) : (1 << 20);
   const bool bigCall = indices && nRows > 0 && indptr[nRows] - indptr[0] >= stageMinNnz;
-  const int hostT = !bigCall ? 0 : (is_pageable(data) ? HostStageTeam::pageable_threads(ctx->nranks)
-                                                      : HostStageTeam::default_threads(ctx->nranks));
+  // packed transport of the values when at least a quarter of a sample of them is exactly 1.0 (one-hot data) AND the
+  // rank has the host threads for it: lossless, 281 instead of 484 bytes per Criteo-shaped row on the link, but the
+  // team then reads the values too and becomes the bound -- measured on this box's 16 cores: 8 threads 83 M rows/s
+  // (worse than the 107 M of the raw route, which is link-bound), 14 threads 127 M (host-memory-bound).
+  // NIMFM_HOST_PACK=0 / 1 forces it off / on.
+  bool packValues = false;
+  if (bigCall && data && HostStageTeam::pageable_threads(ctx->nranks) >= 12) {
+    const int64_t nnzAll = indptr[nRows] - indptr[0], sample = std::min<int64_t>(nnzAll, 1 << 16);
+    int64_t ones = 0;
+    for (int64_t q = 0; q < sample; q++) ones += data[indptr[0] + q * (nnzAll / sample)] == 1.0;
+    packValues = ones * 4 >= sample;
+  }
+  if (const char *e = getenv("NIMFM_HOST_PACK")) packValues = bigCall && data && e[0] == '1';
+  const int hostT = !bigCall ? 0 : ((packValues || is_pageable(data)) ? HostStageTeam::pageable_threads(ctx->nranks)
+                                                                       : HostStageTeam::default_threads(ctx->nranks));
+  if (hostT == 0) packValues = false;
   int rc;
   const size_t capRows = (size_t)std::min(nRows, chunkRows) + 1;
   for (int s = 0; s < 2; s++)
@@ -1387,16 +1408,6 @@ static int stream_host_rows(nimfm_ctx *ctx, nimfm_fm *fm, int64_t nRows, int64_t
   std::unique_ptr<HostStageTeam> team;
   // pageable caller arrays: their values (and targets) travel through the team's pinned slots as well
   const bool pageable = hostT > 0 && is_pageable(data);
-  // packed transport of the values when at least a quarter of a sample of them is exactly 1.0 (one-hot data):
-  // lossless, 281 instead of 484 bytes per Criteo-shaped row on the link (NIMFM_HOST_PACK=0 / 1 forces it off / on)
-  bool packValues = false;
-  if (hostT > 0 && data && nRows > 0) {
-    const int64_t nnzAll = indptr[nRows] - indptr[0], sample = std::min<int64_t>(nnzAll, 1 << 16);
-    int64_t ones = 0;
-    for (int64_t q = 0; q < sample; q++) ones += data[indptr[0] + q * (nnzAll / sample)] == 1.0;
-    packValues = ones * 4 >= sample && sample > 0;
-    if (const char *e = getenv("NIMFM_HOST_PACK")) packValues = e[0] == '1';
-  }
   const bool stageValues = pageable && !packValues;
   if ((pageable || packValues) && (rc = ensure_host_value_slots(ctx, capRows, packValues ? 1 : maxNnz))) return rc;
   if (packValues && (rc = ensure_pack_buffers(ctx, maxNnz))) return rc;
