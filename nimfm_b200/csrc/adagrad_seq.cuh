@@ -193,7 +193,7 @@ static __global__ void __launch_bounds__(ADASEQ_THREADS, 1) adagrad_fm_seq_kerne
 // g_norm rows -- everything the previous sample may have changed -- are one round of independent loads; the forward
 // DP keeps the reference's order on SB8 threads and leaves A[.][1..M-1] in shared memory; updateG and the write-back
 // are one pass over all threads (element <-> thread) straight to global memory.  rows of at most 64 nonzeros.
-// dynamic smem: sP | sGs | sGn (zmax*SB8 each) | sA[SB8*(MAXDEG+1)] | sX[2][zmax] | sW[zmax] | sJ[2][zmax] (int32)
+// dynamic smem: sP | sGs | sGn (zmax*SB8 each) | sA[SB8*(MAXDEG+1)] | sX[2][zmax] | sW[zmax] | sJ[2][zmax] (int32) | sOrd[SB8]
 #define ADAPIPE_THREADS 512
 struct AdaPipeMeta {
   int64_t i, rb;
@@ -216,6 +216,10 @@ static __global__ void __launch_bounds__(ADAPIPE_THREADS, 1) adagrad_fm_pipe_ker
   int32_t *sJb = reinterpret_cast<int32_t *>(sW + zmax);
   const int tid = threadIdx.x, nth = blockDim.x, lastWarp0 = nth - 32;
   double viol = 0.0, lossAcc = 0.0;
+  ElemWalk walk0;
+  walk0.start(tid, nth, SB8);
+  signed char *sOrd = reinterpret_cast<signed char *>(sJb + 2 * zmax);   // [SB8] ANOVA order of (order, component) slot
+  for (int os = tid; os < SB8; os += nth) sOrd[os] = (signed char)(a.degree - os / k);
   if (tid == 0) {
     for (int64_t q = 0; q < 3 && q < a.nRows; ++q) {
       AdaPipeMeta m;
@@ -297,13 +301,14 @@ static __global__ void __launch_bounds__(ADAPIPE_THREADS, 1) adagrad_fm_pipe_ker
     }
     // ---- P / g_sum / g_norm of the row's features, update() of P (adagrad.nim:93-99): one batch of independent loads
     const double tmpP = a.eta0 * t * a.beta;
+    ElemWalk wl = walk0;
     for (int base = tid; base < z * SB8; base += 5 * nth) {
       double gsv[5], gnv[5], pv[5];
 #pragma unroll
       for (int r = 0; r < 5; ++r) {
-        const int e = base + r * nth;
-        const bool ok = e < z * SB8;
-        const int64_t ge = ok ? (int64_t)J[e / SB8] * SB8 + (e % SB8) : 0;
+        const bool ok = wl.u < z;
+        const int64_t ge = ok ? (int64_t)J[wl.u] * SB8 + wl.off : 0;
+        wl.next();
         gsv[r] = ok ? a.gsP[ge] : 0.0;
         gnv[r] = ok ? a.gnP[ge] : 1.0;
         pv[r] = ok ? a.P[ge] : 0.0;
@@ -357,10 +362,12 @@ static __global__ void __launch_bounds__(ADAPIPE_THREADS, 1) adagrad_fm_pipe_ker
     __syncthreads();
     const double dL = sh[1];
     // ---- updateG (adagrad.nim:113-134) + write-back, element <-> thread
+    ElemWalk wk = walk0;
 #pragma unroll 2
     for (int e = tid; e < z * SB8; e += nth) {
-      const int u = e / SB8, os = e - u * SB8;
-      const int M = a.degree - os / k;
+      const int u = wk.u, os = wk.off;
+      wk.next();
+      const int M = sOrd[os];
       const double x = X[u], p = sP[e];
       const double *A = sA + os * AST;
       double g;

@@ -386,6 +386,28 @@ __device__ __forceinline__ double anova_deriv(const AnovaState &A, int M, double
   return g;
 }
 
+// element e = tid + r*nth of a row slice [z][SB8] as (u, off) = (e / SB8, e % SB8) WITHOUT a division per element: the
+// single-block sequential solvers walk thousands of such elements per sample and a runtime integer division costs
+// ~35 instructions.  start() is evaluated once per kernel (tid, nth and SB8 never change), next() is two adds.
+struct ElemWalk {
+  int u, off, du, doff, SB8;
+  __device__ __forceinline__ void start(int tid, int nth, int sb8) {
+    SB8 = sb8;
+    u = tid / sb8;
+    off = tid - u * sb8;
+    du = nth / sb8;
+    doff = nth - du * sb8;
+  }
+  __device__ __forceinline__ void next() {
+    u += du;
+    off += doff;
+    if (off >= SB8) {
+      off -= SB8;
+      ++u;
+    }
+  }
+};
+
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");

@@ -1020,7 +1020,7 @@ int32_t nimfm_fm_adagrad_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset
       q.eta0 = cfg->eta0; q.alpha0 = cfg->alpha0; q.alpha = cfg->alpha; q.beta = cfg->beta;
       q.it0 = *it; q.zmax = zmax;
       const size_t smemPipe = (3 * (size_t)zmax * SB8 + (size_t)SB8 * (NIMFM_MAX_DEGREE + 1) + 3 * (size_t)zmax) * 8 +
-                              2 * (size_t)zmax * 4 + 16;
+                              2 * (size_t)zmax * 4 + (size_t)SB8 + 16;
       if (zmax <= 64 && smemPipe + 4096 <= (size_t)ctx->smemOptin && !(env && env[0] == 's')) {   // NIMFM_ADAGRAD_SEQ=staged
         CK(cudaFuncSetAttribute(adagrad_fm_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemPipe));
         adagrad_fm_pipe_kernel<<<1, ADAPIPE_THREADS, smemPipe, ctx->stream>>>(q);

@@ -273,6 +273,322 @@ __global__ void __launch_bounds__(PSGD_THREADS, 1) psgd_lazy_kernel(const PsgdAr
   }
 }
 
+// The same loop PIPELINED (as sgd_fm_pipe_kernel / adagrad_fm_pipe_kernel): the read-only CSR side of the dependent
+// load chain (permutation -> row pointer / target -> indices / values) is fetched one to three samples ahead by the
+// last warp; the row's P slice, w and the lazy caches -- what the previous sample may have changed -- are ONE round
+// of independent loads held in registers until the lazy factors are known; the step is element <-> thread on the
+// whole block and, for L1, goes straight to global memory.  Rows of at most 64 nonzeros, z*SB8 <= PIPE_R*threads.
+// dynamic smem: sP[zmax*SB8] | sA[SB8*(MAXDEG+1)] | sX[2][zmax] | sW | sSc | sTh (zmax each) | sJ[2][zmax] (int32) | sOrd[SB8]
+#define PSGD_PIPE_THREADS 512
+#define PSGD_PIPE_R 12
+struct PsgdPipeMeta {
+  int64_t i, rb;
+  double y;
+  int z;
+};
+
+__global__ void __launch_bounds__(PSGD_PIPE_THREADS, 1) psgd_lazy_pipe_kernel(const PsgdArgs a) {
+  extern __shared__ __align__(16) unsigned char psgd_smem[];
+  __shared__ double red[PSGD_PIPE_THREADS / 32];
+  __shared__ double sh[8];   // 1 reg scaling, 2 reg threshold, 3 scaling_w, 4 dL
+  __shared__ PsgdPipeMeta meta[4];
+  __shared__ double sEta[8];   // [q & 1][eta_w, eta_P, eta_0, -]
+  const int k = a.k, NO = a.nOrders, SB8 = NO * k, zmax = a.zmax, AST = NIMFM_MAX_DEGREE + 1;
+  double *sP = reinterpret_cast<double *>(psgd_smem);
+  double *sA = sP + (size_t)zmax * SB8;
+  double *sXb = sA + (size_t)SB8 * AST;
+  double *sW = sXb + 2 * (size_t)zmax;
+  double *sSc = sW + zmax;
+  double *sTh = sSc + zmax;
+  int32_t *sJb = reinterpret_cast<int32_t *>(sTh + zmax);
+  const int tid = threadIdx.x, nth = blockDim.x, wid = tid >> 5, nw = nth >> 5, lastWarp0 = nth - 32;
+  const bool isL1 = a.cfg.reg == NIMFM_REG_L1;
+  const double alpha0 = a.cfg.alpha0, alpha = a.cfg.alpha, beta = a.cfg.beta, gamma = a.cfg.gamma;
+  double lossAcc = 0.0;
+  ElemWalk walk0;
+  walk0.start(tid, nth, SB8);
+  signed char *sOrd = reinterpret_cast<signed char *>(sJb + 2 * zmax);   // [SB8] ANOVA order of (order, component) slot
+  for (int os = tid; os < SB8; os += nth) sOrd[os] = (signed char)(a.degree - os / k);
+  if (tid == 32) {
+    sEta[0] = psgd_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, alpha, a.it0);
+    sEta[1] = psgd_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, beta, a.it0);
+    sEta[2] = psgd_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, alpha0, a.it0);
+  }
+  if (tid == 0) {
+    sh[1] = a.scal[0];
+    sh[2] = a.scal[1];
+    sh[3] = a.scal[2];
+    for (int64_t q = 0; q < 3 && q < a.nRows; ++q) {
+      PsgdPipeMeta m;
+      m.i = a.perm ? (int64_t)a.perm[q] : q;
+      m.rb = 0; m.z = 0; m.y = 0.0;
+      if (q < 2) {
+        m.rb = a.indptr[m.i];
+        m.z = (int)(a.indptr[m.i + 1] - m.rb);
+        m.y = a.y[m.i];
+      }
+      meta[q & 3] = m;
+    }
+  }
+  __syncthreads();
+  if (tid >= lastWarp0 && a.nRows > 0) {
+    const PsgdPipeMeta m = meta[0];
+    for (int u = tid - lastWarp0; u < m.z + a.nAug; u += 32) {
+      sJb[u] = u < m.z ? a.indices[m.rb + u] : (int32_t)(a.d + (u - m.z));
+      sXb[u] = u < m.z ? a.data[m.rb + u] : 1.0;
+    }
+  }
+  __syncthreads();
+  for (int64_t q = 0; q < a.nRows; ++q) {
+    const int64_t it = a.it0 + q;
+    const PsgdPipeMeta m = meta[q & 3];
+    const int zReal = m.z, z = zReal + a.nAug;
+    const int32_t *J = sJb + (q & 1) * zmax;
+    const double *X = sXb + (q & 1) * zmax;
+    const double rSc = sh[1], rTh = sh[2], scW = sh[3];
+    // ---- fetch ahead (registers now, shared memory at the end of the iteration)
+    int64_t pfI = 0, pfRb = 0, pfRe = 0;
+    double pfY = 0.0, pfX0 = 0.0, pfX1 = 0.0;
+    int32_t pfJ0 = 0, pfJ1 = 0;
+    if (tid == nth - 1) {
+      if (q + 3 < a.nRows) pfI = a.perm ? (int64_t)a.perm[q + 3] : q + 3;
+      if (q + 2 < a.nRows) {
+        const int64_t i2 = meta[(q + 2) & 3].i;
+        pfRb = a.indptr[i2];
+        pfRe = a.indptr[i2 + 1];
+        pfY = a.y[i2];
+      }
+    }
+    const PsgdPipeMeta m1 = meta[(q + 1) & 3];
+    const int z1 = q + 1 < a.nRows ? m1.z + a.nAug : 0;
+    if (tid >= lastWarp0) {
+      const int u0 = tid - lastWarp0, u1 = u0 + 32;
+      if (u0 < z1) {
+        pfJ0 = u0 < m1.z ? a.indices[m1.rb + u0] : (int32_t)(a.d + (u0 - m1.z));
+        pfX0 = u0 < m1.z ? a.data[m1.rb + u0] : 1.0;
+      }
+      if (u1 < z1) {
+        pfJ1 = u1 < m1.z ? a.indices[m1.rb + u1] : (int32_t)(a.d + (u1 - m1.z));
+        pfX1 = u1 < m1.z ? a.data[m1.rb + u1] : 1.0;
+      }
+    }
+    // ---- the row's P slice (raw) and the lazy factors of every row feature incl. dummies (psgd.nim:121-127)
+    double pv[PSGD_PIPE_R];
+    {
+      ElemWalk wk = walk0;
+#pragma unroll
+      for (int r = 0; r < PSGD_PIPE_R; ++r) {
+        pv[r] = wk.u < z ? a.P[(int64_t)J[wk.u] * SB8 + wk.off] : 0.0;
+        wk.next();
+      }
+    }
+    if (tid < z) {
+      const int u = tid;
+      const int64_t j = J[u];
+      const double sj = a.regScalings[j], tj = a.regThresholds[j];
+      sW[u] = u < zReal ? a.w[j] * (scW / a.scalingsW[j]) : 0.0;       // sfm.w[j] *= scaling_w / scalings_w[j]
+      sSc[u] = rSc / sj;
+      sTh[u] = isL1 ? gamma * rSc * (rTh - tj)                         // l1.nim:89-90
+                    : ((rTh - tj) / sj) * gamma;                       // l21.nim:62-63
+    }
+    // the step sizes (a pow() each: ~1000 dependent FP64 instructions, longer than the load round) are computed ONE
+    // SAMPLE AHEAD by three threads of three different warps and parked with the prefetched rows
+    double etaNext = 0.0;
+    if (tid == nth - 33) etaNext = psgd_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, alpha, it + 1);
+    if (tid == nth - 65) etaNext = psgd_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, beta, it + 1);
+    if (tid == nth - 97) etaNext = psgd_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, alpha0, it + 1);
+    __syncthreads();
+    const double *shEta = sEta + (q & 1) * 4;
+    const double etaW = shEta[0], etaP = shEta[1];
+    const double etaS = etaP / (1.0 + etaP * beta);                     // psgd.nim:134
+    {
+      ElemWalk wk = walk0;
+#pragma unroll
+      for (int r = 0; r < PSGD_PIPE_R; ++r) {
+        if (wk.u < z) {
+          double p = pv[r];
+          if (isL1) {                                                  // l1.nim:86-90
+            p *= sSc[wk.u];
+            p = psgd_soft(p, sTh[wk.u]);
+          }
+          sP[tid + r * nth] = p;
+        }
+        wk.next();
+      }
+    }
+    __syncthreads();
+    if (!isL1) {                                                       // l21.nim:60-65: prox, then scale
+      for (int v = wid; v < z * NO; v += nw) {
+        const int u = v / NO;
+        psgd_l21_prox_warp(sP + (size_t)v * k, k, sTh[u], sSc[u]);
+      }
+      __syncthreads();
+    }
+    // ---- predictWithGrad forward (thread <-> (order, component), nonzeros in row order)
+    double part = 0.0;
+    for (int u = tid; u < zReal; u += nth) part += sW[u] * X[u];
+    if (tid < SB8) {
+      const int o = tid / k, sc = tid - o * k;
+      const int M = a.degree - o;
+      AnovaState A;
+      anova_init(A);
+#pragma unroll 4
+      for (int u = 0; u < z; u++) {
+        const double tv = sP[u * SB8 + o * k + sc] * X[u];
+        if (M == 2) {
+          A[1] += tv;
+          A[2] += tv * tv;
+        } else {
+          anova_step(A, M, tv);
+        }
+      }
+      part += M == 2 ? (A[1] * A[1] - A[2]) / 2.0 : anova_at(A, M);
+#pragma unroll
+      for (int tt = 1; tt < NIMFM_MAX_DEGREE; ++tt)
+        if (tt < M) sA[tid * AST + tt] = A[tt];
+    }
+    const double yh = block_sum(part, red);
+    if (tid == 0) {
+      const double yhat = yh + a.b[0];
+      lossAcc += dev_loss(a.cfg.loss, a.cfg.huberThreshold, m.y, yhat);
+      sh[4] = dev_dloss(a.cfg.loss, a.cfg.huberThreshold, m.y, yhat);
+    }
+    __syncthreads();
+    const double dL = sh[4];
+    // ---- reg.step (l1.nim:127-136 / l21.nim:102-112), element <-> thread
+    {
+      ElemWalk wk = walk0;
+#pragma unroll 2
+      for (int e = tid; e < z * SB8; e += nth) {
+        const int u = wk.u, os = wk.off;
+        wk.next();
+        const int M = sOrd[os];
+        const double x = X[u], p = sP[e];
+        const double *A = sA + os * AST;
+        double g;
+        if (M == 2) g = x * (A[1] - p * x);
+        else {
+          g = x;
+          for (int tt = 1; tt < M; tt++) g = x * (A[tt] - p * g);
+        }
+        const double upd = etaS * (dL * g + beta * p);
+        if (isL1) a.P[(int64_t)J[u] * SB8 + os] = psgd_soft(p - upd, gamma * etaS);
+        else sP[e] = p - upd;
+      }
+    }
+    if (!isL1) {
+      __syncthreads();
+      for (int v = wid; v < z * NO; v += nw) psgd_l21_prox_warp(sP + (size_t)v * k, k, etaS * gamma, 1.0);
+      __syncthreads();
+      ElemWalk wk = walk0;
+      for (int e = tid; e < z * SB8; e += nth) {
+        a.P[(int64_t)J[wk.u] * SB8 + wk.off] = sP[e];
+        wk.next();
+      }
+    }
+    // ---- reg.updateCacheSGD (l1.nim:106-113 / l21.nim:84-90), w, intercept, caches
+    double nSc, nTh;
+    if (isL1) {
+      nTh = rTh + etaS / rSc;
+      nSc = rSc * (1 - etaS * beta);
+    } else {
+      nTh = rTh + etaP * rSc;
+      nSc = rSc / (1 + etaP * beta);
+    }
+    const double nScW = scW / (1.0 + etaW * alpha);                     // psgd.nim:153
+    if (tid < z) {
+      const int u = tid;
+      const int64_t j = J[u];
+      a.regScalings[j] = nSc;
+      a.regThresholds[j] = nTh;
+      if (u < zReal) {
+        if (a.fitLinear) {                                              // fitLinearSGD with eta_w/(1+eta_w*alpha)
+          const double eta = etaW / (1.0 + etaW * alpha);
+          a.w[j] = sW[u] - eta * (dL * X[u] + alpha * sW[u]);
+        }
+        a.scalingsW[j] = nScW;
+      }
+    }
+    // ---- park what was fetched ahead
+    if (tid == nth - 1) {
+      if (q + 3 < a.nRows) meta[(q + 3) & 3].i = pfI;
+      if (q + 2 < a.nRows) {
+        PsgdPipeMeta &m2 = meta[(q + 2) & 3];
+        m2.rb = pfRb;
+        m2.z = (int)(pfRe - pfRb);
+        m2.y = pfY;
+      }
+    }
+    if (tid >= lastWarp0) {
+      int32_t *Jn = sJb + ((q + 1) & 1) * zmax;
+      double *Xn = sXb + ((q + 1) & 1) * zmax;
+      const int u0 = tid - lastWarp0, u1 = u0 + 32;
+      if (u0 < z1) { Jn[u0] = pfJ0; Xn[u0] = pfX0; }
+      if (u1 < z1) { Jn[u1] = pfJ1; Xn[u1] = pfX1; }
+    }
+    if (tid == nth - 33) sEta[((q + 1) & 1) * 4 + 0] = etaNext;
+    if (tid == nth - 65) sEta[((q + 1) & 1) * 4 + 1] = etaNext;
+    if (tid == nth - 97) sEta[((q + 1) & 1) * 4 + 2] = etaNext;
+    if (tid == 0) {                                                     // (sh[1..3] were read before the first barrier)
+      if (a.fitIntercept) {                                             // psgd.nim:146-148
+        const double e0 = shEta[2];
+        const double upd = e0 * (dL + alpha0 * a.b[0]);
+        a.b[0] -= upd / (1.0 + e0 * alpha0);
+      }
+      sh[1] = nSc;
+      sh[2] = nTh;
+      sh[3] = nScW;
+    }
+    // ---- resets against underflow (psgd.nim:158-163; l1.nim:116-124 and l21.nim:93-104 as written): rare
+    if ((a.fitLinear && nScW < 1e-9) || nSc < 1e-8) {
+      __syncthreads();
+      if (a.fitLinear && nScW < 1e-9) {
+        for (int64_t j = tid; j < a.d; j += nth) {
+          double v = a.w[j] * nScW;
+          a.w[j] = v / a.scalingsW[j];
+          a.scalingsW[j] = 1.0;
+        }
+        __syncthreads();
+        if (tid == 0) sh[3] = 1.0;
+        __syncthreads();
+      }
+      if (nSc < 1e-8) {
+        if (isL1) {
+          for (int64_t e = tid; e < a.dd * SB8; e += nth) {
+            const int64_t j = e / SB8;
+            double p = a.P[e] / a.regScalings[j];
+            p = psgd_soft(p, gamma * nTh - a.regThresholds[j]);
+            a.P[e] = p * nTh;
+          }
+        } else {
+          for (int64_t v = wid; v < a.dd * NO; v += nw) {
+            const int64_t j = v / NO;
+            const double thr = (nTh - a.regThresholds[j]) / a.regScalings[j];
+            psgd_l21_prox_warp(a.P + v * k, k, thr * gamma, nSc / a.regScalings[j]);
+          }
+        }
+        __syncthreads();
+        for (int64_t j = tid; j < a.dd; j += nth) {
+          a.regScalings[j] = 1.0;
+          a.regThresholds[j] = 0.0;
+        }
+        if (tid == 0) {
+          sh[1] = 1.0;
+          sh[2] = 0.0;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  lossAcc = block_sum(lossAcc, red);
+  if (tid == 0) {
+    a.scal[0] = sh[1];
+    a.scal[1] = sh[2];
+    a.scal[2] = sh[3];
+    a.scal[3] = lossAcc;
+  }
+}
+
 // finalize (psgd.nim:58-75): w catch-up, reg.lazyUpdateFinal (l1.nim:93-103 resets its caches,
 // l21.nim:68-75 does not)
 __global__ void __launch_bounds__(PSGD_THREADS, 1) psgd_finalize_kernel(const PsgdArgs a) {
@@ -411,8 +727,17 @@ int32_t nimfm_fm_psgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X
     a.P = fm->P; a.w = fm->w; a.b = fm->b;
     a.regScalings = fm->scalingsP; a.regThresholds = fm->psgdThr; a.scalingsW = fm->scalingsW; a.scal = fm->sgdScal;
     a.cfg = *cfg; a.it0 = *it; a.zmax = zmax;
-    CK(cudaFuncSetAttribute(psgd_lazy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    psgd_lazy_kernel<<<1, PSGD_THREADS, smem, ctx->stream>>>(a);
+    const size_t smemPipe = ((size_t)zmax * SB8 + (size_t)SB8 * (NIMFM_MAX_DEGREE + 1) + 5 * (size_t)zmax) * 8 +
+                            2 * (size_t)zmax * 4 + (size_t)SB8 + 16;
+    const char *env = getenv("NIMFM_PSGD_KERNEL");   // "staged": the unpipelined kernel
+    if (zmax <= 64 && (size_t)zmax * SB8 <= (size_t)PSGD_PIPE_R * PSGD_PIPE_THREADS &&
+        smemPipe + 4096 <= (size_t)ctx->smemOptin && !(env && env[0] == 's')) {
+      CK(cudaFuncSetAttribute(psgd_lazy_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemPipe));
+      psgd_lazy_pipe_kernel<<<1, PSGD_PIPE_THREADS, smemPipe, ctx->stream>>>(a);
+    } else {
+      CK(cudaFuncSetAttribute(psgd_lazy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      psgd_lazy_kernel<<<1, PSGD_THREADS, smem, ctx->stream>>>(a);
+    }
     LAUNCHED(ctx);
   } else {
     for (int64_t q = 0; q < nRows; q++) {

@@ -404,8 +404,9 @@ __global__ void __launch_bounds__(SGD_THREADS, 1) sgd_fm_staged_kernel(const Sgd
 //     A[.][1..M-1] in shared memory, and the derivative + update + write-back is spread over ALL threads
 //     (element <-> thread), straight from shared memory to global.
 // Same arithmetic per parameter element as sgd_epoch_kernel<false>; viol is summed in a different order.
-// dynamic smem: sP[zmax*SB8] | sA[SB8*(MAXDEG+1)] | sX[2][zmax] | sW[zmax] | sSc[zmax] | sJ[2][zmax] (int32)
+// dynamic smem: sP[zmax*SB8] | sA[SB8*(MAXDEG+1)] | sX[2][zmax] | sW[zmax] | sSc[zmax] | sJ[2][zmax] (int32) | sOrd[SB8]
 #define SGDP_THREADS 512
+#define SGDP_R 12                       // row slice elements per thread: zmax * SB8 <= SGDP_R * SGDP_THREADS
 struct SgdPipeMeta {
   int64_t i, rb;
   double y;
@@ -415,8 +416,9 @@ struct SgdPipeMeta {
 __global__ void __launch_bounds__(SGDP_THREADS, 1) sgd_fm_pipe_kernel(const SgdArgs a, int zmax) {
   extern __shared__ __align__(16) unsigned char sgd_smem[];
   __shared__ double red[SGDP_THREADS / 32];
-  __shared__ double sh[8];              // [1] scaling_P, [2] scaling_w, [3] dL, [4..6] eta_P, eta_w, eta_b of this sample
+  __shared__ double sh[8];              // [1] scaling_P, [2] scaling_w, [3] dL
   __shared__ SgdPipeMeta meta[4];       // ring: sample q lives in meta[q & 3]
+  __shared__ double sEta[8];            // [q & 1][eta_P, eta_w, eta_b, -]
   const int k = a.k, NO = a.nOrders, SB8 = NO * k, AST = NIMFM_MAX_DEGREE + 1;
   double *sP = reinterpret_cast<double *>(sgd_smem);
   double *sA = sP + (size_t)zmax * SB8;
@@ -429,8 +431,17 @@ __global__ void __launch_bounds__(SGDP_THREADS, 1) sgd_fm_pipe_kernel(const SgdA
   double viol = 0.0, lossAcc = 0.0;
   long long prof[4] = {0, 0, 0, 0};
   const double alpha0 = a.cfg.alpha0, alpha = a.cfg.alpha, beta = a.cfg.beta;
+  ElemWalk walk0;                       // (u, off) of this thread's elements of a row slice without divisions
+  walk0.start(tid, nth, SB8);
+  signed char *sOrd = reinterpret_cast<signed char *>(sJb + 2 * zmax);   // [SB8] ANOVA order of (order, component) slot
+  for (int os = tid; os < SB8; os += nth) sOrd[os] = (signed char)(a.degree - os / k);
 
   // prologue: the read-only chain of the first samples, loaded the plain way
+  if (tid == 32) {
+    sEta[0] = dev_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, beta, a.it0);
+    sEta[1] = dev_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, alpha, a.it0);
+    sEta[2] = dev_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, alpha0, a.it0);
+  }
   if (tid == 0) {
     sh[1] = a.scal[0];
     sh[2] = a.scal[1];
@@ -504,27 +515,31 @@ __global__ void __launch_bounds__(SGDP_THREADS, 1) sgd_fm_pipe_kernel(const SgdA
         sW[tid] = 0.0;
       }
     }
-    for (int base = tid; base < z * SB8; base += 6 * nth) {   // all loads of a batch before the first store: one
-      double pr[6];                                            // memory latency per batch, not one per element
+    double pr[SGDP_R];                                       // the row's P slice: all loads before the first use (one
+    {                                                        // memory latency, not one per element), held in registers
+      ElemWalk wk = walk0;                                   // until the lazy factors are in shared memory
 #pragma unroll
-      for (int r = 0; r < 6; ++r) {
-        const int e = base + r * nth;
-        pr[r] = e < z * SB8 ? a.P[(int64_t)J[e / SB8] * SB8 + (e % SB8)] : 0.0;
-      }
-#pragma unroll
-      for (int r = 0; r < 6; ++r) {
-        const int e = base + r * nth;
-        if (e < z * SB8) sP[e] = pr[r];
+      for (int r = 0; r < SGDP_R; ++r) {
+        pr[r] = wk.u < z ? a.P[(int64_t)J[wk.u] * SB8 + wk.off] : 0.0;
+        wk.next();
       }
     }
-    if (tid == nth - 33) {                                   // an idle thread of the second-to-last warp: the step sizes
-      sh[4] = dev_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, beta, it);
-      sh[5] = dev_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, alpha, it);
-      sh[6] = dev_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, alpha0, it);
-    }
+    // the step sizes (a pow() each: ~1000 dependent FP64 instructions, longer than the load round above) are computed
+    // ONE SAMPLE AHEAD by three threads of three different warps and parked with the prefetched rows
+    double etaNext = 0.0;
+    if (tid == nth - 33) etaNext = dev_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, beta, it + 1);
+    if (tid == nth - 65) etaNext = dev_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, alpha, it + 1);
+    if (tid == nth - 97) etaNext = dev_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, alpha0, it + 1);
     __syncthreads();
     long long c1 = clock64();
-    for (int e = tid; e < zReal * SB8; e += nth) sP[e] *= sSc[e / SB8];
+    {
+      ElemWalk wk = walk0;
+#pragma unroll
+      for (int r = 0; r < SGDP_R; ++r) {
+        if (wk.u < z) sP[tid + r * nth] = wk.u < zReal ? pr[r] * sSc[wk.u] : pr[r];
+        wk.next();
+      }
+    }
     __syncthreads();
     // ---- predictWithGrad: forward, thread <-> (order, component), nonzeros in row order (sgd.nim:146-173)
     double part = 0.0;
@@ -557,13 +572,16 @@ __global__ void __launch_bounds__(SGDP_THREADS, 1) sgd_fm_pipe_kernel(const SgdA
       sh[3] = dev_dloss(a.cfg.loss, a.cfg.huberThreshold, m.y, yhat);
     }
     __syncthreads();
-    const double dL = sh[3], etaP = sh[4], etaW = sh[5];
+    const double *shEta = sEta + (q & 1) * 4;
+    const double dL = sh[3], etaP = shEta[0], etaW = shEta[1];
     long long c3 = clock64();
     // ---- update (sgd.nim:205-243): element <-> thread, derivative recurrence from the stored A (sgd.nim:176-188)
+    ElemWalk wu = walk0;
 #pragma unroll 2
     for (int e = tid; e < z * SB8; e += nth) {
-      const int u = e / SB8, os = e - u * SB8;
-      const int M = a.degree - os / k;
+      const int u = wu.u, os = wu.off;
+      wu.next();
+      const int M = sOrd[os];
       const double x = X[u], p = sP[e];
       const double *A = sA + os * AST;
       double g;
@@ -591,7 +609,7 @@ __global__ void __launch_bounds__(SGDP_THREADS, 1) sgd_fm_pipe_kernel(const SgdA
     }
     if (tid == 0) {
       if (a.fitIntercept) {
-        const double upd = sh[6] * (dL + alpha0 * a.b[0]);
+        const double upd = shEta[2] * (dL + alpha0 * a.b[0]);
         viol += fabs(upd);
         a.b[0] -= upd;
       }
@@ -615,6 +633,9 @@ __global__ void __launch_bounds__(SGDP_THREADS, 1) sgd_fm_pipe_kernel(const SgdA
       if (u0 < z1) { Jn[u0] = pfJ0; Xn[u0] = pfX0; }
       if (u1 < z1) { Jn[u1] = pfJ1; Xn[u1] = pfX1; }
     }
+    if (tid == nth - 33) sEta[((q + 1) & 1) * 4 + 0] = etaNext;
+    if (tid == nth - 65) sEta[((q + 1) & 1) * 4 + 1] = etaNext;
+    if (tid == nth - 97) sEta[((q + 1) & 1) * 4 + 2] = etaNext;
     __syncthreads();
     if (a.nFields == -7 && tid == 0) {   // phase profile (debug): cycles of this sample's phases
       long long c4 = clock64();
@@ -727,8 +748,8 @@ int32_t nimfm_fm_sgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X,
   const int zmax = (int)std::max<int64_t>(X->maxSegNnz + fm->nAug, 1);
   const size_t smem = ((size_t)zmax * SB8 + 3 * (size_t)zmax) * 8 + (size_t)zmax * 8;
   const char *env = getenv("NIMFM_SGD_KERNEL");
-  const size_t smemPipe = ((size_t)zmax * SB8 + (size_t)SB8 * (NIMFM_MAX_DEGREE + 1) + 4 * (size_t)zmax) * 8 + 2 * (size_t)zmax * 4 + 16;
-  if (SB8 <= SGDP_THREADS - 64 && zmax <= 64 && smemPipe <= (size_t)ctx->smemOptin - 4096 && !env) {
+  const size_t smemPipe = ((size_t)zmax * SB8 + (size_t)SB8 * (NIMFM_MAX_DEGREE + 1) + 4 * (size_t)zmax) * 8 + 2 * (size_t)zmax * 4 + (size_t)SB8 + 16;
+  if (SB8 <= SGDP_THREADS - 64 && zmax <= 64 && (size_t)zmax * SB8 <= (size_t)SGDP_R * SGDP_THREADS && smemPipe <= (size_t)ctx->smemOptin - 4096 && !env) {
     if (getenv("NIMFM_SGD_PROFILE")) a.nFields = -7;
     CK(cudaFuncSetAttribute(sgd_fm_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemPipe));
     sgd_fm_pipe_kernel<<<1, SGDP_THREADS, smemPipe, ctx->stream>>>(a, zmax);

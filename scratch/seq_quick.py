@@ -17,3 +17,10 @@ for name, mk in (("SGD", lambda: nf.newSGD(maxIter=2, eta0=0.01, loss=nf.Logisti
     opt.fit(ds, y, fm)
     ep = float(np.min(opt.epoch_seconds))
     print(json.dumps({"solver": name, "rows": n, "s_per_epoch": ep, "samples_per_s": n / ep, "hist": opt.history[-1]}), flush=True)
+for name, reg in (("PSGD L1", nf.newL1), ("PSGD L21", nf.newL21)):
+    fm = nf.newFactorizationMachine(nf.classification, degree=3, nComponents=32, warmStart=True)
+    fm.P, fm.w, fm.intercept, fm.isInitialized = P.copy(), w.copy(), b, True
+    opt = nf.newPSGD(maxIter=2, eta0=0.01, gamma=1e-5, loss=nf.Logistic(), reg=reg(), verbose=0, tol=0.0, shuffle=False)
+    opt.fit(ds, y, fm)
+    ep = float(np.min(opt.epoch_seconds))
+    print(json.dumps({"solver": name, "rows": n, "s_per_epoch": ep, "samples_per_s": n / ep, "hist": opt.history[-1]}), flush=True)

@@ -445,6 +445,29 @@ def test_adagrad_matches_oracle(oracle, degree, fit_lower, mb):
     np.testing.assert_allclose(opt.g_norm["P"], ref["state"]["gnP"], rtol=1e-8, atol=1e-14)
 
 
+@pytest.mark.parametrize("route", ["pipe", "staged", "0"])
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_adagrad_sequential_routes_agree(oracle, monkeypatch, route, shuffle):
+    """miniBatchSize=1 has three device routes (adagrad_seq.cuh pipelined / staged kernels, the minibatch pipeline
+    with one-row batches): each must give the reference's per-sample result (adagrad.nim:164-181), shuffled or not"""
+    monkeypatch.setenv("NIMFM_ADAGRAD_SEQ", route)
+    n, d, k, degree = 150, 40, 8, 3
+    X = make_dense(n, d, 23, density=0.3, positive=False)
+    y = np.sign(np.random.default_rng(6).standard_normal(n))
+    csr = CSR.from_dense(X)
+    P, w, _ = make_fm_params(d, degree, k, "explicit", True, seed=8, scale=0.1)
+    fm = make_fm(degree, k, "explicit", True, True, P, w, 0.0)
+    opt = nf.newAdaGrad(maxIter=3, loss=nf.Logistic(), verbose=0, tol=0.0, shuffle=shuffle, miniBatchSize=1)
+    perms = [np.random.default_rng(30 + e).permutation(n).astype(np.int64) for e in range(3)] if shuffle else []
+    opt.fit(csr_ds(csr), y, fm, perms=perms if shuffle else None)
+    ref = oracle.adagrad_fit(csr, y, P, w, 0.0, degree, "logistic", True, True, max_iter=3, mini_batch_size=1,
+                             perms=np.array(perms) if shuffle else None)
+    np.testing.assert_allclose([h[1] for h in opt.history], ref["loss"], rtol=OBJ_TOL)
+    np.testing.assert_allclose(fm.P, ref["P"], rtol=1e-8, atol=1e-13)
+    np.testing.assert_allclose(fm.w, ref["w"], rtol=1e-8, atol=1e-13)
+    assert abs(fm.intercept - ref["intercept"]) <= 1e-9
+
+
 def test_adagrad_max_threads_maps_to_synchronous_minibatch(oracle):
     """fit(..., maxThreads=T) (the reference's Hogwild entry point) runs the deterministic synchronous
     minibatch of T samples"""
