@@ -117,18 +117,7 @@ static __global__ void __launch_bounds__(ADASEQ_THREADS, 1) adagrad_fm_seq_kerne
     const int o = os < SB8 ? os / k : 0, sc = os - o * k;
     const int M = a.degree - o;
     if (os < SB8) {
-      anova_init(A);
-#pragma unroll 4
-      for (int u = 0; u < z; u++) {
-        const double tv = sP[u * SB8 + o * k + sc] * sX[u];
-        if (M == 2) {
-          A[1] += tv;
-          A[2] += tv * tv;
-        } else {
-          anova_step(A, M, tv);
-        }
-      }
-      part += M == 2 ? (A[1] * A[1] - A[2]) / 2.0 : anova_at(A, M);
+      part += anova_forward_smem(A, M, sP + o * k + sc, SB8, sX, z);
     }
     double yhat = block_sum(part, red);
     if (tid == 0) {
@@ -337,18 +326,7 @@ static __global__ void __launch_bounds__(ADAPIPE_THREADS, 1) adagrad_fm_pipe_ker
       const int o = tid / k, sc = tid - o * k;
       const int M = a.degree - o;
       AnovaState A;
-      anova_init(A);
-#pragma unroll 4
-      for (int u = 0; u < z; u++) {
-        const double tv = sP[u * SB8 + o * k + sc] * X[u];
-        if (M == 2) {
-          A[1] += tv;
-          A[2] += tv * tv;
-        } else {
-          anova_step(A, M, tv);
-        }
-      }
-      part += M == 2 ? (A[1] * A[1] - A[2]) / 2.0 : anova_at(A, M);
+      part += anova_forward_smem(A, M, sP + o * k + sc, SB8, X, z);
 #pragma unroll
       for (int tt = 1; tt < NIMFM_MAX_DEGREE; ++tt)
         if (tt < M) sA[tid * AST + tt] = A[tt];

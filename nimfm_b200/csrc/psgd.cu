@@ -12,6 +12,7 @@
 //    every sample updates ALL parameters and runs the full prox.  Here: row kernel on the one sample
 //    (K2, coef = dloss) -> dense step kernel -> the MBPSGD prox kernels (prox_kernels.cuh).
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -63,6 +64,7 @@ struct PsgdArgs {
   nimfm_psgd_cfg cfg;
   int64_t it0;
   int zmax;
+  int profile;   // NIMFM_PSGD_PROFILE: print the pipelined kernel's cycles per phase (debug)
 };
 
 // L21.prox of the k-vector at v (l21.nim:25-29) by one warp; every lane of the warp must call
@@ -75,6 +77,50 @@ __device__ __forceinline__ void psgd_l21_prox_warp(double *v, int k, double lam,
   for (int s = lane; s < k; s += 32) {
     double p = nrm > lam ? v[s] * f : 0.0;
     v[s] = p * post;
+  }
+}
+
+// the same prox for up to EIGHT vectors of k <= 32 components per warp at a time (v0, v0+nw, ...), as STRAIGHT-LINE
+// code: lane <-> component, the element stays in a register from the norm to the write-back.  This single block is
+// bound by the latency of dependent instructions (~5 cycles each, 9 per FP64 operation, ~100 per sqrt or divide),
+// and the generic form above costs ~1000 of them per vector in loop and branch overhead (measured: 9 000 cycles per
+// prox round of a 39-nonzero row, more than the rest of the sample).  Here the eight sums are reduced with
+// interleaved butterflies (every lane ends up with all of them), LANE c runs the sqrt / divide of vector c, and the
+// factors are broadcast back: one sqrt -> divide chain per call.  lamTab / postTab are indexed by v / NO when
+// non-null (the lazy catch-up), else lamC / 1.0 (the step's prox).  Every lane of the warp must call.
+__device__ __forceinline__ void psgd_l21_prox_warp_x8(double *sP, int v0, int nw, int nv, int k, int NO,
+                                                      const double *lamTab, const double *postTab, double lamC) {
+  const int lane = threadIdx.x & 31;
+  const bool inK = lane < k;
+  double xr[8], ss[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int v = v0 + c * nw;
+    xr[c] = (v < nv && inK) ? sP[(size_t)v * k + lane] : 0.0;
+    ss[c] = xr[c] * xr[c];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) ss[c] += __shfl_xor_sync(0xffffffffu, ss[c], o);
+  double mine = ss[0];
+#pragma unroll
+  for (int c = 1; c < 8; ++c)
+    if (lane == c) mine = ss[c];
+  const int vMine = v0 + lane * nw;
+  double f = 0.0, post = 1.0;
+  if (lane < 8 && vMine < nv) {
+    const double lam = lamTab ? lamTab[vMine / NO] : lamC;
+    if (postTab) post = postTab[vMine / NO];
+    const double nrm = sqrt(mine);
+    f = nrm > lam ? 1.0 - lam / nrm : -1.0;   // -1: the vector is zeroed (a factor is never negative)
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int v = v0 + c * nw;
+    const double fc = __shfl_sync(0xffffffffu, f, c), pc = __shfl_sync(0xffffffffu, post, c);
+    const double p = fc >= 0.0 ? xr[c] * fc : 0.0;
+    if (v < nv && inK) sP[(size_t)v * k + lane] = p * pc;
   }
 }
 
@@ -144,17 +190,7 @@ __global__ void __launch_bounds__(PSGD_THREADS, 1) psgd_lazy_kernel(const PsgdAr
     const int o = os < SB8 ? os / k : 0, sc = os - o * k;
     const int M = a.degree - o;
     if (os < SB8) {
-      anova_init(A);
-      for (int u = 0; u < z; u++) {
-        const double tv = sP[u * SB8 + o * k + sc] * sX[u];
-        if (M == 2) {
-          A[1] += tv;
-          A[2] += tv * tv;
-        } else {
-          anova_step(A, M, tv);
-        }
-      }
-      part += M == 2 ? (A[1] * A[1] - A[2]) / 2.0 : anova_at(A, M);
+      part += anova_forward_smem(A, M, sP + o * k + sc, SB8, sX, z);
     }
     double yhat = block_sum(part, red);
     if (tid == 0) {
@@ -305,6 +341,7 @@ __global__ void __launch_bounds__(PSGD_PIPE_THREADS, 1) psgd_lazy_pipe_kernel(co
   const bool isL1 = a.cfg.reg == NIMFM_REG_L1;
   const double alpha0 = a.cfg.alpha0, alpha = a.cfg.alpha, beta = a.cfg.beta, gamma = a.cfg.gamma;
   double lossAcc = 0.0;
+  long long prof[7] = {0, 0, 0, 0, 0, 0, 0};
   ElemWalk walk0;
   walk0.start(tid, nth, SB8);
   signed char *sOrd = reinterpret_cast<signed char *>(sJb + 2 * zmax);   // [SB8] ANOVA order of (order, component) slot
@@ -372,6 +409,7 @@ __global__ void __launch_bounds__(PSGD_PIPE_THREADS, 1) psgd_lazy_pipe_kernel(co
         pfX1 = u1 < m1.z ? a.data[m1.rb + u1] : 1.0;
       }
     }
+    const long long c0 = clock64();
     // ---- the row's P slice (raw) and the lazy factors of every row feature incl. dummies (psgd.nim:121-127)
     double pv[PSGD_PIPE_R];
     {
@@ -398,6 +436,7 @@ __global__ void __launch_bounds__(PSGD_PIPE_THREADS, 1) psgd_lazy_pipe_kernel(co
     if (tid == nth - 65) etaNext = psgd_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, beta, it + 1);
     if (tid == nth - 97) etaNext = psgd_eta(a.cfg.scheduling, a.cfg.eta0, a.cfg.power, alpha0, it + 1);
     __syncthreads();
+    const long long c1 = clock64();
     const double *shEta = sEta + (q & 1) * 4;
     const double etaW = shEta[0], etaP = shEta[1];
     const double etaS = etaP / (1.0 + etaP * beta);                     // psgd.nim:134
@@ -418,12 +457,14 @@ __global__ void __launch_bounds__(PSGD_PIPE_THREADS, 1) psgd_lazy_pipe_kernel(co
     }
     __syncthreads();
     if (!isL1) {                                                       // l21.nim:60-65: prox, then scale
-      for (int v = wid; v < z * NO; v += nw) {
-        const int u = v / NO;
-        psgd_l21_prox_warp(sP + (size_t)v * k, k, sTh[u], sSc[u]);
+      if (k <= 32) {
+        for (int v = wid; v < z * NO; v += 8 * nw) psgd_l21_prox_warp_x8(sP, v, nw, z * NO, k, NO, sTh, sSc, 0.0);
+      } else {
+        for (int v = wid; v < z * NO; v += nw) psgd_l21_prox_warp(sP + (size_t)v * k, k, sTh[v / NO], sSc[v / NO]);
       }
       __syncthreads();
     }
+    const long long c2 = clock64();
     // ---- predictWithGrad forward (thread <-> (order, component), nonzeros in row order)
     double part = 0.0;
     for (int u = tid; u < zReal; u += nth) part += sW[u] * X[u];
@@ -431,23 +472,14 @@ __global__ void __launch_bounds__(PSGD_PIPE_THREADS, 1) psgd_lazy_pipe_kernel(co
       const int o = tid / k, sc = tid - o * k;
       const int M = a.degree - o;
       AnovaState A;
-      anova_init(A);
-#pragma unroll 4
-      for (int u = 0; u < z; u++) {
-        const double tv = sP[u * SB8 + o * k + sc] * X[u];
-        if (M == 2) {
-          A[1] += tv;
-          A[2] += tv * tv;
-        } else {
-          anova_step(A, M, tv);
-        }
-      }
-      part += M == 2 ? (A[1] * A[1] - A[2]) / 2.0 : anova_at(A, M);
+      part += anova_forward_smem(A, M, sP + o * k + sc, SB8, X, z);
 #pragma unroll
       for (int tt = 1; tt < NIMFM_MAX_DEGREE; ++tt)
         if (tt < M) sA[tid * AST + tt] = A[tt];
     }
+    const long long c2a = clock64();
     const double yh = block_sum(part, red);
+    const long long c2b = clock64();
     if (tid == 0) {
       const double yhat = yh + a.b[0];
       lossAcc += dev_loss(a.cfg.loss, a.cfg.huberThreshold, m.y, yhat);
@@ -455,6 +487,7 @@ __global__ void __launch_bounds__(PSGD_PIPE_THREADS, 1) psgd_lazy_pipe_kernel(co
     }
     __syncthreads();
     const double dL = sh[4];
+    const long long c3 = clock64();
     // ---- reg.step (l1.nim:127-136 / l21.nim:102-112), element <-> thread
     {
       ElemWalk wk = walk0;
@@ -478,7 +511,12 @@ __global__ void __launch_bounds__(PSGD_PIPE_THREADS, 1) psgd_lazy_pipe_kernel(co
     }
     if (!isL1) {
       __syncthreads();
-      for (int v = wid; v < z * NO; v += nw) psgd_l21_prox_warp(sP + (size_t)v * k, k, etaS * gamma, 1.0);
+      if (k <= 32) {
+        for (int v = wid; v < z * NO; v += 8 * nw)
+          psgd_l21_prox_warp_x8(sP, v, nw, z * NO, k, NO, nullptr, nullptr, etaS * gamma);
+      } else {
+        for (int v = wid; v < z * NO; v += nw) psgd_l21_prox_warp(sP + (size_t)v * k, k, etaS * gamma, 1.0);
+      }
       __syncthreads();
       ElemWalk wk = walk0;
       for (int e = tid; e < z * SB8; e += nth) {
@@ -486,6 +524,7 @@ __global__ void __launch_bounds__(PSGD_PIPE_THREADS, 1) psgd_lazy_pipe_kernel(co
         wk.next();
       }
     }
+    const long long c4 = clock64();
     // ---- reg.updateCacheSGD (l1.nim:106-113 / l21.nim:84-90), w, intercept, caches
     double nSc, nTh;
     if (isL1) {
@@ -579,7 +618,16 @@ __global__ void __launch_bounds__(PSGD_PIPE_THREADS, 1) psgd_lazy_pipe_kernel(co
       }
     }
     __syncthreads();
+    if (a.profile && tid == 0) {
+      const long long c5 = clock64();
+      prof[0] += c1 - c0; prof[1] += c2 - c1; prof[2] += c3 - c2; prof[3] += c4 - c3; prof[4] += c5 - c4;
+      prof[5] += c2a - c2; prof[6] += c2b - c2a;
+    }
   }
+  if (a.profile && tid == 0 && a.nRows > 0)
+    printf("psgd pipe cycles/sample: loads %lld  lazy %lld  forward %lld (dp %lld, sum %lld)  step %lld  caches+park %lld\n",
+           prof[0] / a.nRows, prof[1] / a.nRows, prof[2] / a.nRows, prof[5] / a.nRows, prof[6] / a.nRows,
+           prof[3] / a.nRows, prof[4] / a.nRows);
   lossAcc = block_sum(lossAcc, red);
   if (tid == 0) {
     a.scal[0] = sh[1];
@@ -732,6 +780,7 @@ int32_t nimfm_fm_psgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset *X
     const char *env = getenv("NIMFM_PSGD_KERNEL");   // "staged": the unpipelined kernel
     if (zmax <= 64 && (size_t)zmax * SB8 <= (size_t)PSGD_PIPE_R * PSGD_PIPE_THREADS &&
         smemPipe + 4096 <= (size_t)ctx->smemOptin && !(env && env[0] == 's')) {
+      a.profile = getenv("NIMFM_PSGD_PROFILE") != nullptr;
       CK(cudaFuncSetAttribute(psgd_lazy_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemPipe));
       psgd_lazy_pipe_kernel<<<1, PSGD_PIPE_THREADS, smemPipe, ctx->stream>>>(a);
     } else {

@@ -304,17 +304,7 @@ __global__ void __launch_bounds__(SGD_THREADS, 1) sgd_fm_staged_kernel(const Sgd
     const int o = os < SB8 ? os / k : 0, sc = os - o * k;
     const int M = a.degree - o;
     if (os < SB8) {
-      anova_init(A);
-      for (int u = 0; u < z; u++) {
-        const double tv = sP[u * SB8 + o * k + sc] * sX[u];
-        if (M == 2) {
-          A[1] += tv;
-          A[2] += tv * tv;
-        } else {
-          anova_step(A, M, tv);
-        }
-      }
-      part += M == 2 ? (A[1] * A[1] - A[2]) / 2.0 : anova_at(A, M);
+      part += anova_forward_smem(A, M, sP + o * k + sc, SB8, sX, z);
     }
     double yhat = block_sum(part, red);
     if (tid == 0) {
@@ -548,18 +538,7 @@ __global__ void __launch_bounds__(SGDP_THREADS, 1) sgd_fm_pipe_kernel(const SgdA
       const int o = tid / k, sc = tid - o * k;
       const int M = a.degree - o;
       AnovaState A;
-      anova_init(A);
-#pragma unroll 4
-      for (int u = 0; u < z; u++) {
-        const double tv = sP[u * SB8 + o * k + sc] * X[u];
-        if (M == 2) {
-          A[1] += tv;
-          A[2] += tv * tv;
-        } else {
-          anova_step(A, M, tv);
-        }
-      }
-      part += M == 2 ? (A[1] * A[1] - A[2]) / 2.0 : anova_at(A, M);
+      part += anova_forward_smem(A, M, sP + o * k + sc, SB8, X, z);
 #pragma unroll
       for (int t = 1; t < NIMFM_MAX_DEGREE; ++t)
         if (t < M) sA[tid * AST + t] = A[t];
