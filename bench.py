@@ -749,6 +749,50 @@ class Bench:
             line["cd"] = out
         self.barrier()
 
+    # ---- the per-sample solvers (SGD, AdaGrad miniBatchSize=1, PSGD): strictly sequential in the reference, one
+    # persistent thread block here ("replicas only" for multi-GPU) -- rank 0, with the oracle's loops timed beside it
+    def run_seq(self, line):
+        nf = self.nf
+        if self.rank == 0:
+            n = 50_000
+            data, idx, ptr, y = gen_criteo_rows(n, 2000)
+            ds = nf.newCSRDataset(data, idx, ptr, n, D_FEATURES)
+            P, w, b = model_params(7)
+            kw = dict(maxIter=2, loss=nf.Logistic(), verbose=0, tol=0.0, shuffle=False)
+            solvers = (("sgd", lambda: nf.newSGD(eta0=0.01, **kw)),
+                       ("adagrad_mb1", lambda: nf.newAdaGrad(eta0=0.1, miniBatchSize=1, **kw)),
+                       ("psgd_l1", lambda: nf.newPSGD(eta0=0.01, gamma=1e-5, reg=nf.newL1(), **kw)),
+                       ("psgd_l21", lambda: nf.newPSGD(eta0=0.01, gamma=1e-5, reg=nf.newL21(), **kw)))
+            out = {"what": f"samples/s of one epoch over {n} C4-shape rows (degree 3, k = 32), one GPU: the reference's "
+                           "per-sample loops (sgd.nim:255-338, adagrad.nim:164-181, psgd.nim:76-215), same iterates",
+                   "rows": n}
+            for tag, mk in solvers:
+                fm = nf.newFactorizationMachine(nf.classification, degree=DEGREE, nComponents=K, warmStart=True)
+                fm.P, fm.w, fm.intercept, fm.isInitialized = P.copy(), w.copy(), b, True
+                opt = mk()
+                opt.fit(ds, y, fm)
+                ep = float(np.min(opt.epoch_seconds))
+                out[tag] = {"samples_per_s": n / ep, "s_per_epoch": ep}
+            ds.free()
+            if not self.args.no_cpu_baseline:
+                from oracle import oracle as orc
+                from oracle.oracle import CSR
+                orc.build()
+                m = 20_000
+                csr = CSR(data[:ptr[m]], idx[:ptr[m]], ptr[:m + 1], m, D_FEATURES)
+                cpu = {"rows": m, "kind": "port, one thread (the loops are sequential in the reference too)"}
+                for tag, fn in (("sgd", lambda: orc.sgd_fit(csr, y[:m], P, w, b, DEGREE, "logistic", max_iter=1, eta0=0.01)),
+                                ("adagrad_mb1", lambda: orc.adagrad_fit(csr, y[:m], P, w, b, DEGREE, "logistic", max_iter=1,
+                                                                        eta0=0.1, mini_batch_size=1)),
+                                ("psgd_l1", lambda: orc.psgd_fit(csr, y[:m], P, w, b, DEGREE, "logistic", max_iter=1,
+                                                                 eta0=0.01, gamma=1e-5, reg="l1"))):
+                    t0 = time.perf_counter()
+                    fn()
+                    cpu[tag] = m / (time.perf_counter() - t0)
+                out["cpu"] = cpu
+            line["sequential_solvers"] = out
+        self.barrier()
+
     # ---- the headline kernel without cache help
     def run_uniform(self, line):
         args, lib, ctx, _lib, nf = self.args, self.lib, self.ctx, self._lib, self.nf
@@ -797,7 +841,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bounded CPU-baseline sample")
     ap.add_argument("--ref-rows", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--skip", default="", help="comma list of sections to skip: parity,det,e2e,c4_adagrad,c3,c5,cd,uniform")
+    ap.add_argument("--skip", default="", help="comma list of sections to skip: parity,det,e2e,c4_adagrad,c3,c5,cd,seq,uniform")
     ap.add_argument("--dist", default="criteo", choices=["criteo", "uniform", "zipfall"],
                     help="index distribution; anything but 'criteo' is an experiment, not the reported workload")
     args = ap.parse_args()
@@ -830,6 +874,8 @@ def main():
         B.run_c5(line)
     if B.on("cd"):
         B.run_cd(line)
+    if B.on("seq"):
+        B.run_seq(line)
     if world == 1 and B.on("uniform"):
         B.run_uniform(line)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
