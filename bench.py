@@ -545,10 +545,11 @@ class Bench:
                                                        1.0, ne * world, 0, 1, int(world > 1), C.byref(ls)))
                 return ls.value
             one()
+            one()          # (a fresh pageable result array is still being faulted in during the first call)
             self.barrier()
             t0 = time.perf_counter()
             for _ in range(steps):
-                one()
+                one()      # blocking: returns after the result has been read back
             torch.cuda.synchronize()
             dt = self.maxr(time.perf_counter() - t0)
             a, b_, t_ = C.c_int64(), C.c_int64(), C.c_int32()
@@ -837,7 +838,7 @@ def main():
                     help="rows per end-to-end step (host buffers); default: the whole 10 M-row batch of the "
                          "device-resident step on one GPU, 2 M rows per rank under torchrun (pinned host memory "
                          "of 8 ranks on one box)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bounded CPU-baseline sample")
     ap.add_argument("--ref-rows", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
