@@ -259,6 +259,22 @@ static FfmKernel ffm_pairs_block_pick(int k, int mode) {
 }
 
 template <int KT>
+static FfmKernel ffm_pairs_bulk_mode(int mode) {
+  return mode == FFM_GRAD      ? ffm_pairs_block_kernel<FFM_PAIRS_GRAD, KT, FfmArgs, true>
+         : mode == FFM_ADAGRAD ? ffm_pairs_block_kernel<FFM_PAIRS_ADAGRAD, KT, FfmArgs, true>
+                               : nullptr;
+}
+static FfmKernel ffm_pairs_bulk_pick(int k, int mode) {
+  switch (k) {
+    case 4: return ffm_pairs_bulk_mode<4>(mode);
+    case 8: return ffm_pairs_bulk_mode<8>(mode);
+    case 16: return ffm_pairs_bulk_mode<16>(mode);
+    case 32: return ffm_pairs_bulk_mode<32>(mode);
+    default: return nullptr;
+  }
+}
+
+template <int KT>
 static FfmKernel ffm_tma_mode(int mode) {
   return mode == FFM_PREDICT ? ffm_rows_tma_kernel<FFM_PAIRS_PREDICT, KT, FfmArgs>
          : mode == FFM_GRAD  ? ffm_rows_tma_kernel<FFM_PAIRS_GRAD, KT, FfmArgs>
@@ -339,6 +355,37 @@ static int ffm_plan_mode(nimfm_ctx *ctx, const nimfm_ffm *m, const nimfm_dataset
         pl->smem = smem;
         pl->kern = tk;
         pl->block = FFM_TMA_THREADS;
+        pl->partialRows = grid;
+        return NIMFM_OK;
+      }
+    }
+  }
+  // Gradient blocks assembled in shared memory and added by TMA bulk reductions (ffm_pairs.cuh); needs a dataset
+  // without repeated fields in a row (every segment of a block is written by exactly one partner).  Default for
+  // the AdaGrad mode (two reductions per nonzero instead of 2 x 370 warp REDs per row: 13.3 -> 14.8 M samples/s on
+  // C5); predict+grad runs at the L2's FP64-add rate either way (22.3 M rows/s RED, 21.2 M bulk) and keeps the
+  // REDs.  NIMFM_FFM_BULK=0/1 forces either.
+  const char *benv = getenv("NIMFM_FFM_BULK");
+  const bool wantBulk = benv ? atoi(benv) == 1 : mode == FFM_ADAGRAD;
+  if (pk && table && !wantPairWarp && !wantTma && mode != FFM_PREDICT && wantBulk && ((m->nFields * m->k) & 1) == 0) {
+    bool dups = false;
+    int rc = ffm_has_field_dups(ctx, X, &dups);
+    if (rc) return rc;
+    FfmKernel bk = dups ? nullptr : ffm_pairs_bulk_pick(m->k, mode);
+    const int block = 256;
+    const size_t smem = ffm_bulk_smem(CH, (int)(m->nFields * m->k), mode == FFM_ADAGRAD ? 2 : 1, block / 32);
+    if (bk && smem <= (size_t)ctx->smemOptin) {
+      CK(cudaFuncSetAttribute(bk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int occ = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bk, block, smem));
+      if (occ >= 1) {
+        int64_t grid = std::min<int64_t>(nRows, (int64_t)occ * ctx->numSMs);
+        if (grid < 1) grid = 1;
+        pl->CH = CH;
+        pl->grid = (int)grid;
+        pl->smem = smem;
+        pl->kern = bk;
+        pl->block = block;
         pl->partialRows = grid;
         return NIMFM_OK;
       }

@@ -35,6 +35,50 @@ __global__ void __launch_bounds__(256) k(double *buf, uint32_t nSeg, int iters, 
   if (OP == 2 || OP == 4) if (acc == 123.456) sink[0] = acc;
 }
 
+// TMA bulk reduction: the warp writes SEG bytes into one of NBUF shared-memory buffers, one lane issues
+// cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 of the whole segment
+template <int SEG, int NBUF>
+__global__ void __launch_bounds__(256) kbulk(double *buf, uint32_t nSeg, int iters) {
+  __shared__ __align__(128) double sb[8][NBUF][SEG / 8];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  for (int it = 0; it < iters * 8; ++it) {
+    const int b = it % NBUF;
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NBUF - 1) : "memory");
+    __syncwarp();
+    for (int e = lane; e < SEG / 8; e += 32) sb[wib][b][e] = 1.0;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t h = mix((warp * 977u + (it >> 3)) * 64u + (it & 7) * 4u);
+      const uint32_t s = (uint32_t)(((uint64_t)h * nSeg) >> 32);
+      double *dst = buf + (size_t)s * (SEG / 8);
+      const uint32_t src = (uint32_t)__cvta_generic_to_shared(&sb[wib][b][0]);
+      asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dst), "r"(src), "n"(SEG) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+template <int SEG, int NBUF>
+static void runbulk(double *buf, size_t bytes, int clkMHz) {
+  const int blocks = 148 * 8, threads = 256, iters = 256;
+  const uint32_t nSeg = (uint32_t)(bytes / SEG);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  kbulk<SEG, NBUF><<<blocks, threads>>>(buf, nSeg, 16);
+  cudaDeviceSynchronize();
+  cudaEventRecord(e0);
+  kbulk<SEG, NBUF><<<blocks, threads>>>(buf, nSeg, iters);
+  cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  const double bytesMoved = (double)blocks * (threads / 32) * iters * 8 * SEG;
+  const double GBs = bytesMoved / (ms * 1e-3) / 1e9;
+  printf("%-28s seg %3d B  buf %5zu MB  %8.3f ms  %8.1f GB/s  %7.1f B/clk (at %d MHz)  [%d buffers/warp] %s\n",
+         "TMA bulk reduce .add.f64", SEG, bytes >> 20, ms, GBs, GBs * 1e9 / (clkMHz * 1e6), clkMHz, NBUF,
+         cudaGetErrorString(cudaGetLastError()));
+}
+
 template <int OP, int SEG>
 static void run(const char *name, double *buf, size_t bytes, double *sink, int clkMHz) {
   const int blocks = 148 * 8, threads = 256, iters = 256;
@@ -65,6 +109,10 @@ int main() {
     run<1, 64>("store", buf, bytes, sink, clk);
     run<2, 256>("load (nc)", buf, bytes, sink, clk);
     run<2, 64>("load (nc)", buf, bytes, sink, clk);
+    runbulk<256, 4>(buf, bytes, clk);
+    runbulk<512, 4>(buf, bytes, clk);
+    runbulk<512, 2>(buf, bytes, clk);
+    runbulk<2048, 2>(buf, bytes, clk);
   }
   return 0;
 }
