@@ -105,75 +105,70 @@ static __global__ void mbpsgd_step_flat_kernel(double *par, const double *g, int
 // The lazy epoch applies that shrink when the feature is next touched: with cum[t] = prod_{s<t} r_s the
 // pending factor of feature j is cum[t] * inv[j] (inv[j] = 1 / cum at j's last update); the row kernel
 // folds it into x (fm_rows_stream.cuh), so the gradient it scatters is the true one times the same
-// factor.  Two flat kernels then update the touched features only: the P rows (one thread per element,
-// flag-gated, no synchronisation) and the per-feature state (w, inv, flag; block 0 also folds the row
-// kernel's partials into the intercept step and the epoch's loss sum, i.e. reduce_partials + add_tail +
-// the tid == 0 branch of mbpsgd_step_kernel).  SB8 = 1 << shift.
-static __global__ void __launch_bounds__(256) mbpsgd_lazy_P_kernel(double *__restrict__ P, double *__restrict__ gP,
-                                                                   int shift, int64_t nP,
-                                                                   const uint8_t *__restrict__ flag,
-                                                                   const double2 *__restrict__ inv, double cumPt,
-                                                                   double negEtaP, double rP, double aP = 1.0,
-                                                                   double *violPart = nullptr) {
-  // p_new = (aP * p_eff + negEtaP * g) * rP: MBPSGD (aP = 1, rP = 1/(1+eta beta)); minibatch SGD (sgd_mb.cu:
-  // aP = (1-eta beta)^B, rP = 1) also wants viol = sum |p_new - p_eff| (violPart[block*4])
+// factor.  One flat kernel then updates the touched features only: their P rows and the per-feature state (w, inv,
+// flag); its block 0 also folds the row kernel's partials into the intercept step and the epoch's loss sum, i.e.
+// reduce_partials + add_tail + the tid == 0 branch of mbpsgd_step_kernel.  SB8 = 1 << shift.
+// One pass, a warp per 32 consecutive features: ONE coalesced 32-byte read of their flags, a ballot, and only the
+// touched features are visited -- their P rows by 2^shift lanes each (32 >> shift features side by side when a row
+// is shorter than a warp), then w / inv / flag by the lanes that own them.  (Round 1 had an element-wise P kernel
+// that looked a flag up per ELEMENT plus a second walk over the flags for the feature state: same results; the
+// fused form is +16 % on 4 096-row minibatch SGD and even on C3's 25 641-row minibatches, where the touched rows'
+// own traffic -- ~100 MB of scattered 128-byte rows -- is what the step costs.)
+static __global__ void __launch_bounds__(256) mbpsgd_lazy_step_kernel(
+    double *__restrict__ P, double *__restrict__ gP, int shift, int64_t dd, int64_t d, double *w, double *gw,
+    uint8_t *flag, double2 *inv, double cumPt, double cumWt, double invPnext, double invWnext, double negEtaP, double rP,
+    double aP, double negEtaW, double rW, double aW, int fitLinear, double *b, const double *partials,
+    int64_t partialRows, double negEtaB, double rB, int fitIntercept, double *scal, double *violPart) {
   __shared__ double red[8];
   double viol = 0.0;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  for (int64_t e0 = tid; e0 < nP; e0 += 4 * stride) {
-    bool on[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int64_t e = e0 + i * stride;
-      on[i] = e < nP && flag[e >> shift] != 0;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      if (!on[i]) continue;
-      const int64_t e = e0 + i * stride;
-      const double fac = cumPt * inv[e >> shift].x;
-      const double pe = P[e] * fac;
-      const double p = (aP * pe + negEtaP * (gP[e] / fac)) * rP;
-      viol += fabs(p - pe);
-      P[e] = p;
-      gP[e] = 0.0;
-    }
-  }
-  if (violPart) {   // uniform across the grid
-    viol = block_sum(viol, red);
-    if (threadIdx.x == 0) {
-      violPart[blockIdx.x * 4 + 0] = viol;
-      violPart[blockIdx.x * 4 + 1] = 0.0;
-      violPart[blockIdx.x * 4 + 2] = 0.0;
-      violPart[blockIdx.x * 4 + 3] = 0.0;
-    }
-  }
-}
-
-static __global__ void __launch_bounds__(256) mbpsgd_lazy_feat_kernel(
-    int64_t dd, int64_t d, double *w, double *gw, uint8_t *flag, double2 *inv, double cumPt, double cumWt,
-    double invPnext, double invWnext, double negEtaW, double rW, int fitLinear, double *b, const double *partials,
-    int64_t partialRows, double negEtaB, double rB, int fitIntercept, double *scal, double aW = 1.0,
-    double *violPart = nullptr) {
-  // violPart != nullptr: the minibatch-SGD rule (w_new = aW w_eff - eta gw, b_new = rB b - eta gb, viol)
-  __shared__ double red[8];
-  double viol = 0.0;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < dd; j += stride) {
-    if (!flag[j]) continue;
-    const double2 iv = inv[j];
-    if (j < d) {
-      if (fitLinear) {
-        const double we = w[j] * (cumWt * iv.y);
-        const double v = (aW * we + negEtaW * (gw[j] / (cumPt * iv.x))) * rW;
-        viol += fabs(v - we);
-        w[j] = v;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nWarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int SB8 = 1 << shift;
+  const int fpw = shift >= 5 ? 1 : (32 >> shift);          // features side by side in one pass over P
+  const int sub = shift >= 5 ? 0 : (lane >> shift);
+  const int el = shift >= 5 ? lane : (lane & (SB8 - 1));
+  for (int64_t j0 = warp * 32; j0 < dd; j0 += nWarps * 32) {
+    const int64_t j = j0 + lane;
+    const bool on = j < dd && flag[j] != 0;
+    const unsigned mask = __ballot_sync(0xffffffffu, on);
+    if (!mask) continue;
+    double2 iv = make_double2(1.0, 1.0);
+    if (on) iv = inv[j];
+    // ---- P rows of the touched features: p <- (aP p_eff - eta g_true) rP, g <- 0
+    unsigned m = mask;
+    while (m) {
+      unsigned mm = m;                                      // this sub-group takes the sub-th set bit of m
+      for (int i = 0; i < sub; i++) mm &= mm - 1;
+      const int f = mm ? __ffs(mm) - 1 : -1;
+      const double ivx = __shfl_sync(0xffffffffu, iv.x, f < 0 ? 0 : f);
+      if (f >= 0) {
+        const double fac = cumPt * ivx;
+        const int64_t base = (j0 + f) << shift;
+        for (int e = el; e < SB8; e += 32) {
+          const double pe = P[base + e] * fac;
+          const double p = (aP * pe + negEtaP * (gP[base + e] / fac)) * rP;
+          viol += fabs(p - pe);
+          P[base + e] = p;
+          gP[base + e] = 0.0;
+        }
       }
-      gw[j] = 0.0;
+      for (int i = 0; i < fpw && m; i++) m &= m - 1;
     }
-    inv[j] = make_double2(invPnext, invWnext);
-    flag[j] = 0;
+    // ---- per-feature state: w likewise, inv[j] <- 1 / cum[t+1], flag reset
+    if (on) {
+      if (j < d) {
+        if (fitLinear) {
+          const double we = w[j] * (cumWt * iv.y);
+          const double v = (aW * we + negEtaW * (gw[j] / (cumPt * iv.x))) * rW;
+          viol += fabs(v - we);
+          w[j] = v;
+        }
+        gw[j] = 0.0;
+      }
+      inv[j] = make_double2(invPnext, invWnext);
+      flag[j] = 0;
+    }
   }
   if (blockIdx.x == 0) {
     double acc0 = 0.0, acc1 = 0.0;

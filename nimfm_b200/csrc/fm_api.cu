@@ -709,13 +709,10 @@ int32_t nimfm_fm_mbpsgd_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset 
         const double etaB = get_eta(cfg->scheduling, cfg->eta0, cfg->power, cfg->alpha0, *it);
         const double rP = 1.0 / (1.0 + etaP * cfg->beta), rW = 1.0 / (1.0 + etaW * cfg->alpha),
                      rB = 1.0 / (1.0 + etaB * cfg->alpha0);
-        mbpsgd_lazy_P_kernel<<<grid, 256, 0, ctx->stream>>>(fm->P, fm->grad, shift, nP, fm->lazyFlag, fm->lazyInv, lv.cumPt,
-                                                            -etaP, rP);
-        LAUNCHED(ctx);
-        mbpsgd_lazy_feat_kernel<<<(int)std::min<int64_t>((dd + 255) / 256, grid), 256, 0, ctx->stream>>>(
-            dd, d, fm->w, fm->grad + nP, fm->lazyFlag, fm->lazyInv, lv.cumPt, lv.cumWt, 1.0 / cum[inner + 1],
-            1.0 / cum[T + 1 + inner + 1], -etaW, rW, fm->fitLinear, fm->b, ctx->partials, lv.partialRows, -etaB, rB,
-            fm->fitIntercept, ctx->scalars);
+        mbpsgd_lazy_step_kernel<<<grid, 256, 0, ctx->stream>>>(
+            fm->P, fm->grad, shift, dd, d, fm->w, fm->grad + nP, fm->lazyFlag, fm->lazyInv, lv.cumPt, lv.cumWt,
+            1.0 / cum[inner + 1], 1.0 / cum[T + 1 + inner + 1], -etaP, rP, 1.0, -etaW, rW, 1.0, fm->fitLinear, fm->b,
+            ctx->partials, lv.partialRows, -etaB, rB, fm->fitIntercept, ctx->scalars, nullptr);
         LAUNCHED(ctx);
         *it += 1;
         cur = (cur + localBatch) % X->n;
@@ -904,9 +901,8 @@ int nimfm_fm_sgd_mb_lazy_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset
     LAUNCHED(ctx);
   }
   const int grid = ctx->numSMs * 8;
-  const int gridF = (int)std::min<int64_t>((dd + 255) / 256, grid);
   int rc;
-  if ((rc = nimfm_ensure_partials(ctx, (size_t)(plq.nWarps + grid + gridF) * 4))) return rc;
+  if ((rc = nimfm_ensure_partials(ctx, (size_t)(plq.nWarps + grid) * 4))) return rc;
   CK(cudaMemsetAsync(fm->grad, 0, (size_t)nG * 8, ctx->stream));
   CK(cudaMemsetAsync(ctx->scalars, 0, 8, ctx->stream));
   CK(cudaMemsetAsync(ctx->scalars + 20, 0, 4 * 8, ctx->stream));
@@ -920,15 +916,12 @@ int nimfm_fm_sgd_mb_lazy_epoch(nimfm_ctx *ctx, nimfm_fm *fm, const nimfm_dataset
                                nullptr, &lv)))
       return rc;
     double *violPart = ctx->partials + (size_t)lv.partialRows * 4;
-    mbpsgd_lazy_P_kernel<<<grid, 256, 0, ctx->stream>>>(fm->P, fm->grad, shift, nP, fm->lazyFlag, fm->lazyInv, lv.cumPt,
-                                                        -etaP[t], 1.0, sP[t], violPart);
+    mbpsgd_lazy_step_kernel<<<grid, 256, 0, ctx->stream>>>(
+        fm->P, fm->grad, shift, dd, d, fm->w, fm->grad + nP, fm->lazyFlag, fm->lazyInv, lv.cumPt, lv.cumWt,
+        1.0 / cumP[t + 1], 1.0 / cumW[t + 1], -etaP[t], 1.0, sP[t], -etaW[t], 1.0, sW[t], fm->fitLinear, fm->b,
+        ctx->partials, lv.partialRows, -etaB[t], sB[t], fm->fitIntercept, ctx->scalars, violPart);
     LAUNCHED(ctx);
-    mbpsgd_lazy_feat_kernel<<<gridF, 256, 0, ctx->stream>>>(
-        dd, d, fm->w, fm->grad + nP, fm->lazyFlag, fm->lazyInv, lv.cumPt, lv.cumWt, 1.0 / cumP[t + 1], 1.0 / cumW[t + 1],
-        -etaW[t], 1.0, fm->fitLinear, fm->b, ctx->partials, lv.partialRows, -etaB[t], sB[t], fm->fitIntercept,
-        ctx->scalars, sW[t], violPart + (size_t)grid * 4);
-    LAUNCHED(ctx);
-    reduce_partials_kernel<<<1, 256, 0, ctx->stream>>>(violPart, grid + gridF, ctx->scalars + 20, 1);
+    reduce_partials_kernel<<<1, 256, 0, ctx->stream>>>(violPart, grid, ctx->scalars + 20, 1);
     LAUNCHED(ctx);
     *it += Bm;
   }
