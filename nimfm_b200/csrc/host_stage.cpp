@@ -108,13 +108,62 @@ __attribute__((target("avx2,popcnt"))) int64_t pack_avx2(const double *src, int6
   return pack_scalar(src, n, out, mask, blk, outBase, i, cnt);
 }
 
+// AVX-512: the compare yields the mask byte directly and VCOMPRESSPD (register form) does the left-compaction
+__attribute__((target("avx512f,popcnt"))) int64_t pack_avx512(const double *src, int64_t n, double *out, uint64_t *mask,
+                                                              uint32_t *blk, int64_t outBase) {
+  const __m512d ones = _mm512_set1_pd(1.0);
+  int64_t cnt = 0, i = 0;
+  const int64_t n64 = n & ~(int64_t)63;
+  for (; i < n64; i += 64) {
+    if ((i & 255) == 0) blk[i >> 8] = (uint32_t)(outBase + cnt);
+    uint64_t word = 0;
+#pragma GCC unroll 8
+    for (int g = 0; g < 8; g++) {
+      const __m512d v = _mm512_loadu_pd(src + i + 8 * g);
+      const __mmask8 eq = _mm512_cmp_pd_mask(v, ones, _CMP_EQ_OQ);
+      word |= (uint64_t)eq << (8 * g);
+      const __mmask8 keep = (__mmask8)~eq;
+      _mm512_storeu_pd(out + cnt, _mm512_maskz_compress_pd(keep, v));   // the tail is overwritten by the next group
+      cnt += __builtin_popcount((unsigned)keep);
+    }
+    mask[i >> 6] = word;
+  }
+  return pack_scalar(src, n, out, mask, blk, outBase, i, cnt);
+}
+
+// AVX-512: 16 ids per iteration through VPMOVQD, same sign-bit range check as the AVX2 form
+__attribute__((target("avx512f,avx512dq"))) int narrow_avx512(const int64_t *src, int32_t *dst, int64_t n, int64_t d) {
+  const __m512i dm1 = _mm512_set1_epi64(d - 1);
+  __m512i acc = _mm512_setzero_si512();
+  int64_t i = 0;
+  for (; i + 16 <= n; i += 16) {
+    const __m512i a = _mm512_loadu_si512(src + i), b = _mm512_loadu_si512(src + i + 8);
+    acc = _mm512_or_si512(acc, _mm512_or_si512(_mm512_or_si512(a, _mm512_sub_epi64(dm1, a)),
+                                               _mm512_or_si512(b, _mm512_sub_epi64(dm1, b))));
+    const __m512i both = _mm512_inserti64x4(_mm512_castsi256_si512(_mm512_cvtepi64_epi32(a)), _mm512_cvtepi64_epi32(b), 1);
+    _mm512_stream_si512(reinterpret_cast<__m512i *>(dst + i), both);
+  }
+  int bad = _mm512_movepi64_mask(acc) != 0;
+  bad |= narrow_scalar(src + i, dst + i, n - i, d);
+  _mm_sfence();
+  return bad;
+}
+
+bool use_avx512() {
+  static const bool ok = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512dq") &&
+                         __builtin_cpu_supports("popcnt") && !(getenv("NIMFM_HOST_AVX512") && getenv("NIMFM_HOST_AVX512")[0] == '0');
+  return ok;
+}
+
 int64_t pack(const double *src, int64_t n, double *out, uint64_t *mask, uint32_t *blk, int64_t outBase) {
   static const bool haveAvx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("popcnt");
+  if (use_avx512()) return pack_avx512(src, n, out, mask, blk, outBase);
   return haveAvx2 ? pack_avx2(src, n, out, mask, blk, outBase) : pack_scalar(src, n, out, mask, blk, outBase, 0, 0);
 }
 
 int narrow(const int64_t *src, int32_t *dst, int64_t n, int64_t d) {
   static const bool haveAvx2 = __builtin_cpu_supports("avx2");
+  if (use_avx512() && (reinterpret_cast<uintptr_t>(dst) & 63) == 0) return narrow_avx512(src, dst, n, d);
   return haveAvx2 ? narrow_avx2(src, dst, n, d) : narrow_scalar(src, dst, n, d);
 }
 
