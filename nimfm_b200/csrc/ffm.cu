@@ -318,7 +318,7 @@ static int ffm_plan(nimfm_ctx *ctx, const nimfm_ffm *m, const nimfm_dataset *X, 
 // block-per-row kernel ffm_rows_kernel); FFM_ADAGRAD additionally needs a dataset without repeated
 // fields in a row.
 static int ffm_plan_mode(nimfm_ctx *ctx, const nimfm_ffm *m, const nimfm_dataset *X, int64_t nRows, int mode,
-                         FfmPlan *pl) {
+                         FfmPlan *pl, bool targetsAligned16 = true) {
   const char *env = getenv("NIMFM_FFM_KERNEL");
   const bool forceBlock = env && !strcmp(env, "block");
   const int CH = (int)std::max<int64_t>(X->maxSegNnz, 1);
@@ -367,7 +367,9 @@ static int ffm_plan_mode(nimfm_ctx *ctx, const nimfm_ffm *m, const nimfm_dataset
   // REDs.  NIMFM_FFM_BULK=0/1 forces either.
   const char *benv = getenv("NIMFM_FFM_BULK");
   const bool wantBulk = benv ? atoi(benv) == 1 : mode == FFM_ADAGRAD;
-  if (pk && table && !wantPairWarp && !wantTma && mode != FFM_PREDICT && wantBulk && ((m->nFields * m->k) & 1) == 0) {
+  // a bulk reduction wants 16-byte aligned global targets: an even block length and aligned buffer bases
+  if (pk && table && !wantPairWarp && !wantTma && mode != FFM_PREDICT && wantBulk && ((m->nFields * m->k) & 1) == 0 &&
+      targetsAligned16) {
     bool dups = false;
     int rc = ffm_has_field_dups(ctx, X, &dups);
     if (rc) return rc;
@@ -691,7 +693,7 @@ static int ffm_launch_grad(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_dataset *X,
       if (taken) return NIMFM_OK;
     }
   }
-  rc = ffm_plan_mode(ctx, m, X, nRows, FFM_GRAD, &pl);
+  rc = ffm_plan_mode(ctx, m, X, nRows, FFM_GRAD, &pl, (reinterpret_cast<uintptr_t>(m->grad) & 15) == 0);
   if (rc) return rc;
   if ((rc = nimfm_ensure_partials(ctx, (size_t)pl.partialRows * 4))) return rc;
   FfmArgs a;
@@ -751,7 +753,8 @@ int32_t nimfm_ffm_time_loss_grad(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_datas
   if (rc) return rc;
   REQUIRE(reps >= 1 && nRows >= 1 && msPerLaunch, "bad arguments");
   FfmPlan pl;
-  if ((rc = ffm_plan_mode(ctx, m, X, nRows, gradToo ? FFM_GRAD : FFM_PREDICT, &pl))) return rc;
+  if ((rc = ffm_plan_mode(ctx, m, X, nRows, gradToo ? FFM_GRAD : FFM_PREDICT, &pl, (reinterpret_cast<uintptr_t>(m->grad) & 15) == 0)))
+    return rc;
   FfmKernel kern = pl.kern;
   if ((rc = nimfm_ensure_partials(ctx, (size_t)pl.partialRows * 4))) return rc;
   double *dOut = nullptr;
@@ -861,14 +864,15 @@ int32_t nimfm_ffm_adagrad_epoch(nimfm_ctx *ctx, nimfm_ffm *m, const nimfm_datase
       reduce_partials_kernel<<<1, 256, 0, ctx->stream>>>(ctx->partials, rgrid, violPart, 0);
       LAUNCHED(ctx);
     }
+    // one rank: accumulate straight into g_sum / g_norm (see nimfm_fm_adagrad_epoch)
+    const bool direct = ctx->nranks == 1;
     FfmPlan pl;
-    if ((rc = ffm_plan_mode(ctx, m, X, cnt, FFM_ADAGRAD, &pl))) return rc;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(direct ? m->gsP : dGsP) | reinterpret_cast<uintptr_t>(direct ? m->gnP : dGnP)) & 15) == 0;
+    if ((rc = ffm_plan_mode(ctx, m, X, cnt, FFM_ADAGRAD, &pl, aligned))) return rc;
     if ((rc = nimfm_ensure_partials(ctx, (size_t)pl.partialRows * 4))) return rc;
     FfmArgs a;
     ffm_fill_args(a, m, X);
     a.rowBegin = start; a.nRows = cnt; a.rowIdx = rows;
-    // one rank: accumulate straight into g_sum / g_norm (see nimfm_fm_adagrad_epoch)
-    const bool direct = ctx->nranks == 1;
     a.gP = direct ? m->gsP : dGsP; a.gw = direct ? m->gsw : dGsw;
     a.dGnP = direct ? m->gnP : dGnP; a.dGnw = direct ? m->gnw : dGnw;
     a.partials = ctx->partials;

@@ -258,6 +258,46 @@ def test_ffm_adagrad_one_feature_per_field(oracle, monkeypatch, mb, variant):
     assert abs(m.intercept - ref["intercept"]) <= 1e-9
 
 
+def unique_fields_ragged_csr(n, n_fields, per_field, seed):
+    """rows holding a random SUBSET of the fields (each at most once; some rows empty, some with every field)"""
+    rng = np.random.default_rng(seed)
+    data, indices, fields, indptr = [], [], [], [0]
+    for i in range(n):
+        z = 0 if i % 7 == 0 else (n_fields if i % 5 == 0 else int(rng.integers(1, n_fields + 1)))
+        fs = np.sort(rng.choice(n_fields, size=z, replace=False))
+        indices.extend((fs * per_field + rng.integers(0, per_field, z)).tolist())
+        data.extend(np.where(rng.random(z) < 0.5, 1.0, rng.standard_normal(z)).tolist())
+        fields.extend(fs.tolist())
+        indptr.append(len(indices))
+    return CSR(data, indices, indptr, n, n_fields * per_field, fields=np.array(fields, np.int64), n_fields=n_fields)
+
+
+@pytest.mark.parametrize("k", [4, 8, 16, 32])
+@pytest.mark.parametrize("bulk", ["0", "1"])
+def test_ffm_bulk_reduction_route(oracle, monkeypatch, k, bulk):
+    """gradient blocks assembled in shared memory and added by TMA bulk reductions (NIMFM_FFM_BULK=1; the default of
+    the AdaGrad mode) against the RED route (=0) and the oracle: full rows, rows with absent fields (the zero-filled
+    block), empty rows; predict+grad and three AdaGrad epochs"""
+    monkeypatch.setenv("NIMFM_FFM_BULK", bulk)
+    nF = 13
+    for csr in (one_per_field_csr(150, nF, 20, 21), unique_fields_ragged_csr(150, nF, 20, 22)):
+        rng = np.random.default_rng(k)
+        P = rng.standard_normal((nF, csr.d, k)) * 0.15
+        w = rng.standard_normal(csr.d) * 0.1
+        y = np.sign(rng.standard_normal(csr.n))
+        m = make_ffm(P, w, 0.05, task=nf.classification)
+        ls, gP, gw, gb = ffm_dev_loss_grad(m, field_ds(csr), y, nf.Logistic())
+        ref = oracle.ffm_loss_grad(csr, y, P, w, 0.05, "logistic")
+        assert abs(ls - ref["loss"]) <= 1e-10 * max(1.0, abs(ref["loss"]))
+        assert max_rel(gP, ref["gP"]) <= 1e-9 and max_rel(gw, ref["gw"]) <= 1e-9
+        refa = oracle.ffm_adagrad_fit(csr, y, P, np.zeros(csr.d), 0.0, "logistic", max_iter=3, mini_batch_size=32)
+        ma = make_ffm(P, np.zeros(csr.d), 0.0, task=nf.classification)
+        opt = nf.newAdaGrad(maxIter=3, loss=nf.Logistic(), verbose=0, tol=0.0, shuffle=False, miniBatchSize=32)
+        opt.fit(field_ds(csr), y, ma)
+        np.testing.assert_allclose([h[1] for h in opt.history], refa["loss"], rtol=OBJ_TOL)
+        np.testing.assert_allclose(ma.P, refa["P"], rtol=1e-8, atol=1e-13)
+
+
 def test_ffm_adagrad_repeated_fields_falls_back(oracle):
     """rows with two nonzeros of one field: per-sample squares need the field-bucketed kernel (the pair
     kernel would square each pair's share separately); the dispatcher must notice"""
