@@ -891,8 +891,11 @@ def main():
         B.run_c5(line)
     if B.on("cd"):
         B.run_cd(line)
-    if B.on("seq"):
-        B.run_seq(line)
+    if world == 1 and B.on("seq"):
+        B.run_seq(line)          # sequential solvers do not shard ("replicas only"): measured at N = 1
+    elif B.on("seq"):
+        line["sequential_solvers"] = {"skipped": "per-sample SGD / AdaGrad / PSGD are sequential (replicas only): "
+                                                 "the host mirror refuses them while a communicator is up; see the N = 1 line"}
     if world == 1 and B.on("uniform"):
         B.run_uniform(line)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
