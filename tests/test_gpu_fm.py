@@ -173,6 +173,55 @@ def test_loss_grad_host_streaming(oracle, monkeypatch, host_threads, chunk):
         lib.nimfm_fm_free(ctx, h)
 
 
+@pytest.mark.parametrize("memory", ["pageable", "registered"])
+@pytest.mark.parametrize("chunk", [61, 1000])
+def test_loss_grad_host_packed_values(oracle, monkeypatch, memory, chunk):
+    """the lossless packed transport of the values (NIMFM_HOST_PACK=1: bit mask '== 1.0' + the other doubles + block
+    offsets, expanded on the device) through the whole host-fed call, on pageable arrays and on page-locked ones,
+    against the oracle, and bit-identical in the predictions to the resident kernel.  Values: exact ones,
+    1 +/- 1 ulp, -0.0, denormals."""
+    monkeypatch.setenv("NIMFM_HOST_THREADS", "3")
+    monkeypatch.setenv("NIMFM_HOST_STAGE_MIN_NNZ", "0")
+    monkeypatch.setenv("NIMFM_HOST_PACK", "1")
+    n, d, k, degree = 4000, 80, 8, 3
+    csr = ragged_csr(n, d, 23, 12)
+    rng = np.random.default_rng(9)
+    pick = rng.random(len(csr.data))
+    csr.data[pick < 0.6] = 1.0
+    csr.data[(pick >= 0.6) & (pick < 0.63)] = np.nextafter(1.0, 2.0)
+    csr.data[(pick >= 0.63) & (pick < 0.66)] = np.nextafter(1.0, 0.0)
+    csr.data[(pick >= 0.66) & (pick < 0.68)] = -0.0
+    csr.data[(pick >= 0.68) & (pick < 0.70)] = 5e-324
+    y = np.where(rng.random(n) < 0.5, -1.0, 1.0)
+    P, w, _ = make_fm_params(d, degree, k, "explicit", True, seed=6)
+    fm = make_fm(degree, k, "explicit", True, True, P, w, 0.2, task=nf.classification)
+    ref = oracle.fm_loss_grad(csr, y, P, w, 0.2, degree, "logistic", mini_batch_size=n)
+    lib, ctx = _lib.load(), _lib.ctx()
+    arrays = (csr.data, csr.indices, csr.indptr, y)
+    if memory == "registered":
+        for a in arrays:
+            _lib.check(lib.nimfm_host_register(ctx, _lib.ptr(a), a.nbytes))
+    h = fm._to_device(d)
+    try:
+        for _ in range(2):
+            ls = C.c_double()
+            _lib.check(lib.nimfm_fm_loss_grad_host(ctx, h, n, d, _lib.ptr(csr.data), _lib.ptr(csr.indices), _lib.ptr(csr.indptr),
+                                                   _lib.ptr(y), 2, 1.0, n, chunk, 1, 0, C.byref(ls)))
+            gP, gw, gb = np.zeros_like(P), np.zeros(d), C.c_double()
+            _lib.check(lib.nimfm_fm_get_grads(ctx, h, _lib.ptr(gP), _lib.ptr(gw), C.byref(gb)))
+            assert abs(ls.value - ref["loss"]) <= DEC_TOL * abs(ref["loss"])
+            assert max_rel(gP, ref["gP"]) <= 1e-9 and max_rel(gw, ref["gw"]) <= 1e-9
+        out = np.zeros(n)
+        _lib.check(lib.nimfm_fm_decision_function_host(ctx, h, n, d, _lib.ptr(csr.data), _lib.ptr(csr.indices),
+                                                       _lib.ptr(csr.indptr), chunk, _lib.ptr(out)))
+        assert np.array_equal(out, fm.decisionFunction(csr_ds(csr)))
+    finally:
+        lib.nimfm_fm_free(ctx, h)
+        if memory == "registered":
+            for a in arrays:
+                lib.nimfm_host_unregister(ctx, _lib.ptr(a))
+
+
 def test_decision_function_errors():
     X = make_dense(5, 6, 1)
     csr = CSR.from_dense(X)
