@@ -188,7 +188,11 @@ int HostStageTeam::pageable_threads(int nRanks) {
   if (const char *e = getenv("NIMFM_HOST_THREADS")) return std::max(0, atoi(e));
   const int hw = (int)std::thread::hardware_concurrency();
   const int t = hw / std::max(1, nRanks);
-  return t >= 8 ? std::min(t - 2, 24) : 0;
+  if (t >= 8) return std::min(t - 2, 24);
+  // thread-starved ranks (8 ranks on 16 cores): a team of the rank's own cores still beats the driver's pageable
+  // path (one thread, one bounce buffer, ~6 GB/s per rank); NIMFM_HOST_PAGEABLE_SMALL=0 restores that path
+  const char *e = getenv("NIMFM_HOST_PAGEABLE_SMALL");
+  return (e && e[0] == '0') ? 0 : std::max(1, t);
 }
 
 HostStageTeam::HostStageTeam(int nThreads, const int64_t *indices, const int64_t *indptr, int64_t d,
