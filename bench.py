@@ -157,12 +157,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.t0 = index, None, [], 0.0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except Exception:
@@ -170,11 +170,17 @@ class ClockSampler:
 
     def _pump(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
+
+    def mark(self):
+        """the timed region begins now: nvidia-smi was started before the warm-up (its start-up takes longer than a
+        short timed region), only samples that arrive from here on are reported"""
+        self.t0 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t1 = time.time() + 0.06        # one sampling period of pipe latency
         time.sleep(0.15)
         self.proc.terminate()
         try:
@@ -183,7 +189,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if ts < self.t0 or ts > t1:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -462,11 +470,12 @@ class Bench:
                                               int(world > 1), C.byref(ls)))
             return ls.value
 
+        sampler = ClockSampler(self.local_rank)
+        sampler.start()
         for _ in range(args.warmup):
             step()
-        sampler = ClockSampler(self.local_rank)
         self.barrier()
-        sampler.start()
+        sampler.mark()
         l0 = _lib.launch_count()
         _lib.check(lib.nimfm_timer_start(ctx))
         for _ in range(args.steps):
