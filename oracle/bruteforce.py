@@ -359,6 +359,74 @@ def prox_squaredl12_slow(p, lam):
     return p
 
 
+def mbpsgd_slow_fit(X, y, P, w, intercept, degree, fit_linear, fit_intercept, loss, max_iter, eta0, alpha0, alpha,
+                    beta, gamma=0.0, reg="identity", mini_batch_size=-1, max_iter_inner=-1, power=1.0):
+    """Naive dense definition of minibatch proximal SGD, the way the reference's *_slow.nim helpers define their
+    solvers (the reference has no MBPSGDSlow; minibatch_psgd.nim has no test): dense X, yhat and its gradient by
+    subset enumeration (fm_decision_function / fm_grad above), a minibatch = the next `mb` rows of the cyclic order
+    0, 1, ..., n-1 (shuffle = false),
+        g = (1/mb) sum_i dloss_i * grad yhat_i,   theta <- (theta - eta g) / (1 + eta * l2)      (params.nim:90-98)
+    with eta = eta0 / (1 + eta0 * l2 * it)^power per parameter group (sgd.nim:60-65, 'optimal'), then the
+    regulariser's proximal operator with lam = gamma * eta_P / (1 + eta_P * beta) on every order
+    (minibatch_psgd.nim:96-122), it += 1 per minibatch.  The intercept takes its gradient step only when fitLinear
+    holds as well (params.nim:47: `self.fitIntercept and grad.fitLinear`) -- the reference's quirk, part of the
+    definition here.  Default sizes as minibatch_psgd.nim:157-164.  Returns (P, w, intercept, epoch losses).
+    Independent of oracle/ref_cpu.c (CSR, per-sample scatter, the solver layout) and of the device code."""
+    n, d = X.shape
+    P = P.copy()
+    w = w.copy()
+    nnz = int(np.count_nonzero(X))
+    mb = mini_batch_size if mini_batch_size > 0 else max((d * n) // nnz, 1)
+    inner = max_iter_inner if max_iter_inner > 0 else max((n - 1) // mb + 1, 1)
+    it, ii, losses = 1, 0, []
+
+    def eta(l2):
+        return eta0 / (1.0 + eta0 * l2 * it) ** power
+
+    def soft(v, lam):
+        return np.sign(v) * np.maximum(np.abs(v) - lam, 0.0)
+
+    for _ in range(max_iter):
+        run = 0.0
+        for _ in range(inner):
+            gP, gw, gb = np.zeros_like(P), np.zeros(d), 0.0
+            for _ in range(mb):
+                i = ii
+                y_pred = fm_decision_function(X[i:i + 1], P, w, intercept, degree)[0]
+                run += loss_val(loss, y[i], y_pred)
+                dL = dloss_val(loss, y[i], y_pred) / mb
+                fm_grad(X, i, P, degree, dL, gP)
+                gw += dL * X[i]
+                gb += dL
+                ii = (ii + 1) % n
+            eP, eW, eB = eta(beta), eta(alpha), eta(alpha0)
+            P = (P - eP * gP) / (1.0 + eP * beta)
+            if fit_linear:
+                w = (w - eW * gw) / (1.0 + eW * alpha)
+            if fit_intercept:
+                if fit_linear:
+                    intercept -= eB * gb
+                intercept /= 1.0 + eB * alpha0
+            lam = gamma * eP / (1.0 + eP * beta)
+            for o in range(P.shape[0]):          # P[o] is [k, d + nAug] here; the reference's prox sees its transpose
+                if reg == "l1":
+                    P[o] = soft(P[o], lam)
+                elif reg == "l21":               # one vector per feature (l21.nim:25-35)
+                    for j in range(P.shape[2]):
+                        P[o, :, j] = prox_l21_row(P[o, :, j], lam)
+                elif reg == "squaredl12":        # transpose = true: one vector per component over all features
+                    for s_ in range(P.shape[1]):
+                        P[o, s_, :] = prox_squaredl12_sorted(P[o, s_, :], lam)
+                elif reg == "squaredl12_rows":   # transpose = false: one vector per feature
+                    for j in range(P.shape[2]):
+                        P[o, :, j] = prox_squaredl12_sorted(P[o, :, j], lam)
+                elif reg != "identity":
+                    raise ValueError(reg)
+            it += 1
+        losses.append(run / (mb * inner))
+    return P, w, intercept, losses
+
+
 def pcd_slow_fit(X, y, P, w, intercept, degree, fit_linear, fit_intercept, loss, max_iter, alpha0,
                  alpha, beta, gamma, reg):
     """PCDSlow.fit (tests/optimizer/pcd_slow.nim:27-113): the naive dense solver the reference tests

@@ -184,6 +184,34 @@ def test_mbpsgd_reduces_to_full_gradient_step(oracle):
     assert res["it"] == 2
 
 
+@pytest.mark.parametrize("degree,fit_lower", [(2, "explicit"), (3, "explicit"), (3, "augment")])
+@pytest.mark.parametrize("reg,gamma", [("identity", 0.0), ("l1", 0.05), ("l21", 0.05), ("squaredl12", 0.02),
+                                       ("squaredl12_rows", 0.02)])
+@pytest.mark.parametrize("mb,fit_linear", [(-1, True), (5, True), (4, False)])
+def test_mbpsgd_restatement_vs_naive_dense_definition(oracle, degree, fit_lower, reg, gamma, mb, fit_linear):
+    """oracle.mbpsgd_fit (line-by-line restatement of minibatch_psgd.nim:67-211 on CSR data: per-sample scatter,
+    Params.step, the regulariser's prox) against bruteforce.mbpsgd_slow_fit, the naive dense definition (subset
+    enumeration for yhat and its gradient, mean minibatch gradient, dense step, closed-form prox): iterates and
+    epoch losses over three epochs, default and explicit minibatch sizes (a ragged last wrap included: 37 rows),
+    every MBPSGD regulariser, and the intercept quirk of params.nim:47 with fitLinear = false."""
+    n, d, k = 37, 6, 3
+    X = make_dense(n, d, 35, density=0.5, positive=False)
+    y = np.sign(np.random.default_rng(9).standard_normal(n))
+    csr = CSR.from_dense(X)
+    P, w, _ = make_fm_params(d, degree, k, fit_lower, fit_linear, seed=5, scale=0.3)
+    kw = dict(eta0=0.2, alpha0=1e-3, alpha=1e-2, beta=2e-2)
+    got = oracle.mbpsgd_fit(csr, y, P, w, 0.1, degree, "logistic", fit_linear, True, max_iter=3, gamma=gamma, reg=reg,
+                            mini_batch_size=mb, **kw)
+    sP, sw, sb, sl = bf.mbpsgd_slow_fit(X, y, P, w, 0.1, degree, fit_linear, True, "logistic", 3, kw["eta0"],
+                                        kw["alpha0"], kw["alpha"], kw["beta"], gamma=gamma, reg=reg, mini_batch_size=mb)
+    np.testing.assert_allclose(got["P"], sP, rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(got["w"], sw, rtol=1e-9, atol=1e-13)
+    assert abs(got["intercept"] - sb) <= 1e-12
+    np.testing.assert_allclose(got["epoch_loss"], sl, rtol=1e-10)
+    if reg != "identity":
+        assert np.array_equal(got["P"] == 0.0, sP == 0.0)      # the prox leaves the same zero pattern
+
+
 # ---------------------------------------------------------------- proximal operators (SURVEY 8f.1)
 @pytest.mark.parametrize("n,lam", [(1, 0.3), (7, 0.05), (50, 0.5), (200, 1e-3), (64, 10.0)])
 def test_prox_squaredl12_matches_closed_form_and_optimality(oracle, n, lam):
