@@ -245,6 +245,55 @@ def adagrad_slow_fit(X, y, P, w, intercept, degree, fit_linear, fit_intercept, l
     return P, w, intercept
 
 
+def adagrad_minibatch_slow_fit(X, y, P, w, intercept, degree, fit_linear, fit_intercept, loss, B, max_iter, eta0,
+                               alpha0, alpha, beta, eps):
+    """Naive dense definition of the synchronous-minibatch dual-averaging AdaGrad (the `miniBatchSize > 1` variant
+    this repository defines; B = 1 is AdaGradSlow.fit above, adagrad_slow.nim:29-102): before a minibatch EVERY
+    parameter is set from the accumulators, theta = -eta0 G / (eta0 t reg + sqrt(N)) with t = samples seen so far
+    (none before the very first minibatch, which runs on the given parameters); the B samples are evaluated at that
+    snapshot; G += g_i and N += g_i^2 per SAMPLE (adagrad.nim:119-124 squares the per-sample gradient); after the
+    last epoch every parameter is set once more (finalize, adagrad.nim:65-84).  Dense X, subset enumeration --
+    independent of oracle/ref_cpu.c (lazy refresh of the touched features, CSR) and of the device code."""
+    n, d = X.shape
+    P = P.copy()
+    w = w.copy()
+    gsP, gnP = np.zeros_like(P), np.zeros_like(P) + eps
+    gsw, gnw = np.zeros(d), np.zeros(d) + eps
+    gsb, gnb = 0.0, eps
+    seen = 0
+
+    def refresh():
+        nonlocal P, w, intercept
+        t = float(seen)
+        P = -eta0 * gsP / (eta0 * t * beta + np.sqrt(gnP))
+        if fit_linear:
+            w = -eta0 * gsw / (eta0 * t * alpha + np.sqrt(gnw))
+        if fit_intercept:
+            intercept = -eta0 * gsb / (math.sqrt(gnb) + eta0 * t * alpha0)
+
+    for _ in range(max_iter):
+        for q0 in range(0, n, B):
+            rows = range(q0, min(n, q0 + B))
+            if seen > 0:
+                refresh()
+            y_pred = fm_decision_function(X[q0:q0 + len(rows)], P, w, intercept, degree)
+            for t_, i in enumerate(rows):
+                dL = dloss_val(loss, y[i], y_pred[t_])
+                g = np.zeros_like(P)
+                fm_grad(X, i, P, degree, dL, g)
+                gsP += g
+                gnP += g ** 2
+                if fit_linear:
+                    gsw += dL * X[i]
+                    gnw += (dL * X[i]) ** 2
+                if fit_intercept:
+                    gsb += dL
+                    gnb += dL ** 2
+            seen += len(rows)
+    refresh()
+    return P, w, intercept
+
+
 def sgd_slow_fit(X, y, P, w, intercept, degree, fit_linear, fit_intercept, loss, max_iter, eta0,
                  alpha0, alpha, beta, power=1.0):
     """SGDSlow.fit (sgd_slow.nim:38-91), shuffle=false, scheduling=optimal: dense updates with the

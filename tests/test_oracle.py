@@ -127,6 +127,35 @@ def test_adagrad_vs_slow(oracle, degree, fit_lower):
     assert abs(fast["intercept"] - bs) < 1e-7
 
 
+@pytest.mark.parametrize("degree,fit_lower", [(2, "explicit"), (3, "explicit"), (3, "augment")])
+@pytest.mark.parametrize("B", [1, 4, 16])
+@pytest.mark.parametrize("fit_linear,fit_intercept", [(True, True), (False, True), (True, False)])
+def test_adagrad_minibatch_restatement_vs_naive_dense_definition(oracle, degree, fit_lower, B, fit_linear, fit_intercept):
+    """oracle.adagrad_fit with miniBatchSize = B (lazy refresh of the minibatch's features from g_sum / g_norm, CSR,
+    per-sample squares -- the definition the device's synchronous-minibatch AdaGrad is held to) against the naive
+    dense definition bruteforce.adagrad_minibatch_slow_fit (every parameter refreshed before every minibatch);
+    at B = 1 the latter is the reference's AdaGradSlow (tests/optimizer/adagrad_slow.nim:29-102)."""
+    n, d, k = 37, 6, 3
+    X = make_dense(n, d, 41, density=0.5, positive=False)
+    y = np.sign(np.random.default_rng(6).standard_normal(n))
+    csr = CSR.from_dense(X)
+    P, w, _ = make_fm_params(d, degree, k, fit_lower, fit_linear, seed=2, scale=0.2)
+    w = np.zeros(d)
+    kw = dict(eta0=0.1, alpha0=1e-3, alpha=1e-2, beta=2e-2, eps=1e-10)
+    got = oracle.adagrad_fit(csr, y, P, w, 0.0, degree, "logistic", fit_linear, fit_intercept, max_iter=3,
+                             mini_batch_size=B, **kw)
+    sP, sw, sb = bf.adagrad_minibatch_slow_fit(X, y, P, w, 0.0, degree, fit_linear, fit_intercept, "logistic", B, 3,
+                                               kw["eta0"], kw["alpha0"], kw["alpha"], kw["beta"], kw["eps"])
+    np.testing.assert_allclose(got["P"], sP, rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(got["w"], sw, rtol=1e-9, atol=1e-13)
+    assert abs(got["intercept"] - sb) <= 1e-12
+    if B == 1:
+        qP, qw, qb = bf.adagrad_slow_fit(X, y, P, w, 0.0, degree, fit_linear, fit_intercept, "logistic", 3, kw["eta0"],
+                                         kw["alpha0"], kw["alpha"], kw["beta"], kw["eps"])
+        np.testing.assert_allclose(sP, qP, rtol=1e-9, atol=1e-13)
+        np.testing.assert_allclose(sw, qw, rtol=1e-9, atol=1e-13)
+
+
 # tests/test_sgd.nim:92-126 -- SGD (lazy scaling) vs SGDSlow (dense shrink)
 @pytest.mark.parametrize("degree,fit_lower", [(2, "explicit"), (3, "explicit"), (3, "augment"), (4, "none")])
 def test_sgd_vs_slow(oracle, degree, fit_lower):
