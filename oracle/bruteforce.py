@@ -364,6 +364,66 @@ def sgd_minibatch_slow_fit(X, y, P, w, intercept, degree, fit_linear, fit_interc
     return P, w, intercept
 
 
+def ffm_sgd_slow_fit(X, fields, y, P, w, intercept, fit_linear, fit_intercept, loss, max_iter, eta0, alpha0, alpha,
+                     beta, power=1.0):
+    """SGDSlow.fit for FFMSlow (tests/optimizer/sgd_ffm_slow.nim:8-58), shuffle = false, scheduling = optimal: dense
+    updates, the L2 shrink applied to every parameter at every step.  P is [nFields, d, k]."""
+    n, d = X.shape
+    P = P.copy()
+    w = w.copy()
+    it = 1
+
+    def eta(reg):
+        return eta0 / (1.0 + eta0 * reg * it) ** power
+
+    for _ in range(max_iter):
+        for i in range(n):
+            y_pred = ffm_decision_function(X[i:i + 1], fields, P, w, intercept)[0]
+            dL = dloss_val(loss, y[i], y_pred)
+            grad = np.zeros_like(P)
+            ffm_grad(X, fields, i, P, dL, grad)
+            if fit_intercept:
+                intercept -= eta(alpha0) * (dL + alpha0 * intercept)
+            if fit_linear:
+                w -= eta(alpha) * (dL * X[i] + alpha * w)
+            P -= eta(beta) * (grad + beta * P)
+            it += 1
+    return P, w, intercept
+
+
+def ffm_adagrad_slow_fit(X, fields, y, P, w, intercept, fit_linear, fit_intercept, loss, max_iter, eta0, alpha0,
+                         alpha, beta, eps):
+    """AdaGradSlow.fit for FFMSlow (tests/optimizer/adagrad_ffm_slow.nim:8-40 + adagrad_slow.nim:29-69), shuffle =
+    false: dense dual-averaging update of every parameter after every sample."""
+    n, d = X.shape
+    P = P.copy()
+    w = w.copy()
+    gsP, gnP = np.zeros_like(P), np.zeros_like(P) + eps
+    gsw, gnw = np.zeros(d), np.zeros(d) + eps
+    gsb, gnb = 0.0, eps
+    it = 1
+    for _ in range(max_iter):
+        for i in range(n):
+            y_pred = ffm_decision_function(X[i:i + 1], fields, P, w, intercept)[0]
+            dL = dloss_val(loss, y[i], y_pred)
+            grad = np.zeros_like(P)
+            ffm_grad(X, fields, i, P, dL, grad)
+            t = float(it)
+            if fit_intercept:
+                gsb += dL
+                gnb += dL ** 2
+                intercept = -eta0 * gsb / (math.sqrt(gnb) + eta0 * t * alpha0)
+            if fit_linear:
+                gsw += dL * X[i]
+                gnw += (dL * X[i]) ** 2
+                w = -eta0 * gsw / (eta0 * t * alpha + np.sqrt(gnw))
+            gsP += grad
+            gnP += grad ** 2
+            P = -eta0 * gsP / (eta0 * t * beta + np.sqrt(gnP))
+            it += 1
+    return P, w, intercept
+
+
 # ---------------------------------------------------------------- proximal operators (definitions)
 def prox_squaredl12_sorted(p, lam):
     """argmin_q 0.5*||q - p||^2 + lam * ||q||_1^2 in closed form: with a = sort(|p|, descending) and

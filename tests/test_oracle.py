@@ -156,6 +156,50 @@ def test_adagrad_minibatch_restatement_vs_naive_dense_definition(oracle, degree,
         np.testing.assert_allclose(sw, qw, rtol=1e-9, atol=1e-13)
 
 
+# tests/test_sgd_ffm.nim / test_adagrad_ffm.nim "Comparison to naive implementation" (n=80, d=20, 5 fields, k=4)
+@pytest.mark.parametrize("fit_linear", [False, True])
+@pytest.mark.parametrize("fit_intercept", [False, True])
+def test_ffm_sgd_vs_slow(oracle, fit_linear, fit_intercept):
+    """oracle.ffm_sgd_fit (sgd_ffm.nim: lazy L2 scaling) against the reference's naive SGDSlow for FFMSlow
+    (tests/optimizer/sgd_ffm_slow.nim), as tests/test_sgd_ffm.nim does"""
+    n, d, nF, k = 40, 12, 3, 3
+    X, csr, field_of = make_field_csr(n, d, nF, 14)
+    y = np.random.default_rng(3).standard_normal(n)
+    rng = np.random.default_rng(11)
+    P, w = rng.standard_normal((nF, d, k)) * 0.1, np.zeros(d)
+    kw = dict(eta0=0.05, alpha0=1e-3, alpha=1e-2, beta=2e-2)
+    got = oracle.ffm_sgd_fit(csr, y, P, w, 0.0, "squared", fit_linear, fit_intercept, max_iter=3, it=1, **kw)
+    sP, sw, sb = bf.ffm_sgd_slow_fit(X, field_of, y, P, w, 0.0, fit_linear, fit_intercept, "squared", 3, kw["eta0"],
+                                     kw["alpha0"], kw["alpha"], kw["beta"])
+    np.testing.assert_allclose(got["P"], sP, rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(got["w"], sw, rtol=1e-8, atol=1e-12)
+    assert abs(got["intercept"] - sb) <= 1e-10
+    if not fit_linear:
+        assert np.all(got["w"] == 0.0)
+    if not fit_intercept:
+        assert got["intercept"] == 0.0
+
+
+@pytest.mark.parametrize("fit_linear", [False, True])
+@pytest.mark.parametrize("fit_intercept", [False, True])
+def test_ffm_adagrad_vs_slow(oracle, fit_linear, fit_intercept):
+    """oracle.ffm_adagrad_fit (adagrad_ffm.nim: lazy refresh of the row's features over all fields) against the
+    reference's naive AdaGradSlow for FFMSlow (tests/optimizer/adagrad_ffm_slow.nim), as tests/test_adagrad_ffm.nim
+    does (atol 1e-7 there)"""
+    n, d, nF, k = 40, 12, 3, 3
+    X, csr, field_of = make_field_csr(n, d, nF, 15)
+    y = np.random.default_rng(4).standard_normal(n)
+    rng = np.random.default_rng(12)
+    P, w = rng.standard_normal((nF, d, k)) * 0.1, np.zeros(d)
+    kw = dict(eta0=0.1, alpha0=1e-3, alpha=1e-2, beta=2e-2, eps=1e-10)
+    got = oracle.ffm_adagrad_fit(csr, y, P, w, 0.0, "squared", fit_linear, fit_intercept, max_iter=3, **kw)
+    sP, sw, sb = bf.ffm_adagrad_slow_fit(X, field_of, y, P, w, 0.0, fit_linear, fit_intercept, "squared", 3, kw["eta0"],
+                                         kw["alpha0"], kw["alpha"], kw["beta"], kw["eps"])
+    np.testing.assert_allclose(got["P"], sP, rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(got["w"], sw, rtol=1e-7, atol=1e-9)
+    assert abs(got["intercept"] - sb) <= 1e-8
+
+
 # tests/test_sgd.nim:92-126 -- SGD (lazy scaling) vs SGDSlow (dense shrink)
 @pytest.mark.parametrize("degree,fit_lower", [(2, "explicit"), (3, "explicit"), (3, "augment"), (4, "none")])
 def test_sgd_vs_slow(oracle, degree, fit_lower):
