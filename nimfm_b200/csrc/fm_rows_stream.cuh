@@ -20,7 +20,7 @@ __host__ __device__ inline size_t stream_group_smem(int CH, int SB8, int nHotTot
 }
 
 template <int DEGREE, bool EXPLICIT, int MODE, int KT>
-__global__ void __launch_bounds__(256, (RowCfg<DEGREE, EXPLICIT>::NO == 1) ? 4 : 2) fm_rows_stream_kernel(const RowArgs a) {
+__global__ void __launch_bounds__(256, (RowCfg<DEGREE, EXPLICIT>::NO == 1 || MODE == MODE_PREDICT) ? 4 : 2) fm_rows_stream_kernel(const RowArgs a) {
   // MODE_ADAGRAD = MODE_GRAD with coef = dloss (adagrad.nim:113-124) and a second scatter of the
   // squared gradient into the g_norm delta block; P was refreshed by adagrad_refresh_kernel.
   constexpr int NACC = (MODE == MODE_ADAGRAD) ? 2 : 1;
