@@ -128,6 +128,9 @@ def loss_val(kind, y, p):
     if kind == "logistic":
         z = p * y
         return math.log(1 + math.exp(-z)) if z > 0 else math.log(math.exp(z) + 1) - z
+    if kind == "huber":                      # loss.nim:84-87, threshold 1.0
+        z = abs(y - p)
+        return 0.5 * z ** 2 if z < 1.0 else 1.0 * (z - 0.5)
     raise ValueError(kind)
 
 
@@ -140,6 +143,9 @@ def dloss_val(kind, y, p):
     if kind == "logistic":
         z = p * y
         return -y * math.exp(-z) / (1 + math.exp(-z)) if z > 0 else -y / (math.exp(z) + 1)
+    if kind == "huber":                      # loss.nim:90-93 AS WRITTEN: y - p inside the threshold (the negative of
+        z = abs(y - p)                       # d loss / d p) and +threshold outside whatever the sign of y - p
+        return y - p if z < 1.0 else 1.0
     raise ValueError(kind)
 
 

@@ -156,6 +156,31 @@ def test_adagrad_minibatch_restatement_vs_naive_dense_definition(oracle, degree,
         np.testing.assert_allclose(sw, qw, rtol=1e-9, atol=1e-13)
 
 
+def test_losses_match_the_definitions(oracle):
+    """loss.nim:15-102 restated in C (ref_loss / ref_dloss / ref_mu) against the closed forms, and dloss against a
+    centred finite difference of loss for the three smooth losses.  Huber is held to the reference AS WRITTEN:
+    dloss returns y - p inside the threshold and +threshold outside (loss.nim:90-93), which is not the derivative of
+    its loss -- the device reproduces that, so the quirk is pinned here rather than corrected."""
+    rng = np.random.default_rng(0)
+    ys = np.concatenate([np.sign(rng.standard_normal(60)), rng.standard_normal(60) * 2])
+    ps = rng.standard_normal(120) * 3
+    for kind in ("squared", "squared_hinge", "logistic", "huber"):
+        for yv, pv in zip(ys, ps):
+            assert abs(oracle.loss(kind, yv, pv) - bf.loss_val(kind, yv, pv)) <= 1e-14 * max(1.0, abs(bf.loss_val(kind, yv, pv)))
+            assert abs(oracle.dloss(kind, yv, pv) - bf.dloss_val(kind, yv, pv)) <= 1e-14 * max(1.0, abs(bf.dloss_val(kind, yv, pv)))
+            if kind != "huber" and not (kind == "squared_hinge" and abs(1 - pv * yv) < 1e-3):
+                h = 1e-6
+                fd = (bf.loss_val(kind, yv, pv + h) - bf.loss_val(kind, yv, pv - h)) / (2 * h)
+                assert abs(oracle.dloss(kind, yv, pv) - fd) <= 1e-6 * max(1.0, abs(fd))
+    # the quirk itself: inside the threshold the sign is flipped, outside it is +threshold on both sides
+    assert oracle.dloss("huber", 0.0, 0.5) == -0.5 and oracle.dloss("huber", 0.0, -0.5) == 0.5
+    assert oracle.dloss("huber", 0.0, 3.0) == 1.0 and oracle.dloss("huber", 0.0, -3.0) == 1.0
+    assert oracle.loss("huber", 0.0, 3.0) == 2.5 and oracle.loss("huber", 0.0, 0.5) == 0.125
+    # large margins: the two branches of the logistic loss stay finite
+    assert oracle.loss("logistic", 1.0, 800.0) == 0.0 and abs(oracle.loss("logistic", 1.0, -800.0) - 800.0) < 1e-9
+    assert oracle.dloss("logistic", 1.0, 800.0) == 0.0 and oracle.dloss("logistic", 1.0, -800.0) == -1.0
+
+
 # tests/test_sgd_ffm.nim / test_adagrad_ffm.nim "Comparison to naive implementation" (n=80, d=20, 5 fields, k=4)
 @pytest.mark.parametrize("fit_linear", [False, True])
 @pytest.mark.parametrize("fit_intercept", [False, True])
