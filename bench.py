@@ -400,16 +400,22 @@ class Bench:
         return float(t.item())
 
     @staticmethod
-    def l2_add(prof, payload_per_row, rows, backward_ms):
+    def l2_add(prof, payload_per_row, rows, backward_ms, kernel_ms=None):
         """the gradient scatter against the L2's measured FP64-add rate (scratch/red_rate.cu, profiles/r02_red_rate.txt):
         RED payload of the launch over the time the backward pass adds to the forward-only kernel"""
         hi, lo = prof.get("l2_fp64_add_ceiling_resident_GBs"), prof.get("l2_fp64_add_ceiling_missing_GBs")
         if not payload_per_row or not hi or backward_ms <= 0:
             return None
         ach = payload_per_row * rows / (backward_ms / 1e3) / 1e9
-        return {"red_payload_bytes_per_row": payload_per_row, "backward_ms": backward_ms, "achieved_GBs": ach,
-                "ceiling_resident_lines_GBs": hi, "ceiling_missing_lines_GBs": lo, "frac_of_resident_ceiling": ach / hi,
-                "source": prof.get("l2_fp64_add_source")}
+        out = {"red_payload_bytes_per_row": payload_per_row, "backward_ms": backward_ms, "achieved_GBs": ach,
+               "ceiling_resident_lines_GBs": hi, "ceiling_missing_lines_GBs": lo, "frac_of_resident_ceiling": ach / hi,
+               "note": "achieved = payload / (grad kernel - forward-only kernel), i.e. all of the extra time charged to "
+                       "the scatter; over_whole_kernel = payload / grad kernel, the rate if the scatter overlapped the "
+                       "forward pass completely -- the truth lies between",
+               "source": prof.get("l2_fp64_add_source")}
+        if kernel_ms:
+            out["over_whole_kernel_GBs"] = payload_per_row * rows / (kernel_ms / 1e3) / 1e9
+        return out
 
     def timed(self, fn, reps=1):
         """device time (ms) of `reps` calls of fn on the library's stream (CUDA events), MAX over ranks"""
@@ -508,7 +514,8 @@ class Bench:
                     "l2_bytes_per_row": l2_row,
                     "l2_GBs": None if l2_row is None else l2_row * n / (kms.value / 1e3) / 1e9,
                     "what_bounds_it": prof.get("fm_rows_grad_bound"),
-                    "l2_fp64_add": self.l2_add(prof, prof.get("fm_rows_grad_red_payload_bytes_per_row"), n, kms.value - fms.value),
+                    "l2_fp64_add": self.l2_add(prof, prof.get("fm_rows_grad_red_payload_bytes_per_row"), n, kms.value - fms.value,
+                                               kms.value),
                     "algorithmic_bytes_per_row": B_GRAD, "kernel_ms": kms.value,
                     "kernel_share_of_step": kms.value / ms_per_step, "frac_of_nominal_8TBs": achieved / 8000.0,
                     "forward_only": {"kernel": "fm_rows_stream_kernel<3,true,MODE_PREDICT,32>", "kernel_ms": fms.value,
@@ -711,7 +718,8 @@ class Bench:
                         "frac": self.frac(bts, n / (t / 1e3))}
         # the pair gradient is z(z-1) vectors of k FP64 adds per row; against the L2's measured FP64-add rate
         out["predict_grad"]["l2_fp64_add"] = self.l2_add(ncu_profile(), N_FIELDS * (N_FIELDS - 1) * K5 * 8 + N_FIELDS * 8, n,
-                                                         out["predict_grad"]["kernel_ms"] - out["forward"]["kernel_ms"])
+                                                         out["predict_grad"]["kernel_ms"] - out["forward"]["kernel_ms"],
+                                                         out["predict_grad"]["kernel_ms"])
         ls = C.c_double()
 
         def step():
