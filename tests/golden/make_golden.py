@@ -3,7 +3,7 @@
 The reference holds no golden vectors (its tests are differential) and cannot be
 run here (no Nim toolchain), so the committed answers come from the BRUTE-FORCE definitions restated
 from the reference's own test helpers (oracle/bruteforce.py: subset enumeration for ANOVA / FM / FFM,
-naive dense solvers for CD / AdaGrad / SGD) -- independent of both oracle/ref_cpu.c and the CUDA
+naive dense solvers for CD / AdaGrad / SGD / MBPSGD / minibatch AdaGrad) -- independent of both oracle/ref_cpu.c and the CUDA
 code, which are then both checked against these files.  Inputs use NumPy seeds; re-running this
 script must reproduce the files bit for bit.
 
@@ -86,7 +86,30 @@ def solver_cases():
     return out
 
 
+def minibatch_solver_cases():
+    """MBPSGD (L1 and no regulariser, minibatches of 5 over 12 rows: the cyclic order wraps) and the synchronous-
+    minibatch AdaGrad (minibatches of 4) from their naive dense definitions"""
+    out = {}
+    n, d, k = 12, 5, 2
+    X = make_dense(n, d, 410, density=0.7, positive=False)
+    y = np.sign(np.random.default_rng(411).standard_normal(n))
+    for tag, degree, fit_lower in [("a", 2, "explicit"), ("b", 3, "explicit"), ("c", 3, "augment")]:
+        P, w, nA = make_fm_params(d, degree, k, fit_lower, True, seed=412, scale=0.3)
+        for rtag, reg, gamma in (("id", "identity", 0.0), ("l1", "l1", 0.05)):
+            mP, mw, mb, ml = bf.mbpsgd_slow_fit(X, y, P, w, 0.1, degree, True, True, "logistic", 3, 0.2, 1e-3, 1e-2,
+                                                2e-2, gamma=gamma, reg=reg, mini_batch_size=5)
+            out.update({f"{tag}_{rtag}_P": mP, f"{tag}_{rtag}_w": mw, f"{tag}_{rtag}_b": mb,
+                        f"{tag}_{rtag}_loss": np.array(ml)})
+        aP, aw, ab = bf.adagrad_minibatch_slow_fit(X, y, P, w * 0, 0.0, degree, True, True, "logistic", 4, 3, 0.1, 1e-3,
+                                                   1e-2, 2e-2, 1e-10)
+        out.update({f"{tag}_degree": degree, f"{tag}_fit_lower": fit_lower, f"{tag}_P0": P, f"{tag}_w0": w,
+                    f"{tag}_agP": aP, f"{tag}_agw": aw, f"{tag}_agb": ab})
+    out.update(X=X, y=y)
+    return out
+
+
 if __name__ == "__main__":
+    np.savez(os.path.join(HERE, "minibatch_golden.npz"), **minibatch_solver_cases())
     np.savez(os.path.join(HERE, "fm_golden.npz"), **fm_cases())
     np.savez(os.path.join(HERE, "ffm_golden.npz"), **ffm_case())
     np.savez(os.path.join(HERE, "solver_golden.npz"), **solver_cases())
